@@ -1,0 +1,154 @@
+/* rain_b200.h -- C ABI of the B200-native rain-rendering hot path (librain_b200.so).
+ *
+ * Drop-in boundary for the per-frame path of astra-vision/rain-rendering:
+ *   common/generator.py:299-469  (Generator.run per-frame body)
+ *   common/add_attenuation.py:26-95, common/bad_weather.py:272-853,
+ *   common/solid_angle.py:5-102, common/my_utils.py:55-85.
+ * The reference is pure Python, so the binding a maintainer adds is a ctypes stub
+ * (shown in INTEGRATION.md; shipped as rain_rendering_b200/_lib.py).
+ *
+ * Conventions: every function returns 0 on success and a negative rr_status otherwise;
+ * rr_last_error() returns a static/thread-local message.  The caller owns every buffer it
+ * passes; the library owns device memory behind the opaque context.  One context is bound
+ * to one GPU and one CUDA stream; a context is NOT thread-safe, distinct contexts are.
+ * There is no CPU fallback: rr_create fails if no CUDA device is usable.
+ */
+#ifndef RAIN_B200_H
+#define RAIN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rr_context rr_context;
+
+enum rr_status {
+    RR_OK = 0,
+    RR_ERR_CUDA = -1,        /* a CUDA runtime call failed                     */
+    RR_ERR_ARG = -2,         /* invalid argument                               */
+    RR_ERR_STATE = -3,       /* call order violated (no camera / no streak DB) */
+    RR_ERR_CAPACITY = -4     /* a device arena overflowed                      */
+};
+
+/* One imaged streak of one simulator frame, as common/bad_weather.py:46-60 ("Streak") holds it
+ * after load_streaks_from_xml (:200-239) and the in-frame filter (common/generator.py:413-420),
+ * plus the two host-side NumPy RNG draws of the frame (legacy MT19937 stream seeded per frame,
+ * generator.py:318): the texture index (bad_weather.py:250-265) and the wind noise in degrees
+ * (generator.py:136).  Geometry is carried in float64 because the reference computes in
+ * float64.  128 bytes, little-endian, naturally aligned. */
+typedef struct rr_streak_rec {
+    double wp1[3], wp2[3];   /* world start / end, metres, z already negated (bad_weather.py:223) */
+    double iw1, iw2;         /* image diameters in px (after /render_scale)                       */
+    double noise_deg;        /* np.random.normal(0, noise_std) * noise_scale; 0 for Big drops     */
+    double ratio;            /* max_width / actual_length (bad_weather.py:233); informational     */
+    int32_t ip1[2], ip2[2];  /* rounded image start / end (x, y), y down, BEFORE the wind rotation */
+    int32_t ip1m[2], ip2m[2];/* the same AFTER the wind rotation wrote back (generator.py:152-161)  */
+    int32_t max_width;       /* int(max(iw1, iw2))                                                */
+    int32_t length;          /* ceil(|ip1 - ip2|)                                                 */
+    int32_t pid;
+    uint8_t type;            /* 0 Big (max_width >= 4), 1 Medium (> 1), 2 Small                   */
+    uint8_t tex_idx;         /* np.random.randint draw: index into the streak DB                  */
+    uint8_t pad[2];
+} rr_streak_rec;
+
+/* Per (sequence, weather) constants: common/generator.py:51-55,232-233,260-267 and
+ * common/bad_weather.py:344,469,712. */
+typedef struct rr_camera {
+    int32_t W, H;            /* render size                                       */
+    double focal_m;          /* cam_focal / 1000                                  */
+    double f_number;
+    double exposure_ms;
+    double gain;
+    double focus_plane_m;    /* 6   (hard-coded at generator.py:267)              */
+    double pix_size_m;       /* 4.65e-6 (hard-coded at bad_weather.py:469)        */
+    double radius;           /* 10  (generator.py:267)                            */
+    double fov_deg;          /* 165 (generator.py:267)                            */
+    double opacity_att;      /* --opacity_attenuation                             */
+    double fallrate_mmh;     /* rain intensity of the weather                     */
+} rr_camera;
+
+/* timing slots of rr_timings() */
+enum { RR_T_H2D = 0, RR_T_FOG, RR_T_ENV, RR_T_SETUP, RR_T_RASTER, RR_T_BLUR, RR_T_COMPOSITE, RR_T_EPILOGUE,
+       RR_T_D2H, RR_T_TOTAL, RR_T_COUNT };
+
+/* debug read-back selectors of rr_debug_read() (stage parity tests) */
+enum { RR_DBG_FOG_F64 = 0,      /* (3,H,W) float64 planar BGR after the fog stage               */
+       RR_DBG_ENV_U8 = 1,       /* (H,W_env,3) uint8 BGR environment map                         */
+       RR_DBG_OMEGA = 2,        /* (H,W_env) float64 solid angles                                */
+       RR_DBG_PLANS = 3,        /* rr_plan[n_streaks of the frame] (see csrc/rr_types.h)         */
+       RR_DBG_RAINY_F64 = 4,    /* (3,H,W) float64 planar BGR after compositing, before mean shift */
+       RR_DBG_ENV_SRC = 5,      /* (H,W_env) int32 source index table                            */
+       RR_DBG_ARENA = 6,        /* the float64 patch arena (offsets in rr_plan)                  */
+       RR_DBG_FEXT = 7 };       /* (H,W) float32 blurred extinction                              */
+
+int rr_version(void);
+const char *rr_last_error(void);
+
+int rr_create(int device_id, rr_context **out);
+int rr_destroy(rr_context *ctx);
+
+/* Streak DB: n_tex gray textures of common width, concatenated row-major, natural-sort order,
+ * normalised uint8 exactly as DBManager.load_streak_database leaves them (bad_weather.py:139-146;
+ * the reference's BGR copy has three identical channels, one is passed). */
+int rr_set_streak_db(rr_context *ctx, int n_tex, const int32_t *heights, int width, const uint8_t *gray_concat);
+/* Multi-GPU: non-root ranks allocate, the caller broadcasts into the device buffer (NCCL),
+ * see rain_rendering_b200/dist.py. */
+int rr_alloc_streak_db(rr_context *ctx, int n_tex, const int32_t *heights, int width);
+int rr_streak_db_device_ptr(rr_context *ctx, void **dev_ptr, size_t *bytes);
+
+/* Builds the per-camera tables on the device: cylindrical source-index map, hole mask,
+ * solid angles, their row prefix sums (replaces EnvironmentMapGenerator.__init__ + the
+ * geometry half of generate_map, and solid_angle.get_solid_angles which the reference
+ * recomputes every frame).  max_batch frames are provisioned. */
+int rr_set_camera(rr_context *ctx, const rr_camera *cam, int max_batch);
+int rr_env_size(rr_context *ctx, int *H_env, int *W_env);
+
+/* The hot path for a batch of n_frames (<= max_batch) independent frames.  HOST buffers:
+ *   bgr        n*H*W*3 uint8   (cv2.imread order, generator.py:352)
+ *   depth      n*H*W   float32 metres (generator.py:365)
+ *   streaks    concatenated records, frame f owns [streak_offsets[f], streak_offsets[f+1])
+ *   out_bgr    n*H*W*3 float32 BGR mean-shifted rainy image (generator.py:464), may be NULL
+ *   out_mask   n*H*W   float32 rain mask (generator.py:393,467), may be NULL
+ *   out_bgr_u8 n*H*W*3 uint8 floor(clip(out,0,1)*255) BGR, may be NULL
+ * Copies host->device, renders, copies device->host, returns when the outputs are valid. */
+int rr_render_frames(rr_context *ctx, int n_frames, const uint8_t *bgr, const float *depth,
+                     const rr_streak_rec *streaks, const int32_t *streak_offsets,
+                     float *out_bgr, float *out_mask, uint8_t *out_bgr_u8);
+
+/* Same with DEVICE pointers and no copies (inputs already resident in HBM); asynchronous on the
+ * context stream unless sync != 0. */
+int rr_render_frames_device(rr_context *ctx, int n_frames, const uint8_t *d_bgr, const float *d_depth,
+                            const rr_streak_rec *d_streaks, const int32_t *h_streak_offsets,
+                            float *d_out_bgr, float *d_out_mask, uint8_t *d_out_bgr_u8, int sync);
+
+/* Stage-level entry points for parity tests against oracle intermediates (host buffers). */
+int rr_fog_only(rr_context *ctx, int n_frames, const uint8_t *bgr, const float *depth, double *out_planar_bgr_f64);
+int rr_envmap_only(rr_context *ctx, int n_frames, const double *planar_bgr_f64, uint8_t *out_env_bgr_u8);
+int rr_streak_photometry_only(rr_context *ctx, const uint8_t *env_bgr_u8, int n_streaks,
+                              const rr_streak_rec *streaks, double *out_fovx_fovy_dropY /* n*3 */);
+
+int rr_debug_read(rr_context *ctx, int what, int frame, void *dst, size_t bytes);
+int rr_timings(rr_context *ctx, float *ms_per_stage /* RR_T_COUNT */);
+int rr_kernel_launches(rr_context *ctx, long long *count);   /* kernels launched since rr_create */
+int rr_stream(rr_context *ctx, void **cuda_stream);
+
+/* Pinned host staging buffers for the callers of rr_render_frames (async copies need them). */
+int rr_host_alloc(void **ptr, size_t bytes);
+int rr_host_free(void *ptr);
+
+/* Host logic (no GPU): the per-frame NumPy legacy RNG draws of the reference, bit-exact --
+ * np.random.seed(seed); per streak randint(10*bucket, 10*bucket+10) (bad_weather.py:252-264) and,
+ * for non-Big streaks, normal(0, noise_std) * noise_scale (generator.py:136). */
+int rr_host_draw_randoms(uint32_t seed, int n, const uint8_t *types, const int32_t *buckets, double noise_std,
+                         double noise_scale, uint8_t *tex_idx, double *noise_deg);
+/* The OpenCV Gaussian kernels baked into the library (for the CPU test-suite). */
+void rr_host_tables(double *k64_25, float *k32_25, int *k15_fixed);
+int rr_synchronize(rr_context *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAIN_B200_H */

@@ -1,0 +1,107 @@
+"""ctypes binding of librain_b200.so (include/rain_b200.h).
+
+This is the stub a maintainer of the reference would add: the reference is
+pure Python, so its FFI is ctypes.  There is NO fallback: if the shared library is missing it
+is built with nvcc (``build.py``); if that fails, importing raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librain_b200.so")
+
+
+class Camera(C.Structure):
+    """rr_camera"""
+    _fields_ = [("W", C.c_int32), ("H", C.c_int32), ("focal_m", C.c_double), ("f_number", C.c_double),
+                ("exposure_ms", C.c_double), ("gain", C.c_double), ("focus_plane_m", C.c_double),
+                ("pix_size_m", C.c_double), ("radius", C.c_double), ("fov_deg", C.c_double),
+                ("opacity_att", C.c_double), ("fallrate_mmh", C.c_double)]
+
+
+# rr_plan (csrc/rr_types.h) as a numpy dtype, for the stage parity tests
+PLAN_DTYPE = np.dtype([
+    ("valid", "<i4"), ("type", "<i4"), ("pw", "<i4"), ("ph", "<i4"), ("minx", "<i4"), ("miny", "<i4"),
+    ("tex_off", "<i4"), ("tex_h", "<i4"), ("M", "<f8", 9), ("bw0", "<i4"), ("nW", "<i4"), ("nH", "<i4"),
+    ("flip", "<i4"), ("resize_mode", "<i4"), ("_pad0", "<i4"), ("scale_x", "<f8"), ("scale_y", "<f8"),
+    ("sig_y", "<f8"), ("sig_x", "<f8"), ("shift", "<i4"), ("ry", "<i4"), ("rx", "<i4"),
+    ("bx0", "<i4"), ("by0", "<i4"), ("cropx", "<i4"), ("cropy", "<i4"), ("bw", "<i4"), ("bh", "<i4"), ("_pad1", "<i4"),
+    ("g_off", "<i8"), ("a_off", "<i8"), ("kb", "<f8"), ("kg", "<f8"), ("kr", "<f8"), ("a_scale", "<f8"),
+    ("c_scale", "<f8"), ("fov_x", "<f8"), ("fov_y", "<f8"), ("drop_Y", "<f8")])
+assert PLAN_DTYPE.itemsize == 280
+
+T_NAMES = ("h2d", "fog", "env", "setup", "raster", "blur", "composite", "epilogue", "d2h", "total")
+DBG = dict(fog=0, env=1, omega=2, plans=3, rainy=4, env_src=5, arena=6, fext=7)
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load (building first if needed) the CUDA library.  Raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH) or _build.stale():
+        try:
+            _build.build()
+        except Exception as e:  # no silent fallback
+            if not os.path.exists(LIB_PATH):
+                raise RuntimeError("librain_b200.so is missing and could not be built (%s); there is no CPU fallback" % e)
+    lib = C.CDLL(LIB_PATH)
+    vp, i32p, u8p, f32p, f64p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
+    lib.rr_version.restype = C.c_int
+    lib.rr_last_error.restype = C.c_char_p
+    protos = {
+        "rr_create": [C.c_int, C.POINTER(vp)],
+        "rr_destroy": [vp],
+        "rr_set_streak_db": [vp, C.c_int, i32p, C.c_int, u8p],
+        "rr_alloc_streak_db": [vp, C.c_int, i32p, C.c_int],
+        "rr_streak_db_device_ptr": [vp, C.POINTER(vp), C.POINTER(C.c_size_t)],
+        "rr_set_camera": [vp, C.POINTER(Camera), C.c_int],
+        "rr_env_size": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+        "rr_render_frames": [vp, C.c_int, u8p, f32p, vp, i32p, f32p, f32p, u8p],
+        "rr_render_frames_device": [vp, C.c_int, u8p, f32p, vp, i32p, f32p, f32p, u8p, C.c_int],
+        "rr_fog_only": [vp, C.c_int, u8p, f32p, f64p],
+        "rr_envmap_only": [vp, C.c_int, f64p, u8p],
+        "rr_streak_photometry_only": [vp, u8p, C.c_int, vp, f64p],
+        "rr_debug_read": [vp, C.c_int, C.c_int, vp, C.c_size_t],
+        "rr_timings": [vp, f32p],
+        "rr_kernel_launches": [vp, C.POINTER(C.c_longlong)],
+        "rr_stream": [vp, C.POINTER(vp)],
+        "rr_synchronize": [vp],
+        "rr_host_alloc": [C.POINTER(vp), C.c_size_t],
+        "rr_host_free": [vp],
+        "rr_host_draw_randoms": [C.c_uint32, C.c_int, u8p, i32p, C.c_double, C.c_double, u8p, f64p],
+    }
+    for name, args in protos.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = C.c_int
+    lib.rr_host_tables.argtypes = [f64p, f32p, i32p]
+    lib.rr_host_tables.restype = None
+    _lib = lib
+    return lib
+
+
+class RainError(RuntimeError):
+    pass
+
+
+def check(status: int, what: str = ""):
+    if status != 0:
+        msg = load().rr_last_error().decode(errors="replace")
+        raise RainError("%s failed (%d): %s" % (what or "librain_b200", status, msg))
+
+
+def ptr(a):
+    """ctypes pointer of a C-contiguous numpy array (or None)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+    return a.ctypes.data_as(C.c_void_p)

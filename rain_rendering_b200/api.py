@@ -1,0 +1,203 @@
+"""Python face of the C ABI: one ``RainContext`` per GPU (thin; all rendering is in the library)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from .streaks import BIG, STREAK_DTYPE, texture_buckets
+
+
+def draw_randoms(seed: int, types: np.ndarray, buckets: np.ndarray, noise_std: float, noise_scale: float):
+    """The frame's NumPy legacy-RNG draws (np.random.seed(seed); randint per streak; normal per
+    non-Big streak), computed by the library's MT19937 mirror.  -> (tex_idx uint8, noise_deg float64)"""
+    lib = _lib.load()
+    n = len(types)
+    types = np.ascontiguousarray(types, dtype=np.uint8)
+    buckets = np.ascontiguousarray(buckets, dtype=np.int32)
+    tex = np.zeros(n, np.uint8)
+    noise = np.zeros(n, np.float64)
+    _lib.check(lib.rr_host_draw_randoms(C.c_uint32(int(seed) & 0xFFFFFFFF), n, _lib.ptr(types), _lib.ptr(buckets),
+                                        float(noise_std), float(noise_scale), _lib.ptr(tex), _lib.ptr(noise)),
+               "rr_host_draw_randoms")
+    return tex, noise
+
+
+class PinnedBuffer:
+    """Page-locked host memory exposed as a numpy array (rr_host_alloc)."""
+
+    def __init__(self, shape, dtype):
+        lib = _lib.load()
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        _lib.check(lib.rr_host_alloc(C.byref(p), max(nbytes, 1)), "rr_host_alloc")
+        self._p = p
+        buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self._p is not None:
+            self.array = None
+            _lib.load().rr_host_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class RainContext:
+    """rr_create / rr_set_streak_db / rr_set_camera / rr_render_frames."""
+
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self.lib.rr_create(int(device), C.byref(h)), "rr_create")
+        self.h = h
+        self.device = device
+        self.W = self.H = 0
+        self.max_batch = 0
+        self.db_ratios = None
+
+    def close(self):
+        if self.h is not None:
+            self.lib.rr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- streak DB ---------------------------------------------------------------------------
+    def set_streak_db(self, textures, ratios=None):
+        """textures: list of (h, w) uint8 gray arrays (or (h, w, 3) with identical channels) in
+        natural-sort order, normalised like DBManager.load_streak_database leaves them."""
+        gray = []
+        for t in textures:
+            t = np.asarray(t)
+            if t.ndim == 3:
+                assert (t[..., 0] == t[..., 1]).all() and (t[..., 0] == t[..., 2]).all(), "streak textures must be gray"
+                t = t[..., 0]
+            gray.append(np.ascontiguousarray(t, dtype=np.uint8))
+        width = gray[0].shape[1]
+        assert all(g.shape[1] == width for g in gray)
+        heights = np.array([g.shape[0] for g in gray], dtype=np.int32)
+        data = np.concatenate([g.reshape(-1) for g in gray])
+        _lib.check(self.lib.rr_set_streak_db(self.h, len(gray), _lib.ptr(heights), width, _lib.ptr(data)), "rr_set_streak_db")
+        self.db_heights, self.db_width = heights, width
+        self.db_ratios = np.unique(width / heights.astype(np.float64)) if ratios is None else np.asarray(ratios)
+
+    def alloc_streak_db(self, heights, width):
+        heights = np.ascontiguousarray(heights, dtype=np.int32)
+        _lib.check(self.lib.rr_alloc_streak_db(self.h, len(heights), _lib.ptr(heights), int(width)), "rr_alloc_streak_db")
+        self.db_heights, self.db_width = heights, int(width)
+        self.db_ratios = np.unique(width / heights.astype(np.float64))
+
+    def streak_db_device_ptr(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        _lib.check(self.lib.rr_streak_db_device_ptr(self.h, C.byref(p), C.byref(n)), "rr_streak_db_device_ptr")
+        return p.value, n.value
+
+    # -- camera ------------------------------------------------------------------------------
+    def set_camera(self, W, H, focal_mm=6.0, f_number=6.0, exposure_ms=2.0, gain=20.0, fallrate=25.0,
+                   opacity_attenuation=1.0, max_batch=1, focus_plane=6.0, pix_size=4.65e-06, radius=10.0, fov_deg=165.0):
+        cam = _lib.Camera(int(W), int(H), focal_mm / 1000., float(f_number), float(exposure_ms), float(gain),
+                          float(focus_plane), float(pix_size), float(radius), float(fov_deg),
+                          float(opacity_attenuation), float(fallrate))
+        _lib.check(self.lib.rr_set_camera(self.h, C.byref(cam), int(max_batch)), "rr_set_camera")
+        self.W, self.H, self.max_batch = int(W), int(H), int(max_batch)
+        he, we = C.c_int(), C.c_int()
+        _lib.check(self.lib.rr_env_size(self.h, C.byref(he), C.byref(we)), "rr_env_size")
+        self.H_env, self.W_env = he.value, we.value
+
+    # -- hot path ----------------------------------------------------------------------------
+    def render_frames(self, bgr, depth, streaks, offsets, out_bgr=None, out_mask=None, out_u8=None,
+                      want=("bgr", "mask", "u8")):
+        """bgr (n,H,W,3) uint8; depth (n,H,W) float32; streaks STREAK_DTYPE (concatenated);
+        offsets (n+1,) int32.  Returns dict of the requested outputs (numpy arrays)."""
+        n = bgr.shape[0]
+        assert bgr.shape == (n, self.H, self.W, 3) and bgr.dtype == np.uint8
+        assert depth.shape == (n, self.H, self.W) and depth.dtype == np.float32
+        assert streaks.dtype == STREAK_DTYPE
+        offsets = np.ascontiguousarray(offsets, dtype=np.int32)
+        if out_bgr is None and "bgr" in want:
+            out_bgr = np.empty((n, self.H, self.W, 3), np.float32)
+        if out_mask is None and "mask" in want:
+            out_mask = np.empty((n, self.H, self.W), np.float32)
+        if out_u8 is None and "u8" in want:
+            out_u8 = np.empty((n, self.H, self.W, 3), np.uint8)
+        _lib.check(self.lib.rr_render_frames(self.h, n, _lib.ptr(bgr), _lib.ptr(depth), _lib.ptr(streaks), _lib.ptr(offsets),
+                                             _lib.ptr(out_bgr), _lib.ptr(out_mask), _lib.ptr(out_u8)), "rr_render_frames")
+        return dict(bgr=out_bgr, mask=out_mask, u8=out_u8)
+
+    # -- stage entry points (parity tests) -----------------------------------------------------
+    def fog_only(self, bgr, depth):
+        n = bgr.shape[0]
+        out = np.empty((n, 3, self.H, self.W), np.float64)
+        _lib.check(self.lib.rr_fog_only(self.h, n, _lib.ptr(bgr), _lib.ptr(depth), _lib.ptr(out)), "rr_fog_only")
+        return out
+
+    def envmap_only(self, planar_bgr):
+        planar_bgr = np.ascontiguousarray(planar_bgr, dtype=np.float64)
+        n = planar_bgr.shape[0]
+        out = np.empty((n, self.H_env, self.W_env, 3), np.uint8)
+        _lib.check(self.lib.rr_envmap_only(self.h, n, _lib.ptr(planar_bgr), _lib.ptr(out)), "rr_envmap_only")
+        return out
+
+    def streak_photometry_only(self, env_u8, streaks):
+        env_u8 = np.ascontiguousarray(env_u8, dtype=np.uint8)
+        assert env_u8.shape == (self.H_env, self.W_env, 3)
+        out = np.empty((len(streaks), 3), np.float64)
+        _lib.check(self.lib.rr_streak_photometry_only(self.h, _lib.ptr(env_u8), len(streaks), _lib.ptr(streaks), _lib.ptr(out)),
+                   "rr_streak_photometry_only")
+        return out
+
+    def debug_read(self, what: str, frame: int = 0, count: int | None = None):
+        np_img, np_env = self.H * self.W, self.H_env * self.W_env
+        spec = dict(fog=((3, self.H, self.W), np.float64), rainy=((3, self.H, self.W), np.float64),
+                    env=((self.H_env, self.W_env, 3), np.uint8), omega=((self.H_env, self.W_env), np.float64),
+                    env_src=((self.H_env, self.W_env), np.int32), fext=((self.H, self.W), np.float32),
+                    plans=((count or 0,), _lib.PLAN_DTYPE), arena=((count or 0,), np.float64))[what]
+        out = np.zeros(spec[0], spec[1])
+        _lib.check(self.lib.rr_debug_read(self.h, _lib.DBG[what], frame, _lib.ptr(out), out.nbytes), "rr_debug_read")
+        return out
+
+    def timings(self):
+        ms = np.zeros(len(_lib.T_NAMES), np.float32)
+        _lib.check(self.lib.rr_timings(self.h, _lib.ptr(ms)), "rr_timings")
+        return dict(zip(_lib.T_NAMES, ms.tolist()))
+
+    def kernel_launches(self) -> int:
+        v = C.c_longlong()
+        _lib.check(self.lib.rr_kernel_launches(self.h, C.byref(v)), "rr_kernel_launches")
+        return v.value
+
+    def synchronize(self):
+        _lib.check(self.lib.rr_synchronize(self.h), "rr_synchronize")
+
+
+def assemble_frame_records(sim_frame: np.ndarray, W: int, H: int, db_ratios, seed: int, noise_std: float = 0.0,
+                           noise_scale: float = 0.0, mutate: bool = True) -> np.ndarray:
+    """One image frame's records from a simulator frame (STREAK_DTYPE array, XML order):
+    in-frame filter (generator.py:413-420), RNG draws, wind-noise write-back.  With
+    ``mutate`` the write-back also lands in ``sim_frame`` (the reference mutates its shared Streak
+    objects, so a simulator frame reused by a later image frame sees the rotated positions)."""
+    from .streaks import apply_wind_noise, in_frame
+    m = in_frame(sim_frame, W, H)
+    rec = sim_frame[m].copy()
+    buckets = texture_buckets(rec["ratio"], db_ratios)
+    tex, noise = draw_randoms(seed, rec["type"], buckets, noise_std, noise_scale)
+    rec["tex_idx"] = tex
+    rec["noise_deg"] = noise
+    apply_wind_noise(rec, noise)
+    if mutate:
+        sim_frame["ip1m"][m] = rec["ip1m"]
+        sim_frame["ip2m"][m] = rec["ip2m"]
+    return rec

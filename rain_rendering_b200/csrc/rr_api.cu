@@ -1,0 +1,519 @@
+// C ABI of librain_b200.so (include/rain_b200.h): context, device memory, stage orchestration.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include "rr_kernels.cuh"
+
+static thread_local char g_err[1024] = "";
+static void set_err(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            set_err("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));            \
+            return RR_ERR_CUDA;                                                                        \
+        }                                                                                              \
+    } while (0)
+
+struct rr_context {
+    int device = 0, n_sm = 148;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[RR_T_COUNT + 2];
+    float last_ms[RR_T_COUNT];
+    long long launches = 0;
+    // streak DB
+    uint8_t *d_db = nullptr;
+    size_t db_bytes = 0;
+    int n_tex = 0, db_width = 0;
+    int32_t *d_tex_off = nullptr, *d_tex_h = nullptr;
+    // camera
+    bool have_cam = false;
+    rr_camera cam;
+    rr_cam_dev camd;
+    rr_fog_consts fogc;
+    int max_batch = 0, H_env = 0, W_env = 0, cyl_w = 0;
+    int32_t *d_env_src = nullptr;
+    uint8_t *d_env_written = nullptr;
+    double *d_omega = nullptr, *d_omega_pref = nullptr, *d_omega_total = nullptr;
+    // per batch
+    uint8_t *d_bgr = nullptr;
+    float *d_depth = nullptr;
+    rr_streak_rec *d_streaks = nullptr;
+    int32_t *d_offsets = nullptr;
+    int streak_cap = 0;
+    rr_frame_bufs fb;
+    std::vector<void *> owned;       // everything cudaMalloc'ed for the camera (freed on re-set / destroy)
+    int last_n_streaks = 0;
+};
+
+template <class T>
+static cudaError_t dev_alloc(rr_context *c, T **p, size_t count) {
+    cudaError_t e = cudaMalloc((void **)p, count * sizeof(T) + 256);
+    if (e == cudaSuccess) c->owned.push_back((void *)*p);
+    return e;
+}
+
+static void free_camera(rr_context *c) {
+    for (void *p : c->owned) cudaFree(p);
+    c->owned.clear();
+    c->have_cam = false;
+    c->streak_cap = 0;
+    memset(&c->fb, 0, sizeof(c->fb));
+}
+
+extern "C" {
+
+int rr_version(void) { return 100; }
+const char *rr_last_error(void) { return g_err; }
+
+int rr_create(int device_id, rr_context **out) {
+    if (!out) { set_err("rr_create: out is NULL"); return RR_ERR_ARG; }
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_err("rr_create: no usable CUDA device (%s); this library has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+        return RR_ERR_CUDA;
+    }
+    if (device_id < 0 || device_id >= n) { set_err("rr_create: device %d out of range (0..%d)", device_id, n - 1); return RR_ERR_ARG; }
+    CK(cudaSetDevice(device_id));
+    rr_context *c = new rr_context();
+    c->device = device_id;
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device_id));
+    c->n_sm = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < RR_T_COUNT + 2; i++) CK(cudaEventCreate(&c->ev[i]));
+    memset(c->last_ms, 0, sizeof(c->last_ms));
+    memset(&c->fb, 0, sizeof(c->fb));
+    CK(rr_upload_constants());
+    *out = c;
+    return RR_OK;
+}
+
+int rr_destroy(rr_context *c) {
+    if (!c) return RR_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_camera(c);
+    if (c->d_db) cudaFree(c->d_db);
+    if (c->d_tex_off) cudaFree(c->d_tex_off);
+    if (c->d_tex_h) cudaFree(c->d_tex_h);
+    for (int i = 0; i < RR_T_COUNT + 2; i++) cudaEventDestroy(c->ev[i]);
+    cudaStreamDestroy(c->stream);
+    delete c;
+    return RR_OK;
+}
+
+int rr_alloc_streak_db(rr_context *c, int n_tex, const int32_t *heights, int width) {
+    if (!c || n_tex <= 0 || n_tex > 255 || !heights || width <= 0) { set_err("rr_alloc_streak_db: bad arguments"); return RR_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    if (c->d_db) { cudaFree(c->d_db); cudaFree(c->d_tex_off); cudaFree(c->d_tex_h); c->d_db = nullptr; }
+    std::vector<int32_t> off(n_tex);
+    size_t total = 0;
+    for (int i = 0; i < n_tex; i++) {
+        if (heights[i] <= 0) { set_err("rr_alloc_streak_db: texture %d has height %d", i, heights[i]); return RR_ERR_ARG; }
+        off[i] = (int32_t)total;
+        total += (size_t)heights[i] * width;
+    }
+    CK(cudaMalloc((void **)&c->d_db, total + 256));
+    CK(cudaMalloc((void **)&c->d_tex_off, sizeof(int32_t) * n_tex));
+    CK(cudaMalloc((void **)&c->d_tex_h, sizeof(int32_t) * n_tex));
+    CK(cudaMemcpy(c->d_tex_off, off.data(), sizeof(int32_t) * n_tex, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_tex_h, heights, sizeof(int32_t) * n_tex, cudaMemcpyHostToDevice));
+    c->db_bytes = total; c->n_tex = n_tex; c->db_width = width;
+    c->camd.db_width = width; c->camd.n_tex = n_tex;
+    return RR_OK;
+}
+
+int rr_set_streak_db(rr_context *c, int n_tex, const int32_t *heights, int width, const uint8_t *gray_concat) {
+    if (!gray_concat) { set_err("rr_set_streak_db: textures are NULL"); return RR_ERR_ARG; }
+    int r = rr_alloc_streak_db(c, n_tex, heights, width);
+    if (r != RR_OK) return r;
+    CK(cudaMemcpy(c->d_db, gray_concat, c->db_bytes, cudaMemcpyHostToDevice));
+    return RR_OK;
+}
+
+int rr_streak_db_device_ptr(rr_context *c, void **dev_ptr, size_t *bytes) {
+    if (!c || !c->d_db) { set_err("rr_streak_db_device_ptr: no streak DB"); return RR_ERR_STATE; }
+    if (dev_ptr) *dev_ptr = c->d_db;
+    if (bytes) *bytes = c->db_bytes;
+    return RR_OK;
+}
+
+static int ensure_streak_cap(rr_context *c, int n) {
+    if (n <= c->streak_cap) return RR_OK;
+    int cap = n + n / 4 + 1024;
+    CK(dev_alloc(c, &c->d_streaks, (size_t)cap));
+    CK(dev_alloc(c, &c->fb.plans, (size_t)cap));
+    CK(dev_alloc(c, &c->fb.scan, (size_t)(cap + 1) * 6));
+    c->streak_cap = cap;
+    return RR_OK;
+}
+
+int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
+    if (!c || !cam || max_batch <= 0) { set_err("rr_set_camera: bad arguments"); return RR_ERR_ARG; }
+    if (cam->W < 32 || cam->H < 32 || cam->W > 16384 || cam->H > 16384) { set_err("rr_set_camera: unsupported size %dx%d", cam->W, cam->H); return RR_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    free_camera(c);
+    c->cam = *cam;
+    c->max_batch = max_batch;
+    const int W = cam->W, H = cam->H;
+    // EnvironmentMapGenerator.__init__ / max_coord / min_coord  (bad_weather.py:708-740)
+    int f = (int)(((cam->focal_m * 1000) / 12.7) * W);
+    if (f <= 0) { set_err("rr_set_camera: focal length gives a %d px cylinder", f); return RR_ERR_ARG; }
+    int cx = W / 2;
+    int max_x = (int)rint(f * atan((double)cx / f) + cx);
+    int min_x = (int)rint(f * atan((double)-cx / f) + cx);
+    c->cyl_w = max_x - min_x + 1;
+    c->H_env = H;
+    c->W_env = c->cyl_w + 2 * (c->cyl_w / 2);
+    const int He = c->H_env, We = c->W_env;
+    rr_cam_dev &d = c->camd;
+    d.W = W; d.H = H; d.H_env = He; d.W_env = We;
+    d.focal_m = cam->focal_m; d.f_number = cam->f_number; d.focus_plane = cam->focus_plane_m; d.pix_size = cam->pix_size_m;
+    d.radius = cam->radius; d.fov_deg = cam->fov_deg; d.opacity_att = cam->opacity_att;
+    d.exposure_blend = cam->exposure_ms / 1000.;                       // bad_weather.py:344
+    d.db_width = c->db_width; d.n_tex = c->n_tex;
+    // FogRain constants (add_attenuation.py:27-64)
+    double beta_ext = 0.312 * pow(cam->fallrate_mmh, 0.67);
+    c->fogc.neg_beta32 = (float)(-beta_ext);
+    c->fogc.irr_scale_num = 4 * (cam->f_number * cam->f_number);
+    c->fogc.irr_den = (cam->exposure_ms * 1e-3) * cam->gain * 3.141592653589793;
+    {
+        double g = 0.97;
+        double cos_term = cos(90.0 * (3.141592653589793 / 180.0));   // math.cos(math.radians(90))
+        c->fogc.beta_hg = (1 - (g * g)) / (4 * 3.141592653589793 * pow(1 + g * g - 2 * g * cos_term, 1.5));
+    }
+    // static tables
+    CK(dev_alloc(c, &c->d_env_src, (size_t)He * We));
+    CK(dev_alloc(c, &c->d_env_written, (size_t)He * We));
+    CK(dev_alloc(c, &c->d_omega, (size_t)He * We));
+    CK(dev_alloc(c, &c->d_omega_pref, (size_t)He * (We + 1)));
+    CK(dev_alloc(c, &c->d_omega_total, (size_t)1));
+    {
+        int32_t *scratch;
+        CK(cudaMalloc((void **)&scratch, (size_t)H * c->cyl_w * 9 + 256));
+        CK(rr_launch_env_tables(W, H, f, c->cyl_w, min_x, We, c->d_env_src, c->d_env_written, scratch, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaFree(scratch));
+        c->launches += 4;
+    }
+    CK(rr_launch_omega(He, We, c->d_omega, c->d_omega_pref, c->d_omega_total, c->stream));
+    c->launches += 3;
+    // per-batch buffers
+    const size_t F = (size_t)max_batch, np = (size_t)W * H, npe = (size_t)He * We;
+    rr_frame_bufs &b = c->fb;
+    CK(dev_alloc(c, &c->d_bgr, F * np * 3));
+    CK(dev_alloc(c, &c->d_depth, F * np));
+    CK(dev_alloc(c, &c->d_offsets, F + 1));
+    CK(dev_alloc(c, &b.chan_sum, F * 4));
+    CK(dev_alloc(c, &b.rainy, F * 3 * np));
+    CK(dev_alloc(c, &b.bg8, F * np * 3));
+    CK(dev_alloc(c, &b.fblur, F * np));
+    CK(dev_alloc(c, &b.env_fill, F * npe * 3));
+    CK(dev_alloc(c, &b.env8, F * npe * 3));
+    CK(dev_alloc(c, &b.pref, F * 3 * (size_t)He * (We + 1)));
+    CK(dev_alloc(c, &b.rowtot, F * He));
+    CK(dev_alloc(c, &b.ambient, F));
+    CK(dev_alloc(c, &b.err_flag, (size_t)1));
+    size_t tiles = (size_t)((W + RR_TILE_W - 1) / RR_TILE_W) * ((H + RR_TILE_H - 1) / RR_TILE_H);
+    CK(dev_alloc(c, &b.tile_sum, F * tiles));
+    CK(dev_alloc(c, &b.frame_mean, F));
+    CK(dev_alloc(c, &b.out_bgr, F * np * 3));
+    CK(dev_alloc(c, &b.out_mask, F * np));
+    CK(dev_alloc(c, &b.out_u8, F * np * 3));
+    {
+        double mult = 10.0;
+        const char *env = getenv("RR_ARENA_MULT");
+        if (env) mult = atof(env);
+        b.arena_cap = (long long)(mult * (double)(F * np));
+        CK(dev_alloc(c, &b.arena, (size_t)b.arena_cap));
+    }
+    int r = ensure_streak_cap(c, max_batch * 1024);
+    if (r != RR_OK) return r;
+    c->have_cam = true;
+    return RR_OK;
+}
+
+int rr_env_size(rr_context *c, int *H_env, int *W_env) {
+    if (!c || !c->have_cam) { set_err("rr_env_size: no camera"); return RR_ERR_STATE; }
+    if (H_env) *H_env = c->H_env;
+    if (W_env) *W_env = c->W_env;
+    return RR_OK;
+}
+
+static rr_static_tabs tabs_of(rr_context *c) {
+    rr_static_tabs t;
+    t.env_src = c->d_env_src; t.env_written = c->d_env_written; t.omega = c->d_omega; t.omega_pref = c->d_omega_pref;
+    t.omega_total = c->d_omega_total; t.db = c->d_db; t.tex_off = c->d_tex_off; t.tex_h = c->d_tex_h;
+    return t;
+}
+
+static int check_ready(rr_context *c, int n_frames, const char *who) {
+    if (!c) { set_err("%s: context is NULL", who); return RR_ERR_ARG; }
+    if (!c->have_cam) { set_err("%s: rr_set_camera has not been called", who); return RR_ERR_STATE; }
+    if (n_frames <= 0 || n_frames > c->max_batch) { set_err("%s: n_frames %d not in 1..%d", who, n_frames, c->max_batch); return RR_ERR_ARG; }
+    return RR_OK;
+}
+
+// the device pipeline for a batch whose inputs are already in fb.bgr / fb.depth / fb.streaks / fb.offsets
+static int run_pipeline(rr_context *c, int F, int n_streaks, bool timed) {
+    rr_frame_bufs &b = c->fb;
+    const rr_static_tabs t = tabs_of(c);
+    cudaStream_t st = c->stream;
+    const int W = c->cam.W, H = c->cam.H;
+    c->camd.db_width = c->db_width; c->camd.n_tex = c->n_tex;
+    CK(cudaMemsetAsync(b.err_flag, 0, sizeof(int), st));
+    if (timed) CK(cudaEventRecord(c->ev[RR_T_FOG], st));
+    CK(rr_launch_stats(b, F, W, H, st));
+    CK(rr_launch_fog(b, c->fogc, F, W, H, st));
+    if (timed) CK(cudaEventRecord(c->ev[RR_T_ENV], st));
+    CK(rr_launch_env(b, t, F, W, H, c->W_env, st));
+    if (timed) CK(cudaEventRecord(c->ev[RR_T_SETUP], st));
+    CK(rr_launch_setup(b, t, c->camd, F, n_streaks, st));
+    CK(rr_launch_scan(b, n_streaks, st));
+    if (timed) CK(cudaEventRecord(c->ev[RR_T_RASTER], st));
+    CK(rr_launch_raster(b, t, c->camd, n_streaks, c->n_sm, st));
+    if (timed) CK(cudaEventRecord(c->ev[RR_T_BLUR], st));
+    CK(rr_launch_blur(b, n_streaks, c->n_sm, st));
+    if (timed) CK(cudaEventRecord(c->ev[RR_T_COMPOSITE], st));
+    CK(rr_launch_composite(b, c->camd, F, st));
+    if (timed) CK(cudaEventRecord(c->ev[RR_T_EPILOGUE], st));
+    CK(rr_launch_epilogue(b, F, W, H, st));
+    if (timed) CK(cudaEventRecord(c->ev[RR_T_D2H], st));
+    c->launches += 2 + 1 + 4 + (n_streaks ? 1 : 0) + 1 + (n_streaks ? 3 : 0) + 2 + 1;
+    c->last_n_streaks = n_streaks;
+    return RR_OK;
+}
+
+static int finish_timings(rr_context *c) {
+    // ev[RR_T_H2D] .. ev[RR_T_TOTAL] were recorded in order; slot i = time from ev[i] to ev[i+1]
+    for (int i = RR_T_H2D; i < RR_T_TOTAL; i++) {
+        float ms = 0;
+        cudaError_t e = cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]);
+        c->last_ms[i] = e == cudaSuccess ? ms : -1.f;
+    }
+    float tot = 0;
+    cudaError_t e = cudaEventElapsedTime(&tot, c->ev[RR_T_H2D], c->ev[RR_T_TOTAL]);
+    c->last_ms[RR_T_TOTAL] = e == cudaSuccess ? tot : -1.f;
+    return RR_OK;
+}
+
+static int check_flag(rr_context *c) {
+    int flag = 0;
+    CK(cudaMemcpyAsync(&flag, c->fb.err_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (flag) {
+        set_err("patch arena overflow (%lld float64 elements): streaks were dropped; raise RR_ARENA_MULT or lower the batch",
+                c->fb.arena_cap);
+        return RR_ERR_CAPACITY;
+    }
+    return RR_OK;
+}
+
+int rr_render_frames(rr_context *c, int n_frames, const uint8_t *bgr, const float *depth, const rr_streak_rec *streaks,
+                     const int32_t *streak_offsets, float *out_bgr, float *out_mask, uint8_t *out_bgr_u8) {
+    int r = check_ready(c, n_frames, "rr_render_frames");
+    if (r != RR_OK) return r;
+    if (!bgr || !depth || !streak_offsets) { set_err("rr_render_frames: NULL input"); return RR_ERR_ARG; }
+    if (!c->d_db) { set_err("rr_render_frames: no streak DB"); return RR_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    const int F = n_frames, n_streaks = streak_offsets[F];
+    if (streak_offsets[0] != 0 || n_streaks < 0 || (n_streaks > 0 && !streaks)) { set_err("rr_render_frames: bad streak offsets"); return RR_ERR_ARG; }
+    for (int f = 0; f < F; f++)
+        if (streak_offsets[f + 1] < streak_offsets[f]) { set_err("rr_render_frames: streak offsets not monotone"); return RR_ERR_ARG; }
+    r = ensure_streak_cap(c, n_streaks);
+    if (r != RR_OK) return r;
+    const size_t np = (size_t)c->cam.W * c->cam.H;
+    cudaStream_t st = c->stream;
+    rr_frame_bufs &b = c->fb;
+    CK(cudaEventRecord(c->ev[RR_T_H2D], st));
+    CK(cudaMemcpyAsync(c->d_bgr, bgr, F * np * 3, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_depth, depth, F * np * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (n_streaks) CK(cudaMemcpyAsync(c->d_streaks, streaks, (size_t)n_streaks * sizeof(rr_streak_rec), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_offsets, streak_offsets, (F + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    b.bgr = c->d_bgr; b.depth = c->d_depth; b.streaks = c->d_streaks; b.offsets = c->d_offsets;
+    r = run_pipeline(c, F, n_streaks, true);
+    if (r != RR_OK) return r;
+    if (out_bgr) CK(cudaMemcpyAsync(out_bgr, b.out_bgr, F * np * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out_mask) CK(cudaMemcpyAsync(out_mask, b.out_mask, F * np * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (out_bgr_u8) CK(cudaMemcpyAsync(out_bgr_u8, b.out_u8, F * np * 3, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(c->ev[RR_T_TOTAL], st));
+    r = check_flag(c);
+    finish_timings(c);
+    return r;
+}
+
+int rr_render_frames_device(rr_context *c, int n_frames, const uint8_t *d_bgr, const float *d_depth,
+                            const rr_streak_rec *d_streaks, const int32_t *h_streak_offsets, float *d_out_bgr,
+                            float *d_out_mask, uint8_t *d_out_bgr_u8, int sync) {
+    int r = check_ready(c, n_frames, "rr_render_frames_device");
+    if (r != RR_OK) return r;
+    if (!d_bgr || !d_depth || !h_streak_offsets) { set_err("rr_render_frames_device: NULL input"); return RR_ERR_ARG; }
+    if (!c->d_db) { set_err("rr_render_frames_device: no streak DB"); return RR_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    const int F = n_frames, n_streaks = h_streak_offsets[F];
+    r = ensure_streak_cap(c, n_streaks);
+    if (r != RR_OK) return r;
+    cudaStream_t st = c->stream;
+    rr_frame_bufs b_saved = c->fb;
+    rr_frame_bufs &b = c->fb;
+    CK(cudaEventRecord(c->ev[RR_T_H2D], st));
+    CK(cudaMemcpyAsync(c->d_offsets, h_streak_offsets, (F + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    b.bgr = d_bgr; b.depth = d_depth; b.streaks = d_streaks; b.offsets = c->d_offsets;
+    if (d_out_bgr) b.out_bgr = d_out_bgr;
+    if (d_out_mask) b.out_mask = d_out_mask;
+    if (d_out_bgr_u8) b.out_u8 = d_out_bgr_u8;
+    r = run_pipeline(c, F, n_streaks, true);
+    b.out_bgr = b_saved.out_bgr; b.out_mask = b_saved.out_mask; b.out_u8 = b_saved.out_u8;
+    if (r != RR_OK) return r;
+    CK(cudaEventRecord(c->ev[RR_T_TOTAL], st));
+    if (sync) {
+        r = check_flag(c);
+        finish_timings(c);
+    }
+    return r;
+}
+
+int rr_fog_only(rr_context *c, int n_frames, const uint8_t *bgr, const float *depth, double *out_planar) {
+    int r = check_ready(c, n_frames, "rr_fog_only");
+    if (r != RR_OK) return r;
+    CK(cudaSetDevice(c->device));
+    const size_t np = (size_t)c->cam.W * c->cam.H, F = n_frames;
+    cudaStream_t st = c->stream;
+    rr_frame_bufs &b = c->fb;
+    CK(cudaMemcpyAsync(c->d_bgr, bgr, F * np * 3, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_depth, depth, F * np * sizeof(float), cudaMemcpyHostToDevice, st));
+    b.bgr = c->d_bgr; b.depth = c->d_depth;
+    CK(rr_launch_stats(b, n_frames, c->cam.W, c->cam.H, st));
+    CK(rr_launch_fog(b, c->fogc, n_frames, c->cam.W, c->cam.H, st));
+    c->launches += 2;
+    CK(cudaMemcpyAsync(out_planar, b.rainy, F * 3 * np * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return RR_OK;
+}
+
+int rr_envmap_only(rr_context *c, int n_frames, const double *planar, uint8_t *out_env) {
+    int r = check_ready(c, n_frames, "rr_envmap_only");
+    if (r != RR_OK) return r;
+    CK(cudaSetDevice(c->device));
+    const size_t np = (size_t)c->cam.W * c->cam.H, F = n_frames, npe = (size_t)c->H_env * c->W_env;
+    cudaStream_t st = c->stream;
+    rr_frame_bufs &b = c->fb;
+    CK(cudaMemcpyAsync(b.rainy, planar, F * 3 * np * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(rr_launch_planar_to_bg8(b.rainy, b.bg8, n_frames, c->cam.W, c->cam.H, st));
+    CK(rr_launch_env(b, tabs_of(c), n_frames, c->cam.W, c->cam.H, c->W_env, st));
+    c->launches += 5;
+    CK(cudaMemcpyAsync(out_env, b.env8, F * npe * 3, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return RR_OK;
+}
+
+int rr_streak_photometry_only(rr_context *c, const uint8_t *env_bgr_u8, int n_streaks, const rr_streak_rec *streaks,
+                              double *out3) {
+    int r = check_ready(c, 1, "rr_streak_photometry_only");
+    if (r != RR_OK) return r;
+    if (!c->d_db) { set_err("rr_streak_photometry_only: no streak DB"); return RR_ERR_STATE; }
+    if (n_streaks <= 0) return RR_OK;
+    CK(cudaSetDevice(c->device));
+    r = ensure_streak_cap(c, n_streaks);
+    if (r != RR_OK) return r;
+    const size_t npe = (size_t)c->H_env * c->W_env;
+    cudaStream_t st = c->stream;
+    rr_frame_bufs &b = c->fb;
+    CK(cudaMemcpyAsync(b.env8, env_bgr_u8, npe * 3, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->d_streaks, streaks, (size_t)n_streaks * sizeof(rr_streak_rec), cudaMemcpyHostToDevice, st));
+    int32_t off[2] = {0, n_streaks};
+    CK(cudaMemcpyAsync(c->d_offsets, off, sizeof(off), cudaMemcpyHostToDevice, st));
+    b.streaks = c->d_streaks; b.offsets = c->d_offsets;
+    rr_static_tabs t = tabs_of(c);
+    // prefix sums of the given map, then the per-streak set-up
+    CK(rr_launch_env_prefix_only(b, t, 1, c->H_env, c->W_env, st));
+    c->camd.db_width = c->db_width; c->camd.n_tex = c->n_tex;
+    CK(rr_launch_setup(b, t, c->camd, 1, n_streaks, st));
+    c->launches += 3;
+    std::vector<rr_plan> plans(n_streaks);
+    CK(cudaMemcpyAsync(plans.data(), b.plans, sizeof(rr_plan) * n_streaks, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < n_streaks; i++) {
+        out3[3 * i] = plans[i].valid ? plans[i].fov_x : NAN;
+        out3[3 * i + 1] = plans[i].valid ? plans[i].fov_y : NAN;
+        out3[3 * i + 2] = plans[i].valid ? plans[i].drop_Y : NAN;
+    }
+    return RR_OK;
+}
+
+int rr_debug_read(rr_context *c, int what, int frame, void *dst, size_t bytes) {
+    if (!c || !c->have_cam || !dst) { set_err("rr_debug_read: bad arguments"); return RR_ERR_ARG; }
+    if (frame < 0 || frame >= c->max_batch) { set_err("rr_debug_read: frame out of range"); return RR_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    const size_t np = (size_t)c->cam.W * c->cam.H, npe = (size_t)c->H_env * c->W_env;
+    const rr_frame_bufs &b = c->fb;
+    const void *src = nullptr;
+    size_t avail = 0;
+    switch (what) {
+        case RR_DBG_FOG_F64:
+        case RR_DBG_RAINY_F64: src = b.rainy + (size_t)frame * 3 * np; avail = 3 * np * sizeof(double); break;
+        case RR_DBG_ENV_U8: src = b.env8 + (size_t)frame * npe * 3; avail = npe * 3; break;
+        case RR_DBG_OMEGA: src = c->d_omega; avail = npe * sizeof(double); break;
+        case RR_DBG_PLANS: src = b.plans; avail = sizeof(rr_plan) * (size_t)c->last_n_streaks; break;
+        case RR_DBG_ENV_SRC: src = c->d_env_src; avail = npe * sizeof(int32_t); break;
+        case RR_DBG_ARENA: src = b.arena; avail = (size_t)b.arena_cap * sizeof(double); break;
+        case RR_DBG_FEXT: src = b.fblur + (size_t)frame * np; avail = np * sizeof(float); break;
+        default: set_err("rr_debug_read: unknown selector %d", what); return RR_ERR_ARG;
+    }
+    if (bytes > avail) bytes = avail;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
+    return RR_OK;
+}
+
+int rr_timings(rr_context *c, float *ms) {
+    if (!c || !ms) { set_err("rr_timings: bad arguments"); return RR_ERR_ARG; }
+    memcpy(ms, c->last_ms, sizeof(c->last_ms));
+    return RR_OK;
+}
+
+int rr_kernel_launches(rr_context *c, long long *count) {
+    if (!c || !count) { set_err("rr_kernel_launches: bad arguments"); return RR_ERR_ARG; }
+    *count = c->launches;
+    return RR_OK;
+}
+
+int rr_stream(rr_context *c, void **s) {
+    if (!c || !s) { set_err("rr_stream: bad arguments"); return RR_ERR_ARG; }
+    *s = (void *)c->stream;
+    return RR_OK;
+}
+
+int rr_host_alloc(void **ptr, size_t bytes) {
+    if (!ptr) { set_err("rr_host_alloc: ptr is NULL"); return RR_ERR_ARG; }
+    CK(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+    return RR_OK;
+}
+
+int rr_host_free(void *ptr) {
+    if (ptr) CK(cudaFreeHost(ptr));
+    return RR_OK;
+}
+
+int rr_synchronize(rr_context *c) {
+    if (!c) { set_err("rr_synchronize: context is NULL"); return RR_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    int r = c->have_cam ? check_flag(c) : RR_OK;
+    if (c->have_cam) finish_timings(c);
+    return r;
+}
+
+}  // extern "C"

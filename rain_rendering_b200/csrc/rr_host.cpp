@@ -1,0 +1,89 @@
+// Host-side helpers exported through the C ABI (no CUDA): a bit-exact mirror of the two NumPy
+// legacy-RNG draws the reference makes per streak, so the per-frame path needs no Python-level
+// RNG calls.
+//   np.random.seed(frame_idx)                      common/generator.py:318
+//   np.random.randint(10*b, 10*b + 10)             common/bad_weather.py:252-264   (every streak)
+//   np.random.normal(0.0, noise_std) * noise_scale common/generator.py:136         (non-Big streaks)
+// NumPy legacy stream (numpy/random/_mt19937.pyx, src/legacy/legacy-distributions.c):
+// MT19937 seeded by init_genrand; randint = masked rejection on 32-bit draws; normal = polar
+// Box-Muller with a cached second variate on 53-bit doubles.
+#include <math.h>
+#include <stdint.h>
+#include "../../include/rain_b200.h"
+
+namespace {
+struct MT {
+    uint32_t key[624];
+    int pos;
+    int has_gauss;
+    double gauss;
+    void seed(uint32_t s) {
+        for (int i = 0; i < 624; i++) {
+            key[i] = s;
+            s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)i + 1u;
+        }
+        pos = 624; has_gauss = 0; gauss = 0.0;
+    }
+    void gen() {
+        const uint32_t N = 624, M = 397, MATRIX_A = 0x9908b0dfu, UPPER = 0x80000000u, LOWER = 0x7fffffffu;
+        uint32_t y;
+        uint32_t i;
+        for (i = 0; i < N - M; i++) { y = (key[i] & UPPER) | (key[i + 1] & LOWER); key[i] = key[i + M] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MATRIX_A); }
+        for (; i < N - 1; i++) { y = (key[i] & UPPER) | (key[i + 1] & LOWER); key[i] = key[i + (M - N)] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MATRIX_A); }
+        y = (key[N - 1] & UPPER) | (key[0] & LOWER);
+        key[N - 1] = key[M - 1] ^ (y >> 1) ^ (-(int32_t)(y & 1) & MATRIX_A);
+        pos = 0;
+    }
+    uint32_t next32() {
+        if (pos == 624) gen();
+        uint32_t y = key[pos++];
+        y ^= (y >> 11);
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= (y >> 18);
+        return y;
+    }
+    double next_double() {
+        int32_t a = next32() >> 5, b = next32() >> 6;
+        return (a * 67108864.0 + b) / 9007199254740992.0;
+    }
+    // legacy randint(low, low + 10): rng = 9, mask = 15
+    uint32_t bounded(uint32_t rng) {
+        uint32_t mask = rng;
+        mask |= mask >> 1; mask |= mask >> 2; mask |= mask >> 4; mask |= mask >> 8; mask |= mask >> 16;
+        uint32_t v;
+        do { v = next32() & mask; } while (v > rng);
+        return v;
+    }
+    double legacy_gauss() {
+        if (has_gauss) {
+            double t = gauss;
+            has_gauss = 0; gauss = 0.0;
+            return t;
+        }
+        double f, x1, x2, r2;
+        do {
+            x1 = 2.0 * next_double() - 1.0;
+            x2 = 2.0 * next_double() - 1.0;
+            r2 = x1 * x1 + x2 * x2;
+        } while (r2 >= 1.0 || r2 == 0.0);
+        f = sqrt(-2.0 * log(r2) / r2);
+        gauss = f * x1; has_gauss = 1;
+        return f * x2;
+    }
+};
+}  // namespace
+
+extern "C" int rr_host_draw_randoms(uint32_t seed, int n, const uint8_t *types, const int32_t *buckets, double noise_std,
+                                    double noise_scale, uint8_t *tex_idx, double *noise_deg) {
+    if (n < 0 || (n > 0 && (!types || !buckets || !tex_idx || !noise_deg))) return RR_ERR_ARG;
+    MT mt;
+    mt.seed(seed);
+    for (int i = 0; i < n; i++) {
+        int lo = 10 * buckets[i];
+        tex_idx[i] = (uint8_t)(lo + (int)mt.bounded(9));
+        if (types[i] != 0) noise_deg[i] = (0.0 + noise_std * mt.legacy_gauss()) * noise_scale;
+        else noise_deg[i] = 0.0;
+    }
+    return RR_OK;
+}

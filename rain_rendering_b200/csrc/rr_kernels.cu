@@ -1,0 +1,922 @@
+// CUDA kernels of the rain-rendering hot path (sm_100a).  Compiled with -fmad=false: every
+// float64 expression keeps the reference's operation order without FMA contraction.
+// Reference citations are relative to astra-vision/rain-rendering.
+#include "rr_kernels.cuh"
+#include <stdio.h>
+
+// ------------------------------------------------------------------------------------------
+// constants (uploaded once by rr_upload_constants)
+// ------------------------------------------------------------------------------------------
+__constant__ double c_k64[25];      // cv2.getGaussianKernel(25, 25, CV_64F)   (add_attenuation.py:79-80)
+__constant__ float c_k32[25];       // cv2.getGaussianKernel(25, 25, CV_32F)
+__constant__ int c_k15[15];         // OpenCV fixed-point (8 fractional bits) kernel of GaussianBlur((15,15), 0) on uint8
+__device__ float d_cubic[RR_INTER_TAB * 4];   // divergent per-thread indexing: global/L1, not the constant bank
+
+// half of the symmetric 25-tap kernel as OpenCV 4.13 computes it (bit-exact softfloat path);
+// tests/test_host_logic.py checks these against cv2.getGaussianKernel.
+static const double h_k64_half[13] = {
+    0x1.30388bb7cc924p-5, 0x1.35ded00af4b8ep-5, 0x1.3b1ec2bb8377ap-5, 0x1.3ff2529db4fc4p-5, 0x1.4453db9cbbcb7p-5,
+    0x1.483e31b371756p-5, 0x1.4bacab167051ep-5, 0x1.4e9b2973a742ep-5, 0x1.5106222dbfd23p-5, 0x1.52eaa57c51c85p-5,
+    0x1.5446645cd4cffp-5, 0x1.5517b5437ec3fp-5, 0x1.555d977eb8796p-5};
+static const int h_k15[15] = {1, 3, 6, 12, 20, 30, 36, 40, 36, 30, 20, 12, 6, 3, 1};
+
+extern "C" void rr_host_tables(double *k64, float *k32, int *k15) {
+    for (int i = 0; i < 25; i++) {
+        double v = h_k64_half[i <= 12 ? i : 24 - i];
+        k64[i] = v;
+        k32[i] = (float)v;
+    }
+    for (int i = 0; i < 15; i++) k15[i] = h_k15[i];
+}
+
+cudaError_t rr_upload_constants() {
+    double k64[25]; float k32[25]; int k15[15];
+    rr_host_tables(k64, k32, k15);
+    float cub[RR_INTER_TAB * 4];
+    rr_build_cubic_tab(cub);
+    cudaError_t e;
+    if ((e = cudaMemcpyToSymbol(c_k64, k64, sizeof(k64))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_k32, k32, sizeof(k32))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(c_k15, k15, sizeof(k15))) != cudaSuccess) return e;
+    if ((e = cudaMemcpyToSymbol(d_cubic, cub, sizeof(cub))) != cudaSuccess) return e;
+    return cudaSuccess;
+}
+
+__device__ __forceinline__ int r101(int i, int n) {   // BORDER_REFLECT_101
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------
+// init-time: cylindrical environment-map tables  (bad_weather.py:742-812, geometry only)
+// ------------------------------------------------------------------------------------------
+__global__ void k_cyl_scatter(int W, int H, int f, int min_x, int cyl_w, int32_t *first) {
+    int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= W * H) return;
+    int yy = idx / W, xx = idx - yy * W;
+    int cx = W / 2, cy = H / 2;
+    double hh = (double)xx - cx, vv = (double)yy - cy;
+    double fd = (double)f;
+    double rowp = rint((fd * (vv / sqrt(hh * hh + (double)(f * f)))) + cy);      // :724-725,760
+    double colp = rint((fd * atan(hh / fd)) + cx) - min_x;                       // :726,760-761
+    int r = (int)rowp, c = (int)colp;
+    if (r < 0 || r >= H || c < 0 || c >= cyl_w) return;
+    atomicMin(&first[r * cyl_w + c], idx);    // np.unique(..., return_index=True): lowest flat index wins (:762-767)
+}
+
+__global__ void k_cyl_fill(int H, int cyl_w, const int32_t *first, int32_t *filled, uint8_t *written) {
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cyl_w) return;
+    const int NONE = 0x7fffffff;
+    int half = H / 2;
+    int y_up = 0;
+    for (int y = 0; y < half; y++) if (first[y * cyl_w + c] != NONE) { y_up = y; break; }     // np.argmax(mask>0) (:827)
+    int r_dn = 0;
+    for (int r = 0; r < H - half; r++) if (first[(H - 1 - r) * cyl_w + c] != NONE) { r_dn = r; break; }   // :839-841
+    int src_up = first[y_up * cyl_w + c], src_dn = first[(H - 1 - r_dn) * cyl_w + c];
+    for (int y = 0; y < H; y++) {
+        int v = first[y * cyl_w + c];
+        bool w = v != NONE;
+        if (!w) {
+            if (y < half) v = src_up;                  // :785-789
+            else if (y >= H - half) v = src_dn;        // :776-781
+        }
+        filled[y * cyl_w + c] = (v == NONE) ? -1 : v;
+        written[y * cyl_w + c] = w ? 1 : 0;
+    }
+}
+
+__global__ void k_cyl_expand(int H, int cyl_w, int W_env, const int32_t *filled, const uint8_t *written,
+                             int32_t *env_src, uint8_t *env_written) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H * W_env) return;
+    int y = i / W_env, j = i - y * W_env;
+    int pad = cyl_w / 2;
+    int len = cyl_w - cyl_w / 2, start = W_env - len;
+    int c;
+    if (j >= start) c = cyl_w - 1 - (j - start);       // :806-812
+    else if (j < pad) c = pad - 1 - j;                 // :797-803
+    else c = j - pad;                                  // :791
+    env_src[i] = filled[y * cyl_w + c];
+    env_written[i] = written[y * cyl_w + c];
+}
+
+__global__ void k_fill_i32(int32_t *p, int32_t v, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+cudaError_t rr_launch_env_tables(int W, int H, int focal_px, int cyl_w, int min_x, int W_env, int32_t *env_src,
+                                 uint8_t *env_written, int32_t *scratch, cudaStream_t st) {
+    // scratch: [H*cyl_w] first, [H*cyl_w] filled, then H*cyl_w bytes written
+    int32_t *first = scratch, *filled = scratch + (size_t)H * cyl_w;
+    uint8_t *written = (uint8_t *)(filled + (size_t)H * cyl_w);
+    k_fill_i32<<<(unsigned)(((size_t)H * cyl_w + 255) / 256), 256, 0, st>>>(first, 0x7fffffff, (size_t)H * cyl_w);
+    k_cyl_scatter<<<(W * H + 255) / 256, 256, 0, st>>>(W, H, focal_px, min_x, cyl_w, first);
+    k_cyl_fill<<<(cyl_w + 127) / 128, 128, 0, st>>>(H, cyl_w, first, filled, written);
+    k_cyl_expand<<<(H * W_env + 255) / 256, 256, 0, st>>>(H, cyl_w, W_env, filled, written, env_src, env_written);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// init-time: per-pixel solid angles of the lat-long map  (solid_angle.py:5-102)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void sa_corner(int ci, int ri, int W_env, int H_env, double v[3]) {
+    // np.linspace(0, 1, n + 1): i * (1/n), last element exactly 1
+    double u = (ci == W_env) ? 1.0 : ci * (1.0 / W_env);
+    double w = (ri == H_env) ? 1.0 : ri * (1.0 / H_env);
+    u = u * 2;
+    double theta = RR_PI * (u - 1);
+    double phi = RR_PI * w;
+    double sp = sin(phi);
+    v[0] = sp * sin(theta);
+    v[1] = cos(phi);
+    v[2] = -sp * cos(theta);
+}
+
+__device__ __forceinline__ double sa_tetra(const double a[3], const double b[3], const double c[3]) {
+    double ta = acos((b[0] * c[0] + b[1] * c[1]) + b[2] * c[2]);
+    double tb = acos((a[0] * c[0] + a[1] * c[1]) + a[2] * c[2]);
+    double tc = acos((a[0] * b[0] + a[1] * b[1]) + a[2] * b[2]);
+    double ts = (ta + tb + tc) / 2;
+    double product = tan(ts / 2) * tan((ts - ta) / 2) * tan((ts - tb) / 2) * tan((ts - tc) / 2);
+    if (product < 0) product = 0;
+    return 4 * atan(sqrt(product));
+}
+
+__global__ void k_omega(int H_env, int W_env, double *omega) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= H_env * W_env) return;
+    int r = i / W_env, c = i - r * W_env;
+    double a[3], b[3], cc[3], d[3];
+    sa_corner(c, r, W_env, H_env, a);
+    sa_corner(c + 1, r, W_env, H_env, b);
+    sa_corner(c, r + 1, W_env, H_env, cc);
+    sa_corner(c + 1, r + 1, W_env, H_env, d);
+    double o = sa_tetra(a, b, cc);
+    o += sa_tetra(b, cc, d);
+    omega[i] = o;
+}
+
+// one block per row: exclusive prefix (W_env + 1 entries) and the row total
+__global__ void k_row_prefix1(int W_env, const double *vals, double *pref, double *rowtot) {
+    int r = blockIdx.x;
+    if (threadIdx.x == 0) {
+        const double *v = vals + (size_t)r * W_env;
+        double *p = pref + (size_t)r * (W_env + 1);
+        double s = 0;
+        for (int c = 0; c < W_env; c++) { p[c] = s; s += v[c]; }
+        p[W_env] = s;
+        rowtot[r] = s;
+    }
+}
+
+__global__ void k_sum_serial(int n, const double *v, double *out) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double s = 0;
+        for (int i = 0; i < n; i++) s += v[i];
+        *out = s;
+    }
+}
+
+cudaError_t rr_launch_omega(int H_env, int W_env, double *omega, double *omega_pref, double *omega_total, cudaStream_t st) {
+    k_omega<<<(H_env * W_env + 127) / 128, 128, 0, st>>>(H_env, W_env, omega);
+    double *rowtot;
+    cudaError_t e = cudaMalloc(&rowtot, sizeof(double) * H_env);
+    if (e != cudaSuccess) return e;
+    k_row_prefix1<<<H_env, 32, 0, st>>>(W_env, omega, omega_pref, rowtot);
+    k_sum_serial<<<1, 32, 0, st>>>(H_env, rowtot, omega_total);
+    e = cudaStreamSynchronize(st);
+    cudaFree(rowtot);
+    return e != cudaSuccess ? e : cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// per frame: channel sums of the uint8 input (irradiance mean add_attenuation.py:70, bg mean generator.py:462)
+// ------------------------------------------------------------------------------------------
+__global__ void k_stats(const uint8_t *bgr, int npix, unsigned long long *chan_sum) {
+    int f = blockIdx.y;
+    const uint8_t *p = bgr + (size_t)f * npix * 3;
+    unsigned int s0 = 0, s1 = 0, s2 = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += gridDim.x * blockDim.x) {
+        s0 += p[3 * i]; s1 += p[3 * i + 1]; s2 += p[3 * i + 2];
+    }
+    __shared__ unsigned int sh[3][8];
+    for (int o = 16; o > 0; o >>= 1) {
+        s0 += __shfl_xor_sync(0xffffffffu, s0, o);
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    }
+    int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { sh[0][w] = s0; sh[1][w] = s1; sh[2][w] = s2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        unsigned long long t = 0;
+        for (int k = 0; k < (int)(blockDim.x >> 5); k++) t += sh[threadIdx.x][k];
+        atomicAdd(&chan_sum[f * 4 + threadIdx.x], t);      // integer: order independent, exact
+    }
+}
+
+cudaError_t rr_launch_stats(const rr_frame_bufs &b, int F, int W, int H, cudaStream_t st) {
+    cudaMemsetAsync(b.chan_sum, 0, sizeof(unsigned long long) * 4 * F, st);
+    dim3 grid(64, F);
+    k_stats<<<grid, 256, 0, st>>>(b.bgr, W * H, b.chan_sum);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// per frame: fog-like rain attenuation, one fused tile kernel  (add_attenuation.py:40-95)
+//   f_ext  = float32 exp(-beta * depth/1000)                     (:43-48, float32 like numpy)
+//   l_in_c = clip(beta_hg * E_c * (1 - f_ext), 0, 1)             (:53-72)
+//   both blurred 25x25 sigma 25 REFLECT_101                       (:79-80)
+//   l = clip(I * f_blur + l_in_blur, 0, 1)                        (:85-93)
+// ------------------------------------------------------------------------------------------
+#define FOG_TX 64
+#define FOG_TY 32
+#define FOG_R 12
+#define FOG_EW (FOG_TX + 2 * FOG_R)
+#define FOG_EH (FOG_TY + 2 * FOG_R)
+
+__global__ void __launch_bounds__(256) k_fog(rr_frame_bufs b, rr_fog_consts fc, int W, int H) {
+    extern __shared__ unsigned char smem_raw[];
+    float *E = (float *)smem_raw;                         // [FOG_EH][FOG_EW]
+    float *FH = E + FOG_EH * FOG_EW;                      // [FOG_EH][FOG_TX]  float32 row pass of f_ext
+    double *LH = (double *)(FH + FOG_EH * FOG_TX);        // [FOG_EH][FOG_TX]  float64 row pass of one l_in channel
+    const int f = blockIdx.z;
+    const int x0 = blockIdx.x * FOG_TX, y0 = blockIdx.y * FOG_TY;
+    const int tid = threadIdx.x;
+    const float *depth = b.depth + (size_t)f * W * H;
+    const uint8_t *bgr = b.bgr + (size_t)f * W * H * 3;
+    // -- extinction on the haloed tile (reflected coordinates)
+    for (int i = tid; i < FOG_EH * FOG_EW; i += 256) {
+        int ey = i / FOG_EW, ex = i - ey * FOG_EW;
+        int gy = r101(y0 + ey - FOG_R, H), gx = r101(x0 + ex - FOG_R, W);
+        float v = 0.f;
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+            float d = __fdiv_rn(depth[(size_t)gy * W + gx], 1000.f);
+            float xx = __fmul_rn(fc.neg_beta32, d);
+            v = (float)exp((double)xx);                  // correctly rounded float32 exp ("canonical")
+        }
+        E[i] = v;
+    }
+    __syncthreads();
+    // -- float32 row pass of f_ext: exact products, float64 accumulation ascending, one rounding
+    for (int i = tid; i < FOG_EH * FOG_TX; i += 256) {
+        int ey = i / FOG_TX, ox = i - ey * FOG_TX;
+        const float *row = E + ey * FOG_EW + ox;
+        double acc = (double)c_k32[0] * (double)row[0];
+#pragma unroll
+        for (int t = 1; t < 25; t++) acc += (double)c_k32[t] * (double)row[t];
+        FH[i] = (float)acc;
+    }
+    __syncthreads();
+    float fb[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int i = tid + k * 256;
+        int oy = i / FOG_TX, ox = i - oy * FOG_TX;
+        const float *col = FH + oy * FOG_TX + ox;
+        double acc = (double)c_k32[0] * (double)col[0];
+#pragma unroll
+        for (int t = 1; t < 25; t++) acc += (double)c_k32[t] * (double)col[t * FOG_TX];
+        fb[k] = (float)acc;
+        int gy = y0 + oy, gx = x0 + ox;
+        if (gy < H && gx < W && b.fblur) b.fblur[(size_t)f * W * H + (size_t)gy * W + gx] = fb[k];
+    }
+    const double npix = (double)W * (double)H;
+    for (int c = 0; c < 3; c++) {
+        // E_c: mean irradiance of the un-fogged image (:53,70)
+        double sum_b = (double)b.chan_sum[f * 4 + c] / 255.0;
+        double irr_mean = ((fc.irr_scale_num * sum_b) / fc.irr_den) / npix;
+        double Ac = fc.beta_hg * irr_mean;
+        __syncthreads();
+        // float64 row pass (cv::RowFilter order: k[0]*x[0] + k[1]*x[1] + ...)
+        for (int i = tid; i < FOG_EH * FOG_TX; i += 256) {
+            int ey = i / FOG_TX, ox = i - ey * FOG_TX;
+            const float *row = E + ey * FOG_EW + ox;
+            double acc = 0;
+#pragma unroll
+            for (int t = 0; t < 25; t++) {
+                double li = Ac * (double)(1.0f - row[t]);           // (1 - f_ext) is a float32 op in numpy
+                li = li < 0 ? 0 : (li > 1 ? 1 : li);
+                double term = c_k64[t] * li;
+                acc = (t == 0) ? term : acc + term;
+            }
+            LH[i] = acc;
+        }
+        __syncthreads();
+        // float64 column pass (cv::SymmColumnFilter order) + composition
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int i = tid + k * 256;
+            int oy = i / FOG_TX, ox = i - oy * FOG_TX;
+            int gy = y0 + oy, gx = x0 + ox;
+            const double *col = LH + (oy + FOG_R) * FOG_TX + ox;
+            double acc = c_k64[12] * col[0];
+#pragma unroll
+            for (int t = 1; t <= 12; t++) acc += c_k64[12 + t] * (col[t * FOG_TX] + col[-t * FOG_TX]);
+            if (gy < H && gx < W) {
+                size_t pix = (size_t)gy * W + gx;
+                double I = (double)bgr[pix * 3 + c] / 255.0;             // generator.py:352
+                double l = I * (double)fb[k] + acc;                      // :85
+                l = l < 0 ? 0 : (l > 1 ? 1 : l);
+                b.rainy[((size_t)f * 3 + c) * W * H + pix] = l;
+                b.bg8[((size_t)f * W * H + pix) * 3 + c] = (uint8_t)(l * 255);   // bad_weather.py:744
+            }
+        }
+    }
+}
+
+cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, cudaStream_t st) {
+    size_t smem = sizeof(float) * (FOG_EH * FOG_EW + FOG_EH * FOG_TX) + sizeof(double) * FOG_EH * FOG_TX;
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_fog, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    dim3 grid((W + FOG_TX - 1) / FOG_TX, (H + FOG_TY - 1) / FOG_TY, F);
+    k_fog<<<grid, 256, smem, st>>>(b, fc, W, H);
+    return cudaGetLastError();
+}
+
+__global__ void k_planar_to_bg8(const double *planar, uint8_t *bg8, int npix, int F) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)F * npix) return;
+    int f = (int)(i / npix);
+    size_t pix = i - (size_t)f * npix;
+    for (int c = 0; c < 3; c++) bg8[i * 3 + c] = (uint8_t)(planar[((size_t)f * 3 + c) * npix + pix] * 255);
+}
+
+cudaError_t rr_launch_planar_to_bg8(const double *planar, uint8_t *bg8, int F, int W, int H, cudaStream_t st) {
+    size_t n = (size_t)F * W * H;
+    k_planar_to_bg8<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(planar, bg8, W * H, F);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// per frame: environment map = gather + 15x15 uint8 blur on the hole pixels  (bad_weather.py:742-819)
+// ------------------------------------------------------------------------------------------
+__global__ void k_env_gather(const uint8_t *bg8, const int32_t *env_src, uint8_t *env_fill, int npix_img, int npix_env) {
+    int f = blockIdx.y;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix_env) return;
+    int s = env_src[i];
+    uint8_t v0 = 0, v1 = 0, v2 = 0;
+    if (s >= 0) {
+        const uint8_t *p = bg8 + ((size_t)f * npix_img + s) * 3;
+        v0 = p[0]; v1 = p[1]; v2 = p[2];
+    }
+    uint8_t *o = env_fill + ((size_t)f * npix_env + i) * 3;
+    o[0] = v0; o[1] = v1; o[2] = v2;
+}
+
+#define ENV_TX 64
+#define ENV_TY 16
+#define ENV_R 7
+__global__ void __launch_bounds__(256) k_env_blur(const uint8_t *env_fill, const uint8_t *env_written, uint8_t *env8, int H,
+                                                  int W_env) {
+    __shared__ uint8_t in[ENV_TY + 2 * ENV_R][ENV_TX + 2 * ENV_R][3];
+    __shared__ unsigned short hp[ENV_TY + 2 * ENV_R][ENV_TX][3];
+    int f = blockIdx.z;
+    int x0 = blockIdx.x * ENV_TX, y0 = blockIdx.y * ENV_TY;
+    const uint8_t *src = env_fill + (size_t)f * H * W_env * 3;
+    // does this tile contain a hole?  (most tiles do not: plain copy)
+    __shared__ int any_hole;
+    if (threadIdx.x == 0) any_hole = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < ENV_TX * ENV_TY; i += 256) {
+        int oy = i / ENV_TX, ox = i - oy * ENV_TX;
+        int gy = y0 + oy, gx = x0 + ox;
+        if (gy < H && gx < W_env && !env_written[(size_t)gy * W_env + gx]) any_hole = 1;
+    }
+    __syncthreads();
+    if (any_hole) {
+        for (int i = threadIdx.x; i < (ENV_TY + 2 * ENV_R) * (ENV_TX + 2 * ENV_R); i += 256) {
+            int ey = i / (ENV_TX + 2 * ENV_R), ex = i - ey * (ENV_TX + 2 * ENV_R);
+            int gy = r101(y0 + ey - ENV_R, H), gx = r101(x0 + ex - ENV_R, W_env);
+            bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W_env;
+            const uint8_t *p = src + ((size_t)gy * W_env + gx) * 3;
+            in[ey][ex][0] = ok ? p[0] : 0; in[ey][ex][1] = ok ? p[1] : 0; in[ey][ex][2] = ok ? p[2] : 0;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < (ENV_TY + 2 * ENV_R) * ENV_TX; i += 256) {
+            int ey = i / ENV_TX, ox = i - ey * ENV_TX;
+            unsigned s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+            for (int t = 0; t < 15; t++) {
+                s0 += c_k15[t] * in[ey][ox + t][0]; s1 += c_k15[t] * in[ey][ox + t][1]; s2 += c_k15[t] * in[ey][ox + t][2];
+            }
+            hp[ey][ox][0] = (unsigned short)s0; hp[ey][ox][1] = (unsigned short)s1; hp[ey][ox][2] = (unsigned short)s2;
+        }
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < ENV_TX * ENV_TY; i += 256) {
+        int oy = i / ENV_TX, ox = i - oy * ENV_TX;
+        int gy = y0 + oy, gx = x0 + ox;
+        if (gy >= H || gx >= W_env) continue;
+        size_t pix = (size_t)gy * W_env + gx;
+        uint8_t *o = env8 + ((size_t)f * H * W_env + pix) * 3;
+        if (env_written[pix]) {
+            const uint8_t *p = src + pix * 3;
+            o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+        } else {
+            unsigned s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+            for (int t = 0; t < 15; t++) {
+                s0 += c_k15[t] * hp[oy + t][ox][0]; s1 += c_k15[t] * hp[oy + t][ox][1]; s2 += c_k15[t] * hp[oy + t][ox][2];
+            }
+            o[0] = (uint8_t)((s0 + 32768u) >> 16); o[1] = (uint8_t)((s1 + 32768u) >> 16); o[2] = (uint8_t)((s2 + 32768u) >> 16);
+        }
+    }
+}
+
+// one block per (row, frame): xyY, solid-angle weighting, row prefix sums  (generator.py:407-408, bad_weather.py:393-395)
+__global__ void __launch_bounds__(256) k_env_prefix(const uint8_t *env8, const double *omega, double *pref, double *rowtot,
+                                                    int H, int W_env) {
+    int r = blockIdx.x, f = blockIdx.y;
+    const uint8_t *row = env8 + ((size_t)f * H + r) * W_env * 3;
+    const double *om = omega + (size_t)r * W_env;
+    int per = (W_env + 255) / 256;
+    int c0 = threadIdx.x * per, c1 = c0 + per < W_env ? c0 + per : W_env;
+    double sx = 0, sy = 0, sY = 0;
+    for (int c = c0; c < c1; c++) {
+        double bb = (double)row[c * 3] / 255.0, gg = (double)row[c * 3 + 1] / 255.0, rr = (double)row[c * 3 + 2] / 255.0;
+        double X = ((rr * 0.49000 + gg * 0.17697) + bb * 0.00000) / 0.17697;      // my_utils.py:56-59 (row vector x M)
+        double Y = ((rr * 0.31000 + gg * 0.81240) + bb * 0.01000) / 0.17697;
+        double Z = ((rr * 0.20000 + gg * 0.01063) + bb * 0.99000) / 0.17697;
+        double S = (X + Y) + Z;
+        double x = X / S, y = Y / S;
+        if (!(x == x)) x = 0;                                                      // generator.py:408
+        if (!(y == y)) y = 0;
+        sx += x * om[c]; sy += y * om[c]; sY += Y * om[c];
+    }
+    __shared__ double tx[256], ty[256], tY[256];
+    tx[threadIdx.x] = sx; ty[threadIdx.x] = sy; tY[threadIdx.x] = sY;
+    __syncthreads();
+    if (threadIdx.x == 0) {          // serial exclusive scan of 256 thread totals: deterministic
+        double ax = 0, ay = 0, aY = 0;
+        for (int t = 0; t < 256; t++) {
+            double vx = tx[t], vy = ty[t], vY = tY[t];
+            tx[t] = ax; ty[t] = ay; tY[t] = aY;
+            ax += vx; ay += vy; aY += vY;
+        }
+        size_t base = ((size_t)f * 3 * H + r) * (W_env + 1);
+        pref[base + W_env] = ax;
+        pref[base + (size_t)H * (W_env + 1) + W_env] = ay;
+        pref[base + 2 * (size_t)H * (W_env + 1) + W_env] = aY;
+        rowtot[(size_t)f * H + r] = aY;
+    }
+    __syncthreads();
+    double ax = tx[threadIdx.x], ay = ty[threadIdx.x], aY = tY[threadIdx.x];
+    size_t base = ((size_t)f * 3 * H + r) * (W_env + 1);
+    double *px = pref + base, *py = px + (size_t)H * (W_env + 1), *pY = py + (size_t)H * (W_env + 1);
+    for (int c = c0; c < c1; c++) {
+        double bb = (double)row[c * 3] / 255.0, gg = (double)row[c * 3 + 1] / 255.0, rr = (double)row[c * 3 + 2] / 255.0;
+        double X = ((rr * 0.49000 + gg * 0.17697) + bb * 0.00000) / 0.17697;
+        double Y = ((rr * 0.31000 + gg * 0.81240) + bb * 0.01000) / 0.17697;
+        double Z = ((rr * 0.20000 + gg * 0.01063) + bb * 0.99000) / 0.17697;
+        double S = (X + Y) + Z;
+        double x = X / S, y = Y / S;
+        if (!(x == x)) x = 0;
+        if (!(y == y)) y = 0;
+        px[c] = ax; py[c] = ay; pY[c] = aY;
+        ax += x * om[c]; ay += y * om[c]; aY += Y * om[c];
+    }
+}
+
+__global__ void k_ambient(const double *rowtot, double *ambient, int H) {
+    int f = blockIdx.x;
+    if (threadIdx.x == 0) {
+        double s = 0;
+        for (int r = 0; r < H; r++) s += rowtot[(size_t)f * H + r];
+        ambient[f] = s;
+    }
+}
+
+cudaError_t rr_launch_env(const rr_frame_bufs &b, const rr_static_tabs &t, int F, int W, int H, int W_env, cudaStream_t st) {
+    int npe = H * W_env;
+    dim3 g1((npe + 255) / 256, F);
+    k_env_gather<<<g1, 256, 0, st>>>(b.bg8, t.env_src, b.env_fill, W * H, npe);
+    dim3 g2((W_env + ENV_TX - 1) / ENV_TX, (H + ENV_TY - 1) / ENV_TY, F);
+    k_env_blur<<<g2, 256, 0, st>>>(b.env_fill, t.env_written, b.env8, H, W_env);
+    dim3 g3(H, F);
+    k_env_prefix<<<g3, 256, 0, st>>>(b.env8, t.omega, b.pref, b.rowtot, H, W_env);
+    k_ambient<<<F, 32, 0, st>>>(b.rowtot, b.ambient, H);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// per streak: FOV polygon -> mask spans -> solid-angle weighted sums -> tint; patch plan
+//   (bad_weather.py:596-704, 363-413; generator.py:119-171).  One warp per streak.
+// ------------------------------------------------------------------------------------------
+#define SETUP_WARPS 4
+__global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(rr_frame_bufs b, rr_static_tabs t, rr_cam_dev cam, int F,
+                                                             int n_streaks) {
+    __shared__ rr_fcp s_fcp[SETUP_WARPS];
+    __shared__ int s_npts[SETUP_WARPS];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int s = blockIdx.x * SETUP_WARPS + warp;
+    if (s >= n_streaks) return;
+    // frame of this streak: binary search in offsets
+    int lo = 0, hi = F;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (b.offsets[mid] <= s) lo = mid; else hi = mid; }
+    const int f = lo;
+    const rr_streak_rec rec = b.streaks[s];
+    rr_fcp &fc = s_fcp[warp];
+    const int rows = cam.H_env, cols = cam.W_env;
+    if (lane == 0) {
+        double px[RR_MAX_POLY], py[RR_MAX_POLY];
+        int n = rr_fov_polygon(rec, cam.radius, cam.fov_deg, rows, cols, px, py);
+        int m = n > 0 ? rr_clip_fov_polygon(px, py, n, cols, rows, fc.vx, fc.vy) : 0;
+        fc.npts = m;
+        if (m > 0) rr_fcp_prepare(fc, cols, rows);
+        s_npts[warp] = m;
+    }
+    __syncwarp();
+    int m = s_npts[warp];
+    double sx = 0, sy = 0, sY = 0, sw = 0;
+    if (m > 0) {
+        int ymin = 0x7fffffff, ymax = -0x7fffffff;
+        for (int i = 0; i < m; i++) { int vy = fc.vy[i]; ymin = vy < ymin ? vy : ymin; ymax = vy > ymax ? vy : ymax; }
+        if (ymin < 0) ymin = 0;
+        if (ymax > rows - 1) ymax = rows - 1;
+        const size_t stride = (size_t)(cols + 1);
+        const double *Px = b.pref + (size_t)f * 3 * rows * stride;
+        const double *Py = Px + (size_t)rows * stride, *PY = Py + (size_t)rows * stride;
+        int ivl[RR_MAX_POLY + 2], ivh[RR_MAX_POLY + 2];
+        for (int y = ymin + lane; y <= ymax; y += 32) {
+            int k = rr_fcp_row(fc, y, ivl, ivh);
+            for (int j = 0; j < k; j++) {
+                size_t a = (size_t)y * stride + ivl[j], e = (size_t)y * stride + ivh[j] + 1;
+                sx += Px[e] - Px[a]; sy += Py[e] - Py[a]; sY += PY[e] - PY[a];
+                sw += t.omega_pref[e] - t.omega_pref[a];
+            }
+        }
+        sx = warp_sum(sx); sy = warp_sum(sy); sY = warp_sum(sY); sw = warp_sum(sw);
+    }
+    if (lane == 0) {
+        rr_plan p;
+        memset(&p, 0, sizeof(p));
+        bool ok = m > 0 && rec.tex_idx < cam.n_tex;
+        if (ok) ok = rr_plan_patch(rec, cam, t.tex_h[rec.tex_idx], p);
+        if (ok) {
+            p.tex_off = t.tex_off[rec.tex_idx];
+            double omega_total = *t.omega_total;
+            double fov_x = sx / sw, fov_y = sy / sw;                        // bad_weather.py:397
+            double ambient = b.ambient[f] / omega_total;                    // :403-404
+            double avg_fov_lum = sY / omega_total;                          // :407
+            double drop_Y = 0.94 * avg_fov_lum + 0.06 * ambient;            // :408
+            p.fov_x = fov_x; p.fov_y = fov_y; p.drop_Y = drop_Y;
+            rr_tint(fov_x, fov_y, drop_Y, &p.kb, &p.kg, &p.kr);
+        } else {
+            p.pw = p.ph = p.bw = p.bh = 0;
+        }
+        p.valid = ok ? 1 : 0;
+        b.plans[s] = p;
+    }
+}
+
+cudaError_t rr_launch_setup(const rr_frame_bufs &b, const rr_static_tabs &t, const rr_cam_dev &cam, int F, int n_streaks,
+                            cudaStream_t st) {
+    if (n_streaks == 0) return cudaSuccess;
+    k_setup<<<(n_streaks + SETUP_WARPS - 1) / SETUP_WARPS, SETUP_WARPS * 32, 0, st>>>(b, t, cam, F, n_streaks);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// arena layout + work lists: exclusive scans over the streaks (single block, deterministic)
+//   scan[i*6 + 0..2]: element offsets of g (pre-blur patch), v (column-pass result), a (blurred alpha block)
+//   scan[i*6 + 3..5]: chunk prefix of the raster, column-pass and row-pass kernels
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void blur_extents(const rr_plan &p, int *vx0, int *vw) {
+    // padded columns of the column-pass result that the visible block needs and that are non-zero
+    int a = p.cropx - p.rx, e = p.cropx + p.bw + p.rx;
+    if (a < p.shift) a = p.shift;
+    if (e > p.shift + p.pw) e = p.shift + p.pw;
+    *vx0 = a;
+    *vw = e > a ? e - a : 0;
+}
+
+__global__ void __launch_bounds__(1024) k_scan(rr_frame_bufs b, int n) {
+    __shared__ long long tot[1024][4];
+    int tid = threadIdx.x;
+    int per = (n + 1023) / 1024;
+    int i0 = tid * per, i1 = i0 + per < n ? i0 + per : n;
+    long long el = 0, c0 = 0, c1 = 0, c2 = 0;
+    for (int i = i0; i < i1; i++) {
+        const rr_plan &p = b.plans[i];
+        long long g = 0, v = 0, a = 0;
+        if (p.valid && p.bw > 0 && p.bh > 0) {
+            int vx0, vw; blur_extents(p, &vx0, &vw);
+            g = (long long)p.pw * p.ph; v = (long long)vw * p.bh; a = (long long)p.bw * p.bh;
+        }
+        el += g + v + a;
+        c0 += (g + RR_RASTER_CHUNK - 1) / RR_RASTER_CHUNK;
+        c1 += (v + RR_BLUR_CHUNK - 1) / RR_BLUR_CHUNK;
+        c2 += (a + RR_BLUR_CHUNK - 1) / RR_BLUR_CHUNK;
+    }
+    tot[tid][0] = el; tot[tid][1] = c0; tot[tid][2] = c1; tot[tid][3] = c2;
+    __syncthreads();
+    if (tid == 0) {
+        long long a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        for (int t = 0; t < 1024; t++) {
+            long long v0 = tot[t][0], v1 = tot[t][1], v2 = tot[t][2], v3 = tot[t][3];
+            tot[t][0] = a0; tot[t][1] = a1; tot[t][2] = a2; tot[t][3] = a3;
+            a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+        }
+        b.scan[(size_t)n * 6 + 0] = a0; b.scan[(size_t)n * 6 + 3] = a1; b.scan[(size_t)n * 6 + 4] = a2; b.scan[(size_t)n * 6 + 5] = a3;
+        if (a0 > b.arena_cap) *b.err_flag = 1;
+    }
+    __syncthreads();
+    el = tot[tid][0]; c0 = tot[tid][1]; c1 = tot[tid][2]; c2 = tot[tid][3];
+    for (int i = i0; i < i1; i++) {
+        rr_plan &p = b.plans[i];
+        long long g = 0, v = 0, a = 0;
+        if (p.valid && p.bw > 0 && p.bh > 0) {
+            int vx0, vw; blur_extents(p, &vx0, &vw);
+            g = (long long)p.pw * p.ph; v = (long long)vw * p.bh; a = (long long)p.bw * p.bh;
+            if (el + g + v + a > b.arena_cap) { g = v = a = 0; p.bw = p.bh = 0; p.valid = 0; }   // overflow: dropped, error flag set
+        }
+        long long *sc = b.scan + (size_t)i * 6;
+        sc[0] = el; sc[1] = el + g; sc[2] = el + g + v; sc[3] = c0; sc[4] = c1; sc[5] = c2;
+        p.g_off = el; p.a_off = el + g + v;
+        el += g + v + a;
+        c0 += (g + RR_RASTER_CHUNK - 1) / RR_RASTER_CHUNK;
+        c1 += (v + RR_BLUR_CHUNK - 1) / RR_BLUR_CHUNK;
+        c2 += (a + RR_BLUR_CHUNK - 1) / RR_BLUR_CHUNK;
+    }
+}
+
+cudaError_t rr_launch_scan(const rr_frame_bufs &b, int n_streaks, cudaStream_t st) {
+    k_scan<<<1, 1024, 0, st>>>(b, n_streaks);
+    return cudaGetLastError();
+}
+
+// chunk -> streak: largest i with scan[i*6 + field] <= chunk
+__device__ __forceinline__ int find_streak(const long long *scan, int n, int field, long long chunk) {
+    int lo = 0, hi = n;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (scan[(size_t)mid * 6 + field] <= chunk) lo = mid; else hi = mid; }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// pre-blur gray patches  (generator.py:126-171): persistent CTAs over 128-pixel chunks
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(RR_RASTER_CHUNK) k_raster(rr_frame_bufs b, rr_static_tabs t, rr_cam_dev cam, int n) {
+    __shared__ rr_plan sp;
+    const long long total = b.scan[(size_t)n * 6 + 3];
+    for (long long ch = blockIdx.x; ch < total; ch += gridDim.x) {
+        int s = find_streak(b.scan, n, 3, ch);
+        __syncthreads();
+        if (threadIdx.x < sizeof(rr_plan) / 4) ((int *)&sp)[threadIdx.x] = ((const int *)&b.plans[s])[threadIdx.x];
+        __syncthreads();
+        const rr_plan &p = sp;
+        long long e = (ch - b.scan[(size_t)s * 6 + 3]) * RR_RASTER_CHUNK + threadIdx.x;
+        long long g = (long long)p.pw * p.ph;
+        if (e < g) {
+            int y = (int)(e / p.pw), x = (int)(e - (long long)y * p.pw);
+            b.arena[p.g_off + e] = rr_patch_pixel(p, t.db + p.tex_off, cam.db_width, d_cubic, x, y);
+        }
+    }
+}
+
+cudaError_t rr_launch_raster(const rr_frame_bufs &b, const rr_static_tabs &t, const rr_cam_dev &cam, int n_streaks, int n_sm,
+                             cudaStream_t st) {
+    if (n_streaks == 0) return cudaSuccess;
+    k_raster<<<n_sm * 8, RR_RASTER_CHUNK, 0, st>>>(b, t, cam, n_streaks);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// defocus: scipy.ndimage.gaussian_filter(drop, [c, c/2, 0]) on the zero-padded patch
+// (bad_weather.py:286-298).  Only the alpha channel is filtered: before the blur the three
+// colour channels equal alpha * k_c (tint of a gray texture), so blur(colour_c) = k_c * blur(alpha)
+// up to float64 rounding (DESIGN.md "linear tint").
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_weights(double sigma, int r, double *w) {
+    // all threads of the block call this; w in shared memory
+    if (threadIdx.x == 0) rr_gauss_weights(sigma, r, w);
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(RR_BLUR_CHUNK) k_blur_v(rr_frame_bufs b, int n) {
+    __shared__ double w[2 * RR_MAX_GAUSS_R + 1];
+    const long long total = b.scan[(size_t)n * 6 + 4];
+    for (long long ch = blockIdx.x; ch < total; ch += gridDim.x) {
+        int s = find_streak(b.scan, n, 4, ch);
+        const rr_plan &p = b.plans[s];
+        __syncthreads();
+        load_weights(p.sig_y, p.ry, w);
+        int vx0, vw; blur_extents(p, &vx0, &vw);
+        long long e = (ch - b.scan[(size_t)s * 6 + 4]) * RR_BLUR_CHUNK + threadIdx.x;
+        long long nv = (long long)vw * p.bh;
+        if (e < nv) {
+            int yy = (int)(e / vw), xx = (int)(e - (long long)yy * vw);
+            int Y = p.cropy + yy;            // padded row
+            int gx = vx0 + xx - p.shift;     // patch column
+            int gy = Y - p.shift;            // patch row of the centre tap (may be outside)
+            const double *g = b.arena + p.g_off;
+            const int ry = p.ry;
+            // SciPy correlate1d, symmetric weights: centre first, then pairs from the outside in
+            double c = (gy >= 0 && gy < p.ph) ? g[(size_t)gy * p.pw + gx] : 0.0;
+            double tmp = c * w[ry];
+            for (int jj = -ry; jj < 0; jj++) {
+                int ya = gy + jj, yb = gy - jj;
+                double va = (ya >= 0 && ya < p.ph) ? g[(size_t)ya * p.pw + gx] : 0.0;
+                double vb = (yb >= 0 && yb < p.ph) ? g[(size_t)yb * p.pw + gx] : 0.0;
+                tmp += (va + vb) * w[jj + ry];
+            }
+            b.arena[b.scan[(size_t)s * 6 + 1] + e] = tmp;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(RR_BLUR_CHUNK) k_blur_h(rr_frame_bufs b, int n) {
+    __shared__ double w[2 * RR_MAX_GAUSS_R + 1];
+    const long long total = b.scan[(size_t)n * 6 + 5];
+    for (long long ch = blockIdx.x; ch < total; ch += gridDim.x) {
+        int s = find_streak(b.scan, n, 5, ch);
+        const rr_plan &p = b.plans[s];
+        __syncthreads();
+        load_weights(p.sig_x, p.rx, w);
+        int vx0, vw; blur_extents(p, &vx0, &vw);
+        long long e = (ch - b.scan[(size_t)s * 6 + 5]) * RR_BLUR_CHUNK + threadIdx.x;
+        long long na = (long long)p.bw * p.bh;
+        if (e < na) {
+            int yy = (int)(e / p.bw), xx = (int)(e - (long long)yy * p.bw);
+            int X = p.cropx + xx;            // padded column of the output
+            const double *v = b.arena + b.scan[(size_t)s * 6 + 1] + (size_t)yy * vw;
+            const int rx = p.rx;
+            int xc = X - vx0;
+            double c = (xc >= 0 && xc < vw) ? v[xc] : 0.0;
+            double tmp = c * w[rx];
+            for (int jj = -rx; jj < 0; jj++) {
+                int xa = xc + jj, xb = xc - jj;
+                double va = (xa >= 0 && xa < vw) ? v[xa] : 0.0;
+                double vb = (xb >= 0 && xb < vw) ? v[xb] : 0.0;
+                tmp += (va + vb) * w[jj + rx];
+            }
+            b.arena[p.a_off + e] = tmp;
+        }
+    }
+}
+
+cudaError_t rr_launch_blur(const rr_frame_bufs &b, int n_streaks, int n_sm, cudaStream_t st) {
+    if (n_streaks == 0) return cudaSuccess;
+    k_blur_v<<<n_sm * 4, RR_BLUR_CHUNK, 0, st>>>(b, n_streaks);
+    k_blur_h<<<n_sm * 4, RR_BLUR_CHUNK, 0, st>>>(b, n_streaks);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// ordered compositing  (bad_weather.py:429-460): the blend is streak-order dependent, so each
+// pixel walks the streaks that cover its tile in record (XML) order.  No atomics.
+// ------------------------------------------------------------------------------------------
+struct comp_entry { int bx0, by0, bw, bh; long long a_off; double kb, kg, kr, tau_one, c_scale; };
+
+__global__ void __launch_bounds__(RR_TILE_W * RR_TILE_H) k_composite(rr_frame_bufs b, rr_cam_dev cam, int tiles_x, int tiles_y) {
+    __shared__ comp_entry list[256];
+    __shared__ int s_count;
+    __shared__ int warp_cnt[8];
+    __shared__ double red[8];
+    const int f = blockIdx.z;
+    const int W = cam.W, H = cam.H;
+    const int tx0 = blockIdx.x * RR_TILE_W, ty0 = blockIdx.y * RR_TILE_H;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int x = tx0 + (tid % RR_TILE_W), y = ty0 + (tid / RR_TILE_W);
+    const bool inside = x < W && y < H;
+    const size_t npix = (size_t)W * H, pix = (size_t)y * W + x;
+    double vb = 0, vg = 0, vr = 0, mask = 0;
+    if (inside) {
+        vb = b.rainy[((size_t)f * 3 + 0) * npix + pix];
+        vg = b.rainy[((size_t)f * 3 + 1) * npix + pix];
+        vr = b.rainy[((size_t)f * 3 + 2) * npix + pix];
+    }
+    const int s0 = b.offsets[f], s1 = b.offsets[f + 1];
+    const double exposure = cam.exposure_blend;
+    for (int base = s0; base < s1; base += 256) {
+        int s = base + tid;
+        bool hit = false;
+        const rr_plan *pp = b.plans + (s < s1 ? s : s0);
+        int pbx0 = 0, pby0 = 0, pbw = 0, pbh = 0;
+        if (s < s1) {
+            pbx0 = pp->bx0; pby0 = pp->by0; pbw = pp->bw; pbh = pp->bh;
+            hit = pp->valid && pbw > 0 && pbh > 0 && pbx0 < tx0 + RR_TILE_W && pbx0 + pbw > tx0 &&
+                  pby0 < ty0 + RR_TILE_H && pby0 + pbh > ty0;
+        }
+        unsigned bal = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) warp_cnt[warp] = __popc(bal);
+        __syncthreads();
+        int pre = 0;
+        for (int k = 0; k < warp; k++) pre += warp_cnt[k];
+        if (hit) {
+            int slot = pre + __popc(bal & ((1u << lane) - 1));
+            comp_entry e;
+            e.bx0 = pbx0; e.by0 = pby0; e.bw = pbw; e.bh = pbh; e.a_off = pp->a_off;
+            e.kb = pp->kb; e.kg = pp->kg; e.kr = pp->kr; e.tau_one = pp->a_scale; e.c_scale = pp->c_scale;
+            list[slot] = e;
+        }
+        if (tid == 0) { int c = 0; for (int k = 0; k < 8; k++) c += warp_cnt[k]; s_count = c; }
+        __syncthreads();
+        int cnt = s_count;
+        if (inside) {
+            for (int k = 0; k < cnt; k++) {
+                const comp_entry &e = list[k];
+                int lx = x - e.bx0, ly = y - e.by0;
+                if (lx >= 0 && lx < e.bw && ly >= 0 && ly < e.bh) {
+                    double a = b.arena[e.a_off + (size_t)ly * e.bw + lx];
+                    double keep = 1. - ((a * e.tau_one) / exposure);                 // bad_weather.py:443
+                    double nb = (keep * vb) + (e.kb * a) * e.c_scale;
+                    double ng = (keep * vg) + (e.kg * a) * e.c_scale;
+                    double nr = (keep * vr) + (e.kr * a) * e.c_scale;
+                    vb = nb < 0 ? 0 : (nb > 1 ? 1 : nb);                             // :446
+                    vg = ng < 0 ? 0 : (ng > 1 ? 1 : ng);
+                    vr = nr < 0 ? 0 : (nr > 1 ? 1 : nr);
+                    mask += a;                                                       // :450
+                }
+            }
+        }
+        __syncthreads();
+    }
+    double part = 0;
+    if (inside) {
+        b.rainy[((size_t)f * 3 + 0) * npix + pix] = vb;
+        b.rainy[((size_t)f * 3 + 1) * npix + pix] = vg;
+        b.rainy[((size_t)f * 3 + 2) * npix + pix] = vr;
+        if (b.out_mask) b.out_mask[(size_t)f * npix + pix] = (float)mask;
+        part = (vb + vg) + vr;
+    }
+    part = warp_sum(part);
+    if (lane == 0) red[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0;
+        for (int k = 0; k < 8; k++) t += red[k];
+        b.tile_sum[(size_t)f * tiles_x * tiles_y + (size_t)blockIdx.y * tiles_x + blockIdx.x] = t;
+    }
+}
+
+__global__ void k_frame_mean(rr_frame_bufs b, int n_tiles, double npix3) {
+    int f = blockIdx.x;
+    __shared__ double sh[256];
+    double s = 0;
+    for (int i = threadIdx.x; i < n_tiles; i += 256) s += b.tile_sum[(size_t)f * n_tiles + i];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+    if (threadIdx.x == 0) {
+        double mean_rainy = sh[0] / npix3;                                          // generator.py:461
+        unsigned long long sb = b.chan_sum[f * 4] + b.chan_sum[f * 4 + 1] + b.chan_sum[f * 4 + 2];
+        double mean_bg = ((double)sb / 255.0) / npix3;                              // :462
+        b.frame_mean[f] = mean_rainy - mean_bg;                                     // :463
+    }
+}
+
+cudaError_t rr_launch_composite(const rr_frame_bufs &b, const rr_cam_dev &cam, int F, cudaStream_t st) {
+    int tiles_x = (cam.W + RR_TILE_W - 1) / RR_TILE_W, tiles_y = (cam.H + RR_TILE_H - 1) / RR_TILE_H;
+    dim3 grid(tiles_x, tiles_y, F);
+    k_composite<<<grid, RR_TILE_W * RR_TILE_H, 0, st>>>(b, cam, tiles_x, tiles_y);
+    k_frame_mean<<<F, 256, 0, st>>>(b, tiles_x * tiles_y, 3.0 * cam.W * cam.H);
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// epilogue: mean shift, float32 / uint8 outputs  (generator.py:460-466)
+// ------------------------------------------------------------------------------------------
+__global__ void k_epilogue(rr_frame_bufs b, int npix, int F) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)F * npix) return;
+    int f = (int)(i / npix);
+    size_t pix = i - (size_t)f * npix;
+    double d = b.frame_mean[f];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        double v = b.rainy[((size_t)f * 3 + c) * npix + pix] - d;                   // :464
+        if (b.out_bgr) b.out_bgr[i * 3 + c] = (float)v;
+        if (b.out_u8) {
+            double cl = v < 0 ? 0 : (v > 1 ? 1 : v);
+            b.out_u8[i * 3 + c] = (uint8_t)(cl * 255);                              // plt.imsave float -> uint8
+        }
+    }
+}
+
+cudaError_t rr_launch_epilogue(const rr_frame_bufs &b, int F, int W, int H, cudaStream_t st) {
+    size_t n = (size_t)F * W * H;
+    k_epilogue<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b, W * H, F);
+    return cudaGetLastError();
+}
+
+cudaError_t rr_launch_env_prefix_only(const rr_frame_bufs &b, const rr_static_tabs &t, int F, int H, int W_env, cudaStream_t st) {
+    dim3 g3(H, F);
+    k_env_prefix<<<g3, 256, 0, st>>>(b.env8, t.omega, b.pref, b.rowtot, H, W_env);
+    k_ambient<<<F, 32, 0, st>>>(b.rowtot, b.ambient, H);
+    return cudaGetLastError();
+}

@@ -1,0 +1,78 @@
+// Kernel launch wrappers of the rain-rendering hot path (sm_100a).  See DESIGN.md for the
+// data layout; every wrapper launches on the given stream and returns the CUDA error state.
+#pragma once
+#include <cuda_runtime.h>
+#include "rr_streak_geom.h"
+
+struct rr_frame_bufs {
+    // inputs (device)
+    const uint8_t *bgr;        // [F][H][W][3]
+    const float *depth;        // [F][H][W]
+    const rr_streak_rec *streaks;
+    const int32_t *offsets;    // [F+1] device copy
+    // per-frame intermediates
+    unsigned long long *chan_sum;  // [F][4]  sum of uint8 per channel (B,G,R), [3] unused
+    double *rainy;             // [F][3][H][W] planar BGR float64
+    uint8_t *bg8;              // [F][H][W][3] floor(rainy*255)
+    float *fblur;              // [F][H][W] blurred extinction (debug / stage test)
+    uint8_t *env_fill;         // [F][H][W_env][3] gathered cylindrical map
+    uint8_t *env8;             // [F][H][W_env][3] final environment map
+    double *pref;              // [F][3][H][W_env+1] row prefix sums of omega*(x, y, Y)
+    double *rowtot;            // [F][H] row totals of omega*Y
+    double *ambient;           // [F] sum over the map of omega*Y
+    rr_plan *plans;            // [n_streaks]
+    long long *scan;           // [n_streaks+1][4] exclusive prefix: g elems, a elems, raster chunks, blur chunks
+    double *arena;             // patch arena
+    long long arena_cap;       // elements
+    int *err_flag;             // device error flag (arena overflow)
+    double *tile_sum;          // [F][n_tiles] partial sums of the composited image
+    double *frame_mean;        // [F] mean(rainy_bg) - mean(bg)
+    // outputs (device)
+    float *out_bgr;            // [F][H][W][3]
+    float *out_mask;           // [F][H][W]
+    uint8_t *out_u8;           // [F][H][W][3]
+};
+
+struct rr_static_tabs {
+    const int32_t *env_src;    // [H][W_env]
+    const uint8_t *env_written;// [H][W_env]
+    const double *omega;       // [H][W_env]
+    const double *omega_pref;  // [H][W_env+1]
+    const double *omega_total; // [1] numpy-order total
+    const uint8_t *db;         // concatenated textures
+    const int32_t *tex_off;    // [n_tex]
+    const int32_t *tex_h;      // [n_tex]
+};
+
+struct rr_fog_consts {
+    float neg_beta32;          // float32(-beta_ext)
+    double irr_scale_num;      // 4 * N^2
+    double irr_den;            // exposure_time * gain * pi
+    double beta_hg;
+};
+
+#define RR_RASTER_CHUNK 128
+#define RR_BLUR_CHUNK 256
+#define RR_TILE_W 32
+#define RR_TILE_H 8
+
+cudaError_t rr_upload_constants();
+// init-time tables
+cudaError_t rr_launch_env_tables(int W, int H, int focal_px, int cyl_w, int min_x, int W_env, int32_t *env_src,
+                                 uint8_t *env_written, int32_t *cyl_first /* [H][cyl_w] scratch */, cudaStream_t st);
+cudaError_t rr_launch_omega(int H_env, int W_env, double *omega, double *omega_pref, double *omega_total, cudaStream_t st);
+// per batch
+cudaError_t rr_launch_stats(const rr_frame_bufs &b, int F, int W, int H, cudaStream_t st);
+cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, cudaStream_t st);
+cudaError_t rr_launch_env(const rr_frame_bufs &b, const rr_static_tabs &t, int F, int W, int H, int W_env, cudaStream_t st);
+cudaError_t rr_launch_setup(const rr_frame_bufs &b, const rr_static_tabs &t, const rr_cam_dev &cam, int F, int n_streaks,
+                            cudaStream_t st);
+cudaError_t rr_launch_scan(const rr_frame_bufs &b, int n_streaks, cudaStream_t st);
+cudaError_t rr_launch_raster(const rr_frame_bufs &b, const rr_static_tabs &t, const rr_cam_dev &cam, int n_streaks, int n_sm,
+                             cudaStream_t st);
+cudaError_t rr_launch_blur(const rr_frame_bufs &b, int n_streaks, int n_sm, cudaStream_t st);
+cudaError_t rr_launch_composite(const rr_frame_bufs &b, const rr_cam_dev &cam, int F, cudaStream_t st);
+cudaError_t rr_launch_epilogue(const rr_frame_bufs &b, int F, int W, int H, cudaStream_t st);
+// stage helpers
+cudaError_t rr_launch_env_prefix_only(const rr_frame_bufs &b, const rr_static_tabs &t, int F, int H, int W_env, cudaStream_t st);
+cudaError_t rr_launch_planar_to_bg8(const double *planar, uint8_t *bg8, int F, int W, int H, cudaStream_t st);

@@ -1,0 +1,117 @@
+"""Host-side streak records: the particles-XML loader, the in-frame filter and the per-frame
+record assembly that feeds ``rr_render_frames`` (include/rain_b200.h: ``rr_streak_rec``).
+
+Mirrors, on the host, the parts of the reference that are bookkeeping rather than rendering:
+  * DBManager.load_streaks_from_xml      common/bad_weather.py:148-248
+  * DBManager.classify_drop              common/bad_weather.py:99-106
+  * the in-frame streak filter           common/generator.py:413-420
+  * DBManager.take_drop_texture buckets  common/bad_weather.py:250-265
+  * the wind-noise write-back into the shared Streak objects   common/generator.py:149-161
+The two NumPy RNG draws per streak are reproduced by the library's own MT19937 mirror
+(``rr_host_draw_randoms`` in csrc/rr_host.cpp) so that no Python-level RNG call sits on the
+per-frame path.
+"""
+from __future__ import annotations
+
+from xml.etree.ElementTree import parse
+
+import numpy as np
+
+BIG, MEDIUM, SMALL = 0, 1, 2
+
+STREAK_DTYPE = np.dtype([
+    ("wp1", "<f8", 3), ("wp2", "<f8", 3), ("iw1", "<f8"), ("iw2", "<f8"), ("noise_deg", "<f8"), ("ratio", "<f8"),
+    ("ip1", "<i4", 2), ("ip2", "<i4", 2), ("ip1m", "<i4", 2), ("ip2m", "<i4", 2),
+    ("max_width", "<i4"), ("length", "<i4"), ("pid", "<i4"), ("type", "u1"), ("tex_idx", "u1"), ("pad", "u1", 2),
+], align=False)
+assert STREAK_DTYPE.itemsize == 128
+
+
+def _vec(attr: str):
+    return [float(t) for t in attr[1:-1].split(";")]
+
+
+def load_streaks_from_xml(path: str, render_scale: int, W: int, H: int):
+    """-> list (one entry per simulator frame, XML order) of STREAK_DTYPE arrays in XML order,
+    already restricted to ``max_width >= 1 and length >= 1`` (bad_weather.py:238).  A later
+    duplicate ``pid`` replaces the earlier entry but keeps its position, like the reference's
+    dict ``update``."""
+    frames = []
+    for frame in parse(path).getroot():
+        rows = {}
+        for drop in frame:
+            a = drop.attrib
+            rows[int(a["pid"])] = (_vec(a["wp1"]), _vec(a["wp2"]), _vec(a["ip1"]), _vec(a["ip2"]),
+                                   float(a["iw1"]), float(a["iw2"]), int(a["pid"]))
+        n = len(rows)
+        rec = np.zeros(n, dtype=STREAK_DTYPE)
+        if n:
+            vals = list(rows.values())
+            wp1 = np.array([v[0] for v in vals], dtype=np.float64)
+            wp2 = np.array([v[1] for v in vals], dtype=np.float64)
+            ip1 = np.array([v[2] for v in vals], dtype=np.float64) / render_scale        # :208-209
+            ip2 = np.array([v[3] for v in vals], dtype=np.float64) / render_scale
+            iw1 = np.array([v[4] for v in vals], dtype=np.float64) / render_scale        # :210-211
+            iw2 = np.array([v[5] for v in vals], dtype=np.float64) / render_scale
+            ip1[:, 1] = H - ip1[:, 1]                                                    # :221-222
+            ip2[:, 1] = H - ip2[:, 1]
+            wp1[:, 2] *= -1                                                              # :223-224
+            wp2[:, 2] *= -1
+            diff = np.abs(ip1 - ip2)
+            max_width = np.maximum(iw1, iw2).astype(np.int64)                            # :226 int() truncation
+            with np.errstate(divide="ignore", invalid="ignore"):
+                nrm = np.sqrt(diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1])
+                cos_theta = 0 * (diff[:, 0] / nrm) + -1 * (-(diff[:, 1] / nrm))          # :228-231
+                ratio = max_width / (diff[:, 1] / cos_theta)                             # :232-233
+            ip1r = np.round(ip1).astype(np.int64)                                        # :234-235 (half-even)
+            ip2r = np.round(ip2).astype(np.int64)
+            d = (ip1r - ip2r).astype(np.float64)
+            length = np.ceil(np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1])).astype(np.int64)   # :236
+            rec["wp1"], rec["wp2"], rec["iw1"], rec["iw2"] = wp1, wp2, iw1, iw2
+            rec["ratio"] = ratio
+            rec["ip1"], rec["ip2"], rec["ip1m"], rec["ip2m"] = ip1r, ip2r, ip1r, ip2r
+            rec["max_width"], rec["length"] = max_width, length
+            rec["pid"] = np.array([v[6] for v in vals])
+            rec["type"] = np.where(max_width >= 4, BIG, np.where(max_width > 1, MEDIUM, SMALL))   # :99-106
+            rec = rec[(max_width >= 1) & (length >= 1)]
+        frames.append(rec)
+    return frames
+
+
+def in_frame(rec: np.ndarray, W: int, H: int) -> np.ndarray:
+    """Boolean mask of generator.py:413-420 (uses the *current*, possibly wind-mutated, positions)."""
+    m = max(H, W)
+    s, e = rec["ip1m"], rec["ip2m"]
+    ok_w = (1 <= rec["max_width"]) & (rec["max_width"] < m)
+    ok_l = (1 <= rec["length"]) & (rec["length"] < m)
+    ins = (0 <= s[:, 0]) & (s[:, 0] < W) & (0 <= s[:, 1]) & (s[:, 1] < H)
+    ine = (0 <= e[:, 0]) & (e[:, 0] < W) & (0 <= e[:, 1]) & (e[:, 1] < H)
+    return ok_w & ok_l & (ins | ine)
+
+
+def texture_buckets(ratio: np.ndarray, db_ratios: np.ndarray) -> np.ndarray:
+    """First i with ratio < db_ratios[i], else 4 (bad_weather.py:251-265)."""
+    return np.searchsorted(np.asarray(db_ratios[:4], dtype=np.float64), ratio, side="right").astype(np.int32)
+
+
+def apply_wind_noise(rec: np.ndarray, noise_deg: np.ndarray):
+    """generator.py:149-161 for the non-Big streaks of one frame: rotates the (already rounded)
+    end points about their mid point by ``noise`` degrees and writes them back into integer
+    storage (truncation).  ``ip1``/``ip2`` keep the pre-rotation values (the streak angle is taken
+    from them, generator.py:138-144); ``ip1m``/``ip2m`` receive the result.  Returns rec."""
+    rec["ip1"] = rec["ip1m"]
+    rec["ip2"] = rec["ip2m"]
+    sel = rec["type"] != BIG
+    if not sel.any():
+        return rec
+    s = rec["ip1m"][sel].astype(np.float64)
+    e = rec["ip2m"][sel].astype(np.float64)
+    nz = noise_deg[sel]
+    nx, ny = np.cos(np.deg2rad(nz)), np.sin(np.deg2rad(nz))
+    mx = (e[:, 0] + s[:, 0]) / 2
+    my = (e[:, 1] + s[:, 1]) / 2
+    s_new = np.stack([(s[:, 0] - mx) * nx - (s[:, 1] - my) * ny + mx, (s[:, 0] - mx) * ny + (s[:, 1] - my) * nx + my], 1)
+    e_new = np.stack([(e[:, 0] - mx) * nx - (e[:, 1] - my) * ny + mx, (e[:, 0] - mx) * ny + (e[:, 1] - my) * nx + my], 1)
+    rec["ip1m"][sel] = s_new.astype(np.int64)       # assignment into an int array truncates toward zero
+    rec["ip2m"][sel] = e_new.astype(np.int64)
+    return rec
