@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the rain-rendering hot path (BASELINE.json metric: rainy frames/s at 1242x375,
+25 mm/h, HBM GB/s vs roofline).
+
+  python bench.py --gpus N --steps K --warmup W            # the CUDA path (this repo)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle port)
+
+A step = one pass of the hot path over one batch of 64 synthetic KITTI-sized frames
+(BASELINE config C2).  ``value`` is measured with the batch already resident in HBM,
+``e2e`` through rr_render_frames with pinned HOST buffers (H2D and D2H inside the timed region).
+One rank per GPU (torchrun), frames sharded, no data-path collective; the only collective is the
+NCCL broadcast of the streak DB at init.  Rank 0 prints ONE JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from rain_rendering_b200 import synth  # noqa: E402
+from rain_rendering_b200.streaks import STREAK_DTYPE  # noqa: E402
+
+WORKLOAD = "C2"
+BATCH = 64
+METRIC = "rainy frames/sec at 1242x375, 25mm/hr"
+REC_BYTES = STREAK_DTYPE.itemsize
+
+
+def algorithmic_bytes_per_frame(W, H, n_streaks):
+    """compulsory traffic at the C-ABI boundary of one frame: uint8 BGR in, float32
+    depth in, float32 BGR + float32 mask + uint8 BGR out, streak records in."""
+    return 3 * W * H + 4 * W * H + (12 + 4 + 3) * W * H + REC_BYTES * n_streaks
+
+
+def build_batch(wl, rank, batch):
+    """Synthetic batch of one rank: frames + records (host arrays)."""
+    from rain_rendering_b200 import api, streaks as S
+    W, H = wl["W"], wl["H"]
+    cam = synth.CAMERAS[wl["dataset"]]
+    db = synth.make_streak_db(0)
+    frames = [synth.make_frame(W, H, 100000 * rank + i) for i in range(batch)]
+    bgr = np.stack([f[0] for f in frames])
+    depth = np.stack([f[1] for f in frames])
+    parts = synth.make_particles(W, H, batch, wl["n_xml"], cam["cam_exposure"], seed=1000 + rank)
+    with tempfile.TemporaryDirectory() as d:
+        xml = os.path.join(d, "sim_camera0.xml")
+        synth.write_particles_xml(parts, xml, cam["cam_exposure"])
+        sim = S.load_streaks_from_xml(xml, 1, W, H)
+    recs, offs = [], [0]
+    for i in range(batch):
+        r = api.assemble_frame_records(sim[i], W, H, db.ratios, i, 0.0, 0.0)
+        recs.append(r)
+        offs.append(offs[-1] + len(r))
+    return db, bgr, depth, np.concatenate(recs), np.array(offs, np.int32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index):
+        self.path = tempfile.mktemp(suffix=".csv")
+        self.gpu = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                p = [t.strip() for t in line.split(",")]
+                if len(p) < 8:
+                    continue
+                try:
+                    sm.append(float(p[1])); mx.append(float(p[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, p[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        except Exception:
+            pass
+        finally:
+            try:
+                os.unlink(self.path)
+            except OSError:
+                pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline: the oracle port on the host cores (test infrastructure used as the checker/baseline)
+# ----------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    wl_name, frame_idx = args
+    import cv2
+    cv2.setNumThreads(1)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle import rain_oracle as ro
+    wl = synth.WORKLOADS[wl_name]
+    W, H = wl["W"], wl["H"]
+    cam_s = synth.CAMERAS[wl["dataset"]]
+    cam = ro.Camera(W=W, H=H, focal_mm=cam_s["cam_focal"], f_number=cam_s["cam_f_number"], exposure_ms=cam_s["cam_exposure"],
+                    gain=cam_s["cam_gain"], fallrate=wl["fallrate"])
+    db = synth.make_streak_db(0)
+    bgr, depth = synth.make_frame(W, H, frame_idx)
+    parts = synth.make_particles(W, H, 1, wl["n_xml"], cam_s["cam_exposure"], seed=1000 + frame_idx)
+    with tempfile.TemporaryDirectory() as d:
+        xml = os.path.join(d, "sim_camera0.xml")
+        synth.write_particles_xml(parts, xml, cam_s["cam_exposure"])
+        streaks = ro.load_streaks_from_xml(xml, 1, W, H)[0]
+    tables = ro.build_env_tables(W, H, cam.focal_m)
+    omega = ro.solid_angles(H, tables.W_env)
+    t0 = time.perf_counter()
+    r = ro.render_frame(bgr, depth, streaks, db.textures, db.ratios, cam, frame_idx, tables, omega, f32_mode="native")
+    return time.perf_counter() - t0, r.n_streaks
+
+
+def cpu_steps(steps, warmup, n_workers):
+    """Each step: n_workers processes render one C2 frame each (the reference's own scale-out is
+    process-level over disjoint frames, main_threaded.py:109-176).  Returns per-step wall seconds."""
+    import multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    times, streaks = [], []
+    with ctx.Pool(n_workers) as pool:
+        for s in range(warmup + steps):
+            t0 = time.perf_counter()
+            res = pool.map(_cpu_worker, [(WORKLOAD, 7000 + s * n_workers + k) for k in range(n_workers)])
+            dt = time.perf_counter() - t0
+            if s >= warmup:
+                times.append(dt)
+                streaks += [r[1] for r in res]
+    return times, streaks
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = host_cores()
+    workers = max(1, min(cores, 64))
+    wl = synth.WORKLOADS[WORKLOAD]
+    times, streaks = cpu_steps(args.steps, args.warmup, workers)
+    total = float(np.sum(times))
+    fps = workers * len(times) / total
+    sample = "%d processes x 1 frame per step (%dx%d, %d mm/h, ~%d streaks/frame), oracle port of the reference algorithm, " \
+             "cv2 threads 1 per process, tables/solid angles precomputed" % (workers, wl["W"], wl["H"], wl["fallrate"], int(np.mean(streaks)))
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2 KITTI 1242x375 25mm/hr", "frames_per_step": workers, "streaks_per_frame": float(np.mean(streaks))},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": workers, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+# the CUDA path
+# ----------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from rain_rendering_b200 import api, dist as rdist
+    rank, world, local = rdist.init_process_group("nccl")
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
+    torch.cuda.set_device(local)
+    wl = synth.WORKLOADS[WORKLOAD]
+    W, H = wl["W"], wl["H"]
+    cam = synth.CAMERAS[wl["dataset"]]
+    batch = args.batch
+    db, bgr, depth, recs, offs = build_batch(wl, rank, batch)
+    n_streaks = int(offs[-1])
+    ctx = api.RainContext(local)
+    rdist.broadcast_streak_db(ctx, db.textures if rank == 0 else None, src=0)     # the one collective
+    if world == 1:
+        pass
+    ctx.set_camera(W, H, cam["cam_focal"], cam["cam_f_number"], cam["cam_exposure"], cam["cam_gain"], wl["fallrate"], 1.0, batch)
+    lib, C = ctx.lib, __import__("ctypes")
+    stream_ptr = C.c_void_p()
+    lib.rr_stream(ctx.h, C.byref(stream_ptr))
+    stream = torch.cuda.ExternalStream(stream_ptr.value, device=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident arm ----------------------------------------------------------------
+    dev = torch.device("cuda", local)
+    d_bgr = torch.from_numpy(bgr).to(dev)
+    d_depth = torch.from_numpy(depth).to(dev)
+    d_recs = torch.from_numpy(recs.view(np.uint8).reshape(-1)).to(dev)
+    d_out_bgr = torch.empty((batch, H, W, 3), dtype=torch.float32, device=dev)
+    d_out_mask = torch.empty((batch, H, W), dtype=torch.float32, device=dev)
+    d_out_u8 = torch.empty((batch, H, W, 3), dtype=torch.uint8, device=dev)
+    offs_c = np.ascontiguousarray(offs)
+
+    def step_device(sync=0):
+        from rain_rendering_b200 import _lib
+        _lib.check(lib.rr_render_frames_device(ctx.h, batch, d_bgr.data_ptr(), d_depth.data_ptr(), d_recs.data_ptr(), _lib.ptr(offs_c),
+                                               d_out_bgr.data_ptr(), d_out_mask.data_ptr(), d_out_u8.data_ptr(), sync), "rr_render_frames_device")
+
+    for _ in range(max(args.warmup, 3)):
+        step_device(1)
+    stage_ms = {k: 0.0 for k in ctx.timings()}
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_device(1)                      # synchronous per step: also yields the per-stage event timings
+        for k, v in ctx.timings().items():
+            stage_ms[k] += v
+    e1.record(stream)
+    barrier()
+    ms_dev = e0.elapsed_time(e1)
+    launches = ctx.kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- end-to-end arm: pinned host buffers through rr_render_frames --------------------------
+    p_bgr = api.PinnedBuffer(bgr.shape, np.uint8); p_bgr.array[...] = bgr
+    p_depth = api.PinnedBuffer(depth.shape, np.float32); p_depth.array[...] = depth
+    p_recs = api.PinnedBuffer(recs.shape, STREAK_DTYPE); p_recs.array[...] = recs
+    p_out_bgr = api.PinnedBuffer((batch, H, W, 3), np.float32)
+    p_out_mask = api.PinnedBuffer((batch, H, W), np.float32)
+    p_out_u8 = api.PinnedBuffer((batch, H, W, 3), np.uint8)
+
+    def step_e2e():
+        ctx.render_frames(p_bgr.array, p_depth.array, p_recs.array, offs_c, p_out_bgr.array, p_out_mask.array, p_out_u8.array)
+
+    for _ in range(max(args.warmup, 3)):
+        step_e2e()
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record(stream)
+    for _ in range(args.steps):
+        step_e2e()
+    f1.record(stream)
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    h2d = int(bgr.nbytes + depth.nbytes + recs.nbytes + offs_c.nbytes)
+    d2h = int(p_out_bgr.array.nbytes + p_out_mask.array.nbytes + p_out_u8.array.nbytes)
+    checksum = float(p_out_mask.array.sum())
+    # ---- max over ranks ------------------------------------------------------------------------
+    t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev, ms_e2e = float(t[0]), float(t[1])
+    total_frames = batch * world * args.steps
+    if rank == 0:
+        value = total_frames / (ms_dev / 1000.0)
+        e2e = total_frames / (ms_e2e / 1000.0)
+        n_per_frame = n_streaks / batch
+        balg = algorithmic_bytes_per_frame(W, H, n_per_frame)
+        # dominant kernel (stage) of the device-resident step, timed live with CUDA events on the library's stream
+        kern = {k: v / args.steps for k, v in stage_ms.items() if k not in ("h2d", "d2h", "total")}
+        dom = max(kern, key=kern.get)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = balg * batch / (kern[dom] / 1000.0) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(dom)
+        except Exception:
+            pass
+        line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "C2 KITTI 1242x375 25mm/hr", "batch_frames_per_gpu": batch, "streaks_per_frame": n_per_frame,
+                           "l2": "inputs larger than L2 (%.0f MB per step per GPU, no flush)" % ((h2d) / 1e6),
+                           "parallelism": "frames sharded x%d, no data-path collective" % world},
+                "clocks": clocks, "gpu_launches": launches,
+                "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                        "checksum_mask": checksum},
+                "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "traffic": traffic, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
+                             "algorithmic_bytes_per_frame": balg, "whole_step_frac": (balg * batch / (ms_dev / args.steps / 1000.0) / 1e9) / peak},
+                "stage_ms": kern}
+        if world == 1 and not args.no_cpu_baseline:
+            workers = max(1, min(host_cores(), 32))
+            times, streaks = cpu_steps(1, 0, workers)
+            fps = workers / times[0]
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": workers, "kind": "port",
+                                    "sample": "%d processes x 1 frame of the same workload (~%d streaks/frame), oracle port, %.1f s wall" % (
+                                        workers, int(np.mean(streaks)), times[0])}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -62,11 +62,11 @@ def make_frame(W: int, H: int, seed: int):
     img = _bilinear_upsample(small, H, W)
     sky = np.linspace(70.0, -25.0, H)[:, None, None]
     img = np.clip(0.8 * img + sky + rng.uniform(-6, 6, size=(H, W, 3)), 0, 255)
-    bgr = img.astype(np.uint8)
+    bgr = np.ascontiguousarray(img.astype(np.uint8))
     y = np.arange(H, dtype=np.float64)[:, None]
     depth = np.clip(80.0 * (1.0 - y / H) + 2.0 + rng.uniform(0, 2, size=(H, W)), 1.0, 200.0)
     depth_u16 = np.round(depth * 256.0).astype(np.uint16)
-    return bgr, (depth_u16.astype(np.float32) / np.float32(256.0))
+    return bgr, np.ascontiguousarray(depth_u16.astype(np.float32) / np.float32(256.0))
 
 
 @dataclass

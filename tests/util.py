@@ -79,3 +79,31 @@ def ulp_diff_f32(a, b):
     a = np.where(a < 0, -(a & 0x7FFFFFFF), a)
     b = np.where(b < 0, -(b & 0x7FFFFFFF), b)
     return np.abs(a - b)
+
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def golden_scenario(name: str):
+    """Scenario rebuilt from a committed fixture (inputs + outputs of the live reference,
+    see oracle/make_golden.py).  Returns (scenario, npz)."""
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    W, H, nf = int(g["W"]), int(g["H"]), int(g["n_frames"])
+    sc = Scenario.__new__(Scenario)
+    sc.W, sc.H, sc.n_frames = W, H, nf
+    cam = synth.CAMERAS["customdb"]
+    sc.cam = ro.Camera(W=W, H=H, focal_mm=cam["cam_focal"], f_number=cam["cam_f_number"], exposure_ms=cam["cam_exposure"],
+                       gain=cam["cam_gain"], fallrate=int(g["fallrate"]), opacity_attenuation=float(g["opacity"]),
+                       noise_scale=float(g["noise_scale"]), noise_std=float(g["noise_std"]))
+    sc.db = synth.make_streak_db(int(g["db_seed"]))
+    sc.bgr = np.ascontiguousarray(g["bgr"])
+    sc.depth = np.ascontiguousarray(g["depth_u16"].astype(np.float32) / 256.)
+    with tempfile.TemporaryDirectory() as d:
+        xml = os.path.join(d, "sim_camera0.xml")
+        with open(xml, "wb") as f:
+            f.write(g["xml"].tobytes())
+        sc.oracle_frames = ro.load_streaks_from_xml(xml, 1, W, H)
+        sc.sim_frames = S.load_streaks_from_xml(xml, 1, W, H)
+    sc._tables = None
+    sc._omega = None
+    return sc, g
