@@ -64,54 +64,50 @@ def build_batch(wl, rank, batch):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    """SM clocks and throttle reasons sampled through NVML on a thread DURING the timed region."""
 
     def __init__(self, gpu_index):
-        self.path = tempfile.mktemp(suffix=".csv")
         self.gpu = gpu_index
-        self.proc = None
+        self.sm, self.reasons, self.max_mhz = [], set(), None
+        self._stop = None
+        self._thr = None
 
     def start(self):
+        import threading
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = int(vis.split(",")[self.gpu]) if vis and vis.split(",")[self.gpu].isdigit() else self.gpu
+            h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
         except Exception:
-            self.proc = None
+            return
+        names = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+        self._stop = threading.Event()
+
+        def loop():
+            while not self._stop.is_set():
+                try:
+                    self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                    r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for n, bit in names.items():
+                        if r & bit:
+                            self.reasons.add(n)
+                except Exception:
+                    pass
+                self._stop.wait(0.02)
+
+        self._thr = threading.Thread(target=loop, daemon=True)
+        self._thr.start()
 
     def stop(self):
-        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
-        if self.proc is None:
-            return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        try:
-            for line in open(self.path):
-                p = [t.strip() for t in line.split(",")]
-                if len(p) < 8:
-                    continue
-                try:
-                    sm.append(float(p[1])); mx.append(float(p[2]))
-                except ValueError:
-                    continue
-                for n, v in zip(names, p[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-        except Exception:
-            pass
-        finally:
-            try:
-                os.unlink(self.path)
-            except OSError:
-                pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        if self._thr is not None:
+            self._stop.set()
+            self._thr.join(timeout=2)
+        out = dict(sm_mhz=None, sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons), samples=len(self.sm))
+        if self.sm:
+            out["sm_mhz"] = float(np.median(self.sm))
         return out
 
 
@@ -257,12 +253,13 @@ def run_gpu(args):
     p_bgr = api.PinnedBuffer(bgr.shape, np.uint8); p_bgr.array[...] = bgr
     p_depth = api.PinnedBuffer(depth.shape, np.float32); p_depth.array[...] = depth
     p_recs = api.PinnedBuffer(recs.shape, STREAK_DTYPE); p_recs.array[...] = recs
-    p_out_bgr = api.PinnedBuffer((batch, H, W, 3), np.float32)
     p_out_mask = api.PinnedBuffer((batch, H, W), np.float32)
     p_out_u8 = api.PinnedBuffer((batch, H, W, 3), np.uint8)
 
     def step_e2e():
-        ctx.render_frames(p_bgr.array, p_depth.array, p_recs.array, offs_c, p_out_bgr.array, p_out_mask.array, p_out_u8.array)
+        # what Generator.run consumes per frame: the uint8 rainy image and the float rain mask
+        # (generator.py:466-467); the float32 image is a parity-test output and is not copied back
+        ctx.render_frames(p_bgr.array, p_depth.array, p_recs.array, offs_c, None, p_out_mask.array, p_out_u8.array, want=("mask", "u8"))
 
     for _ in range(max(args.warmup, 3)):
         step_e2e()
@@ -275,7 +272,7 @@ def run_gpu(args):
     barrier()
     ms_e2e = f0.elapsed_time(f1)
     h2d = int(bgr.nbytes + depth.nbytes + recs.nbytes + offs_c.nbytes)
-    d2h = int(p_out_bgr.array.nbytes + p_out_mask.array.nbytes + p_out_u8.array.nbytes)
+    d2h = int(p_out_mask.array.nbytes + p_out_u8.array.nbytes)
     checksum = float(p_out_mask.array.sum())
     # ---- max over ranks ------------------------------------------------------------------------
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
@@ -311,7 +308,8 @@ def run_gpu(args):
                            "parallelism": "frames sharded x%d, no data-path collective" % world},
                 "clocks": clocks, "gpu_launches": launches,
                 "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
-                        "checksum_mask": checksum},
+                        "checksum_mask": checksum,
+                        "outputs": "uint8 BGR image + float32 rain mask (what Generator.run saves)"},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
                              "algorithmic_bytes_per_frame": balg, "whole_step_frac": (balg * batch / (ms_dev / args.steps / 1000.0) / 1e9) / peak},

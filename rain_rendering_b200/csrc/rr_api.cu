@@ -233,7 +233,7 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
     CK(dev_alloc(c, &b.out_mask, F * np));
     CK(dev_alloc(c, &b.out_u8, F * np * 3));
     {
-        double mult = 10.0;
+        double mult = 6.0;
         const char *env = getenv("RR_ARENA_MULT");
         if (env) mult = atof(env);
         b.arena_cap = (long long)(mult * (double)(F * np));
@@ -309,16 +309,29 @@ static int finish_timings(rr_context *c) {
     return RR_OK;
 }
 
-static int check_flag(rr_context *c) {
+// -> RR_OK, or RR_ERR_CAPACITY after growing the arena to fit (the caller re-runs the batch)
+static int check_flag(rr_context *c, bool grow) {
     int flag = 0;
     CK(cudaMemcpyAsync(&flag, c->fb.err_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
-    if (flag) {
-        set_err("patch arena overflow (%lld float64 elements): streaks were dropped; raise RR_ARENA_MULT or lower the batch",
-                c->fb.arena_cap);
-        return RR_ERR_CAPACITY;
+    if (!flag) return RR_OK;
+    long long need = 0;
+    CK(cudaMemcpy(&need, c->fb.scan + (size_t)c->last_n_streaks * 6, sizeof(long long), cudaMemcpyDeviceToHost));
+    if (grow) {
+        long long cap = need + need / 4 + 4096;
+        // the old arena stays in c->owned (freed with the camera); allocate the larger one
+        double *na = nullptr;
+        cudaError_t e = cudaMalloc((void **)&na, (size_t)cap * sizeof(double));
+        if (e == cudaSuccess) {
+            for (auto &p : c->owned) if (p == (void *)c->fb.arena) { cudaFree(p); p = (void *)na; }
+            c->fb.arena = na; c->fb.arena_cap = cap;
+            set_err("patch arena grown to %lld float64 elements", cap);
+            return RR_ERR_CAPACITY;
+        }
+        cudaGetLastError();
     }
-    return RR_OK;
+    set_err("patch arena overflow: need %lld float64 elements, have %lld (RR_ARENA_MULT raises the initial size)", need, c->fb.arena_cap);
+    return RR_ERR_CAPACITY;
 }
 
 int rr_render_frames(rr_context *c, int n_frames, const uint8_t *bgr, const float *depth, const rr_streak_rec *streaks,
@@ -343,13 +356,17 @@ int rr_render_frames(rr_context *c, int n_frames, const uint8_t *bgr, const floa
     if (n_streaks) CK(cudaMemcpyAsync(c->d_streaks, streaks, (size_t)n_streaks * sizeof(rr_streak_rec), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->d_offsets, streak_offsets, (F + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     b.bgr = c->d_bgr; b.depth = c->d_depth; b.streaks = c->d_streaks; b.offsets = c->d_offsets;
-    r = run_pipeline(c, F, n_streaks, true);
-    if (r != RR_OK) return r;
-    if (out_bgr) CK(cudaMemcpyAsync(out_bgr, b.out_bgr, F * np * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (out_mask) CK(cudaMemcpyAsync(out_mask, b.out_mask, F * np * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (out_bgr_u8) CK(cudaMemcpyAsync(out_bgr_u8, b.out_u8, F * np * 3, cudaMemcpyDeviceToHost, st));
-    CK(cudaEventRecord(c->ev[RR_T_TOTAL], st));
-    r = check_flag(c);
+    for (int attempt = 0;; attempt++) {
+        r = run_pipeline(c, F, n_streaks, true);
+        if (r != RR_OK) return r;
+        if (out_bgr) CK(cudaMemcpyAsync(out_bgr, b.out_bgr, F * np * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (out_mask) CK(cudaMemcpyAsync(out_mask, b.out_mask, F * np * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (out_bgr_u8) CK(cudaMemcpyAsync(out_bgr_u8, b.out_u8, F * np * 3, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(c->ev[RR_T_TOTAL], st));
+        r = check_flag(c, attempt == 0);
+        if (r == RR_ERR_CAPACITY && attempt == 0 && c->fb.arena_cap > 0 && strstr(g_err, "grown")) continue;   // re-run once with the larger arena
+        break;
+    }
     finish_timings(c);
     return r;
 }
@@ -379,7 +396,19 @@ int rr_render_frames_device(rr_context *c, int n_frames, const uint8_t *d_bgr, c
     if (r != RR_OK) return r;
     CK(cudaEventRecord(c->ev[RR_T_TOTAL], st));
     if (sync) {
-        r = check_flag(c);
+        r = check_flag(c, true);
+        if (r == RR_ERR_CAPACITY && strstr(g_err, "grown")) {     // re-run once with the larger arena
+            b.bgr = d_bgr; b.depth = d_depth; b.streaks = d_streaks; b.offsets = c->d_offsets;
+            if (d_out_bgr) b.out_bgr = d_out_bgr;
+            if (d_out_mask) b.out_mask = d_out_mask;
+            if (d_out_bgr_u8) b.out_u8 = d_out_bgr_u8;
+            CK(cudaEventRecord(c->ev[RR_T_H2D], st));
+            r = run_pipeline(c, F, n_streaks, true);
+            b.out_bgr = b_saved.out_bgr; b.out_mask = b_saved.out_mask; b.out_u8 = b_saved.out_u8;
+            if (r != RR_OK) return r;
+            CK(cudaEventRecord(c->ev[RR_T_TOTAL], st));
+            r = check_flag(c, false);
+        }
         finish_timings(c);
     }
     return r;
@@ -511,7 +540,7 @@ int rr_synchronize(rr_context *c) {
     if (!c) { set_err("rr_synchronize: context is NULL"); return RR_ERR_ARG; }
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
-    int r = c->have_cam ? check_flag(c) : RR_OK;
+    int r = c->have_cam ? check_flag(c, false) : RR_OK;
     if (c->have_cam) finish_timings(c);
     return r;
 }

@@ -596,6 +596,15 @@ cudaError_t rr_launch_setup(const rr_frame_bufs &b, const rr_static_tabs &t, con
 //   scan[i*6 + 0..2]: element offsets of g (pre-blur patch), v (column-pass result), a (blurred alpha block)
 //   scan[i*6 + 3..5]: chunk prefix of the raster, column-pass and row-pass kernels
 // ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void blur_extents(const rr_plan &p, int *vx0, int *vw);
+// arena elements of one streak: g (pre-blur patch), v (column pass), a (visible blurred block)
+__device__ __forceinline__ void plan_sizes(const rr_plan &p, long long *g, long long *v, long long *a, int *vx0, int *vw) {
+    *g = *v = *a = 0; *vx0 = 0; *vw = 0;
+    if (p.valid && p.bw > 0 && p.bh > 0 && p.pw > 0 && p.ph > 0) {
+        blur_extents(p, vx0, vw);
+        *g = (long long)p.pw * p.ph; *v = (long long)(*vw) * p.bh; *a = (long long)p.bw * p.bh;
+    }
+}
 __device__ __forceinline__ void blur_extents(const rr_plan &p, int *vx0, int *vw) {
     // padded columns of the column-pass result that the visible block needs and that are non-zero
     int a = p.cropx - p.rx, e = p.cropx + p.bw + p.rx;
@@ -612,12 +621,8 @@ __global__ void __launch_bounds__(1024) k_scan(rr_frame_bufs b, int n) {
     int i0 = tid * per, i1 = i0 + per < n ? i0 + per : n;
     long long el = 0, c0 = 0, c1 = 0, c2 = 0;
     for (int i = i0; i < i1; i++) {
-        const rr_plan &p = b.plans[i];
-        long long g = 0, v = 0, a = 0;
-        if (p.valid && p.bw > 0 && p.bh > 0) {
-            int vx0, vw; blur_extents(p, &vx0, &vw);
-            g = (long long)p.pw * p.ph; v = (long long)vw * p.bh; a = (long long)p.bw * p.bh;
-        }
+        long long g, v, a; int vx0, vw;
+        plan_sizes(b.plans[i], &g, &v, &a, &vx0, &vw);
         el += g + v + a;
         c0 += (g + RR_RASTER_CHUNK - 1) / RR_RASTER_CHUNK;
         c1 += (v + RR_BLUR_CHUNK - 1) / RR_BLUR_CHUNK;
@@ -625,6 +630,7 @@ __global__ void __launch_bounds__(1024) k_scan(rr_frame_bufs b, int n) {
     }
     tot[tid][0] = el; tot[tid][1] = c0; tot[tid][2] = c1; tot[tid][3] = c2;
     __syncthreads();
+    __shared__ int overflow;
     if (tid == 0) {
         long long a0 = 0, a1 = 0, a2 = 0, a3 = 0;
         for (int t = 0; t < 1024; t++) {
@@ -632,19 +638,17 @@ __global__ void __launch_bounds__(1024) k_scan(rr_frame_bufs b, int n) {
             tot[t][0] = a0; tot[t][1] = a1; tot[t][2] = a2; tot[t][3] = a3;
             a0 += v0; a1 += v1; a2 += v2; a3 += v3;
         }
+        overflow = a0 > b.arena_cap;
+        if (overflow) { *b.err_flag = 1; a1 = a2 = a3 = 0; }    // nothing is rendered: the host grows the arena and re-runs
         b.scan[(size_t)n * 6 + 0] = a0; b.scan[(size_t)n * 6 + 3] = a1; b.scan[(size_t)n * 6 + 4] = a2; b.scan[(size_t)n * 6 + 5] = a3;
-        if (a0 > b.arena_cap) *b.err_flag = 1;
     }
     __syncthreads();
     el = tot[tid][0]; c0 = tot[tid][1]; c1 = tot[tid][2]; c2 = tot[tid][3];
     for (int i = i0; i < i1; i++) {
         rr_plan &p = b.plans[i];
-        long long g = 0, v = 0, a = 0;
-        if (p.valid && p.bw > 0 && p.bh > 0) {
-            int vx0, vw; blur_extents(p, &vx0, &vw);
-            g = (long long)p.pw * p.ph; v = (long long)vw * p.bh; a = (long long)p.bw * p.bh;
-            if (el + g + v + a > b.arena_cap) { g = v = a = 0; p.bw = p.bh = 0; p.valid = 0; }   // overflow: dropped, error flag set
-        }
+        long long g, v, a; int vx0, vw;
+        plan_sizes(p, &g, &v, &a, &vx0, &vw);
+        if (overflow) { p.valid = 0; p.bw = p.bh = 0; }
         long long *sc = b.scan + (size_t)i * 6;
         sc[0] = el; sc[1] = el + g; sc[2] = el + g + v; sc[3] = c0; sc[4] = c1; sc[5] = c2;
         p.g_off = el; p.a_off = el + g + v;
@@ -680,7 +684,8 @@ __global__ void __launch_bounds__(RR_RASTER_CHUNK) k_raster(rr_frame_bufs b, rr_
         __syncthreads();
         const rr_plan &p = sp;
         long long e = (ch - b.scan[(size_t)s * 6 + 3]) * RR_RASTER_CHUNK + threadIdx.x;
-        long long g = (long long)p.pw * p.ph;
+        long long g, vv, aa; int vx0_, vw_;
+        plan_sizes(p, &g, &vv, &aa, &vx0_, &vw_);
         if (e < g) {
             int y = (int)(e / p.pw), x = (int)(e - (long long)y * p.pw);
             b.arena[p.g_off + e] = rr_patch_pixel(p, t.db + p.tex_off, cam.db_width, d_cubic, x, y);
@@ -715,9 +720,9 @@ __global__ void __launch_bounds__(RR_BLUR_CHUNK) k_blur_v(rr_frame_bufs b, int n
         const rr_plan &p = b.plans[s];
         __syncthreads();
         load_weights(p.sig_y, p.ry, w);
-        int vx0, vw; blur_extents(p, &vx0, &vw);
+        long long gg, nv, aa; int vx0, vw;
+        plan_sizes(p, &gg, &nv, &aa, &vx0, &vw);
         long long e = (ch - b.scan[(size_t)s * 6 + 4]) * RR_BLUR_CHUNK + threadIdx.x;
-        long long nv = (long long)vw * p.bh;
         if (e < nv) {
             int yy = (int)(e / vw), xx = (int)(e - (long long)yy * vw);
             int Y = p.cropy + yy;            // padded row
@@ -747,9 +752,9 @@ __global__ void __launch_bounds__(RR_BLUR_CHUNK) k_blur_h(rr_frame_bufs b, int n
         const rr_plan &p = b.plans[s];
         __syncthreads();
         load_weights(p.sig_x, p.rx, w);
-        int vx0, vw; blur_extents(p, &vx0, &vw);
+        long long gg, vv, na; int vx0, vw;
+        plan_sizes(p, &gg, &vv, &na, &vx0, &vw);
         long long e = (ch - b.scan[(size_t)s * 6 + 5]) * RR_BLUR_CHUNK + threadIdx.x;
-        long long na = (long long)p.bw * p.bh;
         if (e < na) {
             int yy = (int)(e / p.bw), xx = (int)(e - (long long)yy * p.bw);
             int X = p.cropx + xx;            // padded column of the output
