@@ -672,23 +672,155 @@ __device__ __forceinline__ int find_streak(const long long *scan, int n, int fie
 }
 
 // ------------------------------------------------------------------------------------------
-// pre-blur gray patches  (generator.py:126-171): persistent CTAs over 128-pixel chunks
+// pre-blur gray patches  (generator.py:126-171): one CTA per streak (persistent, strided).
+//   Big                -> one thread per patch pixel (16-tap bicubic perspective warp)
+//   INTER_AREA shrink  -> the rotated canvas (imutils.rotate_bound) is evaluated ONCE, band by band,
+//                         into shared memory; the per-pixel sums then follow cv::resize's exact
+//                         accumulation order (column terms left to right inside a source row, rows
+//                         top to bottom), so the result is bit-identical to the per-pixel evaluation.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RR_RASTER_CHUNK) k_raster(rr_frame_bufs b, rr_static_tabs t, rr_cam_dev cam, int n) {
+#define RAS_THREADS 128
+#define RAS_CAP 2048          // doubles per staging array
+#define RAS_MAXW 512          // widest rotated canvas / patch handled by the staged path
+
+__device__ __forceinline__ double ras_sample(const uint8_t *tex, int tw, int th, const double *lut, int X, int Y) {
+    // rr_warp_affine_linear with the fixed-point coordinates already formed
+    int sx = rr_clampi(X >> RR_INTER_BITS, -32768, 32767);
+    int sy = rr_clampi(Y >> RR_INTER_BITS, -32768, 32767);
+    int fx = X & (RR_INTER_TAB - 1), fy = Y & (RR_INTER_TAB - 1);
+    const float s = 1.f / RR_INTER_TAB;
+    float ax1 = fx * s, ax0 = 1.f - ax1, ay1 = fy * s, ay0 = 1.f - ay1;
+    float w0 = ay0 * ax0, w1 = ay0 * ax1, w2 = ay1 * ax0, w3 = ay1 * ax1;
+    if ((unsigned)sx < (unsigned)(tw - 1) && (unsigned)sy < (unsigned)(th - 1)) {
+        const uint8_t *S = tex + sy * tw + sx;
+        return lut[S[0]] * w0 + lut[S[1]] * w1 + lut[S[tw]] * w2 + lut[S[tw + 1]] * w3;
+    }
+    if (sx >= tw || sx + 1 < 0 || sy >= th || sy + 1 < 0) return 0.0;
+    bool x0ok = sx >= 0 && sx < tw, x1ok = sx + 1 >= 0 && sx + 1 < tw;
+    bool y0ok = sy >= 0 && sy < th, y1ok = sy + 1 >= 0 && sy + 1 < th;
+    double v0 = (x0ok && y0ok) ? lut[tex[sy * tw + sx]] : 0.0;
+    double v1 = (x1ok && y0ok) ? lut[tex[sy * tw + sx + 1]] : 0.0;
+    double v2 = (x0ok && y1ok) ? lut[tex[(sy + 1) * tw + sx]] : 0.0;
+    double v3 = (x1ok && y1ok) ? lut[tex[(sy + 1) * tw + sx + 1]] : 0.0;
+    return v0 * w0 + v1 * w1 + v2 * w2 + v3 * w3;
+}
+
+struct ras_smem_src {       // functor over a staged band: rows [0, rb) x columns [0, nW)
+    const double *C; int nW;
+    __device__ __forceinline__ double operator()(int sx, int r) const { return C[r * nW + sx]; }
+};
+
+__global__ void __launch_bounds__(RAS_THREADS, 4) k_raster(rr_frame_bufs b, rr_static_tabs t, rr_cam_dev cam, int n) {
     __shared__ rr_plan sp;
-    const long long total = b.scan[(size_t)n * 6 + 3];
-    for (long long ch = blockIdx.x; ch < total; ch += gridDim.x) {
-        int s = find_streak(b.scan, n, 3, ch);
+    __shared__ double lut[256];
+    __shared__ double C[RAS_CAP];
+    __shared__ double BUF[RAS_CAP];
+    __shared__ double SUM[RAS_MAXW];
+    double *ACC = BUF;                 // area-fast mode only (BUF is the area-mode array)
+    __shared__ int adx[RAS_MAXW], bdx[RAS_MAXW];
+    __shared__ int XR[RAS_CAP / 8], YR[RAS_CAP / 8];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 256; i += RAS_THREADS) lut[i] = (double)i / 255.0;     // bad_weather.py:252
+    const int tw = cam.db_width;
+    for (int s = blockIdx.x; s < n; s += gridDim.x) {
         __syncthreads();
-        if (threadIdx.x < sizeof(rr_plan) / 4) ((int *)&sp)[threadIdx.x] = ((const int *)&b.plans[s])[threadIdx.x];
+        if (tid < sizeof(rr_plan) / 4) ((int *)&sp)[tid] = ((const int *)&b.plans[s])[tid];
         __syncthreads();
         const rr_plan &p = sp;
-        long long e = (ch - b.scan[(size_t)s * 6 + 3]) * RR_RASTER_CHUNK + threadIdx.x;
         long long g, vv, aa; int vx0_, vw_;
         plan_sizes(p, &g, &vv, &aa, &vx0_, &vw_);
-        if (e < g) {
-            int y = (int)(e / p.pw), x = (int)(e - (long long)y * p.pw);
-            b.arena[p.g_off + e] = rr_patch_pixel(p, t.db + p.tex_off, cam.db_width, d_cubic, x, y);
+        if (g == 0) continue;
+        const uint8_t *tex = t.db + p.tex_off;
+        double *out = b.arena + p.g_off;
+        const bool staged = p.type != RR_BIG && (p.resize_mode == RR_RESIZE_AREA || p.resize_mode == RR_RESIZE_AREA_FAST) &&
+                            p.nW <= RAS_MAXW && p.pw <= RAS_MAXW;
+        if (!staged) {
+            for (long long e = tid; e < g; e += RAS_THREADS) {
+                int y = (int)(e / p.pw), x = (int)(e - (long long)y * p.pw);
+                out[e] = rr_patch_pixel(p, tex, tw, d_cubic, x, y);
+            }
+            continue;
+        }
+        const int nW = p.nW, nH = p.nH, pw = p.pw, ph = p.ph, th = p.tex_h;
+        const int AB_SCALE = 1 << 10;
+        for (int x = tid; x < nW; x += RAS_THREADS) {
+            adx[x] = rr_round(p.M[0] * x * AB_SCALE);
+            bdx[x] = rr_round(p.M[3] * x * AB_SCALE);
+        }
+        int RB = RAS_CAP / (nW > pw ? nW : pw);
+        if (RB < 1) RB = 1;
+        if (RB > RAS_CAP / 8) RB = RAS_CAP / 8;
+        const bool fast = p.resize_mode == RR_RESIZE_AREA_FAST;
+        const int isx = rr_round(p.scale_x), isy = rr_round(p.scale_y);
+        for (int dy = 0; dy < ph; dy++) {
+            // source rows of this destination row
+            rr_area_span ty;
+            int nr, row0;
+            if (fast) { nr = isy; row0 = dy * isy; ty.has_first = 0; ty.n = isy; ty.has_last = 0; ty.s_first = row0; }
+            else { ty = rr_area_tab(dy, p.scale_y, nH); nr = ty.has_first + ty.n + ty.has_last; row0 = ty.s_first - ty.has_first; }
+            const int area = isx * isy, area4 = area - (area & 3);
+            for (int j0 = 0; j0 < nr; j0 += RB) {
+                const int rb = (nr - j0) < RB ? (nr - j0) : RB;
+                __syncthreads();                         // previous users of C / BUF / XR are done
+                if (tid < rb) {
+                    int sy = row0 + j0 + tid;
+                    int yy = p.flip ? (nH - 1 - sy) : sy;
+                    XR[tid] = rr_round((p.M[1] * yy + p.M[2]) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
+                    YR[tid] = rr_round((p.M[4] * yy + p.M[5]) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
+                }
+                __syncthreads();
+                for (int i = tid; i < rb * nW; i += RAS_THREADS) {          // phase 1: the canvas band, once
+                    int r = i / nW, c = i - r * nW;
+                    int X = (XR[r] + adx[c]) >> (10 - RR_INTER_BITS);
+                    int Y = (YR[r] + bdx[c]) >> (10 - RR_INTER_BITS);
+                    C[i] = ras_sample(tex, tw, th, lut, X, Y);
+                }
+                __syncthreads();
+                if (!fast) {
+                    for (int i = tid; i < rb * pw; i += RAS_THREADS) {      // phase 2a: per (row, dx) column sums
+                        int r = i / pw, dx = i - r * pw;
+                        rr_area_span tx = rr_area_tab(dx, p.scale_x, nW);
+                        ras_smem_src src = {C, nW};
+                        BUF[i] = rr_area_row(src, tx, r);
+                    }
+                    __syncthreads();
+                    for (int dx = tid; dx < pw; dx += RAS_THREADS) {        // phase 2b: rows, in order
+                        double acc = SUM[dx];
+                        for (int r = 0; r < rb; r++) {
+                            int j = j0 + r;
+                            float beta = (ty.has_first && j == 0) ? ty.a_first : ((ty.has_last && j == nr - 1) ? ty.a_last : ty.a_mid);
+                            double v = beta * BUF[r * pw + dx];
+                            acc = (j == 0) ? v : acc + v;
+                        }
+                        SUM[dx] = acc;
+                    }
+                } else {
+                    // cv::resizeAreaFast_: sum += ((a + b) + c) + d over the cell in row-major order, then the tail
+                    for (int dx = tid; dx < pw; dx += RAS_THREADS) {
+                        double sum = (j0 == 0) ? 0.0 : SUM[dx], acc = ACC[dx];
+                        for (int r = 0; r < rb; r++) {
+                            int kbase = (j0 + r) * isx;
+                            const double *row = C + r * nW + dx * isx;
+                            for (int c = 0; c < isx; c++) {
+                                int k = kbase + c;
+                                double v = row[c];
+                                if (k < area4) {
+                                    int pos = k & 3;
+                                    acc = pos == 0 ? v : acc + v;
+                                    if (pos == 3) sum += acc;
+                                } else sum += v;
+                            }
+                        }
+                        SUM[dx] = sum; ACC[dx] = acc;
+                    }
+                }
+            }
+            __syncthreads();
+            for (int dx = tid; dx < pw; dx += RAS_THREADS) {
+                double v = SUM[dx];
+                if (fast) { float scale = 1.f / area; v = v * scale; }
+                out[(size_t)dy * pw + dx] = v < 0 ? 0 : (v > 1 ? 1 : v);
+            }
         }
     }
 }
@@ -696,7 +828,9 @@ __global__ void __launch_bounds__(RR_RASTER_CHUNK) k_raster(rr_frame_bufs b, rr_
 cudaError_t rr_launch_raster(const rr_frame_bufs &b, const rr_static_tabs &t, const rr_cam_dev &cam, int n_streaks, int n_sm,
                              cudaStream_t st) {
     if (n_streaks == 0) return cudaSuccess;
-    k_raster<<<n_sm * 8, RR_RASTER_CHUNK, 0, st>>>(b, t, cam, n_streaks);
+    int grid = n_sm * 4;
+    if (grid > n_streaks) grid = n_streaks;
+    k_raster<<<grid, RAS_THREADS, 0, st>>>(b, t, cam, n_streaks);
     return cudaGetLastError();
 }
 
