@@ -130,6 +130,10 @@ int rr_envmap_only(rr_context *ctx, int n_frames, const double *planar_bgr_f64, 
 int rr_streak_photometry_only(rr_context *ctx, const uint8_t *env_bgr_u8, int n_streaks,
                               const rr_streak_rec *streaks, double *out_fovx_fovy_dropY /* n*3 */);
 
+/* solid_angle.get_solid_angles (common/solid_angle.py:5-29) for an arbitrary (H_env, W_env) lat-long
+ * grid, computed on the device; out is a HOST buffer of H_env*W_env float64. */
+int rr_solid_angles(rr_context *ctx, int H_env, int W_env, double *out);
+
 int rr_debug_read(rr_context *ctx, int what, int frame, void *dst, size_t bytes);
 int rr_timings(rr_context *ctx, float *ms_per_stage /* RR_T_COUNT */);
 int rr_kernel_launches(rr_context *ctx, long long *count);   /* kernels launched since rr_create */

@@ -71,6 +71,7 @@ def load() -> C.CDLL:
         "rr_envmap_only": [vp, C.c_int, f64p, u8p],
         "rr_streak_photometry_only": [vp, u8p, C.c_int, vp, f64p],
         "rr_debug_read": [vp, C.c_int, C.c_int, vp, C.c_size_t],
+        "rr_solid_angles": [vp, C.c_int, C.c_int, f64p],
         "rr_timings": [vp, f32p],
         "rr_kernel_launches": [vp, C.POINTER(C.c_longlong)],
         "rr_stream": [vp, C.POINTER(vp)],

@@ -482,6 +482,22 @@ int rr_streak_photometry_only(rr_context *c, const uint8_t *env_bgr_u8, int n_st
     return RR_OK;
 }
 
+int rr_solid_angles(rr_context *c, int H_env, int W_env, double *out) {
+    if (!c || !out || H_env <= 0 || W_env <= 0) { set_err("rr_solid_angles: bad arguments"); return RR_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    double *om = nullptr, *pref = nullptr, *tot = nullptr;
+    size_t n = (size_t)H_env * W_env;
+    CK(cudaMalloc((void **)&om, n * sizeof(double)));
+    CK(cudaMalloc((void **)&pref, (size_t)H_env * (W_env + 1) * sizeof(double)));
+    CK(cudaMalloc((void **)&tot, sizeof(double)));
+    cudaError_t e = rr_launch_omega(H_env, W_env, om, pref, tot, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpy(out, om, n * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(om); cudaFree(pref); cudaFree(tot);
+    c->launches += 3;
+    CK(e);
+    return RR_OK;
+}
+
 int rr_debug_read(rr_context *c, int what, int frame, void *dst, size_t bytes) {
     if (!c || !c->have_cam || !dst) { set_err("rr_debug_read: bad arguments"); return RR_ERR_ARG; }
     if (frame < 0 || frame >= c->max_batch) { set_err("rr_debug_read: frame out of range"); return RR_ERR_ARG; }

@@ -1,0 +1,242 @@
+"""common.generator.Generator of the reference (common/generator.py:22-473) driving the B200
+library: same constructor, same ``run()`` loops (sequence x weather x frame), same output tree,
+same conflict strategies and per-frame seeding -- but frames are rendered in batches by
+``rr_render_frames`` instead of streak by streak in Python.
+
+Differences that are presentation only: PNGs are written with OpenCV (the reference uses
+``matplotlib.pyplot.imsave``; matplotlib is used here too when it is importable so the files are
+byte-compatible), and progress is printed per batch.
+"""
+import os
+import sys
+import time
+
+import cv2
+import numpy as np
+
+from common import my_utils
+from common.bad_weather import DBManager, RainRenderer, EnvironmentMapGenerator, FovComputation  # noqa: F401 (API parity)
+from rain_rendering_b200 import api as _api
+
+FOG_ATT = 1
+USE_DEPTH_WEIGHTING = 0
+
+
+def _imsave_rgb(path, bgr_u8):
+    cv2.imwrite(path, bgr_u8)
+
+
+def _imsave_mask(path, mask):
+    try:
+        import matplotlib.pyplot as plt        # identical to the reference when matplotlib exists
+        plt.imsave(path, mask)
+        return
+    except Exception:
+        pass
+    lo, hi = float(mask.min()), float(mask.max())
+    norm = (mask - lo) / (hi - lo) if hi > lo else np.zeros_like(mask)
+    cv2.imwrite(path, (norm * 65535.0 + 0.5).astype(np.uint16))     # 16-bit gray, min/max normalised like imsave
+
+
+class Generator:
+    def __init__(self, args):
+        self.conflict_strategy = args.conflict_strategy
+        self.rendering_strategy = args.rendering_strategy
+        if args.rendering_strategy is None:
+            self.output_root = os.path.join(args.output, args.dataset)
+        else:
+            self.output_root = os.path.join(args.output, args.dataset + '_' + args.rendering_strategy)
+        self.dataset = args.dataset
+        self.dataset_root = args.dataset_root
+        self.images = args.images
+        self.sequences = args.sequences
+        self.depth = args.depth
+        self.particles = args.particles
+        self.weather = args.weather
+        self.texture = args.texture
+        self.norm_coeff = args.norm_coeff
+        self.save_envmap = args.save_envmap
+        self.settings = args.settings
+        self.calib = args.calib
+        self.exposure = args.settings["cam_exposure"]
+        self.camera_gain = args.settings["cam_gain"]
+        self.focal = args.settings["cam_focal"] / 1000.
+        self.f_number = args.settings["cam_f_number"]
+        self.focus_plane = args.settings["cam_focus_plane"]
+        self.noise_scale = args.noise_scale
+        self.noise_std = args.noise_std
+        self.opacity_attenuation = args.opacity_attenuation
+        self.frame_start = args.frame_start
+        self.frame_end = args.frame_end
+        self.frame_step = args.frame_step
+        self.frames = args.frames
+        self.verbose = args.verbose
+        self.env_type = 'ours'
+        self.irrad_type = 'ambient'
+        self.db = None
+        self.renderer = None
+        self.fov_comp = None
+        self.BGR_env_map = None
+        self.env_map_xyY = None
+        self.solid_angle_map = None
+        self.batch = int(os.environ.get("RAIN_B200_BATCH", "16"))
+        self.device = int(os.environ.get("LOCAL_RANK", os.environ.get("RAIN_B200_DEVICE", "0")))
+        self._ctx = None
+        self.check_folders()
+
+    def check_folders(self):
+        print('Output directory: {}'.format(self.output_root))
+        existing = []
+        for sequence in self.sequences:
+            for w in self.weather:
+                out_dir = os.path.join(self.output_root, sequence, w["weather"], '{}mm'.format(w["fallrate"]))
+                if os.path.exists(out_dir):
+                    existing.append(out_dir)
+        if len(existing) != 0 and self.conflict_strategy is None:
+            print("\r\nFolders already exist: \n%s" % "\n".join(existing))
+            while self.conflict_strategy not in ["overwrite", "skip", "rename_folder"]:
+                self.conflict_strategy = input("\r\nWhat strategy to use (overwrite|skip|rename_folder):   ")
+        assert (self.conflict_strategy in [None, "overwrite", "skip", "rename_folder"])
+
+    def compute_drop(self, bg, drop_dict, rainy_bg, rainy_mask, rainy_saturation_mask):
+        raise NotImplementedError("streaks are rendered in batches on the GPU (rr_render_frames); there is no per-streak CPU path")
+
+    # ------------------------------------------------------------------------------------------
+    def _decode(self, image_file, depth_file):
+        """generator.py:352-381 on the decode side (I/O): uint8 BGR image and float32 depth."""
+        bg = cv2.imread(image_file)
+        if self.settings["render_scale"] != 1:
+            raise NotImplementedError("render_scale != 1 (the reference resizes the float image on the host, generator.py:354-355) "
+                                      "is not wired into the uint8 C ABI yet")
+        if depth_file.endswith(".png"):
+            depth = cv2.imread(depth_file, cv2.IMREAD_UNCHANGED)
+            if depth is None:
+                print('Missing/Corrupted depth data (%s)' % depth_file)
+                return None, None
+            depth = depth.astype(np.float32) / 256.
+        elif depth_file.endswith(".npy"):
+            depth = np.load(depth_file).astype(np.float32)
+        else:
+            raise Exception("Invalid extension")
+        depthHW = np.array([int((depth.shape[0] * self.settings["depth_scale"]) // self.settings["render_scale"]),
+                            int((depth.shape[1] * self.settings["depth_scale"]) // self.settings["render_scale"])])
+        if not np.all(depth.shape[:2] == depthHW):
+            depth = cv2.resize(depth, (depthHW[1], depthHW[0]))
+        assert (np.all(depth.shape[:2] <= bg.shape[:2])), "Depth cannot be larger than the image"
+        if not np.all(depth.shape[:2] == bg.shape[:2]):
+            bg = my_utils.crop_center(bg, depth.shape[0], depth.shape[1])
+        return np.ascontiguousarray(bg), np.ascontiguousarray(depth, dtype=np.float32)
+
+    def run(self):
+        for folder_idx, sequence in enumerate(self.sequences):
+            print('\nSequence: ' + sequence)
+            depth_folder = self.depth[sequence]
+            for sim_idx, sim_weather in enumerate(self.weather):
+                weather, fallrate = sim_weather["weather"], sim_weather["fallrate"]
+                out_seq_dir = os.path.join(self.output_root, sequence)
+                out_dir = os.path.join(out_seq_dir, weather, '{}mm'.format(fallrate))
+                sim_file = self.particles[sequence][sim_idx]
+                if os.path.exists(out_dir):
+                    if self.conflict_strategy in ("skip", "overwrite"):
+                        pass
+                    elif self.conflict_strategy == "rename_folder":
+                        out_shift = 0
+                        while os.path.exists(out_dir + '_copy%05d' % out_shift):
+                            out_shift += 1
+                        out_dir = out_dir + '_copy%05d' % out_shift
+                    else:
+                        raise NotImplementedError
+                os.makedirs(out_dir, exist_ok=True)
+                if "nuscenes" in self.dataset:
+                    files = list(self.images[sequence])
+                    depth_files = list(self.depth[sequence])
+                else:
+                    files = my_utils.natsorted([os.path.join(self.images[sequence], p) for p in my_utils.os_listdir(self.images[sequence])])
+                    depth_files = my_utils.natsorted([os.path.join(depth_folder, d) for d in my_utils.os_listdir(depth_folder)])
+                files = [f for f in files if os.path.isfile(f)]
+                depth_files = [f for f in depth_files if os.path.isfile(f)]
+                im = files[0]
+                if im.endswith(".png"):
+                    imH, imW = cv2.imread(im).shape[0:2]
+                elif im.endswith(".npy"):
+                    imH, imW = np.load(im).shape[0:2]
+                else:
+                    raise Exception("Invalid extension", im)
+                imH, imW = imH // self.settings["render_scale"], imW // self.settings["render_scale"]
+                print('Simulation: rain {}mm/hr'.format(fallrate))
+                self.db = DBManager(streaks_path_xml=sim_file, streaks_path=self.texture, norm_coeff_path=self.norm_coeff)
+                self.renderer = RainRenderer(focal=self.focal, f_number=self.f_number, focus_plane=6, radius=10, fov=165)
+                self.db.load_streak_database()
+                self.db.load_streaks_from_xml(self.dataset, self.settings, [imW, imH], use_pickle=False, verbose=self.verbose)
+                frame_render_dict = list(self.db.streaks_simulator.values())
+                if self._ctx is None:
+                    self._ctx = _api.RainContext(self.device)
+                ctx = self._ctx
+                ctx.set_streak_db(self.db.streaks_light, self.db.ratio)
+                gain = self.camera_gain if self.camera_gain else 20      # generator.py:232-233,260-261
+                ctx.set_camera(imW, imH, focal_mm=self.focal * 1000., f_number=self.f_number, exposure_ms=self.exposure, gain=gain,
+                               fallrate=fallrate, opacity_attenuation=self.opacity_attenuation, max_batch=self.batch)
+                f_start, f_end, f_step = self.frame_start, self.frame_end, self.frame_step
+                f_end = len(files) if f_end is None else min(f_end, len(files))
+                if self.frames:
+                    idx = np.unique(np.clip(self.frames, 0, f_end - 1)).tolist()
+                else:
+                    idx = list(range(f_start, f_end, f_step))
+                print("{} images".format(len(idx)))
+                frames_exist_nb = 0
+                t0 = time.time()
+                pending = []          # (bgr, depth, records, out paths)
+
+                def flush():
+                    if not pending:
+                        return
+                    bgr = np.stack([p[0] for p in pending])
+                    depth = np.stack([p[1] for p in pending])
+                    recs = np.concatenate([p[2] for p in pending])
+                    offs = np.concatenate([[0], np.cumsum([len(p[2]) for p in pending])]).astype(np.int32)
+                    if (bgr.shape[2], bgr.shape[1]) != (ctx.W, ctx.H):
+                        raise AssertionError("frame size %s differs from the sequence size (%d, %d) (generator.py:250-258 reads it once)" % (bgr.shape, ctx.W, ctx.H))
+                    out = ctx.render_frames(bgr, depth, recs, offs, want=("mask", "u8"))
+                    for k, p in enumerate(pending):
+                        os.makedirs(os.path.dirname(p[3]), exist_ok=True)
+                        os.makedirs(os.path.dirname(p[4]), exist_ok=True)
+                        _imsave_rgb(p[3], out["u8"][k])
+                        _imsave_mask(p[4], out["mask"][k])
+                    pending.clear()
+
+                for f_idx, i in enumerate(idx):
+                    image_file, depth_file = files[i], depth_files[i]
+                    if self.dataset == 'nuscenes':
+                        render_ix = np.linspace(0, len(frame_render_dict), len(files), endpoint=False, dtype=int)
+                        f_name_idx = int(render_ix[i])
+                    else:
+                        f_name_idx = i
+                    assert os.path.exists(image_file), "Image file {} does not exist".format(image_file)
+                    assert os.path.exists(depth_file), "Depth file {} does not exist".format(depth_file)
+                    file_name = os.path.split(image_file)[-1]
+                    out_rainy_path = os.path.join(out_dir, 'rainy_image', '{}.png'.format(file_name[:-4]))
+                    out_rainy_mask_path = os.path.join(out_dir, 'rain_mask', '{}.png'.format(file_name[:-4]))
+                    if os.path.exists(out_rainy_path) or os.path.exists(out_rainy_mask_path):
+                        if self.conflict_strategy == "skip":
+                            frames_exist_nb += 1
+                            continue
+                        elif self.conflict_strategy == "overwrite":
+                            pass
+                        else:
+                            raise NotImplementedError
+                    bg, depth = self._decode(image_file, depth_file)
+                    if bg is None:
+                        continue
+                    sim = frame_render_dict[f_name_idx % len(frame_render_dict)]
+                    # np.random.seed(f_name_idx) + the per-streak draws + the wind write-back (generator.py:318,136,152-161)
+                    recs = _api.assemble_frame_records(sim.records, imW, imH, self.db.ratio, f_name_idx, self.noise_std, self.noise_scale)
+                    assert len(recs) <= 2 ** 16, "Assert that the number of drops doesn't overpass the uint16 rain_mask capacity"
+                    pending.append((bg, depth, recs, out_rainy_path, out_rainy_mask_path))
+                    if len(pending) == self.batch:
+                        flush()
+                        if self.verbose:
+                            sys.stdout.write('\r%d/%d frames, %.1f frames/s   ' % (f_idx + 1, len(idx), (f_idx + 1) / (time.time() - t0)))
+                flush()
+                if frames_exist_nb > 0:
+                    print("Skipped {}/{} already existing renderings".format(frames_exist_nb, len(idx)))
+            print("\n\nEnd of the simulation")

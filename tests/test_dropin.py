@@ -1,0 +1,126 @@
+"""The drop-in ``common`` package: import resolution next to the reference (CPU) and a full
+Generator.run() against the oracle (GPU)."""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import types
+
+import cv2
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DROPIN = os.path.join(ROOT, "rain_rendering_b200", "dropin")
+REF = os.environ.get("RAIN_REFERENCE_ROOT", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "main.py")), reason="reference tree not mounted")
+def test_reference_main_resolves_the_dropin_generator_and_its_own_db():
+    code = r"""
+import sys, os
+sys.path[:0] = [%r, %r, %r, %r]
+os.chdir(%r)
+import main, common.generator, common.db, common.bad_weather
+assert common.generator.__file__.startswith(%r), common.generator.__file__
+assert common.bad_weather.__file__.startswith(%r)
+assert common.db.__file__.startswith(%r), common.db.__file__
+assert main.Generator is common.generator.Generator
+print("OK")
+""" % (DROPIN, ROOT, os.path.join(ROOT, "oracle", "ref_shims"), REF, REF, DROPIN, DROPIN, REF)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
+
+
+def _args(paths, dataset, fallrate, seq="seq1"):
+    from rain_rendering_b200 import synth
+    cam = synth.CAMERAS[dataset]
+    a = types.SimpleNamespace()
+    a.conflict_strategy, a.rendering_strategy = "overwrite", None
+    a.output, a.dataset, a.dataset_root = paths["output"], dataset, os.path.join(paths["dataset_root"], dataset)
+    a.sequences = [seq]
+    a.images = {seq: os.path.join(a.dataset_root, seq, "rgb")}
+    a.depth = {seq: os.path.join(a.dataset_root, seq, "depth")}
+    a.calib = {seq: None}
+    a.particles = {seq: [paths["xml"]]}
+    a.weather = [{"weather": "rain", "fallrate": fallrate}]
+    a.texture = os.path.join(paths["streaks_db"], "env_light_database", "size32")
+    a.norm_coeff = os.path.join(paths["streaks_db"], "env_light_database", "txt", "normalized_env_max.txt")
+    a.save_envmap = False
+    a.settings = dict(cam_exposure=cam["cam_exposure"], cam_gain=cam["cam_gain"], cam_focal=cam["cam_focal"], cam_f_number=cam["cam_f_number"],
+                      cam_focus_plane=6.0, render_scale=1, depth_scale=1)
+    a.noise_scale, a.noise_std, a.opacity_attenuation = 1.0, 2.0, 0.9
+    a.frame_start, a.frame_end, a.frame_step, a.frames, a.verbose = 0, None, 1, [], False
+    return a
+
+
+@pytest.mark.gpu
+def test_generator_run_writes_the_oracle_images():
+    for k in [k for k in sys.modules if k == "common" or k.startswith("common.")]:
+        del sys.modules[k]
+    sys.path.insert(0, DROPIN)
+    try:
+        from rain_rendering_b200 import synth
+        from oracle import rain_oracle as ro
+        import common.generator as gen
+        assert gen.__file__.startswith(DROPIN)
+        root = tempfile.mkdtemp(prefix="rr_dropin_")
+        W, H, nf = 384, 256, 5
+        paths = synth.write_dataset(root, "customdb", "seq1", W, H, nf, 25, 1200, seed=3, n_sim_frames=2)
+        a = _args(paths, "customdb", 25)
+        os.environ["RAIN_B200_BATCH"] = "2"          # 5 frames -> batches of 2, 2, 1
+        g = gen.Generator(a)
+        g.run()
+        out_dir = os.path.join(paths["output"], "customdb", "seq1", "rain", "25mm")
+        tex, ratios = ro.load_streak_database(a.texture, a.norm_coeff)
+        frames = ro.load_streaks_from_xml(paths["xml"], 1, W, H)
+        cam = ro.Camera(W=W, H=H, fallrate=25, noise_scale=1.0, noise_std=2.0, opacity_attenuation=0.9)
+        for i in range(nf):
+            name = "%06d" % i
+            got = cv2.imread(os.path.join(out_dir, "rainy_image", name + ".png"))
+            assert got is not None and os.path.exists(os.path.join(out_dir, "rain_mask", name + ".png"))
+            bg, depth = ro.read_frame(os.path.join(a.images["seq1"], name + ".png"), os.path.join(a.depth["seq1"], name + ".png"))
+            o = ro.render_frame(bg, depth, frames[i % 2], tex, ratios, cam, i, f32_mode="canonical")
+            assert np.abs(got.astype(int) - o.out_u8.astype(int)).max() <= 1
+        # skip strategy: nothing is re-rendered
+        a.conflict_strategy = "skip"
+        t = os.path.getmtime(os.path.join(out_dir, "rainy_image", "000000.png"))
+        gen.Generator(a).run()
+        assert os.path.getmtime(os.path.join(out_dir, "rainy_image", "000000.png")) == t
+        shutil.rmtree(root, ignore_errors=True)
+    finally:
+        sys.path.remove(DROPIN)
+        for k in [k for k in sys.modules if k == "common" or k.startswith("common.")]:
+            del sys.modules[k]
+
+
+@pytest.mark.gpu
+def test_dropin_stage_classes_match_oracle():
+    for k in [k for k in sys.modules if k == "common" or k.startswith("common.")]:
+        del sys.modules[k]
+    sys.path.insert(0, DROPIN)
+    try:
+        from oracle import rain_oracle as ro
+        from rain_rendering_b200 import synth
+        import common.add_attenuation as att
+        import common.bad_weather as bw
+        import common.solid_angle as sa
+        W, H = 320, 200
+        bgr, depth = synth.make_frame(W, H, 11)
+        cam = ro.Camera(W=W, H=H, fallrate=50)
+        fog = att.FogRain(rain_intensity=50, focal=0.006, f_number=6.0, angle=90, exposure=2, camera_gain=20).fog_rain_layer(bgr / 255.0, depth)
+        ofog = ro.fog_rain_layer(bgr / 255.0, depth, cam, "canonical")
+        assert np.abs(fog - ofog).max() < 1e-13
+        env = bw.EnvironmentMapGenerator(0.006, W, H).generate_map(ofog)
+        oenv = ro.generate_map(ofog, ro.build_env_tables(W, H, 0.006))
+        assert np.array_equal(env, oenv)
+        om = sa.get_solid_angles(env)
+        assert np.abs(om / ro.solid_angles(env.shape[0], env.shape[1]) - 1).max() < 1e-7
+        with pytest.raises(NotImplementedError):
+            bw.RainRenderer(0.006, 6.0, 6, 10, 165).add_drop_to_image()
+        assert bw.DBManager.classify_drop(4) == bw.DropType.Big and bw.DBManager.classify_drop(1) == bw.DropType.Small
+    finally:
+        sys.path.remove(DROPIN)
+        for k in [k for k in sys.modules if k == "common" or k.startswith("common.")]:
+            del sys.modules[k]
