@@ -23,6 +23,8 @@ static void set_err(const char *fmt, ...) {
         }                                                                                              \
     } while (0)
 
+#define RR_MAX_SUB 8
+
 struct rr_context {
     int device = 0, n_sm = 148;
     cudaStream_t stream = nullptr;
@@ -52,6 +54,13 @@ struct rr_context {
     rr_frame_bufs fb;
     std::vector<void *> owned;       // everything cudaMalloc'ed for the camera (freed on re-set / destroy)
     int last_n_streaks = 0;
+    // copy/compute overlap inside rr_render_frames (pinned host buffers): sub-batches on three streams
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_in[RR_MAX_SUB], ev_done[RR_MAX_SUB], ev_out;
+    int32_t *d_sub_offsets = nullptr;    // [RR_MAX_SUB][max_batch + 1]
+    long long scan_base[RR_MAX_SUB];     // element index (in units of 6 long long) of each sub-batch's scan block
+    int sub_n[RR_MAX_SUB];
+    int n_sub_last = 1;
 };
 
 template <class T>
@@ -91,6 +100,13 @@ int rr_create(int device_id, rr_context **out) {
     CK(cudaGetDeviceProperties(&prop, device_id));
     c->n_sm = prop.multiProcessorCount;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < RR_MAX_SUB; i++) {
+        CK(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
     for (int i = 0; i < RR_T_COUNT + 2; i++) CK(cudaEventCreate(&c->ev[i]));
     memset(c->last_ms, 0, sizeof(c->last_ms));
     memset(&c->fb, 0, sizeof(c->fb));
@@ -109,6 +125,10 @@ int rr_destroy(rr_context *c) {
     if (c->d_tex_h) cudaFree(c->d_tex_h);
     for (int i = 0; i < RR_T_COUNT + 2; i++) cudaEventDestroy(c->ev[i]);
     cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->s_h2d);
+    cudaStreamDestroy(c->s_d2h);
+    for (int i = 0; i < RR_MAX_SUB; i++) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_done[i]); }
+    cudaEventDestroy(c->ev_out);
     delete c;
     return RR_OK;
 }
@@ -154,7 +174,7 @@ static int ensure_streak_cap(rr_context *c, int n) {
     int cap = n + n / 4 + 1024;
     CK(dev_alloc(c, &c->d_streaks, (size_t)cap));
     CK(dev_alloc(c, &c->fb.plans, (size_t)cap));
-    CK(dev_alloc(c, &c->fb.scan, (size_t)(cap + 1) * 6));
+    CK(dev_alloc(c, &c->fb.scan, (size_t)(cap + 1 + RR_MAX_SUB) * 6));
     c->streak_cap = cap;
     return RR_OK;
 }
@@ -216,6 +236,7 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
     CK(dev_alloc(c, &c->d_bgr, F * np * 3));
     CK(dev_alloc(c, &c->d_depth, F * np));
     CK(dev_alloc(c, &c->d_offsets, F + 1));
+    CK(dev_alloc(c, &c->d_sub_offsets, (size_t)RR_MAX_SUB * (F + 1)));
     CK(dev_alloc(c, &b.chan_sum, F * 4));
     CK(dev_alloc(c, &b.rainy, F * 3 * np));
     CK(dev_alloc(c, &b.bg8, F * np * 3));
@@ -273,7 +294,6 @@ static int run_pipeline(rr_context *c, int F, int n_streaks, bool timed) {
     cudaStream_t st = c->stream;
     const int W = c->cam.W, H = c->cam.H;
     c->camd.db_width = c->db_width; c->camd.n_tex = c->n_tex;
-    CK(cudaMemsetAsync(b.err_flag, 0, sizeof(int), st));
     if (timed) CK(cudaEventRecord(c->ev[RR_T_FOG], st));
     CK(rr_launch_stats(b, F, W, H, st));
     CK(rr_launch_fog(b, c->fogc, F, W, H, st));
@@ -296,6 +316,23 @@ static int run_pipeline(rr_context *c, int F, int n_streaks, bool timed) {
     return RR_OK;
 }
 
+// shifted view of the batch buffers for frames [f0, f0 + ...) whose streaks start at record s0
+static rr_frame_bufs sub_view(const rr_context *c, const rr_frame_bufs &b, int f0, int s0, long long scan_base) {
+    rr_frame_bufs v = b;
+    const size_t np = (size_t)c->cam.W * c->cam.H, npe = (size_t)c->H_env * c->W_env;
+    const size_t tiles = (size_t)((c->cam.W + RR_TILE_W - 1) / RR_TILE_W) * ((c->cam.H + RR_TILE_H - 1) / RR_TILE_H);
+    v.bgr += (size_t)f0 * np * 3; v.depth += (size_t)f0 * np; v.streaks += s0;
+    v.chan_sum += (size_t)f0 * 4; v.rainy += (size_t)f0 * 3 * np; v.bg8 += (size_t)f0 * np * 3; v.fblur += (size_t)f0 * np;
+    v.env_fill += (size_t)f0 * npe * 3; v.env8 += (size_t)f0 * npe * 3;
+    v.pref += (size_t)f0 * 3 * c->H_env * (c->W_env + 1); v.rowtot += (size_t)f0 * c->H_env; v.ambient += f0;
+    v.plans += s0; v.scan += (size_t)scan_base * 6;
+    v.tile_sum += (size_t)f0 * tiles; v.frame_mean += f0;
+    if (v.out_bgr) v.out_bgr += (size_t)f0 * np * 3;
+    if (v.out_mask) v.out_mask += (size_t)f0 * np;
+    if (v.out_u8) v.out_u8 += (size_t)f0 * np * 3;
+    return v;
+}
+
 static int finish_timings(rr_context *c) {
     // ev[RR_T_H2D] .. ev[RR_T_TOTAL] were recorded in order; slot i = time from ev[i] to ev[i+1]
     for (int i = RR_T_H2D; i < RR_T_TOTAL; i++) {
@@ -316,7 +353,11 @@ static int check_flag(rr_context *c, bool grow) {
     CK(cudaStreamSynchronize(c->stream));
     if (!flag) return RR_OK;
     long long need = 0;
-    CK(cudaMemcpy(&need, c->fb.scan + (size_t)c->last_n_streaks * 6, sizeof(long long), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < c->n_sub_last; k++) {
+        long long v = 0;
+        CK(cudaMemcpy(&v, c->fb.scan + (size_t)(c->scan_base[k] + c->sub_n[k]) * 6, sizeof(long long), cudaMemcpyDeviceToHost));
+        if (v > need) need = v;
+    }
     if (grow) {
         long long cap = need + need / 4 + 4096;
         // the old arena stays in c->owned (freed with the camera); allocate the larger one
@@ -350,24 +391,67 @@ int rr_render_frames(rr_context *c, int n_frames, const uint8_t *bgr, const floa
     const size_t np = (size_t)c->cam.W * c->cam.H;
     cudaStream_t st = c->stream;
     rr_frame_bufs &b = c->fb;
-    CK(cudaEventRecord(c->ev[RR_T_H2D], st));
-    CK(cudaMemcpyAsync(c->d_bgr, bgr, F * np * 3, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(c->d_depth, depth, F * np * sizeof(float), cudaMemcpyHostToDevice, st));
-    if (n_streaks) CK(cudaMemcpyAsync(c->d_streaks, streaks, (size_t)n_streaks * sizeof(rr_streak_rec), cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(c->d_offsets, streak_offsets, (F + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    b.bgr = c->d_bgr; b.depth = c->d_depth; b.streaks = c->d_streaks; b.offsets = c->d_offsets;
+    // sub-batches overlap H2D / compute / D2H when the caller's buffers are page-locked
+    int S = 1;
+    {
+        cudaPointerAttributes pa;
+        bool pinned = cudaPointerGetAttributes(&pa, bgr) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        const char *env = getenv("RR_SUB_BATCHES");
+        int want = env ? atoi(env) : 4;
+        if (pinned && want > 1) S = want < RR_MAX_SUB ? want : RR_MAX_SUB;
+        if (S > F) S = F;
+    }
+    std::vector<int32_t> sub_off((size_t)S * (F + 1), 0);
+    int fstart[RR_MAX_SUB + 1];
+    for (int k = 0; k <= S; k++) fstart[k] = (int)((long long)F * k / S);
     for (int attempt = 0;; attempt++) {
-        r = run_pipeline(c, F, n_streaks, true);
-        if (r != RR_OK) return r;
-        if (out_bgr) CK(cudaMemcpyAsync(out_bgr, b.out_bgr, F * np * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
-        if (out_mask) CK(cudaMemcpyAsync(out_mask, b.out_mask, F * np * sizeof(float), cudaMemcpyDeviceToHost, st));
-        if (out_bgr_u8) CK(cudaMemcpyAsync(out_bgr_u8, b.out_u8, F * np * 3, cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(c->ev[RR_T_H2D], st));
+        CK(cudaMemsetAsync(b.err_flag, 0, sizeof(int), st));
+        CK(cudaEventRecord(c->ev_out, st));
+        CK(cudaStreamWaitEvent(c->s_h2d, c->ev_out, 0));       // previous call's compute is done before inputs are overwritten
+        long long sb = 0;
+        for (int k = 0; k < S; k++) {
+            const int f0 = fstart[k], nf = fstart[k + 1] - f0, s0 = streak_offsets[f0], ns = streak_offsets[f0 + nf] - s0;
+            for (int i = 0; i <= nf; i++) sub_off[(size_t)k * (F + 1) + i] = streak_offsets[f0 + i] - s0;
+            cudaStream_t hs = S > 1 ? c->s_h2d : st;
+            CK(cudaMemcpyAsync(c->d_bgr + (size_t)f0 * np * 3, bgr + (size_t)f0 * np * 3, (size_t)nf * np * 3, cudaMemcpyHostToDevice, hs));
+            CK(cudaMemcpyAsync(c->d_depth + (size_t)f0 * np, depth + (size_t)f0 * np, (size_t)nf * np * sizeof(float), cudaMemcpyHostToDevice, hs));
+            if (ns) CK(cudaMemcpyAsync(c->d_streaks + s0, streaks + s0, (size_t)ns * sizeof(rr_streak_rec), cudaMemcpyHostToDevice, hs));
+            CK(cudaMemcpyAsync(c->d_sub_offsets + (size_t)k * (F + 1), sub_off.data() + (size_t)k * (F + 1), (nf + 1) * sizeof(int32_t),
+                               cudaMemcpyHostToDevice, hs));
+            if (S > 1) { CK(cudaEventRecord(c->ev_in[k], hs)); CK(cudaStreamWaitEvent(st, c->ev_in[k], 0)); }
+            b.bgr = c->d_bgr; b.depth = c->d_depth; b.streaks = c->d_streaks; b.offsets = c->d_sub_offsets + (size_t)k * (F + 1);
+            c->scan_base[k] = sb; c->sub_n[k] = ns;
+            rr_frame_bufs saved = c->fb;
+            c->fb = sub_view(c, saved, f0, s0, sb);
+            c->fb.offsets = saved.offsets;
+            r = run_pipeline(c, nf, ns, S == 1);
+            rr_frame_bufs used = c->fb;
+            c->fb = saved;
+            (void)used;
+            if (r != RR_OK) return r;
+            sb += ns + 1;
+            cudaStream_t ds = S > 1 ? c->s_d2h : st;
+            if (S > 1) { CK(cudaEventRecord(c->ev_done[k], st)); CK(cudaStreamWaitEvent(ds, c->ev_done[k], 0)); }
+            if (out_bgr) CK(cudaMemcpyAsync(out_bgr + (size_t)f0 * np * 3, b.out_bgr + (size_t)f0 * np * 3, (size_t)nf * np * 3 * sizeof(float), cudaMemcpyDeviceToHost, ds));
+            if (out_mask) CK(cudaMemcpyAsync(out_mask + (size_t)f0 * np, b.out_mask + (size_t)f0 * np, (size_t)nf * np * sizeof(float), cudaMemcpyDeviceToHost, ds));
+            if (out_bgr_u8) CK(cudaMemcpyAsync(out_bgr_u8 + (size_t)f0 * np * 3, b.out_u8 + (size_t)f0 * np * 3, (size_t)nf * np * 3, cudaMemcpyDeviceToHost, ds));
+        }
+        c->n_sub_last = S;
+        c->last_n_streaks = n_streaks;
+        if (S > 1) { CK(cudaEventRecord(c->ev_out, c->s_d2h)); CK(cudaStreamWaitEvent(st, c->ev_out, 0)); }
         CK(cudaEventRecord(c->ev[RR_T_TOTAL], st));
         r = check_flag(c, attempt == 0);
-        if (r == RR_ERR_CAPACITY && attempt == 0 && c->fb.arena_cap > 0 && strstr(g_err, "grown")) continue;   // re-run once with the larger arena
+        if (r == RR_ERR_CAPACITY && attempt == 0 && strstr(g_err, "grown")) continue;   // re-run once with the larger arena
         break;
     }
-    finish_timings(c);
+    if (S == 1) finish_timings(c);
+    else {
+        memset(c->last_ms, 0, sizeof(c->last_ms));
+        float tot = 0;
+        if (cudaEventElapsedTime(&tot, c->ev[RR_T_H2D], c->ev[RR_T_TOTAL]) == cudaSuccess) c->last_ms[RR_T_TOTAL] = tot;
+    }
     return r;
 }
 
@@ -391,6 +475,8 @@ int rr_render_frames_device(rr_context *c, int n_frames, const uint8_t *d_bgr, c
     if (d_out_bgr) b.out_bgr = d_out_bgr;
     if (d_out_mask) b.out_mask = d_out_mask;
     if (d_out_bgr_u8) b.out_u8 = d_out_bgr_u8;
+    c->n_sub_last = 1; c->scan_base[0] = 0; c->sub_n[0] = n_streaks;
+    CK(cudaMemsetAsync(b.err_flag, 0, sizeof(int), st));
     r = run_pipeline(c, F, n_streaks, true);
     b.out_bgr = b_saved.out_bgr; b.out_mask = b_saved.out_mask; b.out_u8 = b_saved.out_u8;
     if (r != RR_OK) return r;
@@ -403,6 +489,7 @@ int rr_render_frames_device(rr_context *c, int n_frames, const uint8_t *d_bgr, c
             if (d_out_mask) b.out_mask = d_out_mask;
             if (d_out_bgr_u8) b.out_u8 = d_out_bgr_u8;
             CK(cudaEventRecord(c->ev[RR_T_H2D], st));
+            CK(cudaMemsetAsync(b.err_flag, 0, sizeof(int), st));
             r = run_pipeline(c, F, n_streaks, true);
             b.out_bgr = b_saved.out_bgr; b.out_mask = b_saved.out_mask; b.out_u8 = b_saved.out_u8;
             if (r != RR_OK) return r;

@@ -244,98 +244,127 @@ cudaError_t rr_launch_stats(const rr_frame_bufs &b, int F, int W, int H, cudaStr
 #define FOG_EW (FOG_TX + 2 * FOG_R)
 #define FOG_EH (FOG_TY + 2 * FOG_R)
 
-__global__ void __launch_bounds__(256) k_fog(rr_frame_bufs b, rr_fog_consts fc, int W, int H) {
+// Sliding-window separable passes: each thread produces RUN consecutive outputs from RUN+24 inputs
+// held in registers; every output still accumulates its 25 products in the reference order.
+template <int STRIDE_IN>
+__device__ __forceinline__ void fog_taps_f32(const float *in, double acc[4]) {
+    // 4 outputs along the direction of STRIDE_IN, exact float32 products in float64, ascending taps
+    double v[28];
+#pragma unroll
+    for (int i = 0; i < 28; i++) v[i] = (double)in[i * STRIDE_IN];
+#pragma unroll
+    for (int o = 0; o < 4; o++) {
+        double a = (double)c_k32[0] * v[o];
+#pragma unroll
+        for (int t = 1; t < 25; t++) a += (double)c_k32[t] * v[o + t];
+        acc[o] = a;
+    }
+}
+
+__global__ void __launch_bounds__(256, 2) k_fog(rr_frame_bufs b, rr_fog_consts fc, int W, int H) {
     extern __shared__ unsigned char smem_raw[];
-    float *E = (float *)smem_raw;                         // [FOG_EH][FOG_EW]
+    float *E = (float *)smem_raw;                         // [FOG_EH][FOG_EW]  extinction on the haloed tile
     float *FH = E + FOG_EH * FOG_EW;                      // [FOG_EH][FOG_TX]  float32 row pass of f_ext
-    double *LH = (double *)(FH + FOG_EH * FOG_TX);        // [FOG_EH][FOG_TX]  float64 row pass of one l_in channel
+    double *L = (double *)(FH + FOG_EH * FOG_TX);         // [FOG_EH][FOG_EW]  in-scattering of one channel
+    double *LH = L + FOG_EH * FOG_EW;                     // [FOG_EH][FOG_TX]  its float64 row pass
     const int f = blockIdx.z;
     const int x0 = blockIdx.x * FOG_TX, y0 = blockIdx.y * FOG_TY;
     const int tid = threadIdx.x;
     const float *depth = b.depth + (size_t)f * W * H;
     const uint8_t *bgr = b.bgr + (size_t)f * W * H * 3;
-    // -- extinction on the haloed tile (reflected coordinates)
     for (int i = tid; i < FOG_EH * FOG_EW; i += 256) {
         int ey = i / FOG_EW, ex = i - ey * FOG_EW;
         int gy = r101(y0 + ey - FOG_R, H), gx = r101(x0 + ex - FOG_R, W);
         float v = 0.f;
         if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-            float d = __fdiv_rn(depth[(size_t)gy * W + gx], 1000.f);
+            float d = __fdiv_rn(depth[(size_t)gy * W + gx], 1000.f);       // add_attenuation.py:48 (float32)
             float xx = __fmul_rn(fc.neg_beta32, d);
-            v = (float)exp((double)xx);                  // correctly rounded float32 exp ("canonical")
+            v = (float)exp((double)xx);                                     // correctly rounded float32 exp ("canonical")
         }
         E[i] = v;
     }
     __syncthreads();
-    // -- float32 row pass of f_ext: exact products, float64 accumulation ascending, one rounding
-    for (int i = tid; i < FOG_EH * FOG_TX; i += 256) {
-        int ey = i / FOG_TX, ox = i - ey * FOG_TX;
-        const float *row = E + ey * FOG_EW + ox;
-        double acc = (double)c_k32[0] * (double)row[0];
+    // float32 row pass of f_ext: 4 outputs per task
+    for (int i = tid; i < FOG_EH * (FOG_TX / 4); i += 256) {
+        int ey = i / (FOG_TX / 4), ox = (i - ey * (FOG_TX / 4)) * 4;
+        double a[4];
+        fog_taps_f32<1>(E + ey * FOG_EW + ox, a);
 #pragma unroll
-        for (int t = 1; t < 25; t++) acc += (double)c_k32[t] * (double)row[t];
-        FH[i] = (float)acc;
+        for (int o = 0; o < 4; o++) FH[ey * FOG_TX + ox + o] = (float)a[o];
     }
     __syncthreads();
+    // float32 column pass: thread = (column, block of 8 rows)
+    const int cx = tid & (FOG_TX - 1), cy0 = (tid / FOG_TX) * 8;
     float fb[8];
+    {
+        double a[4];
+        fog_taps_f32<FOG_TX>(FH + cy0 * FOG_TX + cx, a);
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        int i = tid + k * 256;
-        int oy = i / FOG_TX, ox = i - oy * FOG_TX;
-        const float *col = FH + oy * FOG_TX + ox;
-        double acc = (double)c_k32[0] * (double)col[0];
+        for (int o = 0; o < 4; o++) fb[o] = (float)a[o];
+        fog_taps_f32<FOG_TX>(FH + (cy0 + 4) * FOG_TX + cx, a);
 #pragma unroll
-        for (int t = 1; t < 25; t++) acc += (double)c_k32[t] * (double)col[t * FOG_TX];
-        fb[k] = (float)acc;
-        int gy = y0 + oy, gx = x0 + ox;
-        if (gy < H && gx < W && b.fblur) b.fblur[(size_t)f * W * H + (size_t)gy * W + gx] = fb[k];
+        for (int o = 0; o < 4; o++) fb[4 + o] = (float)a[o];
+    }
+    if (b.fblur) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            int gy = y0 + cy0 + k, gx = x0 + cx;
+            if (gy < H && gx < W) b.fblur[(size_t)f * W * H + (size_t)gy * W + gx] = fb[k];
+        }
     }
     const double npix = (double)W * (double)H;
     for (int c = 0; c < 3; c++) {
-        // E_c: mean irradiance of the un-fogged image (:53,70)
-        double sum_b = (double)b.chan_sum[f * 4 + c] / 255.0;
+        double sum_b = (double)b.chan_sum[f * 4 + c] / 255.0;                 // mean irradiance of the un-fogged image (:53,70)
         double irr_mean = ((fc.irr_scale_num * sum_b) / fc.irr_den) / npix;
         double Ac = fc.beta_hg * irr_mean;
         __syncthreads();
-        // float64 row pass (cv::RowFilter order: k[0]*x[0] + k[1]*x[1] + ...)
-        for (int i = tid; i < FOG_EH * FOG_TX; i += 256) {
-            int ey = i / FOG_TX, ox = i - ey * FOG_TX;
-            const float *row = E + ey * FOG_EW + ox;
-            double acc = 0;
-#pragma unroll
-            for (int t = 0; t < 25; t++) {
-                double li = Ac * (double)(1.0f - row[t]);           // (1 - f_ext) is a float32 op in numpy
-                li = li < 0 ? 0 : (li > 1 ? 1 : li);
-                double term = c_k64[t] * li;
-                acc = (t == 0) ? term : acc + term;
-            }
-            LH[i] = acc;
+        for (int i = tid; i < FOG_EH * FOG_EW; i += 256) {
+            double li = Ac * (double)(1.0f - E[i]);                           // (1 - f_ext) is a float32 op in numpy (:71)
+            L[i] = li < 0 ? 0 : (li > 1 ? 1 : li);                            // :72
         }
         __syncthreads();
-        // float64 column pass (cv::SymmColumnFilter order) + composition
+        // float64 row pass, cv::RowFilter order: k[0]*x[0] + k[1]*x[1] + ...
+        for (int i = tid; i < FOG_EH * (FOG_TX / 4); i += 256) {
+            int ey = i / (FOG_TX / 4), ox = (i - ey * (FOG_TX / 4)) * 4;
+            const double *row = L + ey * FOG_EW + ox;
+            double v[28];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            int i = tid + k * 256;
-            int oy = i / FOG_TX, ox = i - oy * FOG_TX;
-            int gy = y0 + oy, gx = x0 + ox;
-            const double *col = LH + (oy + FOG_R) * FOG_TX + ox;
-            double acc = c_k64[12] * col[0];
+            for (int k = 0; k < 28; k++) v[k] = row[k];
 #pragma unroll
-            for (int t = 1; t <= 12; t++) acc += c_k64[12 + t] * (col[t * FOG_TX] + col[-t * FOG_TX]);
-            if (gy < H && gx < W) {
-                size_t pix = (size_t)gy * W + gx;
-                double I = (double)bgr[pix * 3 + c] / 255.0;             // generator.py:352
-                double l = I * (double)fb[k] + acc;                      // :85
-                l = l < 0 ? 0 : (l > 1 ? 1 : l);
-                b.rainy[((size_t)f * 3 + c) * W * H + pix] = l;
-                b.bg8[((size_t)f * W * H + pix) * 3 + c] = (uint8_t)(l * 255);   // bad_weather.py:744
+            for (int o = 0; o < 4; o++) {
+                double a = c_k64[0] * v[o];
+#pragma unroll
+                for (int t = 1; t < 25; t++) a += c_k64[t] * v[o + t];
+                LH[ey * FOG_TX + ox + o] = a;
+            }
+        }
+        __syncthreads();
+        // float64 column pass, cv::SymmColumnFilter order: k[c]*x[0] + sum_t k[c+t]*(x[+t] + x[-t]); then compose
+        {
+            double v[32];
+#pragma unroll
+            for (int k = 0; k < 32; k++) v[k] = LH[(cy0 + k) * FOG_TX + cx];
+#pragma unroll
+            for (int o = 0; o < 8; o++) {
+                double acc = c_k64[12] * v[o + 12];
+#pragma unroll
+                for (int t = 1; t <= 12; t++) acc += c_k64[12 + t] * (v[o + 12 + t] + v[o + 12 - t]);
+                int gy = y0 + cy0 + o, gx = x0 + cx;
+                if (gy < H && gx < W) {
+                    size_t pix = (size_t)gy * W + gx;
+                    double I = (double)bgr[pix * 3 + c] / 255.0;             // generator.py:352
+                    double l = I * (double)fb[o] + acc;                      // :85
+                    l = l < 0 ? 0 : (l > 1 ? 1 : l);
+                    b.rainy[((size_t)f * 3 + c) * W * H + pix] = l;
+                    b.bg8[((size_t)f * W * H + pix) * 3 + c] = (uint8_t)(l * 255);   // bad_weather.py:744
+                }
             }
         }
     }
 }
 
 cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, cudaStream_t st) {
-    size_t smem = sizeof(float) * (FOG_EH * FOG_EW + FOG_EH * FOG_TX) + sizeof(double) * FOG_EH * FOG_TX;
+    size_t smem = sizeof(float) * (FOG_EH * FOG_EW + FOG_EH * FOG_TX) + sizeof(double) * (FOG_EH * FOG_EW + FOG_EH * FOG_TX);
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_fog, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -458,25 +487,32 @@ __global__ void __launch_bounds__(256) k_env_prefix(const uint8_t *env8, const d
         if (!(y == y)) y = 0;
         sx += x * om[c]; sy += y * om[c]; sY += Y * om[c];
     }
-    __shared__ double tx[256], ty[256], tY[256];
-    tx[threadIdx.x] = sx; ty[threadIdx.x] = sy; tY[threadIdx.x] = sY;
-    __syncthreads();
-    if (threadIdx.x == 0) {          // serial exclusive scan of 256 thread totals: deterministic
-        double ax = 0, ay = 0, aY = 0;
-        for (int t = 0; t < 256; t++) {
-            double vx = tx[t], vy = ty[t], vY = tY[t];
-            tx[t] = ax; ty[t] = ay; tY[t] = aY;
-            ax += vx; ay += vy; aY += vY;
-        }
-        size_t base = ((size_t)f * 3 * H + r) * (W_env + 1);
-        pref[base + W_env] = ax;
-        pref[base + (size_t)H * (W_env + 1) + W_env] = ay;
-        pref[base + 2 * (size_t)H * (W_env + 1) + W_env] = aY;
-        rowtot[(size_t)f * H + r] = aY;
+    // block-wide exclusive scan of the 256 thread totals: warp shuffles + one pass over the 8 warp
+    // totals (a fixed tree, hence deterministic)
+    __shared__ double wtot[3][8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double ix = sx, iy = sy, iY = sY;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double ux = __shfl_up_sync(0xffffffffu, ix, o), uy = __shfl_up_sync(0xffffffffu, iy, o), uY = __shfl_up_sync(0xffffffffu, iY, o);
+        if (lane >= o) { ix += ux; iy += uy; iY += uY; }
     }
+    if (lane == 31) { wtot[0][warp] = ix; wtot[1][warp] = iy; wtot[2][warp] = iY; }
     __syncthreads();
-    double ax = tx[threadIdx.x], ay = ty[threadIdx.x], aY = tY[threadIdx.x];
+    double ox = 0, oy = 0, oY = 0, allx = 0, ally = 0, allY = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        if (k == warp) { ox = allx; oy = ally; oY = allY; }
+        allx += wtot[0][k]; ally += wtot[1][k]; allY += wtot[2][k];
+    }
+    double ax = ox + (ix - sx), ay = oy + (iy - sy), aY = oY + (iY - sY);   // exclusive prefix of this thread
     size_t base = ((size_t)f * 3 * H + r) * (W_env + 1);
+    if (threadIdx.x == 0) {
+        pref[base + W_env] = allx;
+        pref[base + (size_t)H * (W_env + 1) + W_env] = ally;
+        pref[base + 2 * (size_t)H * (W_env + 1) + W_env] = allY;
+        rowtot[(size_t)f * H + r] = allY;
+    }
     double *px = pref + base, *py = px + (size_t)H * (W_env + 1), *pY = py + (size_t)H * (W_env + 1);
     for (int c = c0; c < c1; c++) {
         double bb = (double)row[c * 3] / 255.0, gg = (double)row[c * 3 + 1] / 255.0, rr = (double)row[c * 3 + 2] / 255.0;
@@ -522,6 +558,7 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(rr_frame_bufs b, rr_
                                                              int n_streaks) {
     __shared__ rr_fcp s_fcp[SETUP_WARPS];
     __shared__ int s_npts[SETUP_WARPS];
+    __shared__ double s_az[SETUP_WARPS][RR_FOV_N], s_px[SETUP_WARPS][RR_MAX_POLY], s_py[SETUP_WARPS][RR_MAX_POLY];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int s = blockIdx.x * SETUP_WARPS + warp;
     if (s >= n_streaks) return;
@@ -532,13 +569,23 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(rr_frame_bufs b, rr_
     const rr_streak_rec rec = b.streaks[s];
     rr_fcp &fc = s_fcp[warp];
     const int rows = cam.H_env, cols = cam.W_env;
-    if (lane == 0) {
-        double px[RR_MAX_POLY], py[RR_MAX_POLY];
-        int n = rr_fov_polygon(rec, cam.radius, cam.fov_deg, rows, cols, px, py);
-        int m = n > 0 ? rr_clip_fov_polygon(px, py, n, cols, rows, fc.vx, fc.vy) : 0;
-        fc.npts = m;
-        if (m > 0) rr_fcp_prepare(fc, cols, rows);
-        s_npts[warp] = m;
+    {
+        // the 20 rays of the view cone, one per lane
+        rr_fov_ctx fctx;
+        rr_fov_begin(rec, cam.fov_deg, fctx);
+        double az = 0, rx = 0, ry = 0;
+        bool ok = fctx.ok;
+        if (lane < RR_FOV_N) ok = rr_fov_ray(fctx, lane, cam.radius, rows, cols, &az, &rx, &ry) && ok;
+        if (lane < RR_FOV_N) { s_az[warp][lane] = az; s_px[warp][lane] = rx; s_py[warp][lane] = ry; }
+        unsigned good = __ballot_sync(0xffffffffu, ok || lane >= RR_FOV_N);
+        __syncwarp();
+        if (lane == 0) {
+            int n = good == 0xffffffffu ? rr_fov_finish(s_az[warp], s_px[warp], s_py[warp], rows, cols) : 0;
+            int m = n > 0 ? rr_clip_fov_polygon(s_px[warp], s_py[warp], n, cols, rows, fc.vx, fc.vy) : 0;
+            fc.npts = m;
+            if (m > 0) rr_fcp_prepare(fc, cols, rows);
+            s_npts[warp] = m;
+        }
     }
     __syncwarp();
     int m = s_npts[warp];
@@ -841,8 +888,17 @@ cudaError_t rr_launch_raster(const rr_frame_bufs &b, const rr_static_tabs &t, co
 // up to float64 rounding (DESIGN.md "linear tint").
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void load_weights(double sigma, int r, double *w) {
-    // all threads of the block call this; w in shared memory
-    if (threadIdx.x == 0) rr_gauss_weights(sigma, r, w);
+    // rr_gauss_weights (SciPy _gaussian_kernel1d) with the exponentials spread over the block; the
+    // normalising sum keeps numpy's order.  All threads of the block call this; w in shared memory.
+    __shared__ double s_norm;
+    const int n = 2 * r + 1;
+    const double f = -0.5 / (sigma * sigma);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) w[i] = exp(f * (double)((i - r) * (i - r)));
+    __syncthreads();
+    if (threadIdx.x == 0) s_norm = rr_np_sum_small(w, n);
+    __syncthreads();
+    const double sn = s_norm;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) w[i] = w[i] / sn;
     __syncthreads();
 }
 

@@ -37,66 +37,74 @@ RR_HD void rr_vecmat(const double v[3], const double M[9], double out[3]) {
     for (int j = 0; j < 3; j++) out[j] = (v[0] * M[j] + v[1] * M[3 + j]) + v[2] * M[6 + j];
 }
 
-// -> number of polygon vertices (20 or 24), 0 when the reference would raise / produce NaNs
-RR_HD int rr_fov_polygon(const rr_streak_rec &s, double radius, double fov_deg, int rows, int cols,
-                         double *px, double *py) {
-    const int N = 20;
-    double P[3];
+// The cone is evaluated in three steps so that a warp can spread the 20 rays over its lanes
+// (k_setup) while the host build runs them in sequence -- same arithmetic either way.
+struct rr_fov_ctx { double P[3], n[3], v[3]; int ok; };
+#define RR_FOV_N 20
+
+RR_HD void rr_fov_begin(const rr_streak_rec &s, double fov_deg, rr_fov_ctx &c) {
+    double *P = c.P, *n = c.n;
     P[0] = (s.wp1[0] + s.wp2[0]) / 2;
     P[2] = (s.wp1[1] + s.wp2[1]) / 2;    // y <-> z swap (bad_weather.py:599)
     P[1] = (s.wp1[2] + s.wp2[2]) / 2;
     double nrm = sqrt((P[0] * P[0] + P[1] * P[1]) + P[2] * P[2]);
-    double n[3] = {P[0] / nrm, P[1] / nrm, P[2] / nrm};
+    n[0] = P[0] / nrm; n[1] = P[1] / nrm; n[2] = P[2] / nrm;
     double theta = (fov_deg / 2) * (RR_PI / 180.0);
-    double a = n[0], b = n[1], c = n[2];
+    double a = n[0], b = n[1], cc = n[2];
     double d = (P[0] * n[0] + P[1] * n[1]) + P[2] * n[2];
     if (b == 0) b = 0.001;
     double qx = P[1];
     double qz = 0;
-    double qy = (-a * qx + d - c * qz) / b;
+    double qy = (-a * qx + d - cc * qz) / b;
     double dq[3] = {P[0] - qx, P[1] - qy, P[2] - qz};
     double dn = sqrt((dq[0] * dq[0] + dq[1] * dq[1]) + dq[2] * dq[2]);
     double u[3] = {dq[0] / dn, dq[1] / dn, dq[2] / dn};
-    if (!(u[0] == u[0]) || !(u[1] == u[1]) || !(u[2] == u[2])) return 0;    // assert ~isnan(u)
+    c.ok = (u[0] == u[0]) && (u[1] == u[1]) && (u[2] == u[2]);            // assert ~isnan(u)
     double rv[3] = {u[1] * n[2] - u[2] * n[1], u[2] * n[0] - u[0] * n[2], u[0] * n[1] - u[1] * n[0]};
-    double R[9], v[3];
+    double R[9];
     rr_rotation_matrix(rv, -theta, R);
-    rr_vecmat(n, R, v);
-    double az[N + 1];
+    rr_vecmat(n, R, c.v);
+}
+
+// ray k of the cone -> azimuth (image encoding) and env-map pixel coordinates; false on NaN
+RR_HD bool rr_fov_ray(const rr_fov_ctx &c, int k, double radius, int rows, int cols, double *az, double *px, double *py) {
     const double two_pi = 2 * RR_PI;
-    const double step = two_pi / N;
-    for (int k = 0; k < N; k++) {
-        double ang = 0 + k * step;
-        double M[9], dv[3];
-        rr_rotation_matrix(n, ang, M);
-        rr_vecmat(v, M, dv);
-        double qa = dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2];
-        double qb = 2 * dv[0] * P[0] + 2 * dv[1] * P[1] + 2 * dv[2] * P[2];
-        double qc = P[0] * P[0] + P[1] * P[1] + P[2] * P[2] - radius * radius;
-        double disc = qb * qb - 4 * qa * qc;
-        double t1 = (-qb + sqrt(disc)) / (2 * qa);
-        double x = P[0] + t1 * dv[0], y = P[1] + t1 * dv[1], z = P[2] + t1 * dv[2];
-        double el = atan2(z, sqrt(x * x + y * y));
-        double azv = atan2(y, x);
-        if (azv < 0) azv += two_pi;
-        if (el < 0) el += two_pi;
-        if (azv > two_pi) azv -= two_pi;
-        if (el > two_pi) el -= two_pi;
-        azv = ((two_pi - azv) - RR_PI / 2);
-        azv = rr_pymod(azv, two_pi);
-        double uu = azv / two_pi;
-        el = el + RR_PI / 2;
-        el = rr_pymod(el, two_pi);
-        double vv = 1. - el / RR_PI;
-        az[k] = azv;
-        px[k] = uu * cols;
-        py[k] = vv * rows;
-        if (!(px[k] == px[k]) || !(py[k] == py[k])) return 0;
-    }
-    az[N] = az[0];
+    const double step = two_pi / RR_FOV_N;
+    const double *P = c.P;
+    double ang = 0 + k * step;
+    double M[9], dv[3];
+    rr_rotation_matrix(c.n, ang, M);
+    rr_vecmat(c.v, M, dv);
+    double qa = dv[0] * dv[0] + dv[1] * dv[1] + dv[2] * dv[2];
+    double qb = 2 * dv[0] * P[0] + 2 * dv[1] * P[1] + 2 * dv[2] * P[2];
+    double qc = P[0] * P[0] + P[1] * P[1] + P[2] * P[2] - radius * radius;
+    double disc = qb * qb - 4 * qa * qc;
+    double t1 = (-qb + sqrt(disc)) / (2 * qa);
+    double x = P[0] + t1 * dv[0], y = P[1] + t1 * dv[1], z = P[2] + t1 * dv[2];
+    double el = atan2(z, sqrt(x * x + y * y));
+    double azv = atan2(y, x);
+    if (azv < 0) azv += two_pi;
+    if (el < 0) el += two_pi;
+    if (azv > two_pi) azv -= two_pi;
+    if (el > two_pi) el -= two_pi;
+    azv = ((two_pi - azv) - RR_PI / 2);
+    azv = rr_pymod(azv, two_pi);
+    double uu = azv / two_pi;
+    el = el + RR_PI / 2;
+    el = rr_pymod(el, two_pi);
+    double vv = 1. - el / RR_PI;
+    *az = azv;
+    *px = uu * cols;
+    *py = vv * rows;
+    return (*px == *px) && (*py == *py);
+}
+
+// wrap detection and corner splice (bad_weather.py:667-695); az has RR_FOV_N entries; -> 20, 24 or 0
+RR_HD int rr_fov_finish(const double *azin, double *px, double *py, int rows, int cols) {
+    const int N = RR_FOV_N;
     int count_true = 0, count_false = 0, pos_true = -1, pos_false = -1;
     for (int k = 0; k < N; k++) {
-        double df = az[k + 1] - az[k];
+        double df = azin[(k + 1) % N] - azin[k];
         bool cond = (fabs(df) <= 1e-8) || (df < 0);      // np.isclose(diff, 0) | (diff < 0)
         if (cond) { count_true++; if (pos_true < 0) pos_true = k; }
         else { count_false++; if (pos_false < 0) pos_false = k; }
@@ -124,6 +132,18 @@ RR_HD int rr_fov_polygon(const rr_streak_rec &s, double radius, double fov_deg, 
     px[pos + 3] = c2x; py[pos + 3] = c2y;
     px[pos + 4] = c3x; py[pos + 4] = c3y;
     return N + 4;
+}
+
+// -> number of polygon vertices (20 or 24), 0 when the reference would raise / produce NaNs
+RR_HD int rr_fov_polygon(const rr_streak_rec &s, double radius, double fov_deg, int rows, int cols,
+                         double *px, double *py) {
+    rr_fov_ctx c;
+    rr_fov_begin(s, fov_deg, c);
+    if (!c.ok) return 0;
+    double az[RR_FOV_N];
+    for (int k = 0; k < RR_FOV_N; k++)
+        if (!rr_fov_ray(c, k, radius, rows, cols, &az[k], &px[k], &py[k])) return 0;
+    return rr_fov_finish(az, px, py, rows, cols);
 }
 
 // ---- Clipper restated for "polygon /\ rectangle (0,0)-(cols,rows)", see oracle/clipper_rect.py ----
