@@ -134,6 +134,42 @@ int rr_streak_photometry_only(rr_context *ctx, const uint8_t *env_bgr_u8, int n_
  * grid, computed on the device; out is a HOST buffer of H_env*W_env float64. */
 int rr_solid_angles(rr_context *ctx, int H_env, int W_env, double *out);
 
+/* ---- on-the-fly particle simulation --------------------------------
+ * B200-native stand-in for the closed AHLSimulation binary the reference drives through pexpect
+ * (tools/simulation.py:259-469): Marshall-Palmer drop sizes, the binary's drag / gravity integrator
+ * (semi-implicit Euler at sim_hz with the raindrop drag law recovered from its rodata), pinhole
+ * shutter-open / shutter-close imaging and field-of-view culling.  Statistical parity only: the
+ * binary cannot run here and its RNG is not reproducible.  One call produces the
+ * imaged streaks of n_frames camera frames with the attributes of the simulator's XML <r> element
+ * (common/bad_weather.py:200-211 reads exactly these). */
+typedef struct rr_sim_params {
+    int32_t W, H;            /* sensor size in px (full resolution, before render_scale)  */
+    double focal_m;          /* cam_focal / 1000                                           */
+    double pix_size_m;       /* cam_CCD_pixsize * 1e-6                                     */
+    double exposure_ms;      /* cam_exposure                                               */
+    double fallrate_mmh;     /* rain intensity                                             */
+    double sim_hz;           /* integrator frequency, 2000 (common/db.py:64)               */
+    double cam_speed_kmh;    /* forward camera motion (sim_steps["cam_motion"])            */
+    double z_near, z_far;    /* visibility range in metres                                 */
+    double d_min_mm, d_max_mm; /* drop size limits, 0.1 .. 10                              */
+    double min_width_px;     /* drops narrower than this everywhere in range are not sampled */
+    uint64_t seed;
+} rr_sim_params;
+
+typedef struct rr_sim_streak {  /* one <r .../> of the simulator XML, 120 bytes               */
+    double wp1[3], wp2[3];   /* world start / end (camera relative, z negative forward)    */
+    double wd1, wd2;         /* diameter in metres                                         */
+    double ip1[2], ip2[2];   /* image start / end in px, y UP (the loader flips it)        */
+    double iw1, iw2;         /* image width in px                                          */
+    int64_t pid;
+} rr_sim_streak;
+
+/* out: capacity max_per_frame records per frame; counts[f] = records produced for frame f (the
+ * expected count is returned through expected_per_frame when not NULL).  Frame f of the call is
+ * simulated for absolute frame index first_frame + f: the result depends only on (seed, index). */
+int rr_simulate_particles(rr_context *ctx, const rr_sim_params *p, int64_t first_frame, int n_frames,
+                          int max_per_frame, rr_sim_streak *out, int32_t *counts, double *expected_per_frame);
+
 int rr_debug_read(rr_context *ctx, int what, int frame, void *dst, size_t bytes);
 int rr_timings(rr_context *ctx, float *ms_per_stage /* RR_T_COUNT */);
 int rr_kernel_launches(rr_context *ctx, long long *count);   /* kernels launched since rr_create */
@@ -148,6 +184,9 @@ int rr_host_free(void *ptr);
  * for non-Big streaks, normal(0, noise_std) * noise_scale (generator.py:136). */
 int rr_host_draw_randoms(uint32_t seed, int n, const uint8_t *types, const int32_t *buckets, double noise_std,
                          double noise_scale, uint8_t *tex_idx, double *noise_deg);
+/* The simulator's force model evaluated on the host (CPU test-suite): terminal velocity solving
+ * m g = F_drag(v), the drag at that speed and the drop mass. */
+void rr_host_sim_physics(double D_m, double *v_terminal, double *drag_at_vt, double *mass);
 /* The OpenCV Gaussian kernels baked into the library (for the CPU test-suite). */
 void rr_host_tables(double *k64_25, float *k32_25, int *k15_fixed);
 int rr_synchronize(rr_context *ctx);

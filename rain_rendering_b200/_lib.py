@@ -25,6 +25,14 @@ class Camera(C.Structure):
                 ("opacity_att", C.c_double), ("fallrate_mmh", C.c_double)]
 
 
+class SimParams(C.Structure):
+    """rr_sim_params"""
+    _fields_ = [("W", C.c_int32), ("H", C.c_int32), ("focal_m", C.c_double), ("pix_size_m", C.c_double), ("exposure_ms", C.c_double),
+                ("fallrate_mmh", C.c_double), ("sim_hz", C.c_double), ("cam_speed_kmh", C.c_double), ("z_near", C.c_double),
+                ("z_far", C.c_double), ("d_min_mm", C.c_double), ("d_max_mm", C.c_double), ("min_width_px", C.c_double),
+                ("seed", C.c_uint64)]
+
+
 # rr_plan (csrc/rr_types.h) as a numpy dtype, for the stage parity tests
 PLAN_DTYPE = np.dtype([
     ("valid", "<i4"), ("type", "<i4"), ("pw", "<i4"), ("ph", "<i4"), ("minx", "<i4"), ("miny", "<i4"),
@@ -72,6 +80,7 @@ def load() -> C.CDLL:
         "rr_streak_photometry_only": [vp, u8p, C.c_int, vp, f64p],
         "rr_debug_read": [vp, C.c_int, C.c_int, vp, C.c_size_t],
         "rr_solid_angles": [vp, C.c_int, C.c_int, f64p],
+        "rr_simulate_particles": [vp, C.POINTER(SimParams), C.c_int64, C.c_int, C.c_int, vp, i32p, C.POINTER(C.c_double)],
         "rr_timings": [vp, f32p],
         "rr_kernel_launches": [vp, C.POINTER(C.c_longlong)],
         "rr_stream": [vp, C.POINTER(vp)],
@@ -86,6 +95,8 @@ def load() -> C.CDLL:
         fn.restype = C.c_int
     lib.rr_host_tables.argtypes = [f64p, f32p, i32p]
     lib.rr_host_tables.restype = None
+    lib.rr_host_sim_physics.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    lib.rr_host_sim_physics.restype = None
     _lib = lib
     return lib
 

@@ -169,6 +169,26 @@ class RainContext:
         _lib.check(self.lib.rr_debug_read(self.h, _lib.DBG[what], frame, _lib.ptr(out), out.nbytes), "rr_debug_read")
         return out
 
+    # -- on-the-fly particle simulation (stand-in for the closed AHLSimulation binary) ------------
+    def simulate_particles(self, first_frame, n_frames, W, H, fallrate, focal_mm=6.0, pix_size_um=4.65, exposure_ms=2.0,
+                           sim_hz=2000.0, cam_speed_kmh=0.0, z_near=0.25, z_far=15.0, d_min_mm=0.1, d_max_mm=10.0,
+                           min_width_px=1.0, seed=0, max_per_frame=None):
+        """-> (list of SIM_STREAK_DTYPE arrays (one per frame, pid order), expected candidates per frame)."""
+        from .streaks import SIM_STREAK_DTYPE
+        p = _lib.SimParams(int(W), int(H), focal_mm / 1000., pix_size_um * 1e-6, float(exposure_ms), float(fallrate), float(sim_hz),
+                           float(cam_speed_kmh), float(z_near), float(z_far), float(d_min_mm), float(d_max_mm), float(min_width_px), int(seed))
+        exp = C.c_double(0)
+        cap = int(max_per_frame or 1 << 16)
+        out = np.zeros((n_frames, cap), SIM_STREAK_DTYPE)
+        counts = np.zeros(n_frames, np.int32)
+        _lib.check(self.lib.rr_simulate_particles(self.h, C.byref(p), int(first_frame), int(n_frames), cap, _lib.ptr(out), _lib.ptr(counts),
+                                                  C.byref(exp)), "rr_simulate_particles")
+        frames = []
+        for f in range(n_frames):
+            r = out[f, :counts[f]]
+            frames.append(r[np.argsort(r["pid"], kind="stable")].copy())
+        return frames, exp.value
+
     def timings(self):
         ms = np.zeros(len(_lib.T_NAMES), np.float32)
         _lib.check(self.lib.rr_timings(self.h, _lib.ptr(ms)), "rr_timings")

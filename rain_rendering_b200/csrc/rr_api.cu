@@ -80,7 +80,9 @@ static void free_camera(rr_context *c) {
 
 extern "C" {
 
-int rr_version(void) { return 100; }
+int rr_version(void) { return 101; }
+int rr_sim_device_of(rr_context *c) { return c ? c->device : 0; }
+void rr_set_error(const char *msg) { set_err("%s", msg); }
 const char *rr_last_error(void) { return g_err; }
 
 int rr_create(int device_id, rr_context **out) {

@@ -31,6 +31,43 @@ def _vec(attr: str):
     return [float(t) for t in attr[1:-1].split(";")]
 
 
+def records_from_raw(wp1, wp2, ip1, ip2, iw1, iw2, pid, render_scale: int, W: int, H: int) -> np.ndarray:
+    """Simulator-convention arrays (image y up, world z negative forward, full sensor resolution) ->
+    STREAK_DTYPE records, restricted to ``max_width >= 1 and length >= 1``: the arithmetic of
+    DBManager.load_streaks_from_xml (bad_weather.py:208-238), vectorised."""
+    n = len(pid)
+    rec = np.zeros(n, dtype=STREAK_DTYPE)
+    if n == 0:
+        return rec
+    wp1 = np.array(wp1, dtype=np.float64)
+    wp2 = np.array(wp2, dtype=np.float64)
+    ip1 = np.array(ip1, dtype=np.float64) / render_scale        # :208-209
+    ip2 = np.array(ip2, dtype=np.float64) / render_scale
+    iw1 = np.array(iw1, dtype=np.float64) / render_scale        # :210-211
+    iw2 = np.array(iw2, dtype=np.float64) / render_scale
+    ip1[:, 1] = H - ip1[:, 1]                                    # :221-222
+    ip2[:, 1] = H - ip2[:, 1]
+    wp1[:, 2] *= -1                                              # :223-224
+    wp2[:, 2] *= -1
+    diff = np.abs(ip1 - ip2)
+    max_width = np.maximum(iw1, iw2).astype(np.int64)            # :226 int() truncation
+    with np.errstate(divide="ignore", invalid="ignore"):
+        nrm = np.sqrt(diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1])
+        cos_theta = 0 * (diff[:, 0] / nrm) + -1 * (-(diff[:, 1] / nrm))          # :228-231
+        ratio = max_width / (diff[:, 1] / cos_theta)                             # :232-233
+    ip1r = np.round(ip1).astype(np.int64)                        # :234-235 (half-even)
+    ip2r = np.round(ip2).astype(np.int64)
+    d = (ip1r - ip2r).astype(np.float64)
+    length = np.ceil(np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1])).astype(np.int64)   # :236
+    rec["wp1"], rec["wp2"], rec["iw1"], rec["iw2"] = wp1, wp2, iw1, iw2
+    rec["ratio"] = ratio
+    rec["ip1"], rec["ip2"], rec["ip1m"], rec["ip2m"] = ip1r, ip2r, ip1r, ip2r
+    rec["max_width"], rec["length"] = max_width, length
+    rec["pid"] = np.asarray(pid)
+    rec["type"] = np.where(max_width >= 4, BIG, np.where(max_width > 1, MEDIUM, SMALL))   # :99-106
+    return rec[(max_width >= 1) & (length >= 1)]
+
+
 def load_streaks_from_xml(path: str, render_scale: int, W: int, H: int):
     """-> list (one entry per simulator frame, XML order) of STREAK_DTYPE arrays in XML order,
     already restricted to ``max_width >= 1 and length >= 1`` (bad_weather.py:238).  A later
@@ -43,39 +80,23 @@ def load_streaks_from_xml(path: str, render_scale: int, W: int, H: int):
             a = drop.attrib
             rows[int(a["pid"])] = (_vec(a["wp1"]), _vec(a["wp2"]), _vec(a["ip1"]), _vec(a["ip2"]),
                                    float(a["iw1"]), float(a["iw2"]), int(a["pid"]))
-        n = len(rows)
-        rec = np.zeros(n, dtype=STREAK_DTYPE)
-        if n:
-            vals = list(rows.values())
-            wp1 = np.array([v[0] for v in vals], dtype=np.float64)
-            wp2 = np.array([v[1] for v in vals], dtype=np.float64)
-            ip1 = np.array([v[2] for v in vals], dtype=np.float64) / render_scale        # :208-209
-            ip2 = np.array([v[3] for v in vals], dtype=np.float64) / render_scale
-            iw1 = np.array([v[4] for v in vals], dtype=np.float64) / render_scale        # :210-211
-            iw2 = np.array([v[5] for v in vals], dtype=np.float64) / render_scale
-            ip1[:, 1] = H - ip1[:, 1]                                                    # :221-222
-            ip2[:, 1] = H - ip2[:, 1]
-            wp1[:, 2] *= -1                                                              # :223-224
-            wp2[:, 2] *= -1
-            diff = np.abs(ip1 - ip2)
-            max_width = np.maximum(iw1, iw2).astype(np.int64)                            # :226 int() truncation
-            with np.errstate(divide="ignore", invalid="ignore"):
-                nrm = np.sqrt(diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1])
-                cos_theta = 0 * (diff[:, 0] / nrm) + -1 * (-(diff[:, 1] / nrm))          # :228-231
-                ratio = max_width / (diff[:, 1] / cos_theta)                             # :232-233
-            ip1r = np.round(ip1).astype(np.int64)                                        # :234-235 (half-even)
-            ip2r = np.round(ip2).astype(np.int64)
-            d = (ip1r - ip2r).astype(np.float64)
-            length = np.ceil(np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1])).astype(np.int64)   # :236
-            rec["wp1"], rec["wp2"], rec["iw1"], rec["iw2"] = wp1, wp2, iw1, iw2
-            rec["ratio"] = ratio
-            rec["ip1"], rec["ip2"], rec["ip1m"], rec["ip2m"] = ip1r, ip2r, ip1r, ip2r
-            rec["max_width"], rec["length"] = max_width, length
-            rec["pid"] = np.array([v[6] for v in vals])
-            rec["type"] = np.where(max_width >= 4, BIG, np.where(max_width > 1, MEDIUM, SMALL))   # :99-106
-            rec = rec[(max_width >= 1) & (length >= 1)]
-        frames.append(rec)
+        vals = list(rows.values())
+        frames.append(records_from_raw([v[0] for v in vals], [v[1] for v in vals], [v[2] for v in vals], [v[3] for v in vals],
+                                       [v[4] for v in vals], [v[5] for v in vals], [v[6] for v in vals], render_scale, W, H)
+                      if vals else np.zeros(0, dtype=STREAK_DTYPE))
     return frames
+
+
+SIM_STREAK_DTYPE = np.dtype([("wp1", "<f8", 3), ("wp2", "<f8", 3), ("wd1", "<f8"), ("wd2", "<f8"), ("ip1", "<f8", 2), ("ip2", "<f8", 2),
+                             ("iw1", "<f8"), ("iw2", "<f8"), ("pid", "<i8")])
+assert SIM_STREAK_DTYPE.itemsize == 120
+
+
+def records_from_sim(sim: np.ndarray, render_scale: int, W: int, H: int) -> np.ndarray:
+    """rr_simulate_particles output of one frame (SIM_STREAK_DTYPE, any order) -> records, in pid
+    order (the device appends with an atomic counter; sorting makes the frame deterministic)."""
+    sim = sim[np.argsort(sim["pid"], kind="stable")]
+    return records_from_raw(sim["wp1"], sim["wp2"], sim["ip1"], sim["ip2"], sim["iw1"], sim["iw2"], sim["pid"], render_scale, W, H)
 
 
 def in_frame(rec: np.ndarray, W: int, H: int) -> np.ndarray:
