@@ -176,6 +176,7 @@ static int ensure_streak_cap(rr_context *c, int n) {
     int cap = n + n / 4 + 1024;
     CK(dev_alloc(c, &c->d_streaks, (size_t)cap));
     CK(dev_alloc(c, &c->fb.plans, (size_t)cap));
+    CK(dev_alloc(c, &c->fb.sizes, (size_t)cap));
     CK(dev_alloc(c, &c->fb.scan, (size_t)(cap + 1 + RR_MAX_SUB) * 6));
     c->streak_cap = cap;
     return RR_OK;
@@ -183,7 +184,7 @@ static int ensure_streak_cap(rr_context *c, int n) {
 
 int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
     if (!c || !cam || max_batch <= 0) { set_err("rr_set_camera: bad arguments"); return RR_ERR_ARG; }
-    if (cam->W < 32 || cam->H < 32 || cam->W > 16384 || cam->H > 16384) { set_err("rr_set_camera: unsupported size %dx%d", cam->W, cam->H); return RR_ERR_ARG; }
+    if (cam->W < 32 || cam->H < 32 || cam->W > 8192 || cam->H > 8192) { set_err("rr_set_camera: unsupported size %dx%d", cam->W, cam->H); return RR_ERR_ARG; }
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     free_camera(c);
@@ -200,6 +201,7 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
     c->H_env = H;
     c->W_env = c->cyl_w + 2 * (c->cyl_w / 2);
     const int He = c->H_env, We = c->W_env;
+    if (We > 3072) { set_err("rr_set_camera: environment map width %d exceeds the supported 3072", We); return RR_ERR_ARG; }
     rr_cam_dev &d = c->camd;
     d.W = W; d.H = H; d.H_env = He; d.W_env = We;
     d.focal_m = cam->focal_m; d.f_number = cam->f_number; d.focus_plane = cam->focus_plane_m; d.pix_size = cam->pix_size_m;
@@ -245,7 +247,7 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
     CK(dev_alloc(c, &b.fblur, F * np));
     CK(dev_alloc(c, &b.env_fill, F * npe * 3));
     CK(dev_alloc(c, &b.env8, F * npe * 3));
-    CK(dev_alloc(c, &b.pref, F * 3 * (size_t)He * (We + 1)));
+    CK(dev_alloc(c, &b.pref, F * 4 * (size_t)He * (We + 1)));
     CK(dev_alloc(c, &b.rowtot, F * He));
     CK(dev_alloc(c, &b.ambient, F));
     CK(dev_alloc(c, &b.err_flag, (size_t)1));
@@ -326,8 +328,8 @@ static rr_frame_bufs sub_view(const rr_context *c, const rr_frame_bufs &b, int f
     v.bgr += (size_t)f0 * np * 3; v.depth += (size_t)f0 * np; v.streaks += s0;
     v.chan_sum += (size_t)f0 * 4; v.rainy += (size_t)f0 * 3 * np; v.bg8 += (size_t)f0 * np * 3; v.fblur += (size_t)f0 * np;
     v.env_fill += (size_t)f0 * npe * 3; v.env8 += (size_t)f0 * npe * 3;
-    v.pref += (size_t)f0 * 3 * c->H_env * (c->W_env + 1); v.rowtot += (size_t)f0 * c->H_env; v.ambient += f0;
-    v.plans += s0; v.scan += (size_t)scan_base * 6;
+    v.pref += (size_t)f0 * 4 * c->H_env * (c->W_env + 1); v.rowtot += (size_t)f0 * c->H_env; v.ambient += f0;
+    v.plans += s0; v.sizes += s0; v.scan += (size_t)scan_base * 6;
     v.tile_sum += (size_t)f0 * tiles; v.frame_mean += f0;
     if (v.out_bgr) v.out_bgr += (size_t)f0 * np * 3;
     if (v.out_mask) v.out_mask += (size_t)f0 * np;

@@ -541,33 +541,32 @@ RR_HD bool rr_fcp_side_x(const rr_fcp &f, int i, int y, int64_t *x) {
     return true;
 }
 
-// Bresenham (8-connected LineIterator) columns of edge k on row y: [a, b], false if none
+// Bresenham (8-connected LineIterator) columns of edge k on row y: [a, b], false if none.
+// Coordinates are below 2^14 (rr_set_camera enforces it), so 2*dx*t fits in 32 bits.
 RR_HD bool rr_line_row(int x0, int y0, int x1, int y1, int y, int *a, int *b) {
     int dx = x1 - x0;            // >= 0 (left to right)
     int dy = y1 - y0;
     int sy = dy < 0 ? -1 : 1;
     int ady = dy < 0 ? -dy : dy;
+    int t = (y - y0) * sy;
+    if (t < 0 || t > ady) return false;
     if (ady > dx) {
-        // y major: one pixel per row
-        int j = (y - y0) * sy;
-        if (j < 0 || j > ady) return false;
-        int m = dx == 0 ? 0 : (int)(((int64_t)2 * dx * j + ady - 1) / ((int64_t)2 * ady));
+        // y major: one pixel per row, minor offset after j steps is floor((2*dx*j + ady - 1) / (2*ady))
+        int m = dx == 0 ? 0 : (2 * dx * t + ady - 1) / (2 * ady);
         *a = *b = x0 + m;
         return true;
     }
     // x major: minor offset after j steps is m_j = floor((2*ady*j + dx - 1) / (2*dx))
-    int t = (y - y0) * sy;
-    if (t < 0 || t > ady) return false;
     if (ady == 0) { *a = x0; *b = x1; return true; }
     // smallest j with m_j >= t:  2*ady*j + dx - 1 >= 2*dx*t
-    int64_t num = (int64_t)2 * dx * t - dx + 1;
-    int64_t jmin = num <= 0 ? 0 : (num + 2 * ady - 1) / ((int64_t)2 * ady);
-    int64_t num2 = (int64_t)2 * dx * (t + 1) - dx + 1;
-    int64_t jnext = num2 <= 0 ? 0 : (num2 + 2 * ady - 1) / ((int64_t)2 * ady);
-    int64_t jmax = jnext - 1;
+    int num = 2 * dx * t - dx + 1;
+    int jmin = num <= 0 ? 0 : (num + 2 * ady - 1) / (2 * ady);
+    int num2 = 2 * dx * (t + 1) - dx + 1;
+    int jnext = num2 <= 0 ? 0 : (num2 + 2 * ady - 1) / (2 * ady);
+    int jmax = jnext - 1;
     if (jmax > dx) jmax = dx;
     if (jmin > jmax) return false;
-    *a = x0 + (int)jmin; *b = x0 + (int)jmax;
+    *a = x0 + jmin; *b = x0 + jmax;
     return true;
 }
 

@@ -467,64 +467,75 @@ __global__ void __launch_bounds__(256) k_env_blur(const uint8_t *env_fill, const
     }
 }
 
-// one block per (row, frame): xyY, solid-angle weighting, row prefix sums  (generator.py:407-408, bad_weather.py:393-395)
-__global__ void __launch_bounds__(256) k_env_prefix(const uint8_t *env8, const double *omega, double *pref, double *rowtot,
+// one block per (row, frame): xyY, solid-angle weighting, row prefix sums  (generator.py:407-408,
+// bad_weather.py:393-395).  pref is interleaved: [F][H][W_env+1][4] = prefix of (w*x, w*y, w*Y, w), so one
+// 32-byte sector serves a span end point in k_setup.
+#define ENVP_MAX_PER 12
+__global__ void __launch_bounds__(256, 2) k_env_prefix(const uint8_t *env8, const double *omega, double *pref, double *rowtot,
                                                     int H, int W_env) {
+    __shared__ double lut[256];
+    __shared__ double wtot[4][8];
+    lut[threadIdx.x] = (double)threadIdx.x / 255.0;
     int r = blockIdx.x, f = blockIdx.y;
     const uint8_t *row = env8 + ((size_t)f * H + r) * W_env * 3;
     const double *om = omega + (size_t)r * W_env;
     int per = (W_env + 255) / 256;
     int c0 = threadIdx.x * per, c1 = c0 + per < W_env ? c0 + per : W_env;
-    double sx = 0, sy = 0, sY = 0;
-    for (int c = c0; c < c1; c++) {
-        double bb = (double)row[c * 3] / 255.0, gg = (double)row[c * 3 + 1] / 255.0, rr = (double)row[c * 3 + 2] / 255.0;
-        double X = ((rr * 0.49000 + gg * 0.17697) + bb * 0.00000) / 0.17697;      // my_utils.py:56-59 (row vector x M)
-        double Y = ((rr * 0.31000 + gg * 0.81240) + bb * 0.01000) / 0.17697;
-        double Z = ((rr * 0.20000 + gg * 0.01063) + bb * 0.99000) / 0.17697;
-        double S = (X + Y) + Z;
-        double x = X / S, y = Y / S;
-        if (!(x == x)) x = 0;                                                      // generator.py:408
-        if (!(y == y)) y = 0;
-        sx += x * om[c]; sy += y * om[c]; sY += Y * om[c];
+    __syncthreads();
+    double vx[ENVP_MAX_PER], vy[ENVP_MAX_PER], vY[ENVP_MAX_PER];
+    double sx = 0, sy = 0, sY = 0, sw = 0;
+#pragma unroll
+    for (int k = 0; k < ENVP_MAX_PER; k++) {
+        int c = c0 + k;
+        vx[k] = vy[k] = vY[k] = 0;
+        if (k < per && c < c1) {
+            double bb = lut[row[c * 3]], gg = lut[row[c * 3 + 1]], rr = lut[row[c * 3 + 2]];
+            double X = ((rr * 0.49000 + gg * 0.17697) + bb * 0.00000) / 0.17697;      // my_utils.py:56-59 (row vector x M)
+            double Y = ((rr * 0.31000 + gg * 0.81240) + bb * 0.01000) / 0.17697;
+            double Z = ((rr * 0.20000 + gg * 0.01063) + bb * 0.99000) / 0.17697;
+            double S = (X + Y) + Z;
+            double x = X / S, y = Y / S;
+            if (!(x == x)) x = 0;                                                      // generator.py:408
+            if (!(y == y)) y = 0;
+            double w = om[c];
+            vx[k] = x * w; vy[k] = y * w; vY[k] = Y * w;
+            sx += vx[k]; sy += vy[k]; sY += vY[k]; sw += w;
+        }
     }
-    // block-wide exclusive scan of the 256 thread totals: warp shuffles + one pass over the 8 warp
-    // totals (a fixed tree, hence deterministic)
-    __shared__ double wtot[3][8];
+    // block-wide exclusive scan of the thread totals: warp shuffles + the 8 warp totals (fixed tree: deterministic)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double ix = sx, iy = sy, iY = sY;
+    double ix = sx, iy = sy, iY = sY, iw = sw;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-        double ux = __shfl_up_sync(0xffffffffu, ix, o), uy = __shfl_up_sync(0xffffffffu, iy, o), uY = __shfl_up_sync(0xffffffffu, iY, o);
-        if (lane >= o) { ix += ux; iy += uy; iY += uY; }
+        double ux = __shfl_up_sync(0xffffffffu, ix, o), uy = __shfl_up_sync(0xffffffffu, iy, o);
+        double uY = __shfl_up_sync(0xffffffffu, iY, o), uw = __shfl_up_sync(0xffffffffu, iw, o);
+        if (lane >= o) { ix += ux; iy += uy; iY += uY; iw += uw; }
     }
-    if (lane == 31) { wtot[0][warp] = ix; wtot[1][warp] = iy; wtot[2][warp] = iY; }
+    if (lane == 31) { wtot[0][warp] = ix; wtot[1][warp] = iy; wtot[2][warp] = iY; wtot[3][warp] = iw; }
+    double ex = __shfl_up_sync(0xffffffffu, ix, 1), ey = __shfl_up_sync(0xffffffffu, iy, 1);
+    double eY = __shfl_up_sync(0xffffffffu, iY, 1), ew = __shfl_up_sync(0xffffffffu, iw, 1);
+    if (lane == 0) { ex = ey = eY = ew = 0; }
     __syncthreads();
-    double ox = 0, oy = 0, oY = 0, allx = 0, ally = 0, allY = 0;
+    double ox = 0, oy = 0, oY = 0, ow = 0, allx = 0, ally = 0, allY = 0, allw = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        if (k == warp) { ox = allx; oy = ally; oY = allY; }
-        allx += wtot[0][k]; ally += wtot[1][k]; allY += wtot[2][k];
+        if (k == warp) { ox = allx; oy = ally; oY = allY; ow = allw; }
+        allx += wtot[0][k]; ally += wtot[1][k]; allY += wtot[2][k]; allw += wtot[3][k];
     }
-    double ax = ox + (ix - sx), ay = oy + (iy - sy), aY = oY + (iY - sY);   // exclusive prefix of this thread
-    size_t base = ((size_t)f * 3 * H + r) * (W_env + 1);
+    double ax = ox + ex, ay = oy + ey, aY = oY + eY, aw = ow + ew;       // exclusive prefix of this thread
+    double4 *p = (double4 *)pref + ((size_t)f * H + r) * (W_env + 1);
     if (threadIdx.x == 0) {
-        pref[base + W_env] = allx;
-        pref[base + (size_t)H * (W_env + 1) + W_env] = ally;
-        pref[base + 2 * (size_t)H * (W_env + 1) + W_env] = allY;
+        p[W_env] = make_double4(allx, ally, allY, allw);
         rowtot[(size_t)f * H + r] = allY;
     }
-    double *px = pref + base, *py = px + (size_t)H * (W_env + 1), *pY = py + (size_t)H * (W_env + 1);
-    for (int c = c0; c < c1; c++) {
-        double bb = (double)row[c * 3] / 255.0, gg = (double)row[c * 3 + 1] / 255.0, rr = (double)row[c * 3 + 2] / 255.0;
-        double X = ((rr * 0.49000 + gg * 0.17697) + bb * 0.00000) / 0.17697;
-        double Y = ((rr * 0.31000 + gg * 0.81240) + bb * 0.01000) / 0.17697;
-        double Z = ((rr * 0.20000 + gg * 0.01063) + bb * 0.99000) / 0.17697;
-        double S = (X + Y) + Z;
-        double x = X / S, y = Y / S;
-        if (!(x == x)) x = 0;
-        if (!(y == y)) y = 0;
-        px[c] = ax; py[c] = ay; pY[c] = aY;
-        ax += x * om[c]; ay += y * om[c]; aY += Y * om[c];
+    if (per > ENVP_MAX_PER) return;    // rr_set_camera rejects such widths
+#pragma unroll
+    for (int k = 0; k < ENVP_MAX_PER; k++) {
+        int c = c0 + k;
+        if (k < per && c < c1) {
+            p[c] = make_double4(ax, ay, aY, aw);
+            ax += vx[k]; ay += vy[k]; aY += vY[k]; aw += om[c];
+        }
     }
 }
 
@@ -553,6 +564,8 @@ cudaError_t rr_launch_env(const rr_frame_bufs &b, const rr_static_tabs &t, int F
 // per streak: FOV polygon -> mask spans -> solid-angle weighted sums -> tint; patch plan
 //   (bad_weather.py:596-704, 363-413; generator.py:119-171).  One warp per streak.
 // ------------------------------------------------------------------------------------------
+struct rr_plan;
+__device__ __forceinline__ void plan_sizes(const rr_plan &p, long long *g, long long *v, long long *a, int *vx0, int *vw);
 #define SETUP_WARPS 4
 __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(rr_frame_bufs b, rr_static_tabs t, rr_cam_dev cam, int F,
                                                              int n_streaks) {
@@ -596,15 +609,13 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(rr_frame_bufs b, rr_
         if (ymin < 0) ymin = 0;
         if (ymax > rows - 1) ymax = rows - 1;
         const size_t stride = (size_t)(cols + 1);
-        const double *Px = b.pref + (size_t)f * 3 * rows * stride;
-        const double *Py = Px + (size_t)rows * stride, *PY = Py + (size_t)rows * stride;
+        const double4 *P = (const double4 *)b.pref + (size_t)f * rows * stride;
         int ivl[RR_MAX_POLY + 2], ivh[RR_MAX_POLY + 2];
         for (int y = ymin + lane; y <= ymax; y += 32) {
             int k = rr_fcp_row(fc, y, ivl, ivh);
             for (int j = 0; j < k; j++) {
-                size_t a = (size_t)y * stride + ivl[j], e = (size_t)y * stride + ivh[j] + 1;
-                sx += Px[e] - Px[a]; sy += Py[e] - Py[a]; sY += PY[e] - PY[a];
-                sw += t.omega_pref[e] - t.omega_pref[a];
+                double4 a = P[(size_t)y * stride + ivl[j]], e = P[(size_t)y * stride + ivh[j] + 1];
+                sx += e.x - a.x; sy += e.y - a.y; sY += e.z - a.z; sw += e.w - a.w;
             }
         }
         sx = warp_sum(sx); sy = warp_sum(sy); sY = warp_sum(sY); sw = warp_sum(sw);
@@ -628,6 +639,9 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(rr_frame_bufs b, rr_
         }
         p.valid = ok ? 1 : 0;
         b.plans[s] = p;
+        long long g_, v_, a_; int vx0_, vw_;
+        plan_sizes(p, &g_, &v_, &a_, &vx0_, &vw_);
+        b.sizes[s] = make_int4((int)g_, (int)v_, (int)a_, 0);
     }
 }
 
@@ -668,8 +682,8 @@ __global__ void __launch_bounds__(1024) k_scan(rr_frame_bufs b, int n) {
     int i0 = tid * per, i1 = i0 + per < n ? i0 + per : n;
     long long el = 0, c0 = 0, c1 = 0, c2 = 0;
     for (int i = i0; i < i1; i++) {
-        long long g, v, a; int vx0, vw;
-        plan_sizes(b.plans[i], &g, &v, &a, &vx0, &vw);
+        int4 sz = b.sizes[i];
+        long long g = sz.x, v = sz.y, a = sz.z;
         el += g + v + a;
         c0 += (g + RR_RASTER_CHUNK - 1) / RR_RASTER_CHUNK;
         c1 += (v + RR_BLUR_CHUNK - 1) / RR_BLUR_CHUNK;
@@ -693,8 +707,8 @@ __global__ void __launch_bounds__(1024) k_scan(rr_frame_bufs b, int n) {
     el = tot[tid][0]; c0 = tot[tid][1]; c1 = tot[tid][2]; c2 = tot[tid][3];
     for (int i = i0; i < i1; i++) {
         rr_plan &p = b.plans[i];
-        long long g, v, a; int vx0, vw;
-        plan_sizes(p, &g, &v, &a, &vx0, &vw);
+        int4 sz = b.sizes[i];
+        long long g = sz.x, v = sz.y, a = sz.z;
         if (overflow) { p.valid = 0; p.bw = p.bh = 0; }
         long long *sc = b.scan + (size_t)i * 6;
         sc[0] = el; sc[1] = el + g; sc[2] = el + g + v; sc[3] = c0; sc[4] = c1; sc[5] = c2;
@@ -727,7 +741,8 @@ __device__ __forceinline__ int find_streak(const long long *scan, int n, int fie
 //                         top to bottom), so the result is bit-identical to the per-pixel evaluation.
 // ------------------------------------------------------------------------------------------
 #define RAS_THREADS 128
-#define RAS_CAP 2048          // doubles per staging array
+#define RAS_CAP 1792          // doubles per staging array
+#define RAS_TXN 128           // cached column spans (computeResizeAreaTab entries) per streak
 #define RAS_MAXW 512          // widest rotated canvas / patch handled by the staged path
 
 __device__ __forceinline__ double ras_sample(const uint8_t *tex, int tw, int th, const double *lut, int X, int Y) {
@@ -766,6 +781,7 @@ __global__ void __launch_bounds__(RAS_THREADS, 4) k_raster(rr_frame_bufs b, rr_s
     double *ACC = BUF;                 // area-fast mode only (BUF is the area-mode array)
     __shared__ int adx[RAS_MAXW], bdx[RAS_MAXW];
     __shared__ int XR[RAS_CAP / 8], YR[RAS_CAP / 8];
+    __shared__ rr_area_span TX[RAS_TXN];
     const int tid = threadIdx.x;
     for (int i = tid; i < 256; i += RAS_THREADS) lut[i] = (double)i / 255.0;     // bad_weather.py:252
     const int tw = cam.db_width;
@@ -794,6 +810,9 @@ __global__ void __launch_bounds__(RAS_THREADS, 4) k_raster(rr_frame_bufs b, rr_s
             adx[x] = rr_round(p.M[0] * x * AB_SCALE);
             bdx[x] = rr_round(p.M[3] * x * AB_SCALE);
         }
+        const bool tx_cached = pw <= RAS_TXN;
+        if (tx_cached && p.resize_mode == RR_RESIZE_AREA)
+            for (int dx = tid; dx < pw; dx += RAS_THREADS) TX[dx] = rr_area_tab(dx, p.scale_x, nW);
         int RB = RAS_CAP / (nW > pw ? nW : pw);
         if (RB < 1) RB = 1;
         if (RB > RAS_CAP / 8) RB = RAS_CAP / 8;
@@ -816,17 +835,21 @@ __global__ void __launch_bounds__(RAS_THREADS, 4) k_raster(rr_frame_bufs b, rr_s
                     YR[tid] = rr_round((p.M[4] * yy + p.M[5]) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
                 }
                 __syncthreads();
-                for (int i = tid; i < rb * nW; i += RAS_THREADS) {          // phase 1: the canvas band, once
-                    int r = i / nW, c = i - r * nW;
-                    int X = (XR[r] + adx[c]) >> (10 - RR_INTER_BITS);
-                    int Y = (YR[r] + bdx[c]) >> (10 - RR_INTER_BITS);
-                    C[i] = ras_sample(tex, tw, th, lut, X, Y);
+                {                                                           // phase 1: the canvas band, once
+                    int r = tid / nW, c = tid - r * nW;
+                    for (int i = tid; i < rb * nW; i += RAS_THREADS) {
+                        int X = (XR[r] + adx[c]) >> (10 - RR_INTER_BITS);
+                        int Y = (YR[r] + bdx[c]) >> (10 - RR_INTER_BITS);
+                        C[i] = ras_sample(tex, tw, th, lut, X, Y);
+                        c += RAS_THREADS;
+                        while (c >= nW) { c -= nW; r++; }
+                    }
                 }
                 __syncthreads();
                 if (!fast) {
                     for (int i = tid; i < rb * pw; i += RAS_THREADS) {      // phase 2a: per (row, dx) column sums
                         int r = i / pw, dx = i - r * pw;
-                        rr_area_span tx = rr_area_tab(dx, p.scale_x, nW);
+                        rr_area_span tx = tx_cached ? TX[dx] : rr_area_tab(dx, p.scale_x, nW);
                         ras_smem_src src = {C, nW};
                         BUF[i] = rr_area_row(src, tx, r);
                     }

@@ -17,10 +17,11 @@ struct rr_frame_bufs {
     float *fblur;              // [F][H][W] blurred extinction (debug / stage test)
     uint8_t *env_fill;         // [F][H][W_env][3] gathered cylindrical map
     uint8_t *env8;             // [F][H][W_env][3] final environment map
-    double *pref;              // [F][3][H][W_env+1] row prefix sums of omega*(x, y, Y)
+    double *pref;              // [F][H][W_env+1][4] row prefix sums of (omega*x, omega*y, omega*Y, omega), interleaved
     double *rowtot;            // [F][H] row totals of omega*Y
     double *ambient;           // [F] sum over the map of omega*Y
     rr_plan *plans;            // [n_streaks]
+    int4 *sizes;               // [n_streaks] arena elements (g, v, a) of each streak, written by k_setup for k_scan
     long long *scan;           // [n_streaks+1][4] exclusive prefix: g elems, a elems, raster chunks, blur chunks
     double *arena;             // patch arena
     long long arena_cap;       // elements
