@@ -742,8 +742,10 @@ __device__ __forceinline__ int find_streak(const long long *scan, int n, int fie
 // ------------------------------------------------------------------------------------------
 #define RAS_THREADS 128
 #define RAS_CAP 1792          // doubles per staging array
-#define RAS_TXN 128           // cached column spans (computeResizeAreaTab entries) per streak
-#define RAS_MAXW 512          // widest rotated canvas / patch handled by the staged path
+#define RAS_MAXW 512          // widest rotated canvas handled by the staged path
+#define RAS_TXN 128           // widest / tallest patch with cached computeResizeAreaTab spans
+#define RAS_MAXD 1024         // patch pixels with accumulators resident in shared memory
+#define RAS_RBMAX 256
 
 __device__ __forceinline__ double ras_sample(const uint8_t *tex, int tw, int th, const double *lut, int X, int Y) {
     // rr_warp_affine_linear with the fixed-point coordinates already formed
@@ -773,15 +775,17 @@ struct ras_smem_src {       // functor over a staged band: rows [0, rb) x column
 };
 
 __global__ void __launch_bounds__(RAS_THREADS, 4) k_raster(rr_frame_bufs b, rr_static_tabs t, rr_cam_dev cam, int n) {
+    extern __shared__ double ras_smem[];
+    double *C = ras_smem;                       // [RAS_CAP]   canvas band
+    double *BUF = C + RAS_CAP;                  // [RAS_CAP]   per (source row, dx) column sums (area) / quad accumulators (area-fast)
+    double *SUM = BUF + RAS_CAP;                // [RAS_MAXD]  per patch pixel running sum
+    double *lut = SUM + RAS_MAXD;               // [256]       u8 / 255.0
+    rr_area_span *TX = (rr_area_span *)(lut + 256);     // [RAS_TXN]
+    rr_area_span *TY = TX + RAS_TXN;                     // [RAS_TXN]
+    int *adx = (int *)(TY + RAS_TXN), *bdx = adx + RAS_MAXW;   // [RAS_MAXW] each
+    int *XR = bdx + RAS_MAXW, *YR = XR + RAS_RBMAX;            // [RAS_RBMAX] each
+    double *ACC = BUF;
     __shared__ rr_plan sp;
-    __shared__ double lut[256];
-    __shared__ double C[RAS_CAP];
-    __shared__ double BUF[RAS_CAP];
-    __shared__ double SUM[RAS_MAXW];
-    double *ACC = BUF;                 // area-fast mode only (BUF is the area-mode array)
-    __shared__ int adx[RAS_MAXW], bdx[RAS_MAXW];
-    __shared__ int XR[RAS_CAP / 8], YR[RAS_CAP / 8];
-    __shared__ rr_area_span TX[RAS_TXN];
     const int tid = threadIdx.x;
     for (int i = tid; i < 256; i += RAS_THREADS) lut[i] = (double)i / 255.0;     // bad_weather.py:252
     const int tw = cam.db_width;
@@ -796,7 +800,7 @@ __global__ void __launch_bounds__(RAS_THREADS, 4) k_raster(rr_frame_bufs b, rr_s
         const uint8_t *tex = t.db + p.tex_off;
         double *out = b.arena + p.g_off;
         const bool staged = p.type != RR_BIG && (p.resize_mode == RR_RESIZE_AREA || p.resize_mode == RR_RESIZE_AREA_FAST) &&
-                            p.nW <= RAS_MAXW && p.pw <= RAS_MAXW;
+                            p.nW <= RAS_MAXW && p.pw <= RAS_TXN && p.ph <= RAS_TXN && g <= RAS_MAXD;
         if (!staged) {
             for (long long e = tid; e < g; e += RAS_THREADS) {
                 int y = (int)(e / p.pw), x = (int)(e - (long long)y * p.pw);
@@ -804,93 +808,99 @@ __global__ void __launch_bounds__(RAS_THREADS, 4) k_raster(rr_frame_bufs b, rr_s
             }
             continue;
         }
-        const int nW = p.nW, nH = p.nH, pw = p.pw, ph = p.ph, th = p.tex_h;
+        const int nW = p.nW, nH = p.nH, pw = p.pw, ph = p.ph, th = p.tex_h, npx = pw * ph;
         const int AB_SCALE = 1 << 10;
+        const bool fast = p.resize_mode == RR_RESIZE_AREA_FAST;
+        const int isx = rr_round(p.scale_x), isy = rr_round(p.scale_y);
+        const int area = isx * isy, area4 = area - (area & 3);
         for (int x = tid; x < nW; x += RAS_THREADS) {
             adx[x] = rr_round(p.M[0] * x * AB_SCALE);
             bdx[x] = rr_round(p.M[3] * x * AB_SCALE);
         }
-        const bool tx_cached = pw <= RAS_TXN;
-        if (tx_cached && p.resize_mode == RR_RESIZE_AREA)
+        if (!fast) {
             for (int dx = tid; dx < pw; dx += RAS_THREADS) TX[dx] = rr_area_tab(dx, p.scale_x, nW);
+            for (int dy = tid; dy < ph; dy += RAS_THREADS) TY[dy] = rr_area_tab(dy, p.scale_y, nH);
+        }
         int RB = RAS_CAP / (nW > pw ? nW : pw);
         if (RB < 1) RB = 1;
-        if (RB > RAS_CAP / 8) RB = RAS_CAP / 8;
-        const bool fast = p.resize_mode == RR_RESIZE_AREA_FAST;
-        const int isx = rr_round(p.scale_x), isy = rr_round(p.scale_y);
-        for (int dy = 0; dy < ph; dy++) {
-            // source rows of this destination row
-            rr_area_span ty;
-            int nr, row0;
-            if (fast) { nr = isy; row0 = dy * isy; ty.has_first = 0; ty.n = isy; ty.has_last = 0; ty.s_first = row0; }
-            else { ty = rr_area_tab(dy, p.scale_y, nH); nr = ty.has_first + ty.n + ty.has_last; row0 = ty.s_first - ty.has_first; }
-            const int area = isx * isy, area4 = area - (area & 3);
-            for (int j0 = 0; j0 < nr; j0 += RB) {
-                const int rb = (nr - j0) < RB ? (nr - j0) : RB;
-                __syncthreads();                         // previous users of C / BUF / XR are done
-                if (tid < rb) {
-                    int sy = row0 + j0 + tid;
-                    int yy = p.flip ? (nH - 1 - sy) : sy;
-                    XR[tid] = rr_round((p.M[1] * yy + p.M[2]) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
-                    YR[tid] = rr_round((p.M[4] * yy + p.M[5]) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
-                }
-                __syncthreads();
-                {                                                           // phase 1: the canvas band, once
-                    int r = tid / nW, c = tid - r * nW;
-                    for (int i = tid; i < rb * nW; i += RAS_THREADS) {
-                        int X = (XR[r] + adx[c]) >> (10 - RR_INTER_BITS);
-                        int Y = (YR[r] + bdx[c]) >> (10 - RR_INTER_BITS);
-                        C[i] = ras_sample(tex, tw, th, lut, X, Y);
-                        c += RAS_THREADS;
-                        while (c >= nW) { c -= nW; r++; }
-                    }
-                }
-                __syncthreads();
-                if (!fast) {
-                    for (int i = tid; i < rb * pw; i += RAS_THREADS) {      // phase 2a: per (row, dx) column sums
-                        int r = i / pw, dx = i - r * pw;
-                        rr_area_span tx = tx_cached ? TX[dx] : rr_area_tab(dx, p.scale_x, nW);
-                        ras_smem_src src = {C, nW};
-                        BUF[i] = rr_area_row(src, tx, r);
-                    }
-                    __syncthreads();
-                    for (int dx = tid; dx < pw; dx += RAS_THREADS) {        // phase 2b: rows, in order
-                        double acc = SUM[dx];
-                        for (int r = 0; r < rb; r++) {
-                            int j = j0 + r;
-                            float beta = (ty.has_first && j == 0) ? ty.a_first : ((ty.has_last && j == nr - 1) ? ty.a_last : ty.a_mid);
-                            double v = beta * BUF[r * pw + dx];
-                            acc = (j == 0) ? v : acc + v;
-                        }
-                        SUM[dx] = acc;
-                    }
-                } else {
-                    // cv::resizeAreaFast_: sum += ((a + b) + c) + d over the cell in row-major order, then the tail
-                    for (int dx = tid; dx < pw; dx += RAS_THREADS) {
-                        double sum = (j0 == 0) ? 0.0 : SUM[dx], acc = ACC[dx];
-                        for (int r = 0; r < rb; r++) {
-                            int kbase = (j0 + r) * isx;
-                            const double *row = C + r * nW + dx * isx;
-                            for (int c = 0; c < isx; c++) {
-                                int k = kbase + c;
-                                double v = row[c];
-                                if (k < area4) {
-                                    int pos = k & 3;
-                                    acc = pos == 0 ? v : acc + v;
-                                    if (pos == 3) sum += acc;
-                                } else sum += v;
-                            }
-                        }
-                        SUM[dx] = sum; ACC[dx] = acc;
-                    }
+        if (RB > RAS_RBMAX) RB = RAS_RBMAX;
+        // bands of canvas rows; every canvas pixel is sampled exactly once
+        for (int s0 = 0; s0 < nH; s0 += RB) {
+            const int rb = (nH - s0) < RB ? (nH - s0) : RB;
+            __syncthreads();                         // previous band fully consumed (C, BUF, XR)
+            for (int r = tid; r < rb; r += RAS_THREADS) {
+                int sy = s0 + r;
+                int yy = p.flip ? (nH - 1 - sy) : sy;
+                XR[r] = rr_round((p.M[1] * yy + p.M[2]) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
+                YR[r] = rr_round((p.M[4] * yy + p.M[5]) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
+            }
+            __syncthreads();
+            {
+                int r = tid / nW, c = tid - r * nW;
+                for (int i = tid; i < rb * nW; i += RAS_THREADS) {
+                    int X = (XR[r] + adx[c]) >> (10 - RR_INTER_BITS);
+                    int Y = (YR[r] + bdx[c]) >> (10 - RR_INTER_BITS);
+                    C[i] = ras_sample(tex, tw, th, lut, X, Y);
+                    c += RAS_THREADS;
+                    while (c >= nW) { c -= nW; r++; }
                 }
             }
             __syncthreads();
-            for (int dx = tid; dx < pw; dx += RAS_THREADS) {
-                double v = SUM[dx];
-                if (fast) { float scale = 1.f / area; v = v * scale; }
-                out[(size_t)dy * pw + dx] = v < 0 ? 0 : (v > 1 ? 1 : v);
+            if (!fast) {
+                // cv::resizeArea_: buf[dx] = sum_k S[sx_k] * alpha_k (left to right) for every source row of the band ...
+                for (int i = tid; i < rb * pw; i += RAS_THREADS) {
+                    int r = i / pw, dx = i - r * pw;
+                    ras_smem_src src = {C, nW};
+                    BUF[i] = rr_area_row(src, TX[dx], r);
+                }
+                __syncthreads();
+                // ... then sum[dx] (+)= beta * buf[dx], rows top to bottom; a patch pixel's rows may span bands
+                for (int e = tid; e < npx; e += RAS_THREADS) {
+                    int dy = e / pw, dx = e - dy * pw;
+                    const rr_area_span ty = TY[dy];
+                    const int nr = ty.has_first + ty.n + ty.has_last, row0 = ty.s_first - ty.has_first;
+                    int jlo = s0 - row0; if (jlo < 0) jlo = 0;
+                    int jhi = s0 + rb - row0; if (jhi > nr) jhi = nr;
+                    if (jlo >= jhi) continue;
+                    double acc = SUM[e];
+                    for (int j = jlo; j < jhi; j++) {
+                        float beta = (ty.has_first && j == 0) ? ty.a_first : ((ty.has_last && j == nr - 1) ? ty.a_last : ty.a_mid);
+                        double v = beta * BUF[(row0 + j - s0) * pw + dx];
+                        acc = (j == 0) ? v : acc + v;
+                    }
+                    SUM[e] = acc;
+                }
+            } else {
+                // cv::resizeAreaFast_: sum += ((a + b) + c) + d over the cell in row-major order, then the tail
+                for (int e = tid; e < npx; e += RAS_THREADS) {
+                    int dy = e / pw, dx = e - dy * pw;
+                    const int row0 = dy * isy;
+                    int jlo = s0 - row0; if (jlo < 0) jlo = 0;
+                    int jhi = s0 + rb - row0; if (jhi > isy) jhi = isy;
+                    if (jlo >= jhi) continue;
+                    double sum = (jlo == 0) ? 0.0 : SUM[e], acc = (jlo == 0) ? 0.0 : ACC[RAS_CAP - 1 - e];
+                    for (int j = jlo; j < jhi; j++) {
+                        const int kbase = j * isx;
+                        const double *row = C + (row0 + j - s0) * nW + dx * isx;
+                        for (int c = 0; c < isx; c++) {
+                            int k = kbase + c;
+                            double v = row[c];
+                            if (k < area4) {
+                                int pos = k & 3;
+                                acc = pos == 0 ? v : acc + v;
+                                if (pos == 3) sum += acc;
+                            } else sum += v;
+                        }
+                    }
+                    SUM[e] = sum; ACC[RAS_CAP - 1 - e] = acc;
+                }
             }
+        }
+        __syncthreads();
+        for (int e = tid; e < npx; e += RAS_THREADS) {
+            double v = SUM[e];
+            if (fast) { float scale = 1.f / area; v = v * scale; }
+            out[e] = v < 0 ? 0 : (v > 1 ? 1 : v);
         }
     }
 }
@@ -898,9 +908,17 @@ __global__ void __launch_bounds__(RAS_THREADS, 4) k_raster(rr_frame_bufs b, rr_s
 cudaError_t rr_launch_raster(const rr_frame_bufs &b, const rr_static_tabs &t, const rr_cam_dev &cam, int n_streaks, int n_sm,
                              cudaStream_t st) {
     if (n_streaks == 0) return cudaSuccess;
+    const size_t smem = sizeof(double) * (2 * RAS_CAP + RAS_MAXD + 256) + sizeof(rr_area_span) * 2 * RAS_TXN +
+                        sizeof(int) * (2 * RAS_MAXW + 2 * RAS_RBMAX);
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
     int grid = n_sm * 4;
     if (grid > n_streaks) grid = n_streaks;
-    k_raster<<<grid, RAS_THREADS, 0, st>>>(b, t, cam, n_streaks);
+    k_raster<<<grid, RAS_THREADS, smem, st>>>(b, t, cam, n_streaks);
     return cudaGetLastError();
 }
 
