@@ -68,6 +68,9 @@ typedef struct rr_camera {
     double fov_deg;          /* 165 (generator.py:267)                            */
     double opacity_att;      /* --opacity_attenuation                             */
     double fallrate_mmh;     /* rain intensity of the weather                     */
+    int32_t render_scale;    /* settings["render_scale"]: 1, or 2 = the input frames are (2H, 2W) and are
+                              * reduced like cv2.resize does for an exact factor 2 (generator.py:354-355) */
+    int32_t reserved;
 } rr_camera;
 
 /* timing slots of rr_timings() */
@@ -107,7 +110,7 @@ int rr_set_camera(rr_context *ctx, const rr_camera *cam, int max_batch);
 int rr_env_size(rr_context *ctx, int *H_env, int *W_env);
 
 /* The hot path for a batch of n_frames (<= max_batch) independent frames.  HOST buffers:
- *   bgr        n*H*W*3 uint8   (cv2.imread order, generator.py:352)
+ *   bgr        n*(rs*H)*(rs*W)*3 uint8   (cv2.imread order, generator.py:352; rs = render_scale)
  *   depth      n*H*W   float32 metres (generator.py:365)
  *   streaks    concatenated records, frame f owns [streak_offsets[f], streak_offsets[f+1])
  *   out_bgr    n*H*W*3 float32 BGR mean-shifted rainy image (generator.py:464), may be NULL

@@ -579,11 +579,14 @@ class FrameResult:
 
 def render_frame(bg_u8: np.ndarray, depth: np.ndarray, streaks, textures, ratios, cam: Camera, seed: int,
                  tables: EnvTables | None = None, omega: np.ndarray | None = None,
-                 f32_mode: str = "native", keep_patches: bool = False) -> FrameResult:
+                 f32_mode: str = "native", keep_patches: bool = False, render_scale: int = 1) -> FrameResult:
     """One frame of Generator.run (common/generator.py:318-469) on decoded arrays.
-    ``streaks``: the simulator frame's Streak list (XML order, unfiltered)."""
+    ``streaks``: the simulator frame's Streak list (XML order, unfiltered).  With ``render_scale`` > 1
+    ``bg_u8`` is the full-resolution frame and is reduced like generator.py:354-355."""
     np.random.seed(seed)                                                  # :318
     bg = bg_u8 / 255.0                                                    # :352
+    if render_scale != 1:                                                 # :354-355
+        bg = cv2.resize(bg, (int(bg.shape[1] // render_scale), int(bg.shape[0] // render_scale)))
     rainy_bg = fog_rain_layer(bg, depth, cam, f32_mode)                   # :386
     fog = rainy_bg.copy()
     tables = tables or build_env_tables(cam.W, cam.H, cam.focal_m)

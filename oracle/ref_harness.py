@@ -84,7 +84,7 @@ def load_reference():
 
 
 def run_reference(paths: dict, dataset: str, fallrate: int, frames=None, capture_stages=True,
-                  noise_scale=0.0, noise_std=0.0, opacity_attenuation=1.0, sequences="seq1"):
+                  noise_scale=0.0, noise_std=0.0, opacity_attenuation=1.0, sequences="seq1", settings_override=None):
     """Drive ``main.check_arg`` + ``Generator.run()`` of the reference on a tree laid out by
     ``rain_rendering_b200.synth.write_dataset``.  Returns {frame_name: {...arrays...}}."""
     m = load_reference()
@@ -133,6 +133,10 @@ def run_reference(paths: dict, dataset: str, fallrate: int, frames=None, capture
         att.FogRain.fog_rain_layer = fog_wrap
         bw.EnvironmentMapGenerator.generate_map = env_wrap
         bw.RainRenderer.add_drop_to_image = add_wrap
+    import common.db as ref_db
+    saved_defaults = dict(ref_db._settings_defaults)
+    if settings_override:
+        ref_db._settings_defaults.update(settings_override)     # customdb does not set these keys, so the defaults apply
     cwd = os.getcwd()
     try:
         os.chdir(REFERENCE_ROOT)  # config.<dataset> modules are imported relative to the reference root
@@ -144,6 +148,8 @@ def run_reference(paths: dict, dataset: str, fallrate: int, frames=None, capture
             g.run()
     finally:
         os.chdir(cwd)
+        ref_db._settings_defaults.clear()
+        ref_db._settings_defaults.update(saved_defaults)
         att.FogRain.fog_rain_layer = orig_fog
         bw.EnvironmentMapGenerator.generate_map = orig_env
         bw.RainRenderer.add_drop_to_image = orig_add

@@ -22,7 +22,7 @@ class Camera(C.Structure):
     _fields_ = [("W", C.c_int32), ("H", C.c_int32), ("focal_m", C.c_double), ("f_number", C.c_double),
                 ("exposure_ms", C.c_double), ("gain", C.c_double), ("focus_plane_m", C.c_double),
                 ("pix_size_m", C.c_double), ("radius", C.c_double), ("fov_deg", C.c_double),
-                ("opacity_att", C.c_double), ("fallrate_mmh", C.c_double)]
+                ("opacity_att", C.c_double), ("fallrate_mmh", C.c_double), ("render_scale", C.c_int32), ("reserved", C.c_int32)]
 
 
 class SimParams(C.Structure):

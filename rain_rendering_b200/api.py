@@ -107,12 +107,13 @@ class RainContext:
 
     # -- camera ------------------------------------------------------------------------------
     def set_camera(self, W, H, focal_mm=6.0, f_number=6.0, exposure_ms=2.0, gain=20.0, fallrate=25.0,
-                   opacity_attenuation=1.0, max_batch=1, focus_plane=6.0, pix_size=4.65e-06, radius=10.0, fov_deg=165.0):
+                   opacity_attenuation=1.0, max_batch=1, focus_plane=6.0, pix_size=4.65e-06, radius=10.0, fov_deg=165.0,
+                   render_scale=1):
         cam = _lib.Camera(int(W), int(H), focal_mm / 1000., float(f_number), float(exposure_ms), float(gain),
                           float(focus_plane), float(pix_size), float(radius), float(fov_deg),
-                          float(opacity_attenuation), float(fallrate))
+                          float(opacity_attenuation), float(fallrate), int(render_scale), 0)
         _lib.check(self.lib.rr_set_camera(self.h, C.byref(cam), int(max_batch)), "rr_set_camera")
-        self.W, self.H, self.max_batch = int(W), int(H), int(max_batch)
+        self.W, self.H, self.max_batch, self.render_scale = int(W), int(H), int(max_batch), int(render_scale)
         he, we = C.c_int(), C.c_int()
         _lib.check(self.lib.rr_env_size(self.h, C.byref(he), C.byref(we)), "rr_env_size")
         self.H_env, self.W_env = he.value, we.value
@@ -123,7 +124,8 @@ class RainContext:
         """bgr (n,H,W,3) uint8; depth (n,H,W) float32; streaks STREAK_DTYPE (concatenated);
         offsets (n+1,) int32.  Returns dict of the requested outputs (numpy arrays)."""
         n = bgr.shape[0]
-        assert bgr.shape == (n, self.H, self.W, 3) and bgr.dtype == np.uint8
+        rs = self.render_scale
+        assert bgr.shape == (n, self.H * rs, self.W * rs, 3) and bgr.dtype == np.uint8
         assert depth.shape == (n, self.H, self.W) and depth.dtype == np.float32
         assert streaks.dtype == STREAK_DTYPE
         offsets = np.ascontiguousarray(offsets, dtype=np.int32)

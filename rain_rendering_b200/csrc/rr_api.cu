@@ -47,6 +47,7 @@ struct rr_context {
     double *d_omega = nullptr, *d_omega_pref = nullptr, *d_omega_total = nullptr;
     // per batch
     uint8_t *d_bgr = nullptr;
+    double *d_bgf = nullptr;         // reduced float64 image (render_scale == 2)
     float *d_depth = nullptr;
     rr_streak_rec *d_streaks = nullptr;
     int32_t *d_offsets = nullptr;
@@ -184,6 +185,7 @@ static int ensure_streak_cap(rr_context *c, int n) {
 
 int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
     if (!c || !cam || max_batch <= 0) { set_err("rr_set_camera: bad arguments"); return RR_ERR_ARG; }
+    if (cam->render_scale != 0 && cam->render_scale != 1 && cam->render_scale != 2) { set_err("rr_set_camera: render_scale %d is not supported (1 or 2)", cam->render_scale); return RR_ERR_ARG; }
     if (cam->W < 32 || cam->H < 32 || cam->W > 8192 || cam->H > 8192) { set_err("rr_set_camera: unsupported size %dx%d", cam->W, cam->H); return RR_ERR_ARG; }
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
@@ -236,12 +238,16 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
     c->launches += 3;
     // per-batch buffers
     const size_t F = (size_t)max_batch, np = (size_t)W * H, npe = (size_t)He * We;
+    const int rs = cam->render_scale == 2 ? 2 : 1;
     rr_frame_bufs &b = c->fb;
-    CK(dev_alloc(c, &c->d_bgr, F * np * 3));
+    CK(dev_alloc(c, &c->d_bgr, F * np * 3 * rs * rs));
     CK(dev_alloc(c, &c->d_depth, F * np));
     CK(dev_alloc(c, &c->d_offsets, F + 1));
     CK(dev_alloc(c, &c->d_sub_offsets, (size_t)RR_MAX_SUB * (F + 1)));
     CK(dev_alloc(c, &b.chan_sum, F * 4));
+    CK(dev_alloc(c, &b.bg_sum, F * 4));
+    c->d_bgf = nullptr;
+    if (rs == 2) CK(dev_alloc(c, &c->d_bgf, F * 3 * np));
     CK(dev_alloc(c, &b.rainy, F * 3 * np));
     CK(dev_alloc(c, &b.bg8, F * np * 3));
     CK(dev_alloc(c, &b.fblur, F * np));
@@ -252,7 +258,7 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
     CK(dev_alloc(c, &b.ambient, F));
     CK(dev_alloc(c, &b.err_flag, (size_t)1));
     size_t tiles = (size_t)((W + RR_TILE_W - 1) / RR_TILE_W) * ((H + RR_TILE_H - 1) / RR_TILE_H);
-    CK(dev_alloc(c, &b.tile_sum, F * tiles));
+    CK(dev_alloc(c, &b.tile_sum, F * (tiles > 256 ? tiles : 256)));     // also holds the 64x4 partial sums of k_downscale2
     CK(dev_alloc(c, &b.frame_mean, F));
     CK(dev_alloc(c, &b.out_bgr, F * np * 3));
     CK(dev_alloc(c, &b.out_mask, F * np));
@@ -299,7 +305,8 @@ static int run_pipeline(rr_context *c, int F, int n_streaks, bool timed) {
     const int W = c->cam.W, H = c->cam.H;
     c->camd.db_width = c->db_width; c->camd.n_tex = c->n_tex;
     if (timed) CK(cudaEventRecord(c->ev[RR_T_FOG], st));
-    CK(rr_launch_stats(b, F, W, H, st));
+    const int rs = c->cam.render_scale == 2 ? 2 : 1;
+    CK(rr_launch_stats(b, F, W, H, rs, (double *)b.bgf, st));
     CK(rr_launch_fog(b, c->fogc, F, W, H, st));
     if (timed) CK(cudaEventRecord(c->ev[RR_T_ENV], st));
     CK(rr_launch_env(b, t, F, W, H, c->W_env, st));
@@ -315,7 +322,7 @@ static int run_pipeline(rr_context *c, int F, int n_streaks, bool timed) {
     if (timed) CK(cudaEventRecord(c->ev[RR_T_EPILOGUE], st));
     CK(rr_launch_epilogue(b, F, W, H, st));
     if (timed) CK(cudaEventRecord(c->ev[RR_T_D2H], st));
-    c->launches += 2 + 1 + 4 + (n_streaks ? 1 : 0) + 1 + (n_streaks ? 3 : 0) + 2 + 1;
+    c->launches += 3 + 1 + 4 + (n_streaks ? 1 : 0) + 1 + (n_streaks ? 3 : 0) + 2 + 1;
     c->last_n_streaks = n_streaks;
     return RR_OK;
 }
@@ -325,7 +332,10 @@ static rr_frame_bufs sub_view(const rr_context *c, const rr_frame_bufs &b, int f
     rr_frame_bufs v = b;
     const size_t np = (size_t)c->cam.W * c->cam.H, npe = (size_t)c->H_env * c->W_env;
     const size_t tiles = (size_t)((c->cam.W + RR_TILE_W - 1) / RR_TILE_W) * ((c->cam.H + RR_TILE_H - 1) / RR_TILE_H);
-    v.bgr += (size_t)f0 * np * 3; v.depth += (size_t)f0 * np; v.streaks += s0;
+    const int rs2 = c->cam.render_scale == 2 ? 4 : 1;
+    v.bgr += (size_t)f0 * np * 3 * rs2; v.depth += (size_t)f0 * np; v.streaks += s0;
+    if (v.bgf) v.bgf += (size_t)f0 * 3 * np;
+    v.bg_sum += (size_t)f0 * 4;
     v.chan_sum += (size_t)f0 * 4; v.rainy += (size_t)f0 * 3 * np; v.bg8 += (size_t)f0 * np * 3; v.fblur += (size_t)f0 * np;
     v.env_fill += (size_t)f0 * npe * 3; v.env8 += (size_t)f0 * npe * 3;
     v.pref += (size_t)f0 * 4 * c->H_env * (c->W_env + 1); v.rowtot += (size_t)f0 * c->H_env; v.ambient += f0;
@@ -393,8 +403,10 @@ int rr_render_frames(rr_context *c, int n_frames, const uint8_t *bgr, const floa
     r = ensure_streak_cap(c, n_streaks);
     if (r != RR_OK) return r;
     const size_t np = (size_t)c->cam.W * c->cam.H;
+    const size_t rs2 = c->cam.render_scale == 2 ? 4 : 1;
     cudaStream_t st = c->stream;
     rr_frame_bufs &b = c->fb;
+    b.bgf = c->d_bgf;
     // sub-batches overlap H2D / compute / D2H when the caller's buffers are page-locked
     int S = 1;
     {
@@ -419,7 +431,7 @@ int rr_render_frames(rr_context *c, int n_frames, const uint8_t *bgr, const floa
             const int f0 = fstart[k], nf = fstart[k + 1] - f0, s0 = streak_offsets[f0], ns = streak_offsets[f0 + nf] - s0;
             for (int i = 0; i <= nf; i++) sub_off[(size_t)k * (F + 1) + i] = streak_offsets[f0 + i] - s0;
             cudaStream_t hs = S > 1 ? c->s_h2d : st;
-            CK(cudaMemcpyAsync(c->d_bgr + (size_t)f0 * np * 3, bgr + (size_t)f0 * np * 3, (size_t)nf * np * 3, cudaMemcpyHostToDevice, hs));
+            CK(cudaMemcpyAsync(c->d_bgr + (size_t)f0 * np * 3 * rs2, bgr + (size_t)f0 * np * 3 * rs2, (size_t)nf * np * 3 * rs2, cudaMemcpyHostToDevice, hs));
             CK(cudaMemcpyAsync(c->d_depth + (size_t)f0 * np, depth + (size_t)f0 * np, (size_t)nf * np * sizeof(float), cudaMemcpyHostToDevice, hs));
             if (ns) CK(cudaMemcpyAsync(c->d_streaks + s0, streaks + s0, (size_t)ns * sizeof(rr_streak_rec), cudaMemcpyHostToDevice, hs));
             CK(cudaMemcpyAsync(c->d_sub_offsets + (size_t)k * (F + 1), sub_off.data() + (size_t)k * (F + 1), (nf + 1) * sizeof(int32_t),
@@ -475,7 +487,7 @@ int rr_render_frames_device(rr_context *c, int n_frames, const uint8_t *d_bgr, c
     rr_frame_bufs &b = c->fb;
     CK(cudaEventRecord(c->ev[RR_T_H2D], st));
     CK(cudaMemcpyAsync(c->d_offsets, h_streak_offsets, (F + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    b.bgr = d_bgr; b.depth = d_depth; b.streaks = d_streaks; b.offsets = c->d_offsets;
+    b.bgr = d_bgr; b.depth = d_depth; b.streaks = d_streaks; b.offsets = c->d_offsets; b.bgf = c->d_bgf;
     if (d_out_bgr) b.out_bgr = d_out_bgr;
     if (d_out_mask) b.out_mask = d_out_mask;
     if (d_out_bgr_u8) b.out_u8 = d_out_bgr_u8;
@@ -512,12 +524,13 @@ int rr_fog_only(rr_context *c, int n_frames, const uint8_t *bgr, const float *de
     const size_t np = (size_t)c->cam.W * c->cam.H, F = n_frames;
     cudaStream_t st = c->stream;
     rr_frame_bufs &b = c->fb;
-    CK(cudaMemcpyAsync(c->d_bgr, bgr, F * np * 3, cudaMemcpyHostToDevice, st));
+    const size_t rs2 = c->cam.render_scale == 2 ? 4 : 1;
+    CK(cudaMemcpyAsync(c->d_bgr, bgr, F * np * 3 * rs2, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->d_depth, depth, F * np * sizeof(float), cudaMemcpyHostToDevice, st));
-    b.bgr = c->d_bgr; b.depth = c->d_depth;
-    CK(rr_launch_stats(b, n_frames, c->cam.W, c->cam.H, st));
+    b.bgr = c->d_bgr; b.depth = c->d_depth; b.bgf = c->d_bgf;
+    CK(rr_launch_stats(b, n_frames, c->cam.W, c->cam.H, rs2 == 4 ? 2 : 1, c->d_bgf, st));
     CK(rr_launch_fog(b, c->fogc, n_frames, c->cam.W, c->cam.H, st));
-    c->launches += 2;
+    c->launches += 3;
     CK(cudaMemcpyAsync(out_planar, b.rainy, F * 3 * np * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return RR_OK;

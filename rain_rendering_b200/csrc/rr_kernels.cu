@@ -224,10 +224,65 @@ __global__ void k_stats(const uint8_t *bgr, int npix, unsigned long long *chan_s
     }
 }
 
-cudaError_t rr_launch_stats(const rr_frame_bufs &b, int F, int W, int H, cudaStream_t st) {
+__global__ void k_stats_final(const unsigned long long *chan_sum, double *bg_sum, int F) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < F * 4) bg_sum[i] = (double)chan_sum[i] / 255.0;
+}
+
+// render_scale == 2: cv2.resize(bg / 255.0, (W, H)) with the default INTER_LINEAR switches to the exact
+// 2x2 area average (resizeAreaFast_): sum = ((a + b) + c) + d in row-major cell order, times float 0.25
+// (reference common/generator.py:352-355).  Output planar float64 plus per-block channel partial sums.
+__global__ void __launch_bounds__(256) k_downscale2(const uint8_t *bgr, double *bgf, double *partial, int W, int H) {
+    int f = blockIdx.y;
+    const size_t np = (size_t)W * H;
+    const uint8_t *src = bgr + (size_t)f * np * 4 * 3;
+    double s0 = 0, s1 = 0, s2 = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < np; i += (size_t)gridDim.x * blockDim.x) {
+        int y = (int)(i / W), x = (int)(i - (size_t)y * W);
+        const uint8_t *p00 = src + ((size_t)(2 * y) * (2 * W) + 2 * x) * 3, *p10 = p00 + (size_t)(2 * W) * 3;
+        double v[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            double a = (double)p00[c] / 255.0, bq = (double)p00[3 + c] / 255.0, cq = (double)p10[c] / 255.0, d = (double)p10[3 + c] / 255.0;
+            double sum = ((a + bq) + cq) + d;
+            v[c] = sum * 0.25f;
+            bgf[((size_t)f * 3 + c) * np + i] = v[c];
+        }
+        s0 += v[0]; s1 += v[1]; s2 += v[2];
+    }
+    __shared__ double sh[3][8];
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2);
+    int w = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { sh[0][w] = s0; sh[1][w] = s1; sh[2][w] = s2; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double t = 0;
+        for (int k = 0; k < 8; k++) t += sh[threadIdx.x][k];
+        partial[((size_t)f * gridDim.x + blockIdx.x) * 4 + threadIdx.x] = t;
+    }
+}
+
+__global__ void k_downscale2_final(const double *partial, double *bg_sum, int nblk) {
+    int f = blockIdx.x;
+    if (threadIdx.x < 3) {
+        double t = 0;
+        for (int k = 0; k < nblk; k++) t += partial[((size_t)f * nblk + k) * 4 + threadIdx.x];     // fixed order: deterministic
+        bg_sum[f * 4 + threadIdx.x] = t;
+    }
+}
+
+cudaError_t rr_launch_stats(const rr_frame_bufs &b, int F, int W, int H, int render_scale, double *bgf_out, cudaStream_t st) {
+    if (render_scale == 2) {
+        dim3 grid(64, F);
+        // partial sums live at the head of the (not yet used) tile_sum buffer
+        k_downscale2<<<grid, 256, 0, st>>>(b.bgr, bgf_out, b.tile_sum, W, H);
+        k_downscale2_final<<<F, 32, 0, st>>>(b.tile_sum, b.bg_sum, 64);
+        return cudaGetLastError();
+    }
     cudaMemsetAsync(b.chan_sum, 0, sizeof(unsigned long long) * 4 * F, st);
     dim3 grid(64, F);
     k_stats<<<grid, 256, 0, st>>>(b.bgr, W * H, b.chan_sum);
+    k_stats_final<<<(F * 4 + 127) / 128, 128, 0, st>>>(b.chan_sum, b.bg_sum, F);
     return cudaGetLastError();
 }
 
@@ -313,10 +368,20 @@ __global__ void __launch_bounds__(256, 2) k_fog(rr_frame_bufs b, rr_fog_consts f
         }
     }
     const double npix = (double)W * (double)H;
+    double Acs[3];
+#pragma unroll
     for (int c = 0; c < 3; c++) {
-        double sum_b = (double)b.chan_sum[f * 4 + c] / 255.0;                 // mean irradiance of the un-fogged image (:53,70)
+        double sum_b = b.bg_sum[f * 4 + c];                                    // mean irradiance of the un-fogged image (:53,70)
         double irr_mean = ((fc.irr_scale_num * sum_b) / fc.irr_den) / npix;
-        double Ac = fc.beta_hg * irr_mean;
+        Acs[c] = fc.beta_hg * irr_mean;
+    }
+    // When beta_hg * E_c <= 1 for all channels the clip at :72 can never act (0 <= 1 - f_ext <= 1), the three
+    // in-scatter images are the same image times a scalar, and one blur serves all three: blur(A*d) = A*blur(d)
+    // up to float64 rounding (shortcut 3).  Otherwise each channel is blurred on its own.
+    const bool linear = Acs[0] >= 0 && Acs[0] <= 1 && Acs[1] >= 0 && Acs[1] <= 1 && Acs[2] >= 0 && Acs[2] <= 1;
+    const int npass = linear ? 1 : 3;
+    for (int c = 0; c < npass; c++) {
+        const double Ac = linear ? 1.0 : Acs[c];
         __syncthreads();
         for (int i = tid; i < FOG_EH * FOG_EW; i += 256) {
             double li = Ac * (double)(1.0f - E[i]);                           // (1 - f_ext) is a float32 op in numpy (:71)
@@ -352,11 +417,14 @@ __global__ void __launch_bounds__(256, 2) k_fog(rr_frame_bufs b, rr_fog_consts f
                 int gy = y0 + cy0 + o, gx = x0 + cx;
                 if (gy < H && gx < W) {
                     size_t pix = (size_t)gy * W + gx;
-                    double I = (double)bgr[pix * 3 + c] / 255.0;             // generator.py:352
-                    double l = I * (double)fb[o] + acc;                      // :85
-                    l = l < 0 ? 0 : (l > 1 ? 1 : l);
-                    b.rainy[((size_t)f * 3 + c) * W * H + pix] = l;
-                    b.bg8[((size_t)f * W * H + pix) * 3 + c] = (uint8_t)(l * 255);   // bad_weather.py:744
+                    for (int cc = linear ? 0 : c; cc < (linear ? 3 : c + 1); cc++) {
+                        double I = b.bgf ? b.bgf[((size_t)f * 3 + cc) * W * H + pix] : (double)bgr[pix * 3 + cc] / 255.0;   // generator.py:352-355
+                        double lin_in = linear ? Acs[cc] * acc : acc;
+                        double l = I * (double)fb[o] + lin_in;               // :85
+                        l = l < 0 ? 0 : (l > 1 ? 1 : l);
+                        b.rainy[((size_t)f * 3 + cc) * W * H + pix] = l;
+                        b.bg8[((size_t)f * W * H + pix) * 3 + cc] = (uint8_t)(l * 255);   // bad_weather.py:744
+                    }
                 }
             }
         }
@@ -1110,8 +1178,8 @@ __global__ void k_frame_mean(rr_frame_bufs b, int n_tiles, double npix3) {
     for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
     if (threadIdx.x == 0) {
         double mean_rainy = sh[0] / npix3;                                          // generator.py:461
-        unsigned long long sb = b.chan_sum[f * 4] + b.chan_sum[f * 4 + 1] + b.chan_sum[f * 4 + 2];
-        double mean_bg = ((double)sb / 255.0) / npix3;                              // :462
+        double mean_bg = b.bgf ? ((b.bg_sum[f * 4] + b.bg_sum[f * 4 + 1]) + b.bg_sum[f * 4 + 2]) / npix3
+                               : ((double)(b.chan_sum[f * 4] + b.chan_sum[f * 4 + 1] + b.chan_sum[f * 4 + 2]) / 255.0) / npix3;   // :462
         b.frame_mean[f] = mean_rainy - mean_bg;                                     // :463
     }
 }

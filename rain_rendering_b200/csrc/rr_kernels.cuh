@@ -6,7 +6,9 @@
 
 struct rr_frame_bufs {
     // inputs (device)
-    const uint8_t *bgr;        // [F][H][W][3]
+    const uint8_t *bgr;        // [F][rs*H][rs*W][3]
+    const double *bgf;         // [F][3][H][W] reduced float64 image when render_scale == 2, else NULL
+    double *bg_sum;            // [F][4] per-channel sum of the (reduced) image in [0,1]
     const float *depth;        // [F][H][W]
     const rr_streak_rec *streaks;
     const int32_t *offsets;    // [F+1] device copy
@@ -63,7 +65,7 @@ cudaError_t rr_launch_env_tables(int W, int H, int focal_px, int cyl_w, int min_
                                  uint8_t *env_written, int32_t *cyl_first /* [H][cyl_w] scratch */, cudaStream_t st);
 cudaError_t rr_launch_omega(int H_env, int W_env, double *omega, double *omega_pref, double *omega_total, cudaStream_t st);
 // per batch
-cudaError_t rr_launch_stats(const rr_frame_bufs &b, int F, int W, int H, cudaStream_t st);
+cudaError_t rr_launch_stats(const rr_frame_bufs &b, int F, int W, int H, int render_scale, double *bgf_out, cudaStream_t st);
 cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, cudaStream_t st);
 cudaError_t rr_launch_env(const rr_frame_bufs &b, const rr_static_tabs &t, int F, int W, int H, int W_env, cudaStream_t st);
 cudaError_t rr_launch_setup(const rr_frame_bufs &b, const rr_static_tabs &t, const rr_cam_dev &cam, int F, int n_streaks,

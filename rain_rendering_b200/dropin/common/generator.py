@@ -103,11 +103,12 @@ class Generator:
 
     # ------------------------------------------------------------------------------------------
     def _decode(self, image_file, depth_file):
-        """generator.py:352-381 on the decode side (I/O): uint8 BGR image and float32 depth."""
+        """generator.py:352-381 on the decode side (I/O): uint8 BGR image (at sensor resolution: the
+        render_scale reduction of generator.py:354-355 happens on the device) and float32 depth."""
         bg = cv2.imread(image_file)
-        if self.settings["render_scale"] != 1:
-            raise NotImplementedError("render_scale != 1 (the reference resizes the float image on the host, generator.py:354-355) "
-                                      "is not wired into the uint8 C ABI yet")
+        rs = self.settings["render_scale"]
+        if rs not in (1, 2) or bg.shape[0] % rs or bg.shape[1] % rs:
+            raise NotImplementedError("render_scale %r: only 1 and an exact factor 2 (cv2's 2x2 area path) are implemented on the device" % (rs,))
         if depth_file.endswith(".png"):
             depth = cv2.imread(depth_file, cv2.IMREAD_UNCHANGED)
             if depth is None:
@@ -118,13 +119,17 @@ class Generator:
             depth = np.load(depth_file).astype(np.float32)
         else:
             raise Exception("Invalid extension")
-        depthHW = np.array([int((depth.shape[0] * self.settings["depth_scale"]) // self.settings["render_scale"]),
-                            int((depth.shape[1] * self.settings["depth_scale"]) // self.settings["render_scale"])])
+        depthHW = np.array([int((depth.shape[0] * self.settings["depth_scale"]) // rs),
+                            int((depth.shape[1] * self.settings["depth_scale"]) // rs)])
         if not np.all(depth.shape[:2] == depthHW):
             depth = cv2.resize(depth, (depthHW[1], depthHW[0]))
-        assert (np.all(depth.shape[:2] <= bg.shape[:2])), "Depth cannot be larger than the image"
-        if not np.all(depth.shape[:2] == bg.shape[:2]):
-            bg = my_utils.crop_center(bg, depth.shape[0], depth.shape[1])
+        rh, rw = bg.shape[0] // rs, bg.shape[1] // rs
+        assert depth.shape[0] <= rh and depth.shape[1] <= rw, "Depth cannot be larger than the image"
+        if (depth.shape[0], depth.shape[1]) != (rh, rw):
+            # crop_center of the reduced image (generator.py:379-381) == the same crop at sensor resolution
+            x1 = int((rh - depth.shape[0]) / 2) * rs
+            y1 = int((rw - depth.shape[1]) / 2) * rs
+            bg = bg[x1:x1 + depth.shape[0] * rs, y1:y1 + depth.shape[1] * rs]
         return np.ascontiguousarray(bg), np.ascontiguousarray(depth, dtype=np.float32)
 
     def run(self):
@@ -175,7 +180,8 @@ class Generator:
                 ctx.set_streak_db(self.db.streaks_light, self.db.ratio)
                 gain = self.camera_gain if self.camera_gain else 20      # generator.py:232-233,260-261
                 ctx.set_camera(imW, imH, focal_mm=self.focal * 1000., f_number=self.f_number, exposure_ms=self.exposure, gain=gain,
-                               fallrate=fallrate, opacity_attenuation=self.opacity_attenuation, max_batch=self.batch)
+                               fallrate=fallrate, opacity_attenuation=self.opacity_attenuation, max_batch=self.batch,
+                               render_scale=self.settings["render_scale"])
                 f_start, f_end, f_step = self.frame_start, self.frame_end, self.frame_step
                 f_end = len(files) if f_end is None else min(f_end, len(files))
                 if self.frames:
@@ -194,7 +200,7 @@ class Generator:
                     depth = np.stack([p[1] for p in pending])
                     recs = np.concatenate([p[2] for p in pending])
                     offs = np.concatenate([[0], np.cumsum([len(p[2]) for p in pending])]).astype(np.int32)
-                    if (bgr.shape[2], bgr.shape[1]) != (ctx.W, ctx.H):
+                    if (bgr.shape[2], bgr.shape[1]) != (ctx.W * ctx.render_scale, ctx.H * ctx.render_scale):
                         raise AssertionError("frame size %s differs from the sequence size (%d, %d) (generator.py:250-258 reads it once)" % (bgr.shape, ctx.W, ctx.H))
                     out = ctx.render_frames(bgr, depth, recs, offs, want=("mask", "u8"))
                     for k, p in enumerate(pending):

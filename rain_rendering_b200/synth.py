@@ -194,18 +194,21 @@ def write_particles_xml(frames, path: str, exposure_ms: float):
 
 
 def write_dataset(root: str, dataset: str, seq: str, W: int, H: int, n_frames: int, fallrate: int,
-                  n_xml: int, seed: int = 0, n_sim_frames: int | None = None):
+                  n_xml: int, seed: int = 0, n_sim_frames: int | None = None, render_scale: int | None = None):
     """Lay out a complete reference-style tree under ``root`` (customdb layout,
     config/customdb.py:5-20): images, uint16 depth PNGs, streak DB and particles XML.
     Returns the dict of paths main.check_arg needs."""
     import cv2
     cam = CAMERAS[dataset]
-    rs = cam["render_scale"]
+    rs = render_scale or cam["render_scale"]
     src = os.path.join(root, "source", dataset, seq)
     os.makedirs(os.path.join(src, "rgb"), exist_ok=True)
     os.makedirs(os.path.join(src, "depth"), exist_ok=True)
     for i in range(n_frames):
-        bgr, depth = make_frame(W * rs, H * rs, seed * 1000 + i)
+        # the image at sensor resolution (W*rs, H*rs); the depth map at render resolution (depth_scale = rs,
+        # the Cityscapes arrangement, config/cityscapes.py:41-42)
+        bgr, _ = make_frame(W * rs, H * rs, seed * 1000 + i)
+        _, depth = make_frame(W, H, seed * 1000 + i)
         cv2.imwrite(os.path.join(src, "rgb", "%06d.png" % i), bgr)
         cv2.imwrite(os.path.join(src, "depth", "%06d.png" % i), np.round(depth * 256.0).astype(np.uint16))
     db = make_streak_db(seed)

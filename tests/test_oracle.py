@@ -87,6 +87,32 @@ def test_oracle_bit_exact_against_live_reference():
         shutil.rmtree(root, ignore_errors=True)
 
 
+@pytest.mark.skipif(not ref_harness.reference_available(), reason="reference tree not mounted")
+def test_oracle_bit_exact_against_live_reference_render_scale_2():
+    """Cityscapes arrangement (config/cityscapes.py:41-42): frames at twice the render size, depth at
+    render size, simulator positions at sensor resolution."""
+    from rain_rendering_b200 import synth
+    root = tempfile.mkdtemp(prefix="rr_live2_")
+    try:
+        W, H = 192, 128
+        paths = synth.write_dataset(root, "customdb", "seq1", W, H, 1, 50, 900, seed=6, render_scale=2)
+        ref = ref_harness.run_reference(paths, "customdb", 50, settings_override={"render_scale": 2, "depth_scale": 2})
+        cam = ro.Camera(W=W, H=H, fallrate=50)
+        tex, ratios = ro.load_streak_database(os.path.join(paths["streaks_db"], "env_light_database", "size32"),
+                                              os.path.join(paths["streaks_db"], "env_light_database", "txt", "normalized_env_max.txt"))
+        frames = ro.load_streaks_from_xml(paths["xml"], 2, W, H)
+        name = sorted(ref)[0]
+        bg, depth = ro.read_frame(os.path.join(root, "source/customdb/seq1/rgb", name + ".png"),
+                                  os.path.join(root, "source/customdb/seq1/depth", name + ".png"))
+        assert bg.shape[:2] == (2 * H, 2 * W) and depth.shape == (H, W)
+        r = ro.render_frame(bg, depth, frames[0], tex, ratios, cam, 0, render_scale=2)
+        assert np.array_equal(r.fog, ref[name]["fog"])
+        assert np.array_equal(np.clip(r.out_bgr[..., ::-1], 0, 1), ref[name]["rainy_rgb"])
+        assert np.array_equal(r.rain_mask, ref[name]["rain_mask"]) and r.n_streaks == len(ref[name]["streaks"]) > 5
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def test_env_tables_match_reference_formula_for_all_baseline_sizes():
     # shapes quoted in SURVEY.md section 8: C1 480x985, C2 375x1909, C3 512x1573, C4 900x2373
     for (W, H, f_mm, want) in [(640, 480, 6.0, 985), (1242, 375, 6.0, 1909), (1024, 512, 6.0, 1573), (1600, 900, 5.5, 2373)]:

@@ -50,6 +50,20 @@ def test_full_frames_match_oracle(W, H, n_xml, dataset, fallrate, noise):
     ctx.close()
 
 
+def test_render_scale_2_cityscapes_arrangement():
+    """BASELINE C3 shape: frames arrive at twice the render size and are reduced on the device."""
+    sc = Scenario(512, 256, 2, 1800, fallrate=50, dataset="cityscapes", render_scale=2)
+    assert sc.bgr.shape == (2, 512, 1024, 3)
+    ctx = sc.context()
+    recs, offs = sc.records()
+    out = ctx.render_frames(sc.bgr, sc.depth, recs, offs)
+    for i in range(sc.n_frames):
+        o = sc.oracle_frame(i, "canonical")
+        assert o.n_streaks == offs[i + 1] - offs[i] > 20
+        _check_frame(out, i, o)
+    ctx.close()
+
+
 def test_stage_parity_tables_fog_env_photometry():
     sc = Scenario(640, 480, 1, 1500, fallrate=25)
     ctx = sc.context()

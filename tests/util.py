@@ -13,23 +13,23 @@ from rain_rendering_b200 import api, streaks as S, synth
 
 class Scenario:
     def __init__(self, W, H, n_frames, n_xml, fallrate=25, dataset="kitti", noise_scale=0.0, noise_std=0.0,
-                 opacity=1.0, seed=0, n_sim_frames=None):
+                 opacity=1.0, seed=0, n_sim_frames=None, render_scale=1):
         cam = synth.CAMERAS[dataset]
-        self.W, self.H, self.n_frames = W, H, n_frames
+        self.W, self.H, self.n_frames, self.render_scale = W, H, n_frames, render_scale
         self.cam = ro.Camera(W=W, H=H, focal_mm=cam["cam_focal"], f_number=cam["cam_f_number"],
                              exposure_ms=cam["cam_exposure"], gain=cam["cam_gain"], fallrate=fallrate,
                              opacity_attenuation=opacity, noise_scale=noise_scale, noise_std=noise_std)
         self.db = synth.make_streak_db(seed)
-        frames = [synth.make_frame(W, H, seed * 1000 + i) for i in range(n_frames)]
-        self.bgr = np.stack([f[0] for f in frames])
-        self.depth = np.stack([f[1] for f in frames])
+        rs = render_scale
+        self.bgr = np.stack([synth.make_frame(W * rs, H * rs, seed * 1000 + i)[0] for i in range(n_frames)])
+        self.depth = np.stack([synth.make_frame(W, H, seed * 1000 + i)[1] for i in range(n_frames)])
         nsf = n_sim_frames or n_frames
-        parts = synth.make_particles(W, H, nsf, n_xml, cam["cam_exposure"], seed, 1)
+        parts = synth.make_particles(W, H, nsf, n_xml, cam["cam_exposure"], seed, rs)
         with tempfile.TemporaryDirectory() as d:
             xml = os.path.join(d, "sim_camera0.xml")
             synth.write_particles_xml(parts, xml, cam["cam_exposure"])
-            self.oracle_frames = ro.load_streaks_from_xml(xml, 1, W, H)
-            self.sim_frames = S.load_streaks_from_xml(xml, 1, W, H)
+            self.oracle_frames = ro.load_streaks_from_xml(xml, rs, W, H)
+            self.sim_frames = S.load_streaks_from_xml(xml, rs, W, H)
         self._tables = None
         self._omega = None
 
@@ -49,7 +49,7 @@ class Scenario:
     def oracle_frame(self, i, f32_mode="canonical", keep_patches=False):
         return ro.render_frame(self.bgr[i], self.depth[i], self.oracle_frames[i % len(self.oracle_frames)],
                                self.db.textures, self.db.ratios, self.cam, i, self.tables, self.omega,
-                               f32_mode=f32_mode, keep_patches=keep_patches)
+                               f32_mode=f32_mode, keep_patches=keep_patches, render_scale=getattr(self, "render_scale", 1))
 
     # ---- product side ----
     def records(self):
@@ -68,7 +68,7 @@ class Scenario:
         ctx.set_streak_db(self.db.textures, self.db.ratios)
         c = self.cam
         ctx.set_camera(self.W, self.H, c.focal_mm, c.f_number, c.exposure_ms, c.gain, c.fallrate, c.opacity_attenuation,
-                       max_batch or self.n_frames)
+                       max_batch or self.n_frames, render_scale=getattr(self, "render_scale", 1))
         return ctx
 
 
@@ -90,7 +90,7 @@ def golden_scenario(name: str):
     g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     W, H, nf = int(g["W"]), int(g["H"]), int(g["n_frames"])
     sc = Scenario.__new__(Scenario)
-    sc.W, sc.H, sc.n_frames = W, H, nf
+    sc.W, sc.H, sc.n_frames, sc.render_scale = W, H, nf, 1
     cam = synth.CAMERAS["customdb"]
     sc.cam = ro.Camera(W=W, H=H, focal_mm=cam["cam_focal"], f_number=cam["cam_f_number"], exposure_ms=cam["cam_exposure"],
                        gain=cam["cam_gain"], fallrate=int(g["fallrate"]), opacity_attenuation=float(g["opacity"]),
