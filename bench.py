@@ -47,7 +47,7 @@ def build_batch(wl, rank, batch):
     W, H = wl["W"], wl["H"]
     cam = synth.CAMERAS[wl["dataset"]]
     db = synth.make_streak_db(0)
-    frames = [synth.make_frame(W, H, 100000 * rank + i) for i in range(batch)]
+    frames = [synth.make_frame(W, H, 1000 * rank + i) for i in range(batch)]
     bgr = np.stack([f[0] for f in frames])
     depth = np.stack([f[1] for f in frames])
     parts = synth.make_particles(W, H, batch, wl["n_xml"], cam["cam_exposure"], seed=1000 + rank)

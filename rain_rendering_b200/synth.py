@@ -57,7 +57,7 @@ def make_frame(W: int, H: int, seed: int):
     height like a road scene.  Depth is quantised to 1/256 m so the uint16 PNG round trip
     of the reference (common/generator.py:360-365: ``imread(...)/256.``) is lossless.
     """
-    rng = np.random.RandomState(1234 + 7919 * seed)
+    rng = np.random.RandomState((1234 + 7919 * int(seed)) % (2 ** 32))
     small = rng.uniform(0, 255, size=(max(H // 8, 2), max(W // 8, 2), 3))
     img = _bilinear_upsample(small, H, W)
     sky = np.linspace(70.0, -25.0, H)[:, None, None]
@@ -90,7 +90,7 @@ DB_HEIGHTS = (640, 320, 160, 80, 40)
 def make_streak_db(seed: int = 0, heights=DB_HEIGHTS, width: int = 32) -> StreakDB:
     """5 ``cv`` x 10 ``osc`` textures, width 32, Gaussian-profile streaks with an
     osc-dependent modulation, 16-bit, plus normalisation coefficients in [0.5, 0.95]."""
-    rng = np.random.RandomState(4321 + seed)
+    rng = np.random.RandomState((4321 + int(seed)) % (2 ** 32))
     raw16, textures, norm = [], [], {}
     for k, h in enumerate(heights):
         coeffs = [float(np.round(rng.uniform(0.5, 0.95), 6)) for _ in range(10)]
@@ -144,7 +144,7 @@ def make_particles(W: int, H: int, n_frames: int, n_xml: int, exposure_ms: float
     Returns a list (per frame) of dicts of arrays: pid, wp1, wp2 (n,3), wd (n,), ip1, ip2 (n,2),
     iw1, iw2 (n,).  Pinhole with f_px = 6e-3/4.65e-6 * (W*render_scale/1242).
     """
-    rng = np.random.RandomState(99 + seed)
+    rng = np.random.RandomState((99 + int(seed)) % (2 ** 32))
     Wf, Hf = W * render_scale, H * render_scale
     f_px = 6e-3 / 4.65e-6 * (Wf / 1242.0)
     T = exposure_ms / 1000.0
