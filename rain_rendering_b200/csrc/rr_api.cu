@@ -178,6 +178,7 @@ static int ensure_streak_cap(rr_context *c, int n) {
     CK(dev_alloc(c, &c->d_streaks, (size_t)cap));
     CK(dev_alloc(c, &c->fb.plans, (size_t)cap));
     CK(dev_alloc(c, &c->fb.sizes, (size_t)cap));
+    CK(dev_alloc(c, &c->fb.boxes, (size_t)cap));
     CK(dev_alloc(c, &c->fb.scan, (size_t)(cap + 1 + RR_MAX_SUB) * 6));
     c->streak_cap = cap;
     return RR_OK;
@@ -339,7 +340,7 @@ static rr_frame_bufs sub_view(const rr_context *c, const rr_frame_bufs &b, int f
     v.chan_sum += (size_t)f0 * 4; v.rainy += (size_t)f0 * 3 * np; v.bg8 += (size_t)f0 * np * 3; v.fblur += (size_t)f0 * np;
     v.env_fill += (size_t)f0 * npe * 3; v.env8 += (size_t)f0 * npe * 3;
     v.pref += (size_t)f0 * 4 * c->H_env * (c->W_env + 1); v.rowtot += (size_t)f0 * c->H_env; v.ambient += f0;
-    v.plans += s0; v.sizes += s0; v.scan += (size_t)scan_base * 6;
+    v.plans += s0; v.sizes += s0; v.boxes += s0; v.scan += (size_t)scan_base * 6;
     v.tile_sum += (size_t)f0 * tiles; v.frame_mean += f0;
     if (v.out_bgr) v.out_bgr += (size_t)f0 * np * 3;
     if (v.out_mask) v.out_mask += (size_t)f0 * np;

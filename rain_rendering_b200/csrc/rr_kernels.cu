@@ -538,10 +538,10 @@ __global__ void __launch_bounds__(256) k_env_blur(const uint8_t *env_fill, const
 // one block per (row, frame): xyY, solid-angle weighting, row prefix sums  (generator.py:407-408,
 // bad_weather.py:393-395).  pref is interleaved: [F][H][W_env+1][4] = prefix of (w*x, w*y, w*Y, w), so one
 // 32-byte sector serves a span end point in k_setup.
-#define ENVP_MAX_PER 12
-__global__ void __launch_bounds__(256, 2) k_env_prefix(const uint8_t *env8, const double *omega, double *pref, double *rowtot,
+__global__ void __launch_bounds__(256) k_env_prefix(const uint8_t *env8, const double *omega, double *pref, double *rowtot,
                                                     int H, int W_env) {
-    __shared__ double lut[256];
+    extern __shared__ double envp_smem[];          // [3][W_env] weighted x, y, Y of the row, then the 256-entry LUT
+    double *vx = envp_smem, *vy = vx + W_env, *vY = vy + W_env, *lut = vY + W_env;
     __shared__ double wtot[4][8];
     lut[threadIdx.x] = (double)threadIdx.x / 255.0;
     int r = blockIdx.x, f = blockIdx.y;
@@ -550,25 +550,20 @@ __global__ void __launch_bounds__(256, 2) k_env_prefix(const uint8_t *env8, cons
     int per = (W_env + 255) / 256;
     int c0 = threadIdx.x * per, c1 = c0 + per < W_env ? c0 + per : W_env;
     __syncthreads();
-    double vx[ENVP_MAX_PER], vy[ENVP_MAX_PER], vY[ENVP_MAX_PER];
     double sx = 0, sy = 0, sY = 0, sw = 0;
-#pragma unroll
-    for (int k = 0; k < ENVP_MAX_PER; k++) {
-        int c = c0 + k;
-        vx[k] = vy[k] = vY[k] = 0;
-        if (k < per && c < c1) {
-            double bb = lut[row[c * 3]], gg = lut[row[c * 3 + 1]], rr = lut[row[c * 3 + 2]];
-            double X = ((rr * 0.49000 + gg * 0.17697) + bb * 0.00000) / 0.17697;      // my_utils.py:56-59 (row vector x M)
-            double Y = ((rr * 0.31000 + gg * 0.81240) + bb * 0.01000) / 0.17697;
-            double Z = ((rr * 0.20000 + gg * 0.01063) + bb * 0.99000) / 0.17697;
-            double S = (X + Y) + Z;
-            double x = X / S, y = Y / S;
-            if (!(x == x)) x = 0;                                                      // generator.py:408
-            if (!(y == y)) y = 0;
-            double w = om[c];
-            vx[k] = x * w; vy[k] = y * w; vY[k] = Y * w;
-            sx += vx[k]; sy += vy[k]; sY += vY[k]; sw += w;
-        }
+    for (int c = c0; c < c1; c++) {
+        double bb = lut[row[c * 3]], gg = lut[row[c * 3 + 1]], rr = lut[row[c * 3 + 2]];
+        double X = ((rr * 0.49000 + gg * 0.17697) + bb * 0.00000) / 0.17697;      // my_utils.py:56-59 (row vector x M)
+        double Y = ((rr * 0.31000 + gg * 0.81240) + bb * 0.01000) / 0.17697;
+        double Z = ((rr * 0.20000 + gg * 0.01063) + bb * 0.99000) / 0.17697;
+        double S = (X + Y) + Z;
+        double x = X / S, y = Y / S;
+        if (!(x == x)) x = 0;                                                      // generator.py:408
+        if (!(y == y)) y = 0;
+        double w = om[c];
+        double ax_ = x * w, ay_ = y * w, aY_ = Y * w;
+        vx[c] = ax_; vy[c] = ay_; vY[c] = aY_;
+        sx += ax_; sy += ay_; sY += aY_; sw += w;
     }
     // block-wide exclusive scan of the thread totals: warp shuffles + the 8 warp totals (fixed tree: deterministic)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -596,15 +591,24 @@ __global__ void __launch_bounds__(256, 2) k_env_prefix(const uint8_t *env8, cons
         p[W_env] = make_double4(allx, ally, allY, allw);
         rowtot[(size_t)f * H + r] = allY;
     }
-    if (per > ENVP_MAX_PER) return;    // rr_set_camera rejects such widths
-#pragma unroll
-    for (int k = 0; k < ENVP_MAX_PER; k++) {
-        int c = c0 + k;
-        if (k < per && c < c1) {
-            p[c] = make_double4(ax, ay, aY, aw);
-            ax += vx[k]; ay += vy[k]; aY += vY[k]; aw += om[c];
-        }
+    for (int c = c0; c < c1; c++) {
+        p[c] = make_double4(ax, ay, aY, aw);
+        ax += vx[c]; ay += vy[c]; aY += vY[c]; aw += om[c];
     }
+}
+
+static cudaError_t launch_env_prefix(const uint8_t *env8, const double *omega, double *pref, double *rowtot, int F, int H, int W_env,
+                                     cudaStream_t st) {
+    size_t smem = sizeof(double) * (3 * (size_t)W_env + 256);
+    static size_t attr = 0;
+    if (smem > attr) {
+        cudaError_t e = cudaFuncSetAttribute(k_env_prefix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = smem;
+    }
+    dim3 g3(H, F);
+    k_env_prefix<<<g3, 256, smem, st>>>(env8, omega, pref, rowtot, H, W_env);
+    return cudaGetLastError();
 }
 
 __global__ void k_ambient(const double *rowtot, double *ambient, int H) {
@@ -622,8 +626,8 @@ cudaError_t rr_launch_env(const rr_frame_bufs &b, const rr_static_tabs &t, int F
     k_env_gather<<<g1, 256, 0, st>>>(b.bg8, t.env_src, b.env_fill, W * H, npe);
     dim3 g2((W_env + ENV_TX - 1) / ENV_TX, (H + ENV_TY - 1) / ENV_TY, F);
     k_env_blur<<<g2, 256, 0, st>>>(b.env_fill, t.env_written, b.env8, H, W_env);
-    dim3 g3(H, F);
-    k_env_prefix<<<g3, 256, 0, st>>>(b.env8, t.omega, b.pref, b.rowtot, H, W_env);
+    cudaError_t e = launch_env_prefix(b.env8, t.omega, b.pref, b.rowtot, F, H, W_env, st);
+    if (e != cudaSuccess) return e;
     k_ambient<<<F, 32, 0, st>>>(b.rowtot, b.ambient, H);
     return cudaGetLastError();
 }
@@ -778,6 +782,7 @@ __global__ void __launch_bounds__(1024) k_scan(rr_frame_bufs b, int n) {
         int4 sz = b.sizes[i];
         long long g = sz.x, v = sz.y, a = sz.z;
         if (overflow) { p.valid = 0; p.bw = p.bh = 0; }
+        b.boxes[i] = (p.valid && a > 0) ? make_int4(p.bx0, p.by0, p.bw, p.bh) : make_int4(0, 0, 0, 0);
         long long *sc = b.scan + (size_t)i * 6;
         sc[0] = el; sc[1] = el + g; sc[2] = el + g + v; sc[3] = c0; sc[4] = c1; sc[5] = c2;
         p.g_off = el; p.a_off = el + g + v;
@@ -870,8 +875,8 @@ __global__ void __launch_bounds__(RAS_THREADS, 4) k_raster(rr_frame_bufs b, rr_s
         const bool staged = p.type != RR_BIG && (p.resize_mode == RR_RESIZE_AREA || p.resize_mode == RR_RESIZE_AREA_FAST) &&
                             p.nW <= RAS_MAXW && p.pw <= RAS_TXN && p.ph <= RAS_TXN && g <= RAS_MAXD;
         if (!staged) {
-            for (long long e = tid; e < g; e += RAS_THREADS) {
-                int y = (int)(e / p.pw), x = (int)(e - (long long)y * p.pw);
+            for (int e = tid; e < (int)g; e += RAS_THREADS) {
+                int y = e / p.pw, x = e - y * p.pw;
                 out[e] = rr_patch_pixel(p, tex, tw, d_cubic, x, y);
             }
             continue;
@@ -1011,55 +1016,63 @@ __device__ __forceinline__ void load_weights(double sigma, int r, double *w) {
     __syncthreads();
 }
 
-__global__ void __launch_bounds__(RR_BLUR_CHUNK) k_blur_v(rr_frame_bufs b, int n) {
+// chunk -> streak lookup done once per block
+__device__ __forceinline__ int find_streak_block(const long long *scan, int n, int field, long long chunk) {
+    __shared__ int s_idx;
+    __syncthreads();
+    if (threadIdx.x == 0) s_idx = find_streak(scan, n, field, chunk);
+    __syncthreads();
+    return s_idx;
+}
+
+__global__ void __launch_bounds__(RR_BLUR_THREADS) k_blur_v(rr_frame_bufs b, int n) {
     __shared__ double w[2 * RR_MAX_GAUSS_R + 1];
     const long long total = b.scan[(size_t)n * 6 + 4];
     for (long long ch = blockIdx.x; ch < total; ch += gridDim.x) {
-        int s = find_streak(b.scan, n, 4, ch);
+        const int s = find_streak_block(b.scan, n, 4, ch);
         const rr_plan &p = b.plans[s];
-        __syncthreads();
         load_weights(p.sig_y, p.ry, w);
         long long gg, nv, aa; int vx0, vw;
         plan_sizes(p, &gg, &nv, &aa, &vx0, &vw);
-        long long e = (ch - b.scan[(size_t)s * 6 + 4]) * RR_BLUR_CHUNK + threadIdx.x;
-        if (e < nv) {
-            int yy = (int)(e / vw), xx = (int)(e - (long long)yy * vw);
-            int Y = p.cropy + yy;            // padded row
-            int gx = vx0 + xx - p.shift;     // patch column
-            int gy = Y - p.shift;            // patch row of the centre tap (may be outside)
-            const double *g = b.arena + p.g_off;
-            const int ry = p.ry;
+        const int base = (int)((ch - b.scan[(size_t)s * 6 + 4]) * RR_BLUR_CHUNK);
+        const int pw = p.pw, ph = p.ph, ry = p.ry, cropy = p.cropy, shift = p.shift;
+        const double *g = b.arena + p.g_off;
+        double *vout = b.arena + b.scan[(size_t)s * 6 + 1];
+        for (int e = base + threadIdx.x; e < base + RR_BLUR_CHUNK && e < (int)nv; e += RR_BLUR_THREADS) {
+            int yy = e / vw, xx = e - yy * vw;
+            int gx = vx0 + xx - shift;       // patch column
+            int gy = cropy + yy - shift;     // patch row of the centre tap (may be outside: zero padding)
             // SciPy correlate1d, symmetric weights: centre first, then pairs from the outside in
-            double c = (gy >= 0 && gy < p.ph) ? g[(size_t)gy * p.pw + gx] : 0.0;
+            double c = (gy >= 0 && gy < ph) ? g[gy * pw + gx] : 0.0;
             double tmp = c * w[ry];
             for (int jj = -ry; jj < 0; jj++) {
                 int ya = gy + jj, yb = gy - jj;
-                double va = (ya >= 0 && ya < p.ph) ? g[(size_t)ya * p.pw + gx] : 0.0;
-                double vb = (yb >= 0 && yb < p.ph) ? g[(size_t)yb * p.pw + gx] : 0.0;
+                double va = (ya >= 0 && ya < ph) ? g[ya * pw + gx] : 0.0;
+                double vb = (yb >= 0 && yb < ph) ? g[yb * pw + gx] : 0.0;
                 tmp += (va + vb) * w[jj + ry];
             }
-            b.arena[b.scan[(size_t)s * 6 + 1] + e] = tmp;
+            vout[e] = tmp;
         }
     }
 }
 
-__global__ void __launch_bounds__(RR_BLUR_CHUNK) k_blur_h(rr_frame_bufs b, int n) {
+__global__ void __launch_bounds__(RR_BLUR_THREADS) k_blur_h(rr_frame_bufs b, int n) {
     __shared__ double w[2 * RR_MAX_GAUSS_R + 1];
     const long long total = b.scan[(size_t)n * 6 + 5];
     for (long long ch = blockIdx.x; ch < total; ch += gridDim.x) {
-        int s = find_streak(b.scan, n, 5, ch);
+        const int s = find_streak_block(b.scan, n, 5, ch);
         const rr_plan &p = b.plans[s];
-        __syncthreads();
         load_weights(p.sig_x, p.rx, w);
         long long gg, vv, na; int vx0, vw;
         plan_sizes(p, &gg, &vv, &na, &vx0, &vw);
-        long long e = (ch - b.scan[(size_t)s * 6 + 5]) * RR_BLUR_CHUNK + threadIdx.x;
-        if (e < na) {
-            int yy = (int)(e / p.bw), xx = (int)(e - (long long)yy * p.bw);
-            int X = p.cropx + xx;            // padded column of the output
-            const double *v = b.arena + b.scan[(size_t)s * 6 + 1] + (size_t)yy * vw;
-            const int rx = p.rx;
-            int xc = X - vx0;
+        const int base = (int)((ch - b.scan[(size_t)s * 6 + 5]) * RR_BLUR_CHUNK);
+        const int bw = p.bw, rx = p.rx, cropx = p.cropx;
+        const double *vin = b.arena + b.scan[(size_t)s * 6 + 1];
+        double *aout = b.arena + p.a_off;
+        for (int e = base + threadIdx.x; e < base + RR_BLUR_CHUNK && e < (int)na; e += RR_BLUR_THREADS) {
+            int yy = e / bw, xx = e - yy * bw;
+            const double *v = vin + yy * vw;
+            int xc = cropx + xx - vx0;        // column of the centre tap in the column-pass result
             double c = (xc >= 0 && xc < vw) ? v[xc] : 0.0;
             double tmp = c * w[rx];
             for (int jj = -rx; jj < 0; jj++) {
@@ -1068,15 +1081,15 @@ __global__ void __launch_bounds__(RR_BLUR_CHUNK) k_blur_h(rr_frame_bufs b, int n
                 double vb = (xb >= 0 && xb < vw) ? v[xb] : 0.0;
                 tmp += (va + vb) * w[jj + rx];
             }
-            b.arena[p.a_off + e] = tmp;
+            aout[e] = tmp;
         }
     }
 }
 
 cudaError_t rr_launch_blur(const rr_frame_bufs &b, int n_streaks, int n_sm, cudaStream_t st) {
     if (n_streaks == 0) return cudaSuccess;
-    k_blur_v<<<n_sm * 4, RR_BLUR_CHUNK, 0, st>>>(b, n_streaks);
-    k_blur_h<<<n_sm * 4, RR_BLUR_CHUNK, 0, st>>>(b, n_streaks);
+    k_blur_v<<<n_sm * 8, RR_BLUR_THREADS, 0, st>>>(b, n_streaks);
+    k_blur_h<<<n_sm * 8, RR_BLUR_THREADS, 0, st>>>(b, n_streaks);
     return cudaGetLastError();
 }
 
@@ -1112,8 +1125,9 @@ __global__ void __launch_bounds__(RR_TILE_W * RR_TILE_H) k_composite(rr_frame_bu
         const rr_plan *pp = b.plans + (s < s1 ? s : s0);
         int pbx0 = 0, pby0 = 0, pbw = 0, pbh = 0;
         if (s < s1) {
-            pbx0 = pp->bx0; pby0 = pp->by0; pbw = pp->bw; pbh = pp->bh;
-            hit = pp->valid && pbw > 0 && pbh > 0 && pbx0 < tx0 + RR_TILE_W && pbx0 + pbw > tx0 &&
+            int4 box = b.boxes[s];                       // (bx0, by0, bw, bh), bw = 0 for streaks that draw nothing
+            pbx0 = box.x; pby0 = box.y; pbw = box.z; pbh = box.w;
+            hit = pbw > 0 && pbh > 0 && pbx0 < tx0 + RR_TILE_W && pbx0 + pbw > tx0 &&
                   pby0 < ty0 + RR_TILE_H && pby0 + pbh > ty0;
         }
         unsigned bal = __ballot_sync(0xffffffffu, hit);
@@ -1219,8 +1233,8 @@ cudaError_t rr_launch_epilogue(const rr_frame_bufs &b, int F, int W, int H, cuda
 }
 
 cudaError_t rr_launch_env_prefix_only(const rr_frame_bufs &b, const rr_static_tabs &t, int F, int H, int W_env, cudaStream_t st) {
-    dim3 g3(H, F);
-    k_env_prefix<<<g3, 256, 0, st>>>(b.env8, t.omega, b.pref, b.rowtot, H, W_env);
+    cudaError_t e = launch_env_prefix(b.env8, t.omega, b.pref, b.rowtot, F, H, W_env, st);
+    if (e != cudaSuccess) return e;
     k_ambient<<<F, 32, 0, st>>>(b.rowtot, b.ambient, H);
     return cudaGetLastError();
 }

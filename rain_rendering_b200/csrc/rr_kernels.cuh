@@ -23,6 +23,7 @@ struct rr_frame_bufs {
     double *rowtot;            // [F][H] row totals of omega*Y
     double *ambient;           // [F] sum over the map of omega*Y
     rr_plan *plans;            // [n_streaks]
+    int4 *boxes;               // [n_streaks] (bx0, by0, bw, bh) of the composited block, zeros when nothing is drawn (k_scan)
     int4 *sizes;               // [n_streaks] arena elements (g, v, a) of each streak, written by k_setup for k_scan
     long long *scan;           // [n_streaks+1][4] exclusive prefix: g elems, a elems, raster chunks, blur chunks
     double *arena;             // patch arena
@@ -55,7 +56,8 @@ struct rr_fog_consts {
 };
 
 #define RR_RASTER_CHUNK 128
-#define RR_BLUR_CHUNK 256
+#define RR_BLUR_CHUNK 1024       // elements per work-list chunk (4 per thread)
+#define RR_BLUR_THREADS 256
 #define RR_TILE_W 32
 #define RR_TILE_H 8
 
