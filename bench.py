@@ -189,7 +189,10 @@ def run_reference(args):
     if rank != 0:
         return
     cores = host_cores()
-    workers = max(1, min(cores, 64))
+    # one process per frame like main_threaded.py (at most 10 children there).  More than ~16 concurrent renders
+    # do not raise the throughput on the B200 host (memory-bound masked gathers: 64 processes 1.53 frames/s,
+    # 32 processes 1.8 frames/s on 128 cores) and only stretch the step, so the sample is capped at 16.
+    workers = max(1, min(cores, 16))
     wl = synth.WORKLOADS[WORKLOAD]
     times, streaks = cpu_steps(args.steps, args.warmup, workers)
     total = float(np.sum(times))
@@ -339,7 +342,7 @@ def run_gpu(args):
                              "algorithmic_bytes_per_frame": balg, "whole_step_frac": (balg * batch / (ms_dev / args.steps / 1000.0) / 1e9) / peak},
                 "stage_ms": kern}
         if world == 1 and not args.no_cpu_baseline:
-            workers = max(1, min(host_cores(), 32))
+            workers = max(1, min(host_cores(), 16))
             times, streaks = cpu_steps(1, 1, workers)
             fps = workers / times[0]
             line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": workers, "kind": "port",

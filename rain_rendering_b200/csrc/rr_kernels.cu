@@ -540,8 +540,10 @@ __global__ void __launch_bounds__(256) k_env_blur(const uint8_t *env_fill, const
 // 32-byte sector serves a span end point in k_setup.
 __global__ void __launch_bounds__(256) k_env_prefix(const uint8_t *env8, const double *omega, double *pref, double *rowtot,
                                                     int H, int W_env) {
-    extern __shared__ double envp_smem[];          // [3][W_env] weighted x, y, Y of the row, then the 256-entry LUT
-    double *vx = envp_smem, *vy = vx + W_env, *vY = vy + W_env, *lut = vY + W_env;
+    extern __shared__ double envp_smem[];          // [3][per][256] weighted x, y, Y of the row (element k of thread t at
+                                                   // k*256 + t: conflict free), then the 256-entry LUT
+    const int per_ = (W_env + 255) / 256;
+    double *vx = envp_smem, *vy = vx + per_ * 256, *vY = vy + per_ * 256, *lut = vY + per_ * 256;
     __shared__ double wtot[4][8];
     lut[threadIdx.x] = (double)threadIdx.x / 255.0;
     int r = blockIdx.x, f = blockIdx.y;
@@ -562,7 +564,8 @@ __global__ void __launch_bounds__(256) k_env_prefix(const uint8_t *env8, const d
         if (!(y == y)) y = 0;
         double w = om[c];
         double ax_ = x * w, ay_ = y * w, aY_ = Y * w;
-        vx[c] = ax_; vy[c] = ay_; vY[c] = aY_;
+        const int slot = (c - c0) * 256 + threadIdx.x;
+        vx[slot] = ax_; vy[slot] = ay_; vY[slot] = aY_;
         sx += ax_; sy += ay_; sY += aY_; sw += w;
     }
     // block-wide exclusive scan of the thread totals: warp shuffles + the 8 warp totals (fixed tree: deterministic)
@@ -593,13 +596,14 @@ __global__ void __launch_bounds__(256) k_env_prefix(const uint8_t *env8, const d
     }
     for (int c = c0; c < c1; c++) {
         p[c] = make_double4(ax, ay, aY, aw);
-        ax += vx[c]; ay += vy[c]; aY += vY[c]; aw += om[c];
+        const int slot = (c - c0) * 256 + threadIdx.x;
+        ax += vx[slot]; ay += vy[slot]; aY += vY[slot]; aw += om[c];
     }
 }
 
 static cudaError_t launch_env_prefix(const uint8_t *env8, const double *omega, double *pref, double *rowtot, int F, int H, int W_env,
                                      cudaStream_t st) {
-    size_t smem = sizeof(double) * (3 * (size_t)W_env + 256);
+    size_t smem = sizeof(double) * (3 * (size_t)((W_env + 255) / 256) * 256 + 256);
     static size_t attr = 0;
     if (smem > attr) {
         cudaError_t e = cudaFuncSetAttribute(k_env_prefix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
