@@ -540,78 +540,65 @@ __global__ void __launch_bounds__(256) k_env_blur(const uint8_t *env_fill, const
 // 32-byte sector serves a span end point in k_setup.
 __global__ void __launch_bounds__(256) k_env_prefix(const uint8_t *env8, const double *omega, double *pref, double *rowtot,
                                                     int H, int W_env) {
-    extern __shared__ double envp_smem[];          // [3][per][256] weighted x, y, Y of the row (element k of thread t at
-                                                   // k*256 + t: conflict free), then the 256-entry LUT
-    const int per_ = (W_env + 255) / 256;
-    double *vx = envp_smem, *vy = vx + per_ * 256, *vY = vy + per_ * 256, *lut = vY + per_ * 256;
+    // The row is scanned in tiles of 256 consecutive pixels (all global accesses coalesced); inside a tile a
+    // warp-shuffle scan plus the 8 warp totals, between tiles a running carry.  Fixed tree: deterministic.
+    __shared__ double lut[256];
     __shared__ double wtot[4][8];
     lut[threadIdx.x] = (double)threadIdx.x / 255.0;
-    int r = blockIdx.x, f = blockIdx.y;
+    const int r = blockIdx.x, f = blockIdx.y;
     const uint8_t *row = env8 + ((size_t)f * H + r) * W_env * 3;
     const double *om = omega + (size_t)r * W_env;
-    int per = (W_env + 255) / 256;
-    int c0 = threadIdx.x * per, c1 = c0 + per < W_env ? c0 + per : W_env;
-    __syncthreads();
-    double sx = 0, sy = 0, sY = 0, sw = 0;
-    for (int c = c0; c < c1; c++) {
-        double bb = lut[row[c * 3]], gg = lut[row[c * 3 + 1]], rr = lut[row[c * 3 + 2]];
-        double X = ((rr * 0.49000 + gg * 0.17697) + bb * 0.00000) / 0.17697;      // my_utils.py:56-59 (row vector x M)
-        double Y = ((rr * 0.31000 + gg * 0.81240) + bb * 0.01000) / 0.17697;
-        double Z = ((rr * 0.20000 + gg * 0.01063) + bb * 0.99000) / 0.17697;
-        double S = (X + Y) + Z;
-        double x = X / S, y = Y / S;
-        if (!(x == x)) x = 0;                                                      // generator.py:408
-        if (!(y == y)) y = 0;
-        double w = om[c];
-        double ax_ = x * w, ay_ = y * w, aY_ = Y * w;
-        const int slot = (c - c0) * 256 + threadIdx.x;
-        vx[slot] = ax_; vy[slot] = ay_; vY[slot] = aY_;
-        sx += ax_; sy += ay_; sY += aY_; sw += w;
-    }
-    // block-wide exclusive scan of the thread totals: warp shuffles + the 8 warp totals (fixed tree: deterministic)
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double ix = sx, iy = sy, iY = sY, iw = sw;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        double ux = __shfl_up_sync(0xffffffffu, ix, o), uy = __shfl_up_sync(0xffffffffu, iy, o);
-        double uY = __shfl_up_sync(0xffffffffu, iY, o), uw = __shfl_up_sync(0xffffffffu, iw, o);
-        if (lane >= o) { ix += ux; iy += uy; iY += uY; iw += uw; }
-    }
-    if (lane == 31) { wtot[0][warp] = ix; wtot[1][warp] = iy; wtot[2][warp] = iY; wtot[3][warp] = iw; }
-    double ex = __shfl_up_sync(0xffffffffu, ix, 1), ey = __shfl_up_sync(0xffffffffu, iy, 1);
-    double eY = __shfl_up_sync(0xffffffffu, iY, 1), ew = __shfl_up_sync(0xffffffffu, iw, 1);
-    if (lane == 0) { ex = ey = eY = ew = 0; }
-    __syncthreads();
-    double ox = 0, oy = 0, oY = 0, ow = 0, allx = 0, ally = 0, allY = 0, allw = 0;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        if (k == warp) { ox = allx; oy = ally; oY = allY; ow = allw; }
-        allx += wtot[0][k]; ally += wtot[1][k]; allY += wtot[2][k]; allw += wtot[3][k];
-    }
-    double ax = ox + ex, ay = oy + ey, aY = oY + eY, aw = ow + ew;       // exclusive prefix of this thread
     double4 *p = (double4 *)pref + ((size_t)f * H + r) * (W_env + 1);
-    if (threadIdx.x == 0) {
-        p[W_env] = make_double4(allx, ally, allY, allw);
-        rowtot[(size_t)f * H + r] = allY;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double cx = 0, cy = 0, cY = 0, cw = 0;          // carry: prefix of everything left of the tile
+    __syncthreads();
+    for (int c0 = 0; c0 < W_env; c0 += 256) {
+        const int c = c0 + threadIdx.x;
+        double ax_ = 0, ay_ = 0, aY_ = 0, w = 0;
+        if (c < W_env) {
+            double bb = lut[row[c * 3]], gg = lut[row[c * 3 + 1]], rr = lut[row[c * 3 + 2]];
+            double X = ((rr * 0.49000 + gg * 0.17697) + bb * 0.00000) / 0.17697;      // my_utils.py:56-59 (row vector x M)
+            double Y = ((rr * 0.31000 + gg * 0.81240) + bb * 0.01000) / 0.17697;
+            double Z = ((rr * 0.20000 + gg * 0.01063) + bb * 0.99000) / 0.17697;
+            double S = (X + Y) + Z;
+            double x = X / S, y = Y / S;
+            if (!(x == x)) x = 0;                                                      // generator.py:408
+            if (!(y == y)) y = 0;
+            w = om[c];
+            ax_ = x * w; ay_ = y * w; aY_ = Y * w;
+        }
+        double ix = ax_, iy = ay_, iY = aY_, iw = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double ux = __shfl_up_sync(0xffffffffu, ix, o), uy = __shfl_up_sync(0xffffffffu, iy, o);
+            double uY = __shfl_up_sync(0xffffffffu, iY, o), uw = __shfl_up_sync(0xffffffffu, iw, o);
+            if (lane >= o) { ix += ux; iy += uy; iY += uY; iw += uw; }
+        }
+        if (lane == 31) { wtot[0][warp] = ix; wtot[1][warp] = iy; wtot[2][warp] = iY; wtot[3][warp] = iw; }
+        double ex = __shfl_up_sync(0xffffffffu, ix, 1), ey = __shfl_up_sync(0xffffffffu, iy, 1);
+        double eY = __shfl_up_sync(0xffffffffu, iY, 1), ew = __shfl_up_sync(0xffffffffu, iw, 1);
+        if (lane == 0) { ex = ey = eY = ew = 0; }
+        __syncthreads();
+        double ox = cx, oy = cy, oY = cY, ow = cw, tx_ = cx, ty_ = cy, tY_ = cY, tw_ = cw;
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            if (k == warp) { ox = tx_; oy = ty_; oY = tY_; ow = tw_; }
+            tx_ += wtot[0][k]; ty_ += wtot[1][k]; tY_ += wtot[2][k]; tw_ += wtot[3][k];
+        }
+        if (c < W_env) p[c] = make_double4(ox + ex, oy + ey, oY + eY, ow + ew);
+        cx = tx_; cy = ty_; cY = tY_; cw = tw_;
+        __syncthreads();
     }
-    for (int c = c0; c < c1; c++) {
-        p[c] = make_double4(ax, ay, aY, aw);
-        const int slot = (c - c0) * 256 + threadIdx.x;
-        ax += vx[slot]; ay += vy[slot]; aY += vY[slot]; aw += om[c];
+    if (threadIdx.x == 0) {
+        p[W_env] = make_double4(cx, cy, cY, cw);
+        rowtot[(size_t)f * H + r] = cY;
     }
 }
 
 static cudaError_t launch_env_prefix(const uint8_t *env8, const double *omega, double *pref, double *rowtot, int F, int H, int W_env,
                                      cudaStream_t st) {
-    size_t smem = sizeof(double) * (3 * (size_t)((W_env + 255) / 256) * 256 + 256);
-    static size_t attr = 0;
-    if (smem > attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_env_prefix, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr = smem;
-    }
     dim3 g3(H, F);
-    k_env_prefix<<<g3, 256, smem, st>>>(env8, omega, pref, rowtot, H, W_env);
+    k_env_prefix<<<g3, 256, 0, st>>>(env8, omega, pref, rowtot, H, W_env);
     return cudaGetLastError();
 }
 
@@ -825,24 +812,22 @@ __device__ __forceinline__ int find_streak(const long long *scan, int n, int fie
 #define RAS_RBMAX 256
 
 __device__ __forceinline__ double ras_sample(const uint8_t *tex, int tw, int th, const double *lut, int X, int Y) {
-    // rr_warp_affine_linear with the fixed-point coordinates already formed
-    int sx = rr_clampi(X >> RR_INTER_BITS, -32768, 32767);
-    int sy = rr_clampi(Y >> RR_INTER_BITS, -32768, 32767);
-    int fx = X & (RR_INTER_TAB - 1), fy = Y & (RR_INTER_TAB - 1);
+    // rr_warp_affine_linear with the fixed-point coordinates already formed.  One code path for interior and
+    // border samples (out-of-texture taps contribute the border value 0 with their weight, exactly the
+    // expression remapBilinear evaluates), so a warp does not diverge along the texture outline.
+    const int sx = X >> RR_INTER_BITS, sy = Y >> RR_INTER_BITS;     // |coordinates| << 2^15: the short saturation cannot act
+    const bool x0ok = (unsigned)sx < (unsigned)tw, x1ok = (unsigned)(sx + 1) < (unsigned)tw;
+    const bool y0ok = (unsigned)sy < (unsigned)th, y1ok = (unsigned)(sy + 1) < (unsigned)th;
+    if (!((x0ok | x1ok) & (y0ok | y1ok))) return 0.0;               // all four taps outside: the border constant
+    const int fx = X & (RR_INTER_TAB - 1), fy = Y & (RR_INTER_TAB - 1);
     const float s = 1.f / RR_INTER_TAB;
-    float ax1 = fx * s, ax0 = 1.f - ax1, ay1 = fy * s, ay0 = 1.f - ay1;
-    float w0 = ay0 * ax0, w1 = ay0 * ax1, w2 = ay1 * ax0, w3 = ay1 * ax1;
-    if ((unsigned)sx < (unsigned)(tw - 1) && (unsigned)sy < (unsigned)(th - 1)) {
-        const uint8_t *S = tex + sy * tw + sx;
-        return lut[S[0]] * w0 + lut[S[1]] * w1 + lut[S[tw]] * w2 + lut[S[tw + 1]] * w3;
-    }
-    if (sx >= tw || sx + 1 < 0 || sy >= th || sy + 1 < 0) return 0.0;
-    bool x0ok = sx >= 0 && sx < tw, x1ok = sx + 1 >= 0 && sx + 1 < tw;
-    bool y0ok = sy >= 0 && sy < th, y1ok = sy + 1 >= 0 && sy + 1 < th;
-    double v0 = (x0ok && y0ok) ? lut[tex[sy * tw + sx]] : 0.0;
-    double v1 = (x1ok && y0ok) ? lut[tex[sy * tw + sx + 1]] : 0.0;
-    double v2 = (x0ok && y1ok) ? lut[tex[(sy + 1) * tw + sx]] : 0.0;
-    double v3 = (x1ok && y1ok) ? lut[tex[(sy + 1) * tw + sx + 1]] : 0.0;
+    const float ax1 = fx * s, ax0 = 1.f - ax1, ay1 = fy * s, ay0 = 1.f - ay1;
+    const float w0 = ay0 * ax0, w1 = ay0 * ax1, w2 = ay1 * ax0, w3 = ay1 * ax1;
+    const uint8_t *S = tex + sy * tw + sx;
+    const double v0 = (x0ok & y0ok) ? lut[S[0]] : 0.0;
+    const double v1 = (x1ok & y0ok) ? lut[S[1]] : 0.0;
+    const double v2 = (x0ok & y1ok) ? lut[S[tw]] : 0.0;
+    const double v3 = (x1ok & y1ok) ? lut[S[tw + 1]] : 0.0;
     return v0 * w0 + v1 * w1 + v2 * w2 + v3 * w3;
 }
 
@@ -901,6 +886,8 @@ __global__ void __launch_bounds__(RAS_THREADS, 4) k_raster(rr_frame_bufs b, rr_s
         int RB = RAS_CAP / (nW > pw ? nW : pw);
         if (RB < 1) RB = 1;
         if (RB > RAS_RBMAX) RB = RAS_RBMAX;
+        const int step_r = RAS_THREADS / nW, step_c = RAS_THREADS - step_r * nW;
+        const int r_first = tid / nW, c_first = tid - r_first * nW;
         // bands of canvas rows; every canvas pixel is sampled exactly once
         for (int s0 = 0; s0 < nH; s0 += RB) {
             const int rb = (nH - s0) < RB ? (nH - s0) : RB;
@@ -913,13 +900,13 @@ __global__ void __launch_bounds__(RAS_THREADS, 4) k_raster(rr_frame_bufs b, rr_s
             }
             __syncthreads();
             {
-                int r = tid / nW, c = tid - r * nW;
+                int r = r_first, c = c_first;                       // (row, column) of flattened index tid
                 for (int i = tid; i < rb * nW; i += RAS_THREADS) {
                     int X = (XR[r] + adx[c]) >> (10 - RR_INTER_BITS);
                     int Y = (YR[r] + bdx[c]) >> (10 - RR_INTER_BITS);
                     C[i] = ras_sample(tex, tw, th, lut, X, Y);
-                    c += RAS_THREADS;
-                    while (c >= nW) { c -= nW; r++; }
+                    c += step_c; r += step_r;                       // advance by RAS_THREADS without a division
+                    if (c >= nW) { c -= nW; r++; }
                 }
             }
             __syncthreads();
