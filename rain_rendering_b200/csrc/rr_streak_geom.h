@@ -192,7 +192,7 @@ RR_HD int rr_clip_fov_polygon(const double *px, const double *py, int n, int col
     while (changed && n >= 3) {
         changed = false;
         for (int i = 0; i < n; i++) {
-            int p = (i + n - 1) % n, q = (i + 1) % n;
+            int p = i ? i - 1 : n - 1, q = i + 1 < n ? i + 1 : 0;
             bool dup = (vx[i] == vx[p] && vy[i] == vy[p]) || (vx[i] == vx[q] && vy[i] == vy[q]);
             bool col = (int64_t)(vy[i] - vy[p]) * (vx[q] - vx[i]) == (int64_t)(vx[i] - vx[p]) * (vy[q] - vy[i]);
             if (dup || col) {
@@ -206,7 +206,7 @@ RR_HD int rr_clip_fov_polygon(const double *px, const double *py, int n, int col
     if (n < 3) return 0;
     int64_t a = 0;
     for (int i = 0; i < n; i++) {
-        int j = (i + n - 1) % n;
+        int j = i ? i - 1 : n - 1;
         a += (int64_t)(vx[j] + vx[i]) * (vy[j] - vy[i]);
     }
     if (-a < 0) {   // negative Clipper area: reverse
@@ -279,18 +279,27 @@ RR_HD bool rr_plan_patch(const rr_streak_rec &s, const rr_cam_dev &cam, int tex_
     p.ry = c > 1e-15 ? rr_gauss_radius(c) : 0;
     p.rx = (c / 2) > 1e-15 ? rr_gauss_radius(c / 2) : 0;
     if (p.ry > RR_MAX_GAUSS_R || p.rx > RR_MAX_GAUSS_R) return false;
-    // placement (bad_weather.py:418-434)
-    int tx = p.minx - p.shift, ty = p.miny - p.shift;
-    int bx0 = tx < 0 ? 0 : (tx > cam.W ? cam.W : tx);
-    int by0 = ty < 0 ? 0 : (ty > cam.H ? cam.H : ty);
-    int dxl = bx0 - tx, dyl = by0 - ty;
+    // placement (bad_weather.py:418-434).  The reference composites the whole zero-padded block
+    // (pw + 2 shift) x (ph + 2 shift); the blurred alpha is exactly 0.0 farther than the kernel radius
+    // from the patch (every tap there reads padding), and alpha == 0 leaves image and mask bit-for-bit
+    // unchanged, so only the block [shift - r, shift + size + r) is blurred, stored and composited.
+    int tx = p.minx - p.shift, ty = p.miny - p.shift;                 // image position of padded (0, 0)
     int BW = p.pw + 2 * p.shift, BH = p.ph + 2 * p.shift;
-    int visw, vish;
-    if (dxl < 0) visw = 0; else { visw = BW - dxl; if (visw > cam.W - bx0) visw = cam.W - bx0; if (visw < 0) visw = 0; }
-    if (dyl < 0) vish = 0; else { vish = BH - dyl; if (vish > cam.H - by0) vish = cam.H - by0; if (vish < 0) vish = 0; }
-    if (visw == 0 || vish == 0) { visw = 0; vish = 0; }
-    p.bx0 = bx0; p.by0 = by0;
-    p.cropx = dxl > 0 ? dxl : 0; p.cropy = dyl > 0 ? dyl : 0;
+    bool empty = tx > cam.W || ty > cam.H;                            // reference: negative delta -> empty slices
+    int Xa = p.shift - p.rx, Xb = p.shift + p.pw + p.rx;
+    int Ya = p.shift - p.ry, Yb = p.shift + p.ph + p.ry;
+    if (Xa < 0) Xa = 0;
+    if (Ya < 0) Ya = 0;
+    if (Xb > BW) Xb = BW;
+    if (Yb > BH) Yb = BH;
+    if (Xa < -tx) Xa = -tx;                                            // clip to the image
+    if (Ya < -ty) Ya = -ty;
+    if (Xb > cam.W - tx) Xb = cam.W - tx;
+    if (Yb > cam.H - ty) Yb = cam.H - ty;
+    int visw = Xb - Xa, vish = Yb - Ya;
+    if (empty || visw <= 0 || vish <= 0) { visw = 0; vish = 0; Xa = 0; Ya = 0; }
+    p.bx0 = tx + Xa; p.by0 = ty + Ya;
+    p.cropx = Xa; p.cropy = Ya;
     p.bw = visw; p.bh = vish;
     // blend constants (bad_weather.py:376,425-427)
     double d_avg = (s.iw1 + s.iw2) / 2.;
