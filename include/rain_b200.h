@@ -121,6 +121,17 @@ int rr_render_frames(rr_context *ctx, int n_frames, const uint8_t *bgr, const fl
                      const rr_streak_rec *streaks, const int32_t *streak_offsets,
                      float *out_bgr, float *out_mask, uint8_t *out_bgr_u8);
 
+/* Asynchronous form: rr_submit_frames enqueues the copies and kernels of one batch and returns; the
+ * buffers of that batch (inputs and outputs, which must be page-locked for the copies to overlap)
+ * belong to the library until the matching rr_wait_frames returns.  At most two batches are in flight
+ * (a third submission first waits for the oldest); batches complete in submission order.  With two
+ * sets of host buffers the host->device copy of batch k+1 and the device->host copy of batch k-1
+ * overlap the kernels of batch k.  rr_render_frames == submit + wait. */
+int rr_submit_frames(rr_context *ctx, int n_frames, const uint8_t *bgr, const float *depth,
+                     const rr_streak_rec *streaks, const int32_t *streak_offsets,
+                     float *out_bgr, float *out_mask, uint8_t *out_bgr_u8);
+int rr_wait_frames(rr_context *ctx);
+
 /* Same with DEVICE pointers and no copies (inputs already resident in HBM); asynchronous on the
  * context stream unless sync != 0. */
 int rr_render_frames_device(rr_context *ctx, int n_frames, const uint8_t *d_bgr, const float *d_depth,

@@ -74,6 +74,8 @@ def load() -> C.CDLL:
         "rr_set_camera": [vp, C.POINTER(Camera), C.c_int],
         "rr_env_size": [vp, C.POINTER(C.c_int), C.POINTER(C.c_int)],
         "rr_render_frames": [vp, C.c_int, u8p, f32p, vp, i32p, f32p, f32p, u8p],
+        "rr_submit_frames": [vp, C.c_int, u8p, f32p, vp, i32p, f32p, f32p, u8p],
+        "rr_wait_frames": [vp],
         "rr_render_frames_device": [vp, C.c_int, u8p, f32p, vp, i32p, f32p, f32p, u8p, C.c_int],
         "rr_fog_only": [vp, C.c_int, u8p, f32p, f64p],
         "rr_envmap_only": [vp, C.c_int, f64p, u8p],

@@ -139,6 +139,20 @@ class RainContext:
                                              _lib.ptr(out_bgr), _lib.ptr(out_mask), _lib.ptr(out_u8)), "rr_render_frames")
         return dict(bgr=out_bgr, mask=out_mask, u8=out_u8)
 
+    def submit_frames(self, bgr, depth, streaks, offsets, out_bgr=None, out_mask=None, out_u8=None):
+        """Asynchronous rr_submit_frames: all arrays (page-locked for the copies to overlap) must stay
+        alive and untouched until the matching ``wait_frames``; at most two batches in flight."""
+        n = bgr.shape[0]
+        rs = self.render_scale
+        assert bgr.shape == (n, self.H * rs, self.W * rs, 3) and bgr.dtype == np.uint8
+        assert depth.shape == (n, self.H, self.W) and depth.dtype == np.float32 and streaks.dtype == STREAK_DTYPE
+        assert offsets.dtype == np.int32 and offsets.flags["C_CONTIGUOUS"]
+        _lib.check(self.lib.rr_submit_frames(self.h, n, _lib.ptr(bgr), _lib.ptr(depth), _lib.ptr(streaks), _lib.ptr(offsets),
+                                             _lib.ptr(out_bgr), _lib.ptr(out_mask), _lib.ptr(out_u8)), "rr_submit_frames")
+
+    def wait_frames(self):
+        _lib.check(self.lib.rr_wait_frames(self.h), "rr_wait_frames")
+
     # -- stage entry points (parity tests) -----------------------------------------------------
     def fog_only(self, bgr, depth):
         n = bgr.shape[0]

@@ -57,11 +57,20 @@ struct rr_context {
     int last_n_streaks = 0;
     // copy/compute overlap inside rr_render_frames (pinned host buffers): sub-batches on three streams
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
-    cudaEvent_t ev_in[RR_MAX_SUB], ev_done[RR_MAX_SUB], ev_out;
+    cudaEvent_t ev_in[RR_MAX_SUB], ev_done[RR_MAX_SUB], ev_d2h[RR_MAX_SUB], ev_out;
     int32_t *d_sub_offsets = nullptr;    // [RR_MAX_SUB][max_batch + 1]
     long long scan_base[RR_MAX_SUB];     // element index (in units of 6 long long) of each sub-batch's scan block
     int sub_n[RR_MAX_SUB];
     int n_sub_last = 1;
+    // asynchronous submissions (rr_submit_frames / rr_wait_frames): at most two batches in flight
+    cudaEvent_t ev_call[2];
+    int inflight = 0, parity = 0;        // parity: slot the next submission uses; oldest in flight = parity ^ (inflight == 2 ? 0 : 1)
+    int call_S[2] = {1, 1}, call_F[2] = {0, 0}, call_n[2] = {0, 0};
+    long long call_scan_base[2][RR_MAX_SUB];
+    int call_sub_n[2][RR_MAX_SUB];
+    int32_t *h_sub_off = nullptr;        // pinned staging [2][RR_MAX_SUB][max_batch + 1]
+    int *d_err2 = nullptr;               // [2] overflow flags, one per slot
+    int sub_cap = 0;                     // records per sub-batch slot of d_streaks
 };
 
 template <class T>
@@ -72,6 +81,9 @@ static cudaError_t dev_alloc(rr_context *c, T **p, size_t count) {
 }
 
 static void free_camera(rr_context *c) {
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_d2h); }
+    c->inflight = 0; c->parity = 0; c->sub_cap = 0;
+    if (c->h_sub_off) { cudaFreeHost(c->h_sub_off); c->h_sub_off = nullptr; }
     for (void *p : c->owned) cudaFree(p);
     c->owned.clear();
     c->have_cam = false;
@@ -108,7 +120,9 @@ int rr_create(int device_id, rr_context **out) {
     for (int i = 0; i < RR_MAX_SUB; i++) {
         CK(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&c->ev_d2h[i], cudaEventDisableTiming));
     }
+    for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&c->ev_call[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
     for (int i = 0; i < RR_T_COUNT + 2; i++) CK(cudaEventCreate(&c->ev[i]));
     memset(c->last_ms, 0, sizeof(c->last_ms));
@@ -130,7 +144,9 @@ int rr_destroy(rr_context *c) {
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->s_h2d);
     cudaStreamDestroy(c->s_d2h);
-    for (int i = 0; i < RR_MAX_SUB; i++) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_done[i]); }
+    for (int i = 0; i < RR_MAX_SUB; i++) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_done[i]); cudaEventDestroy(c->ev_d2h[i]); }
+    for (int i = 0; i < 2; i++) cudaEventDestroy(c->ev_call[i]);
+    if (c->h_sub_off) cudaFreeHost(c->h_sub_off);
     cudaEventDestroy(c->ev_out);
     delete c;
     return RR_OK;
@@ -172,15 +188,28 @@ int rr_streak_db_device_ptr(rr_context *c, void **dev_ptr, size_t *bytes) {
     return RR_OK;
 }
 
-static int ensure_streak_cap(rr_context *c, int n) {
-    if (n <= c->streak_cap) return RR_OK;
-    int cap = n + n / 4 + 1024;
-    CK(dev_alloc(c, &c->d_streaks, (size_t)cap));
-    CK(dev_alloc(c, &c->fb.plans, (size_t)cap));
-    CK(dev_alloc(c, &c->fb.sizes, (size_t)cap));
-    CK(dev_alloc(c, &c->fb.boxes, (size_t)cap));
-    CK(dev_alloc(c, &c->fb.scan, (size_t)(cap + 1 + RR_MAX_SUB) * 6));
-    c->streak_cap = cap;
+static void drain(rr_context *c) {
+    cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_d2h);
+}
+
+// n: records of the whole batch (plans / sizes / boxes / scan); n_sub: records of the largest sub-batch slot
+static int ensure_streak_cap(rr_context *c, int n, int n_sub = -1) {
+    if (n_sub < 0) n_sub = n;
+    if (n > c->streak_cap) {
+        drain(c);
+        int cap = n + n / 4 + 1024;
+        CK(dev_alloc(c, &c->fb.plans, (size_t)cap));
+        CK(dev_alloc(c, &c->fb.sizes, (size_t)cap));
+        CK(dev_alloc(c, &c->fb.boxes, (size_t)cap));
+        CK(dev_alloc(c, &c->fb.scan, (size_t)(cap + 1 + RR_MAX_SUB) * 6));
+        c->streak_cap = cap;
+    }
+    if (n_sub > c->sub_cap) {
+        drain(c);
+        int cap = n_sub + n_sub / 4 + 1024;
+        CK(dev_alloc(c, &c->d_streaks, (size_t)cap * RR_MAX_SUB));
+        c->sub_cap = cap;
+    }
     return RR_OK;
 }
 
@@ -245,6 +274,8 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
     CK(dev_alloc(c, &c->d_depth, F * np));
     CK(dev_alloc(c, &c->d_offsets, F + 1));
     CK(dev_alloc(c, &c->d_sub_offsets, (size_t)RR_MAX_SUB * (F + 1)));
+    CK(cudaHostAlloc((void **)&c->h_sub_off, sizeof(int32_t) * 2 * RR_MAX_SUB * (F + 1), cudaHostAllocDefault));
+    CK(dev_alloc(c, &c->d_err2, (size_t)2));
     CK(dev_alloc(c, &b.chan_sum, F * 4));
     CK(dev_alloc(c, &b.bg_sum, F * 4));
     c->d_bgf = nullptr;
@@ -257,7 +288,7 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
     CK(dev_alloc(c, &b.pref, F * 4 * (size_t)He * (We + 1)));
     CK(dev_alloc(c, &b.rowtot, F * He));
     CK(dev_alloc(c, &b.ambient, F));
-    CK(dev_alloc(c, &b.err_flag, (size_t)1));
+    b.err_flag = nullptr;
     size_t tiles = (size_t)((W + RR_TILE_W - 1) / RR_TILE_W) * ((H + RR_TILE_H - 1) / RR_TILE_H);
     CK(dev_alloc(c, &b.tile_sum, F * (tiles > 256 ? tiles : 256)));     // also holds the 64x4 partial sums of k_downscale2
     CK(dev_alloc(c, &b.frame_mean, F));
@@ -271,7 +302,7 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
         b.arena_cap = (long long)(mult * (double)(F * np));
         CK(dev_alloc(c, &b.arena, (size_t)b.arena_cap));
     }
-    int r = ensure_streak_cap(c, max_batch * 1024);
+    int r = ensure_streak_cap(c, max_batch * 1024, max_batch * 1024);
     if (r != RR_OK) return r;
     c->have_cam = true;
     return RR_OK;
@@ -361,21 +392,21 @@ static int finish_timings(rr_context *c) {
     return RR_OK;
 }
 
-// -> RR_OK, or RR_ERR_CAPACITY after growing the arena to fit (the caller re-runs the batch)
-static int check_flag(rr_context *c, bool grow) {
+// Overflow flag of one submission slot (the stream work of that slot must be complete).
+// -> RR_OK, or RR_ERR_CAPACITY; with grow (nothing else in flight) the arena is enlarged to fit and the
+// message says "grown" so that the caller re-runs the batch.
+static int check_flag_slot(rr_context *c, const int *d_flag, int n_sub, const long long *scan_base, const int *sub_n, bool grow) {
     int flag = 0;
-    CK(cudaMemcpyAsync(&flag, c->fb.err_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost));
     if (!flag) return RR_OK;
     long long need = 0;
-    for (int k = 0; k < c->n_sub_last; k++) {
+    for (int k = 0; k < n_sub; k++) {
         long long v = 0;
-        CK(cudaMemcpy(&v, c->fb.scan + (size_t)(c->scan_base[k] + c->sub_n[k]) * 6, sizeof(long long), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&v, c->fb.scan + (size_t)(scan_base[k] + sub_n[k]) * 6, sizeof(long long), cudaMemcpyDeviceToHost));
         if (v > need) need = v;
     }
     if (grow) {
         long long cap = need + need / 4 + 4096;
-        // the old arena stays in c->owned (freed with the camera); allocate the larger one
         double *na = nullptr;
         cudaError_t e = cudaMalloc((void **)&na, (size_t)cap * sizeof(double));
         if (e == cudaSuccess) {
@@ -386,28 +417,31 @@ static int check_flag(rr_context *c, bool grow) {
         }
         cudaGetLastError();
     }
-    set_err("patch arena overflow: need %lld float64 elements, have %lld (RR_ARENA_MULT raises the initial size)", need, c->fb.arena_cap);
+    set_err("patch arena overflow: need %lld float64 elements, have %lld (RR_ARENA_MULT raises the initial size; a synchronous "
+            "rr_render_frames call grows it automatically)", need, c->fb.arena_cap);
     return RR_ERR_CAPACITY;
 }
 
-int rr_render_frames(rr_context *c, int n_frames, const uint8_t *bgr, const float *depth, const rr_streak_rec *streaks,
-                     const int32_t *streak_offsets, float *out_bgr, float *out_mask, uint8_t *out_bgr_u8) {
-    int r = check_ready(c, n_frames, "rr_render_frames");
-    if (r != RR_OK) return r;
-    if (!bgr || !depth || !streak_offsets) { set_err("rr_render_frames: NULL input"); return RR_ERR_ARG; }
-    if (!c->d_db) { set_err("rr_render_frames: no streak DB"); return RR_ERR_STATE; }
-    CK(cudaSetDevice(c->device));
-    const int F = n_frames, n_streaks = streak_offsets[F];
-    if (streak_offsets[0] != 0 || n_streaks < 0 || (n_streaks > 0 && !streaks)) { set_err("rr_render_frames: bad streak offsets"); return RR_ERR_ARG; }
-    for (int f = 0; f < F; f++)
-        if (streak_offsets[f + 1] < streak_offsets[f]) { set_err("rr_render_frames: streak offsets not monotone"); return RR_ERR_ARG; }
-    r = ensure_streak_cap(c, n_streaks);
-    if (r != RR_OK) return r;
+static int check_flag(rr_context *c, bool grow) {          // single-stream entry points (device / stage variants)
+    CK(cudaStreamSynchronize(c->stream));
+    return check_flag_slot(c, c->fb.err_flag, c->n_sub_last, c->scan_base, c->sub_n, grow);
+}
+
+// ---- asynchronous submission ---------------------------------------------------------------------
+static int wait_oldest(rr_context *c, bool grow) {
+    if (c->inflight == 0) return RR_OK;
+    const int slot = c->inflight == 2 ? c->parity : (c->parity ^ 1);
+    CK(cudaEventSynchronize(c->ev_call[slot]));
+    c->inflight--;
+    return check_flag_slot(c, c->d_err2 + slot, c->call_S[slot], c->call_scan_base[slot], c->call_sub_n[slot], grow && c->inflight == 0);
+}
+
+static int submit_frames(rr_context *c, int F, const uint8_t *bgr, const float *depth, const rr_streak_rec *streaks,
+                         const int32_t *streak_offsets, float *out_bgr, float *out_mask, uint8_t *out_bgr_u8, bool timed) {
+    const int n_streaks = streak_offsets[F];
     const size_t np = (size_t)c->cam.W * c->cam.H;
     const size_t rs2 = c->cam.render_scale == 2 ? 4 : 1;
     cudaStream_t st = c->stream;
-    rr_frame_bufs &b = c->fb;
-    b.bgf = c->d_bgf;
     // sub-batches overlap H2D / compute / D2H when the caller's buffers are page-locked
     int S = 1;
     {
@@ -419,57 +453,116 @@ int rr_render_frames(rr_context *c, int n_frames, const uint8_t *bgr, const floa
         if (pinned && want > 1) S = want < RR_MAX_SUB ? want : RR_MAX_SUB;
         if (S > F) S = F;
     }
-    std::vector<int32_t> sub_off((size_t)S * (F + 1), 0);
-    int fstart[RR_MAX_SUB + 1];
+    int fstart[RR_MAX_SUB + 1], max_ns = 0;
     for (int k = 0; k <= S; k++) fstart[k] = (int)((long long)F * k / S);
-    for (int attempt = 0;; attempt++) {
-        CK(cudaEventRecord(c->ev[RR_T_H2D], st));
-        CK(cudaMemsetAsync(b.err_flag, 0, sizeof(int), st));
-        CK(cudaEventRecord(c->ev_out, st));
-        CK(cudaStreamWaitEvent(c->s_h2d, c->ev_out, 0));       // previous call's compute is done before inputs are overwritten
-        long long sb = 0;
-        for (int k = 0; k < S; k++) {
-            const int f0 = fstart[k], nf = fstart[k + 1] - f0, s0 = streak_offsets[f0], ns = streak_offsets[f0 + nf] - s0;
-            for (int i = 0; i <= nf; i++) sub_off[(size_t)k * (F + 1) + i] = streak_offsets[f0 + i] - s0;
-            cudaStream_t hs = S > 1 ? c->s_h2d : st;
-            CK(cudaMemcpyAsync(c->d_bgr + (size_t)f0 * np * 3 * rs2, bgr + (size_t)f0 * np * 3 * rs2, (size_t)nf * np * 3 * rs2, cudaMemcpyHostToDevice, hs));
-            CK(cudaMemcpyAsync(c->d_depth + (size_t)f0 * np, depth + (size_t)f0 * np, (size_t)nf * np * sizeof(float), cudaMemcpyHostToDevice, hs));
-            if (ns) CK(cudaMemcpyAsync(c->d_streaks + s0, streaks + s0, (size_t)ns * sizeof(rr_streak_rec), cudaMemcpyHostToDevice, hs));
-            CK(cudaMemcpyAsync(c->d_sub_offsets + (size_t)k * (F + 1), sub_off.data() + (size_t)k * (F + 1), (nf + 1) * sizeof(int32_t),
-                               cudaMemcpyHostToDevice, hs));
-            if (S > 1) { CK(cudaEventRecord(c->ev_in[k], hs)); CK(cudaStreamWaitEvent(st, c->ev_in[k], 0)); }
-            b.bgr = c->d_bgr; b.depth = c->d_depth; b.streaks = c->d_streaks; b.offsets = c->d_sub_offsets + (size_t)k * (F + 1);
-            c->scan_base[k] = sb; c->sub_n[k] = ns;
-            rr_frame_bufs saved = c->fb;
-            c->fb = sub_view(c, saved, f0, s0, sb);
-            c->fb.offsets = saved.offsets;
-            r = run_pipeline(c, nf, ns, S == 1);
-            rr_frame_bufs used = c->fb;
-            c->fb = saved;
-            (void)used;
-            if (r != RR_OK) return r;
-            sb += ns + 1;
-            cudaStream_t ds = S > 1 ? c->s_d2h : st;
-            if (S > 1) { CK(cudaEventRecord(c->ev_done[k], st)); CK(cudaStreamWaitEvent(ds, c->ev_done[k], 0)); }
-            if (out_bgr) CK(cudaMemcpyAsync(out_bgr + (size_t)f0 * np * 3, b.out_bgr + (size_t)f0 * np * 3, (size_t)nf * np * 3 * sizeof(float), cudaMemcpyDeviceToHost, ds));
-            if (out_mask) CK(cudaMemcpyAsync(out_mask + (size_t)f0 * np, b.out_mask + (size_t)f0 * np, (size_t)nf * np * sizeof(float), cudaMemcpyDeviceToHost, ds));
-            if (out_bgr_u8) CK(cudaMemcpyAsync(out_bgr_u8 + (size_t)f0 * np * 3, b.out_u8 + (size_t)f0 * np * 3, (size_t)nf * np * 3, cudaMemcpyDeviceToHost, ds));
+    for (int k = 0; k < S; k++) { int ns = streak_offsets[fstart[k + 1]] - streak_offsets[fstart[k]]; if (ns > max_ns) max_ns = ns; }
+    int r = ensure_streak_cap(c, n_streaks, max_ns);
+    if (r != RR_OK) return r;
+    if (c->inflight == 2) { r = wait_oldest(c, false); if (r != RR_OK) return r; }
+    const int slot = c->parity, prev = slot ^ 1;
+    if (c->inflight && (c->call_S[prev] != S || c->call_F[prev] != F)) drain(c);    // slot regions would not line up
+    rr_frame_bufs &b = c->fb;
+    b.bgf = c->d_bgf;
+    b.err_flag = c->d_err2 + slot;
+    int32_t *sub_off = c->h_sub_off + (size_t)slot * RR_MAX_SUB * (c->max_batch + 1);
+    if (timed) CK(cudaEventRecord(c->ev[RR_T_H2D], st));
+    CK(cudaMemsetAsync(b.err_flag, 0, sizeof(int), st));
+    long long sb = 0;
+    for (int k = 0; k < S; k++) {
+        const int f0 = fstart[k], nf = fstart[k + 1] - f0, s0 = streak_offsets[f0], ns = streak_offsets[f0 + nf] - s0;
+        int32_t *so = sub_off + (size_t)k * (c->max_batch + 1);
+        for (int i = 0; i <= nf; i++) so[i] = streak_offsets[f0 + i] - s0;
+        cudaStream_t hs = S > 1 ? c->s_h2d : st;
+        rr_streak_rec *d_slot = c->d_streaks + (size_t)k * c->sub_cap;
+        if (S > 1) CK(cudaStreamWaitEvent(hs, c->ev_done[k], 0));      // the previous batch no longer reads slot k's inputs
+        CK(cudaMemcpyAsync(c->d_bgr + (size_t)f0 * np * 3 * rs2, bgr + (size_t)f0 * np * 3 * rs2, (size_t)nf * np * 3 * rs2, cudaMemcpyHostToDevice, hs));
+        CK(cudaMemcpyAsync(c->d_depth + (size_t)f0 * np, depth + (size_t)f0 * np, (size_t)nf * np * sizeof(float), cudaMemcpyHostToDevice, hs));
+        if (ns) CK(cudaMemcpyAsync(d_slot, streaks + s0, (size_t)ns * sizeof(rr_streak_rec), cudaMemcpyHostToDevice, hs));
+        CK(cudaMemcpyAsync(c->d_sub_offsets + (size_t)k * (c->max_batch + 1), so, (nf + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, hs));
+        if (S > 1) {
+            CK(cudaEventRecord(c->ev_in[k], hs));
+            CK(cudaStreamWaitEvent(st, c->ev_in[k], 0));
+            CK(cudaStreamWaitEvent(st, c->ev_d2h[k], 0));             // the previous batch's outputs of slot k have left the device
         }
-        c->n_sub_last = S;
-        c->last_n_streaks = n_streaks;
+        c->scan_base[k] = sb; c->sub_n[k] = ns;
+        c->call_scan_base[slot][k] = sb; c->call_sub_n[slot][k] = ns;
+        rr_frame_bufs saved = c->fb;
+        saved.bgr = c->d_bgr; saved.depth = c->d_depth; saved.streaks = d_slot - s0;   // sub_view adds s0 back
+        saved.offsets = c->d_sub_offsets + (size_t)k * (c->max_batch + 1);
+        c->fb = sub_view(c, saved, f0, s0, sb);
+        c->fb.offsets = saved.offsets;
+        r = run_pipeline(c, nf, ns, timed && S == 1);
+        saved.bgr = nullptr; saved.depth = nullptr; saved.streaks = nullptr;
+        c->fb = saved;
+        if (r != RR_OK) return r;
+        sb += ns + 1;
+        cudaStream_t ds = S > 1 ? c->s_d2h : st;
+        if (S > 1) { CK(cudaEventRecord(c->ev_done[k], st)); CK(cudaStreamWaitEvent(ds, c->ev_done[k], 0)); }
+        if (out_bgr) CK(cudaMemcpyAsync(out_bgr + (size_t)f0 * np * 3, b.out_bgr + (size_t)f0 * np * 3, (size_t)nf * np * 3 * sizeof(float), cudaMemcpyDeviceToHost, ds));
+        if (out_mask) CK(cudaMemcpyAsync(out_mask + (size_t)f0 * np, b.out_mask + (size_t)f0 * np, (size_t)nf * np * sizeof(float), cudaMemcpyDeviceToHost, ds));
+        if (out_bgr_u8) CK(cudaMemcpyAsync(out_bgr_u8 + (size_t)f0 * np * 3, b.out_u8 + (size_t)f0 * np * 3, (size_t)nf * np * 3, cudaMemcpyDeviceToHost, ds));
+        if (S > 1) CK(cudaEventRecord(c->ev_d2h[k], ds));
+    }
+    c->n_sub_last = S;
+    c->last_n_streaks = n_streaks;
+    c->call_S[slot] = S; c->call_F[slot] = F; c->call_n[slot] = n_streaks;
+    if (timed) {
         if (S > 1) { CK(cudaEventRecord(c->ev_out, c->s_d2h)); CK(cudaStreamWaitEvent(st, c->ev_out, 0)); }
         CK(cudaEventRecord(c->ev[RR_T_TOTAL], st));
-        r = check_flag(c, attempt == 0);
+    }
+    CK(cudaEventRecord(c->ev_call[slot], S > 1 ? c->s_d2h : st));
+    c->inflight++;
+    c->parity ^= 1;
+    return RR_OK;
+}
+
+static int validate_batch(rr_context *c, int n_frames, const uint8_t *bgr, const float *depth, const rr_streak_rec *streaks,
+                          const int32_t *streak_offsets, const char *who) {
+    int r = check_ready(c, n_frames, who);
+    if (r != RR_OK) return r;
+    if (!bgr || !depth || !streak_offsets) { set_err("%s: NULL input", who); return RR_ERR_ARG; }
+    if (!c->d_db) { set_err("%s: no streak DB", who); return RR_ERR_STATE; }
+    const int n_streaks = streak_offsets[n_frames];
+    if (streak_offsets[0] != 0 || n_streaks < 0 || (n_streaks > 0 && !streaks)) { set_err("%s: bad streak offsets", who); return RR_ERR_ARG; }
+    for (int f = 0; f < n_frames; f++)
+        if (streak_offsets[f + 1] < streak_offsets[f]) { set_err("%s: streak offsets not monotone", who); return RR_ERR_ARG; }
+    return RR_OK;
+}
+
+int rr_submit_frames(rr_context *c, int n_frames, const uint8_t *bgr, const float *depth, const rr_streak_rec *streaks,
+                     const int32_t *streak_offsets, float *out_bgr, float *out_mask, uint8_t *out_bgr_u8) {
+    int r = validate_batch(c, n_frames, bgr, depth, streaks, streak_offsets, "rr_submit_frames");
+    if (r != RR_OK) return r;
+    CK(cudaSetDevice(c->device));
+    return submit_frames(c, n_frames, bgr, depth, streaks, streak_offsets, out_bgr, out_mask, out_bgr_u8, false);
+}
+
+int rr_wait_frames(rr_context *c) {
+    if (!c) { set_err("rr_wait_frames: context is NULL"); return RR_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    return wait_oldest(c, true);
+}
+
+int rr_render_frames(rr_context *c, int n_frames, const uint8_t *bgr, const float *depth, const rr_streak_rec *streaks,
+                     const int32_t *streak_offsets, float *out_bgr, float *out_mask, uint8_t *out_bgr_u8) {
+    int r = validate_batch(c, n_frames, bgr, depth, streaks, streak_offsets, "rr_render_frames");
+    if (r != RR_OK) return r;
+    CK(cudaSetDevice(c->device));
+    while (c->inflight) { r = wait_oldest(c, false); if (r != RR_OK) return r; }
+    for (int attempt = 0;; attempt++) {
+        r = submit_frames(c, n_frames, bgr, depth, streaks, streak_offsets, out_bgr, out_mask, out_bgr_u8, true);
+        if (r != RR_OK) return r;
+        const int S = c->n_sub_last;
+        r = wait_oldest(c, attempt == 0);
         if (r == RR_ERR_CAPACITY && attempt == 0 && strstr(g_err, "grown")) continue;   // re-run once with the larger arena
-        break;
+        if (S == 1) finish_timings(c);
+        else {
+            memset(c->last_ms, 0, sizeof(c->last_ms));
+            float tot = 0;
+            if (cudaEventElapsedTime(&tot, c->ev[RR_T_H2D], c->ev[RR_T_TOTAL]) == cudaSuccess) c->last_ms[RR_T_TOTAL] = tot;
+        }
+        return r;
     }
-    if (S == 1) finish_timings(c);
-    else {
-        memset(c->last_ms, 0, sizeof(c->last_ms));
-        float tot = 0;
-        if (cudaEventElapsedTime(&tot, c->ev[RR_T_H2D], c->ev[RR_T_TOTAL]) == cudaSuccess) c->last_ms[RR_T_TOTAL] = tot;
-    }
-    return r;
 }
 
 int rr_render_frames_device(rr_context *c, int n_frames, const uint8_t *d_bgr, const float *d_depth,
@@ -481,8 +574,10 @@ int rr_render_frames_device(rr_context *c, int n_frames, const uint8_t *d_bgr, c
     if (!c->d_db) { set_err("rr_render_frames_device: no streak DB"); return RR_ERR_STATE; }
     CK(cudaSetDevice(c->device));
     const int F = n_frames, n_streaks = h_streak_offsets[F];
-    r = ensure_streak_cap(c, n_streaks);
+    while (c->inflight) { r = wait_oldest(c, false); if (r != RR_OK) return r; }
+    r = ensure_streak_cap(c, n_streaks, 0);
     if (r != RR_OK) return r;
+    c->fb.err_flag = c->d_err2;
     cudaStream_t st = c->stream;
     rr_frame_bufs b_saved = c->fb;
     rr_frame_bufs &b = c->fb;
@@ -522,6 +617,7 @@ int rr_fog_only(rr_context *c, int n_frames, const uint8_t *bgr, const float *de
     int r = check_ready(c, n_frames, "rr_fog_only");
     if (r != RR_OK) return r;
     CK(cudaSetDevice(c->device));
+    while (c->inflight) { r = wait_oldest(c, false); if (r != RR_OK) return r; }
     const size_t np = (size_t)c->cam.W * c->cam.H, F = n_frames;
     cudaStream_t st = c->stream;
     rr_frame_bufs &b = c->fb;
@@ -541,6 +637,7 @@ int rr_envmap_only(rr_context *c, int n_frames, const double *planar, uint8_t *o
     int r = check_ready(c, n_frames, "rr_envmap_only");
     if (r != RR_OK) return r;
     CK(cudaSetDevice(c->device));
+    while (c->inflight) { r = wait_oldest(c, false); if (r != RR_OK) return r; }
     const size_t np = (size_t)c->cam.W * c->cam.H, F = n_frames, npe = (size_t)c->H_env * c->W_env;
     cudaStream_t st = c->stream;
     rr_frame_bufs &b = c->fb;
@@ -560,7 +657,8 @@ int rr_streak_photometry_only(rr_context *c, const uint8_t *env_bgr_u8, int n_st
     if (!c->d_db) { set_err("rr_streak_photometry_only: no streak DB"); return RR_ERR_STATE; }
     if (n_streaks <= 0) return RR_OK;
     CK(cudaSetDevice(c->device));
-    r = ensure_streak_cap(c, n_streaks);
+    while (c->inflight) { r = wait_oldest(c, false); if (r != RR_OK) return r; }
+    r = ensure_streak_cap(c, n_streaks, n_streaks);
     if (r != RR_OK) return r;
     const size_t npe = (size_t)c->H_env * c->W_env;
     cudaStream_t st = c->stream;
@@ -607,6 +705,7 @@ int rr_debug_read(rr_context *c, int what, int frame, void *dst, size_t bytes) {
     if (!c || !c->have_cam || !dst) { set_err("rr_debug_read: bad arguments"); return RR_ERR_ARG; }
     if (frame < 0 || frame >= c->max_batch) { set_err("rr_debug_read: frame out of range"); return RR_ERR_ARG; }
     CK(cudaSetDevice(c->device));
+    while (c->inflight) { int q = wait_oldest(c, false); if (q != RR_OK) return q; }
     const size_t np = (size_t)c->cam.W * c->cam.H, npe = (size_t)c->H_env * c->W_env;
     const rr_frame_bufs &b = c->fb;
     const void *src = nullptr;
@@ -660,8 +759,10 @@ int rr_host_free(void *ptr) {
 int rr_synchronize(rr_context *c) {
     if (!c) { set_err("rr_synchronize: context is NULL"); return RR_ERR_ARG; }
     CK(cudaSetDevice(c->device));
+    int r = RR_OK;
+    while (c->inflight) { int q = wait_oldest(c, false); if (q != RR_OK) r = q; }
     CK(cudaStreamSynchronize(c->stream));
-    int r = c->have_cam ? check_flag(c, false) : RR_OK;
+    if (c->have_cam && c->fb.err_flag) { int q = check_flag(c, false); if (q != RR_OK) r = q; }
     if (c->have_cam) finish_timings(c);
     return r;
 }

@@ -29,7 +29,7 @@ spans = sorted((int(o[0]), int(o[1])) for o in out)
 assert spans[0][0] == 0 and spans[-1][1] == n and spans[0][1] == spans[1][0]
 assert abs((spans[0][1] - spans[0][0]) - (spans[1][1] - spans[1][0])) <= 1
 dist.barrier()
-print("rank", rank, "ok")
+open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "rank" + str(rank) + ".ok"), "w").write("ok")
 """ % ROOT
 
 
@@ -45,7 +45,7 @@ def test_gloo_world_size_2_db_broadcast_and_sharding(tmp_path):
     env = dict(os.environ, OMP_NUM_THREADS="1")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+    assert (tmp_path / "rank0.ok").exists() and (tmp_path / "rank1.ok").exists(), out.stdout[-2000:] + out.stderr[-2000:]
 
 
 def test_shard_range_properties():

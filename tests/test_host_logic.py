@@ -28,7 +28,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_struct_sizes_match_header():
     assert S.STREAK_DTYPE.itemsize == 128
-    assert ctypes.sizeof(_lib.Camera) == 8 + 10 * 8
+    assert ctypes.sizeof(_lib.Camera) == 8 + 10 * 8 + 8      # W, H, ten doubles, render_scale + reserved
     assert _lib.PLAN_DTYPE.itemsize == 280
 
 
