@@ -65,7 +65,7 @@ struct rr_context {
     // asynchronous submissions (rr_submit_frames / rr_wait_frames): at most two batches in flight
     cudaEvent_t ev_call[2];
     int inflight = 0, parity = 0;        // parity: slot the next submission uses; oldest in flight = parity ^ (inflight == 2 ? 0 : 1)
-    int call_S[2] = {1, 1}, call_F[2] = {0, 0}, call_n[2] = {0, 0};
+    int call_S[2] = {1, 1}, call_F[2] = {0, 0}, call_n[2] = {0, 0}, call_multi[2] = {0, 0};
     long long call_scan_base[2][RR_MAX_SUB];
     int call_sub_n[2][RR_MAX_SUB];
     int32_t *h_sub_off = nullptr;        // pinned staging [2][RR_MAX_SUB][max_batch + 1]
@@ -437,20 +437,23 @@ static int wait_oldest(rr_context *c, bool grow) {
 }
 
 static int submit_frames(rr_context *c, int F, const uint8_t *bgr, const float *depth, const rr_streak_rec *streaks,
-                         const int32_t *streak_offsets, float *out_bgr, float *out_mask, uint8_t *out_bgr_u8, bool timed) {
+                         const int32_t *streak_offsets, float *out_bgr, float *out_mask, uint8_t *out_bgr_u8, bool timed,
+                         int default_sub) {
     const int n_streaks = streak_offsets[F];
     const size_t np = (size_t)c->cam.W * c->cam.H;
     const size_t rs2 = c->cam.render_scale == 2 ? 4 : 1;
     cudaStream_t st = c->stream;
-    // sub-batches overlap H2D / compute / D2H when the caller's buffers are page-locked
+    // With page-locked caller buffers the copies run on their own streams: inside one call sub-batches overlap
+    // H2D / compute / D2H (synchronous rr_render_frames: 4), across calls whole batches do (rr_submit_frames: 1).
     int S = 1;
+    bool multi = false;
     {
         cudaPointerAttributes pa;
-        bool pinned = cudaPointerGetAttributes(&pa, bgr) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+        multi = cudaPointerGetAttributes(&pa, bgr) == cudaSuccess && pa.type == cudaMemoryTypeHost;
         cudaGetLastError();
-        const char *env = getenv("RR_SUB_BATCHES");
-        int want = env ? atoi(env) : 4;
-        if (pinned && want > 1) S = want < RR_MAX_SUB ? want : RR_MAX_SUB;
+        const char *env = getenv(timed ? "RR_SUB_BATCHES" : "RR_SUB_BATCHES_ASYNC");
+        int want = env ? atoi(env) : default_sub;
+        if (multi && want > 1) S = want < RR_MAX_SUB ? want : RR_MAX_SUB;
         if (S > F) S = F;
     }
     int fstart[RR_MAX_SUB + 1], max_ns = 0;
@@ -460,7 +463,7 @@ static int submit_frames(rr_context *c, int F, const uint8_t *bgr, const float *
     if (r != RR_OK) return r;
     if (c->inflight == 2) { r = wait_oldest(c, false); if (r != RR_OK) return r; }
     const int slot = c->parity, prev = slot ^ 1;
-    if (c->inflight && (c->call_S[prev] != S || c->call_F[prev] != F)) drain(c);    // slot regions would not line up
+    if (c->inflight && (c->call_S[prev] != S || c->call_F[prev] != F || c->call_multi[prev] != (int)multi)) drain(c);    // slot regions would not line up
     rr_frame_bufs &b = c->fb;
     b.bgf = c->d_bgf;
     b.err_flag = c->d_err2 + slot;
@@ -472,14 +475,14 @@ static int submit_frames(rr_context *c, int F, const uint8_t *bgr, const float *
         const int f0 = fstart[k], nf = fstart[k + 1] - f0, s0 = streak_offsets[f0], ns = streak_offsets[f0 + nf] - s0;
         int32_t *so = sub_off + (size_t)k * (c->max_batch + 1);
         for (int i = 0; i <= nf; i++) so[i] = streak_offsets[f0 + i] - s0;
-        cudaStream_t hs = S > 1 ? c->s_h2d : st;
+        cudaStream_t hs = multi ? c->s_h2d : st;
         rr_streak_rec *d_slot = c->d_streaks + (size_t)k * c->sub_cap;
-        if (S > 1) CK(cudaStreamWaitEvent(hs, c->ev_done[k], 0));      // the previous batch no longer reads slot k's inputs
+        if (multi) CK(cudaStreamWaitEvent(hs, c->ev_done[k], 0));      // the previous batch no longer reads slot k's inputs
         CK(cudaMemcpyAsync(c->d_bgr + (size_t)f0 * np * 3 * rs2, bgr + (size_t)f0 * np * 3 * rs2, (size_t)nf * np * 3 * rs2, cudaMemcpyHostToDevice, hs));
         CK(cudaMemcpyAsync(c->d_depth + (size_t)f0 * np, depth + (size_t)f0 * np, (size_t)nf * np * sizeof(float), cudaMemcpyHostToDevice, hs));
         if (ns) CK(cudaMemcpyAsync(d_slot, streaks + s0, (size_t)ns * sizeof(rr_streak_rec), cudaMemcpyHostToDevice, hs));
         CK(cudaMemcpyAsync(c->d_sub_offsets + (size_t)k * (c->max_batch + 1), so, (nf + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, hs));
-        if (S > 1) {
+        if (multi) {
             CK(cudaEventRecord(c->ev_in[k], hs));
             CK(cudaStreamWaitEvent(st, c->ev_in[k], 0));
             CK(cudaStreamWaitEvent(st, c->ev_d2h[k], 0));             // the previous batch's outputs of slot k have left the device
@@ -496,21 +499,21 @@ static int submit_frames(rr_context *c, int F, const uint8_t *bgr, const float *
         c->fb = saved;
         if (r != RR_OK) return r;
         sb += ns + 1;
-        cudaStream_t ds = S > 1 ? c->s_d2h : st;
-        if (S > 1) { CK(cudaEventRecord(c->ev_done[k], st)); CK(cudaStreamWaitEvent(ds, c->ev_done[k], 0)); }
+        cudaStream_t ds = multi ? c->s_d2h : st;
+        if (multi) { CK(cudaEventRecord(c->ev_done[k], st)); CK(cudaStreamWaitEvent(ds, c->ev_done[k], 0)); }
         if (out_bgr) CK(cudaMemcpyAsync(out_bgr + (size_t)f0 * np * 3, b.out_bgr + (size_t)f0 * np * 3, (size_t)nf * np * 3 * sizeof(float), cudaMemcpyDeviceToHost, ds));
         if (out_mask) CK(cudaMemcpyAsync(out_mask + (size_t)f0 * np, b.out_mask + (size_t)f0 * np, (size_t)nf * np * sizeof(float), cudaMemcpyDeviceToHost, ds));
         if (out_bgr_u8) CK(cudaMemcpyAsync(out_bgr_u8 + (size_t)f0 * np * 3, b.out_u8 + (size_t)f0 * np * 3, (size_t)nf * np * 3, cudaMemcpyDeviceToHost, ds));
-        if (S > 1) CK(cudaEventRecord(c->ev_d2h[k], ds));
+        if (multi) CK(cudaEventRecord(c->ev_d2h[k], ds));
     }
     c->n_sub_last = S;
     c->last_n_streaks = n_streaks;
-    c->call_S[slot] = S; c->call_F[slot] = F; c->call_n[slot] = n_streaks;
+    c->call_S[slot] = S; c->call_F[slot] = F; c->call_n[slot] = n_streaks; c->call_multi[slot] = (int)multi;
     if (timed) {
-        if (S > 1) { CK(cudaEventRecord(c->ev_out, c->s_d2h)); CK(cudaStreamWaitEvent(st, c->ev_out, 0)); }
+        if (multi) { CK(cudaEventRecord(c->ev_out, c->s_d2h)); CK(cudaStreamWaitEvent(st, c->ev_out, 0)); }
         CK(cudaEventRecord(c->ev[RR_T_TOTAL], st));
     }
-    CK(cudaEventRecord(c->ev_call[slot], S > 1 ? c->s_d2h : st));
+    CK(cudaEventRecord(c->ev_call[slot], multi ? c->s_d2h : st));
     c->inflight++;
     c->parity ^= 1;
     return RR_OK;
@@ -534,7 +537,7 @@ int rr_submit_frames(rr_context *c, int n_frames, const uint8_t *bgr, const floa
     int r = validate_batch(c, n_frames, bgr, depth, streaks, streak_offsets, "rr_submit_frames");
     if (r != RR_OK) return r;
     CK(cudaSetDevice(c->device));
-    return submit_frames(c, n_frames, bgr, depth, streaks, streak_offsets, out_bgr, out_mask, out_bgr_u8, false);
+    return submit_frames(c, n_frames, bgr, depth, streaks, streak_offsets, out_bgr, out_mask, out_bgr_u8, false, 1);
 }
 
 int rr_wait_frames(rr_context *c) {
@@ -550,7 +553,7 @@ int rr_render_frames(rr_context *c, int n_frames, const uint8_t *bgr, const floa
     CK(cudaSetDevice(c->device));
     while (c->inflight) { r = wait_oldest(c, false); if (r != RR_OK) return r; }
     for (int attempt = 0;; attempt++) {
-        r = submit_frames(c, n_frames, bgr, depth, streaks, streak_offsets, out_bgr, out_mask, out_bgr_u8, true);
+        r = submit_frames(c, n_frames, bgr, depth, streaks, streak_offsets, out_bgr, out_mask, out_bgr_u8, true, 4);
         if (r != RR_OK) return r;
         const int S = c->n_sub_last;
         r = wait_oldest(c, attempt == 0);
