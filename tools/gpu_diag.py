@@ -48,27 +48,7 @@ def main():
         r = recs[offs[i]:offs[i + 1]]
         print("  tex_idx equal", np.array_equal(r["tex_idx"], np.array(o.tex_idx)), "noise equal", np.array_equal(r["noise_deg"], np.array(o.noise)))
         pl = plans[offs[i]:offs[i + 1]]
-        bad = 0
-        for k, (p, q) in enumerate(zip(pl, o.per_streak)):
-            if (p["bx0"], p["by0"]) != tuple(q["minC"]) or (p["bh"], p["bw"]) != tuple(q["shape"]):
-                if q["shape"][0] * q["shape"][1] == 0 and p["bw"] * p["bh"] == 0:
-                    continue
-                bad += 1
-                if bad < 5:
-                    print("   plan mismatch", k, (p["bx0"], p["by0"], p["bw"], p["bh"]), q["minC"], q["shape"])
-        print("  plan placement mismatches", bad)
-        if i == 0:
-            arena_n = int((pl["a_off"] + pl["bw"].astype(np.int64) * pl["bh"]).max()) if len(pl) else 0
-            arena = ctx.debug_read("arena", 0, arena_n)
-            worst = 0
-            for k, (p, q) in enumerate(zip(pl, o.per_streak)):
-                n = int(p["bw"]) * int(p["bh"])
-                if n == 0 or "patch" not in q:
-                    continue
-                a = arena[p["a_off"]:p["a_off"] + n].reshape(p["bh"], p["bw"])
-                dd = np.abs(a - q["patch"][..., 3]).max()
-                worst = max(worst, dd)
-            print("  blurred alpha max abs diff", worst)
+        # (plan placement is the tight block of DESIGN.md 6.4, not the reference's padded block: not compared)
         dm = np.abs(out["mask"][i].astype(np.float64) - o.rain_mask)
         print("  mask support equal", np.array_equal(out["mask"][i] > 0, o.rain_mask > 0), "mask f32 ulp max",
               int(ulp_diff_f32(out["mask"][i], o.rain_mask.astype(np.float32)).max()), "maxabs", dm.max())
