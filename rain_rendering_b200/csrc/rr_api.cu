@@ -73,8 +73,13 @@ struct rr_context {
     int sub_cap = 0;                     // records per sub-batch slot of d_streaks
 };
 
+// allocates (releasing what *p pointed to before, if the context owned it)
 template <class T>
 static cudaError_t dev_alloc(rr_context *c, T **p, size_t count) {
+    if (*p)
+        for (size_t i = 0; i < c->owned.size(); i++)
+            if (c->owned[i] == (void *)*p) { cudaFree(*p); c->owned.erase(c->owned.begin() + i); break; }
+    *p = nullptr;
     cudaError_t e = cudaMalloc((void **)p, count * sizeof(T) + 256);
     if (e == cudaSuccess) c->owned.push_back((void *)*p);
     return e;
@@ -89,6 +94,9 @@ static void free_camera(rr_context *c) {
     c->have_cam = false;
     c->streak_cap = 0;
     memset(&c->fb, 0, sizeof(c->fb));
+    c->d_env_src = nullptr; c->d_env_written = nullptr; c->d_omega = c->d_omega_pref = c->d_omega_total = nullptr;
+    c->d_bgr = nullptr; c->d_bgf = nullptr; c->d_depth = nullptr; c->d_streaks = nullptr; c->d_offsets = nullptr;
+    c->d_sub_offsets = nullptr; c->d_err2 = nullptr;
 }
 
 extern "C" {

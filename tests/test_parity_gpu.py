@@ -108,6 +108,29 @@ def test_edge_cases_empty_ragged_and_out_of_frame():
     ctx.close()
 
 
+def test_degenerate_streaks_are_skipped_like_the_reference():
+    """The reference wraps every streak in try/except and skips the ones that raise
+    (common/generator.py:180-189): a streak at the camera centre (no view direction) and one at zero
+    depth (infinite circle of confusion) must vanish on both sides, the frame must not."""
+    sc = Scenario(512, 256, 1, 900, fallrate=25)
+    ctx = sc.context()
+    bad_a, bad_b = sc.oracle_frames[0][3], sc.oracle_frames[0][7]
+    bad_a.wp1[:] = 0; bad_a.wp2[:] = 0                     # |P| = 0 -> NaN direction -> "Drop skipped"
+    bad_b.wp1[2] = 0.0                                     # o = 0 -> c = inf -> int(10 c) raises
+    sc.sim_frames[0]["wp1"][3] = 0; sc.sim_frames[0]["wp2"][3] = 0
+    sc.sim_frames[0]["wp1"][7, 2] = 0.0
+    recs, offs = sc.records()
+    pids = {int(bad_a.pid), int(bad_b.pid)}
+    assert pids <= set(recs["pid"].tolist()), "the degenerate streaks must be inside the frame for this test"
+    out = ctx.render_frames(sc.bgr, sc.depth, recs, offs)
+    o = sc.oracle_frame(0, "canonical")
+    assert {p for p, _ in o.skipped} == pids
+    _check_frame(out, 0, o)
+    plans = ctx.debug_read("plans", 0, len(recs))
+    assert sorted(recs["pid"][plans["valid"] == 0].tolist()) == sorted(pids)
+    ctx.close()
+
+
 def test_determinism_and_batch_independence():
     sc = Scenario(512, 256, 3, 900, fallrate=25)
     ctx = sc.context()
