@@ -291,7 +291,6 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
     CK(dev_alloc(c, &b.rainy, F * 3 * np));
     CK(dev_alloc(c, &b.bg8, F * np * 3));
     CK(dev_alloc(c, &b.fblur, F * np));
-    CK(dev_alloc(c, &b.env_fill, F * npe * 3));
     CK(dev_alloc(c, &b.env8, F * npe * 3));
     CK(dev_alloc(c, &b.pref, F * 4 * (size_t)He * (We + 1)));
     CK(dev_alloc(c, &b.rowtot, F * He));
@@ -362,7 +361,7 @@ static int run_pipeline(rr_context *c, int F, int n_streaks, bool timed) {
     if (timed) CK(cudaEventRecord(c->ev[RR_T_EPILOGUE], st));
     CK(rr_launch_epilogue(b, F, W, H, st));
     if (timed) CK(cudaEventRecord(c->ev[RR_T_D2H], st));
-    c->launches += 3 + 1 + 4 + (n_streaks ? 1 : 0) + 1 + (n_streaks ? 3 : 0) + 2 + 1;
+    c->launches += 3 + 1 + 3 + (n_streaks ? 1 : 0) + 1 + (n_streaks ? 3 : 0) + 2 + 1;
     c->last_n_streaks = n_streaks;
     return RR_OK;
 }
@@ -377,7 +376,7 @@ static rr_frame_bufs sub_view(const rr_context *c, const rr_frame_bufs &b, int f
     if (v.bgf) v.bgf += (size_t)f0 * 3 * np;
     v.bg_sum += (size_t)f0 * 4;
     v.chan_sum += (size_t)f0 * 4; v.rainy += (size_t)f0 * 3 * np; v.bg8 += (size_t)f0 * np * 3; v.fblur += (size_t)f0 * np;
-    v.env_fill += (size_t)f0 * npe * 3; v.env8 += (size_t)f0 * npe * 3;
+    v.env8 += (size_t)f0 * npe * 3;
     v.pref += (size_t)f0 * 4 * c->H_env * (c->W_env + 1); v.rowtot += (size_t)f0 * c->H_env; v.ambient += f0;
     v.plans += s0; v.sizes += s0; v.boxes += s0; v.scan += (size_t)scan_base * 6;
     v.tile_sum += (size_t)f0 * tiles; v.frame_mean += f0;
@@ -658,7 +657,7 @@ int rr_envmap_only(rr_context *c, int n_frames, const double *planar, uint8_t *o
     CK(cudaMemcpyAsync(b.rainy, planar, F * 3 * np * sizeof(double), cudaMemcpyHostToDevice, st));
     CK(rr_launch_planar_to_bg8(b.rainy, b.bg8, n_frames, c->cam.W, c->cam.H, st));
     CK(rr_launch_env(b, tabs_of(c), n_frames, c->cam.W, c->cam.H, c->W_env, st));
-    c->launches += 5;
+    c->launches += 4;
     CK(cudaMemcpyAsync(out_env, b.env8, F * npe * 3, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return RR_OK;

@@ -461,32 +461,19 @@ cudaError_t rr_launch_planar_to_bg8(const double *planar, uint8_t *bg8, int F, i
 // ------------------------------------------------------------------------------------------
 // per frame: environment map = gather + 15x15 uint8 blur on the hole pixels  (bad_weather.py:742-819)
 // ------------------------------------------------------------------------------------------
-__global__ void k_env_gather(const uint8_t *bg8, const int32_t *env_src, uint8_t *env_fill, int npix_img, int npix_env) {
-    int f = blockIdx.y;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= npix_env) return;
-    int s = env_src[i];
-    uint8_t v0 = 0, v1 = 0, v2 = 0;
-    if (s >= 0) {
-        const uint8_t *p = bg8 + ((size_t)f * npix_img + s) * 3;
-        v0 = p[0]; v1 = p[1]; v2 = p[2];
-    }
-    uint8_t *o = env_fill + ((size_t)f * npix_env + i) * 3;
-    o[0] = v0; o[1] = v1; o[2] = v2;
-}
-
 #define ENV_TX 64
 #define ENV_TY 16
 #define ENV_R 7
-__global__ void __launch_bounds__(256) k_env_blur(const uint8_t *env_fill, const uint8_t *env_written, uint8_t *env8, int H,
-                                                  int W_env) {
+// Gather through the static source-index table and, for the never-written pixels, OpenCV's fixed-point
+// 15x15 Gaussian of the gathered map (bad_weather.py:814-817), in one pass: tiles without holes are a pure gather.
+__global__ void __launch_bounds__(256) k_env_map(const uint8_t *bg8, const int32_t *env_src, const uint8_t *env_written, uint8_t *env8,
+                                                 int H, int W_env, int npix_img) {
     __shared__ uint8_t in[ENV_TY + 2 * ENV_R][ENV_TX + 2 * ENV_R][3];
     __shared__ unsigned short hp[ENV_TY + 2 * ENV_R][ENV_TX][3];
-    int f = blockIdx.z;
-    int x0 = blockIdx.x * ENV_TX, y0 = blockIdx.y * ENV_TY;
-    const uint8_t *src = env_fill + (size_t)f * H * W_env * 3;
-    // does this tile contain a hole?  (most tiles do not: plain copy)
     __shared__ int any_hole;
+    const int f = blockIdx.z;
+    const int x0 = blockIdx.x * ENV_TX, y0 = blockIdx.y * ENV_TY;
+    const uint8_t *img = bg8 + (size_t)f * npix_img * 3;
     if (threadIdx.x == 0) any_hole = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < ENV_TX * ENV_TY; i += 256) {
@@ -499,9 +486,12 @@ __global__ void __launch_bounds__(256) k_env_blur(const uint8_t *env_fill, const
         for (int i = threadIdx.x; i < (ENV_TY + 2 * ENV_R) * (ENV_TX + 2 * ENV_R); i += 256) {
             int ey = i / (ENV_TX + 2 * ENV_R), ex = i - ey * (ENV_TX + 2 * ENV_R);
             int gy = r101(y0 + ey - ENV_R, H), gx = r101(x0 + ex - ENV_R, W_env);
-            bool ok = gy >= 0 && gy < H && gx >= 0 && gx < W_env;
-            const uint8_t *p = src + ((size_t)gy * W_env + gx) * 3;
-            in[ey][ex][0] = ok ? p[0] : 0; in[ey][ex][1] = ok ? p[1] : 0; in[ey][ex][2] = ok ? p[2] : 0;
+            uint8_t v0 = 0, v1 = 0, v2 = 0;
+            if (gy >= 0 && gy < H && gx >= 0 && gx < W_env) {
+                int sidx = env_src[(size_t)gy * W_env + gx];
+                if (sidx >= 0) { const uint8_t *p = img + (size_t)sidx * 3; v0 = p[0]; v1 = p[1]; v2 = p[2]; }
+            }
+            in[ey][ex][0] = v0; in[ey][ex][1] = v1; in[ey][ex][2] = v2;
         }
         __syncthreads();
         for (int i = threadIdx.x; i < (ENV_TY + 2 * ENV_R) * ENV_TX; i += 256) {
@@ -522,8 +512,13 @@ __global__ void __launch_bounds__(256) k_env_blur(const uint8_t *env_fill, const
         size_t pix = (size_t)gy * W_env + gx;
         uint8_t *o = env8 + ((size_t)f * H * W_env + pix) * 3;
         if (env_written[pix]) {
-            const uint8_t *p = src + pix * 3;
-            o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+            if (any_hole) { o[0] = in[oy + ENV_R][ox + ENV_R][0]; o[1] = in[oy + ENV_R][ox + ENV_R][1]; o[2] = in[oy + ENV_R][ox + ENV_R][2]; }
+            else {
+                int sidx = env_src[pix];
+                uint8_t v0 = 0, v1 = 0, v2 = 0;
+                if (sidx >= 0) { const uint8_t *p = img + (size_t)sidx * 3; v0 = p[0]; v1 = p[1]; v2 = p[2]; }
+                o[0] = v0; o[1] = v1; o[2] = v2;
+            }
         } else {
             unsigned s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
@@ -612,11 +607,8 @@ __global__ void k_ambient(const double *rowtot, double *ambient, int H) {
 }
 
 cudaError_t rr_launch_env(const rr_frame_bufs &b, const rr_static_tabs &t, int F, int W, int H, int W_env, cudaStream_t st) {
-    int npe = H * W_env;
-    dim3 g1((npe + 255) / 256, F);
-    k_env_gather<<<g1, 256, 0, st>>>(b.bg8, t.env_src, b.env_fill, W * H, npe);
     dim3 g2((W_env + ENV_TX - 1) / ENV_TX, (H + ENV_TY - 1) / ENV_TY, F);
-    k_env_blur<<<g2, 256, 0, st>>>(b.env_fill, t.env_written, b.env8, H, W_env);
+    k_env_map<<<g2, 256, 0, st>>>(b.bg8, t.env_src, t.env_written, b.env8, H, W_env, W * H);
     cudaError_t e = launch_env_prefix(b.env8, t.omega, b.pref, b.rowtot, F, H, W_env, st);
     if (e != cudaSuccess) return e;
     k_ambient<<<F, 32, 0, st>>>(b.rowtot, b.ambient, H);
@@ -705,6 +697,7 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(rr_frame_bufs b, rr_
         long long g_, v_, a_; int vx0_, vw_;
         plan_sizes(p, &g_, &v_, &a_, &vx0_, &vw_);
         b.sizes[s] = make_int4((int)g_, (int)v_, (int)a_, 0);
+        b.boxes[s] = a_ > 0 ? make_int4(p.bx0, p.by0, p.bw, p.bh) : make_int4(0, 0, 0, 0);
     }
 }
 
@@ -739,44 +732,60 @@ __device__ __forceinline__ void blur_extents(const rr_plan &p, int *vx0, int *vw
 }
 
 __global__ void __launch_bounds__(1024) k_scan(rr_frame_bufs b, int n) {
-    __shared__ long long tot[1024][4];
-    int tid = threadIdx.x;
-    int per = (n + 1023) / 1024;
-    int i0 = tid * per, i1 = i0 + per < n ? i0 + per : n;
-    long long el = 0, c0 = 0, c1 = 0, c2 = 0;
-    for (int i = i0; i < i1; i++) {
-        int4 sz = b.sizes[i];
-        long long g = sz.x, v = sz.y, a = sz.z;
-        el += g + v + a;
-        c0 += (g + RR_RASTER_CHUNK - 1) / RR_RASTER_CHUNK;
-        c1 += (v + RR_BLUR_CHUNK - 1) / RR_BLUR_CHUNK;
-        c2 += (a + RR_BLUR_CHUNK - 1) / RR_BLUR_CHUNK;
-    }
-    tot[tid][0] = el; tot[tid][1] = c0; tot[tid][2] = c1; tot[tid][3] = c2;
-    __syncthreads();
+    // one block: per-thread chunk totals, a shuffle scan over the 1024 threads, then the chunk prefixes.
+    // Integer sums: exact and order independent.
+    __shared__ long long wtot[32][4];
+    __shared__ long long grand[4];
     __shared__ int overflow;
-    if (tid == 0) {
-        long long a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-        for (int t = 0; t < 1024; t++) {
-            long long v0 = tot[t][0], v1 = tot[t][1], v2 = tot[t][2], v3 = tot[t][3];
-            tot[t][0] = a0; tot[t][1] = a1; tot[t][2] = a2; tot[t][3] = a3;
-            a0 += v0; a1 += v1; a2 += v2; a3 += v3;
-        }
-        overflow = a0 > b.arena_cap;
-        if (overflow) { *b.err_flag = 1; a1 = a2 = a3 = 0; }    // nothing is rendered: the host grows the arena and re-runs
-        b.scan[(size_t)n * 6 + 0] = a0; b.scan[(size_t)n * 6 + 3] = a1; b.scan[(size_t)n * 6 + 4] = a2; b.scan[(size_t)n * 6 + 5] = a3;
-    }
-    __syncthreads();
-    el = tot[tid][0]; c0 = tot[tid][1]; c1 = tot[tid][2]; c2 = tot[tid][3];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int per = (n + 1023) / 1024;
+    const int i0 = tid * per, i1 = i0 + per < n ? i0 + per : n;
+    long long t[4] = {0, 0, 0, 0};
     for (int i = i0; i < i1; i++) {
-        rr_plan &p = b.plans[i];
         int4 sz = b.sizes[i];
         long long g = sz.x, v = sz.y, a = sz.z;
-        if (overflow) { p.valid = 0; p.bw = p.bh = 0; }
-        b.boxes[i] = (p.valid && a > 0) ? make_int4(p.bx0, p.by0, p.bw, p.bh) : make_int4(0, 0, 0, 0);
+        t[0] += g + v + a;
+        t[1] += (g + RR_RASTER_CHUNK - 1) / RR_RASTER_CHUNK;
+        t[2] += (v + RR_BLUR_CHUNK - 1) / RR_BLUR_CHUNK;
+        t[3] += (a + RR_BLUR_CHUNK - 1) / RR_BLUR_CHUNK;
+    }
+    long long inc[4], exc[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        long long v = t[q];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { long long u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+        inc[q] = v;
+        if (lane == 31) wtot[warp][q] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            long long v = wtot[lane][q], w = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { long long u = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += u; }
+            wtot[lane][q] = w - v;                       // exclusive prefix of the warp totals
+            if (lane == 31) grand[q] = w;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        overflow = grand[0] > b.arena_cap;
+        if (overflow) *b.err_flag = 1;                   // nothing is rendered: the host grows the arena and re-runs
+        long long *sc = b.scan + (size_t)n * 6;
+        sc[0] = grand[0]; sc[3] = overflow ? 0 : grand[1]; sc[4] = overflow ? 0 : grand[2]; sc[5] = overflow ? 0 : grand[3];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; q++) exc[q] = wtot[warp][q] + inc[q] - t[q];
+    long long el = exc[0], c0 = exc[1], c1 = exc[2], c2 = exc[3];
+    for (int i = i0; i < i1; i++) {
+        int4 sz = b.sizes[i];
+        long long g = sz.x, v = sz.y, a = sz.z;
+        if (overflow) { b.plans[i].valid = 0; b.boxes[i] = make_int4(0, 0, 0, 0); }
         long long *sc = b.scan + (size_t)i * 6;
         sc[0] = el; sc[1] = el + g; sc[2] = el + g + v; sc[3] = c0; sc[4] = c1; sc[5] = c2;
-        p.g_off = el; p.a_off = el + g + v;
         el += g + v + a;
         c0 += (g + RR_RASTER_CHUNK - 1) / RR_RASTER_CHUNK;
         c1 += (v + RR_BLUR_CHUNK - 1) / RR_BLUR_CHUNK;
@@ -860,7 +869,7 @@ __global__ void __launch_bounds__(RAS_THREADS, 4) k_raster(rr_frame_bufs b, rr_s
         plan_sizes(p, &g, &vv, &aa, &vx0_, &vw_);
         if (g == 0) continue;
         const uint8_t *tex = t.db + p.tex_off;
-        double *out = b.arena + p.g_off;
+        double *out = b.arena + b.scan[(size_t)s * 6 + 0];
         const bool staged = p.type != RR_BIG && (p.resize_mode == RR_RESIZE_AREA || p.resize_mode == RR_RESIZE_AREA_FAST) &&
                             p.nW <= RAS_MAXW && p.pw <= RAS_TXN && p.ph <= RAS_TXN && g <= RAS_MAXD;
         if (!staged) {
@@ -1027,7 +1036,7 @@ __global__ void __launch_bounds__(RR_BLUR_THREADS) k_blur_v(rr_frame_bufs b, int
         plan_sizes(p, &gg, &nv, &aa, &vx0, &vw);
         const int base = (int)((ch - b.scan[(size_t)s * 6 + 4]) * RR_BLUR_CHUNK);
         const int pw = p.pw, ph = p.ph, ry = p.ry, cropy = p.cropy, shift = p.shift;
-        const double *g = b.arena + p.g_off;
+        const double *g = b.arena + b.scan[(size_t)s * 6 + 0];
         double *vout = b.arena + b.scan[(size_t)s * 6 + 1];
         for (int e = base + threadIdx.x; e < base + RR_BLUR_CHUNK && e < (int)nv; e += RR_BLUR_THREADS) {
             int yy = e / vw, xx = e - yy * vw;
@@ -1059,7 +1068,7 @@ __global__ void __launch_bounds__(RR_BLUR_THREADS) k_blur_h(rr_frame_bufs b, int
         const int base = (int)((ch - b.scan[(size_t)s * 6 + 5]) * RR_BLUR_CHUNK);
         const int bw = p.bw, rx = p.rx, cropx = p.cropx;
         const double *vin = b.arena + b.scan[(size_t)s * 6 + 1];
-        double *aout = b.arena + p.a_off;
+        double *aout = b.arena + b.scan[(size_t)s * 6 + 2];
         for (int e = base + threadIdx.x; e < base + RR_BLUR_CHUNK && e < (int)na; e += RR_BLUR_THREADS) {
             int yy = e / bw, xx = e - yy * bw;
             const double *v = vin + yy * vw;
@@ -1129,7 +1138,7 @@ __global__ void __launch_bounds__(RR_TILE_W * RR_TILE_H) k_composite(rr_frame_bu
         if (hit) {
             int slot = pre + __popc(bal & ((1u << lane) - 1));
             comp_entry e;
-            e.bx0 = pbx0; e.by0 = pby0; e.bw = pbw; e.bh = pbh; e.a_off = pp->a_off;
+            e.bx0 = pbx0; e.by0 = pby0; e.bw = pbw; e.bh = pbh; e.a_off = b.scan[(size_t)s * 6 + 2];
             e.kb = pp->kb; e.kg = pp->kg; e.kr = pp->kr; e.tau_one = pp->a_scale; e.c_scale = pp->c_scale;
             list[slot] = e;
         }

@@ -17,7 +17,6 @@ struct rr_frame_bufs {
     double *rainy;             // [F][3][H][W] planar BGR float64
     uint8_t *bg8;              // [F][H][W][3] floor(rainy*255)
     float *fblur;              // [F][H][W] blurred extinction (debug / stage test)
-    uint8_t *env_fill;         // [F][H][W_env][3] gathered cylindrical map
     uint8_t *env8;             // [F][H][W_env][3] final environment map
     double *pref;              // [F][H][W_env+1][4] row prefix sums of (omega*x, omega*y, omega*Y, omega), interleaved
     double *rowtot;            // [F][H] row totals of omega*Y
