@@ -14,7 +14,7 @@ import numpy as np
 from . import build as _build
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librain_b200.so")
+LIB_PATH = os.environ.get("RR_LIB_OVERRIDE") or os.path.join(_HERE, "librain_b200.so")     # override: tuning experiments only
 
 
 class Camera(C.Structure):
@@ -55,7 +55,7 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH) or _build.stale():
+    if not os.environ.get("RR_LIB_OVERRIDE") and (not os.path.exists(LIB_PATH) or _build.stale()):
         try:
             _build.build()
         except Exception as e:  # no silent fallback

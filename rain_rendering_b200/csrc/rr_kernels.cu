@@ -622,7 +622,10 @@ cudaError_t rr_launch_env(const rr_frame_bufs &b, const rr_static_tabs &t, int F
 struct rr_plan;
 __device__ __forceinline__ void plan_sizes(const rr_plan &p, long long *g, long long *v, long long *a, int *vx0, int *vw);
 #define SETUP_WARPS 4
-__global__ void __launch_bounds__(SETUP_WARPS * 32) k_setup(rr_frame_bufs b, rr_static_tabs t, rr_cam_dev cam, int F,
+#ifndef SETUP_MINB
+#define SETUP_MINB 8          // 64 registers: the lane-0 serial sections are latency bound, more resident warps win (sweep r01h)
+#endif
+__global__ void __launch_bounds__(SETUP_WARPS * 32, SETUP_MINB) k_setup(rr_frame_bufs b, rr_static_tabs t, rr_cam_dev cam, int F,
                                                              int n_streaks) {
     __shared__ rr_fcp s_fcp[SETUP_WARPS];
     __shared__ int s_npts[SETUP_WARPS];
@@ -814,7 +817,12 @@ __device__ __forceinline__ int find_streak(const long long *scan, int n, int fie
 //                         top to bottom), so the result is bit-identical to the per-pixel evaluation.
 // ------------------------------------------------------------------------------------------
 #define RAS_THREADS 128
-#define RAS_CAP 1792          // doubles per staging array
+#ifndef RAS_CAP
+#define RAS_CAP 1280          // doubles per staging array (sweep r01h: 1024/6 CTAs 2.86 ms, 1280/5 2.05, 1792/4 2.16, 2304/3 2.47)
+#endif
+#ifndef RAS_MINB
+#define RAS_MINB 5            // resident CTAs per SM the register allocation is tuned for
+#endif
 #define RAS_MAXW 512          // widest rotated canvas handled by the staged path
 #define RAS_TXN 128           // widest / tallest patch with cached computeResizeAreaTab spans
 #define RAS_MAXD 1024         // patch pixels with accumulators resident in shared memory
@@ -845,7 +853,7 @@ struct ras_smem_src {       // functor over a staged band: rows [0, rb) x column
     __device__ __forceinline__ double operator()(int sx, int r) const { return C[r * nW + sx]; }
 };
 
-__global__ void __launch_bounds__(RAS_THREADS, 4) k_raster(rr_frame_bufs b, rr_static_tabs t, rr_cam_dev cam, int n) {
+__global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs b, rr_static_tabs t, rr_cam_dev cam, int n) {
     extern __shared__ double ras_smem[];
     double *C = ras_smem;                       // [RAS_CAP]   canvas band
     double *BUF = C + RAS_CAP;                  // [RAS_CAP]   per (source row, dx) column sums (area) / quad accumulators (area-fast)
@@ -989,7 +997,7 @@ cudaError_t rr_launch_raster(const rr_frame_bufs &b, const rr_static_tabs &t, co
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    int grid = n_sm * 4;
+    int grid = n_sm * RAS_MINB;
     if (grid > n_streaks) grid = n_streaks;
     k_raster<<<grid, RAS_THREADS, smem, st>>>(b, t, cam, n_streaks);
     return cudaGetLastError();
