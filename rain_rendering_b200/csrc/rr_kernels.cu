@@ -1107,11 +1107,13 @@ cudaError_t rr_launch_blur(const rr_frame_bufs &b, int n_streaks, int n_sm, cuda
 // ------------------------------------------------------------------------------------------
 struct comp_entry { int bx0, by0, bw, bh; long long a_off; double kb, kg, kr, tau_one, c_scale; };
 
+#define COMP_THREADS (RR_TILE_W * RR_TILE_H)
+#define COMP_WARPS (COMP_THREADS / 32)
 __global__ void __launch_bounds__(RR_TILE_W * RR_TILE_H) k_composite(rr_frame_bufs b, rr_cam_dev cam, int tiles_x, int tiles_y) {
-    __shared__ comp_entry list[256];
+    __shared__ comp_entry list[COMP_THREADS];
     __shared__ int s_count;
-    __shared__ int warp_cnt[8];
-    __shared__ double red[8];
+    __shared__ int warp_cnt[COMP_WARPS];
+    __shared__ double red[COMP_WARPS];
     const int f = blockIdx.z;
     const int W = cam.W, H = cam.H;
     const int tx0 = blockIdx.x * RR_TILE_W, ty0 = blockIdx.y * RR_TILE_H;
@@ -1127,7 +1129,7 @@ __global__ void __launch_bounds__(RR_TILE_W * RR_TILE_H) k_composite(rr_frame_bu
     }
     const int s0 = b.offsets[f], s1 = b.offsets[f + 1];
     const double exposure = cam.exposure_blend;
-    for (int base = s0; base < s1; base += 256) {
+    for (int base = s0; base < s1; base += COMP_THREADS) {
         int s = base + tid;
         bool hit = false;
         const rr_plan *pp = b.plans + (s < s1 ? s : s0);
@@ -1150,7 +1152,7 @@ __global__ void __launch_bounds__(RR_TILE_W * RR_TILE_H) k_composite(rr_frame_bu
             e.kb = pp->kb; e.kg = pp->kg; e.kr = pp->kr; e.tau_one = pp->a_scale; e.c_scale = pp->c_scale;
             list[slot] = e;
         }
-        if (tid == 0) { int c = 0; for (int k = 0; k < 8; k++) c += warp_cnt[k]; s_count = c; }
+        if (tid == 0) { int c = 0; for (int k = 0; k < COMP_WARPS; k++) c += warp_cnt[k]; s_count = c; }
         __syncthreads();
         int cnt = s_count;
         if (inside) {
@@ -1185,7 +1187,7 @@ __global__ void __launch_bounds__(RR_TILE_W * RR_TILE_H) k_composite(rr_frame_bu
     __syncthreads();
     if (tid == 0) {
         double t = 0;
-        for (int k = 0; k < 8; k++) t += red[k];
+        for (int k = 0; k < COMP_WARPS; k++) t += red[k];
         b.tile_sum[(size_t)f * tiles_x * tiles_y + (size_t)blockIdx.y * tiles_x + blockIdx.x] = t;
     }
 }

@@ -55,10 +55,16 @@ struct rr_fog_consts {
 };
 
 #define RR_RASTER_CHUNK 128
-#define RR_BLUR_CHUNK 1024       // elements per work-list chunk (4 per thread)
-#define RR_BLUR_THREADS 256
+#ifndef RR_BLUR_CHUNK
+#define RR_BLUR_CHUNK 512        // elements per work-list chunk, 4 per thread (sweep r01h: 1024/256 thr 0.58 ms, 512/128 thr 0.41 ms)
+#endif
+#ifndef RR_BLUR_THREADS
+#define RR_BLUR_THREADS 128
+#endif
 #define RR_TILE_W 32
+#ifndef RR_TILE_H
 #define RR_TILE_H 8
+#endif
 
 cudaError_t rr_upload_constants();
 // init-time tables
