@@ -33,6 +33,64 @@ RR_HD int rr_clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi :
 RR_HD double rr_mind(double a, double b) { return a < b ? a : b; }
 RR_HD double rr_maxd(double a, double b) { return a > b ? a : b; }
 
+// ---------------------------------------------------------------------------------------
+// Correctly rounded float64 division through a correctly rounded reciprocal (Markstein):
+// q0 = n * rd, then one residual correction with two fused multiply-adds.  With rd = RN(1/d) and
+// a faithful q0 the result equals RN(n / d); it is used only where tests/test_cvmath_host.py
+// proves it EXHAUSTIVELY over the whole input domain: the environment-map xyY conversion (all
+// 2^24 colours), where it replaces the five IEEE divisions per pixel (each a ~40-instruction
+// sequence on the GPU).
+// ---------------------------------------------------------------------------------------
+RR_HD double rr_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return fma(a, b, c);
+#endif
+}
+RR_HD double rr_rcp(double d) {      // RN(1 / d)
+#if defined(__CUDA_ARCH__)
+    return __drcp_rn(d);
+#else
+    return 1.0 / d;
+#endif
+}
+RR_HD double rr_div_rcp(double n, double d, double rd) {
+    double q = n * rd;
+    double r = rr_fma(-q, d, n);
+    return rr_fma(r, rd, q);
+}
+
+// uint8 / 255.0 (the reference's image normalisation, common/generator.py:352) without the division;
+// equal to the IEEE quotient for all 256 inputs (tests/test_cvmath_host.py).
+RR_HD double rr_u8_unit(uint8_t v) { return rr_div_rcp((double)v, 255.0, 1.0 / 255.0); }
+
+// RGB -> xyY of one environment-map pixel (reference common/my_utils.py:55-68, row vector x M, then
+// NaN -> 0 for black, common/generator.py:408).  bb, gg, rr are the uint8 values / 255.0.
+// rr_env_xyY_div is the literal form (IEEE divisions), rr_env_xyY the division-free form the kernel runs.
+RR_HD void rr_env_xyY_div(double bb, double gg, double rr, double *x, double *y, double *Y) {
+    double X = ((rr * 0.49000 + gg * 0.17697) + bb * 0.00000) / 0.17697;
+    double Yv = ((rr * 0.31000 + gg * 0.81240) + bb * 0.01000) / 0.17697;
+    double Z = ((rr * 0.20000 + gg * 0.01063) + bb * 0.99000) / 0.17697;
+    double S = (X + Yv) + Z;
+    double xv = X / S, yv = Yv / S;
+    if (!(xv == xv)) xv = 0;
+    if (!(yv == yv)) yv = 0;
+    *x = xv; *y = yv; *Y = Yv;
+}
+RR_HD void rr_env_xyY(double bb, double gg, double rr, double *x, double *y, double *Y) {
+    const double D = 0.17697, RD = 1.0 / 0.17697;      // RN(1/D), folded by the compiler
+    double X = rr_div_rcp((rr * 0.49000 + gg * 0.17697) + bb * 0.00000, D, RD);
+    double Yv = rr_div_rcp((rr * 0.31000 + gg * 0.81240) + bb * 0.01000, D, RD);
+    double Z = rr_div_rcp((rr * 0.20000 + gg * 0.01063) + bb * 0.99000, D, RD);
+    double S = (X + Yv) + Z;
+    double rs = rr_rcp(S);
+    double xv = rr_div_rcp(X, S, rs), yv = rr_div_rcp(Yv, S, rs);
+    if (!(xv == xv)) xv = 0;                             // black pixel: 0 * inf = NaN, like 0 / 0
+    if (!(yv == yv)) yv = 0;
+    *x = xv; *y = yv; *Y = Yv;
+}
+
 // texture fetch: streak textures are uint8 gray; the reference divides by 255.0
 // (common/bad_weather.py:252) before every resampling call.
 RR_HD double rr_tex(const uint8_t *tex, int tw, int x, int y) { return (double)tex[y * tw + x] / 255.0; }
@@ -240,6 +298,37 @@ RR_HD double rr_warp_affine_linear(const uint8_t *tex, int tw, int th, const dou
     double v2 = (x0ok && y1ok) ? (double)tex[(sy + 1) * tw + sx] / 255.0 : 0.0;
     double v3 = (x1ok && y1ok) ? (double)tex[(sy + 1) * tw + sx + 1] / 255.0 : 0.0;
     return v0 * w0 + v1 * w1 + v2 * w2 + v3 * w3;
+}
+
+// Conservative column range of one row of the rotated canvas outside of which every bilinear tap falls
+// outside the texture (the sample is then exactly the border constant 0).  The fixed-point source column of
+// canvas column c is (B + round(a1024 * c)) >> 10 with a1024 = M * 1024 (see rr_warp_affine_linear); it can
+// touch the texture only when lo <= B + round(a1024 * c) <= hi with lo = -1024, hi = size * 1024 - 1.
+// round() moves the value by at most 0.5, the computed quotient is widened by one column on both sides, so
+// the returned inclusive range [*cmin, *cmax] is a superset of the touching columns (checked against the
+// sampling predicate itself by tests/test_cvmath_host.py).
+RR_HD void rr_canvas_axis_range(double a1024, int B, int size, int *cmin, int *cmax) {
+    const double lo = -1024.0, hi = (double)size * 1024.0 - 1.0;
+    if (a1024 >= 1.0) {
+        *cmin = (int)floor((lo - B - 0.5) / a1024) - 1;
+        *cmax = (int)floor((hi - B + 0.5) / a1024) + 1;
+    } else if (a1024 <= -1.0) {
+        *cmin = (int)floor((hi - B + 0.5) / a1024) - 1;
+        *cmax = (int)floor((lo - B - 0.5) / a1024) + 1;
+    } else {
+        *cmin = -0x3fffffff; *cmax = 0x3fffffff;     // (nearly) constant along the row: no restriction
+    }
+}
+// -> first column and number of columns of row (XR, YR) that must be sampled; the rest of the row is 0
+RR_HD void rr_canvas_row_span(const double *M, int XR, int YR, int nW, int tw, int th, int *c0, int *cn) {
+    int ax, bx, ay, by;
+    rr_canvas_axis_range(M[0] * 1024.0, XR, tw, &ax, &bx);
+    rr_canvas_axis_range(M[3] * 1024.0, YR, th, &ay, &by);
+    int a = ax > ay ? ax : ay, b = bx < by ? bx : by;
+    if (a < 0) a = 0;
+    if (b > nW - 1) b = nW - 1;
+    *c0 = a;
+    *cn = b >= a ? b - a + 1 : 0;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -8,7 +8,7 @@
 // constants (uploaded once by rr_upload_constants)
 // ------------------------------------------------------------------------------------------
 __constant__ double c_k64[25];      // cv2.getGaussianKernel(25, 25, CV_64F)   (add_attenuation.py:79-80)
-__constant__ float c_k32[25];       // cv2.getGaussianKernel(25, 25, CV_32F)
+__constant__ double c_k32d[25];     // cv2.getGaussianKernel(25, 25, CV_32F), the float32 values widened to float64
 __constant__ int c_k15[15];         // OpenCV fixed-point (8 fractional bits) kernel of GaussianBlur((15,15), 0) on uint8
 __device__ float d_cubic[RR_INTER_TAB * 4];   // divergent per-thread indexing: global/L1, not the constant bank
 
@@ -36,7 +36,9 @@ cudaError_t rr_upload_constants() {
     rr_build_cubic_tab(cub);
     cudaError_t e;
     if ((e = cudaMemcpyToSymbol(c_k64, k64, sizeof(k64))) != cudaSuccess) return e;
-    if ((e = cudaMemcpyToSymbol(c_k32, k32, sizeof(k32))) != cudaSuccess) return e;
+    double k32d[25];
+    for (int i = 0; i < 25; i++) k32d[i] = (double)k32[i];
+    if ((e = cudaMemcpyToSymbol(c_k32d, k32d, sizeof(k32d))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(c_k15, k15, sizeof(k15))) != cudaSuccess) return e;
     if ((e = cudaMemcpyToSymbol(d_cubic, cub, sizeof(cub))) != cudaSuccess) return e;
     return cudaSuccess;
@@ -303,17 +305,29 @@ cudaError_t rr_launch_stats(const rr_frame_bufs &b, int F, int W, int H, int ren
 // held in registers; every output still accumulates its 25 products in the reference order.
 template <int STRIDE_IN>
 __device__ __forceinline__ void fog_taps_f32(const float *in, double acc[4]) {
-    // 4 outputs along the direction of STRIDE_IN, exact float32 products in float64, ascending taps
+    // 4 outputs along the direction of STRIDE_IN, exact float32 products in float64, ascending taps.
+    // The product of two float32 values is exact in float64, so fma(k, v, a) == a + k * v bit for bit:
+    // one instruction per tap instead of two.
     double v[28];
 #pragma unroll
     for (int i = 0; i < 28; i++) v[i] = (double)in[i * STRIDE_IN];
 #pragma unroll
     for (int o = 0; o < 4; o++) {
-        double a = (double)c_k32[0] * v[o];
+        double a = c_k32d[0] * v[o];
 #pragma unroll
-        for (int t = 1; t < 25; t++) a += (double)c_k32[t] * v[o + t];
+        for (int t = 1; t < 25; t++) a = __fma_rn(c_k32d[t], v[o + t], a);
         acc[o] = a;
     }
+}
+
+// extinction f_ext = float32 exp(-beta * depth / 1000), once per pixel (add_attenuation.py:43-48); k_fog's
+// overlapping tiles read it back (2.4 haloed reads per pixel) instead of re-evaluating the exponential
+__global__ void __launch_bounds__(256) k_fext(const float *depth, float *fext, float neg_beta32, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float d = __fdiv_rn(depth[i], 1000.f);                                  // add_attenuation.py:48 (float32)
+    float xx = __fmul_rn(neg_beta32, d);
+    fext[i] = (float)exp((double)xx);                                       // correctly rounded float32 exp ("canonical")
 }
 
 __global__ void __launch_bounds__(256, 2) k_fog(rr_frame_bufs b, rr_fog_consts fc, int W, int H) {
@@ -325,17 +339,13 @@ __global__ void __launch_bounds__(256, 2) k_fog(rr_frame_bufs b, rr_fog_consts f
     const int f = blockIdx.z;
     const int x0 = blockIdx.x * FOG_TX, y0 = blockIdx.y * FOG_TY;
     const int tid = threadIdx.x;
-    const float *depth = b.depth + (size_t)f * W * H;
+    const float *fext = b.fext + (size_t)f * W * H;
     const uint8_t *bgr = b.bgr + (size_t)f * W * H * 3;
     for (int i = tid; i < FOG_EH * FOG_EW; i += 256) {
         int ey = i / FOG_EW, ex = i - ey * FOG_EW;
         int gy = r101(y0 + ey - FOG_R, H), gx = r101(x0 + ex - FOG_R, W);
         float v = 0.f;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
-            float d = __fdiv_rn(depth[(size_t)gy * W + gx], 1000.f);       // add_attenuation.py:48 (float32)
-            float xx = __fmul_rn(fc.neg_beta32, d);
-            v = (float)exp((double)xx);                                     // correctly rounded float32 exp ("canonical")
-        }
+        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = fext[(size_t)gy * W + gx];    // k_fext
         E[i] = v;
     }
     __syncthreads();
@@ -418,7 +428,7 @@ __global__ void __launch_bounds__(256, 2) k_fog(rr_frame_bufs b, rr_fog_consts f
                 if (gy < H && gx < W) {
                     size_t pix = (size_t)gy * W + gx;
                     for (int cc = linear ? 0 : c; cc < (linear ? 3 : c + 1); cc++) {
-                        double I = b.bgf ? b.bgf[((size_t)f * 3 + cc) * W * H + pix] : (double)bgr[pix * 3 + cc] / 255.0;   // generator.py:352-355
+                        double I = b.bgf ? b.bgf[((size_t)f * 3 + cc) * W * H + pix] : rr_u8_unit(bgr[pix * 3 + cc]);   // generator.py:352-355
                         double lin_in = linear ? Acs[cc] * acc : acc;
                         double l = I * (double)fb[o] + lin_in;               // :85
                         l = l < 0 ? 0 : (l > 1 ? 1 : l);
@@ -433,6 +443,10 @@ __global__ void __launch_bounds__(256, 2) k_fog(rr_frame_bufs b, rr_fog_consts f
 
 cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, cudaStream_t st) {
     size_t smem = sizeof(float) * (FOG_EH * FOG_EW + FOG_EH * FOG_TX) + sizeof(double) * (FOG_EH * FOG_EW + FOG_EH * FOG_TX);
+    {
+        size_t n = (size_t)F * W * H;
+        k_fext<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.depth, b.fext, fc.neg_beta32, n);
+    }
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_fog, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -533,59 +547,109 @@ __global__ void __launch_bounds__(256) k_env_map(const uint8_t *bg8, const int32
 // one block per (row, frame): xyY, solid-angle weighting, row prefix sums  (generator.py:407-408,
 // bad_weather.py:393-395).  pref is interleaved: [F][H][W_env+1][4] = prefix of (w*x, w*y, w*Y, w), so one
 // 32-byte sector serves a span end point in k_setup.
-__global__ void __launch_bounds__(256) k_env_prefix(const uint8_t *env8, const double *omega, double *pref, double *rowtot,
-                                                    int H, int W_env) {
-    // The row is scanned in tiles of 256 consecutive pixels (all global accesses coalesced); inside a tile a
-    // warp-shuffle scan plus the 8 warp totals, between tiles a running carry.  Fixed tree: deterministic.
+//
+// The row is cut into tiles of EP_TILE pixels.  Every thread owns EP_PER CONSECUTIVE pixels: it converts them
+// (division-free xyY, rr_cvmath.h), keeps the running sums in registers (a serial prefix costs one add per
+// value instead of a five-step shuffle scan) and parks its local exclusive prefixes in shared memory; one
+// shuffle scan over the thread totals and the warp totals gives every thread its offset; the tile then
+// leaves shared memory as fully coalesced 16-byte stores.  The row bytes arrive the same way (16-byte
+// coalesced loads into shared memory, then each thread unpacks its 24 bytes).  Fixed tree: deterministic.
+#define EP_THREADS 128
+#define EP_PER 8
+#define EP_TILE (EP_THREADS * EP_PER)
+#define EP_WARPS (EP_THREADS / 32)
+// shared staging of the tile's prefixes: 32 bytes per pixel plus 16 bytes after every 8 pixels, so that the
+// per-thread 16-byte stores (stride 272 bytes between lanes) and the per-warp linear reads are conflict free
+#define EP_STAGE_BYTES (EP_TILE * 32 + EP_THREADS * 16)
+__global__ void __launch_bounds__(EP_THREADS) k_env_prefix(const uint8_t *env8, const double *omega, double *pref, double *rowtot,
+                                                           int H, int W_env) {
     __shared__ double lut[256];
-    __shared__ double wtot[4][8];
-    lut[threadIdx.x] = (double)threadIdx.x / 255.0;
+    __shared__ __align__(16) unsigned char s_bytes[EP_TILE * 3 + 32];
+    __shared__ __align__(16) unsigned char s_stage[EP_STAGE_BYTES];
+    __shared__ __align__(16) double s_toff[EP_THREADS][4];
+    __shared__ double s_wtot[EP_WARPS][4];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < 256; i += EP_THREADS) lut[i] = (double)i / 255.0;
     const int r = blockIdx.x, f = blockIdx.y;
     const uint8_t *row = env8 + ((size_t)f * H + r) * W_env * 3;
     const double *om = omega + (size_t)r * W_env;
-    double4 *p = (double4 *)pref + ((size_t)f * H + r) * (W_env + 1);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double2 *p2 = (double2 *)pref + ((size_t)f * H + r) * (W_env + 1) * 2;
     double cx = 0, cy = 0, cY = 0, cw = 0;          // carry: prefix of everything left of the tile
-    __syncthreads();
-    for (int c0 = 0; c0 < W_env; c0 += 256) {
-        const int c = c0 + threadIdx.x;
-        double ax_ = 0, ay_ = 0, aY_ = 0, w = 0;
-        if (c < W_env) {
-            double bb = lut[row[c * 3]], gg = lut[row[c * 3 + 1]], rr = lut[row[c * 3 + 2]];
-            double X = ((rr * 0.49000 + gg * 0.17697) + bb * 0.00000) / 0.17697;      // my_utils.py:56-59 (row vector x M)
-            double Y = ((rr * 0.31000 + gg * 0.81240) + bb * 0.01000) / 0.17697;
-            double Z = ((rr * 0.20000 + gg * 0.01063) + bb * 0.99000) / 0.17697;
-            double S = (X + Y) + Z;
-            double x = X / S, y = Y / S;
-            if (!(x == x)) x = 0;                                                      // generator.py:408
-            if (!(y == y)) y = 0;
-            w = om[c];
-            ax_ = x * w; ay_ = y * w; aY_ = Y * w;
+    for (int c0 = 0; c0 < W_env; c0 += EP_TILE) {
+        const int n = (W_env - c0) < EP_TILE ? (W_env - c0) : EP_TILE;
+        // ---- row bytes -> shared memory, 16 bytes per load (the buffers carry 256 bytes of slack) ----
+        const uint8_t *gsrc = row + (size_t)c0 * 3;
+        const int shift = (int)((size_t)gsrc & 15);
+        const uint4 *gal = (const uint4 *)(gsrc - shift);
+        const int nvec = (shift + n * 3 + 15) >> 4;
+        __syncthreads();                            // previous tile fully written out (s_stage, s_toff, s_bytes), lut ready
+        for (int i = tid; i < nvec; i += EP_THREADS) ((uint4 *)s_bytes)[i] = gal[i];
+        __syncthreads();
+        // ---- this thread's EP_PER consecutive pixels ----
+        const int px0 = tid * EP_PER;
+        unsigned wds[EP_PER * 3 / 4 + 1];
+        {
+            const int bo = shift + px0 * 3;         // (bo & 3) == (shift & 3) for every thread
+            const unsigned *sw = (const unsigned *)s_bytes + (bo >> 2);
+            const int sh = (bo & 3) * 8;
+            unsigned raw[EP_PER * 3 / 4 + 1];
+#pragma unroll
+            for (int k = 0; k < EP_PER * 3 / 4 + 1; k++) raw[k] = sw[k];
+#pragma unroll
+            for (int k = 0; k < EP_PER * 3 / 4; k++) wds[k] = __funnelshift_r(raw[k], raw[k + 1], sh);
         }
-        double ix = ax_, iy = ay_, iY = aY_, iw = w;
+        double sx = 0, sy = 0, sY = 0, sw_ = 0;
+        unsigned char *st = s_stage + (size_t)tid * (EP_PER * 32 + 16);
+#pragma unroll
+        for (int k = 0; k < EP_PER; k++) {
+            ((double2 *)(st + k * 32))[0] = make_double2(sx, sy);
+            ((double2 *)(st + k * 32))[1] = make_double2(sY, sw_);
+            const int c = c0 + px0 + k;
+            if (px0 + k < n) {
+                const int b0 = 3 * k, b1 = 3 * k + 1, b2 = 3 * k + 2;
+                const double bb = lut[(wds[b0 >> 2] >> ((b0 & 3) * 8)) & 255u];
+                const double gg = lut[(wds[b1 >> 2] >> ((b1 & 3) * 8)) & 255u];
+                const double rr = lut[(wds[b2 >> 2] >> ((b2 & 3) * 8)) & 255u];
+                double x, y, Y;
+                rr_env_xyY(bb, gg, rr, &x, &y, &Y);                 // my_utils.py:56-68, generator.py:408
+                const double w = om[c];
+                sx += x * w; sy += y * w; sY += Y * w; sw_ += w;
+            }
+        }
+        // ---- exclusive scan of the thread totals: shuffle scan inside the warp, then the warp totals ----
+        double ix = sx, iy = sy, iY = sY, iw = sw_;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             double ux = __shfl_up_sync(0xffffffffu, ix, o), uy = __shfl_up_sync(0xffffffffu, iy, o);
             double uY = __shfl_up_sync(0xffffffffu, iY, o), uw = __shfl_up_sync(0xffffffffu, iw, o);
             if (lane >= o) { ix += ux; iy += uy; iY += uY; iw += uw; }
         }
-        if (lane == 31) { wtot[0][warp] = ix; wtot[1][warp] = iy; wtot[2][warp] = iY; wtot[3][warp] = iw; }
+        if (lane == 31) { s_wtot[warp][0] = ix; s_wtot[warp][1] = iy; s_wtot[warp][2] = iY; s_wtot[warp][3] = iw; }
         double ex = __shfl_up_sync(0xffffffffu, ix, 1), ey = __shfl_up_sync(0xffffffffu, iy, 1);
         double eY = __shfl_up_sync(0xffffffffu, iY, 1), ew = __shfl_up_sync(0xffffffffu, iw, 1);
         if (lane == 0) { ex = ey = eY = ew = 0; }
         __syncthreads();
         double ox = cx, oy = cy, oY = cY, ow = cw, tx_ = cx, ty_ = cy, tY_ = cY, tw_ = cw;
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
+        for (int k = 0; k < EP_WARPS; k++) {
             if (k == warp) { ox = tx_; oy = ty_; oY = tY_; ow = tw_; }
-            tx_ += wtot[0][k]; ty_ += wtot[1][k]; tY_ += wtot[2][k]; tw_ += wtot[3][k];
+            tx_ += s_wtot[k][0]; ty_ += s_wtot[k][1]; tY_ += s_wtot[k][2]; tw_ += s_wtot[k][3];
         }
-        if (c < W_env) p[c] = make_double4(ox + ex, oy + ey, oY + eY, ow + ew);
+        s_toff[tid][0] = ox + ex; s_toff[tid][1] = oy + ey; s_toff[tid][2] = oY + eY; s_toff[tid][3] = ow + ew;
         cx = tx_; cy = ty_; cY = tY_; cw = tw_;
         __syncthreads();
+        // ---- coalesced write-out: half-entries (16 bytes) in linear order ----
+        double2 *dst = p2 + (size_t)c0 * 2;
+        for (int h = tid; h < 2 * n; h += EP_THREADS) {
+            const int px = h >> 1, half = h & 1;
+            const double2 v = *(const double2 *)(s_stage + (size_t)px * 32 + (size_t)(px >> 3) * 16 + half * 16);
+            const double2 o = *(const double2 *)&s_toff[px >> 3][half * 2];
+            dst[h] = make_double2(o.x + v.x, o.y + v.y);
+        }
     }
-    if (threadIdx.x == 0) {
-        p[W_env] = make_double4(cx, cy, cY, cw);
+    if (tid == 0) {
+        p2[(size_t)W_env * 2] = make_double2(cx, cy);
+        p2[(size_t)W_env * 2 + 1] = make_double2(cY, cw);
         rowtot[(size_t)f * H + r] = cY;
     }
 }
@@ -593,7 +657,7 @@ __global__ void __launch_bounds__(256) k_env_prefix(const uint8_t *env8, const d
 static cudaError_t launch_env_prefix(const uint8_t *env8, const double *omega, double *pref, double *rowtot, int F, int H, int W_env,
                                      cudaStream_t st) {
     dim3 g3(H, F);
-    k_env_prefix<<<g3, 256, 0, st>>>(env8, omega, pref, rowtot, H, W_env);
+    k_env_prefix<<<g3, EP_THREADS, 0, st>>>(env8, omega, pref, rowtot, H, W_env);
     return cudaGetLastError();
 }
 
@@ -826,7 +890,7 @@ __device__ __forceinline__ int find_streak(const long long *scan, int n, int fie
 #define RAS_MAXW 512          // widest rotated canvas handled by the staged path
 #define RAS_TXN 128           // widest / tallest patch with cached computeResizeAreaTab spans
 #define RAS_MAXD 1024         // patch pixels with accumulators resident in shared memory
-#define RAS_RBMAX 256
+#define RAS_RBMAX 128         // rows per band (RAS_CAP / canvas width; canvases are at least 32 wide)
 
 __device__ __forceinline__ double ras_sample(const uint8_t *tex, int tw, int th, const double *lut, int X, int Y) {
     // rr_warp_affine_linear with the fixed-point coordinates already formed.  One code path for interior and
@@ -863,6 +927,8 @@ __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs 
     rr_area_span *TY = TX + RAS_TXN;                     // [RAS_TXN]
     int *adx = (int *)(TY + RAS_TXN), *bdx = adx + RAS_MAXW;   // [RAS_MAXW] each
     int *XR = bdx + RAS_MAXW, *YR = XR + RAS_RBMAX;            // [RAS_RBMAX] each
+    int *CL = YR + RAS_RBMAX, *CN = CL + RAS_RBMAX;            // [RAS_RBMAX] each: sampled column span of a band row
+    __shared__ int s_wmax;                                     // widest span of the band
     double *ACC = BUF;
     __shared__ rr_plan sp;
     const int tid = threadIdx.x;
@@ -871,6 +937,7 @@ __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs 
     for (int s = blockIdx.x; s < n; s += gridDim.x) {
         __syncthreads();
         if (tid < sizeof(rr_plan) / 4) ((int *)&sp)[tid] = ((const int *)&b.plans[s])[tid];
+        if (tid == 0) s_wmax = 0;
         __syncthreads();
         const rr_plan &p = sp;
         long long g, vv, aa; int vx0_, vw_;
@@ -912,21 +979,44 @@ __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs 
             for (int r = tid; r < rb; r += RAS_THREADS) {
                 int sy = s0 + r;
                 int yy = p.flip ? (nH - 1 - sy) : sy;
-                XR[r] = rr_round((p.M[1] * yy + p.M[2]) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
-                YR[r] = rr_round((p.M[4] * yy + p.M[5]) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
+                int xr = rr_round((p.M[1] * yy + p.M[2]) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
+                int yr = rr_round((p.M[4] * yy + p.M[5]) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
+                XR[r] = xr; YR[r] = yr;
+                // the rotated texture covers a slanted band of the canvas: outside [cl, cl + cn) every tap of the
+                // row misses the texture and the sample is exactly 0 (rr_canvas_row_span is a superset)
+                int cl, cn;
+                rr_canvas_row_span(p.M, xr, yr, nW, tw, th, &cl, &cn);
+                CL[r] = cl; CN[r] = cn;
+                if (cn > 0) atomicMax(&s_wmax, cn);
             }
             __syncthreads();
+            const int wmax = s_wmax;
             {
+                // zeros outside the spans ...
                 int r = r_first, c = c_first;                       // (row, column) of flattened index tid
                 for (int i = tid; i < rb * nW; i += RAS_THREADS) {
-                    int X = (XR[r] + adx[c]) >> (10 - RR_INTER_BITS);
-                    int Y = (YR[r] + bdx[c]) >> (10 - RR_INTER_BITS);
-                    C[i] = ras_sample(tex, tw, th, lut, X, Y);
+                    if ((unsigned)(c - CL[r]) >= (unsigned)CN[r]) C[i] = 0.0;
                     c += step_c; r += step_r;                       // advance by RAS_THREADS without a division
                     if (c >= nW) { c -= nW; r++; }
                 }
             }
+            if (wmax > 0) {
+                // ... samples inside: work items (row, k < wmax), so that the lanes of a warp are (nearly) all inside
+                const int st_r = RAS_THREADS / wmax, st_k = RAS_THREADS - st_r * wmax;
+                int r = tid / wmax, k = tid - r * wmax;
+                for (int i = tid; i < rb * wmax; i += RAS_THREADS) {
+                    if (k < CN[r]) {
+                        const int c = CL[r] + k;
+                        int X = (XR[r] + adx[c]) >> (10 - RR_INTER_BITS);
+                        int Y = (YR[r] + bdx[c]) >> (10 - RR_INTER_BITS);
+                        C[r * nW + c] = ras_sample(tex, tw, th, lut, X, Y);
+                    }
+                    k += st_k; r += st_r;
+                    if (k >= wmax) { k -= wmax; r++; }
+                }
+            }
             __syncthreads();
+            if (tid == 0) s_wmax = 0;                               // next band's atomicMax comes after its first barrier
             if (!fast) {
                 // cv::resizeArea_: buf[dx] = sum_k S[sx_k] * alpha_k (left to right) for every source row of the band ...
                 for (int i = tid; i < rb * pw; i += RAS_THREADS) {
@@ -990,7 +1080,7 @@ cudaError_t rr_launch_raster(const rr_frame_bufs &b, const rr_static_tabs &t, co
                              cudaStream_t st) {
     if (n_streaks == 0) return cudaSuccess;
     const size_t smem = sizeof(double) * (2 * RAS_CAP + RAS_MAXD + 256) + sizeof(rr_area_span) * 2 * RAS_TXN +
-                        sizeof(int) * (2 * RAS_MAXW + 2 * RAS_RBMAX);
+                        sizeof(int) * (2 * RAS_MAXW + 4 * RAS_RBMAX);
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -16,6 +16,7 @@ struct rr_frame_bufs {
     unsigned long long *chan_sum;  // [F][4]  sum of uint8 per channel (B,G,R), [3] unused
     double *rainy;             // [F][3][H][W] planar BGR float64
     uint8_t *bg8;              // [F][H][W][3] floor(rainy*255)
+    float *fext;               // [F][H][W] extinction exp(-beta d), written by k_fext for k_fog
     float *fblur;              // [F][H][W] blurred extinction (debug / stage test)
     uint8_t *env8;             // [F][H][W_env][3] final environment map
     double *pref;              // [F][H][W_env+1][4] row prefix sums of (omega*x, omega*y, omega*Y, omega), interleaved

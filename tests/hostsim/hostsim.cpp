@@ -76,3 +76,47 @@ int hs_sizeof_plan() { return (int)sizeof(rr_plan); }
 int hs_sizeof_rec() { return (int)sizeof(rr_streak_rec); }
 int hs_sizeof_cam_dev() { return (int)sizeof(rr_cam_dev); }
 }
+
+// exhaustive: division-free xyY (the form k_env_prefix runs) against the literal IEEE divisions, all 2^24 colours
+extern "C" long hs_env_xyY_mismatches() {
+    long bad = 0;
+    for (int b = 0; b < 256; b++)
+        for (int g = 0; g < 256; g++)
+            for (int r = 0; r < 256; r++) {
+                double bb = b / 255.0, gg = g / 255.0, rr = r / 255.0, x0, y0, Y0, x1, y1, Y1;
+                rr_env_xyY_div(bb, gg, rr, &x0, &y0, &Y0);
+                rr_env_xyY(bb, gg, rr, &x1, &y1, &Y1);
+                bad += memcmp(&x0, &x1, 8) != 0 || memcmp(&y0, &y1, 8) != 0 || memcmp(&Y0, &Y1, 8) != 0;
+            }
+    return bad;
+}
+
+// Canvas row spans of k_raster (rr_canvas_row_span) against the sampling predicate of every canvas pixel:
+// returns the number of pixels outside the span whose bilinear footprint touches the texture (must be 0);
+// stats[0] += canvas pixels, stats[1] += pixels inside the spans, stats[2] += pixels that really touch.
+extern "C" long hs_canvas_span_violations(const rr_plan *p, int tw, long *stats) {
+    const int AB_SCALE = 1 << 10;
+    long bad = 0;
+    for (int sy = 0; sy < p->nH; sy++) {
+        int yy = p->flip ? (p->nH - 1 - sy) : sy;
+        int XR = rr_round((p->M[1] * yy + p->M[2]) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
+        int YR = rr_round((p->M[4] * yy + p->M[5]) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
+        int c0, cn;
+        rr_canvas_row_span(p->M, XR, YR, p->nW, tw, p->tex_h, &c0, &cn);
+        stats[0] += p->nW; stats[1] += cn;
+        for (int c = 0; c < p->nW; c++) {
+            int sx = (XR + rr_round(p->M[0] * c * AB_SCALE)) >> 10, syy = (YR + rr_round(p->M[3] * c * AB_SCALE)) >> 10;
+            bool touch = sx >= -1 && sx <= tw - 1 && syy >= -1 && syy <= p->tex_h - 1;
+            stats[2] += touch;
+            if (touch && (c < c0 || c >= c0 + cn)) bad++;
+        }
+    }
+    return bad;
+}
+
+extern "C" long hs_u8_unit_mismatches() {
+    long bad = 0;
+    for (int v = 0; v < 256; v++) { double a = (double)v / 255.0, b = rr_u8_unit((uint8_t)v); bad += memcmp(&a, &b, 8) != 0; }
+    return bad;
+}
+extern "C" void hs_env_xyY(double bb, double gg, double rr, double *out3) { rr_env_xyY_div(bb, gg, rr, out3, out3 + 1, out3 + 2); }

@@ -107,3 +107,47 @@ def test_scipy_gaussian_weights(hs):
         imp[r.value] = 1.0
         ref = gaussian_filter1d(imp, sigma, mode="constant")
         assert np.abs(w[:2 * r.value + 1] - ref).max() < 1e-15
+
+
+def test_division_free_xyY_is_bit_exact_for_every_colour(hs):
+    """k_env_prefix converts BGR -> xyY with reciprocal + FMA corrections instead of five IEEE divisions;
+    the two forms must agree bit for bit on the whole input domain (all 2^24 uint8 colours, NaN -> 0 included)."""
+    hs.hs_env_xyY_mismatches.restype = C.c_long
+    assert hs.hs_env_xyY_mismatches() == 0
+    hs.hs_u8_unit_mismatches.restype = C.c_long
+    assert hs.hs_u8_unit_mismatches() == 0
+    # and the literal form is the reference's arithmetic (common/my_utils.py:55-68)
+    rng = np.random.RandomState(5)
+    bgr = rng.randint(0, 256, (500, 3)).astype(np.uint8)
+    bgr[:3] = [[0, 0, 0], [255, 255, 255], [0, 0, 1]]
+    out = np.zeros(3)
+    for b, g, r in bgr:
+        hs.hs_env_xyY(C.c_double(b / 255.0), C.c_double(g / 255.0), C.c_double(r / 255.0), _lib.ptr(out))
+        with np.errstate(all="ignore"):
+            ref = np.nan_to_num(ro.rgb_to_xyY(np.array([[[r / 255.0, g / 255.0, b / 255.0]]]))[0, 0])
+        assert np.allclose(out, ref, rtol=1e-14, atol=0), (b, g, r)      # np.dot's BLAS order / FMA differs in the last bit
+
+
+@pytest.mark.parametrize("W,H,n_xml,noise", [(1242, 375, 700, 3.0), (640, 480, 2500, 0.0), (1242, 375, 900, 25.0)])
+def test_canvas_row_spans_cover_every_sample_that_touches_the_texture(hs, W, H, n_xml, noise):
+    """k_raster samples only the column span rr_canvas_row_span returns for a canvas row and writes zeros elsewhere:
+    no pixel outside a span may have a bilinear tap inside the texture."""
+    sc = Scenario(W, H, 1, n_xml, noise_scale=1.0 if noise else 0.0, noise_std=noise, seed=11)
+    cam = sc.cam
+    cd = CamDev(W, H, H, sc.tables.W_env, cam.focal_m, cam.f_number, cam.focus_plane, cam.pix_size, cam.radius, cam.fov_deg,
+                cam.opacity_attenuation, cam.exposure_ms / 1000., 32, 50)
+    recs, _ = sc.records()
+    hs.hs_canvas_span_violations.restype = C.c_long
+    plan = np.zeros(1, _lib.PLAN_DTYPE)
+    stats = np.zeros(3, np.int64)
+    n_checked = 0
+    for r in recs:
+        rr = np.array([r])
+        tex = np.ascontiguousarray(sc.db.textures[r["tex_idx"]])
+        hs.hs_patch(_lib.ptr(rr), C.byref(cd), _lib.ptr(tex), tex.shape[0], _lib.ptr(plan), None, 0)
+        if not plan[0]["valid"] or plan[0]["type"] == 0:
+            continue
+        assert hs.hs_canvas_span_violations(_lib.ptr(plan), 32, _lib.ptr(stats)) == 0, int(r["pid"])
+        n_checked += 1
+    assert n_checked > 100
+    assert stats[2] <= stats[1] <= stats[0] and stats[1] < 1.15 * stats[2] + 4 * n_checked * 400     # spans are tight, not just safe
