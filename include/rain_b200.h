@@ -198,6 +198,30 @@ int rr_host_free(void *ptr);
  * for non-Big streaks, normal(0, noise_std) * noise_scale (generator.py:136). */
 int rr_host_draw_randoms(uint32_t seed, int n, const uint8_t *types, const int32_t *buckets, double noise_std,
                          double noise_scale, uint8_t *tex_idx, double *noise_deg);
+/* Host logic (no GPU): native loader of the particle simulator's XML output -- replaces
+ * DBManager.load_streaks_from_xml (common/bad_weather.py:148-248).  The root's children are camera
+ * frames (<i id t d rs>), their children imaged streaks (<r pid wp1 wd1 wp2 wd2 ip1 iw1 ip2 iw2/>).
+ * Every streak becomes an rr_streak_rec exactly as the reference builds its Streak object (:200-236:
+ * /render_scale, y flip with the image height H, z negation, max_width, ratio, half-even rounding,
+ * length, type) with tex_idx = 0 and noise_deg = 0 (drawn per frame later); kept iff max_width >= 1 and
+ * length >= 1 (:238).  Streaks keep XML order; a repeated pid replaces the earlier entry in place and a
+ * repeated frame id the earlier frame (dict.update, :238,241).  Malformed files return RR_ERR_ARG with
+ * the reference's advice in rr_last_error() (:184-187). */
+typedef struct rr_xml_frame {   /* one <i> element, 32 bytes                                   */
+    int32_t id;              /* frame id (key of DBManager.streaks_simulator)                 */
+    int32_t exposure_t;      /* "t"                                                           */
+    int32_t start_d;         /* "d"                                                           */
+    int32_t streaks_count;   /* "rs": the simulator's own count (before the loader's filter)  */
+    int64_t first, count;    /* records [first, first + count) of the concatenated array      */
+} rr_xml_frame;
+typedef struct rr_xml_particles rr_xml_particles;
+int rr_host_load_particles_xml(const char *path, int render_scale, int W, int H, rr_xml_particles **out);
+int rr_host_particles_info(const rr_xml_particles *p, int32_t *n_frames, int64_t *n_records);
+int rr_host_particles_copy(const rr_xml_particles *p, rr_xml_frame *frames, rr_streak_rec *records);
+void rr_host_free_particles(rr_xml_particles *p);
+/* np.linalg.norm of n 2-vectors the way NumPy's BLAS evaluates it, sqrt(fma(y, y, x * x)): the loader's
+ * direction norm (bad_weather.py:229), shared with the Python-side record builder of the on-the-fly simulator. */
+void rr_host_norm2(int n, const double *x, const double *y, double *out);
 /* The simulator's force model evaluated on the host (CPU test-suite): terminal velocity solving
  * m g = F_drag(v), the drag at that speed and the drop mass. */
 void rr_host_sim_physics(double D_m, double *v_terminal, double *drag_at_vt, double *mass);

@@ -44,6 +44,10 @@ PLAN_DTYPE = np.dtype([
     ("c_scale", "<f8"), ("fov_x", "<f8"), ("fov_y", "<f8"), ("drop_Y", "<f8")])
 assert PLAN_DTYPE.itemsize == 280
 
+# rr_xml_frame
+XML_FRAME_DTYPE = np.dtype([("id", "<i4"), ("t", "<i4"), ("d", "<i4"), ("rs", "<i4"), ("first", "<i8"), ("count", "<i8")])
+assert XML_FRAME_DTYPE.itemsize == 32
+
 T_NAMES = ("h2d", "fog", "env", "setup", "raster", "blur", "composite", "epilogue", "d2h", "total")
 DBG = dict(fog=0, env=1, omega=2, plans=3, rainy=4, env_src=5, arena=6, fext=7)
 
@@ -90,11 +94,18 @@ def load() -> C.CDLL:
         "rr_host_alloc": [C.POINTER(vp), C.c_size_t],
         "rr_host_free": [vp],
         "rr_host_draw_randoms": [C.c_uint32, C.c_int, u8p, i32p, C.c_double, C.c_double, u8p, f64p],
+        "rr_host_load_particles_xml": [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)],
+        "rr_host_particles_info": [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64)],
+        "rr_host_particles_copy": [vp, vp, vp],
     }
     for name, args in protos.items():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_int
+    lib.rr_host_free_particles.argtypes = [vp]
+    lib.rr_host_free_particles.restype = None
+    lib.rr_host_norm2.argtypes = [C.c_int, f64p, f64p, f64p]
+    lib.rr_host_norm2.restype = None
     lib.rr_host_tables.argtypes = [f64p, f32p, i32p]
     lib.rr_host_tables.restype = None
     lib.rr_host_sim_physics.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]

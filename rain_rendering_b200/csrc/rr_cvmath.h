@@ -304,31 +304,33 @@ RR_HD double rr_warp_affine_linear(const uint8_t *tex, int tw, int th, const dou
 // outside the texture (the sample is then exactly the border constant 0).  The fixed-point source column of
 // canvas column c is (B + round(a1024 * c)) >> 10 with a1024 = M * 1024 (see rr_warp_affine_linear); it can
 // touch the texture only when lo <= B + round(a1024 * c) <= hi with lo = -1024, hi = size * 1024 - 1.
-// round() moves the value by at most 0.5, the computed quotient is widened by one column on both sides, so
-// the returned inclusive range [*cmin, *cmax] is a superset of the touching columns (checked against the
-// sampling predicate itself by tests/test_cvmath_host.py).
-RR_HD void rr_canvas_axis_range(double a1024, int B, int size, int *cmin, int *cmax) {
+// round() moves the value by at most 0.5 and the quotient (a multiplication by the reciprocal inv = 1 / a1024,
+// off by far less than one column) is widened by one column on both sides, so the returned inclusive range
+// [*cmin, *cmax] is a superset of the touching columns (checked against the sampling predicate itself by
+// tests/test_cvmath_host.py).
+RR_HD double rr_canvas_inv(double a1024) { return (a1024 >= 1.0 || a1024 <= -1.0) ? 1.0 / a1024 : 0.0; }
+RR_HD void rr_canvas_axis_range(double a1024, double inv, int B, int size, int *cmin, int *cmax) {
     const double lo = -1024.0, hi = (double)size * 1024.0 - 1.0;
     if (a1024 >= 1.0) {
-        *cmin = (int)floor((lo - B - 0.5) / a1024) - 1;
-        *cmax = (int)floor((hi - B + 0.5) / a1024) + 1;
+        *cmin = (int)floor((lo - B - 0.5) * inv) - 1;
+        *cmax = (int)floor((hi - B + 0.5) * inv) + 1;
     } else if (a1024 <= -1.0) {
-        *cmin = (int)floor((hi - B + 0.5) / a1024) - 1;
-        *cmax = (int)floor((lo - B - 0.5) / a1024) + 1;
+        *cmin = (int)floor((hi - B + 0.5) * inv) - 1;
+        *cmax = (int)floor((lo - B - 0.5) * inv) + 1;
     } else {
         *cmin = -0x3fffffff; *cmax = 0x3fffffff;     // (nearly) constant along the row: no restriction
     }
 }
-// -> first column and number of columns of row (XR, YR) that must be sampled; the rest of the row is 0
-RR_HD void rr_canvas_row_span(const double *M, int XR, int YR, int nW, int tw, int th, int *c0, int *cn) {
+// -> inclusive column range [*c_lo, *c_hi] of row (XR, YR) that can be non-zero (empty when c_lo > c_hi);
+// inv0 / inv3 = rr_canvas_inv(M[0] * 1024) / rr_canvas_inv(M[3] * 1024)
+RR_HD void rr_canvas_row_span(const double *M, double inv0, double inv3, int XR, int YR, int nW, int tw, int th, int *c_lo, int *c_hi) {
     int ax, bx, ay, by;
-    rr_canvas_axis_range(M[0] * 1024.0, XR, tw, &ax, &bx);
-    rr_canvas_axis_range(M[3] * 1024.0, YR, th, &ay, &by);
+    rr_canvas_axis_range(M[0] * 1024.0, inv0, XR, tw, &ax, &bx);
+    rr_canvas_axis_range(M[3] * 1024.0, inv3, YR, th, &ay, &by);
     int a = ax > ay ? ax : ay, b = bx < by ? bx : by;
     if (a < 0) a = 0;
     if (b > nW - 1) b = nW - 1;
-    *c0 = a;
-    *cn = b >= a ? b - a + 1 : 0;
+    *c_lo = a; *c_hi = b;
 }
 
 // ---------------------------------------------------------------------------------------

@@ -296,21 +296,36 @@ cudaError_t rr_launch_stats(const rr_frame_bufs &b, int F, int W, int H, int ren
 //   l = clip(I * f_blur + l_in_blur, 0, 1)                        (:85-93)
 // ------------------------------------------------------------------------------------------
 #define FOG_TX 64
-#define FOG_TY 32
+#ifndef FOG_TY
+#define FOG_TY 32             // rows per tile, a multiple of 8: FOG_TX x (FOG_TY / 8) threads, 8 output rows per thread
+#endif
+#define FOG_THREADS (FOG_TX * (FOG_TY / 8))
+#define FOG_MINB (FOG_THREADS <= 256 ? 2 : 1)
 #define FOG_R 12
 #define FOG_EW (FOG_TX + 2 * FOG_R)
 #define FOG_EH (FOG_TY + 2 * FOG_R)
+// Shared-memory layout.  In the row passes a thread produces 4 consecutive outputs from 28 consecutive inputs,
+// so the lanes of a warp are 4 elements apart: unpadded, a float32 load hits 8 banks (4-way conflict) and a
+// float64 load 4 bank pairs.  One padding element after every 4 (column x lives at x + x/4) makes the lane
+// stride 5 elements, which is conflict free for both widths; the float32 row stride is 16 mod 32 words so
+// that the two rows a warp covers use complementary banks.
+#define FOG_PAD(x) ((x) + ((x) >> 2))
+#define FOG_ES 112            // float32 row stride of E   (>= FOG_PAD(FOG_EW - 1) + 1, 16 mod 32)
+#define FOG_FS 80             // row stride of FH / LH     (== FOG_PAD(FOG_TX), 16 mod 32)
+#define FOG_LS 110            // float64 row stride of D   (>= FOG_PAD(FOG_EW - 1) + 1)
+#define FOG_BYTES_A (sizeof(float) * FOG_EH * (FOG_ES + FOG_FS))     // E + FH, later LH (float64, FOG_EH x FOG_FS)
+#define FOG_BYTES_B (sizeof(double) * FOG_EH * FOG_LS)              // D
 
-// Sliding-window separable passes: each thread produces RUN consecutive outputs from RUN+24 inputs
-// held in registers; every output still accumulates its 25 products in the reference order.
-template <int STRIDE_IN>
+// Sliding-window separable passes: each thread produces 4 consecutive outputs from 28 inputs held in
+// registers; every output still accumulates its 25 products in the reference order.
+// ROW: inputs are consecutive padded columns starting at a multiple of 4; else rows STRIDE apart.
+template <bool ROW, int STRIDE>
 __device__ __forceinline__ void fog_taps_f32(const float *in, double acc[4]) {
-    // 4 outputs along the direction of STRIDE_IN, exact float32 products in float64, ascending taps.
-    // The product of two float32 values is exact in float64, so fma(k, v, a) == a + k * v bit for bit:
-    // one instruction per tap instead of two.
+    // exact float32 products in float64, ascending taps.  The product of two float32 values is exact in
+    // float64, so fma(k, v, a) == a + k * v bit for bit: one instruction per tap instead of two.
     double v[28];
 #pragma unroll
-    for (int i = 0; i < 28; i++) v[i] = (double)in[i * STRIDE_IN];
+    for (int i = 0; i < 28; i++) v[i] = (double)in[ROW ? FOG_PAD(i) : i * STRIDE];
 #pragma unroll
     for (int o = 0; o < 4; o++) {
         double a = c_k32d[0] * v[o];
@@ -330,43 +345,60 @@ __global__ void __launch_bounds__(256) k_fext(const float *depth, float *fext, f
     fext[i] = (float)exp((double)xx);                                       // correctly rounded float32 exp ("canonical")
 }
 
-__global__ void __launch_bounds__(256, 2) k_fog(rr_frame_bufs b, rr_fog_consts fc, int W, int H) {
-    extern __shared__ unsigned char smem_raw[];
-    float *E = (float *)smem_raw;                         // [FOG_EH][FOG_EW]  extinction on the haloed tile
-    float *FH = E + FOG_EH * FOG_EW;                      // [FOG_EH][FOG_TX]  float32 row pass of f_ext
-    double *L = (double *)(FH + FOG_EH * FOG_TX);         // [FOG_EH][FOG_EW]  in-scattering of one channel
-    double *LH = L + FOG_EH * FOG_EW;                     // [FOG_EH][FOG_TX]  its float64 row pass
+__global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, rr_fog_consts fc, int W, int H) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *E = (float *)smem_raw;                         // [FOG_EH][FOG_ES]  extinction on the haloed tile
+    float *FH = E + FOG_EH * FOG_ES;                      // [FOG_EH][FOG_FS]  float32 row pass of f_ext
+    double *LH = (double *)smem_raw;                      // [FOG_EH][FOG_FS]  float64 row pass; reuses E + FH once both are consumed
+    double *D = (double *)(smem_raw + FOG_BYTES_A);       // [FOG_EH][FOG_LS]  1 - f_ext (float32 op, widened)
     const int f = blockIdx.z;
     const int x0 = blockIdx.x * FOG_TX, y0 = blockIdx.y * FOG_TY;
     const int tid = threadIdx.x;
     const float *fext = b.fext + (size_t)f * W * H;
     const uint8_t *bgr = b.bgr + (size_t)f * W * H * 3;
-    for (int i = tid; i < FOG_EH * FOG_EW; i += 256) {
+    const double npix = (double)W * (double)H;
+    double Acs[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        double sum_b = b.bg_sum[f * 4 + c];                                    // mean irradiance of the un-fogged image (:53,70)
+        double irr_mean = ((fc.irr_scale_num * sum_b) / fc.irr_den) / npix;
+        Acs[c] = fc.beta_hg * irr_mean;
+    }
+    // When beta_hg * E_c <= 1 for all channels the clip at :72 can only act on a negative 1 - f_ext (negative
+    // depth), the three in-scatter images are the same image times a scalar, and one blur serves all three:
+    // blur(A*d) = A*blur(d) up to float64 rounding (shortcut 3).  Otherwise each channel is
+    // blurred on its own: l_in_c = clip(A_c * (1 - f_ext), 0, 1) is then formed while the row pass loads its inputs.
+    const bool linear = Acs[0] >= 0 && Acs[0] <= 1 && Acs[1] >= 0 && Acs[1] <= 1 && Acs[2] >= 0 && Acs[2] <= 1;
+    for (int i = tid; i < FOG_EH * FOG_EW; i += FOG_THREADS) {
         int ey = i / FOG_EW, ex = i - ey * FOG_EW;
         int gy = r101(y0 + ey - FOG_R, H), gx = r101(x0 + ex - FOG_R, W);
         float v = 0.f;
         if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = fext[(size_t)gy * W + gx];    // k_fext
-        E[i] = v;
+        E[ey * FOG_ES + FOG_PAD(ex)] = v;
+        double d = (double)(1.0f - v);                                      // (1 - f_ext) is a float32 op in numpy (:71)
+        if (linear) d = d < 0 ? 0 : (d > 1 ? 1 : d);                        // clip(A d, 0, 1) = A clip(d, 0, 1) for 0 <= A <= 1
+        D[ey * FOG_LS + FOG_PAD(ex)] = d;
     }
     __syncthreads();
     // float32 row pass of f_ext: 4 outputs per task
-    for (int i = tid; i < FOG_EH * (FOG_TX / 4); i += 256) {
+    for (int i = tid; i < FOG_EH * (FOG_TX / 4); i += FOG_THREADS) {
         int ey = i / (FOG_TX / 4), ox = (i - ey * (FOG_TX / 4)) * 4;
         double a[4];
-        fog_taps_f32<1>(E + ey * FOG_EW + ox, a);
+        fog_taps_f32<true, 0>(E + ey * FOG_ES + FOG_PAD(ox), a);
 #pragma unroll
-        for (int o = 0; o < 4; o++) FH[ey * FOG_TX + ox + o] = (float)a[o];
+        for (int o = 0; o < 4; o++) FH[ey * FOG_FS + FOG_PAD(ox) + o] = (float)a[o];
     }
     __syncthreads();
     // float32 column pass: thread = (column, block of 8 rows)
     const int cx = tid & (FOG_TX - 1), cy0 = (tid / FOG_TX) * 8;
+    const int pcx = FOG_PAD(cx);
     float fb[8];
     {
         double a[4];
-        fog_taps_f32<FOG_TX>(FH + cy0 * FOG_TX + cx, a);
+        fog_taps_f32<false, FOG_FS>(FH + cy0 * FOG_FS + pcx, a);
 #pragma unroll
         for (int o = 0; o < 4; o++) fb[o] = (float)a[o];
-        fog_taps_f32<FOG_TX>(FH + (cy0 + 4) * FOG_TX + cx, a);
+        fog_taps_f32<false, FOG_FS>(FH + (cy0 + 4) * FOG_FS + pcx, a);
 #pragma unroll
         for (int o = 0; o < 4; o++) fb[4 + o] = (float)a[o];
     }
@@ -377,40 +409,27 @@ __global__ void __launch_bounds__(256, 2) k_fog(rr_frame_bufs b, rr_fog_consts f
             if (gy < H && gx < W) b.fblur[(size_t)f * W * H + (size_t)gy * W + gx] = fb[k];
         }
     }
-    const double npix = (double)W * (double)H;
-    double Acs[3];
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-        double sum_b = b.bg_sum[f * 4 + c];                                    // mean irradiance of the un-fogged image (:53,70)
-        double irr_mean = ((fc.irr_scale_num * sum_b) / fc.irr_den) / npix;
-        Acs[c] = fc.beta_hg * irr_mean;
-    }
-    // When beta_hg * E_c <= 1 for all channels the clip at :72 can never act (0 <= 1 - f_ext <= 1), the three
-    // in-scatter images are the same image times a scalar, and one blur serves all three: blur(A*d) = A*blur(d)
-    // up to float64 rounding (shortcut 3).  Otherwise each channel is blurred on its own.
-    const bool linear = Acs[0] >= 0 && Acs[0] <= 1 && Acs[1] >= 0 && Acs[1] <= 1 && Acs[2] >= 0 && Acs[2] <= 1;
     const int npass = linear ? 1 : 3;
     for (int c = 0; c < npass; c++) {
-        const double Ac = linear ? 1.0 : Acs[c];
-        __syncthreads();
-        for (int i = tid; i < FOG_EH * FOG_EW; i += 256) {
-            double li = Ac * (double)(1.0f - E[i]);                           // (1 - f_ext) is a float32 op in numpy (:71)
-            L[i] = li < 0 ? 0 : (li > 1 ? 1 : li);                            // :72
-        }
-        __syncthreads();
+        const double Ac = Acs[c];
+        __syncthreads();            // E and FH consumed (first pass) / LH of the previous channel consumed
         // float64 row pass, cv::RowFilter order: k[0]*x[0] + k[1]*x[1] + ...
-        for (int i = tid; i < FOG_EH * (FOG_TX / 4); i += 256) {
+        for (int i = tid; i < FOG_EH * (FOG_TX / 4); i += FOG_THREADS) {
             int ey = i / (FOG_TX / 4), ox = (i - ey * (FOG_TX / 4)) * 4;
-            const double *row = L + ey * FOG_EW + ox;
+            const double *row = D + ey * FOG_LS + FOG_PAD(ox);
             double v[28];
 #pragma unroll
-            for (int k = 0; k < 28; k++) v[k] = row[k];
+            for (int k = 0; k < 28; k++) v[k] = row[FOG_PAD(k)];
+            if (!linear) {
+#pragma unroll
+                for (int k = 0; k < 28; k++) { double li = Ac * v[k]; v[k] = li < 0 ? 0 : (li > 1 ? 1 : li); }   // :71-72
+            }
 #pragma unroll
             for (int o = 0; o < 4; o++) {
                 double a = c_k64[0] * v[o];
 #pragma unroll
                 for (int t = 1; t < 25; t++) a += c_k64[t] * v[o + t];
-                LH[ey * FOG_TX + ox + o] = a;
+                LH[ey * FOG_FS + FOG_PAD(ox) + o] = a;
             }
         }
         __syncthreads();
@@ -418,7 +437,7 @@ __global__ void __launch_bounds__(256, 2) k_fog(rr_frame_bufs b, rr_fog_consts f
         {
             double v[32];
 #pragma unroll
-            for (int k = 0; k < 32; k++) v[k] = LH[(cy0 + k) * FOG_TX + cx];
+            for (int k = 0; k < 32; k++) v[k] = LH[(cy0 + k) * FOG_FS + pcx];
 #pragma unroll
             for (int o = 0; o < 8; o++) {
                 double acc = c_k64[12] * v[o + 12];
@@ -442,7 +461,9 @@ __global__ void __launch_bounds__(256, 2) k_fog(rr_frame_bufs b, rr_fog_consts f
 }
 
 cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, cudaStream_t st) {
-    size_t smem = sizeof(float) * (FOG_EH * FOG_EW + FOG_EH * FOG_TX) + sizeof(double) * (FOG_EH * FOG_EW + FOG_EH * FOG_TX);
+    static_assert(FOG_ES >= FOG_PAD(FOG_EW - 1) + 1 && FOG_LS >= FOG_PAD(FOG_EW - 1) + 1 && FOG_FS >= FOG_PAD(FOG_TX - 1) + 1, "fog strides");
+    static_assert(sizeof(double) * FOG_EH * FOG_FS <= FOG_BYTES_A, "LH must fit in the E + FH region");
+    size_t smem = FOG_BYTES_A + FOG_BYTES_B;
     {
         size_t n = (size_t)F * W * H;
         k_fext<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.depth, b.fext, fc.neg_beta32, n);
@@ -454,7 +475,7 @@ cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F
         attr = true;
     }
     dim3 grid((W + FOG_TX - 1) / FOG_TX, (H + FOG_TY - 1) / FOG_TY, F);
-    k_fog<<<grid, 256, smem, st>>>(b, fc, W, H);
+    k_fog<<<grid, FOG_THREADS, smem, st>>>(b, fc, W, H);
     return cudaGetLastError();
 }
 
@@ -875,10 +896,14 @@ __device__ __forceinline__ int find_streak(const long long *scan, int n, int fie
 // ------------------------------------------------------------------------------------------
 // pre-blur gray patches  (generator.py:126-171): one CTA per streak (persistent, strided).
 //   Big                -> one thread per patch pixel (16-tap bicubic perspective warp)
-//   INTER_AREA shrink  -> the rotated canvas (imutils.rotate_bound) is evaluated ONCE, band by band,
-//                         into shared memory; the per-pixel sums then follow cv::resize's exact
-//                         accumulation order (column terms left to right inside a source row, rows
-//                         top to bottom), so the result is bit-identical to the per-pixel evaluation.
+//   INTER_AREA shrink  -> cv::resizeArea_ order: for every canvas row and patch column dx the weighted
+//                         sum of the row's canvas pixels (left to right), then the rows top to bottom.
+//                         One thread owns one (canvas row, dx) chain and evaluates its canvas pixels
+//                         (imutils.rotate_bound -> warpAffine fixed-point bilinear) on the fly, skipping
+//                         the columns where the rotated texture cannot be (exact zeros); the chains of a
+//                         whole canvas usually fit one band, so a streak costs three barriers.
+//   integer-factor INTER_AREA (resizeAreaFast_): rare; its 4-wide groups run across rows, so the canvas
+//                         is staged band by band in shared memory and every patch pixel walks its cell.
 // ------------------------------------------------------------------------------------------
 #define RAS_THREADS 128
 #ifndef RAS_CAP
@@ -890,7 +915,7 @@ __device__ __forceinline__ int find_streak(const long long *scan, int n, int fie
 #define RAS_MAXW 512          // widest rotated canvas handled by the staged path
 #define RAS_TXN 128           // widest / tallest patch with cached computeResizeAreaTab spans
 #define RAS_MAXD 1024         // patch pixels with accumulators resident in shared memory
-#define RAS_RBMAX 128         // rows per band (RAS_CAP / canvas width; canvases are at least 32 wide)
+#define RAS_RBMAX 128         // rows per band of the area-fast path (RAS_CAP / canvas width; canvases are at least 32 wide)
 
 __device__ __forceinline__ double ras_sample(const uint8_t *tex, int tw, int th, const double *lut, int X, int Y) {
     // rr_warp_affine_linear with the fixed-point coordinates already formed.  One code path for interior and
@@ -912,24 +937,18 @@ __device__ __forceinline__ double ras_sample(const uint8_t *tex, int tw, int th,
     return v0 * w0 + v1 * w1 + v2 * w2 + v3 * w3;
 }
 
-struct ras_smem_src {       // functor over a staged band: rows [0, rb) x columns [0, nW)
-    const double *C; int nW;
-    __device__ __forceinline__ double operator()(int sx, int r) const { return C[r * nW + sx]; }
-};
-
 __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs b, rr_static_tabs t, rr_cam_dev cam, int n) {
     extern __shared__ double ras_smem[];
-    double *C = ras_smem;                       // [RAS_CAP]   canvas band
-    double *BUF = C + RAS_CAP;                  // [RAS_CAP]   per (source row, dx) column sums (area) / quad accumulators (area-fast)
+    double *C = ras_smem;                       // [RAS_CAP]   area-fast: canvas band;  area: first half of the chain sums
+    double *BUF = C + RAS_CAP;                  // [RAS_CAP]   area-fast: quad accumulators; area: second half of the chain sums
     double *SUM = BUF + RAS_CAP;                // [RAS_MAXD]  per patch pixel running sum
     double *lut = SUM + RAS_MAXD;               // [256]       u8 / 255.0
     rr_area_span *TX = (rr_area_span *)(lut + 256);     // [RAS_TXN]
     rr_area_span *TY = TX + RAS_TXN;                     // [RAS_TXN]
     int *adx = (int *)(TY + RAS_TXN), *bdx = adx + RAS_MAXW;   // [RAS_MAXW] each
-    int *XR = bdx + RAS_MAXW, *YR = XR + RAS_RBMAX;            // [RAS_RBMAX] each
-    int *CL = YR + RAS_RBMAX, *CN = CL + RAS_RBMAX;            // [RAS_RBMAX] each: sampled column span of a band row
-    __shared__ int s_wmax;                                     // widest span of the band
+    int *XR = bdx + RAS_MAXW, *YR = XR + RAS_RBMAX;            // [RAS_RBMAX] each (area-fast)
     double *ACC = BUF;
+    double *CB = C;                             // [2 * RAS_CAP] chain sums of the area path: CB[r * pw + dx]
     __shared__ rr_plan sp;
     const int tid = threadIdx.x;
     for (int i = tid; i < 256; i += RAS_THREADS) lut[i] = (double)i / 255.0;     // bad_weather.py:252
@@ -937,7 +956,6 @@ __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs 
     for (int s = blockIdx.x; s < n; s += gridDim.x) {
         __syncthreads();
         if (tid < sizeof(rr_plan) / 4) ((int *)&sp)[tid] = ((const int *)&b.plans[s])[tid];
-        if (tid == 0) s_wmax = 0;
         __syncthreads();
         const rr_plan &p = sp;
         long long g, vv, aa; int vx0_, vw_;
@@ -957,8 +975,6 @@ __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs 
         const int nW = p.nW, nH = p.nH, pw = p.pw, ph = p.ph, th = p.tex_h, npx = pw * ph;
         const int AB_SCALE = 1 << 10;
         const bool fast = p.resize_mode == RR_RESIZE_AREA_FAST;
-        const int isx = rr_round(p.scale_x), isy = rr_round(p.scale_y);
-        const int area = isx * isy, area4 = area - (area & 3);
         for (int x = tid; x < nW; x += RAS_THREADS) {
             adx[x] = rr_round(p.M[0] * x * AB_SCALE);
             bdx[x] = rr_round(p.M[3] * x * AB_SCALE);
@@ -966,63 +982,37 @@ __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs 
         if (!fast) {
             for (int dx = tid; dx < pw; dx += RAS_THREADS) TX[dx] = rr_area_tab(dx, p.scale_x, nW);
             for (int dy = tid; dy < ph; dy += RAS_THREADS) TY[dy] = rr_area_tab(dy, p.scale_y, nH);
-        }
-        int RB = RAS_CAP / (nW > pw ? nW : pw);
-        if (RB < 1) RB = 1;
-        if (RB > RAS_RBMAX) RB = RAS_RBMAX;
-        const int step_r = RAS_THREADS / nW, step_c = RAS_THREADS - step_r * nW;
-        const int r_first = tid / nW, c_first = tid - r_first * nW;
-        // bands of canvas rows; every canvas pixel is sampled exactly once
-        for (int s0 = 0; s0 < nH; s0 += RB) {
-            const int rb = (nH - s0) < RB ? (nH - s0) : RB;
-            __syncthreads();                         // previous band fully consumed (C, BUF, XR)
-            for (int r = tid; r < rb; r += RAS_THREADS) {
-                int sy = s0 + r;
-                int yy = p.flip ? (nH - 1 - sy) : sy;
-                int xr = rr_round((p.M[1] * yy + p.M[2]) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
-                int yr = rr_round((p.M[4] * yy + p.M[5]) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
-                XR[r] = xr; YR[r] = yr;
-                // the rotated texture covers a slanted band of the canvas: outside [cl, cl + cn) every tap of the
-                // row misses the texture and the sample is exactly 0 (rr_canvas_row_span is a superset)
-                int cl, cn;
-                rr_canvas_row_span(p.M, xr, yr, nW, tw, th, &cl, &cn);
-                CL[r] = cl; CN[r] = cn;
-                if (cn > 0) atomicMax(&s_wmax, cn);
-            }
-            __syncthreads();
-            const int wmax = s_wmax;
-            {
-                // zeros outside the spans ...
-                int r = r_first, c = c_first;                       // (row, column) of flattened index tid
-                for (int i = tid; i < rb * nW; i += RAS_THREADS) {
-                    if ((unsigned)(c - CL[r]) >= (unsigned)CN[r]) C[i] = 0.0;
-                    c += step_c; r += step_r;                       // advance by RAS_THREADS without a division
-                    if (c >= nW) { c -= nW; r++; }
-                }
-            }
-            if (wmax > 0) {
-                // ... samples inside: work items (row, k < wmax), so that the lanes of a warp are (nearly) all inside
-                const int st_r = RAS_THREADS / wmax, st_k = RAS_THREADS - st_r * wmax;
-                int r = tid / wmax, k = tid - r * wmax;
-                for (int i = tid; i < rb * wmax; i += RAS_THREADS) {
-                    if (k < CN[r]) {
-                        const int c = CL[r] + k;
-                        int X = (XR[r] + adx[c]) >> (10 - RR_INTER_BITS);
-                        int Y = (YR[r] + bdx[c]) >> (10 - RR_INTER_BITS);
-                        C[r * nW + c] = ras_sample(tex, tw, th, lut, X, Y);
-                    }
-                    k += st_k; r += st_r;
-                    if (k >= wmax) { k -= wmax; r++; }
-                }
-            }
-            __syncthreads();
-            if (tid == 0) s_wmax = 0;                               // next band's atomicMax comes after its first barrier
-            if (!fast) {
+            const double M0 = p.M[0], M1 = p.M[1], M2 = p.M[2], M3 = p.M[3], M4 = p.M[4], M5 = p.M[5];
+            const double inv0 = rr_canvas_inv(M0 * 1024.0), inv3 = rr_canvas_inv(M3 * 1024.0);
+            int RB = (2 * RAS_CAP) / pw;             // pw <= RAS_TXN: at least 20 rows
+            if (RB > nH) RB = nH;
+            for (int s0 = 0; s0 < nH; s0 += RB) {
+                const int rb = (nH - s0) < RB ? (nH - s0) : RB;
+                __syncthreads();                     // tables ready / previous band's chain sums consumed
                 // cv::resizeArea_: buf[dx] = sum_k S[sx_k] * alpha_k (left to right) for every source row of the band ...
                 for (int i = tid; i < rb * pw; i += RAS_THREADS) {
-                    int r = i / pw, dx = i - r * pw;
-                    ras_smem_src src = {C, nW};
-                    BUF[i] = rr_area_row(src, TX[dx], r);
+                    const int r = i / pw, dx = i - r * pw;
+                    const int sy = s0 + r;
+                    const int yy = p.flip ? (nH - 1 - sy) : sy;
+                    const int xr = rr_round((M1 * yy + M2) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
+                    const int yr = rr_round((M4 * yy + M5) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
+                    const rr_area_span tx = TX[dx];
+                    // canvas columns of this chain: [first partial] s_first .. s_first + n - 1 [last partial] ...
+                    int c_lo = tx.s_first - tx.has_first, c_hi = tx.s_first + tx.n - 1 + tx.has_last;
+                    // ... of which only the slanted band the rotated texture covers can be non-zero; a zero sample adds
+                    // exactly +0.0 to the running sum, so skipping it leaves the sum bit for bit unchanged
+                    int z_lo, z_hi;
+                    rr_canvas_row_span(p.M, inv0, inv3, xr, yr, nW, tw, th, &z_lo, &z_hi);
+                    if (c_lo < z_lo) c_lo = z_lo;
+                    if (c_hi > z_hi) c_hi = z_hi;
+                    double buf = 0;
+                    for (int c = c_lo; c <= c_hi; c++) {
+                        const float alpha = c < tx.s_first ? tx.a_first : (c >= tx.s_first + tx.n ? tx.a_last : tx.a_mid);
+                        const int X = (xr + adx[c]) >> (10 - RR_INTER_BITS);
+                        const int Y = (yr + bdx[c]) >> (10 - RR_INTER_BITS);
+                        buf += ras_sample(tex, tw, th, lut, X, Y) * alpha;
+                    }
+                    CB[i] = buf;
                 }
                 __syncthreads();
                 // ... then sum[dx] (+)= beta * buf[dx], rows top to bottom; a patch pixel's rows may span bands
@@ -1036,41 +1026,76 @@ __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs 
                     double acc = SUM[e];
                     for (int j = jlo; j < jhi; j++) {
                         float beta = (ty.has_first && j == 0) ? ty.a_first : ((ty.has_last && j == nr - 1) ? ty.a_last : ty.a_mid);
-                        double v = beta * BUF[(row0 + j - s0) * pw + dx];
+                        double v = beta * CB[(row0 + j - s0) * pw + dx];
                         acc = (j == 0) ? v : acc + v;
                     }
                     SUM[e] = acc;
                 }
-            } else {
-                // cv::resizeAreaFast_: sum += ((a + b) + c) + d over the cell in row-major order, then the tail
-                for (int e = tid; e < npx; e += RAS_THREADS) {
-                    int dy = e / pw, dx = e - dy * pw;
-                    const int row0 = dy * isy;
-                    int jlo = s0 - row0; if (jlo < 0) jlo = 0;
-                    int jhi = s0 + rb - row0; if (jhi > isy) jhi = isy;
-                    if (jlo >= jhi) continue;
-                    double sum = (jlo == 0) ? 0.0 : SUM[e], acc = (jlo == 0) ? 0.0 : ACC[RAS_CAP - 1 - e];
-                    for (int j = jlo; j < jhi; j++) {
-                        const int kbase = j * isx;
-                        const double *row = C + (row0 + j - s0) * nW + dx * isx;
-                        for (int c = 0; c < isx; c++) {
-                            int k = kbase + c;
-                            double v = row[c];
-                            if (k < area4) {
-                                int pos = k & 3;
-                                acc = pos == 0 ? v : acc + v;
-                                if (pos == 3) sum += acc;
-                            } else sum += v;
-                        }
-                    }
-                    SUM[e] = sum; ACC[RAS_CAP - 1 - e] = acc;
+            }
+            __syncthreads();
+            for (int e = tid; e < npx; e += RAS_THREADS) {
+                double v = SUM[e];
+                out[e] = v < 0 ? 0 : (v > 1 ? 1 : v);
+            }
+            continue;
+        }
+        // ---- integer-factor area mode: the canvas staged band by band; every canvas pixel is sampled exactly once ----
+        const int isx = rr_round(p.scale_x), isy = rr_round(p.scale_y);
+        const int area = isx * isy, area4 = area - (area & 3);
+        int RB = RAS_CAP / (nW > pw ? nW : pw);
+        if (RB < 1) RB = 1;
+        if (RB > RAS_RBMAX) RB = RAS_RBMAX;
+        const int step_r = RAS_THREADS / nW, step_c = RAS_THREADS - step_r * nW;
+        const int r_first = tid / nW, c_first = tid - r_first * nW;
+        for (int s0 = 0; s0 < nH; s0 += RB) {
+            const int rb = (nH - s0) < RB ? (nH - s0) : RB;
+            __syncthreads();                         // previous band fully consumed (C, ACC, XR)
+            for (int r = tid; r < rb; r += RAS_THREADS) {
+                int sy = s0 + r;
+                int yy = p.flip ? (nH - 1 - sy) : sy;
+                XR[r] = rr_round((p.M[1] * yy + p.M[2]) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
+                YR[r] = rr_round((p.M[4] * yy + p.M[5]) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
+            }
+            __syncthreads();
+            {
+                int r = r_first, c = c_first;                       // (row, column) of flattened index tid
+                for (int i = tid; i < rb * nW; i += RAS_THREADS) {
+                    int X = (XR[r] + adx[c]) >> (10 - RR_INTER_BITS);
+                    int Y = (YR[r] + bdx[c]) >> (10 - RR_INTER_BITS);
+                    C[i] = ras_sample(tex, tw, th, lut, X, Y);
+                    c += step_c; r += step_r;                       // advance by RAS_THREADS without a division
+                    if (c >= nW) { c -= nW; r++; }
                 }
+            }
+            __syncthreads();
+            // cv::resizeAreaFast_: sum += ((a + b) + c) + d over the cell in row-major order, then the tail
+            for (int e = tid; e < npx; e += RAS_THREADS) {
+                int dy = e / pw, dx = e - dy * pw;
+                const int row0 = dy * isy;
+                int jlo = s0 - row0; if (jlo < 0) jlo = 0;
+                int jhi = s0 + rb - row0; if (jhi > isy) jhi = isy;
+                if (jlo >= jhi) continue;
+                double sum = (jlo == 0) ? 0.0 : SUM[e], acc = (jlo == 0) ? 0.0 : ACC[RAS_CAP - 1 - e];
+                for (int j = jlo; j < jhi; j++) {
+                    const int kbase = j * isx;
+                    const double *row = C + (row0 + j - s0) * nW + dx * isx;
+                    for (int c = 0; c < isx; c++) {
+                        int k = kbase + c;
+                        double v = row[c];
+                        if (k < area4) {
+                            int pos = k & 3;
+                            acc = pos == 0 ? v : acc + v;
+                            if (pos == 3) sum += acc;
+                        } else sum += v;
+                    }
+                }
+                SUM[e] = sum; ACC[RAS_CAP - 1 - e] = acc;
             }
         }
         __syncthreads();
         for (int e = tid; e < npx; e += RAS_THREADS) {
-            double v = SUM[e];
-            if (fast) { float scale = 1.f / area; v = v * scale; }
+            float scale = 1.f / area;
+            double v = SUM[e] * scale;
             out[e] = v < 0 ? 0 : (v > 1 ? 1 : v);
         }
     }
@@ -1080,7 +1105,7 @@ cudaError_t rr_launch_raster(const rr_frame_bufs &b, const rr_static_tabs &t, co
                              cudaStream_t st) {
     if (n_streaks == 0) return cudaSuccess;
     const size_t smem = sizeof(double) * (2 * RAS_CAP + RAS_MAXD + 256) + sizeof(rr_area_span) * 2 * RAS_TXN +
-                        sizeof(int) * (2 * RAS_MAXW + 4 * RAS_RBMAX);
+                        sizeof(int) * (2 * RAS_MAXW + 2 * RAS_RBMAX);
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

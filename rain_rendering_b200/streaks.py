@@ -13,6 +13,7 @@ per-frame path.
 """
 from __future__ import annotations
 
+import os
 from xml.etree.ElementTree import parse
 
 import numpy as np
@@ -31,14 +32,23 @@ def _vec(attr: str):
     return [float(t) for t in attr[1:-1].split(";")]
 
 
-def records_from_raw(wp1, wp2, ip1, ip2, iw1, iw2, pid, render_scale: int, W: int, H: int) -> np.ndarray:
+def _norm2(x, y):
+    """np.linalg.norm of 2-vectors as NumPy's BLAS evaluates it (sqrt(fma(y, y, x*x)), rr_host_norm2)."""
+    from . import _lib
+    x, y = np.ascontiguousarray(x, np.float64), np.ascontiguousarray(y, np.float64)
+    out = np.empty_like(x)
+    _lib.load().rr_host_norm2(len(x), _lib.ptr(x), _lib.ptr(y), _lib.ptr(out))
+    return out
+
+
+def records_from_raw(wp1, wp2, ip1, ip2, iw1, iw2, pid, render_scale: int, W: int, H: int, return_mask: bool = False):
     """Simulator-convention arrays (image y up, world z negative forward, full sensor resolution) ->
     STREAK_DTYPE records, restricted to ``max_width >= 1 and length >= 1``: the arithmetic of
     DBManager.load_streaks_from_xml (bad_weather.py:208-238), vectorised."""
     n = len(pid)
     rec = np.zeros(n, dtype=STREAK_DTYPE)
     if n == 0:
-        return rec
+        return (rec, np.zeros(0, bool)) if return_mask else rec
     wp1 = np.array(wp1, dtype=np.float64)
     wp2 = np.array(wp2, dtype=np.float64)
     ip1 = np.array(ip1, dtype=np.float64) / render_scale        # :208-209
@@ -52,7 +62,7 @@ def records_from_raw(wp1, wp2, ip1, ip2, iw1, iw2, pid, render_scale: int, W: in
     diff = np.abs(ip1 - ip2)
     max_width = np.maximum(iw1, iw2).astype(np.int64)            # :226 int() truncation
     with np.errstate(divide="ignore", invalid="ignore"):
-        nrm = np.sqrt(diff[:, 0] * diff[:, 0] + diff[:, 1] * diff[:, 1])
+        nrm = _norm2(diff[:, 0], diff[:, 1])                                     # np.linalg.norm(diff), :229
         cos_theta = 0 * (diff[:, 0] / nrm) + -1 * (-(diff[:, 1] / nrm))          # :228-231
         ratio = max_width / (diff[:, 1] / cos_theta)                             # :232-233
     ip1r = np.round(ip1).astype(np.int64)                        # :234-235 (half-even)
@@ -65,25 +75,61 @@ def records_from_raw(wp1, wp2, ip1, ip2, iw1, iw2, pid, render_scale: int, W: in
     rec["max_width"], rec["length"] = max_width, length
     rec["pid"] = np.asarray(pid)
     rec["type"] = np.where(max_width >= 4, BIG, np.where(max_width > 1, MEDIUM, SMALL))   # :99-106
-    return rec[(max_width >= 1) & (length >= 1)]
+    keep = (max_width >= 1) & (length >= 1)
+    return (rec[keep], keep) if return_mask else rec[keep]
 
 
-def load_streaks_from_xml(path: str, render_scale: int, W: int, H: int):
-    """-> list (one entry per simulator frame, XML order) of STREAK_DTYPE arrays in XML order,
-    already restricted to ``max_width >= 1 and length >= 1`` (bad_weather.py:238).  A later
-    duplicate ``pid`` replaces the earlier entry but keeps its position, like the reference's
-    dict ``update``."""
-    frames = []
+def load_streaks_from_xml_py(path: str, render_scale: int, W: int, H: int, with_ids: bool = False):
+    """Pure-Python statement of the loader (xml.etree + the vectorised arithmetic above): the comparand of
+    the native loader in the CPU test-suite.  -> list (one entry per simulator frame, dict order of the
+    frame ids) of STREAK_DTYPE arrays in dict order of the pids, restricted to ``max_width >= 1 and
+    length >= 1``; a streak that fails that test never enters the dict, a later one with the same pid
+    replaces the earlier entry in place (bad_weather.py:238), frames likewise by id (:241)."""
+    frames = {}
     for frame in parse(path).getroot():
-        rows = {}
-        for drop in frame:
-            a = drop.attrib
-            rows[int(a["pid"])] = (_vec(a["wp1"]), _vec(a["wp2"]), _vec(a["ip1"]), _vec(a["ip2"]),
-                                   float(a["iw1"]), float(a["iw2"]), int(a["pid"]))
-        vals = list(rows.values())
-        frames.append(records_from_raw([v[0] for v in vals], [v[1] for v in vals], [v[2] for v in vals], [v[3] for v in vals],
-                                       [v[4] for v in vals], [v[5] for v in vals], [v[6] for v in vals], render_scale, W, H)
-                      if vals else np.zeros(0, dtype=STREAK_DTYPE))
+        fid = int(frame.attrib["id"])
+        int(frame.attrib["t"]), int(frame.attrib["d"]), int(frame.attrib["rs"])      # read (and required) by the reference
+        vals = [(_vec(a["wp1"]), _vec(a["wp2"]), _vec(a["ip1"]), _vec(a["ip2"]), float(a["iw1"]), float(a["iw2"]), int(a["pid"]),
+                 float(a["wd1"]), float(a["wd2"])) for a in (drop.attrib for drop in frame)]
+        if vals:
+            n_all = len(vals)
+            rec, kept = records_from_raw([v[0] for v in vals], [v[1] for v in vals], [v[2] for v in vals], [v[3] for v in vals],
+                                         [v[4] for v in vals], [v[5] for v in vals], [v[6] for v in vals], render_scale, W, H,
+                                         return_mask=True)
+            assert len(kept) == n_all
+            rows = {}
+            for r in rec:
+                rows[int(r["pid"])] = r
+            rec = np.array(list(rows.values()), dtype=STREAK_DTYPE) if rows else np.zeros(0, dtype=STREAK_DTYPE)
+        else:
+            rec = np.zeros(0, dtype=STREAK_DTYPE)
+        frames[fid] = rec
+    if with_ids:
+        return list(frames.values()), list(frames.keys())
+    return list(frames.values())
+
+
+def load_streaks_from_xml(path: str, render_scale: int, W: int, H: int, with_ids: bool = False):
+    """DBManager.load_streaks_from_xml (bad_weather.py:148-248) through the library's native loader
+    (``rr_host_load_particles_xml``, csrc/rr_host_xml.cpp).  -> list, one entry per simulator frame in
+    the order the reference's dict holds them, of STREAK_DTYPE arrays (tex_idx / noise_deg still zero: they
+    are drawn per rendered frame).  ``with_ids`` also returns the frame ids."""
+    import ctypes as C
+    from . import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    _lib.check(lib.rr_host_load_particles_xml(os.fsencode(path), int(render_scale), int(W), int(H), C.byref(h)), "rr_host_load_particles_xml")
+    try:
+        nf, nr = C.c_int32(0), C.c_int64(0)
+        _lib.check(lib.rr_host_particles_info(h, C.byref(nf), C.byref(nr)), "rr_host_particles_info")
+        hdr = np.zeros(nf.value, dtype=_lib.XML_FRAME_DTYPE)
+        rec = np.zeros(nr.value, dtype=STREAK_DTYPE)
+        _lib.check(lib.rr_host_particles_copy(h, _lib.ptr(hdr), _lib.ptr(rec)), "rr_host_particles_copy")
+    finally:
+        lib.rr_host_free_particles(h)
+    frames = [rec[int(f["first"]):int(f["first"] + f["count"])].copy() for f in hdr]
+    if with_ids:
+        return frames, [int(f["id"]) for f in hdr]
     return frames
 
 

@@ -101,8 +101,9 @@ extern "C" long hs_canvas_span_violations(const rr_plan *p, int tw, long *stats)
         int yy = p->flip ? (p->nH - 1 - sy) : sy;
         int XR = rr_round((p->M[1] * yy + p->M[2]) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
         int YR = rr_round((p->M[4] * yy + p->M[5]) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
-        int c0, cn;
-        rr_canvas_row_span(p->M, XR, YR, p->nW, tw, p->tex_h, &c0, &cn);
+        int c0, c1;
+        rr_canvas_row_span(p->M, rr_canvas_inv(p->M[0] * 1024.0), rr_canvas_inv(p->M[3] * 1024.0), XR, YR, p->nW, tw, p->tex_h, &c0, &c1);
+        int cn = c1 >= c0 ? c1 - c0 + 1 : 0;
         stats[0] += p->nW; stats[1] += cn;
         for (int c = 0; c < p->nW; c++) {
             int sx = (XR + rr_round(p->M[0] * c * AB_SCALE)) >> 10, syy = (YR + rr_round(p->M[3] * c * AB_SCALE)) >> 10;
