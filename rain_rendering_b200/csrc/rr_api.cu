@@ -362,9 +362,9 @@ static int run_pipeline(rr_context *c, int F, int n_streaks, bool timed) {
     if (timed) CK(cudaEventRecord(c->ev[RR_T_EPILOGUE], st));
     CK(rr_launch_epilogue(b, F, W, H, st));
     if (timed) CK(cudaEventRecord(c->ev[RR_T_D2H], st));
-    // stats 2, extinction 1, fog 1, env map + prefix + ambient 3, set-up 1, scan 1, raster + two blur passes 3,
+    // stats 2, extinction 1, fog 1, env map + prefix + ambient 3, plan + set-up 2, scan 1, raster + two blur passes 3,
     // composite + frame mean 2, epilogue 1
-    c->launches += 2 + 1 + 1 + 3 + (n_streaks ? 1 : 0) + 1 + (n_streaks ? 3 : 0) + 2 + 1;
+    c->launches += 2 + 1 + 1 + 3 + (n_streaks ? 2 : 0) + 1 + (n_streaks ? 3 : 0) + 2 + 1;
     c->last_n_streaks = n_streaks;
     return RR_OK;
 }
@@ -689,7 +689,7 @@ int rr_streak_photometry_only(rr_context *c, const uint8_t *env_bgr_u8, int n_st
     CK(rr_launch_env_prefix_only(b, t, 1, c->H_env, c->W_env, st));
     c->camd.db_width = c->db_width; c->camd.n_tex = c->n_tex;
     CK(rr_launch_setup(b, t, c->camd, 1, n_streaks, st));
-    c->launches += 3;
+    c->launches += 4;
     std::vector<rr_plan> plans(n_streaks);
     CK(cudaMemcpyAsync(plans.data(), b.plans, sizeof(rr_plan) * n_streaks, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

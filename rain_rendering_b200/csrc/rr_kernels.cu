@@ -351,6 +351,7 @@ __global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, 
     float *FH = E + FOG_EH * FOG_ES;                      // [FOG_EH][FOG_FS]  float32 row pass of f_ext
     double *LH = (double *)smem_raw;                      // [FOG_EH][FOG_FS]  float64 row pass; reuses E + FH once both are consumed
     double *D = (double *)(smem_raw + FOG_BYTES_A);       // [FOG_EH][FOG_LS]  1 - f_ext (float32 op, widened)
+    uint8_t *IB = smem_raw + FOG_BYTES_A + FOG_BYTES_B;   // [FOG_TY][FOG_TX * 3]  the tile's image bytes
     const int f = blockIdx.z;
     const int x0 = blockIdx.x * FOG_TX, y0 = blockIdx.y * FOG_TY;
     const int tid = threadIdx.x;
@@ -369,15 +370,45 @@ __global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, 
     // blur(A*d) = A*blur(d) up to float64 rounding (shortcut 3).  Otherwise each channel is
     // blurred on its own: l_in_c = clip(A_c * (1 - f_ext), 0, 1) is then formed while the row pass loads its inputs.
     const bool linear = Acs[0] >= 0 && Acs[0] <= 1 && Acs[1] >= 0 && Acs[1] <= 1 && Acs[2] >= 0 && Acs[2] <= 1;
-    for (int i = tid; i < FOG_EH * FOG_EW; i += FOG_THREADS) {
-        int ey = i / FOG_EW, ex = i - ey * FOG_EW;
-        int gy = r101(y0 + ey - FOG_R, H), gx = r101(x0 + ex - FOG_R, W);
-        float v = 0.f;
-        if (gy >= 0 && gy < H && gx >= 0 && gx < W) v = fext[(size_t)gy * W + gx];    // k_fext
-        E[ey * FOG_ES + FOG_PAD(ex)] = v;
-        double d = (double)(1.0f - v);                                      // (1 - f_ext) is a float32 op in numpy (:71)
-        if (linear) d = d < 0 ? 0 : (d > 1 ? 1 : d);                        // clip(A d, 0, 1) = A clip(d, 0, 1) for 0 <= A <= 1
-        D[ey * FOG_LS + FOG_PAD(ex)] = d;
+    // All global loads of the tile are issued up front, back to back (the kernel runs 4 warps per scheduler, too
+    // few to hide a load that is consumed right away): the haloed extinction values, and the tile's own image
+    // bytes, which wait in shared memory for the compose step at the very end.
+    {
+        constexpr int EL = (FOG_EH * FOG_EW + FOG_THREADS - 1) / FOG_THREADS;
+        constexpr int BL = FOG_TY * FOG_TX * 3 / FOG_THREADS;               // 24 bytes per thread
+        float ev[EL];
+        uint8_t bv[BL];
+#pragma unroll
+        for (int k = 0; k < EL; k++) {
+            int i = tid + k * FOG_THREADS;
+            int ey = i / FOG_EW, ex = i - ey * FOG_EW;
+            int gy = r101(y0 + ey - FOG_R, H), gx = r101(x0 + ex - FOG_R, W);
+            ev[k] = (i < FOG_EH * FOG_EW && gy >= 0 && gy < H && gx >= 0 && gx < W) ? fext[(size_t)gy * W + gx] : 0.f;    // k_fext
+        }
+        if (!b.bgf) {
+#pragma unroll
+            for (int k = 0; k < BL; k++) {
+                int j = tid + k * FOG_THREADS;
+                int row = j / (FOG_TX * 3), col = j - row * (FOG_TX * 3);
+                bv[k] = (y0 + row < H && x0 * 3 + col < W * 3) ? bgr[((size_t)(y0 + row) * W + x0) * 3 + col] : (uint8_t)0;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < EL; k++) {
+            int i = tid + k * FOG_THREADS;
+            if (i < FOG_EH * FOG_EW) {
+                int ey = i / FOG_EW, ex = i - ey * FOG_EW;
+                float v = ev[k];
+                E[ey * FOG_ES + FOG_PAD(ex)] = v;
+                double d = (double)(1.0f - v);                              // (1 - f_ext) is a float32 op in numpy (:71)
+                if (linear) d = d < 0 ? 0 : (d > 1 ? 1 : d);                // clip(A d, 0, 1) = A clip(d, 0, 1) for 0 <= A <= 1
+                D[ey * FOG_LS + FOG_PAD(ex)] = d;
+            }
+        }
+        if (!b.bgf) {
+#pragma unroll
+            for (int k = 0; k < BL; k++) IB[tid + k * FOG_THREADS] = bv[k];
+        }
     }
     __syncthreads();
     // float32 row pass of f_ext: 4 outputs per task
@@ -447,7 +478,7 @@ __global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, 
                 if (gy < H && gx < W) {
                     size_t pix = (size_t)gy * W + gx;
                     for (int cc = linear ? 0 : c; cc < (linear ? 3 : c + 1); cc++) {
-                        double I = b.bgf ? b.bgf[((size_t)f * 3 + cc) * W * H + pix] : rr_u8_unit(bgr[pix * 3 + cc]);   // generator.py:352-355
+                        double I = b.bgf ? b.bgf[((size_t)f * 3 + cc) * W * H + pix] : rr_u8_unit(IB[((cy0 + o) * FOG_TX + cx) * 3 + cc]);   // generator.py:352-355
                         double lin_in = linear ? Acs[cc] * acc : acc;
                         double l = I * (double)fb[o] + lin_in;               // :85
                         l = l < 0 ? 0 : (l > 1 ? 1 : l);
@@ -463,7 +494,7 @@ __global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, 
 cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, cudaStream_t st) {
     static_assert(FOG_ES >= FOG_PAD(FOG_EW - 1) + 1 && FOG_LS >= FOG_PAD(FOG_EW - 1) + 1 && FOG_FS >= FOG_PAD(FOG_TX - 1) + 1, "fog strides");
     static_assert(sizeof(double) * FOG_EH * FOG_FS <= FOG_BYTES_A, "LH must fit in the E + FH region");
-    size_t smem = FOG_BYTES_A + FOG_BYTES_B;
+    size_t smem = FOG_BYTES_A + FOG_BYTES_B + FOG_TY * FOG_TX * 3;
     {
         size_t n = (size_t)F * W * H;
         k_fext<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.depth, b.fext, fc.neg_beta32, n);
@@ -764,34 +795,53 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32, SETUP_MINB) k_setup(rr_frame
         sx = warp_sum(sx); sy = warp_sum(sy); sY = warp_sum(sY); sw = warp_sum(sw);
     }
     if (lane == 0) {
-        rr_plan p;
-        memset(&p, 0, sizeof(p));
-        bool ok = m > 0 && rec.tex_idx < cam.n_tex;
-        if (ok) ok = rr_plan_patch(rec, cam, t.tex_h[rec.tex_idx], p);
+        // the geometric half of the plan was written by k_plan; add the photometry, or withdraw the streak
+        rr_plan &P = b.plans[s];
+        const bool ok = P.valid && m > 0;
         if (ok) {
-            p.tex_off = t.tex_off[rec.tex_idx];
             double omega_total = *t.omega_total;
             double fov_x = sx / sw, fov_y = sy / sw;                        // bad_weather.py:397
             double ambient = b.ambient[f] / omega_total;                    // :403-404
             double avg_fov_lum = sY / omega_total;                          // :407
             double drop_Y = 0.94 * avg_fov_lum + 0.06 * ambient;            // :408
-            p.fov_x = fov_x; p.fov_y = fov_y; p.drop_Y = drop_Y;
-            rr_tint(fov_x, fov_y, drop_Y, &p.kb, &p.kg, &p.kr);
+            P.fov_x = fov_x; P.fov_y = fov_y; P.drop_Y = drop_Y;
+            double kb, kg, kr;
+            rr_tint(fov_x, fov_y, drop_Y, &kb, &kg, &kr);
+            P.kb = kb; P.kg = kg; P.kr = kr;
         } else {
-            p.pw = p.ph = p.bw = p.bh = 0;
+            P.valid = 0;
+            P.pw = P.ph = P.bw = P.bh = 0;
+            b.sizes[s] = make_int4(0, 0, 0, 0);
+            b.boxes[s] = make_int4(0, 0, 0, 0);
         }
-        p.valid = ok ? 1 : 0;
-        b.plans[s] = p;
-        long long g_, v_, a_; int vx0_, vw_;
-        plan_sizes(p, &g_, &v_, &a_, &vx0_, &vw_);
-        b.sizes[s] = make_int4((int)g_, (int)v_, (int)a_, 0);
-        b.boxes[s] = a_ > 0 ? make_int4(p.bx0, p.by0, p.bw, p.bh) : make_int4(0, 0, 0, 0);
     }
+}
+
+// The geometric half of the plan (patch warp, defocus, placement: rr_plan_patch) needs nothing from the frame:
+// one THREAD per streak (it is a serial computation -- an 8x8 LU for Big drops, trigonometry for the others --
+// that would leave 31 lanes of k_setup's warp idle), before k_setup adds the photometry.
+__global__ void __launch_bounds__(128) k_plan(rr_frame_bufs b, rr_static_tabs t, rr_cam_dev cam, int n_streaks) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streaks) return;
+    const rr_streak_rec rec = b.streaks[s];
+    rr_plan p;
+    memset(&p, 0, sizeof(p));
+    bool ok = rec.tex_idx < cam.n_tex;
+    if (ok) ok = rr_plan_patch(rec, cam, t.tex_h[rec.tex_idx], p);
+    if (ok) p.tex_off = t.tex_off[rec.tex_idx];
+    else p.pw = p.ph = p.bw = p.bh = 0;
+    p.valid = ok ? 1 : 0;
+    b.plans[s] = p;
+    long long g_, v_, a_; int vx0_, vw_;
+    plan_sizes(p, &g_, &v_, &a_, &vx0_, &vw_);
+    b.sizes[s] = make_int4((int)g_, (int)v_, (int)a_, 0);
+    b.boxes[s] = a_ > 0 ? make_int4(p.bx0, p.by0, p.bw, p.bh) : make_int4(0, 0, 0, 0);
 }
 
 cudaError_t rr_launch_setup(const rr_frame_bufs &b, const rr_static_tabs &t, const rr_cam_dev &cam, int F, int n_streaks,
                             cudaStream_t st) {
     if (n_streaks == 0) return cudaSuccess;
+    k_plan<<<(n_streaks + 127) / 128, 128, 0, st>>>(b, t, cam, n_streaks);
     k_setup<<<(n_streaks + SETUP_WARPS - 1) / SETUP_WARPS, SETUP_WARPS * 32, 0, st>>>(b, t, cam, F, n_streaks);
     return cudaGetLastError();
 }
@@ -990,8 +1040,10 @@ __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs 
                 const int rb = (nH - s0) < RB ? (nH - s0) : RB;
                 __syncthreads();                     // tables ready / previous band's chain sums consumed
                 // cv::resizeArea_: buf[dx] = sum_k S[sx_k] * alpha_k (left to right) for every source row of the band ...
+                // consecutive threads take consecutive ROWS of the same patch column: their column ranges (and the
+                // part of them the slanted texture covers) nearly coincide, so a warp's loops run in step
                 for (int i = tid; i < rb * pw; i += RAS_THREADS) {
-                    const int r = i / pw, dx = i - r * pw;
+                    const int dx = i / rb, r = i - dx * rb;
                     const int sy = s0 + r;
                     const int yy = p.flip ? (nH - 1 - sy) : sy;
                     const int xr = rr_round((M1 * yy + M2) * AB_SCALE) + AB_SCALE / RR_INTER_TAB / 2;
@@ -1012,7 +1064,7 @@ __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs 
                         const int Y = (yr + bdx[c]) >> (10 - RR_INTER_BITS);
                         buf += ras_sample(tex, tw, th, lut, X, Y) * alpha;
                     }
-                    CB[i] = buf;
+                    CB[r * pw + dx] = buf;
                 }
                 __syncthreads();
                 // ... then sum[dx] (+)= beta * buf[dx], rows top to bottom; a patch pixel's rows may span bands
