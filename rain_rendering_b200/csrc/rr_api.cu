@@ -207,6 +207,7 @@ static int ensure_streak_cap(rr_context *c, int n, int n_sub = -1) {
         drain(c);
         int cap = n + n / 4 + 1024;
         CK(dev_alloc(c, &c->fb.plans, (size_t)cap));
+        CK(dev_alloc(c, &c->fb.fcp, (size_t)cap));
         CK(dev_alloc(c, &c->fb.sizes, (size_t)cap));
         CK(dev_alloc(c, &c->fb.boxes, (size_t)cap));
         CK(dev_alloc(c, &c->fb.scan, (size_t)(cap + 1 + RR_MAX_SUB) * 6));
@@ -297,8 +298,7 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
     CK(dev_alloc(c, &b.rowtot, F * He));
     CK(dev_alloc(c, &b.ambient, F));
     b.err_flag = nullptr;
-    size_t tiles = (size_t)((W + RR_TILE_W - 1) / RR_TILE_W) * ((H + RR_TILE_H - 1) / RR_TILE_H);
-    CK(dev_alloc(c, &b.tile_sum, F * (tiles > 256 ? tiles : 256)));     // also holds the 64x4 partial sums of k_downscale2
+    CK(dev_alloc(c, &b.tile_sum, F * rr_n_partials(W, H)));             // also holds the 64x4 partial sums of k_downscale2
     CK(dev_alloc(c, &b.frame_mean, F));
     CK(dev_alloc(c, &b.out_bgr, F * np * 3));
     CK(dev_alloc(c, &b.out_mask, F * np));
@@ -362,9 +362,9 @@ static int run_pipeline(rr_context *c, int F, int n_streaks, bool timed) {
     if (timed) CK(cudaEventRecord(c->ev[RR_T_EPILOGUE], st));
     CK(rr_launch_epilogue(b, F, W, H, st));
     if (timed) CK(cudaEventRecord(c->ev[RR_T_D2H], st));
-    // stats 2, extinction 1, fog 1, env map + prefix + ambient 3, plan + set-up 2, scan 1, raster + two blur passes 3,
+    // stats 2, extinction 1, fog 1, env map + prefix + ambient 3, plan + set-up 2, scan 1, raster + blur 2,
     // composite + frame mean 2, epilogue 1
-    c->launches += 2 + 1 + 1 + 3 + (n_streaks ? 2 : 0) + 1 + (n_streaks ? 3 : 0) + 2 + 1;
+    c->launches += 2 + 1 + 1 + 3 + (n_streaks ? 2 : 0) + 1 + (n_streaks ? 2 : 0) + 2 + 1;
     c->last_n_streaks = n_streaks;
     return RR_OK;
 }
@@ -373,7 +373,7 @@ static int run_pipeline(rr_context *c, int F, int n_streaks, bool timed) {
 static rr_frame_bufs sub_view(const rr_context *c, const rr_frame_bufs &b, int f0, int s0, long long scan_base) {
     rr_frame_bufs v = b;
     const size_t np = (size_t)c->cam.W * c->cam.H, npe = (size_t)c->H_env * c->W_env;
-    const size_t tiles = (size_t)((c->cam.W + RR_TILE_W - 1) / RR_TILE_W) * ((c->cam.H + RR_TILE_H - 1) / RR_TILE_H);
+    const size_t tiles = rr_n_partials(c->cam.W, c->cam.H);
     const int rs2 = c->cam.render_scale == 2 ? 4 : 1;
     v.bgr += (size_t)f0 * np * 3 * rs2; v.depth += (size_t)f0 * np; v.streaks += s0;
     if (v.bgf) v.bgf += (size_t)f0 * 3 * np;
@@ -381,7 +381,7 @@ static rr_frame_bufs sub_view(const rr_context *c, const rr_frame_bufs &b, int f
     v.chan_sum += (size_t)f0 * 4; v.rainy += (size_t)f0 * 3 * np; v.bg8 += (size_t)f0 * np * 3; v.fblur += (size_t)f0 * np; v.fext += (size_t)f0 * np;
     v.env8 += (size_t)f0 * npe * 3;
     v.pref += (size_t)f0 * 4 * c->H_env * (c->W_env + 1); v.rowtot += (size_t)f0 * c->H_env; v.ambient += f0;
-    v.plans += s0; v.sizes += s0; v.boxes += s0; v.scan += (size_t)scan_base * 6;
+    v.plans += s0; v.fcp += s0; v.sizes += s0; v.boxes += s0; v.scan += (size_t)scan_base * 6;
     v.tile_sum += (size_t)f0 * tiles; v.frame_mean += f0;
     if (v.out_bgr) v.out_bgr += (size_t)f0 * np * 3;
     if (v.out_mask) v.out_mask += (size_t)f0 * np;

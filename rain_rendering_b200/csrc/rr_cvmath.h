@@ -93,7 +93,7 @@ RR_HD void rr_env_xyY(double bb, double gg, double rr, double *x, double *y, dou
 
 // texture fetch: streak textures are uint8 gray; the reference divides by 255.0
 // (common/bad_weather.py:252) before every resampling call.
-RR_HD double rr_tex(const uint8_t *tex, int tw, int x, int y) { return (double)tex[y * tw + x] / 255.0; }
+RR_HD double rr_tex(const uint8_t *tex, int tw, int x, int y) { return rr_u8_unit(tex[y * tw + x]); }
 
 // ---------------------------------------------------------------------------------------
 // OpenCV interpolation tables (imgwarp.cpp: interpolateCubic / initInterTab2D), float
@@ -216,8 +216,8 @@ RR_HD double rr_warp_persp_cubic(const uint8_t *tex, int tw, int th, const doubl
         for (int i = 0; i < 4; i++) {
             const uint8_t *S = tex + (sy + i) * tw + sx;
             float w0 = wy[i] * wx[0], w1 = wy[i] * wx[1], w2 = wy[i] * wx[2], w3 = wy[i] * wx[3];
-            double r = ((double)S[0] / 255.0) * w0 + ((double)S[1] / 255.0) * w1 + ((double)S[2] / 255.0) * w2 +
-                       ((double)S[3] / 255.0) * w3;
+            double r = rr_u8_unit(S[0]) * w0 + rr_u8_unit(S[1]) * w1 + rr_u8_unit(S[2]) * w2 +
+                       rr_u8_unit(S[3]) * w3;
             sum = (i == 0) ? r : sum + r;
         }
         out = sum;
@@ -232,7 +232,7 @@ RR_HD double rr_warp_persp_cubic(const uint8_t *tex, int tw, int th, const doubl
                 int xj = sx + j;
                 if (xj < 0 || xj >= tw) continue;
                 float w = wy[i] * wx[j];
-                sum += ((double)tex[yi * tw + xj] / 255.0 - 0.0) * w;
+                sum += (rr_u8_unit(tex[yi * tw + xj]) - 0.0) * w;
             }
         }
         out = sum;
@@ -287,16 +287,16 @@ RR_HD double rr_warp_affine_linear(const uint8_t *tex, int tw, int th, const dou
     unsigned width1 = tw - 1 > 0 ? tw - 1 : 0, height1 = th - 1 > 0 ? th - 1 : 0;
     if ((unsigned)sx < width1 && (unsigned)sy < height1) {
         const uint8_t *S = tex + sy * tw + sx;
-        return ((double)S[0] / 255.0) * w0 + ((double)S[1] / 255.0) * w1 + ((double)S[tw] / 255.0) * w2 +
-               ((double)S[tw + 1] / 255.0) * w3;
+        return rr_u8_unit(S[0]) * w0 + rr_u8_unit(S[1]) * w1 + rr_u8_unit(S[tw]) * w2 +
+               rr_u8_unit(S[tw + 1]) * w3;
     }
     if (sx >= tw || sx + 1 < 0 || sy >= th || sy + 1 < 0) return 0.0;
     bool x0ok = sx >= 0 && sx < tw, x1ok = sx + 1 >= 0 && sx + 1 < tw;
     bool y0ok = sy >= 0 && sy < th, y1ok = sy + 1 >= 0 && sy + 1 < th;
-    double v0 = (x0ok && y0ok) ? (double)tex[sy * tw + sx] / 255.0 : 0.0;
-    double v1 = (x1ok && y0ok) ? (double)tex[sy * tw + sx + 1] / 255.0 : 0.0;
-    double v2 = (x0ok && y1ok) ? (double)tex[(sy + 1) * tw + sx] / 255.0 : 0.0;
-    double v3 = (x1ok && y1ok) ? (double)tex[(sy + 1) * tw + sx + 1] / 255.0 : 0.0;
+    double v0 = (x0ok && y0ok) ? rr_u8_unit(tex[sy * tw + sx]) : 0.0;
+    double v1 = (x1ok && y0ok) ? rr_u8_unit(tex[sy * tw + sx + 1]) : 0.0;
+    double v2 = (x0ok && y1ok) ? rr_u8_unit(tex[(sy + 1) * tw + sx]) : 0.0;
+    double v3 = (x1ok && y1ok) ? rr_u8_unit(tex[(sy + 1) * tw + sx + 1]) : 0.0;
     return v0 * w0 + v1 * w1 + v2 * w2 + v3 * w3;
 }
 
@@ -383,13 +383,17 @@ RR_HD rr_area_span rr_area_tab(int d, double scale, int ssize) {
     int sx1 = rr_ceil(fsx1), sx2 = rr_floor(fsx2);
     sx2 = sx2 < ssize - 1 ? sx2 : ssize - 1;
     sx1 = sx1 < sx2 ? sx1 : sx2;
+    // the partial-pixel weights are divided out only when they exist: a double division with a zero numerator
+    // leaves the GPU's inline fast path for a ~70-instruction subroutine
     t.has_first = (sx1 - fsx1 > 1e-3);
-    t.a_first = t.has_first ? (float)((sx1 - fsx1) / cellWidth) : 0.f;
+    t.a_first = 0.f;
+    if (t.has_first) t.a_first = (float)((sx1 - fsx1) / cellWidth);
     t.s_first = sx1;
     t.n = sx2 - sx1 > 0 ? sx2 - sx1 : 0;
     t.a_mid = (float)(1.0 / cellWidth);
     t.has_last = (fsx2 - sx2 > 1e-3);
-    t.a_last = t.has_last ? (float)(rr_mind(rr_mind(fsx2 - sx2, 1.), cellWidth) / cellWidth) : 0.f;
+    t.a_last = 0.f;
+    if (t.has_last) t.a_last = (float)(rr_mind(rr_mind(fsx2 - sx2, 1.), cellWidth) / cellWidth);
     return t;
 }
 
@@ -507,7 +511,9 @@ struct rr_fcp {
     int ne;
     int ex0[RR_MAX_POLY], ey0[RR_MAX_POLY], ex1[RR_MAX_POLY], ey1[RR_MAX_POLY];
     int W, H;
+    int pad_[2];             // sizeof is a multiple of 16: the struct travels between kernels as int4 words
 };
+static_assert(sizeof(rr_fcp) % 16 == 0, "rr_fcp is copied as int4");
 
 // cv::clipLine(Size, pt1, pt2) on int64 coordinates; returns false when fully outside
 RR_HD bool rr_clip_line(int W, int H, int64_t &x1, int64_t &y1, int64_t &x2, int64_t &y2) {

@@ -245,7 +245,7 @@ __global__ void __launch_bounds__(256) k_downscale2(const uint8_t *bgr, double *
         double v[3];
 #pragma unroll
         for (int c = 0; c < 3; c++) {
-            double a = (double)p00[c] / 255.0, bq = (double)p00[3 + c] / 255.0, cq = (double)p10[c] / 255.0, d = (double)p10[3 + c] / 255.0;
+            double a = rr_u8_unit(p00[c]), bq = rr_u8_unit(p00[3 + c]), cq = rr_u8_unit(p10[c]), d = rr_u8_unit(p10[3 + c]);
             double sum = ((a + bq) + cq) + d;
             v[c] = sum * 0.25f;
             bgf[((size_t)f * 3 + c) * np + i] = v[c];
@@ -739,13 +739,13 @@ struct rr_plan;
 __device__ __forceinline__ void plan_sizes(const rr_plan &p, long long *g, long long *v, long long *a, int *vx0, int *vw);
 #define SETUP_WARPS 4
 #ifndef SETUP_MINB
-#define SETUP_MINB 8          // 64 registers: the lane-0 serial sections are latency bound, more resident warps win (sweep r01h)
+#define SETUP_MINB 8          // 64 registers: latency bound, more resident warps win (sweep r01h)
 #endif
+// One warp per streak: the prepared polygon walker (k_plan) is copied into shared memory, the 32 lanes take the
+// rows of the mask, merge the scan span with the Bresenham outline runs, and read pref[hi+1]-pref[lo].
 __global__ void __launch_bounds__(SETUP_WARPS * 32, SETUP_MINB) k_setup(rr_frame_bufs b, rr_static_tabs t, rr_cam_dev cam, int F,
                                                              int n_streaks) {
-    __shared__ rr_fcp s_fcp[SETUP_WARPS];
-    __shared__ int s_npts[SETUP_WARPS];
-    __shared__ double s_az[SETUP_WARPS][RR_FOV_N], s_px[SETUP_WARPS][RR_MAX_POLY], s_py[SETUP_WARPS][RR_MAX_POLY];
+    __shared__ __align__(16) rr_fcp s_fcp[SETUP_WARPS];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int s = blockIdx.x * SETUP_WARPS + warp;
     if (s >= n_streaks) return;
@@ -753,29 +753,15 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32, SETUP_MINB) k_setup(rr_frame
     int lo = 0, hi = F;
     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (b.offsets[mid] <= s) lo = mid; else hi = mid; }
     const int f = lo;
-    const rr_streak_rec rec = b.streaks[s];
     rr_fcp &fc = s_fcp[warp];
-    const int rows = cam.H_env, cols = cam.W_env;
     {
-        // the 20 rays of the view cone, one per lane
-        rr_fov_ctx fctx;
-        rr_fov_begin(rec, cam.fov_deg, fctx);
-        double az = 0, rx = 0, ry = 0;
-        bool ok = fctx.ok;
-        if (lane < RR_FOV_N) ok = rr_fov_ray(fctx, lane, cam.radius, rows, cols, &az, &rx, &ry) && ok;
-        if (lane < RR_FOV_N) { s_az[warp][lane] = az; s_px[warp][lane] = rx; s_py[warp][lane] = ry; }
-        unsigned good = __ballot_sync(0xffffffffu, ok || lane >= RR_FOV_N);
-        __syncwarp();
-        if (lane == 0) {
-            int n = good == 0xffffffffu ? rr_fov_finish(s_az[warp], s_px[warp], s_py[warp], rows, cols) : 0;
-            int m = n > 0 ? rr_clip_fov_polygon(s_px[warp], s_py[warp], n, cols, rows, fc.vx, fc.vy) : 0;
-            fc.npts = m;
-            if (m > 0) rr_fcp_prepare(fc, cols, rows);
-            s_npts[warp] = m;
-        }
+        const int4 *src = (const int4 *)(b.fcp + s);
+        int4 *dst = (int4 *)&fc;
+        for (int i = lane; i < (int)(sizeof(rr_fcp) / sizeof(int4)); i += 32) dst[i] = src[i];
     }
     __syncwarp();
-    int m = s_npts[warp];
+    const int rows = cam.H_env, cols = cam.W_env;
+    const int m = fc.npts;
     double sx = 0, sy = 0, sY = 0, sw = 0;
     if (m > 0) {
         int ymin = 0x7fffffff, ymax = -0x7fffffff;
@@ -817,9 +803,12 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32, SETUP_MINB) k_setup(rr_frame
     }
 }
 
-// The geometric half of the plan (patch warp, defocus, placement: rr_plan_patch) needs nothing from the frame:
-// one THREAD per streak (it is a serial computation -- an 8x8 LU for Big drops, trigonometry for the others --
-// that would leave 31 lanes of k_setup's warp idle), before k_setup adds the photometry.
+// Everything about a streak that needs nothing from the frame, one THREAD per streak (serial computations that would
+// leave 31 lanes of k_setup's warp idle):
+//   * the geometric half of the plan (patch warp, defocus, placement: rr_plan_patch -- an 8x8 LU for Big drops,
+//     trigonometry for the others)
+//   * the field-of-view polygon: 20 cone rays -> lat-long vertices, wrap splice, Clipper restatement, and the
+//     prepared cv::fillConvexPoly walker (bad_weather.py:596-704, 363-373, 388), left in global memory for k_setup
 __global__ void __launch_bounds__(128) k_plan(rr_frame_bufs b, rr_static_tabs t, rr_cam_dev cam, int n_streaks) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_streaks) return;
@@ -836,6 +825,22 @@ __global__ void __launch_bounds__(128) k_plan(rr_frame_bufs b, rr_static_tabs t,
     plan_sizes(p, &g_, &v_, &a_, &vx0_, &vw_);
     b.sizes[s] = make_int4((int)g_, (int)v_, (int)a_, 0);
     b.boxes[s] = a_ > 0 ? make_int4(p.bx0, p.by0, p.bw, p.bh) : make_int4(0, 0, 0, 0);
+    // field-of-view mask
+    __align__(16) rr_fcp fc;
+    memset(&fc, 0, sizeof(fc));
+    if (ok) {
+        const int rows = cam.H_env, cols = cam.W_env;
+        double px[RR_MAX_POLY], py[RR_MAX_POLY];
+        const int npoly = rr_fov_polygon(rec, cam.radius, cam.fov_deg, rows, cols, px, py);
+        const int m = npoly > 0 ? rr_clip_fov_polygon(px, py, npoly, cols, rows, fc.vx, fc.vy) : 0;
+        fc.npts = m;
+        if (m > 0) rr_fcp_prepare(fc, cols, rows);
+    }
+    {
+        const int4 *src = (const int4 *)&fc;
+        int4 *dst = (int4 *)(b.fcp + s);
+        for (int i = 0; i < (int)(sizeof(rr_fcp) / sizeof(int4)); i++) dst[i] = src[i];
+    }
 }
 
 cudaError_t rr_launch_setup(const rr_frame_bufs &b, const rr_static_tabs &t, const rr_cam_dev &cam, int F, int n_streaks,
@@ -849,7 +854,7 @@ cudaError_t rr_launch_setup(const rr_frame_bufs &b, const rr_static_tabs &t, con
 // ------------------------------------------------------------------------------------------
 // arena layout + work lists: exclusive scans over the streaks (single block, deterministic)
 //   scan[i*6 + 0..2]: element offsets of g (pre-blur patch), v (column-pass result), a (blurred alpha block)
-//   scan[i*6 + 3..5]: chunk prefix of the raster, column-pass and row-pass kernels
+//   scan[n*6]: total elements (read back by the host when the arena overflows)
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void blur_extents(const rr_plan &p, int *vx0, int *vw);
 // arena elements of one streak: g (pre-blur patch), v (column pass), a (visible blurred block)
@@ -870,77 +875,52 @@ __device__ __forceinline__ void blur_extents(const rr_plan &p, int *vx0, int *vw
 }
 
 __global__ void __launch_bounds__(1024) k_scan(rr_frame_bufs b, int n) {
-    // one block: per-thread chunk totals, a shuffle scan over the 1024 threads, then the chunk prefixes.
+    // one block: per-thread totals, a shuffle scan over the 1024 threads, then the per-streak offsets.
     // Integer sums: exact and order independent.
-    __shared__ long long wtot[32][4];
-    __shared__ long long grand[4];
+    __shared__ long long wtot[32];
+    __shared__ long long grand;
     __shared__ int overflow;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int per = (n + 1023) / 1024;
     const int i0 = tid * per, i1 = i0 + per < n ? i0 + per : n;
-    long long t[4] = {0, 0, 0, 0};
+    long long t = 0;
     for (int i = i0; i < i1; i++) {
         int4 sz = b.sizes[i];
-        long long g = sz.x, v = sz.y, a = sz.z;
-        t[0] += g + v + a;
-        t[1] += (g + RR_RASTER_CHUNK - 1) / RR_RASTER_CHUNK;
-        t[2] += (v + RR_BLUR_CHUNK - 1) / RR_BLUR_CHUNK;
-        t[3] += (a + RR_BLUR_CHUNK - 1) / RR_BLUR_CHUNK;
+        t += (long long)sz.x + sz.y + sz.z;
     }
-    long long inc[4], exc[4];
+    long long inc = t;
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
-        long long v = t[q];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { long long u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-        inc[q] = v;
-        if (lane == 31) wtot[warp][q] = v;
-    }
+    for (int o = 1; o < 32; o <<= 1) { long long u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+    if (lane == 31) wtot[warp] = inc;
     __syncthreads();
     if (warp == 0) {
+        long long v = wtot[lane], w = v;
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            long long v = wtot[lane][q], w = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { long long u = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += u; }
-            wtot[lane][q] = w - v;                       // exclusive prefix of the warp totals
-            if (lane == 31) grand[q] = w;
-        }
+        for (int o = 1; o < 32; o <<= 1) { long long u = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += u; }
+        wtot[lane] = w - v;                          // exclusive prefix of the warp totals
+        if (lane == 31) grand = w;
     }
     __syncthreads();
     if (tid == 0) {
-        overflow = grand[0] > b.arena_cap;
+        overflow = grand > b.arena_cap;
         if (overflow) *b.err_flag = 1;                   // nothing is rendered: the host grows the arena and re-runs
-        long long *sc = b.scan + (size_t)n * 6;
-        sc[0] = grand[0]; sc[3] = overflow ? 0 : grand[1]; sc[4] = overflow ? 0 : grand[2]; sc[5] = overflow ? 0 : grand[3];
+        b.scan[(size_t)n * 6] = grand;
     }
     __syncthreads();
-#pragma unroll
-    for (int q = 0; q < 4; q++) exc[q] = wtot[warp][q] + inc[q] - t[q];
-    long long el = exc[0], c0 = exc[1], c1 = exc[2], c2 = exc[3];
+    long long el = wtot[warp] + inc - t;
     for (int i = i0; i < i1; i++) {
         int4 sz = b.sizes[i];
         long long g = sz.x, v = sz.y, a = sz.z;
-        if (overflow) { b.plans[i].valid = 0; b.boxes[i] = make_int4(0, 0, 0, 0); }
+        if (overflow) { b.plans[i].valid = 0; b.plans[i].bw = b.plans[i].bh = 0; b.boxes[i] = make_int4(0, 0, 0, 0); }
         long long *sc = b.scan + (size_t)i * 6;
-        sc[0] = el; sc[1] = el + g; sc[2] = el + g + v; sc[3] = c0; sc[4] = c1; sc[5] = c2;
+        sc[0] = el; sc[1] = el + g; sc[2] = el + g + v;
         el += g + v + a;
-        c0 += (g + RR_RASTER_CHUNK - 1) / RR_RASTER_CHUNK;
-        c1 += (v + RR_BLUR_CHUNK - 1) / RR_BLUR_CHUNK;
-        c2 += (a + RR_BLUR_CHUNK - 1) / RR_BLUR_CHUNK;
     }
 }
 
 cudaError_t rr_launch_scan(const rr_frame_bufs &b, int n_streaks, cudaStream_t st) {
     k_scan<<<1, 1024, 0, st>>>(b, n_streaks);
     return cudaGetLastError();
-}
-
-// chunk -> streak: largest i with scan[i*6 + field] <= chunk
-__device__ __forceinline__ int find_streak(const long long *scan, int n, int field, long long chunk) {
-    int lo = 0, hi = n;
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (scan[(size_t)mid * 6 + field] <= chunk) lo = mid; else hi = mid; }
-    return lo;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1176,85 +1156,67 @@ cudaError_t rr_launch_raster(const rr_frame_bufs &b, const rr_static_tabs &t, co
 // colour channels equal alpha * k_c (tint of a gray texture), so blur(colour_c) = k_c * blur(alpha)
 // up to float64 rounding (DESIGN.md "linear tint").
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_weights(double sigma, int r, double *w) {
-    // rr_gauss_weights (SciPy _gaussian_kernel1d) with the exponentials spread over the block; the
-    // normalising sum keeps numpy's order.  All threads of the block call this; w in shared memory.
-    __shared__ double s_norm;
-    const int n = 2 * r + 1;
-    const double f = -0.5 / (sigma * sigma);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) w[i] = exp(f * (double)((i - r) * (i - r)));
-    __syncthreads();
-    if (threadIdx.x == 0) s_norm = rr_np_sum_small(w, n);
-    __syncthreads();
-    const double sn = s_norm;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) w[i] = w[i] / sn;
-    __syncthreads();
-}
-
-// chunk -> streak lookup done once per block
-__device__ __forceinline__ int find_streak_block(const long long *scan, int n, int field, long long chunk) {
-    __shared__ int s_idx;
-    __syncthreads();
-    if (threadIdx.x == 0) s_idx = find_streak(scan, n, field, chunk);
-    __syncthreads();
-    return s_idx;
-}
-
-__global__ void __launch_bounds__(RR_BLUR_THREADS) k_blur_v(rr_frame_bufs b, int n) {
-    __shared__ double w[2 * RR_MAX_GAUSS_R + 1];
-    const long long total = b.scan[(size_t)n * 6 + 4];
-    for (long long ch = blockIdx.x; ch < total; ch += gridDim.x) {
-        const int s = find_streak_block(b.scan, n, 4, ch);
+// One CTA per streak (persistent, strided): both passes of the streak back to back, its two weight tables built
+// once.  The column-pass result goes through the arena (written and read by the same CTA, a barrier in between).
+#define BLUR_THREADS 128
+__global__ void __launch_bounds__(BLUR_THREADS) k_blur(rr_frame_bufs b, int n) {
+    __shared__ double wy[2 * RR_MAX_GAUSS_R + 1], wx[2 * RR_MAX_GAUSS_R + 1];
+    __shared__ double s_norm[2];
+    const int tid = threadIdx.x;
+    for (int s = blockIdx.x; s < n; s += gridDim.x) {
         const rr_plan &p = b.plans[s];
-        load_weights(p.sig_y, p.ry, w);
-        long long gg, nv, aa; int vx0, vw;
-        plan_sizes(p, &gg, &nv, &aa, &vx0, &vw);
-        const int base = (int)((ch - b.scan[(size_t)s * 6 + 4]) * RR_BLUR_CHUNK);
-        const int pw = p.pw, ph = p.ph, ry = p.ry, cropy = p.cropy, shift = p.shift;
+        long long gg, nv, na; int vx0, vw;
+        plan_sizes(p, &gg, &nv, &na, &vx0, &vw);
+        if (na == 0) continue;                                   // block-uniform
+        const int pw = p.pw, ph = p.ph, ry = p.ry, rx = p.rx, cropy = p.cropy, cropx = p.cropx, shift = p.shift, bw = p.bw;
+        // rr_gauss_weights (SciPy _gaussian_kernel1d) for both axes, the exponentials spread over the block; the
+        // normalising sums keep numpy's order (one thread each, in different warps)
+        {
+            const int ny = 2 * ry + 1, nx = 2 * rx + 1;
+            const double fy = -0.5 / (p.sig_y * p.sig_y), fx = -0.5 / (p.sig_x * p.sig_x);
+            __syncthreads();                                     // previous streak done with the tables
+            for (int i = tid; i < ny; i += BLUR_THREADS) wy[i] = ry > 0 ? exp(fy * (double)((i - ry) * (i - ry))) : 1.0;
+            for (int i = tid; i < nx; i += BLUR_THREADS) wx[i] = rx > 0 ? exp(fx * (double)((i - rx) * (i - rx))) : 1.0;
+            __syncthreads();
+            if (tid == 0) s_norm[0] = rr_np_sum_small(wy, ny);
+            if (tid == 32) s_norm[1] = rr_np_sum_small(wx, nx);
+            __syncthreads();
+            const double sy = s_norm[0], sx = s_norm[1];
+            for (int i = tid; i < ny; i += BLUR_THREADS) wy[i] = wy[i] / sy;
+            for (int i = tid; i < nx; i += BLUR_THREADS) wx[i] = wx[i] / sx;
+            __syncthreads();
+        }
         const double *g = b.arena + b.scan[(size_t)s * 6 + 0];
-        double *vout = b.arena + b.scan[(size_t)s * 6 + 1];
-        for (int e = base + threadIdx.x; e < base + RR_BLUR_CHUNK && e < (int)nv; e += RR_BLUR_THREADS) {
+        double *v = b.arena + b.scan[(size_t)s * 6 + 1];
+        double *aout = b.arena + b.scan[(size_t)s * 6 + 2];
+        // column pass (axis 0, sigma c): SciPy correlate1d, symmetric weights: centre first, then pairs from the outside in
+        for (int e = tid; e < (int)nv; e += BLUR_THREADS) {
             int yy = e / vw, xx = e - yy * vw;
             int gx = vx0 + xx - shift;       // patch column
             int gy = cropy + yy - shift;     // patch row of the centre tap (may be outside: zero padding)
-            // SciPy correlate1d, symmetric weights: centre first, then pairs from the outside in
             double c = (gy >= 0 && gy < ph) ? g[gy * pw + gx] : 0.0;
-            double tmp = c * w[ry];
+            double tmp = c * wy[ry];
             for (int jj = -ry; jj < 0; jj++) {
                 int ya = gy + jj, yb = gy - jj;
                 double va = (ya >= 0 && ya < ph) ? g[ya * pw + gx] : 0.0;
                 double vb = (yb >= 0 && yb < ph) ? g[yb * pw + gx] : 0.0;
-                tmp += (va + vb) * w[jj + ry];
+                tmp += (va + vb) * wy[jj + ry];
             }
-            vout[e] = tmp;
+            v[e] = tmp;
         }
-    }
-}
-
-__global__ void __launch_bounds__(RR_BLUR_THREADS) k_blur_h(rr_frame_bufs b, int n) {
-    __shared__ double w[2 * RR_MAX_GAUSS_R + 1];
-    const long long total = b.scan[(size_t)n * 6 + 5];
-    for (long long ch = blockIdx.x; ch < total; ch += gridDim.x) {
-        const int s = find_streak_block(b.scan, n, 5, ch);
-        const rr_plan &p = b.plans[s];
-        load_weights(p.sig_x, p.rx, w);
-        long long gg, vv, na; int vx0, vw;
-        plan_sizes(p, &gg, &vv, &na, &vx0, &vw);
-        const int base = (int)((ch - b.scan[(size_t)s * 6 + 5]) * RR_BLUR_CHUNK);
-        const int bw = p.bw, rx = p.rx, cropx = p.cropx;
-        const double *vin = b.arena + b.scan[(size_t)s * 6 + 1];
-        double *aout = b.arena + b.scan[(size_t)s * 6 + 2];
-        for (int e = base + threadIdx.x; e < base + RR_BLUR_CHUNK && e < (int)na; e += RR_BLUR_THREADS) {
+        __syncthreads();                                         // the CTA's own global writes are visible to it after the barrier
+        // row pass (axis 1, sigma c / 2) over the visible block only
+        for (int e = tid; e < (int)na; e += BLUR_THREADS) {
             int yy = e / bw, xx = e - yy * bw;
-            const double *v = vin + yy * vw;
+            const double *vr = v + yy * vw;
             int xc = cropx + xx - vx0;        // column of the centre tap in the column-pass result
-            double c = (xc >= 0 && xc < vw) ? v[xc] : 0.0;
-            double tmp = c * w[rx];
+            double c = (xc >= 0 && xc < vw) ? vr[xc] : 0.0;
+            double tmp = c * wx[rx];
             for (int jj = -rx; jj < 0; jj++) {
                 int xa = xc + jj, xb = xc - jj;
-                double va = (xa >= 0 && xa < vw) ? v[xa] : 0.0;
-                double vb = (xb >= 0 && xb < vw) ? v[xb] : 0.0;
-                tmp += (va + vb) * w[jj + rx];
+                double va = (xa >= 0 && xa < vw) ? vr[xa] : 0.0;
+                double vb = (xb >= 0 && xb < vw) ? vr[xb] : 0.0;
+                tmp += (va + vb) * wx[jj + rx];
             }
             aout[e] = tmp;
         }
@@ -1263,8 +1225,9 @@ __global__ void __launch_bounds__(RR_BLUR_THREADS) k_blur_h(rr_frame_bufs b, int
 
 cudaError_t rr_launch_blur(const rr_frame_bufs &b, int n_streaks, int n_sm, cudaStream_t st) {
     if (n_streaks == 0) return cudaSuccess;
-    k_blur_v<<<n_sm * 8, RR_BLUR_THREADS, 0, st>>>(b, n_streaks);
-    k_blur_h<<<n_sm * 8, RR_BLUR_THREADS, 0, st>>>(b, n_streaks);
+    int grid = n_sm * 16;
+    if (grid > n_streaks) grid = n_streaks;
+    k_blur<<<grid, BLUR_THREADS, 0, st>>>(b, n_streaks);
     return cudaGetLastError();
 }
 
@@ -1272,98 +1235,131 @@ cudaError_t rr_launch_blur(const rr_frame_bufs &b, int n_streaks, int n_sm, cuda
 // ordered compositing  (bad_weather.py:429-460): the blend is streak-order dependent, so each
 // pixel walks the streaks that cover its tile in record (XML) order.  No atomics.
 // ------------------------------------------------------------------------------------------
-struct comp_entry { int bx0, by0, bw, bh; long long a_off; double kb, kg, kr, tau_one, c_scale; };
-
-#define COMP_THREADS (RR_TILE_W * RR_TILE_H)
-#define COMP_WARPS (COMP_THREADS / 32)
-__global__ void __launch_bounds__(RR_TILE_W * RR_TILE_H) k_composite(rr_frame_bufs b, rr_cam_dev cam, int tiles_x, int tiles_y) {
-    __shared__ comp_entry list[COMP_THREADS];
-    __shared__ int s_count;
-    __shared__ int warp_cnt[COMP_WARPS];
-    __shared__ double red[COMP_WARPS];
+// A CTA owns a region of 32 x (RR_COMP_WARPS * RR_COMP_PY) pixels, each warp a strip of 32 x RR_COMP_PY of it (a lane
+// = one column).  Two stages per round of COMP_ROUND streaks: (1) every thread tests two streak boxes against the
+// REGION and the hits are compacted, in record order, into a shared list (one barrier pair per round; a frame of
+// the headline workload is one round); (2) each warp walks the list 32 entries at a time, tests them against its
+// own strip, and applies the hits in ballot order = record order.
+#define COMP_THREADS (RR_COMP_WARPS * 32)
+#define COMP_ROUND (2 * COMP_THREADS)
+#ifndef RR_COMP_MINB
+#define RR_COMP_MINB 4         // sweep r01h: (rows per lane, CTAs per SM) (2,4) 0.558 ms, (4,4) 0.560, (4,3) 0.583, (4,2) 0.673, (8,2) 0.767
+#endif
+__global__ void __launch_bounds__(COMP_THREADS, RR_COMP_MINB) k_composite(rr_frame_bufs b, rr_cam_dev cam, int tiles_x, int n_partials) {
+    __shared__ int4 s_box[COMP_ROUND];
+    __shared__ int s_idx[COMP_ROUND];
+    __shared__ int s_wcnt[2][RR_COMP_WARPS];
     const int f = blockIdx.z;
     const int W = cam.W, H = cam.H;
-    const int tx0 = blockIdx.x * RR_TILE_W, ty0 = blockIdx.y * RR_TILE_H;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int x = tx0 + (tid % RR_TILE_W), y = ty0 + (tid / RR_TILE_W);
-    const bool inside = x < W && y < H;
-    const size_t npix = (size_t)W * H, pix = (size_t)y * W + x;
-    double vb = 0, vg = 0, vr = 0, mask = 0;
-    if (inside) {
-        vb = b.rainy[((size_t)f * 3 + 0) * npix + pix];
-        vg = b.rainy[((size_t)f * 3 + 1) * npix + pix];
-        vr = b.rainy[((size_t)f * 3 + 2) * npix + pix];
+    const int tx0 = blockIdx.x * 32, x = tx0 + lane;
+    const int ry0 = blockIdx.y * (RR_COMP_WARPS * RR_COMP_PY);           // region rows [ry0, ry0 + RR_COMP_WARPS * RR_COMP_PY)
+    const int strip = blockIdx.y * RR_COMP_WARPS + warp, y0 = strip * RR_COMP_PY;
+    const size_t npix = (size_t)W * H;
+    double vb[RR_COMP_PY], vg[RR_COMP_PY], vr[RR_COMP_PY], mask[RR_COMP_PY];
+    bool touched[RR_COMP_PY];
+    double *rb = b.rainy + ((size_t)f * 3 + 0) * npix, *rg = rb + npix, *rr = rg + npix;
+#pragma unroll
+    for (int k = 0; k < RR_COMP_PY; k++) {
+        const bool inside = x < W && y0 + k < H;
+        const size_t pix = (size_t)(y0 + k) * W + x;
+        vb[k] = inside ? rb[pix] : 0.0; vg[k] = inside ? rg[pix] : 0.0; vr[k] = inside ? rr[pix] : 0.0;
+        mask[k] = 0; touched[k] = false;
     }
     const int s0 = b.offsets[f], s1 = b.offsets[f + 1];
     const double exposure = cam.exposure_blend;
-    for (int base = s0; base < s1; base += COMP_THREADS) {
-        int s = base + tid;
-        bool hit = false;
-        const rr_plan *pp = b.plans + (s < s1 ? s : s0);
-        int pbx0 = 0, pby0 = 0, pbw = 0, pbh = 0;
-        if (s < s1) {
-            int4 box = b.boxes[s];                       // (bx0, by0, bw, bh), bw = 0 for streaks that draw nothing
-            pbx0 = box.x; pby0 = box.y; pbw = box.z; pbh = box.w;
-            hit = pbw > 0 && pbh > 0 && pbx0 < tx0 + RR_TILE_W && pbx0 + pbw > tx0 &&
-                  pby0 < ty0 + RR_TILE_H && pby0 + pbh > ty0;
+    for (int base = s0; base < s1; base += COMP_ROUND) {
+        // ---- stage 1: region hits of this round, compacted in record order ----
+        int4 box[2];
+        unsigned bal[2];
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const int s = base + h * COMP_THREADS + tid;
+            box[h] = make_int4(0, 0, 0, 0);
+            if (s < s1) box[h] = b.boxes[s];                // (bx0, by0, bw, bh), bw = 0 for streaks that draw nothing
+            const bool hit = box[h].z > 0 && box[h].w > 0 && box[h].x < tx0 + 32 && box[h].x + box[h].z > tx0 &&
+                             box[h].y < ry0 + RR_COMP_WARPS * RR_COMP_PY && box[h].y + box[h].w > ry0;
+            bal[h] = __ballot_sync(0xffffffffu, hit);
+            if (lane == 0) s_wcnt[h][warp] = __popc(bal[h]);
         }
-        unsigned bal = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) warp_cnt[warp] = __popc(bal);
         __syncthreads();
-        int pre = 0;
-        for (int k = 0; k < warp; k++) pre += warp_cnt[k];
-        if (hit) {
-            int slot = pre + __popc(bal & ((1u << lane) - 1));
-            comp_entry e;
-            e.bx0 = pbx0; e.by0 = pby0; e.bw = pbw; e.bh = pbh; e.a_off = b.scan[(size_t)s * 6 + 2];
-            e.kb = pp->kb; e.kg = pp->kg; e.kr = pp->kr; e.tau_one = pp->a_scale; e.c_scale = pp->c_scale;
-            list[slot] = e;
-        }
-        if (tid == 0) { int c = 0; for (int k = 0; k < COMP_WARPS; k++) c += warp_cnt[k]; s_count = c; }
-        __syncthreads();
-        int cnt = s_count;
-        if (inside) {
-            for (int k = 0; k < cnt; k++) {
-                const comp_entry &e = list[k];
-                int lx = x - e.bx0, ly = y - e.by0;
-                if (lx >= 0 && lx < e.bw && ly >= 0 && ly < e.bh) {
-                    double a = b.arena[e.a_off + (size_t)ly * e.bw + lx];
-                    double keep = 1. - ((a * e.tau_one) / exposure);                 // bad_weather.py:443
-                    double nb = (keep * vb) + (e.kb * a) * e.c_scale;
-                    double ng = (keep * vg) + (e.kg * a) * e.c_scale;
-                    double nr = (keep * vr) + (e.kr * a) * e.c_scale;
-                    vb = nb < 0 ? 0 : (nb > 1 ? 1 : nb);                             // :446
-                    vg = ng < 0 ? 0 : (ng > 1 ? 1 : ng);
-                    vr = nr < 0 ? 0 : (nr > 1 ? 1 : nr);
-                    mask += a;                                                       // :450
-                }
+        int total = 0;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            int pre = total;
+#pragma unroll
+            for (int k = 0; k < RR_COMP_WARPS; k++) {
+                const int c = s_wcnt[h][k];
+                if (k < warp) pre += c;
+                total += c;
+            }
+            if (bal[h] & (1u << lane)) {
+                const int slot = pre + __popc(bal[h] & ((1u << lane) - 1));
+                s_box[slot] = box[h];
+                s_idx[slot] = base + h * COMP_THREADS + tid;
             }
         }
         __syncthreads();
+        // ---- stage 2: this warp's strip ----
+        if (y0 < H) {
+            for (int j0 = 0; j0 < total; j0 += 32) {
+                const int j = j0 + lane;
+                int4 bx = make_int4(0, 0, 0, 0);
+                if (j < total) bx = s_box[j];
+                const bool hit = j < total && bx.y < y0 + RR_COMP_PY && bx.y + bx.w > y0;
+                unsigned hb = __ballot_sync(0xffffffffu, hit);
+                while (hb) {
+                    const int k = __ffs(hb) - 1;
+                    hb &= hb - 1;
+                    const int sk = s_idx[j0 + k];
+                    const int bx0 = __shfl_sync(0xffffffffu, bx.x, k), by0 = __shfl_sync(0xffffffffu, bx.y, k);
+                    const int bw = __shfl_sync(0xffffffffu, bx.z, k), bh = __shfl_sync(0xffffffffu, bx.w, k);
+                    const rr_plan *pp = b.plans + sk;        // same address in every lane: one broadcast transaction
+                    const double kb = pp->kb, kg = pp->kg, kr = pp->kr, tau_one = pp->a_scale, c_scale = pp->c_scale;
+                    const double *A = b.arena + b.scan[(size_t)sk * 6 + 2];
+                    const int lx = x - bx0;
+#pragma unroll
+                    for (int q = 0; q < RR_COMP_PY; q++) {
+                        const int ly = y0 + q - by0;
+                        if (lx >= 0 && lx < bw && ly >= 0 && ly < bh && x < W) {
+                            const double a = A[(size_t)ly * bw + lx];
+                            if (a == 0.0) continue;          // keep = 1, colour + 0, mask + 0: bit for bit a no-op
+                            const double keep = 1. - ((a * tau_one) / exposure);         // bad_weather.py:443
+                            const double nb = (keep * vb[q]) + (kb * a) * c_scale;
+                            const double ng = (keep * vg[q]) + (kg * a) * c_scale;
+                            const double nr = (keep * vr[q]) + (kr * a) * c_scale;
+                            vb[q] = nb < 0 ? 0 : (nb > 1 ? 1 : nb);                      // :446
+                            vg[q] = ng < 0 ? 0 : (ng > 1 ? 1 : ng);
+                            vr[q] = nr < 0 ? 0 : (nr > 1 ? 1 : nr);
+                            mask[q] += a;                                                // :450
+                            touched[q] = true;
+                        }
+                    }
+                }
+            }
+        }
+        if (base + COMP_ROUND < s1) __syncthreads();         // the lists are rewritten by the next round
     }
     double part = 0;
-    if (inside) {
-        b.rainy[((size_t)f * 3 + 0) * npix + pix] = vb;
-        b.rainy[((size_t)f * 3 + 1) * npix + pix] = vg;
-        b.rainy[((size_t)f * 3 + 2) * npix + pix] = vr;
-        if (b.out_mask) b.out_mask[(size_t)f * npix + pix] = (float)mask;
-        part = (vb + vg) + vr;
+#pragma unroll
+    for (int k = 0; k < RR_COMP_PY; k++) {
+        const bool inside = x < W && y0 + k < H;
+        if (inside) {
+            const size_t pix = (size_t)(y0 + k) * W + x;
+            if (touched[k]) { rb[pix] = vb[k]; rg[pix] = vg[k]; rr[pix] = vr[k]; }       // untouched pixels keep the fogged value
+            if (b.out_mask) b.out_mask[(size_t)f * npix + pix] = (float)mask[k];
+            part += (vb[k] + vg[k]) + vr[k];
+        }
     }
     part = warp_sum(part);
-    if (lane == 0) red[warp] = part;
-    __syncthreads();
-    if (tid == 0) {
-        double t = 0;
-        for (int k = 0; k < COMP_WARPS; k++) t += red[k];
-        b.tile_sum[(size_t)f * tiles_x * tiles_y + (size_t)blockIdx.y * tiles_x + blockIdx.x] = t;
-    }
+    if (lane == 0) b.tile_sum[(size_t)f * n_partials + (size_t)strip * tiles_x + blockIdx.x] = part;
 }
 
-__global__ void k_frame_mean(rr_frame_bufs b, int n_tiles, double npix3) {
+__global__ void k_frame_mean(rr_frame_bufs b, int n_tiles, int stride, double npix3) {
     int f = blockIdx.x;
     __shared__ double sh[256];
     double s = 0;
-    for (int i = threadIdx.x; i < n_tiles; i += 256) s += b.tile_sum[(size_t)f * n_tiles + i];
+    for (int i = threadIdx.x; i < n_tiles; i += 256) s += b.tile_sum[(size_t)f * stride + i];
     sh[threadIdx.x] = s;
     __syncthreads();
     for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
@@ -1376,10 +1372,11 @@ __global__ void k_frame_mean(rr_frame_bufs b, int n_tiles, double npix3) {
 }
 
 cudaError_t rr_launch_composite(const rr_frame_bufs &b, const rr_cam_dev &cam, int F, cudaStream_t st) {
-    int tiles_x = (cam.W + RR_TILE_W - 1) / RR_TILE_W, tiles_y = (cam.H + RR_TILE_H - 1) / RR_TILE_H;
-    dim3 grid(tiles_x, tiles_y, F);
-    k_composite<<<grid, RR_TILE_W * RR_TILE_H, 0, st>>>(b, cam, tiles_x, tiles_y);
-    k_frame_mean<<<F, 256, 0, st>>>(b, tiles_x * tiles_y, 3.0 * cam.W * cam.H);
+    const int tiles_x = (cam.W + 31) / 32, ctas_y = (cam.H + RR_COMP_PY * RR_COMP_WARPS - 1) / (RR_COMP_PY * RR_COMP_WARPS);
+    const int n_partials = (int)rr_n_partials(cam.W, cam.H);
+    dim3 grid(tiles_x, ctas_y, F);
+    k_composite<<<grid, RR_COMP_WARPS * 32, 0, st>>>(b, cam, tiles_x, n_partials);
+    k_frame_mean<<<F, 256, 0, st>>>(b, tiles_x * ctas_y * RR_COMP_WARPS, n_partials, 3.0 * cam.W * cam.H);
     return cudaGetLastError();
 }
 

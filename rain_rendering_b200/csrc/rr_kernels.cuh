@@ -23,13 +23,14 @@ struct rr_frame_bufs {
     double *rowtot;            // [F][H] row totals of omega*Y
     double *ambient;           // [F] sum over the map of omega*Y
     rr_plan *plans;            // [n_streaks]
+    rr_fcp *fcp;               // [n_streaks] prepared field-of-view polygon walkers (k_plan -> k_setup)
     int4 *boxes;               // [n_streaks] (bx0, by0, bw, bh) of the composited block, zeros when nothing is drawn (k_scan)
     int4 *sizes;               // [n_streaks] arena elements (g, v, a) of each streak, written by k_setup for k_scan
-    long long *scan;           // [n_streaks+1][4] exclusive prefix: g elems, a elems, raster chunks, blur chunks
+    long long *scan;           // [n_streaks+1][6] arena element offsets of g, v, a per streak (3 slots spare); [n][0] = total
     double *arena;             // patch arena
     long long arena_cap;       // elements
     int *err_flag;             // device error flag (arena overflow)
-    double *tile_sum;          // [F][n_tiles] partial sums of the composited image
+    double *tile_sum;          // [F][rr_n_partials] partial sums of the composited image, one per compositor strip
     double *frame_mean;        // [F] mean(rainy_bg) - mean(bg)
     // outputs (device)
     float *out_bgr;            // [F][H][W][3]
@@ -55,17 +56,17 @@ struct rr_fog_consts {
     double beta_hg;
 };
 
-#define RR_RASTER_CHUNK 128
-#ifndef RR_BLUR_CHUNK
-#define RR_BLUR_CHUNK 512        // elements per work-list chunk, 4 per thread (sweep r01h: 1024/256 thr 0.58 ms, 512/128 thr 0.41 ms)
+// compositor: a warp owns a strip of 32 x RR_COMP_PY pixels, RR_COMP_WARPS strips (stacked) per CTA
+#ifndef RR_COMP_PY
+#define RR_COMP_PY 2
 #endif
-#ifndef RR_BLUR_THREADS
-#define RR_BLUR_THREADS 128
-#endif
-#define RR_TILE_W 32
-#ifndef RR_TILE_H
-#define RR_TILE_H 8
-#endif
+#define RR_COMP_WARPS 8
+// per-frame partial sums of the composited image, one per strip (also scratch of k_downscale2: at least 256)
+static inline size_t rr_n_partials(int W, int H) {
+    size_t strips = (size_t)((H + RR_COMP_PY * RR_COMP_WARPS - 1) / (RR_COMP_PY * RR_COMP_WARPS)) * RR_COMP_WARPS;
+    size_t n = (size_t)((W + 31) / 32) * strips;
+    return n > 256 ? n : 256;
+}
 
 cudaError_t rr_upload_constants();
 // init-time tables
