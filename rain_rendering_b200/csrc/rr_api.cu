@@ -57,6 +57,9 @@ struct rr_context {
     int last_n_streaks = 0;
     // copy/compute overlap inside rr_render_frames (pinned host buffers): sub-batches on three streams
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    // k_plan (per-streak geometry, needs only the records) runs beside the frame stages of the same (sub-)batch
+    cudaStream_t s_plan = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_in[RR_MAX_SUB], ev_done[RR_MAX_SUB], ev_d2h[RR_MAX_SUB], ev_out;
     int32_t *d_sub_offsets = nullptr;    // [RR_MAX_SUB][max_batch + 1]
     long long scan_base[RR_MAX_SUB];     // element index (in units of 6 long long) of each sub-batch's scan block
@@ -86,7 +89,7 @@ static cudaError_t dev_alloc(rr_context *c, T **p, size_t count) {
 }
 
 static void free_camera(rr_context *c) {
-    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_d2h); }
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_d2h); cudaStreamSynchronize(c->s_plan); }
     c->inflight = 0; c->parity = 0; c->sub_cap = 0;
     if (c->h_sub_off) { cudaFreeHost(c->h_sub_off); c->h_sub_off = nullptr; }
     for (void *p : c->owned) cudaFree(p);
@@ -125,6 +128,9 @@ int rr_create(int device_id, rr_context **out) {
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->s_plan, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (int i = 0; i < RR_MAX_SUB; i++) {
         CK(cudaEventCreateWithFlags(&c->ev_in[i], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
@@ -152,6 +158,9 @@ int rr_destroy(rr_context *c) {
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->s_h2d);
     cudaStreamDestroy(c->s_d2h);
+    cudaStreamSynchronize(c->s_plan);
+    cudaStreamDestroy(c->s_plan);
+    cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
     for (int i = 0; i < RR_MAX_SUB; i++) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_done[i]); cudaEventDestroy(c->ev_d2h[i]); }
     for (int i = 0; i < 2; i++) cudaEventDestroy(c->ev_call[i]);
     if (c->h_sub_off) cudaFreeHost(c->h_sub_off);
@@ -197,7 +206,7 @@ int rr_streak_db_device_ptr(rr_context *c, void **dev_ptr, size_t *bytes) {
 }
 
 static void drain(rr_context *c) {
-    cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_d2h);
+    cudaStreamSynchronize(c->s_h2d); cudaStreamSynchronize(c->s_plan); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_d2h);
 }
 
 // n: records of the whole batch (plans / sizes / boxes / scan); n_sub: records of the largest sub-batch slot
@@ -290,10 +299,10 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
     c->d_bgf = nullptr;
     if (rs == 2) CK(dev_alloc(c, &c->d_bgf, F * 3 * np));
     CK(dev_alloc(c, &b.rainy, F * 3 * np));
-    CK(dev_alloc(c, &b.bg8, F * np * 3));
+    CK(dev_alloc(c, &b.bg8, F * np * 4));
     CK(dev_alloc(c, &b.fext, F * np));
     CK(dev_alloc(c, &b.fblur, F * np));
-    CK(dev_alloc(c, &b.env8, F * npe * 3));
+    CK(dev_alloc(c, &b.env8, F * npe * 4));
     CK(dev_alloc(c, &b.pref, F * 4 * (size_t)He * (We + 1)));
     CK(dev_alloc(c, &b.rowtot, F * He));
     CK(dev_alloc(c, &b.ambient, F));
@@ -345,12 +354,19 @@ static int run_pipeline(rr_context *c, int F, int n_streaks, bool timed) {
     const int W = c->cam.W, H = c->cam.H;
     c->camd.db_width = c->db_width; c->camd.n_tex = c->n_tex;
     if (timed) CK(cudaEventRecord(c->ev[RR_T_FOG], st));
+    // fork: everything this (sub-)batch depends on has been enqueued on st (inputs landed, the previous user of the plan /
+    // walker buffers is done); the geometry kernel runs on its own stream and joins before the photometry
+    CK(cudaEventRecord(c->ev_fork, st));
+    CK(cudaStreamWaitEvent(c->s_plan, c->ev_fork, 0));
+    CK(rr_launch_plan(b, t, c->camd, n_streaks, c->s_plan));
+    CK(cudaEventRecord(c->ev_join, c->s_plan));
     const int rs = c->cam.render_scale == 2 ? 2 : 1;
     CK(rr_launch_stats(b, F, W, H, rs, (double *)b.bgf, st));
     CK(rr_launch_fog(b, c->fogc, F, W, H, st));
     if (timed) CK(cudaEventRecord(c->ev[RR_T_ENV], st));
     CK(rr_launch_env(b, t, F, W, H, c->W_env, st));
     if (timed) CK(cudaEventRecord(c->ev[RR_T_SETUP], st));
+    CK(cudaStreamWaitEvent(st, c->ev_join, 0));
     CK(rr_launch_setup(b, t, c->camd, F, n_streaks, st));
     CK(rr_launch_scan(b, n_streaks, st));
     if (timed) CK(cudaEventRecord(c->ev[RR_T_RASTER], st));
@@ -378,8 +394,8 @@ static rr_frame_bufs sub_view(const rr_context *c, const rr_frame_bufs &b, int f
     v.bgr += (size_t)f0 * np * 3 * rs2; v.depth += (size_t)f0 * np; v.streaks += s0;
     if (v.bgf) v.bgf += (size_t)f0 * 3 * np;
     v.bg_sum += (size_t)f0 * 4;
-    v.chan_sum += (size_t)f0 * 4; v.rainy += (size_t)f0 * 3 * np; v.bg8 += (size_t)f0 * np * 3; v.fblur += (size_t)f0 * np; v.fext += (size_t)f0 * np;
-    v.env8 += (size_t)f0 * npe * 3;
+    v.chan_sum += (size_t)f0 * 4; v.rainy += (size_t)f0 * 3 * np; v.bg8 += (size_t)f0 * np * 4; v.fblur += (size_t)f0 * np; v.fext += (size_t)f0 * np;
+    v.env8 += (size_t)f0 * npe * 4;
     v.pref += (size_t)f0 * 4 * c->H_env * (c->W_env + 1); v.rowtot += (size_t)f0 * c->H_env; v.ambient += f0;
     v.plans += s0; v.fcp += s0; v.sizes += s0; v.boxes += s0; v.scan += (size_t)scan_base * 6;
     v.tile_sum += (size_t)f0 * tiles; v.frame_mean += f0;
@@ -661,8 +677,10 @@ int rr_envmap_only(rr_context *c, int n_frames, const double *planar, uint8_t *o
     CK(rr_launch_planar_to_bg8(b.rainy, b.bg8, n_frames, c->cam.W, c->cam.H, st));
     CK(rr_launch_env(b, tabs_of(c), n_frames, c->cam.W, c->cam.H, c->W_env, st));
     c->launches += 4;
-    CK(cudaMemcpyAsync(out_env, b.env8, F * npe * 3, cudaMemcpyDeviceToHost, st));
+    std::vector<uint8_t> tmp(F * npe * 4);                     // the device keeps (B, G, R, 0) words
+    CK(cudaMemcpyAsync(tmp.data(), b.env8, F * npe * 4, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < F * npe; i++) { out_env[3 * i] = tmp[4 * i]; out_env[3 * i + 1] = tmp[4 * i + 1]; out_env[3 * i + 2] = tmp[4 * i + 2]; }
     return RR_OK;
 }
 
@@ -679,7 +697,9 @@ int rr_streak_photometry_only(rr_context *c, const uint8_t *env_bgr_u8, int n_st
     const size_t npe = (size_t)c->H_env * c->W_env;
     cudaStream_t st = c->stream;
     rr_frame_bufs &b = c->fb;
-    CK(cudaMemcpyAsync(b.env8, env_bgr_u8, npe * 3, cudaMemcpyHostToDevice, st));
+    std::vector<uint8_t> env4(npe * 4, 0);                     // the device keeps (B, G, R, 0) words
+    for (size_t i = 0; i < npe; i++) { env4[4 * i] = env_bgr_u8[3 * i]; env4[4 * i + 1] = env_bgr_u8[3 * i + 1]; env4[4 * i + 2] = env_bgr_u8[3 * i + 2]; }
+    CK(cudaMemcpyAsync(b.env8, env4.data(), npe * 4, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->d_streaks, streaks, (size_t)n_streaks * sizeof(rr_streak_rec), cudaMemcpyHostToDevice, st));
     int32_t off[2] = {0, n_streaks};
     CK(cudaMemcpyAsync(c->d_offsets, off, sizeof(off), cudaMemcpyHostToDevice, st));
@@ -688,6 +708,7 @@ int rr_streak_photometry_only(rr_context *c, const uint8_t *env_bgr_u8, int n_st
     // prefix sums of the given map, then the per-streak set-up
     CK(rr_launch_env_prefix_only(b, t, 1, c->H_env, c->W_env, st));
     c->camd.db_width = c->db_width; c->camd.n_tex = c->n_tex;
+    CK(rr_launch_plan(b, t, c->camd, n_streaks, st));
     CK(rr_launch_setup(b, t, c->camd, 1, n_streaks, st));
     c->launches += 4;
     std::vector<rr_plan> plans(n_streaks);
@@ -729,7 +750,14 @@ int rr_debug_read(rr_context *c, int what, int frame, void *dst, size_t bytes) {
     switch (what) {
         case RR_DBG_FOG_F64:
         case RR_DBG_RAINY_F64: src = b.rainy + (size_t)frame * 3 * np; avail = 3 * np * sizeof(double); break;
-        case RR_DBG_ENV_U8: src = b.env8 + (size_t)frame * npe * 3; avail = npe * 3; break;
+        case RR_DBG_ENV_U8: {                                  // device words (B, G, R, 0) -> packed BGR for the caller
+            std::vector<uint8_t> tmp(npe * 4);
+            CK(cudaStreamSynchronize(c->stream));
+            CK(cudaMemcpy(tmp.data(), b.env8 + (size_t)frame * npe * 4, npe * 4, cudaMemcpyDeviceToHost));
+            uint8_t *o = (uint8_t *)dst;
+            for (size_t i = 0; i < npe && 3 * i + 2 < bytes; i++) { o[3 * i] = tmp[4 * i]; o[3 * i + 1] = tmp[4 * i + 1]; o[3 * i + 2] = tmp[4 * i + 2]; }
+            return RR_OK;
+        }
         case RR_DBG_OMEGA: src = c->d_omega; avail = npe * sizeof(double); break;
         case RR_DBG_PLANS: src = b.plans; avail = sizeof(rr_plan) * (size_t)c->last_n_streaks; break;
         case RR_DBG_ENV_SRC: src = c->d_env_src; avail = npe * sizeof(int32_t); break;

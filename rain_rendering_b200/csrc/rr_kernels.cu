@@ -444,7 +444,10 @@ __global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, 
     for (int c = 0; c < npass; c++) {
         const double Ac = Acs[c];
         __syncthreads();            // E and FH consumed (first pass) / LH of the previous channel consumed
-        // float64 row pass, cv::RowFilter order: k[0]*x[0] + k[1]*x[1] + ...
+        // float64 row pass, cv::RowFilter order: s = k[0]*x[0]; s += k[t]*x[t] ... -- OpenCV's AVX2-dispatched build of that
+        // scalar loop is contracted to fused multiply-adds by its compiler (measured: the FMA chain reproduces
+        // cv2.sepFilter2D bit for bit on float64, the separate multiply-add does not), so the chain is fused here too.
+        // The column filter (SymmColumnFilter) is not contracted in that build and stays multiply + add.
         for (int i = tid; i < FOG_EH * (FOG_TX / 4); i += FOG_THREADS) {
             int ey = i / (FOG_TX / 4), ox = (i - ey * (FOG_TX / 4)) * 4;
             const double *row = D + ey * FOG_LS + FOG_PAD(ox);
@@ -459,7 +462,7 @@ __global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, 
             for (int o = 0; o < 4; o++) {
                 double a = c_k64[0] * v[o];
 #pragma unroll
-                for (int t = 1; t < 25; t++) a += c_k64[t] * v[o + t];
+                for (int t = 1; t < 25; t++) a = __fma_rn(c_k64[t], v[o + t], a);
                 LH[ey * FOG_FS + FOG_PAD(ox) + o] = a;
             }
         }
@@ -477,14 +480,18 @@ __global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, 
                 int gy = y0 + cy0 + o, gx = x0 + cx;
                 if (gy < H && gx < W) {
                     size_t pix = (size_t)gy * W + gx;
+                    unsigned packed = 0;
                     for (int cc = linear ? 0 : c; cc < (linear ? 3 : c + 1); cc++) {
                         double I = b.bgf ? b.bgf[((size_t)f * 3 + cc) * W * H + pix] : rr_u8_unit(IB[((cy0 + o) * FOG_TX + cx) * 3 + cc]);   // generator.py:352-355
                         double lin_in = linear ? Acs[cc] * acc : acc;
                         double l = I * (double)fb[o] + lin_in;               // :85
                         l = l < 0 ? 0 : (l > 1 ? 1 : l);
                         b.rainy[((size_t)f * 3 + cc) * W * H + pix] = l;
-                        b.bg8[((size_t)f * W * H + pix) * 3 + cc] = (uint8_t)(l * 255);   // bad_weather.py:744
+                        const unsigned q = (unsigned)(uint8_t)(l * 255);     // bad_weather.py:744
+                        if (linear) packed |= q << (8 * cc);
+                        else b.bg8[((size_t)f * W * H + pix) * 4 + cc] = (uint8_t)q;
                     }
+                    if (linear) ((unsigned *)b.bg8)[(size_t)f * W * H + pix] = packed;
                 }
             }
         }
@@ -515,7 +522,9 @@ __global__ void k_planar_to_bg8(const double *planar, uint8_t *bg8, int npix, in
     if (i >= (size_t)F * npix) return;
     int f = (int)(i / npix);
     size_t pix = i - (size_t)f * npix;
-    for (int c = 0; c < 3; c++) bg8[i * 3 + c] = (uint8_t)(planar[((size_t)f * 3 + c) * npix + pix] * 255);
+    unsigned packed = 0;
+    for (int c = 0; c < 3; c++) packed |= (unsigned)(uint8_t)(planar[((size_t)f * 3 + c) * npix + pix] * 255) << (8 * c);
+    ((unsigned *)bg8)[i] = packed;
 }
 
 cudaError_t rr_launch_planar_to_bg8(const double *planar, uint8_t *bg8, int F, int W, int H, cudaStream_t st) {
@@ -532,14 +541,16 @@ cudaError_t rr_launch_planar_to_bg8(const double *planar, uint8_t *bg8, int F, i
 #define ENV_R 7
 // Gather through the static source-index table and, for the never-written pixels, OpenCV's fixed-point
 // 15x15 Gaussian of the gathered map (bad_weather.py:814-817), in one pass: tiles without holes are a pure gather.
+// Pixels travel as one 32-bit word (B, G, R, 0): one load and one store per pixel instead of three each.
 __global__ void __launch_bounds__(256) k_env_map(const uint8_t *bg8, const int32_t *env_src, const uint8_t *env_written, uint8_t *env8,
                                                  int H, int W_env, int npix_img) {
-    __shared__ uint8_t in[ENV_TY + 2 * ENV_R][ENV_TX + 2 * ENV_R][3];
+    __shared__ unsigned in[ENV_TY + 2 * ENV_R][ENV_TX + 2 * ENV_R];
     __shared__ unsigned short hp[ENV_TY + 2 * ENV_R][ENV_TX][3];
     __shared__ int any_hole;
     const int f = blockIdx.z;
     const int x0 = blockIdx.x * ENV_TX, y0 = blockIdx.y * ENV_TY;
-    const uint8_t *img = bg8 + (size_t)f * npix_img * 3;
+    const unsigned *img = (const unsigned *)bg8 + (size_t)f * npix_img;
+    unsigned *out = (unsigned *)env8 + (size_t)f * H * W_env;
     if (threadIdx.x == 0) any_hole = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < ENV_TX * ENV_TY; i += 256) {
@@ -552,12 +563,12 @@ __global__ void __launch_bounds__(256) k_env_map(const uint8_t *bg8, const int32
         for (int i = threadIdx.x; i < (ENV_TY + 2 * ENV_R) * (ENV_TX + 2 * ENV_R); i += 256) {
             int ey = i / (ENV_TX + 2 * ENV_R), ex = i - ey * (ENV_TX + 2 * ENV_R);
             int gy = r101(y0 + ey - ENV_R, H), gx = r101(x0 + ex - ENV_R, W_env);
-            uint8_t v0 = 0, v1 = 0, v2 = 0;
+            unsigned v = 0;
             if (gy >= 0 && gy < H && gx >= 0 && gx < W_env) {
                 int sidx = env_src[(size_t)gy * W_env + gx];
-                if (sidx >= 0) { const uint8_t *p = img + (size_t)sidx * 3; v0 = p[0]; v1 = p[1]; v2 = p[2]; }
+                if (sidx >= 0) v = img[sidx];
             }
-            in[ey][ex][0] = v0; in[ey][ex][1] = v1; in[ey][ex][2] = v2;
+            in[ey][ex] = v;
         }
         __syncthreads();
         for (int i = threadIdx.x; i < (ENV_TY + 2 * ENV_R) * ENV_TX; i += 256) {
@@ -565,7 +576,8 @@ __global__ void __launch_bounds__(256) k_env_map(const uint8_t *bg8, const int32
             unsigned s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
             for (int t = 0; t < 15; t++) {
-                s0 += c_k15[t] * in[ey][ox + t][0]; s1 += c_k15[t] * in[ey][ox + t][1]; s2 += c_k15[t] * in[ey][ox + t][2];
+                const unsigned v = in[ey][ox + t];
+                s0 += c_k15[t] * (v & 255u); s1 += c_k15[t] * ((v >> 8) & 255u); s2 += c_k15[t] * ((v >> 16) & 255u);
             }
             hp[ey][ox][0] = (unsigned short)s0; hp[ey][ox][1] = (unsigned short)s1; hp[ey][ox][2] = (unsigned short)s2;
         }
@@ -576,14 +588,11 @@ __global__ void __launch_bounds__(256) k_env_map(const uint8_t *bg8, const int32
         int gy = y0 + oy, gx = x0 + ox;
         if (gy >= H || gx >= W_env) continue;
         size_t pix = (size_t)gy * W_env + gx;
-        uint8_t *o = env8 + ((size_t)f * H * W_env + pix) * 3;
         if (env_written[pix]) {
-            if (any_hole) { o[0] = in[oy + ENV_R][ox + ENV_R][0]; o[1] = in[oy + ENV_R][ox + ENV_R][1]; o[2] = in[oy + ENV_R][ox + ENV_R][2]; }
+            if (any_hole) out[pix] = in[oy + ENV_R][ox + ENV_R];
             else {
                 int sidx = env_src[pix];
-                uint8_t v0 = 0, v1 = 0, v2 = 0;
-                if (sidx >= 0) { const uint8_t *p = img + (size_t)sidx * 3; v0 = p[0]; v1 = p[1]; v2 = p[2]; }
-                o[0] = v0; o[1] = v1; o[2] = v2;
+                out[pix] = sidx >= 0 ? img[sidx] : 0u;
             }
         } else {
             unsigned s0 = 0, s1 = 0, s2 = 0;
@@ -591,7 +600,7 @@ __global__ void __launch_bounds__(256) k_env_map(const uint8_t *bg8, const int32
             for (int t = 0; t < 15; t++) {
                 s0 += c_k15[t] * hp[oy + t][ox][0]; s1 += c_k15[t] * hp[oy + t][ox][1]; s2 += c_k15[t] * hp[oy + t][ox][2];
             }
-            o[0] = (uint8_t)((s0 + 32768u) >> 16); o[1] = (uint8_t)((s1 + 32768u) >> 16); o[2] = (uint8_t)((s2 + 32768u) >> 16);
+            out[pix] = ((s0 + 32768u) >> 16) | (((s1 + 32768u) >> 16) << 8) | (((s2 + 32768u) >> 16) << 16);
         }
     }
 }
@@ -604,8 +613,8 @@ __global__ void __launch_bounds__(256) k_env_map(const uint8_t *bg8, const int32
 // (division-free xyY, rr_cvmath.h), keeps the running sums in registers (a serial prefix costs one add per
 // value instead of a five-step shuffle scan) and parks its local exclusive prefixes in shared memory; one
 // shuffle scan over the thread totals and the warp totals gives every thread its offset; the tile then
-// leaves shared memory as fully coalesced 16-byte stores.  The row bytes arrive the same way (16-byte
-// coalesced loads into shared memory, then each thread unpacks its 24 bytes).  Fixed tree: deterministic.
+// leaves shared memory as fully coalesced 16-byte stores.  The row's pixels (32-bit words) arrive the same way
+// (16-byte coalesced loads into shared memory, then each thread reads its 8 words).  Fixed tree: deterministic.
 #define EP_THREADS 128
 #define EP_PER 8
 #define EP_TILE (EP_THREADS * EP_PER)
@@ -615,56 +624,46 @@ __global__ void __launch_bounds__(256) k_env_map(const uint8_t *bg8, const int32
 #define EP_STAGE_BYTES (EP_TILE * 32 + EP_THREADS * 16)
 __global__ void __launch_bounds__(EP_THREADS) k_env_prefix(const uint8_t *env8, const double *omega, double *pref, double *rowtot,
                                                            int H, int W_env) {
-    __shared__ double lut[256];
-    __shared__ __align__(16) unsigned char s_bytes[EP_TILE * 3 + 32];
+    __shared__ __align__(16) unsigned char s_bytes[EP_TILE * 4 + 32];
     __shared__ __align__(16) unsigned char s_stage[EP_STAGE_BYTES];
     __shared__ __align__(16) double s_toff[EP_THREADS][4];
     __shared__ double s_wtot[EP_WARPS][4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < 256; i += EP_THREADS) lut[i] = (double)i / 255.0;
     const int r = blockIdx.x, f = blockIdx.y;
-    const uint8_t *row = env8 + ((size_t)f * H + r) * W_env * 3;
+    const uint8_t *row = env8 + ((size_t)f * H + r) * W_env * 4;          // pixels are 32-bit words (B, G, R, 0)
     const double *om = omega + (size_t)r * W_env;
     double2 *p2 = (double2 *)pref + ((size_t)f * H + r) * (W_env + 1) * 2;
     double cx = 0, cy = 0, cY = 0, cw = 0;          // carry: prefix of everything left of the tile
     for (int c0 = 0; c0 < W_env; c0 += EP_TILE) {
         const int n = (W_env - c0) < EP_TILE ? (W_env - c0) : EP_TILE;
         // ---- row bytes -> shared memory, 16 bytes per load (the buffers carry 256 bytes of slack) ----
-        const uint8_t *gsrc = row + (size_t)c0 * 3;
-        const int shift = (int)((size_t)gsrc & 15);
+        const uint8_t *gsrc = row + (size_t)c0 * 4;
+        const int shift = (int)((size_t)gsrc & 15);                        // a multiple of 4
         const uint4 *gal = (const uint4 *)(gsrc - shift);
-        const int nvec = (shift + n * 3 + 15) >> 4;
-        __syncthreads();                            // previous tile fully written out (s_stage, s_toff, s_bytes), lut ready
+        const int nvec = (shift + n * 4 + 15) >> 4;
+        // the thread's solid angles are requested now and consumed after the staging barrier
+        const int px0 = tid * EP_PER;
+        double wv[EP_PER];
+#pragma unroll
+        for (int k = 0; k < EP_PER; k++) wv[k] = (px0 + k < n) ? om[c0 + px0 + k] : 0.0;
+        __syncthreads();                            // previous tile fully written out (s_stage, s_toff, s_bytes)
         for (int i = tid; i < nvec; i += EP_THREADS) ((uint4 *)s_bytes)[i] = gal[i];
         __syncthreads();
         // ---- this thread's EP_PER consecutive pixels ----
-        const int px0 = tid * EP_PER;
-        unsigned wds[EP_PER * 3 / 4 + 1];
-        {
-            const int bo = shift + px0 * 3;         // (bo & 3) == (shift & 3) for every thread
-            const unsigned *sw = (const unsigned *)s_bytes + (bo >> 2);
-            const int sh = (bo & 3) * 8;
-            unsigned raw[EP_PER * 3 / 4 + 1];
-#pragma unroll
-            for (int k = 0; k < EP_PER * 3 / 4 + 1; k++) raw[k] = sw[k];
-#pragma unroll
-            for (int k = 0; k < EP_PER * 3 / 4; k++) wds[k] = __funnelshift_r(raw[k], raw[k + 1], sh);
-        }
+        const unsigned *wds = (const unsigned *)s_bytes + (shift >> 2) + px0;
         double sx = 0, sy = 0, sY = 0, sw_ = 0;
         unsigned char *st = s_stage + (size_t)tid * (EP_PER * 32 + 16);
 #pragma unroll
         for (int k = 0; k < EP_PER; k++) {
             ((double2 *)(st + k * 32))[0] = make_double2(sx, sy);
             ((double2 *)(st + k * 32))[1] = make_double2(sY, sw_);
-            const int c = c0 + px0 + k;
             if (px0 + k < n) {
-                const int b0 = 3 * k, b1 = 3 * k + 1, b2 = 3 * k + 2;
-                const double bb = lut[(wds[b0 >> 2] >> ((b0 & 3) * 8)) & 255u];
-                const double gg = lut[(wds[b1 >> 2] >> ((b1 & 3) * 8)) & 255u];
-                const double rr = lut[(wds[b2 >> 2] >> ((b2 & 3) * 8)) & 255u];
+                const unsigned pxw = wds[k];
+                const double bb = rr_u8_unit((uint8_t)(pxw & 255u)), gg = rr_u8_unit((uint8_t)((pxw >> 8) & 255u)),
+                             rr = rr_u8_unit((uint8_t)((pxw >> 16) & 255u));
                 double x, y, Y;
                 rr_env_xyY(bb, gg, rr, &x, &y, &Y);                 // my_utils.py:56-68, generator.py:408
-                const double w = om[c];
+                const double w = wv[k];
                 sx += x * w; sy += y * w; sY += Y * w; sw_ += w;
             }
         }
@@ -843,10 +842,15 @@ __global__ void __launch_bounds__(128) k_plan(rr_frame_bufs b, rr_static_tabs t,
     }
 }
 
+cudaError_t rr_launch_plan(const rr_frame_bufs &b, const rr_static_tabs &t, const rr_cam_dev &cam, int n_streaks, cudaStream_t st) {
+    if (n_streaks == 0) return cudaSuccess;
+    k_plan<<<(n_streaks + 127) / 128, 128, 0, st>>>(b, t, cam, n_streaks);
+    return cudaGetLastError();
+}
+
 cudaError_t rr_launch_setup(const rr_frame_bufs &b, const rr_static_tabs &t, const rr_cam_dev &cam, int F, int n_streaks,
                             cudaStream_t st) {
     if (n_streaks == 0) return cudaSuccess;
-    k_plan<<<(n_streaks + 127) / 128, 128, 0, st>>>(b, t, cam, n_streaks);
     k_setup<<<(n_streaks + SETUP_WARPS - 1) / SETUP_WARPS, SETUP_WARPS * 32, 0, st>>>(b, t, cam, F, n_streaks);
     return cudaGetLastError();
 }

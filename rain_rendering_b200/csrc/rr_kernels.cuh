@@ -15,10 +15,10 @@ struct rr_frame_bufs {
     // per-frame intermediates
     unsigned long long *chan_sum;  // [F][4]  sum of uint8 per channel (B,G,R), [3] unused
     double *rainy;             // [F][3][H][W] planar BGR float64
-    uint8_t *bg8;              // [F][H][W][3] floor(rainy*255)
+    uint8_t *bg8;              // [F][H][W][4] floor(rainy*255) as (B, G, R, 0): one 32-bit word per pixel
     float *fext;               // [F][H][W] extinction exp(-beta d), written by k_fext for k_fog
     float *fblur;              // [F][H][W] blurred extinction (debug / stage test)
-    uint8_t *env8;             // [F][H][W_env][3] final environment map
+    uint8_t *env8;             // [F][H][W_env][4] final environment map, (B, G, R, 0) words
     double *pref;              // [F][H][W_env+1][4] row prefix sums of (omega*x, omega*y, omega*Y, omega), interleaved
     double *rowtot;            // [F][H] row totals of omega*Y
     double *ambient;           // [F] sum over the map of omega*Y
@@ -77,6 +77,8 @@ cudaError_t rr_launch_omega(int H_env, int W_env, double *omega, double *omega_p
 cudaError_t rr_launch_stats(const rr_frame_bufs &b, int F, int W, int H, int render_scale, double *bgf_out, cudaStream_t st);
 cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, cudaStream_t st);
 cudaError_t rr_launch_env(const rr_frame_bufs &b, const rr_static_tabs &t, int F, int W, int H, int W_env, cudaStream_t st);
+// k_plan needs only the streak records: it may run on another stream while the frame stages (fog, environment map) run
+cudaError_t rr_launch_plan(const rr_frame_bufs &b, const rr_static_tabs &t, const rr_cam_dev &cam, int n_streaks, cudaStream_t st);
 cudaError_t rr_launch_setup(const rr_frame_bufs &b, const rr_static_tabs &t, const rr_cam_dev &cam, int F, int n_streaks,
                             cudaStream_t st);
 cudaError_t rr_launch_scan(const rr_frame_bufs &b, int n_streaks, cudaStream_t st);
