@@ -372,42 +372,69 @@ __global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, 
     const bool linear = Acs[0] >= 0 && Acs[0] <= 1 && Acs[1] >= 0 && Acs[1] <= 1 && Acs[2] >= 0 && Acs[2] <= 1;
     // All global loads of the tile are issued up front, back to back (the kernel runs 4 warps per scheduler, too
     // few to hide a load that is consumed right away): the haloed extinction values, and the tile's own image
-    // bytes, which wait in shared memory for the compose step at the very end.
+    // bytes, which wait in shared memory for the compose step at the very end.  A warp takes whole rows (the
+    // reflected row index is warp-uniform, the reflected column indices are formed once per lane), so an element
+    // costs a handful of instructions of index arithmetic.
     {
-        constexpr int EL = (FOG_EH * FOG_EW + FOG_THREADS - 1) / FOG_THREADS;
-        constexpr int BL = FOG_TY * FOG_TX * 3 / FOG_THREADS;               // 24 bytes per thread
-        float ev[EL];
-        uint8_t bv[BL];
+        constexpr int NW = FOG_THREADS / 32;                                // warps
+        constexpr int ER = (FOG_EH + NW - 1) / NW;                          // extinction rows per warp
+        constexpr int EC = (FOG_EW + 31) / 32;                              // column steps per row
+        constexpr int BR = FOG_TY / NW;                                     // image rows per warp
+        constexpr int BC = FOG_TX * 3 / 32;                                 // byte steps per image row
+        const int lane = tid & 31, warp = tid >> 5;
+        int gxs[EC], pex[EC];
 #pragma unroll
-        for (int k = 0; k < EL; k++) {
-            int i = tid + k * FOG_THREADS;
-            int ey = i / FOG_EW, ex = i - ey * FOG_EW;
-            int gy = r101(y0 + ey - FOG_R, H), gx = r101(x0 + ex - FOG_R, W);
-            ev[k] = (i < FOG_EH * FOG_EW && gy >= 0 && gy < H && gx >= 0 && gx < W) ? fext[(size_t)gy * W + gx] : 0.f;    // k_fext
+        for (int j = 0; j < EC; j++) {
+            const int ex = lane + 32 * j;
+            const int gx = r101(x0 + ex - FOG_R, W);
+            gxs[j] = (ex < FOG_EW && gx >= 0 && gx < W) ? gx : -1;
+            pex[j] = ex < FOG_EW ? FOG_PAD(ex) : -1;
+        }
+        float ev[ER][EC];
+        uint8_t bv[BR][BC];
+#pragma unroll
+        for (int q = 0; q < ER; q++) {
+            const int ey = warp + NW * q;
+            const int gy = r101(y0 + ey - FOG_R, H);
+            const bool rok = ey < FOG_EH && gy >= 0 && gy < H;
+            const float *src = fext + (size_t)(rok ? gy : 0) * W;
+#pragma unroll
+            for (int j = 0; j < EC; j++) ev[q][j] = (rok && gxs[j] >= 0) ? src[gxs[j]] : 0.f;                       // k_fext
         }
         if (!b.bgf) {
 #pragma unroll
-            for (int k = 0; k < BL; k++) {
-                int j = tid + k * FOG_THREADS;
-                int row = j / (FOG_TX * 3), col = j - row * (FOG_TX * 3);
-                bv[k] = (y0 + row < H && x0 * 3 + col < W * 3) ? bgr[((size_t)(y0 + row) * W + x0) * 3 + col] : (uint8_t)0;
+            for (int q = 0; q < BR; q++) {
+                const int row = warp + NW * q;
+                const bool rok = y0 + row < H;
+                const uint8_t *src = bgr + ((size_t)(rok ? y0 + row : 0) * W + x0) * 3;
+#pragma unroll
+                for (int j = 0; j < BC; j++) {
+                    const int col = lane + 32 * j;
+                    bv[q][j] = (rok && x0 * 3 + col < W * 3) ? src[col] : (uint8_t)0;
+                }
             }
         }
 #pragma unroll
-        for (int k = 0; k < EL; k++) {
-            int i = tid + k * FOG_THREADS;
-            if (i < FOG_EH * FOG_EW) {
-                int ey = i / FOG_EW, ex = i - ey * FOG_EW;
-                float v = ev[k];
-                E[ey * FOG_ES + FOG_PAD(ex)] = v;
-                double d = (double)(1.0f - v);                              // (1 - f_ext) is a float32 op in numpy (:71)
-                if (linear) d = d < 0 ? 0 : (d > 1 ? 1 : d);                // clip(A d, 0, 1) = A clip(d, 0, 1) for 0 <= A <= 1
-                D[ey * FOG_LS + FOG_PAD(ex)] = d;
+        for (int q = 0; q < ER; q++) {
+            const int ey = warp + NW * q;
+            if (ey < FOG_EH) {
+#pragma unroll
+                for (int j = 0; j < EC; j++) {
+                    if (pex[j] >= 0) {
+                        const float v = ev[q][j];
+                        E[ey * FOG_ES + pex[j]] = v;
+                        double d = (double)(1.0f - v);                      // (1 - f_ext) is a float32 op in numpy (:71)
+                        if (linear) d = d < 0 ? 0 : (d > 1 ? 1 : d);        // clip(A d, 0, 1) = A clip(d, 0, 1) for 0 <= A <= 1
+                        D[ey * FOG_LS + pex[j]] = d;
+                    }
+                }
             }
         }
         if (!b.bgf) {
 #pragma unroll
-            for (int k = 0; k < BL; k++) IB[tid + k * FOG_THREADS] = bv[k];
+            for (int q = 0; q < BR; q++)
+#pragma unroll
+                for (int j = 0; j < BC; j++) IB[(warp + NW * q) * (FOG_TX * 3) + lane + 32 * j] = bv[q][j];
         }
     }
     __syncthreads();
@@ -951,6 +978,42 @@ cudaError_t rr_launch_scan(const rr_frame_bufs &b, int n_streaks, cudaStream_t s
 #define RAS_MAXD 1024         // patch pixels with accumulators resident in shared memory
 #define RAS_RBMAX 128         // rows per band of the area-fast path (RAS_CAP / canvas width; canvases are at least 32 wide)
 
+#define RAS_DO_PRAGMA_(x) _Pragma(#x)
+#define RAS_DO_PRAGMA(x) RAS_DO_PRAGMA_(x)
+#ifdef RAS_UNROLL
+#define RAS_PRAGMA_UNROLL RAS_DO_PRAGMA(unroll RAS_UNROLL)
+#else
+#define RAS_PRAGMA_UNROLL
+#endif
+#ifndef RAS_INTW
+#define RAS_INTW 1            // bilinear weights from integer products (below) instead of float32 arithmetic
+#endif
+#ifndef RAS_INTERIOR
+#define RAS_INTERIOR 0        // runs whose taps all lie inside the texture skip the border predicates (sweep r01h: slower, 1.23 vs 1.13 ms)
+#endif
+// Bilinear weights of remapBilinear: w = (1 - fy/32 or fy/32) * (1 - fx/32 or fx/32) in float32.  With 5-bit fractions
+// both factors and their product are exact, so w == p / 1024 with the integer p = {32 - fy, fy} * {32 - fx, fx}, and
+// fl(v * w) == fl((v / 1024) * p) bit for bit (scaling by a power of two is exact): with RAS_INTW the kernel keeps the
+// texture look-up table pre-scaled by 2^-10 (lut[u] = u / 255.0 / 1024) and multiplies by the integer products.
+struct ras_w { double w0, w1, w2, w3; };
+__device__ __forceinline__ ras_w ras_weights(int X, int Y) {
+    const int fx = X & (RR_INTER_TAB - 1), fy = Y & (RR_INTER_TAB - 1);
+    ras_w w;
+#if RAS_INTW
+    const int gx = RR_INTER_TAB - fx, gy = RR_INTER_TAB - fy;
+    w.w0 = (double)(gy * gx); w.w1 = (double)(gy * fx); w.w2 = (double)(fy * gx); w.w3 = (double)(fy * fx);
+#else
+    const float s = 1.f / RR_INTER_TAB;
+    const float ax1 = fx * s, ax0 = 1.f - ax1, ay1 = fy * s, ay0 = 1.f - ay1;
+    w.w0 = ay0 * ax0; w.w1 = ay0 * ax1; w.w2 = ay1 * ax0; w.w3 = ay1 * ax1;
+#endif
+    return w;
+}
+#if RAS_INTW
+#define RAS_LUT_SCALE 0.0009765625
+#else
+#define RAS_LUT_SCALE 1.0
+#endif
 __device__ __forceinline__ double ras_sample(const uint8_t *tex, int tw, int th, const double *lut, int X, int Y) {
     // rr_warp_affine_linear with the fixed-point coordinates already formed.  One code path for interior and
     // border samples (out-of-texture taps contribute the border value 0 with their weight, exactly the
@@ -959,16 +1022,20 @@ __device__ __forceinline__ double ras_sample(const uint8_t *tex, int tw, int th,
     const bool x0ok = (unsigned)sx < (unsigned)tw, x1ok = (unsigned)(sx + 1) < (unsigned)tw;
     const bool y0ok = (unsigned)sy < (unsigned)th, y1ok = (unsigned)(sy + 1) < (unsigned)th;
     if (!((x0ok | x1ok) & (y0ok | y1ok))) return 0.0;               // all four taps outside: the border constant
-    const int fx = X & (RR_INTER_TAB - 1), fy = Y & (RR_INTER_TAB - 1);
-    const float s = 1.f / RR_INTER_TAB;
-    const float ax1 = fx * s, ax0 = 1.f - ax1, ay1 = fy * s, ay0 = 1.f - ay1;
-    const float w0 = ay0 * ax0, w1 = ay0 * ax1, w2 = ay1 * ax0, w3 = ay1 * ax1;
+    const ras_w w = ras_weights(X, Y);
     const uint8_t *S = tex + sy * tw + sx;
     const double v0 = (x0ok & y0ok) ? lut[S[0]] : 0.0;
     const double v1 = (x1ok & y0ok) ? lut[S[1]] : 0.0;
     const double v2 = (x0ok & y1ok) ? lut[S[tw]] : 0.0;
     const double v3 = (x1ok & y1ok) ? lut[S[tw + 1]] : 0.0;
-    return v0 * w0 + v1 * w1 + v2 * w2 + v3 * w3;
+    return v0 * w.w0 + v1 * w.w1 + v2 * w.w2 + v3 * w.w3;
+}
+// the same for a sample whose four taps are known to lie inside the texture
+__device__ __forceinline__ double ras_sample_interior(const uint8_t *tex, int tw, const double *lut, int X, int Y) {
+    const int sx = X >> RR_INTER_BITS, sy = Y >> RR_INTER_BITS;
+    const ras_w w = ras_weights(X, Y);
+    const uint8_t *S = tex + sy * tw + sx;
+    return lut[S[0]] * w.w0 + lut[S[1]] * w.w1 + lut[S[tw]] * w.w2 + lut[S[tw + 1]] * w.w3;
 }
 
 __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs b, rr_static_tabs t, rr_cam_dev cam, int n) {
@@ -976,7 +1043,7 @@ __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs 
     double *C = ras_smem;                       // [RAS_CAP]   area-fast: canvas band;  area: first half of the chain sums
     double *BUF = C + RAS_CAP;                  // [RAS_CAP]   area-fast: quad accumulators; area: second half of the chain sums
     double *SUM = BUF + RAS_CAP;                // [RAS_MAXD]  per patch pixel running sum
-    double *lut = SUM + RAS_MAXD;               // [256]       u8 / 255.0
+    double *lut = SUM + RAS_MAXD;               // [256]       u8 / 255.0 / 1024 (see ras_sample)
     rr_area_span *TX = (rr_area_span *)(lut + 256);     // [RAS_TXN]
     rr_area_span *TY = TX + RAS_TXN;                     // [RAS_TXN]
     int *adx = (int *)(TY + RAS_TXN), *bdx = adx + RAS_MAXW;   // [RAS_MAXW] each
@@ -985,7 +1052,7 @@ __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs 
     double *CB = C;                             // [2 * RAS_CAP] chain sums of the area path: CB[r * pw + dx]
     __shared__ rr_plan sp;
     const int tid = threadIdx.x;
-    for (int i = tid; i < 256; i += RAS_THREADS) lut[i] = (double)i / 255.0;     // bad_weather.py:252
+    for (int i = tid; i < 256; i += RAS_THREADS) lut[i] = rr_u8_unit((uint8_t)i) * RAS_LUT_SCALE;     // bad_weather.py:252
     const int tw = cam.db_width;
     for (int s = blockIdx.x; s < n; s += gridDim.x) {
         __syncthreads();
@@ -1042,11 +1109,31 @@ __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs 
                     if (c_lo < z_lo) c_lo = z_lo;
                     if (c_hi > z_hi) c_hi = z_hi;
                     double buf = 0;
-                    for (int c = c_lo; c <= c_hi; c++) {
-                        const float alpha = c < tx.s_first ? tx.a_first : (c >= tx.s_first + tx.n ? tx.a_last : tx.a_mid);
-                        const int X = (xr + adx[c]) >> (10 - RR_INTER_BITS);
-                        const int Y = (yr + bdx[c]) >> (10 - RR_INTER_BITS);
-                        buf += ras_sample(tex, tw, th, lut, X, Y) * alpha;
+                    if (c_lo <= c_hi) {
+                        const double aF = tx.a_first, aM = tx.a_mid, aL = tx.a_last;
+                        const int m_lo = tx.s_first, m_hi = tx.s_first + tx.n;       // full-weight columns [m_lo, m_hi)
+                        // source coordinates move monotonically along the row: if both ends of the run have all four
+                        // taps inside the texture, every sample of the run has
+                        const int sxa = (xr + adx[c_lo]) >> 10, sxb = (xr + adx[c_hi]) >> 10;
+                        const int sya = (yr + bdx[c_lo]) >> 10, syb = (yr + bdx[c_hi]) >> 10;
+                        const bool interior = RAS_INTERIOR && sxa >= 0 && sxb >= 0 && sxa <= tw - 2 && sxb <= tw - 2 &&
+                                              sya >= 0 && syb >= 0 && sya <= th - 2 && syb <= th - 2;
+                        if (interior) {
+                            for (int c = c_lo; c <= c_hi; c++) {
+                                const double alpha = c < m_lo ? aF : (c >= m_hi ? aL : aM);
+                                const int X = (xr + adx[c]) >> (10 - RR_INTER_BITS);
+                                const int Y = (yr + bdx[c]) >> (10 - RR_INTER_BITS);
+                                buf += ras_sample_interior(tex, tw, lut, X, Y) * alpha;
+                            }
+                        } else {
+                            RAS_PRAGMA_UNROLL
+                            for (int c = c_lo; c <= c_hi; c++) {
+                                const double alpha = c < m_lo ? aF : (c >= m_hi ? aL : aM);
+                                const int X = (xr + adx[c]) >> (10 - RR_INTER_BITS);
+                                const int Y = (yr + bdx[c]) >> (10 - RR_INTER_BITS);
+                                buf += ras_sample(tex, tw, th, lut, X, Y) * alpha;
+                            }
+                        }
                     }
                     CB[r * pw + dx] = buf;
                 }
@@ -1388,10 +1475,10 @@ cudaError_t rr_launch_composite(const rr_frame_bufs &b, const rr_cam_dev &cam, i
 // epilogue: mean shift, float32 / uint8 outputs  (generator.py:460-466)
 // ------------------------------------------------------------------------------------------
 __global__ void k_epilogue(rr_frame_bufs b, int npix, int F) {
-    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)F * npix) return;
-    int f = (int)(i / npix);
-    size_t pix = i - (size_t)f * npix;
+    const int f = blockIdx.y;
+    const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pix >= (size_t)npix) return;
+    const size_t i = (size_t)f * npix + pix;
     double d = b.frame_mean[f];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
@@ -1405,8 +1492,8 @@ __global__ void k_epilogue(rr_frame_bufs b, int npix, int F) {
 }
 
 cudaError_t rr_launch_epilogue(const rr_frame_bufs &b, int F, int W, int H, cudaStream_t st) {
-    size_t n = (size_t)F * W * H;
-    k_epilogue<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b, W * H, F);
+    dim3 grid((unsigned)(((size_t)W * H + 255) / 256), F);
+    k_epilogue<<<grid, 256, 0, st>>>(b, W * H, F);
     return cudaGetLastError();
 }
 
