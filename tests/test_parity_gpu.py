@@ -50,6 +50,26 @@ def test_full_frames_match_oracle(W, H, n_xml, dataset, fallrate, noise):
     ctx.close()
 
 
+def test_many_streaks_per_frame_and_a_wide_environment_map():
+    """More than 512 streaks in a frame (the compositor's hit lists then take several rounds) and an environment
+    map wider than 2048 pixels (BASELINE C4 shape: three prefix-sum tiles per row)."""
+    sc = Scenario(400, 300, 1, 9000, fallrate=100)
+    ctx = sc.context()
+    recs, offs = sc.records()
+    assert offs[-1] > 1100
+    out = ctx.render_frames(sc.bgr, sc.depth, recs, offs)
+    _check_frame(out, 0, sc.oracle_frame(0, "canonical"))
+    ctx.close()
+    sc = Scenario(1600, 900, 1, 260, fallrate=5, dataset="nuscenes")
+    ctx = sc.context()
+    assert ctx.W_env > 2048
+    recs, offs = sc.records()
+    assert offs[-1] > 20
+    out = ctx.render_frames(sc.bgr, sc.depth, recs, offs)
+    _check_frame(out, 0, sc.oracle_frame(0, "canonical"))
+    ctx.close()
+
+
 def test_render_scale_2_cityscapes_arrangement():
     """BASELINE C3 shape: frames arrive at twice the render size and are reduced on the device."""
     sc = Scenario(512, 256, 2, 1800, fallrate=50, dataset="cityscapes", render_scale=2)
