@@ -17,6 +17,7 @@ import numpy as np
 from common import my_utils
 from common.bad_weather import DBManager, RainRenderer, EnvironmentMapGenerator, FovComputation  # noqa: F401 (API parity)
 from rain_rendering_b200 import api as _api
+from rain_rendering_b200._lib import RainError as _RainError
 
 FOG_ATT = 1
 USE_DEPTH_WEIGHTING = 0
@@ -36,6 +37,122 @@ def _imsave_mask(path, mask):
     lo, hi = float(mask.min()), float(mask.max())
     norm = (mask - lo) / (hi - lo) if hi > lo else np.zeros_like(mask)
     cv2.imwrite(path, (norm * 65535.0 + 0.5).astype(np.uint16))     # 16-bit gray, min/max normalised like imsave
+
+
+class _FramePipeline:
+    """Decode -> render -> encode with everything overlapped: PNG decoding and encoding run on a thread pool
+    (OpenCV releases the GIL), batches go through ``rr_submit_frames`` / ``rr_wait_frames`` with two sets of
+    page-locked buffers, so while batch k renders, batch k+1 is being decoded and copied in and batch k-1 is being
+    copied out and written.  The first batch is rendered synchronously (it sizes the patch arena)."""
+
+    def __init__(self, ctx, batch, io_threads, alloc=None):
+        from concurrent.futures import ThreadPoolExecutor
+        self.ctx, self.batch = ctx, batch
+        rs, W, H = ctx.render_scale, ctx.W, ctx.H
+        alloc = alloc or _api.PinnedBuffer            # page-locked, so that the copies overlap the kernels
+        self.sets = []
+        for _ in range(2):
+            self.sets.append(dict(bgr=alloc((batch, H * rs, W * rs, 3), np.uint8), depth=alloc((batch, H, W), np.float32),
+                                  mask=alloc((batch, H, W), np.float32), u8=alloc((batch, H, W, 3), np.uint8),
+                                  writes=[], recs=None, offs=None, paths=[]))
+        self.pool = ThreadPoolExecutor(max_workers=max(1, io_threads))
+        self.inflight = []            # indices of the sets submitted and not yet waited for, oldest first
+        self.turn = 0
+        self.first = True
+        self.frames_done = 0
+
+    def decode_async(self, fn, *a):
+        return self.pool.submit(fn, *a)
+
+    def _write(self, s, k, rgb_path, mask_path):
+        os.makedirs(os.path.dirname(rgb_path), exist_ok=True)
+        os.makedirs(os.path.dirname(mask_path), exist_ok=True)
+        _imsave_rgb(rgb_path, s["u8"].array[k])
+        _imsave_mask(mask_path, s["mask"].array[k])
+
+    def _finish_oldest(self):
+        si = self.inflight[0]
+        s = self.sets[si]
+        try:
+            self.ctx.wait_frames()
+        except _RainError as e:
+            if "arena" not in str(e):
+                raise
+            # the patch arena overflowed: drain, then render what was in flight synchronously (that call grows it)
+            try:
+                self.ctx.synchronize()
+            except _RainError:
+                pass
+            for sj in self.inflight:
+                t = self.sets[sj]
+                n = len(t["paths"])
+                self.ctx.render_frames(t["bgr"].array[:n], t["depth"].array[:n], t["recs"], t["offs"], None, t["mask"].array[:n], t["u8"].array[:n],
+                                       want=("mask", "u8"))
+                self._schedule_writes(sj)
+            self.inflight = []
+            return
+        self.inflight.pop(0)
+        self._schedule_writes(si)
+
+    def _schedule_writes(self, si):
+        s = self.sets[si]
+        s["writes"] = [self.pool.submit(self._write, s, k, p[0], p[1]) for k, p in enumerate(s["paths"])]
+        self.frames_done += len(s["paths"])
+
+    def process(self, decoded, assemble):
+        """decoded: list of (future -> (bg, depth) or (None, None), frame index for the records, rgb path, mask path);
+        assemble(frame index) -> records of that frame (called in frame order: the wind write-back is stateful)."""
+        si = self.turn
+        s = self.sets[si]
+        if si in self.inflight:                       # (only with a single set in use) never overwrite buffers in flight
+            self._finish_oldest()
+        for w in s["writes"]:
+            w.result()                                # the previous user of this set has been written to disk
+        s["writes"] = []
+        recs, offs, paths, n = [], [0], [], 0
+        for fut, f_name_idx, rgb_path, mask_path in decoded:
+            bg, depth = fut.result()
+            if bg is None:
+                continue
+            if (bg.shape[1], bg.shape[0]) != (self.ctx.W * self.ctx.render_scale, self.ctx.H * self.ctx.render_scale):
+                raise AssertionError("frame size %s differs from the sequence size (%d, %d) (generator.py:250-258 reads it once)" % (bg.shape, self.ctx.W, self.ctx.H))
+            r = assemble(f_name_idx)
+            assert len(r) <= 2 ** 16, "Assert that the number of drops doesn't overpass the uint16 rain_mask capacity"
+            s["bgr"].array[n] = bg
+            s["depth"].array[n] = depth
+            recs.append(r); offs.append(offs[-1] + len(r)); paths.append((rgb_path, mask_path))
+            n += 1
+        if n == 0:
+            return
+        s["recs"] = np.concatenate(recs)
+        s["offs"] = np.ascontiguousarray(offs, np.int32)
+        s["paths"] = paths
+        if self.first:
+            self.ctx.render_frames(s["bgr"].array[:n], s["depth"].array[:n], s["recs"], s["offs"], None, s["mask"].array[:n], s["u8"].array[:n],
+                                   want=("mask", "u8"))
+            self.first = False
+            self._schedule_writes(si)
+        else:
+            self.ctx.submit_frames(s["bgr"].array[:n], s["depth"].array[:n], s["recs"], s["offs"], None, s["mask"].array[:n], s["u8"].array[:n])
+            self.inflight.append(si)
+            if len(self.inflight) == 2:
+                self._finish_oldest()
+        self.turn ^= 1
+
+    def finish(self):
+        while self.inflight:
+            self._finish_oldest()
+        for s in self.sets:
+            for w in s["writes"]:
+                w.result()
+            s["writes"] = []
+
+    def close(self):
+        self.finish()
+        self.pool.shutdown(wait=True)
+        for s in self.sets:
+            for k in ("bgr", "depth", "mask", "u8"):
+                s[k].free()
 
 
 class Generator:
@@ -80,6 +197,7 @@ class Generator:
         self.env_map_xyY = None
         self.solid_angle_map = None
         self.batch = int(os.environ.get("RAIN_B200_BATCH", "16"))
+        self.io_threads = int(os.environ.get("RAIN_B200_IO_THREADS", "8"))
         self.device = int(os.environ.get("LOCAL_RANK", os.environ.get("RAIN_B200_DEVICE", "0")))
         self._ctx = None
         self.check_folders()
@@ -191,58 +309,44 @@ class Generator:
                 print("{} images".format(len(idx)))
                 frames_exist_nb = 0
                 t0 = time.time()
-                pending = []          # (bgr, depth, records, out paths)
+                pipe = _FramePipeline(ctx, self.batch, self.io_threads)
+                queue = []            # (decode future, frame index for the records, out paths)
 
-                def flush():
-                    if not pending:
-                        return
-                    bgr = np.stack([p[0] for p in pending])
-                    depth = np.stack([p[1] for p in pending])
-                    recs = np.concatenate([p[2] for p in pending])
-                    offs = np.concatenate([[0], np.cumsum([len(p[2]) for p in pending])]).astype(np.int32)
-                    if (bgr.shape[2], bgr.shape[1]) != (ctx.W * ctx.render_scale, ctx.H * ctx.render_scale):
-                        raise AssertionError("frame size %s differs from the sequence size (%d, %d) (generator.py:250-258 reads it once)" % (bgr.shape, ctx.W, ctx.H))
-                    out = ctx.render_frames(bgr, depth, recs, offs, want=("mask", "u8"))
-                    for k, p in enumerate(pending):
-                        os.makedirs(os.path.dirname(p[3]), exist_ok=True)
-                        os.makedirs(os.path.dirname(p[4]), exist_ok=True)
-                        _imsave_rgb(p[3], out["u8"][k])
-                        _imsave_mask(p[4], out["mask"][k])
-                    pending.clear()
-
-                for f_idx, i in enumerate(idx):
-                    image_file, depth_file = files[i], depth_files[i]
-                    if self.dataset == 'nuscenes':
-                        render_ix = np.linspace(0, len(frame_render_dict), len(files), endpoint=False, dtype=int)
-                        f_name_idx = int(render_ix[i])
-                    else:
-                        f_name_idx = i
-                    assert os.path.exists(image_file), "Image file {} does not exist".format(image_file)
-                    assert os.path.exists(depth_file), "Depth file {} does not exist".format(depth_file)
-                    file_name = os.path.split(image_file)[-1]
-                    out_rainy_path = os.path.join(out_dir, 'rainy_image', '{}.png'.format(file_name[:-4]))
-                    out_rainy_mask_path = os.path.join(out_dir, 'rain_mask', '{}.png'.format(file_name[:-4]))
-                    if os.path.exists(out_rainy_path) or os.path.exists(out_rainy_mask_path):
-                        if self.conflict_strategy == "skip":
-                            frames_exist_nb += 1
-                            continue
-                        elif self.conflict_strategy == "overwrite":
-                            pass
-                        else:
-                            raise NotImplementedError
-                    bg, depth = self._decode(image_file, depth_file)
-                    if bg is None:
-                        continue
+                def assemble(f_name_idx):
                     sim = frame_render_dict[f_name_idx % len(frame_render_dict)]
                     # np.random.seed(f_name_idx) + the per-streak draws + the wind write-back (generator.py:318,136,152-161)
-                    recs = _api.assemble_frame_records(sim.records, imW, imH, self.db.ratio, f_name_idx, self.noise_std, self.noise_scale)
-                    assert len(recs) <= 2 ** 16, "Assert that the number of drops doesn't overpass the uint16 rain_mask capacity"
-                    pending.append((bg, depth, recs, out_rainy_path, out_rainy_mask_path))
-                    if len(pending) == self.batch:
-                        flush()
-                        if self.verbose:
-                            sys.stdout.write('\r%d/%d frames, %.1f frames/s   ' % (f_idx + 1, len(idx), (f_idx + 1) / (time.time() - t0)))
-                flush()
+                    return _api.assemble_frame_records(sim.records, imW, imH, self.db.ratio, f_name_idx, self.noise_std, self.noise_scale)
+
+                try:
+                    for f_idx, i in enumerate(idx):
+                        image_file, depth_file = files[i], depth_files[i]
+                        if self.dataset == 'nuscenes':
+                            render_ix = np.linspace(0, len(frame_render_dict), len(files), endpoint=False, dtype=int)
+                            f_name_idx = int(render_ix[i])
+                        else:
+                            f_name_idx = i
+                        assert os.path.exists(image_file), "Image file {} does not exist".format(image_file)
+                        assert os.path.exists(depth_file), "Depth file {} does not exist".format(depth_file)
+                        file_name = os.path.split(image_file)[-1]
+                        out_rainy_path = os.path.join(out_dir, 'rainy_image', '{}.png'.format(file_name[:-4]))
+                        out_rainy_mask_path = os.path.join(out_dir, 'rain_mask', '{}.png'.format(file_name[:-4]))
+                        if os.path.exists(out_rainy_path) or os.path.exists(out_rainy_mask_path):
+                            if self.conflict_strategy == "skip":
+                                frames_exist_nb += 1
+                                continue
+                            elif self.conflict_strategy == "overwrite":
+                                pass
+                            else:
+                                raise NotImplementedError
+                        queue.append((pipe.decode_async(self._decode, image_file, depth_file), f_name_idx, out_rainy_path, out_rainy_mask_path))
+                        if len(queue) == self.batch:
+                            pipe.process(queue, assemble)
+                            queue = []
+                            if self.verbose:
+                                sys.stdout.write('\r%d/%d frames, %.1f frames/s   ' % (f_idx + 1, len(idx), (f_idx + 1) / (time.time() - t0)))
+                    pipe.process(queue, assemble)
+                finally:
+                    pipe.close()
                 if frames_exist_nb > 0:
                     print("Skipped {}/{} already existing renderings".format(frames_exist_nb, len(idx)))
             print("\n\nEnd of the simulation")

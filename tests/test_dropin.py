@@ -124,3 +124,91 @@ def test_dropin_stage_classes_match_oracle():
         sys.path.remove(DROPIN)
         for k in [k for k in sys.modules if k == "common" or k.startswith("common.")]:
             del sys.modules[k]
+
+
+class _FakeBuf:
+    def __init__(self, shape, dtype):
+        self.array = np.zeros(shape, dtype)
+
+    def free(self):
+        self.array = None
+
+
+class _FakeCtx:
+    """Stands in for RainContext: 'renders' u8 = bgr + 1, mask = depth * 2 when a batch is waited for, and can be told
+    to report a patch-arena overflow on the n-th wait (the asynchronous API does not grow the arena itself)."""
+    W, H, render_scale = 24, 16, 1
+
+    def __init__(self, overflow_on_wait=None):
+        self.q, self.log, self.waits, self.overflow_on_wait = [], [], 0, overflow_on_wait
+
+    def _render(self, bgr, depth, mask, u8):
+        u8[...] = bgr + 1
+        mask[...] = depth * 2
+
+    def render_frames(self, bgr, depth, recs, offs, out_bgr, out_mask, out_u8, want=()):
+        self.log.append(("sync", len(bgr), int(offs[-1])))
+        self._render(bgr, depth, out_mask, out_u8)
+
+    def submit_frames(self, bgr, depth, recs, offs, out_bgr, out_mask, out_u8):
+        assert len(self.q) < 2
+        self.log.append(("submit", len(bgr), int(offs[-1])))
+        self.q.append((bgr, depth, out_mask, out_u8))
+
+    def wait_frames(self):
+        from rain_rendering_b200._lib import RainError
+        self.waits += 1
+        item = self.q.pop(0)
+        if self.overflow_on_wait == self.waits:
+            raise RainError("rr_wait_frames failed (-4): patch arena overflow: need 10 float64 elements, have 5")
+        self._render(*item)
+
+    def synchronize(self):
+        self.q = []
+
+
+@pytest.mark.parametrize("overflow_on_wait", [None, 2])
+def test_frame_pipeline_orders_batches_and_recovers_from_arena_overflow(tmp_path, overflow_on_wait):
+    for k in [k for k in sys.modules if k == "common" or k.startswith("common.")]:
+        del sys.modules[k]
+    sys.path.insert(0, DROPIN)
+    try:
+        import common.generator as gen
+        from rain_rendering_b200.streaks import STREAK_DTYPE
+        ctx = _FakeCtx(overflow_on_wait)
+        pipe = gen._FramePipeline(ctx, batch=3, io_threads=4, alloc=_FakeBuf)
+        order = []
+
+        def decode(i):
+            if i == 4:
+                return None, None                      # corrupt depth: the frame is skipped (generator.py:361-363)
+            return np.full((16, 24, 3), i, np.uint8), np.full((16, 24), float(i), np.float32)
+
+        def assemble(i):
+            order.append(i)
+            return np.zeros(i % 3 + 1, STREAK_DTYPE)
+
+        frames = list(range(11))
+        for b0 in range(0, 11, 3):
+            q = [(pipe.decode_async(decode, i), i, str(tmp_path / "rainy_image" / ("%03d.png" % i)), str(tmp_path / "rain_mask" / ("%03d.png" % i)))
+                 for i in frames[b0:b0 + 3]]
+            pipe.process(q, assemble)
+        pipe.close()
+        assert order == [i for i in frames if i != 4]               # records are assembled in frame order
+        assert ctx.log[0][0] == "sync" and ctx.log[0][1] == 3       # the first batch sizes the arena
+        assert [e[1] for e in ctx.log if e[0] == "submit"] == [2, 3, 2]
+        if overflow_on_wait:
+            assert [e[0] for e in ctx.log].count("sync") >= 2       # the batches in flight were re-rendered synchronously
+        for i in frames:
+            p = tmp_path / "rainy_image" / ("%03d.png" % i)
+            if i == 4:
+                assert not p.exists()
+                continue
+            img = cv2.imread(str(p))
+            assert img is not None and (img == i + 1).all(), i
+            assert (tmp_path / "rain_mask" / ("%03d.png" % i)).exists()
+        assert pipe.frames_done == 10
+    finally:
+        sys.path.remove(DROPIN)
+        for k in [k for k in sys.modules if k == "common" or k.startswith("common.")]:
+            del sys.modules[k]
