@@ -30,7 +30,9 @@ enum rr_status {
     RR_ERR_CUDA = -1,        /* a CUDA runtime call failed                     */
     RR_ERR_ARG = -2,         /* invalid argument                               */
     RR_ERR_STATE = -3,       /* call order violated (no camera / no streak DB) */
-    RR_ERR_CAPACITY = -4     /* a device arena overflowed                      */
+    RR_ERR_CAPACITY = -4,    /* a device arena overflowed                      */
+    RR_PNG_UNSUPPORTED = -5, /* a valid PNG the native codec does not decode (palette, interlace, < 8 bits) */
+    RR_PNG_SIZE = -6         /* decoded, but not the expected width x height   */
 };
 
 /* One imaged streak of one simulator frame, as common/bad_weather.py:46-60 ("Streak") holds it
@@ -222,6 +224,17 @@ void rr_host_free_particles(rr_xml_particles *p);
 /* np.linalg.norm of n 2-vectors the way NumPy's BLAS evaluates it, sqrt(fma(y, y, x * x)): the loader's
  * direction norm (bad_weather.py:229), shared with the Python-side record builder of the on-the-fly simulator. */
 void rr_host_norm2(int n, const double *x, const double *y, double *out);
+/* Host logic (no GPU): native PNG codec of the frame pipeline, on a pool of threads, straight from / into the batch
+ * buffers of rr_submit_frames.  Decoding reproduces cv2.imread(path) (BGR uint8, common/generator.py:352) and
+ * cv2.imread(path, IMREAD_UNCHANGED).astype(float32) / 256 (depth, generator.py:360-365) for non-interlaced 8/16-bit
+ * gray / RGB(A) files; encoding writes what the drop-in Generator saves (generator.py:466-467): the uint8 image as RGB
+ * and the rain mask min/max-normalised to 16-bit gray.  status[i] tells the caller which frames need its fallback
+ * decoder.  level = zlib level 0..9 (0 stores, 1 is Huffman-only deflate). */
+int rr_host_png_info(const char *path, int32_t *w, int32_t *h, int32_t *channels, int32_t *bit_depth);
+int rr_host_png_read_batch(int n, const char *const *image_paths, const char *const *depth_paths, uint8_t *bgr, int Wi, int Hi,
+                           float *depth, int Wd, int Hd, int n_threads, int32_t *status);
+int rr_host_png_write_batch(int n, const char *const *image_paths, const uint8_t *bgr, const char *const *mask_paths,
+                            const float *mask, int W, int H, int level, int n_threads);
 /* The simulator's force model evaluated on the host (CPU test-suite): terminal velocity solving
  * m g = F_drag(v), the drag at that speed and the drop mass. */
 void rr_host_sim_physics(double D_m, double *v_terminal, double *drag_at_vt, double *mass);

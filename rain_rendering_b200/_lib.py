@@ -97,6 +97,9 @@ def load() -> C.CDLL:
         "rr_host_load_particles_xml": [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)],
         "rr_host_particles_info": [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64)],
         "rr_host_particles_copy": [vp, vp, vp],
+        "rr_host_png_info": [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
+        "rr_host_png_read_batch": [C.c_int, vp, vp, u8p, C.c_int, C.c_int, f32p, C.c_int, C.c_int, C.c_int, i32p],
+        "rr_host_png_write_batch": [C.c_int, vp, u8p, vp, f32p, C.c_int, C.c_int, C.c_int, C.c_int],
     }
     for name, args in protos.items():
         fn = getattr(lib, name)

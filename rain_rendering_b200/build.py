@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "librain_b200.so")
-SOURCES = ["rr_api.cu", "rr_kernels.cu", "rr_sim.cu", "rr_host.cpp", "rr_host_xml.cpp"]
+SOURCES = ["rr_api.cu", "rr_kernels.cu", "rr_sim.cu", "rr_host.cpp", "rr_host_xml.cpp", "rr_host_png.cpp"]
 HEADERS = ["rr_types.h", "rr_cvmath.h", "rr_streak_geom.h", "rr_kernels.cuh", os.path.join("..", "..", "include", "rain_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false",            # keep the reference's float64 operation order (no FMA contraction)
@@ -35,7 +35,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not stale():
         return LIB
     cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+          ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES] + ["-lz"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

@@ -1,0 +1,321 @@
+// Native PNG codec of the frame pipeline (no CUDA): the reference decodes every frame with cv2.imread
+// (common/generator.py:352,360) and encodes two PNGs per frame through matplotlib (generator.py:466-467);
+// once rendering takes 0.1 ms per frame those ~115 ms of single-threaded libpng work per frame are the whole
+// run time.  This codec does the same job on a pool of native threads, straight from / into the page-locked
+// batch buffers of rr_submit_frames:
+//   * decode: non-interlaced 8-bit gray / gray+alpha / RGB / RGBA and 16-bit gray / RGB, exactly the arrays
+//     cv2.imread(path) (3-channel BGR uint8, alpha dropped, 16-bit reduced to its high byte) and
+//     cv2.imread(path, IMREAD_UNCHANGED).astype(float32) / 256 (the depth path, generator.py:360-365) give;
+//     anything else (palette, interlace, sub-byte depths) reports RR_PNG_UNSUPPORTED and the caller falls back
+//   * encode: 8-bit RGB from the BGR batch buffer, and the rain mask min/max-normalised to 16-bit gray (the
+//     drop-in's stand-in for plt.imsave of a 2-D array); one fixed filter per image (Sub) and, at the default
+//     level 1, Huffman-only deflate: about a third of cv2.imwrite's time per file.
+// zlib (inflate / deflate / crc32) is the only dependency.
+#include <errno.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <zlib.h>
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+#include "../../include/rain_b200.h"
+
+extern "C" void rr_set_error(const char *msg);
+
+namespace {
+
+const unsigned char kSig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+
+uint32_t be32(const unsigned char *p) { return ((uint32_t)p[0] << 24) | ((uint32_t)p[1] << 16) | ((uint32_t)p[2] << 8) | p[3]; }
+void put32(unsigned char *p, uint32_t v) { p[0] = v >> 24; p[1] = v >> 16; p[2] = v >> 8; p[3] = v; }
+
+bool read_file(const char *path, std::vector<unsigned char> *buf) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return false;
+    fseek(f, 0, SEEK_END);
+    long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    if (n < 0) { fclose(f); return false; }
+    buf->resize((size_t)n);
+    size_t got = n ? fread(buf->data(), 1, (size_t)n, f) : 0;
+    fclose(f);
+    return got == (size_t)n;
+}
+
+struct Image {
+    int w = 0, h = 0, channels = 0, depth = 0;     // depth: bits per sample (8 or 16)
+    std::vector<unsigned char> px;                  // unfiltered scanlines, h * w * channels * depth/8, samples big-endian
+};
+
+int paeth(int a, int b, int c) {
+    int p = a + b - c, pa = abs(p - a), pb = abs(p - b), pc = abs(p - c);
+    return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+}
+
+// -> RR_OK, RR_PNG_UNSUPPORTED (valid PNG this codec does not handle) or RR_ERR_ARG (not a readable PNG)
+int decode(const char *path, Image *img, bool header_only) {
+    std::vector<unsigned char> file;
+    if (!read_file(path, &file)) return RR_ERR_ARG;
+    if (file.size() < 8 + 25 || memcmp(file.data(), kSig, 8) != 0) return RR_ERR_ARG;
+    size_t pos = 8;
+    bool have_hdr = false;
+    int color = 0, interlace = 0;
+    std::vector<unsigned char> raw;
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    bool z_open = false, z_done = false;
+    size_t stride = 0;
+    int ret = RR_ERR_ARG;
+    while (pos + 12 <= file.size()) {
+        uint32_t len = be32(&file[pos]);
+        const unsigned char *type = &file[pos + 4], *data = &file[pos + 8];
+        if (pos + 12 + (size_t)len > file.size()) break;
+        if (!memcmp(type, "IHDR", 4)) {
+            if (len != 13) break;
+            img->w = (int)be32(data); img->h = (int)be32(data + 4);
+            img->depth = data[8]; color = data[9]; interlace = data[12];
+            if (img->w <= 0 || img->h <= 0 || img->w > 65536 || img->h > 65536) break;
+            have_hdr = true;
+            img->channels = color == 0 ? 1 : color == 2 ? 3 : color == 4 ? 2 : color == 6 ? 4 : 0;
+            if (header_only) { if (color == 3) img->channels = 3; return RR_OK; }
+            if (img->channels == 0 || interlace != 0 || (img->depth != 8 && img->depth != 16) || data[10] != 0 || data[11] != 0) {
+                ret = RR_PNG_UNSUPPORTED;
+                break;
+            }
+            stride = (size_t)img->w * img->channels * (img->depth / 8);
+            raw.resize((stride + 1) * (size_t)img->h);
+            if (inflateInit(&zs) != Z_OK) break;
+            z_open = true;
+            zs.next_out = raw.data();
+            zs.avail_out = (uInt)raw.size();
+        } else if (!memcmp(type, "IDAT", 4)) {
+            if (!have_hdr || !z_open) break;
+            zs.next_in = const_cast<unsigned char *>(data);
+            zs.avail_in = len;
+            int r = inflate(&zs, Z_NO_FLUSH);
+            if (r == Z_STREAM_END) z_done = true;
+            else if (r != Z_OK && r != Z_BUF_ERROR) break;
+        } else if (!memcmp(type, "IEND", 4)) {
+            if (z_open && (z_done || zs.avail_out == 0) && zs.total_out == raw.size()) ret = RR_OK;
+            break;
+        }
+        pos += 12 + (size_t)len;
+    }
+    if (z_open) inflateEnd(&zs);
+    if (ret != RR_OK) return ret;
+    // unfilter in place into img->px
+    const int bpp = img->channels * (img->depth / 8);
+    img->px.resize(stride * (size_t)img->h);
+    const unsigned char *prev = nullptr;
+    for (int y = 0; y < img->h; y++) {
+        const unsigned char *src = raw.data() + (stride + 1) * (size_t)y;
+        unsigned char *dst = img->px.data() + stride * (size_t)y;
+        const int ft = src[0];
+        src++;
+        switch (ft) {
+            case 0: memcpy(dst, src, stride); break;
+            case 1:
+                for (size_t i = 0; i < stride; i++) dst[i] = (unsigned char)(src[i] + (i >= (size_t)bpp ? dst[i - bpp] : 0));
+                break;
+            case 2:
+                for (size_t i = 0; i < stride; i++) dst[i] = (unsigned char)(src[i] + (prev ? prev[i] : 0));
+                break;
+            case 3:
+                for (size_t i = 0; i < stride; i++) {
+                    int a = i >= (size_t)bpp ? dst[i - bpp] : 0, b = prev ? prev[i] : 0;
+                    dst[i] = (unsigned char)(src[i] + ((a + b) >> 1));
+                }
+                break;
+            case 4:
+                for (size_t i = 0; i < stride; i++) {
+                    int a = i >= (size_t)bpp ? dst[i - bpp] : 0, b = prev ? prev[i] : 0, c = (prev && i >= (size_t)bpp) ? prev[i - bpp] : 0;
+                    dst[i] = (unsigned char)(src[i] + paeth(a, b, c));
+                }
+                break;
+            default: return RR_ERR_ARG;
+        }
+        prev = dst;
+    }
+    return RR_OK;
+}
+
+// cv2.imread(path) semantics: BGR uint8, gray replicated, alpha dropped, 16-bit -> high byte
+int to_bgr8(const Image &im, uint8_t *dst) {
+    const int step = im.depth / 8, ch = im.channels;
+    const size_t n = (size_t)im.w * im.h;
+    const unsigned char *s = im.px.data();
+    if (ch == 1 || ch == 2) {
+        for (size_t i = 0; i < n; i++) { uint8_t g = s[i * ch * step]; dst[3 * i] = dst[3 * i + 1] = dst[3 * i + 2] = g; }
+    } else {
+        for (size_t i = 0; i < n; i++) {
+            const unsigned char *p = s + i * ch * step;
+            dst[3 * i] = p[2 * step]; dst[3 * i + 1] = p[step]; dst[3 * i + 2] = p[0];
+        }
+    }
+    return RR_OK;
+}
+
+// cv2.imread(path, IMREAD_UNCHANGED).astype(np.float32) / 256. for a single-channel file
+int to_depth_f32(const Image &im, float *dst) {
+    if (im.channels != 1) return RR_PNG_UNSUPPORTED;
+    const size_t n = (size_t)im.w * im.h;
+    const unsigned char *s = im.px.data();
+    if (im.depth == 16) for (size_t i = 0; i < n; i++) dst[i] = (float)((s[2 * i] << 8) | s[2 * i + 1]) / 256.f;
+    else for (size_t i = 0; i < n; i++) dst[i] = (float)s[i] / 256.f;
+    return RR_OK;
+}
+
+void chunk(std::vector<unsigned char> *out, const char *type, const unsigned char *data, size_t len) {
+    unsigned char hdr[8];
+    put32(hdr, (uint32_t)len);
+    memcpy(hdr + 4, type, 4);
+    out->insert(out->end(), hdr, hdr + 8);
+    if (len) out->insert(out->end(), data, data + len);
+    uLong c = crc32(0L, hdr + 4, 4);
+    if (len) c = crc32(c, data, (uInt)len);
+    unsigned char tail[4];
+    put32(tail, (uint32_t)c);
+    out->insert(out->end(), tail, tail + 4);
+}
+
+// rows: h scanlines of `stride` bytes (samples already big-endian / RGB order); bpp = bytes per pixel
+int encode(const char *path, const unsigned char *rows, int w, int h, int color, int depth, int bpp, int level) {
+    const size_t stride = (size_t)w * bpp;
+    std::vector<unsigned char> filt((stride + 1) * (size_t)h);
+    const int ft = level > 0 ? 1 : 0;           // Sub: cheap, and what makes smooth images compressible; None when storing
+    for (int y = 0; y < h; y++) {
+        const unsigned char *s = rows + stride * (size_t)y;
+        unsigned char *d = filt.data() + (stride + 1) * (size_t)y;
+        d[0] = (unsigned char)ft;
+        d++;
+        if (ft == 0) memcpy(d, s, stride);
+        else {
+            for (int i = 0; i < bpp && (size_t)i < stride; i++) d[i] = s[i];
+            for (size_t i = bpp; i < stride; i++) d[i] = (unsigned char)(s[i] - s[i - bpp]);
+        }
+    }
+    z_stream zs;
+    memset(&zs, 0, sizeof(zs));
+    // level 1 = Huffman coding only (no match search): 3x faster than zlib's level-1 matcher and no larger on Sub-filtered
+    // camera noise; higher levels use the regular matcher
+    if (deflateInit2(&zs, level, Z_DEFLATED, 15, 8, level == 1 ? Z_HUFFMAN_ONLY : Z_DEFAULT_STRATEGY) != Z_OK) return RR_ERR_ARG;
+    std::vector<unsigned char> comp(deflateBound(&zs, (uLong)filt.size()));
+    zs.next_in = filt.data(); zs.avail_in = (uInt)filt.size();
+    zs.next_out = comp.data(); zs.avail_out = (uInt)comp.size();
+    int r = deflate(&zs, Z_FINISH);
+    size_t clen = zs.total_out;
+    deflateEnd(&zs);
+    if (r != Z_STREAM_END) return RR_ERR_ARG;
+    std::vector<unsigned char> out;
+    out.reserve(clen + 128);
+    out.insert(out.end(), kSig, kSig + 8);
+    unsigned char ihdr[13];
+    put32(ihdr, (uint32_t)w); put32(ihdr + 4, (uint32_t)h);
+    ihdr[8] = (unsigned char)depth; ihdr[9] = (unsigned char)color; ihdr[10] = ihdr[11] = ihdr[12] = 0;
+    chunk(&out, "IHDR", ihdr, 13);
+    chunk(&out, "IDAT", comp.data(), clen);
+    chunk(&out, "IEND", nullptr, 0);
+    std::string tmp = std::string(path) + ".part";
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return RR_ERR_ARG;
+    bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); return RR_ERR_ARG; }
+    return RR_OK;
+}
+
+int write_bgr8(const char *path, const uint8_t *bgr, int w, int h, int level) {
+    std::vector<unsigned char> rgb((size_t)w * h * 3);
+    for (size_t i = 0, n = (size_t)w * h; i < n; i++) { rgb[3 * i] = bgr[3 * i + 2]; rgb[3 * i + 1] = bgr[3 * i + 1]; rgb[3 * i + 2] = bgr[3 * i]; }
+    return encode(path, rgb.data(), w, h, 2, 8, 3, level);
+}
+
+// the drop-in's mask file: (mask - min) / (max - min) * 65535 + 0.5 as 16-bit gray (zeros when the mask is flat)
+int write_mask16(const char *path, const float *mask, int w, int h, int level) {
+    const size_t n = (size_t)w * h;
+    float lo = mask[0], hi = mask[0];
+    for (size_t i = 1; i < n; i++) { lo = mask[i] < lo ? mask[i] : lo; hi = mask[i] > hi ? mask[i] : hi; }
+    std::vector<unsigned char> g(n * 2);
+    const double dlo = lo, range = (double)hi - (double)lo;
+    for (size_t i = 0; i < n; i++) {
+        double v = range > 0 ? ((double)mask[i] - dlo) / range : 0.0;
+        unsigned q = (unsigned)(v * 65535.0 + 0.5);
+        g[2 * i] = (unsigned char)(q >> 8); g[2 * i + 1] = (unsigned char)q;
+    }
+    return encode(path, g.data(), w, h, 0, 16, 2, level);
+}
+
+template <class F>
+void parallel_for(int n, int n_threads, F fn) {
+    if (n_threads > n) n_threads = n;
+    if (n_threads <= 1) { for (int i = 0; i < n; i++) fn(i); return; }
+    std::atomic<int> next(0);
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++)
+        th.emplace_back([&]() { for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) fn(i); });
+    for (auto &t : th) t.join();
+}
+
+}  // namespace
+
+extern "C" int rr_host_png_info(const char *path, int32_t *w, int32_t *h, int32_t *channels, int32_t *bit_depth) {
+    if (!path) { rr_set_error("rr_host_png_info: path is NULL"); return RR_ERR_ARG; }
+    Image im;
+    int r = decode(path, &im, true);
+    if (r != RR_OK) { rr_set_error((std::string("rr_host_png_info: cannot read ") + path).c_str()); return r; }
+    if (w) *w = im.w;
+    if (h) *h = im.h;
+    if (channels) *channels = im.channels;
+    if (bit_depth) *bit_depth = im.depth;
+    return RR_OK;
+}
+
+// Decodes n frames into the batch buffers (frame i at bgr + i * 3 * Wi * Hi and depth + i * Wd * Hd); a NULL path
+// list skips that kind.  status[i] receives RR_OK, RR_PNG_UNSUPPORTED / RR_ERR_ARG (file i must go through the
+// caller's fallback decoder) or RR_PNG_SIZE (decodable, but not the expected size).  Returns the number of
+// frames that are not RR_OK.
+extern "C" int rr_host_png_read_batch(int n, const char *const *image_paths, const char *const *depth_paths, uint8_t *bgr, int Wi, int Hi,
+                                      float *depth, int Wd, int Hd, int n_threads, int32_t *status) {
+    if (n < 0 || !status || (image_paths && !bgr) || (depth_paths && !depth)) { rr_set_error("rr_host_png_read_batch: bad arguments"); return RR_ERR_ARG; }
+    for (int i = 0; i < n; i++) status[i] = RR_OK;
+    const int jobs = 2 * n;
+    parallel_for(jobs, n_threads, [&](int j) {
+        const int i = j >> 1, kind = j & 1;
+        const char *const *paths = kind ? depth_paths : image_paths;
+        if (!paths || !paths[i]) return;
+        Image im;
+        int r = decode(paths[i], &im, false);
+        if (r == RR_OK) {
+            if (kind == 0) r = (im.w == Wi && im.h == Hi) ? to_bgr8(im, bgr + (size_t)i * 3 * Wi * Hi) : RR_PNG_SIZE;
+            else r = (im.w == Wd && im.h == Hd) ? to_depth_f32(im, depth + (size_t)i * Wd * Hd) : RR_PNG_SIZE;
+        }
+        if (r != RR_OK) status[i] = r;          // two writers at most, both storing a failure code
+    });
+    int bad = 0;
+    for (int i = 0; i < n; i++) bad += status[i] != RR_OK;
+    return bad;
+}
+
+// Encodes n frames: 8-bit RGB files from bgr (n x H x W x 3, BGR order like the cv2.imwrite input) and 16-bit gray
+// mask files from the float32 masks; either list may be NULL.  Returns the number of files that failed.
+extern "C" int rr_host_png_write_batch(int n, const char *const *image_paths, const uint8_t *bgr, const char *const *mask_paths,
+                                       const float *mask, int W, int H, int level, int n_threads) {
+    if (n < 0 || W <= 0 || H <= 0 || (image_paths && !bgr) || (mask_paths && !mask) || level < 0 || level > 9) {
+        rr_set_error("rr_host_png_write_batch: bad arguments");
+        return RR_ERR_ARG;
+    }
+    std::atomic<int> bad(0);
+    parallel_for(2 * n, n_threads, [&](int j) {
+        const int i = j >> 1, kind = j & 1;
+        int r = RR_OK;
+        if (kind == 0 && image_paths && image_paths[i]) r = write_bgr8(image_paths[i], bgr + (size_t)i * 3 * W * H, W, H, level);
+        if (kind == 1 && mask_paths && mask_paths[i]) r = write_mask16(mask_paths[i], mask + (size_t)i * W * H, W, H, level);
+        if (r != RR_OK) bad.fetch_add(1);
+    });
+    if (bad.load()) rr_set_error("rr_host_png_write_batch: some files could not be written");
+    return bad.load();
+}

@@ -23,6 +23,13 @@ FOG_ATT = 1
 USE_DEPTH_WEIGHTING = 0
 
 
+try:
+    import matplotlib.pyplot as _plt        # noqa: F401  (identical mask files to the reference when matplotlib exists)
+    _HAVE_MATPLOTLIB = True
+except Exception:
+    _HAVE_MATPLOTLIB = False
+
+
 def _imsave_rgb(path, bgr_u8):
     cv2.imwrite(path, bgr_u8)
 
@@ -40,39 +47,83 @@ def _imsave_mask(path, mask):
 
 
 class _FramePipeline:
-    """Decode -> render -> encode with everything overlapped: PNG decoding and encoding run on a thread pool
-    (OpenCV releases the GIL), batches go through ``rr_submit_frames`` / ``rr_wait_frames`` with two sets of
-    page-locked buffers, so while batch k renders, batch k+1 is being decoded and copied in and batch k-1 is being
-    copied out and written.  The first batch is rendered synchronously (it sizes the patch arena)."""
+    """Decode -> render -> encode with everything overlapped.  Batches go through ``rr_submit_frames`` /
+    ``rr_wait_frames`` with two sets of page-locked buffers; PNG decoding and encoding run on native threads
+    (``rr_host_png_read_batch`` / ``rr_host_png_write_batch``, one ctypes call per batch, straight into / out of the
+    page-locked buffers), driven from two helper threads so that, while batch k renders, batch k+1 is being decoded
+    and batch k-1 is being written.  Files the native codec does not handle (or that need the reference's resize /
+    crop, generator.py:372-381) take ``fallback_decode`` (OpenCV).  The first batch is rendered synchronously (it
+    sizes the patch arena)."""
 
-    def __init__(self, ctx, batch, io_threads, alloc=None):
+    def __init__(self, ctx, batch, io_threads, fallback_decode=None, alloc=None, png_level=1):
         from concurrent.futures import ThreadPoolExecutor
-        self.ctx, self.batch = ctx, batch
+        self.ctx, self.batch, self.io_threads, self.png_level = ctx, batch, max(1, io_threads), png_level
+        self.fallback_decode = fallback_decode
         rs, W, H = ctx.render_scale, ctx.W, ctx.H
         alloc = alloc or _api.PinnedBuffer            # page-locked, so that the copies overlap the kernels
         self.sets = []
         for _ in range(2):
             self.sets.append(dict(bgr=alloc((batch, H * rs, W * rs, 3), np.uint8), depth=alloc((batch, H, W), np.float32),
                                   mask=alloc((batch, H, W), np.float32), u8=alloc((batch, H, W, 3), np.uint8),
-                                  writes=[], recs=None, offs=None, paths=[]))
-        self.pool = ThreadPoolExecutor(max_workers=max(1, io_threads))
+                                  writes=None, recs=None, offs=None, paths=[]))
+        self.pool = ThreadPoolExecutor(max_workers=2)      # one decode call and one encode call at a time; the threads are native
         self.inflight = []            # indices of the sets submitted and not yet waited for, oldest first
         self.turn = 0
         self.first = True
         self.frames_done = 0
+        self.pending = None           # (set index, decode future) of the batch pushed last
 
-    def decode_async(self, fn, *a):
-        return self.pool.submit(fn, *a)
+    # ---- decode ------------------------------------------------------------------------------------------------
+    def _decode_batch(self, si, entries):
+        """entries: (image file, depth file, frame index for the records, rgb path, mask path).  Fills the set's input
+        arrays, compacted over the frames that could be decoded; returns the surviving entries."""
+        from rain_rendering_b200 import pngio
+        s = self.sets[si]
+        n = len(entries)
+        if all(e[0].lower().endswith(".png") and e[1].lower().endswith(".png") for e in entries):
+            status = pngio.read_batch([e[0] for e in entries], [e[1] for e in entries], s["bgr"].array, s["depth"].array, self.io_threads)
+        else:
+            status = np.full(n, -1, np.int32)
+        ok = []
+        for k, e in enumerate(entries):
+            if status[k] != 0:
+                bg, depth = self.fallback_decode(e[0], e[1])
+                if bg is None:
+                    continue                              # corrupt depth: the reference skips the frame (generator.py:361-363)
+                if bg.shape != s["bgr"].array.shape[1:] or depth.shape != s["depth"].array.shape[1:]:
+                    raise AssertionError("frame size %s differs from the sequence size (%d, %d) (generator.py:250-258 reads it once)" % (bg.shape, self.ctx.W, self.ctx.H))
+                s["bgr"].array[k] = bg
+                s["depth"].array[k] = depth
+            ok.append(k)
+        for j, k in enumerate(ok):
+            if j != k:
+                s["bgr"].array[j] = s["bgr"].array[k]
+                s["depth"].array[j] = s["depth"].array[k]
+        return [entries[k] for k in ok]
 
-    def _write(self, s, k, rgb_path, mask_path):
-        os.makedirs(os.path.dirname(rgb_path), exist_ok=True)
-        os.makedirs(os.path.dirname(mask_path), exist_ok=True)
-        _imsave_rgb(rgb_path, s["u8"].array[k])
-        _imsave_mask(mask_path, s["mask"].array[k])
+    # ---- encode ------------------------------------------------------------------------------------------------
+    def _write_batch(self, si):
+        from rain_rendering_b200 import pngio
+        s = self.sets[si]
+        paths = s["paths"]
+        for d in {os.path.dirname(p) for pair in paths for p in pair}:
+            os.makedirs(d, exist_ok=True)
+        if _HAVE_MATPLOTLIB:              # byte-compatible mask files need matplotlib's colormap: per-file path
+            for k, (rgb_path, mask_path) in enumerate(paths):
+                _imsave_rgb(rgb_path, s["u8"].array[k])
+                _imsave_mask(mask_path, s["mask"].array[k])
+            return
+        bad = pngio.write_batch([p[0] for p in paths], s["u8"].array, [p[1] for p in paths], s["mask"].array, self.png_level, self.io_threads)
+        if bad:
+            raise IOError("%d output files could not be written under %s" % (bad, os.path.dirname(paths[0][0])))
+
+    def _schedule_writes(self, si):
+        s = self.sets[si]
+        s["writes"] = self.pool.submit(self._write_batch, si)
+        self.frames_done += len(s["paths"])
 
     def _finish_oldest(self):
         si = self.inflight[0]
-        s = self.sets[si]
         try:
             self.ctx.wait_frames()
         except _RainError as e:
@@ -94,39 +145,43 @@ class _FramePipeline:
         self.inflight.pop(0)
         self._schedule_writes(si)
 
-    def _schedule_writes(self, si):
-        s = self.sets[si]
-        s["writes"] = [self.pool.submit(self._write, s, k, p[0], p[1]) for k, p in enumerate(s["paths"])]
-        self.frames_done += len(s["paths"])
-
-    def process(self, decoded, assemble):
-        """decoded: list of (future -> (bg, depth) or (None, None), frame index for the records, rgb path, mask path);
-        assemble(frame index) -> records of that frame (called in frame order: the wind write-back is stateful)."""
+    # ---- the pipeline ------------------------------------------------------------------------------------------
+    def push(self, entries, assemble):
+        """Renders the batch pushed before this one, then starts decoding ``entries`` (so that the decode overlaps the
+        kernels just submitted).  assemble(frame index) -> records of that frame; it is called in frame order (the wind
+        write-back is stateful)."""
+        self._render_pending(assemble)
+        if not entries:
+            return
         si = self.turn
+        self.turn ^= 1
         s = self.sets[si]
-        if si in self.inflight:                       # (only with a single set in use) never overwrite buffers in flight
+        if si in self.inflight:                       # never overwrite buffers the GPU still reads
             self._finish_oldest()
-        for w in s["writes"]:
-            w.result()                                # the previous user of this set has been written to disk
-        s["writes"] = []
-        recs, offs, paths, n = [], [0], [], 0
-        for fut, f_name_idx, rgb_path, mask_path in decoded:
-            bg, depth = fut.result()
-            if bg is None:
-                continue
-            if (bg.shape[1], bg.shape[0]) != (self.ctx.W * self.ctx.render_scale, self.ctx.H * self.ctx.render_scale):
-                raise AssertionError("frame size %s differs from the sequence size (%d, %d) (generator.py:250-258 reads it once)" % (bg.shape, self.ctx.W, self.ctx.H))
-            r = assemble(f_name_idx)
-            assert len(r) <= 2 ** 16, "Assert that the number of drops doesn't overpass the uint16 rain_mask capacity"
-            s["bgr"].array[n] = bg
-            s["depth"].array[n] = depth
-            recs.append(r); offs.append(offs[-1] + len(r)); paths.append((rgb_path, mask_path))
-            n += 1
+        self.pending = (si, self.pool.submit(self._decode_batch, si, list(entries)))
+
+    def _render_pending(self, assemble):
+        if self.pending is None:
+            return
+        si, fut = self.pending
+        self.pending = None
+        s = self.sets[si]
+        kept = fut.result()
+        if s["writes"] is not None:
+            s["writes"].result()                      # the previous user of this set's output arrays is on disk
+            s["writes"] = None
+        n = len(kept)
         if n == 0:
             return
+        recs, offs = [], [0]
+        for e in kept:
+            r = assemble(e[2])
+            assert len(r) <= 2 ** 16, "Assert that the number of drops doesn't overpass the uint16 rain_mask capacity"
+            recs.append(r)
+            offs.append(offs[-1] + len(r))
         s["recs"] = np.concatenate(recs)
         s["offs"] = np.ascontiguousarray(offs, np.int32)
-        s["paths"] = paths
+        s["paths"] = [(e[3], e[4]) for e in kept]
         if self.first:
             self.ctx.render_frames(s["bgr"].array[:n], s["depth"].array[:n], s["recs"], s["offs"], None, s["mask"].array[:n], s["u8"].array[:n],
                                    want=("mask", "u8"))
@@ -137,22 +192,24 @@ class _FramePipeline:
             self.inflight.append(si)
             if len(self.inflight) == 2:
                 self._finish_oldest()
-        self.turn ^= 1
 
-    def finish(self):
+    def finish(self, assemble=None):
+        self._render_pending(assemble)
         while self.inflight:
             self._finish_oldest()
         for s in self.sets:
-            for w in s["writes"]:
-                w.result()
-            s["writes"] = []
+            if s["writes"] is not None:
+                s["writes"].result()
+                s["writes"] = None
 
     def close(self):
-        self.finish()
-        self.pool.shutdown(wait=True)
-        for s in self.sets:
-            for k in ("bgr", "depth", "mask", "u8"):
-                s[k].free()
+        try:
+            self.finish()
+        finally:
+            self.pool.shutdown(wait=True)
+            for s in self.sets:
+                for k in ("bgr", "depth", "mask", "u8"):
+                    s[k].free()
 
 
 class Generator:
@@ -197,7 +254,7 @@ class Generator:
         self.env_map_xyY = None
         self.solid_angle_map = None
         self.batch = int(os.environ.get("RAIN_B200_BATCH", "16"))
-        self.io_threads = int(os.environ.get("RAIN_B200_IO_THREADS", "8"))
+        self.io_threads = int(os.environ.get("RAIN_B200_IO_THREADS", str(min(32, os.cpu_count() or 8))))
         self.device = int(os.environ.get("LOCAL_RANK", os.environ.get("RAIN_B200_DEVICE", "0")))
         self._ctx = None
         self.check_folders()
@@ -309,8 +366,9 @@ class Generator:
                 print("{} images".format(len(idx)))
                 frames_exist_nb = 0
                 t0 = time.time()
-                pipe = _FramePipeline(ctx, self.batch, self.io_threads)
-                queue = []            # (decode future, frame index for the records, out paths)
+                pipe = _FramePipeline(ctx, self.batch, self.io_threads, fallback_decode=self._decode,
+                                      png_level=int(os.environ.get("RAIN_B200_PNG_LEVEL", "1")))
+                queue = []            # (image file, depth file, frame index for the records, out paths)
 
                 def assemble(f_name_idx):
                     sim = frame_render_dict[f_name_idx % len(frame_render_dict)]
@@ -338,13 +396,14 @@ class Generator:
                                 pass
                             else:
                                 raise NotImplementedError
-                        queue.append((pipe.decode_async(self._decode, image_file, depth_file), f_name_idx, out_rainy_path, out_rainy_mask_path))
+                        queue.append((image_file, depth_file, f_name_idx, out_rainy_path, out_rainy_mask_path))
                         if len(queue) == self.batch:
-                            pipe.process(queue, assemble)
+                            pipe.push(queue, assemble)
                             queue = []
                             if self.verbose:
                                 sys.stdout.write('\r%d/%d frames, %.1f frames/s   ' % (f_idx + 1, len(idx), (f_idx + 1) / (time.time() - t0)))
-                    pipe.process(queue, assemble)
+                    pipe.push(queue, assemble)
+                    pipe.finish(assemble)
                 finally:
                     pipe.close()
                 if frames_exist_nb > 0:

@@ -174,26 +174,41 @@ def test_frame_pipeline_orders_batches_and_recovers_from_arena_overflow(tmp_path
     sys.path.insert(0, DROPIN)
     try:
         import common.generator as gen
+        from PIL import Image
         from rain_rendering_b200.streaks import STREAK_DTYPE
-        ctx = _FakeCtx(overflow_on_wait)
-        pipe = gen._FramePipeline(ctx, batch=3, io_threads=4, alloc=_FakeBuf)
-        order = []
+        H, W = 16, 24
+        src = tmp_path / "src"
+        src.mkdir()
+        frames = list(range(11))
+        for i in frames:
+            cv2.imwrite(str(src / ("i%03d.png" % i)), np.full((H, W, 3), i, np.uint8))
+            cv2.imwrite(str(src / ("d%03d.png" % i)), np.full((H, W), i * 256, np.uint16))
+        (src / "d004.png").write_bytes(b"corrupt")                                  # the frame is skipped (generator.py:361-363)
+        Image.fromarray(np.full((H, W, 3), 7, np.uint8)).convert("P").save(str(src / "i007.png"))     # palette: OpenCV fallback
+        fallbacks = []
 
-        def decode(i):
-            if i == 4:
-                return None, None                      # corrupt depth: the frame is skipped (generator.py:361-363)
-            return np.full((16, 24, 3), i, np.uint8), np.full((16, 24), float(i), np.float32)
+        def fallback(image_file, depth_file):
+            fallbacks.append(os.path.basename(image_file))
+            d = cv2.imread(depth_file, cv2.IMREAD_UNCHANGED)
+            if d is None:
+                return None, None
+            return cv2.imread(image_file), d.astype(np.float32) / 256.
+
+        ctx = _FakeCtx(overflow_on_wait)
+        pipe = gen._FramePipeline(ctx, batch=3, io_threads=4, fallback_decode=fallback, alloc=_FakeBuf)
+        order = []
 
         def assemble(i):
             order.append(i)
             return np.zeros(i % 3 + 1, STREAK_DTYPE)
 
-        frames = list(range(11))
         for b0 in range(0, 11, 3):
-            q = [(pipe.decode_async(decode, i), i, str(tmp_path / "rainy_image" / ("%03d.png" % i)), str(tmp_path / "rain_mask" / ("%03d.png" % i)))
-                 for i in frames[b0:b0 + 3]]
-            pipe.process(q, assemble)
+            q = [(str(src / ("i%03d.png" % i)), str(src / ("d%03d.png" % i)), i, str(tmp_path / "rainy_image" / ("%03d.png" % i)),
+                  str(tmp_path / "rain_mask" / ("%03d.png" % i))) for i in frames[b0:b0 + 3]]
+            pipe.push(q, assemble)
+        pipe.finish(assemble)
         pipe.close()
+        assert sorted(fallbacks) == ["i004.png", "i007.png"]
         assert order == [i for i in frames if i != 4]               # records are assembled in frame order
         assert ctx.log[0][0] == "sync" and ctx.log[0][1] == 3       # the first batch sizes the arena
         assert [e[1] for e in ctx.log if e[0] == "submit"] == [2, 3, 2]
@@ -205,7 +220,7 @@ def test_frame_pipeline_orders_batches_and_recovers_from_arena_overflow(tmp_path
                 assert not p.exists()
                 continue
             img = cv2.imread(str(p))
-            assert img is not None and (img == i + 1).all(), i
+            assert img is not None and np.array_equal(img, cv2.imread(str(src / ("i%03d.png" % i))) + 1), i      # the fake context renders u8 = bgr + 1
             assert (tmp_path / "rain_mask" / ("%03d.png" % i)).exists()
         assert pipe.frames_done == 10
     finally:
