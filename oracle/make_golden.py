@@ -8,6 +8,8 @@ exact inputs.  Two fixtures:
   small_256x192.npz  2 frames, wind noise on, full float64 outputs + stage intermediates
   c1_640x480.npz     BASELINE config C1 (640x480, 10 mm/h, pre-computed XML): outputs as
                      float32 + SHA-256 of the float64 arrays (bit-exact pin of the oracle)
+  c2_1242x375.npz    BASELINE config C2's frame (1242x375, 25 mm/h): SHA-256 of the float64 outputs +
+                     the uint8 image the reference would save
 """
 from __future__ import annotations
 
@@ -40,7 +42,7 @@ def host_signature() -> str:
     return "numpy %s; cv2 %s [%s]; %s" % (np.__version__, cv2.__version__, ",".join(feats), platform.machine())
 
 
-def run(name, W, H, n_frames, fallrate, n_xml, seed, noise_scale, noise_std, opacity, n_sim_frames, full64):
+def run(name, W, H, n_frames, fallrate, n_xml, seed, noise_scale, noise_std, opacity, n_sim_frames, full64, compact=False):
     import cv2
     root = tempfile.mkdtemp(prefix="rr_golden_")
     try:
@@ -65,6 +67,8 @@ def run(name, W, H, n_frames, fallrate, n_xml, seed, noise_scale, noise_std, opa
             out["rain_mask"] = mask
             out["fog0"] = ref[names[0]]["fog"]
             out["env0_u8"] = np.round(ref[names[0]]["env"] * 255).astype(np.uint8)
+        elif compact:      # hashes of the float64 arrays + what plt.imsave would quantise to (small fixture for a large frame)
+            out["rainy_u8"] = (rainy * 255).astype(np.uint8)
         else:
             out["rainy_rgb_f32"] = rainy.astype(np.float32)
             out["rain_mask_f32"] = mask.astype(np.float32)
@@ -77,5 +81,11 @@ def run(name, W, H, n_frames, fallrate, n_xml, seed, noise_scale, noise_std, opa
 
 if __name__ == "__main__":
     assert ref_harness.reference_available(), "needs /root/reference (run in the build container)"
+    only = sys.argv[1:]
+    if not only or "c2_1242x375" in only:
+        # BASELINE config C2's frame shape and rain rate (KITTI optics, odd height): hashes + the quantised image
+        run("c2_1242x375", 1242, 375, 1, 25, 1000, seed=4, noise_scale=0.0, noise_std=0.0, opacity=1.0, n_sim_frames=1, full64=False, compact=True)
+    if only:
+        sys.exit(0)
     run("small_256x192", 256, 192, 3, 25, 600, seed=1, noise_scale=1.5, noise_std=3.0, opacity=0.8, n_sim_frames=2, full64=True)
     run("c1_640x480", 640, 480, 1, 10, 420, seed=2, noise_scale=0.0, noise_std=0.0, opacity=1.0, n_sim_frames=1, full64=False)

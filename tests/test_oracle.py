@@ -50,6 +50,19 @@ def test_oracle_native_reproduces_reference_golden_c1():
     assert np.abs(rainy - g["rainy_rgb_f32"]).max() < 5e-7
 
 
+def test_oracle_native_reproduces_reference_golden_c2_frame():
+    """BASELINE C2's frame shape (1242x375, odd height, KITTI optics) at 25 mm/h, 609 streaks: the fixture holds the
+    SHA-256 of the reference's float64 outputs and the uint8 image it would save."""
+    sc, g = golden_scenario("c2_1242x375")
+    outs, rainy, mask = _render_all(sc, "native")
+    assert [o.n_streaks for o in outs] == g["n_streaks"].tolist() == [609]
+    assert _sha(mask) == str(g["mask_sha"])                      # never touches the float32 stages: always bit-exact
+    if str(g["host"]) == host_signature():
+        assert _sha(rainy) == str(g["rainy_sha"])
+    u8 = (rainy * 255).astype(np.uint8)
+    assert np.abs(u8.astype(int) - g["rainy_u8"].astype(int)).max() <= 1 and (u8 != g["rainy_u8"]).mean() < 1e-4
+
+
 def test_canonical_mode_stays_within_float32_noise_of_native():
     sc, g = golden_scenario("small_256x192")
     _, rainy_c, mask_c = _render_all(sc, "canonical")
