@@ -70,6 +70,30 @@ def test_many_streaks_per_frame_and_a_wide_environment_map():
     ctx.close()
 
 
+def test_bright_frames_take_the_per_channel_in_scatter_path():
+    """With KITTI optics beta_hg * E_c exceeds 1 once the mean image level passes ~0.52: the clip of
+    add_attenuation.py:72 then acts on distant pixels and the three in-scatter images are no longer one image times a
+    scalar, so k_fog blurs each channel on its own.  Every other scenario of this suite stays below 1."""
+    sc = Scenario(320, 240, 1, 2500, fallrate=25)
+    sc.bgr = np.clip(sc.bgr.astype(np.float32) * 1.35 + 10, 0, 255).astype(np.uint8)
+    sc.depth = (sc.depth * 30).astype(np.float32)          # up to ~2.4 km: 1 - f_ext reaches 1, A (1 - f_ext) exceeds 1
+    c = sc.cam
+    g = 0.97
+    beta_hg = (1 - g * g) / (4 * np.pi * (1 + g * g) ** 1.5)
+    A = beta_hg * 4 * c.f_number ** 2 * (sc.bgr[0] / 255.0).reshape(-1, 3).mean(0) / (c.exposure_ms * 1e-3 * c.gain * np.pi)
+    assert (A > 1.05).all(), A
+    ctx = sc.context()
+    o = sc.oracle_frame(0, "canonical")
+    fog = ctx.fog_only(sc.bgr, sc.depth)[0]
+    assert np.abs(fog - np.moveaxis(o.fog, -1, 0)).max() < 1e-13
+    f_ext = np.exp(-0.312 * 25 ** 0.67 * sc.depth[0] / 1000.0)
+    assert (A.min() * (1 - f_ext)).max() > 1.0                                           # the clip at :72 really acts
+    recs, offs = sc.records()
+    out = ctx.render_frames(sc.bgr, sc.depth, recs, offs)
+    _check_frame(out, 0, o)
+    ctx.close()
+
+
 def test_render_scale_2_cityscapes_arrangement():
     """BASELINE C3 shape: frames arrive at twice the render size and are reduced on the device."""
     sc = Scenario(512, 256, 2, 1800, fallrate=50, dataset="cityscapes", render_scale=2)
