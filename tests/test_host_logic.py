@@ -104,3 +104,29 @@ def test_xml_loader_and_record_assembly_match_the_oracle_parser():
             if s.drop_type != ro.BIG:
                 ro.make_patch(s, sc.db.textures[ti], sc.cam, noise)      # mutates s.ip1/ip2 like the reference
             assert np.array_equal(s.ip1, q["ip1m"]) and np.array_equal(s.ip2, q["ip2m"])
+
+
+def test_public_header_is_plain_c(tmp_path):
+    """include/rain_b200.h is the drop-in boundary: it must compile as C (no C++ types in the signatures) and a C
+    caller must be able to link the host-side entry points."""
+    import subprocess
+    from rain_rendering_b200 import build as B
+    src = tmp_path / "use.c"
+    src.write_text(
+        '#include "rain_b200.h"\n'
+        '#include <stdio.h>\n'
+        'int main(void) {\n'
+        '    rr_streak_rec r; rr_camera c; rr_sim_params p; rr_sim_streak s; rr_xml_frame f;\n'
+        '    double k64[25]; float k32[25]; int k15[15];\n'
+        '    (void)r; (void)c; (void)p; (void)s; (void)f;\n'
+        '    rr_host_tables(k64, k32, k15);\n'
+        '    printf("%d %d %d %d %.6f\\n", rr_version(), (int)sizeof(rr_streak_rec), (int)sizeof(rr_sim_streak), (int)sizeof(rr_xml_frame), k64[12]);\n'
+        '    return 0;\n'
+        '}\n')
+    exe = str(tmp_path / "use")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", exe,
+                           B.LIB, "-Wl,-rpath," + os.path.dirname(B.LIB)])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert out.returncode == 0, out.stderr
+    ver, rec, sim, xf, k = out.stdout.split()
+    assert (int(rec), int(sim), int(xf)) == (128, 120, 32) and int(ver) >= 100 and abs(float(k) - 0.041670) < 1e-5
