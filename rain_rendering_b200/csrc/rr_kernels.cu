@@ -978,42 +978,11 @@ cudaError_t rr_launch_scan(const rr_frame_bufs &b, int n_streaks, cudaStream_t s
 #define RAS_MAXD 1024         // patch pixels with accumulators resident in shared memory
 #define RAS_RBMAX 128         // rows per band of the area-fast path (RAS_CAP / canvas width; canvases are at least 32 wide)
 
-#define RAS_DO_PRAGMA_(x) _Pragma(#x)
-#define RAS_DO_PRAGMA(x) RAS_DO_PRAGMA_(x)
-#ifdef RAS_UNROLL
-#define RAS_PRAGMA_UNROLL RAS_DO_PRAGMA(unroll RAS_UNROLL)
-#else
-#define RAS_PRAGMA_UNROLL
-#endif
-#ifndef RAS_INTW
-#define RAS_INTW 1            // bilinear weights from integer products (below) instead of float32 arithmetic
-#endif
-#ifndef RAS_INTERIOR
-#define RAS_INTERIOR 0        // runs whose taps all lie inside the texture skip the border predicates (sweep r01h: slower, 1.23 vs 1.13 ms)
-#endif
 // Bilinear weights of remapBilinear: w = (1 - fy/32 or fy/32) * (1 - fx/32 or fx/32) in float32.  With 5-bit fractions
 // both factors and their product are exact, so w == p / 1024 with the integer p = {32 - fy, fy} * {32 - fx, fx}, and
-// fl(v * w) == fl((v / 1024) * p) bit for bit (scaling by a power of two is exact): with RAS_INTW the kernel keeps the
-// texture look-up table pre-scaled by 2^-10 (lut[u] = u / 255.0 / 1024) and multiplies by the integer products.
-struct ras_w { double w0, w1, w2, w3; };
-__device__ __forceinline__ ras_w ras_weights(int X, int Y) {
-    const int fx = X & (RR_INTER_TAB - 1), fy = Y & (RR_INTER_TAB - 1);
-    ras_w w;
-#if RAS_INTW
-    const int gx = RR_INTER_TAB - fx, gy = RR_INTER_TAB - fy;
-    w.w0 = (double)(gy * gx); w.w1 = (double)(gy * fx); w.w2 = (double)(fy * gx); w.w3 = (double)(fy * fx);
-#else
-    const float s = 1.f / RR_INTER_TAB;
-    const float ax1 = fx * s, ax0 = 1.f - ax1, ay1 = fy * s, ay0 = 1.f - ay1;
-    w.w0 = ay0 * ax0; w.w1 = ay0 * ax1; w.w2 = ay1 * ax0; w.w3 = ay1 * ax1;
-#endif
-    return w;
-}
-#if RAS_INTW
+// fl(v * w) == fl((v / 1024) * p) bit for bit (scaling by a power of two is exact): the kernel keeps the texture
+// look-up table pre-scaled by 2^-10 (lut[u] = u / 255.0 / 1024) and multiplies by the integer products.
 #define RAS_LUT_SCALE 0.0009765625
-#else
-#define RAS_LUT_SCALE 1.0
-#endif
 __device__ __forceinline__ double ras_sample(const uint8_t *tex, int tw, int th, const double *lut, int X, int Y) {
     // rr_warp_affine_linear with the fixed-point coordinates already formed.  One code path for interior and
     // border samples (out-of-texture taps contribute the border value 0 with their weight, exactly the
@@ -1022,20 +991,15 @@ __device__ __forceinline__ double ras_sample(const uint8_t *tex, int tw, int th,
     const bool x0ok = (unsigned)sx < (unsigned)tw, x1ok = (unsigned)(sx + 1) < (unsigned)tw;
     const bool y0ok = (unsigned)sy < (unsigned)th, y1ok = (unsigned)(sy + 1) < (unsigned)th;
     if (!((x0ok | x1ok) & (y0ok | y1ok))) return 0.0;               // all four taps outside: the border constant
-    const ras_w w = ras_weights(X, Y);
+    const int fx = X & (RR_INTER_TAB - 1), fy = Y & (RR_INTER_TAB - 1);
+    const int gx = RR_INTER_TAB - fx, gy = RR_INTER_TAB - fy;
+    const double w0 = (double)(gy * gx), w1 = (double)(gy * fx), w2 = (double)(fy * gx), w3 = (double)(fy * fx);
     const uint8_t *S = tex + sy * tw + sx;
     const double v0 = (x0ok & y0ok) ? lut[S[0]] : 0.0;
     const double v1 = (x1ok & y0ok) ? lut[S[1]] : 0.0;
     const double v2 = (x0ok & y1ok) ? lut[S[tw]] : 0.0;
     const double v3 = (x1ok & y1ok) ? lut[S[tw + 1]] : 0.0;
-    return v0 * w.w0 + v1 * w.w1 + v2 * w.w2 + v3 * w.w3;
-}
-// the same for a sample whose four taps are known to lie inside the texture
-__device__ __forceinline__ double ras_sample_interior(const uint8_t *tex, int tw, const double *lut, int X, int Y) {
-    const int sx = X >> RR_INTER_BITS, sy = Y >> RR_INTER_BITS;
-    const ras_w w = ras_weights(X, Y);
-    const uint8_t *S = tex + sy * tw + sx;
-    return lut[S[0]] * w.w0 + lut[S[1]] * w.w1 + lut[S[tw]] * w.w2 + lut[S[tw + 1]] * w.w3;
+    return v0 * w0 + v1 * w1 + v2 * w2 + v3 * w3;
 }
 
 __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs b, rr_static_tabs t, rr_cam_dev cam, int n) {
@@ -1112,27 +1076,11 @@ __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs 
                     if (c_lo <= c_hi) {
                         const double aF = tx.a_first, aM = tx.a_mid, aL = tx.a_last;
                         const int m_lo = tx.s_first, m_hi = tx.s_first + tx.n;       // full-weight columns [m_lo, m_hi)
-                        // source coordinates move monotonically along the row: if both ends of the run have all four
-                        // taps inside the texture, every sample of the run has
-                        const int sxa = (xr + adx[c_lo]) >> 10, sxb = (xr + adx[c_hi]) >> 10;
-                        const int sya = (yr + bdx[c_lo]) >> 10, syb = (yr + bdx[c_hi]) >> 10;
-                        const bool interior = RAS_INTERIOR && sxa >= 0 && sxb >= 0 && sxa <= tw - 2 && sxb <= tw - 2 &&
-                                              sya >= 0 && syb >= 0 && sya <= th - 2 && syb <= th - 2;
-                        if (interior) {
-                            for (int c = c_lo; c <= c_hi; c++) {
-                                const double alpha = c < m_lo ? aF : (c >= m_hi ? aL : aM);
-                                const int X = (xr + adx[c]) >> (10 - RR_INTER_BITS);
-                                const int Y = (yr + bdx[c]) >> (10 - RR_INTER_BITS);
-                                buf += ras_sample_interior(tex, tw, lut, X, Y) * alpha;
-                            }
-                        } else {
-                            RAS_PRAGMA_UNROLL
-                            for (int c = c_lo; c <= c_hi; c++) {
-                                const double alpha = c < m_lo ? aF : (c >= m_hi ? aL : aM);
-                                const int X = (xr + adx[c]) >> (10 - RR_INTER_BITS);
-                                const int Y = (yr + bdx[c]) >> (10 - RR_INTER_BITS);
-                                buf += ras_sample(tex, tw, th, lut, X, Y) * alpha;
-                            }
+                        for (int c = c_lo; c <= c_hi; c++) {
+                            const double alpha = c < m_lo ? aF : (c >= m_hi ? aL : aM);
+                            const int X = (xr + adx[c]) >> (10 - RR_INTER_BITS);
+                            const int Y = (yr + bdx[c]) >> (10 - RR_INTER_BITS);
+                            buf += ras_sample(tex, tw, th, lut, X, Y) * alpha;
                         }
                     }
                     CB[r * pw + dx] = buf;
