@@ -27,8 +27,11 @@ assert common.generator.__file__.startswith(%r), common.generator.__file__
 assert common.bad_weather.__file__.startswith(%r)
 assert common.db.__file__.startswith(%r), common.db.__file__
 assert main.Generator is common.generator.Generator
+import tools.particles_simulation as tps          # what main.py:206-208 imports when a particles XML is missing
+assert tps.__file__.startswith(%r), tps.__file__
+assert callable(tps.process)
 print("OK")
-""" % (DROPIN, ROOT, os.path.join(ROOT, "oracle", "ref_shims"), REF, REF, DROPIN, DROPIN, REF)
+""" % (DROPIN, ROOT, os.path.join(ROOT, "oracle", "ref_shims"), REF, REF, DROPIN, DROPIN, REF, DROPIN)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
 
@@ -226,4 +229,78 @@ def test_frame_pipeline_orders_batches_and_recovers_from_arena_overflow(tmp_path
     finally:
         sys.path.remove(DROPIN)
         for k in [k for k in sys.modules if k == "common" or k.startswith("common.")]:
+            del sys.modules[k]
+
+
+class _FakeSimCtx:
+    """Stands in for RainContext.simulate_particles: deterministic streaks, records the calls."""
+
+    def __init__(self):
+        self.calls = []
+
+    def simulate_particles(self, first_frame, n_frames, W, H, fallrate, **kw):
+        from rain_rendering_b200.streaks import SIM_STREAK_DTYPE
+        self.calls.append((first_frame, n_frames, W, H, fallrate, kw))
+        frames = []
+        for f in range(first_frame, first_frame + n_frames):
+            rng = np.random.RandomState(1000 + f)
+            n = 40 + f
+            r = np.zeros(n, SIM_STREAK_DTYPE)
+            r["pid"] = np.arange(n) + 7
+            z = rng.uniform(0.3, 4, n)
+            r["wp1"] = np.stack([rng.uniform(-1, 1, n), rng.uniform(-0.5, 0.5, n), -z], 1)
+            r["wp2"] = r["wp1"] + np.stack([np.zeros(n), -rng.uniform(0.005, 0.02, n), np.zeros(n)], 1)
+            r["wd1"] = r["wd2"] = rng.uniform(5e-4, 4e-3, n)
+            r["ip1"] = np.stack([rng.uniform(0, W, n), rng.uniform(0, H, n)], 1)
+            r["ip2"] = r["ip1"] + np.stack([rng.normal(0, 1, n), -rng.uniform(3, 60, n)], 1)
+            r["iw1"] = r["iw2"] = rng.uniform(0.3, 6, n)
+            frames.append(r)
+        return frames, 123.0
+
+
+def test_dropin_particles_simulation_writes_the_xml_main_py_expects(tmp_path):
+    for k in [k for k in sys.modules if k == "tools" or k.startswith("tools.")]:
+        del sys.modules[k]
+    sys.path.insert(0, DROPIN)
+    try:
+        import tools.particles_simulation as ps
+        from rain_rendering_b200 import streaks as S
+        assert ps.__file__.startswith(DROPIN)
+        opts = dict(cam_hz=10, cam_WH=[640, 480], cam_CCD_WH=[640, 480], cam_CCD_pixsize=4.65, cam_focal=6, cam_exposure=2, sim_hz=2000,
+                    sim_mode="normal", sim_duration=0.6, sim_steps={}, sequences={"a": 1})
+        ctx = _FakeSimCtx()
+        root = str(tmp_path / "particles" / "customdb" / "seq1")
+        weather = {"weather": "rain", "fallrate": 25}
+        path = ps.simulate_to_xml(root, opts, weather, ctx=ctx)
+        # the file main.py globs for (common/my_utils.py:172-173), one device call for the six frames of 0.6 s at 10 Hz
+        import glob
+        assert glob.glob(os.path.join(root, "rain", "25mm", "*_camera0.xml")) == [path]
+        assert [(c[0], c[1], c[2], c[3], c[4]) for c in ctx.calls] == [(0, 6, 640, 480, 25.0)]
+        assert ctx.calls[0][5]["focal_mm"] == 6.0 and ctx.calls[0][5]["sim_hz"] == 2000.0 and ctx.calls[0][5]["seed"] == 0
+        assert os.path.exists(os.path.join(root, "rain", "25mm", "sim_options.json"))
+        # the loader reads back exactly the records the in-memory path would build from the device output
+        frames, ids = S.load_streaks_from_xml(path, 1, 640, 480, with_ids=True)
+        want, _ = _FakeSimCtx().simulate_particles(0, 6, 640, 480, 25)
+        assert ids == list(range(6))
+        for got, w in zip(frames, want):
+            ref = S.records_from_sim(w, 1, 640, 480)
+            assert got.tobytes() == ref.tobytes() or all(np.array_equal(got[n], ref[n], equal_nan=True) if got[n].dtype.kind == "f" else
+                                                         np.array_equal(got[n], ref[n]) for n in S.STREAK_DTYPE.names)
+        # an existing simulation is kept unless forced (tools/simulation.py:262-269)
+        assert ps.simulate_to_xml(root, opts, weather, ctx=ctx) is None and len(ctx.calls) == 1
+        assert ps.simulate_to_xml(root, opts, weather, redo=True, ctx=ctx) == path and len(ctx.calls) == 2
+        # steps mode: one camera frame per step, a parameter stays applied until changed (common/db.py:44-58)
+        opts2 = dict(opts, sim_mode="steps", sim_steps={"cam_motion": [0, 0, 30, 30, 50], "rain_fallrate": [5, 5, 5, 5, 5]})
+        ctx2 = _FakeSimCtx()
+        ps.simulate_to_xml(str(tmp_path / "p2"), opts2, weather, ctx=ctx2)
+        assert [(c[0], c[1], c[4], c[5]["cam_speed_kmh"]) for c in ctx2.calls] == [(0, 2, 5.0, 0.0), (2, 2, 5.0, 30.0), (4, 1, 5.0, 50.0)]
+        # process(): the reference's signature and loops (tools/particles_simulation.py:23-42)
+        ps._ctx = _FakeSimCtx()
+        out = ps.process({"path": [str(tmp_path / "p3"), str(tmp_path / "p4")], "options": [opts, opts],
+                          "weather": [weather, {"weather": "rain", "fallrate": 50}]}, force_recompute=True)
+        assert len(out) == 4 and len(ps._ctx.calls) == 4
+        ps._ctx = None
+    finally:
+        sys.path.remove(DROPIN)
+        for k in [k for k in sys.modules if k == "tools" or k.startswith("tools.")]:
             del sys.modules[k]
