@@ -293,7 +293,7 @@ extern "C" int rr_host_png_read_batch(int n, const char *const *image_paths, con
             if (kind == 0) r = (im.w == Wi && im.h == Hi) ? to_bgr8(im, bgr + (size_t)i * 3 * Wi * Hi) : RR_PNG_SIZE;
             else r = (im.w == Wd && im.h == Hd) ? to_depth_f32(im, depth + (size_t)i * Wd * Hd) : RR_PNG_SIZE;
         }
-        if (r != RR_OK) status[i] = r;          // two writers at most, both storing a failure code
+        if (r != RR_OK) __atomic_store_n(&status[i], (int32_t)r, __ATOMIC_RELAXED);     // two writers at most (image, depth), both storing a failure code
     });
     int bad = 0;
     for (int i = 0; i < n; i++) bad += status[i] != RR_OK;
