@@ -203,7 +203,7 @@ RR_HD int rr_clip_fov_polygon(const double *px, const double *py, int n, int col
             }
         }
     }
-    if (n < 3) return 0;
+    if (n < 3 || n >= RR_MAX_POLY) return 0;      // the closing vertex needs slot n (24 cone vertices + clipping never get there)
     int64_t a = 0;
     for (int i = 0; i < n; i++) {
         int j = i ? i - 1 : n - 1;
