@@ -124,13 +124,9 @@ def process(sim, force_recompute=False):
 
 
 def process_sequences(sequences, weathers, force_recompute=False):
+    """(dataset, sequence) pairs -> their simulation folders and per-sequence options (``common.db.sim``), then
+    ``process`` -- the entry point of the reference's stand-alone script (tools/particles_simulation.py:8-20)."""
     from common import my_utils, db
-    simulations = {"path": [], "options": [], "weather": weathers}
-    print("Resolve sequences...")
-    for s in sequences:
-        db_n, seq = s[0], my_utils.path_os_s(s[1])
-        sim = db.sim(db_n, seq, os.path.join(particles_root, db_n))
-        simulations["path"].append(sim["path"])
-        simulations["options"].append(sim["options"])
-    print("Run process...")
-    return process(simulations, force_recompute=force_recompute)
+    sims = [db.sim(name, my_utils.path_os_s(seq), os.path.join(particles_root, name)) for name, seq in sequences]
+    return process({"path": [s["path"] for s in sims], "options": [s["options"] for s in sims], "weather": weathers},
+                   force_recompute=force_recompute)
