@@ -61,7 +61,8 @@ def test_fill_convex_poly_restatement_equals_cv2(hs):
         assert np.array_equal(mine.astype(bool), ref.astype(bool)), (trial, pts.tolist())
 
 
-@pytest.mark.parametrize("W,H,n_xml,exposure_ds,noise", [(1242, 375, 700, "kitti", 3.0), (640, 480, 2500, "kitti", 0.0), (1600, 900, 400, "nuscenes", 0.0)])
+@pytest.mark.parametrize("W,H,n_xml,exposure_ds,noise", [(1242, 375, 700, "kitti", 3.0), (640, 480, 2500, "kitti", 0.0), (1600, 900, 400, "nuscenes", 0.0),
+                                                         (1024, 512, 500, "cityscapes", 8.0)])
 def test_patch_and_fov_mask_equal_oracle(hs, W, H, n_xml, exposure_ds, noise):
     sc = Scenario(W, H, 1, n_xml, dataset=exposure_ds, noise_scale=1.0 if noise else 0.0, noise_std=noise, seed=3)
     cam = sc.cam
