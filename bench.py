@@ -154,14 +154,18 @@ def _cpu_worker(step):
     return time.perf_counter() - t0, r.n_streaks
 
 
-def cpu_steps(steps, warmup, n_workers):
+def cpu_steps(steps, warmup, n_workers, budget_s=None):
     """Each step: n_workers processes render one C2 frame each (the reference's own scale-out is
-    process-level over disjoint frames, main_threaded.py:109-176).  Returns per-step wall seconds."""
+    process-level over disjoint frames, main_threaded.py:109-176).  Returns per-step wall seconds.
+    A frame takes several seconds on a core, so a step cannot be made shorter than that; with ``budget_s`` the run
+    stops early (after at least one timed step) once warm-up + timed steps have used the budget, so that the arm
+    always ends within a few minutes whatever --steps says."""
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     times, streaks = [], []
     with ctx.Pool(n_workers, initializer=_cpu_init, initargs=(WORKLOAD, 7000)) as pool:
         pool.map(_cpu_ready, range(n_workers * 4))          # all workers initialised before anything is timed
+        t_start = time.perf_counter()
         for s in range(warmup + steps):
             t0 = time.perf_counter()
             res = pool.map(_cpu_worker, [s] * n_workers, chunksize=1)
@@ -169,6 +173,12 @@ def cpu_steps(steps, warmup, n_workers):
             if s >= warmup:
                 times.append(dt)
                 streaks += [r[1] for r in res]
+            used = time.perf_counter() - t_start
+            if budget_s is not None and used + dt > budget_s:
+                if s < warmup:
+                    warmup = s + 1                            # no time for more warm-up: the next step is timed
+                elif times:
+                    break
     return times, streaks
 
 
@@ -194,12 +204,16 @@ def run_reference(args):
     # 32 processes 1.8 frames/s on 128 cores) and only stretch the step, so the sample is capped at 16.
     workers = max(1, min(cores, 16))
     wl = synth.WORKLOADS[WORKLOAD]
-    times, streaks = cpu_steps(args.steps, args.warmup, workers)
+    budget = float(os.environ.get("RR_REFERENCE_BUDGET_S", "240"))
+    times, streaks = cpu_steps(args.steps, args.warmup, workers, budget_s=budget)
     total = float(np.sum(times))
     fps = workers * len(times) / total
     sample = "%d processes x 1 frame per step (%dx%d, %d mm/h, ~%d streaks/frame), oracle port of the reference algorithm, " \
              "cv2 threads 1 per process, per-camera tables/solid angles and synthetic inputs prepared outside the timed region" % (workers, wl["W"], wl["H"], wl["fallrate"], int(np.mean(streaks)))
-    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+    if len(times) < args.steps:
+        sample += "; %d of the %d requested steps timed (a step is %.1f s of CPU work per core; wall-clock budget %d s, RR_REFERENCE_BUDGET_S)" % (
+            len(times), args.steps, total / len(times), int(budget))
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": len(times), "steps_requested": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C2 KITTI 1242x375 25mm/hr", "frames_per_step": workers, "streaks_per_frame": float(np.mean(streaks))},
