@@ -87,7 +87,7 @@ int decode(const char *path, Image *img, bool header_only) {
                 break;
             }
             stride = (size_t)img->w * img->channels * (img->depth / 8);
-            raw.resize((stride + 1) * (size_t)img->h);
+            raw.resize((stride + 1) * (size_t)img->h + 1);      // one spare byte: the stream must END (Adler-32 verified), not just fill the image
             if (inflateInit(&zs) != Z_OK) break;
             z_open = true;
             zs.next_out = raw.data();
@@ -100,7 +100,7 @@ int decode(const char *path, Image *img, bool header_only) {
             if (r == Z_STREAM_END) z_done = true;
             else if (r != Z_OK && r != Z_BUF_ERROR) break;
         } else if (!memcmp(type, "IEND", 4)) {
-            if (z_open && (z_done || zs.avail_out == 0) && zs.total_out == raw.size()) ret = RR_OK;
+            if (z_open && z_done && zs.total_out == raw.size() - 1) ret = RR_OK;
             break;
         }
         pos += 12 + (size_t)len;

@@ -95,3 +95,60 @@ def test_codec_speed_on_a_kitti_sized_frame(tmp_path):
     t0 = time.perf_counter(); [(cv2.imwrite(p + "c.png", out[0]), cv2.imwrite(p + "cm.png", (m[0] * 65535).astype(np.uint16))) for _ in range(3)]; t_cw = (time.perf_counter() - t0) / 3
     print("decode native %.1f ms vs cv2 %.1f ms; encode native %.1f ms vs cv2 %.1f ms (one thread, image + depth/mask)" % (t_rd * 1e3, t_cv * 1e3, t_wr * 1e3, t_cw * 1e3))
     assert np.array_equal(out[0], bgr) and t_wr < 1.2 * t_cw and t_rd < 1.5 * t_cv
+
+
+def test_corrupted_pixel_data_is_rejected_not_decoded(tmp_path):
+    """A flipped byte inside the compressed stream must fail zlib's Adler-32 (or the stream structure), never yield a
+    silently different image: the frame then takes the OpenCV fallback, which reports the file the way the reference
+    sees it."""
+    arr = _rand((40, 64, 3), np.uint8, 3)
+    p = str(tmp_path / "a.png")
+    cv2.imwrite(p, arr)
+    raw = bytearray(open(p, "rb").read())
+    i = raw.index(b"IDAT") + 4 + 40
+    raw[i] ^= 0x55
+    q = str(tmp_path / "bad.png")
+    open(q, "wb").write(bytes(raw))
+    out = np.zeros((2, 40, 64, 3), np.uint8)
+    st = pngio.read_batch([p, q], None, out, None, 2)
+    assert st[0] == 0 and st[1] != 0 and np.array_equal(out[0], arr)
+
+
+def test_native_parsers_survive_mutated_files(tmp_path):
+    """Truncated / mutated PNG and particles-XML files must be rejected (or read), never crash the process: run in a child."""
+    import subprocess
+    import sys
+    code = r'''
+import os, random, sys
+import numpy as np, cv2
+sys.path.insert(0, %r)
+from rain_rendering_b200 import pngio, streaks as S, synth, _lib
+random.seed(7); rng = np.random.RandomState(7); d = %r
+H, W = 21, 35
+base = []
+for k, arr in enumerate([rng.randint(0, 256, (H, W, 3)).astype(np.uint8), rng.randint(0, 65536, (H, W)).astype(np.uint16)]):
+    p = os.path.join(d, "b%%d.png" %% k); cv2.imwrite(p, arr); base.append(open(p, "rb").read())
+out = np.zeros((1, H, W, 3), np.uint8); dep = np.zeros((1, H, W), np.float32)
+def mutate(b, alphabet=None):
+    b = bytearray(b); m = random.random()
+    if m < 0.3: return bytes(b[:random.randrange(len(b))])
+    if m < 0.8:
+        for _ in range(random.randrange(1, 6)): b[random.randrange(len(b))] = random.choice(alphabet) if alphabet else random.randrange(256)
+        return bytes(b)
+    i = random.randrange(len(b)); b[i:i] = bytes((random.choice(alphabet) if alphabet else random.randrange(256)) for _ in range(random.randrange(1, 30)))
+    return bytes(b)
+for it in range(400):
+    p = os.path.join(d, "f.png"); open(p, "wb").write(mutate(random.choice(base)))
+    pngio.read_batch([p], [p], out, dep, 2)
+    try: pngio.info(p)
+    except Exception: pass
+parts = synth.make_particles(320, 240, 2, 40, 2.0, seed=3)
+x = os.path.join(d, "s_camera0.xml"); synth.write_particles_xml(parts, x, 2.0); xb = open(x, "rb").read()
+for it in range(400):
+    p = os.path.join(d, "f.xml"); open(p, "wb").write(mutate(xb, b"<>/\"'=[]; \n0123456789.e-x&"))
+    try: S.load_streaks_from_xml(p, 1, 320, 240)
+    except _lib.RainError: pass
+print("SURVIVED")
+''' % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(tmp_path))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "SURVIVED" in out.stdout, (out.returncode, out.stderr[-1500:])
