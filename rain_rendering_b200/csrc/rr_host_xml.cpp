@@ -199,6 +199,8 @@ bool make_record(const std::vector<Attr> &attrs, int render_scale, int H, rr_str
     const double nrm = norm2_np(dx, dy);
     const double cos_theta = 0 * (dx / nrm) + -1 * (-(dy / nrm));                     // :228-231
     const double ratio = (double)max_width / (dy / cos_theta);                        // :232-233
+    for (int i = 0; i < 2; i++)                                                       // a coordinate no image has: refuse it rather than
+        if (!(fabs(ip1[i]) < 1e9) || !(fabs(ip2[i]) < 1e9)) return false;             // overflow the integer conversions below (NaN included)
     const long long x1 = (long long)nearbyint(ip1[0]), y1 = (long long)nearbyint(ip1[1]);   // :234-235 half-even
     const long long x2 = (long long)nearbyint(ip2[0]), y2 = (long long)nearbyint(ip2[1]);
     const double ex = (double)(x1 - x2), ey = (double)(y1 - y2);
