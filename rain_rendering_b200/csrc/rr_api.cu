@@ -43,7 +43,7 @@ struct rr_context {
     rr_fog_consts fogc;
     int max_batch = 0, H_env = 0, W_env = 0, cyl_w = 0;
     int32_t *d_env_src = nullptr;
-    uint8_t *d_env_written = nullptr;
+    uint8_t *d_env_written = nullptr, *d_env_tile_hole = nullptr;
     double *d_omega = nullptr, *d_omega_pref = nullptr, *d_omega_total = nullptr;
     // per batch
     uint8_t *d_bgr = nullptr;
@@ -97,7 +97,7 @@ static void free_camera(rr_context *c) {
     c->have_cam = false;
     c->streak_cap = 0;
     memset(&c->fb, 0, sizeof(c->fb));
-    c->d_env_src = nullptr; c->d_env_written = nullptr; c->d_omega = c->d_omega_pref = c->d_omega_total = nullptr;
+    c->d_env_src = nullptr; c->d_env_written = nullptr; c->d_env_tile_hole = nullptr; c->d_omega = c->d_omega_pref = c->d_omega_total = nullptr;
     c->d_bgr = nullptr; c->d_bgf = nullptr; c->d_depth = nullptr; c->d_streaks = nullptr; c->d_offsets = nullptr;
     c->d_sub_offsets = nullptr; c->d_err2 = nullptr;
 }
@@ -271,6 +271,7 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
     // static tables
     CK(dev_alloc(c, &c->d_env_src, (size_t)He * We));
     CK(dev_alloc(c, &c->d_env_written, (size_t)He * We));
+    CK(dev_alloc(c, &c->d_env_tile_hole, (size_t)((He + 15) / 16) * ((We + 63) / 64)));
     CK(dev_alloc(c, &c->d_omega, (size_t)He * We));
     CK(dev_alloc(c, &c->d_omega_pref, (size_t)He * (We + 1)));
     CK(dev_alloc(c, &c->d_omega_total, (size_t)1));
@@ -278,9 +279,10 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
         int32_t *scratch;
         CK(cudaMalloc((void **)&scratch, (size_t)H * c->cyl_w * 9 + 256));
         CK(rr_launch_env_tables(W, H, f, c->cyl_w, min_x, We, c->d_env_src, c->d_env_written, scratch, c->stream));
+        CK(rr_launch_env_tile_flags(c->d_env_written, c->d_env_tile_hole, He, We, c->stream));
         CK(cudaStreamSynchronize(c->stream));
         CK(cudaFree(scratch));
-        c->launches += 4;
+        c->launches += 5;
     }
     CK(rr_launch_omega(He, We, c->d_omega, c->d_omega_pref, c->d_omega_total, c->stream));
     c->launches += 3;
@@ -334,7 +336,7 @@ int rr_env_size(rr_context *c, int *H_env, int *W_env) {
 
 static rr_static_tabs tabs_of(rr_context *c) {
     rr_static_tabs t;
-    t.env_src = c->d_env_src; t.env_written = c->d_env_written; t.omega = c->d_omega; t.omega_pref = c->d_omega_pref;
+    t.env_src = c->d_env_src; t.env_written = c->d_env_written; t.env_tile_hole = c->d_env_tile_hole; t.omega = c->d_omega; t.omega_pref = c->d_omega_pref;
     t.omega_total = c->d_omega_total; t.db = c->d_db; t.tex_off = c->d_tex_off; t.tex_h = c->d_tex_h;
     return t;
 }

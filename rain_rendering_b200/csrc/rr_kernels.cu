@@ -569,15 +569,10 @@ cudaError_t rr_launch_planar_to_bg8(const double *planar, uint8_t *bg8, int F, i
 // Gather through the static source-index table and, for the never-written pixels, OpenCV's fixed-point
 // 15x15 Gaussian of the gathered map (bad_weather.py:814-817), in one pass: tiles without holes are a pure gather.
 // Pixels travel as one 32-bit word (B, G, R, 0): one load and one store per pixel instead of three each.
-__global__ void __launch_bounds__(256) k_env_map(const uint8_t *bg8, const int32_t *env_src, const uint8_t *env_written, uint8_t *env8,
-                                                 int H, int W_env, int npix_img) {
-    __shared__ unsigned in[ENV_TY + 2 * ENV_R][ENV_TX + 2 * ENV_R];
-    __shared__ unsigned short hp[ENV_TY + 2 * ENV_R][ENV_TX][3];
+// per-camera: does the tile contain a never-written pixel?  (the answer is the same for every frame)
+__global__ void __launch_bounds__(256) k_env_tile_flags(const uint8_t *env_written, uint8_t *tile_hole, int H, int W_env) {
     __shared__ int any_hole;
-    const int f = blockIdx.z;
     const int x0 = blockIdx.x * ENV_TX, y0 = blockIdx.y * ENV_TY;
-    const unsigned *img = (const unsigned *)bg8 + (size_t)f * npix_img;
-    unsigned *out = (unsigned *)env8 + (size_t)f * H * W_env;
     if (threadIdx.x == 0) any_hole = 0;
     __syncthreads();
     for (int i = threadIdx.x; i < ENV_TX * ENV_TY; i += 256) {
@@ -586,6 +581,24 @@ __global__ void __launch_bounds__(256) k_env_map(const uint8_t *bg8, const int32
         if (gy < H && gx < W_env && !env_written[(size_t)gy * W_env + gx]) any_hole = 1;
     }
     __syncthreads();
+    if (threadIdx.x == 0) tile_hole[blockIdx.y * gridDim.x + blockIdx.x] = any_hole ? 1 : 0;
+}
+
+cudaError_t rr_launch_env_tile_flags(const uint8_t *env_written, uint8_t *tile_hole, int H, int W_env, cudaStream_t st) {
+    dim3 g((W_env + ENV_TX - 1) / ENV_TX, (H + ENV_TY - 1) / ENV_TY);
+    k_env_tile_flags<<<g, 256, 0, st>>>(env_written, tile_hole, H, W_env);
+    return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) k_env_map(const uint8_t *bg8, const int32_t *env_src, const uint8_t *env_written,
+                                                 const uint8_t *tile_hole, uint8_t *env8, int H, int W_env, int npix_img) {
+    __shared__ unsigned in[ENV_TY + 2 * ENV_R][ENV_TX + 2 * ENV_R];
+    __shared__ unsigned short hp[ENV_TY + 2 * ENV_R][ENV_TX][3];
+    const int f = blockIdx.z;
+    const int x0 = blockIdx.x * ENV_TX, y0 = blockIdx.y * ENV_TY;
+    const unsigned *img = (const unsigned *)bg8 + (size_t)f * npix_img;
+    unsigned *out = (unsigned *)env8 + (size_t)f * H * W_env;
+    const bool any_hole = tile_hole[blockIdx.y * gridDim.x + blockIdx.x] != 0;      // block-uniform, static per camera
     if (any_hole) {
         for (int i = threadIdx.x; i < (ENV_TY + 2 * ENV_R) * (ENV_TX + 2 * ENV_R); i += 256) {
             int ey = i / (ENV_TX + 2 * ENV_R), ex = i - ey * (ENV_TX + 2 * ENV_R);
@@ -750,7 +763,7 @@ __global__ void k_ambient(const double *rowtot, double *ambient, int H) {
 
 cudaError_t rr_launch_env(const rr_frame_bufs &b, const rr_static_tabs &t, int F, int W, int H, int W_env, cudaStream_t st) {
     dim3 g2((W_env + ENV_TX - 1) / ENV_TX, (H + ENV_TY - 1) / ENV_TY, F);
-    k_env_map<<<g2, 256, 0, st>>>(b.bg8, t.env_src, t.env_written, b.env8, H, W_env, W * H);
+    k_env_map<<<g2, 256, 0, st>>>(b.bg8, t.env_src, t.env_written, t.env_tile_hole, b.env8, H, W_env, W * H);
     cudaError_t e = launch_env_prefix(b.env8, t.omega, b.pref, b.rowtot, F, H, W_env, st);
     if (e != cudaSuccess) return e;
     k_ambient<<<F, 32, 0, st>>>(b.rowtot, b.ambient, H);

@@ -41,6 +41,7 @@ struct rr_frame_bufs {
 struct rr_static_tabs {
     const int32_t *env_src;    // [H][W_env]
     const uint8_t *env_written;// [H][W_env]
+    const uint8_t *env_tile_hole; // [tiles_y][tiles_x] of k_env_map: 1 when the 64x16 tile holds a never-written pixel
     const double *omega;       // [H][W_env]
     const double *omega_pref;  // [H][W_env+1]
     const double *omega_total; // [1] numpy-order total
@@ -72,6 +73,7 @@ cudaError_t rr_upload_constants();
 // init-time tables
 cudaError_t rr_launch_env_tables(int W, int H, int focal_px, int cyl_w, int min_x, int W_env, int32_t *env_src,
                                  uint8_t *env_written, int32_t *cyl_first /* [H][cyl_w] scratch */, cudaStream_t st);
+cudaError_t rr_launch_env_tile_flags(const uint8_t *env_written, uint8_t *tile_hole, int H, int W_env, cudaStream_t st);
 cudaError_t rr_launch_omega(int H_env, int W_env, double *omega, double *omega_pref, double *omega_total, cudaStream_t st);
 // per batch
 cudaError_t rr_launch_stats(const rr_frame_bufs &b, int F, int W, int H, int render_scale, double *bgf_out, cudaStream_t st);
