@@ -298,6 +298,7 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
     CK(dev_alloc(c, &c->d_err2, (size_t)2));
     CK(dev_alloc(c, &b.chan_sum, F * 4));
     CK(dev_alloc(c, &b.bg_sum, F * 4));
+    CK(dev_alloc(c, &b.acs, F * 4));
     c->d_bgf = nullptr;
     if (rs == 2) CK(dev_alloc(c, &c->d_bgf, F * 3 * np));
     CK(dev_alloc(c, &b.rainy, F * 3 * np));
@@ -380,9 +381,9 @@ static int run_pipeline(rr_context *c, int F, int n_streaks, bool timed) {
     if (timed) CK(cudaEventRecord(c->ev[RR_T_EPILOGUE], st));
     CK(rr_launch_epilogue(b, F, W, H, st));
     if (timed) CK(cudaEventRecord(c->ev[RR_T_D2H], st));
-    // stats 2, extinction 1, fog 1, env map + prefix + ambient 3, plan + set-up 2, scan 1, raster + blur 2,
+    // stats 2, extinction + fog constants 2, fog 1, env map + prefix + ambient 3, plan + set-up 2, scan 1, raster + blur 2,
     // composite + frame mean 2, epilogue 1
-    c->launches += 2 + 1 + 1 + 3 + (n_streaks ? 2 : 0) + 1 + (n_streaks ? 2 : 0) + 2 + 1;
+    c->launches += 2 + 2 + 1 + 3 + (n_streaks ? 2 : 0) + 1 + (n_streaks ? 2 : 0) + 2 + 1;
     c->last_n_streaks = n_streaks;
     return RR_OK;
 }
@@ -395,7 +396,7 @@ static rr_frame_bufs sub_view(const rr_context *c, const rr_frame_bufs &b, int f
     const int rs2 = c->cam.render_scale == 2 ? 4 : 1;
     v.bgr += (size_t)f0 * np * 3 * rs2; v.depth += (size_t)f0 * np; v.streaks += s0;
     if (v.bgf) v.bgf += (size_t)f0 * 3 * np;
-    v.bg_sum += (size_t)f0 * 4;
+    v.bg_sum += (size_t)f0 * 4; v.acs += (size_t)f0 * 4;
     v.chan_sum += (size_t)f0 * 4; v.rainy += (size_t)f0 * 3 * np; v.bg8 += (size_t)f0 * np * 4; v.fblur += (size_t)f0 * np; v.fext += (size_t)f0 * np;
     v.env8 += (size_t)f0 * npe * 4;
     v.pref += (size_t)f0 * 4 * c->H_env * (c->W_env + 1); v.rowtot += (size_t)f0 * c->H_env; v.ambient += f0;
@@ -661,7 +662,7 @@ int rr_fog_only(rr_context *c, int n_frames, const uint8_t *bgr, const float *de
     b.bgr = c->d_bgr; b.depth = c->d_depth; b.bgf = c->d_bgf;
     CK(rr_launch_stats(b, n_frames, c->cam.W, c->cam.H, rs2 == 4 ? 2 : 1, c->d_bgf, st));
     CK(rr_launch_fog(b, c->fogc, n_frames, c->cam.W, c->cam.H, st));
-    c->launches += 4;
+    c->launches += 5;
     CK(cudaMemcpyAsync(out_planar, b.rainy, F * 3 * np * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return RR_OK;

@@ -345,6 +345,15 @@ __global__ void __launch_bounds__(256) k_fext(const float *depth, float *fext, f
     fext[i] = (float)exp((double)xx);                                       // correctly rounded float32 exp ("canonical")
 }
 
+// per frame and channel: A_c = beta_hg * mean irradiance of the un-fogged image (add_attenuation.py:53,70) -- once, not
+// once per thread of every tile (two float64 divisions each)
+__global__ void k_fog_acs(const double *bg_sum, double *acs, rr_fog_consts fc, double npix, int F) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= F * 4) return;
+    double irr_mean = ((fc.irr_scale_num * bg_sum[i]) / fc.irr_den) / npix;
+    acs[i] = fc.beta_hg * irr_mean;
+}
+
 __global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, rr_fog_consts fc, int W, int H) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float *E = (float *)smem_raw;                         // [FOG_EH][FOG_ES]  extinction on the haloed tile
@@ -357,14 +366,9 @@ __global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, 
     const int tid = threadIdx.x;
     const float *fext = b.fext + (size_t)f * W * H;
     const uint8_t *bgr = b.bgr + (size_t)f * W * H * 3;
-    const double npix = (double)W * (double)H;
     double Acs[3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-        double sum_b = b.bg_sum[f * 4 + c];                                    // mean irradiance of the un-fogged image (:53,70)
-        double irr_mean = ((fc.irr_scale_num * sum_b) / fc.irr_den) / npix;
-        Acs[c] = fc.beta_hg * irr_mean;
-    }
+    for (int c = 0; c < 3; c++) Acs[c] = b.acs[f * 4 + c];                      // beta_hg * E_c of the frame (k_fog_acs)
     // When beta_hg * E_c <= 1 for all channels the clip at :72 can only act on a negative 1 - f_ext (negative
     // depth), the three in-scatter images are the same image times a scalar, and one blur serves all three:
     // blur(A*d) = A*blur(d) up to float64 rounding (shortcut 3).  Otherwise each channel is
@@ -532,6 +536,7 @@ cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F
     {
         size_t n = (size_t)F * W * H;
         k_fext<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.depth, b.fext, fc.neg_beta32, n);
+        k_fog_acs<<<(F * 4 + 127) / 128, 128, 0, st>>>(b.bg_sum, b.acs, fc, (double)W * (double)H, F);
     }
     static bool attr = false;
     if (!attr) {

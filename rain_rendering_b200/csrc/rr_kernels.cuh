@@ -9,6 +9,7 @@ struct rr_frame_bufs {
     const uint8_t *bgr;        // [F][rs*H][rs*W][3]
     const double *bgf;         // [F][3][H][W] reduced float64 image when render_scale == 2, else NULL
     double *bg_sum;            // [F][4] per-channel sum of the (reduced) image in [0,1]
+    double *acs;               // [F][4] beta_hg * mean irradiance per channel (k_fog_acs)
     const float *depth;        // [F][H][W]
     const rr_streak_rec *streaks;
     const int32_t *offsets;    // [F+1] device copy
