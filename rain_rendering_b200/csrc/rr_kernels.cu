@@ -1220,8 +1220,12 @@ __global__ void __launch_bounds__(BLUR_THREADS) k_blur(rr_frame_bufs b, int n) {
     __shared__ double wy[2 * RR_MAX_GAUSS_R + 1], wx[2 * RR_MAX_GAUSS_R + 1];
     __shared__ double s_norm[2];
     const int tid = threadIdx.x;
+    __shared__ rr_plan sp;
     for (int s = blockIdx.x; s < n; s += gridDim.x) {
-        const rr_plan &p = b.plans[s];
+        __syncthreads();                                         // previous streak done with the plan and the tables
+        if (tid < (int)(sizeof(rr_plan) / 4)) ((int *)&sp)[tid] = ((const int *)&b.plans[s])[tid];      // one coalesced read
+        __syncthreads();
+        const rr_plan &p = sp;
         long long gg, nv, na; int vx0, vw;
         plan_sizes(p, &gg, &nv, &na, &vx0, &vw);
         if (na == 0) continue;                                   // block-uniform
@@ -1231,7 +1235,6 @@ __global__ void __launch_bounds__(BLUR_THREADS) k_blur(rr_frame_bufs b, int n) {
         {
             const int ny = 2 * ry + 1, nx = 2 * rx + 1;
             const double fy = -0.5 / (p.sig_y * p.sig_y), fx = -0.5 / (p.sig_x * p.sig_x);
-            __syncthreads();                                     // previous streak done with the tables
             for (int i = tid; i < ny; i += BLUR_THREADS) wy[i] = ry > 0 ? exp(fy * (double)((i - ry) * (i - ry))) : 1.0;
             for (int i = tid; i < nx; i += BLUR_THREADS) wx[i] = rx > 0 ? exp(fx * (double)((i - rx) * (i - rx))) : 1.0;
             __syncthreads();
