@@ -679,20 +679,41 @@ __global__ void __launch_bounds__(EP_THREADS) k_env_prefix(const uint8_t *env8, 
     const double *om = omega + (size_t)r * W_env;
     double2 *p2 = (double2 *)pref + ((size_t)f * H + r) * (W_env + 1) * 2;
     double cx = 0, cy = 0, cY = 0, cw = 0;          // carry: prefix of everything left of the tile
+    // The pixels of a tile travel global -> registers -> shared memory, and the registers are refilled with the NEXT
+    // tile's pixels right after they have been parked, so that load runs under this tile's arithmetic.
+    constexpr int EP_VEC = (EP_TILE * 4 + 16 + 15) / 16 / EP_THREADS + 1;      // 16-byte vectors per thread (3)
+    uint4 pv[EP_VEC];
+    auto tile_src = [&](int c0, int *shift, int *nvec) -> const uint4 * {
+        const int n = (W_env - c0) < EP_TILE ? (W_env - c0) : EP_TILE;
+        const uint8_t *gsrc = row + (size_t)c0 * 4;
+        *shift = (int)((size_t)gsrc & 15);                                 // a multiple of 4
+        *nvec = (*shift + n * 4 + 15) >> 4;
+        return (const uint4 *)(gsrc - *shift);                             // the buffers carry 256 bytes of slack
+    };
+    {
+        int sh0, nv0;
+        const uint4 *g0 = tile_src(0, &sh0, &nv0);
+#pragma unroll
+        for (int q = 0; q < EP_VEC; q++) { const int i = tid + q * EP_THREADS; pv[q] = i < nv0 ? g0[i] : make_uint4(0, 0, 0, 0); }
+    }
     for (int c0 = 0; c0 < W_env; c0 += EP_TILE) {
         const int n = (W_env - c0) < EP_TILE ? (W_env - c0) : EP_TILE;
-        // ---- row bytes -> shared memory, 16 bytes per load (the buffers carry 256 bytes of slack) ----
-        const uint8_t *gsrc = row + (size_t)c0 * 4;
-        const int shift = (int)((size_t)gsrc & 15);                        // a multiple of 4
-        const uint4 *gal = (const uint4 *)(gsrc - shift);
-        const int nvec = (shift + n * 4 + 15) >> 4;
+        int shift, nvec;
+        tile_src(c0, &shift, &nvec);
         // the thread's solid angles are requested now and consumed after the staging barrier
         const int px0 = tid * EP_PER;
         double wv[EP_PER];
 #pragma unroll
         for (int k = 0; k < EP_PER; k++) wv[k] = (px0 + k < n) ? om[c0 + px0 + k] : 0.0;
         __syncthreads();                            // previous tile fully written out (s_stage, s_toff, s_bytes)
-        for (int i = tid; i < nvec; i += EP_THREADS) ((uint4 *)s_bytes)[i] = gal[i];
+#pragma unroll
+        for (int q = 0; q < EP_VEC; q++) { const int i = tid + q * EP_THREADS; if (i < nvec) ((uint4 *)s_bytes)[i] = pv[q]; }
+        if (c0 + EP_TILE < W_env) {
+            int sh1, nv1;
+            const uint4 *g1 = tile_src(c0 + EP_TILE, &sh1, &nv1);
+#pragma unroll
+            for (int q = 0; q < EP_VEC; q++) { const int i = tid + q * EP_THREADS; pv[q] = i < nv1 ? g1[i] : make_uint4(0, 0, 0, 0); }
+        }
         __syncthreads();
         // ---- this thread's EP_PER consecutive pixels ----
         const unsigned *wds = (const unsigned *)s_bytes + (shift >> 2) + px0;
