@@ -36,13 +36,15 @@ REC_BYTES = STREAK_DTYPE.itemsize
 
 
 def algorithmic_bytes_per_frame(W, H, n_streaks):
-    """compulsory traffic at the C-ABI boundary of one frame: uint8 BGR in, float32
-    depth in, float32 BGR + float32 mask + uint8 BGR out, streak records in."""
-    return 3 * W * H + 4 * W * H + (12 + 4 + 3) * W * H + REC_BYTES * n_streaks
+    """compulsory traffic at the C-ABI boundary of one frame of the device-resident arm: uint8 BGR in,
+    uint16 depth samples in (round 1: float32, 4 bytes), float32 BGR + float32 mask + uint8 BGR + uint8 mask index out,
+    streak records in."""
+    return 3 * W * H + 2 * W * H + (12 + 4 + 3 + 1) * W * H + REC_BYTES * n_streaks
 
 
 def build_batch(wl, rank, batch):
-    """Synthetic batch of one rank: frames + records (host arrays)."""
+    """Synthetic batch of one rank: frames + simulator frames (host arrays).  Frame i of rank r is synth frame
+    1000 * r + i, rendered with simulator frame i of particle set 1000 + r and np.random.seed(i)."""
     from rain_rendering_b200 import api, streaks as S
     W, H = wl["W"], wl["H"]
     cam = synth.CAMERAS[wl["dataset"]]
@@ -50,17 +52,15 @@ def build_batch(wl, rank, batch):
     frames = [synth.make_frame(W, H, 1000 * rank + i) for i in range(batch)]
     bgr = np.stack([f[0] for f in frames])
     depth = np.stack([f[1] for f in frames])
+    d16 = np.rint(depth * 256.0).astype(np.uint16)           # the depth PNG's samples (synth depth is a multiple of 1/256 m)
+    assert np.array_equal(d16.astype(np.float32) / 256., depth)
     parts = synth.make_particles(W, H, batch, wl["n_xml"], cam["cam_exposure"], seed=1000 + rank)
     with tempfile.TemporaryDirectory() as d:
         xml = os.path.join(d, "sim_camera0.xml")
         synth.write_particles_xml(parts, xml, cam["cam_exposure"])
         sim = S.load_streaks_from_xml(xml, 1, W, H)
-    recs, offs = [], [0]
-    for i in range(batch):
-        r = api.assemble_frame_records(sim[i], W, H, db.ratios, i, 0.0, 0.0)
-        recs.append(r)
-        offs.append(offs[-1] + len(r))
-    return db, bgr, depth, np.concatenate(recs), np.array(offs, np.int32)
+    recs, offs = api.assemble_batch(sim[:batch], list(range(batch)), W, H, db.ratios)
+    return db, bgr, depth, d16, sim[:batch], recs.copy(), offs
 
 
 class ClockSampler:
@@ -119,25 +119,26 @@ _W = {}
 
 def _cpu_init(wl_name, base_seed):
     """Pool initializer: everything that is not the per-frame path (imports, synthetic inputs, the
-    per-camera tables) is prepared once per worker, outside the timed region."""
+    per-camera tables) is prepared once per worker, outside the timed region.  Worker k renders frame
+    base_seed + k OF THE GPU ARM'S BATCH (rank 0): the same image, depth, simulator frame and RNG seed."""
     import multiprocessing as mp
     import cv2
     cv2.setNumThreads(1)
     from oracle import rain_oracle as ro
     ident = mp.current_process()._identity
-    k = ident[0] if ident else 0
+    k = (ident[0] - 1) if ident else 0
     wl = synth.WORKLOADS[wl_name]
     W, H = wl["W"], wl["H"]
     cam_s = synth.CAMERAS[wl["dataset"]]
     cam = ro.Camera(W=W, H=H, focal_mm=cam_s["cam_focal"], f_number=cam_s["cam_f_number"], exposure_ms=cam_s["cam_exposure"],
                     gain=cam_s["cam_gain"], fallrate=wl["fallrate"])
     db = synth.make_streak_db(0)
-    frame_idx = base_seed + k
-    bgr, depth = synth.make_frame(W, H, frame_idx)
-    parts = synth.make_particles(W, H, 1, wl["n_xml"], cam_s["cam_exposure"], seed=1000 + frame_idx)
+    frame_idx = (base_seed + k) % BATCH
+    bgr, depth = synth.make_frame(W, H, frame_idx)                       # rank 0: synth frame 1000 * 0 + i
+    parts = synth.make_particles(W, H, BATCH, wl["n_xml"], cam_s["cam_exposure"], seed=1000)
     with tempfile.TemporaryDirectory() as d:
         xml = os.path.join(d, "sim_camera0.xml")
-        synth.write_particles_xml(parts, xml, cam_s["cam_exposure"])
+        synth.write_particles_xml(parts[frame_idx:frame_idx + 1], xml, cam_s["cam_exposure"])
         streaks = ro.load_streaks_from_xml(xml, 1, W, H)[0]
     tables = ro.build_env_tables(W, H, cam.focal_m)
     omega = ro.solid_angles(H, tables.W_env)
@@ -163,7 +164,7 @@ def cpu_steps(steps, warmup, n_workers, budget_s=None):
     import multiprocessing as mp
     ctx = mp.get_context("spawn")
     times, streaks = [], []
-    with ctx.Pool(n_workers, initializer=_cpu_init, initargs=(WORKLOAD, 7000)) as pool:
+    with ctx.Pool(n_workers, initializer=_cpu_init, initargs=(WORKLOAD, 0)) as pool:
         pool.map(_cpu_ready, range(n_workers * 4))          # all workers initialised before anything is timed
         t_start = time.perf_counter()
         for s in range(warmup + steps):
@@ -208,8 +209,9 @@ def run_reference(args):
     times, streaks = cpu_steps(args.steps, args.warmup, workers, budget_s=budget)
     total = float(np.sum(times))
     fps = workers * len(times) / total
-    sample = "%d processes x 1 frame per step (%dx%d, %d mm/h, ~%d streaks/frame), oracle port of the reference algorithm, " \
-             "cv2 threads 1 per process, per-camera tables/solid angles and synthetic inputs prepared outside the timed region" % (workers, wl["W"], wl["H"], wl["fallrate"], int(np.mean(streaks)))
+    sample = "%d processes x 1 frame per step (frames 0..%d of the GPU arm's rank-0 batch: %dx%d, %d mm/h, ~%d streaks/frame), oracle port of the " \
+             "reference algorithm, cv2 threads 1 per process, per-camera tables/solid angles and synthetic inputs prepared outside the timed " \
+             "region; host has %d cores" % (workers, workers - 1, wl["W"], wl["H"], wl["fallrate"], int(np.mean(streaks)), cores)
     if len(times) < args.steps:
         sample += "; %d of the %d requested steps timed (a step is %.1f s of CPU work per core; wall-clock budget %d s, RR_REFERENCE_BUDGET_S)" % (
             len(times), args.steps, total / len(times), int(budget))
@@ -217,7 +219,8 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "C2 KITTI 1242x375 25mm/hr", "frames_per_step": workers, "streaks_per_frame": float(np.mean(streaks))},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": workers, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": workers, "host_cores": cores, "kind": "port", "sample": sample},
+            "host_cores": cores,
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
@@ -229,6 +232,7 @@ def run_gpu(args):
     import torch
     import torch.distributed as dist
     from rain_rendering_b200 import api, dist as rdist
+    numa = rdist.bind_to_gpu_numa(rdist.env_rank()[2])         # before any page-locked buffer exists
     rank, world, local = rdist.init_process_group("nccl")
     assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node %d" % args.gpus
     torch.cuda.set_device(local)
@@ -236,13 +240,12 @@ def run_gpu(args):
     W, H = wl["W"], wl["H"]
     cam = synth.CAMERAS[wl["dataset"]]
     batch = args.batch
-    db, bgr, depth, recs, offs = build_batch(wl, rank, batch)
+    db, bgr, depth, d16, sim, recs, offs = build_batch(wl, rank, batch)
     n_streaks = int(offs[-1])
     ctx = api.RainContext(local)
     rdist.broadcast_streak_db(ctx, db.textures if rank == 0 else None, src=0)     # the one collective
-    if world == 1:
-        pass
     ctx.set_camera(W, H, cam["cam_focal"], cam["cam_f_number"], cam["cam_exposure"], cam["cam_gain"], wl["fallrate"], 1.0, batch)
+    from rain_rendering_b200 import _lib
     lib, C = ctx.lib, __import__("ctypes")
     stream_ptr = C.c_void_p()
     lib.rr_stream(ctx.h, C.byref(stream_ptr))
@@ -254,19 +257,21 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---- device-resident arm ----------------------------------------------------------------
+    # inputs as the files hold them (uint8 image, uint16 depth samples), every output form the library offers
     dev = torch.device("cuda", local)
     d_bgr = torch.from_numpy(bgr).to(dev)
-    d_depth = torch.from_numpy(depth).to(dev)
+    d_depth = torch.from_numpy(d16.view(np.int16)).to(dev)
     d_recs = torch.from_numpy(recs.view(np.uint8).reshape(-1)).to(dev)
     d_out_bgr = torch.empty((batch, H, W, 3), dtype=torch.float32, device=dev)
     d_out_mask = torch.empty((batch, H, W), dtype=torch.float32, device=dev)
     d_out_u8 = torch.empty((batch, H, W, 3), dtype=torch.uint8, device=dev)
+    d_out_idx8 = torch.empty((batch, H, W), dtype=torch.uint8, device=dev)
     offs_c = np.ascontiguousarray(offs)
+    io_dev = _lib.FrameIO(d_bgr.data_ptr(), d_depth.data_ptr(), _lib.DEPTH_U16_256, 0, d_recs.data_ptr(), _lib.ptr(offs_c).value,
+                          d_out_bgr.data_ptr(), d_out_mask.data_ptr(), d_out_u8.data_ptr(), d_out_idx8.data_ptr(), None, None)
 
     def step_device(sync=0):
-        from rain_rendering_b200 import _lib
-        _lib.check(lib.rr_render_frames_device(ctx.h, batch, d_bgr.data_ptr(), d_depth.data_ptr(), d_recs.data_ptr(), _lib.ptr(offs_c),
-                                               d_out_bgr.data_ptr(), d_out_mask.data_ptr(), d_out_u8.data_ptr(), sync), "rr_render_frames_device")
+        _lib.check(lib.rr_render_frames_device_io(ctx.h, batch, C.byref(io_dev), sync), "rr_render_frames_device_io")
 
     for _ in range(max(args.warmup, 3)):
         step_device(1)
@@ -288,21 +293,25 @@ def run_gpu(args):
     launches = ctx.kernel_launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
     # ---- end-to-end arm: pinned HOST buffers through the public API ---------------------------------
-    # rr_submit_frames / rr_wait_frames with two sets of host buffers: while batch k renders, batch k+1 is
-    # copied in and batch k-1 is copied out.  Every step copies its inputs host->device and what
-    # Generator.run saves (uint8 image + float32 mask, generator.py:466-467) device->host.
+    # rr_submit_frames_io / rr_wait_frames with two sets of host buffers: while batch k renders, batch k+1 is
+    # copied in and batch k-1 is copied out.  Every step builds its streak records from the simulator frames
+    # (in-frame filter + the NumPy RNG mirror, rr_host_assemble_batch -- host work a caller pays per frame), copies its
+    # inputs host->device in the forms the files hold (uint8 image, uint16 depth samples) and copies back what
+    # Generator.run saves (generator.py:466-467): the uint8 image and the mask as plt.imsave's colormap index + range.
     sets = []
     for _ in range(2):
-        hb = dict(bgr=api.PinnedBuffer(bgr.shape, np.uint8), depth=api.PinnedBuffer(depth.shape, np.float32),
-                  recs=api.PinnedBuffer(recs.shape, STREAK_DTYPE), mask=api.PinnedBuffer((batch, H, W), np.float32),
-                  u8=api.PinnedBuffer((batch, H, W, 3), np.uint8))
-        hb["bgr"].array[...] = bgr; hb["depth"].array[...] = depth; hb["recs"].array[...] = recs
+        hb = dict(bgr=api.PinnedBuffer(bgr.shape, np.uint8), depth=api.PinnedBuffer(d16.shape, np.uint16),
+                  recs=api.PinnedBuffer((sum(len(f) for f in sim),), STREAK_DTYPE), idx8=api.PinnedBuffer((batch, H, W), np.uint8),
+                  u8=api.PinnedBuffer((batch, H, W, 3), np.uint8), rng=api.PinnedBuffer((batch, 2), np.float64))
+        hb["bgr"].array[...] = bgr; hb["depth"].array[...] = d16
         sets.append(hb)
-    p_out_mask, p_out_u8 = sets[0]["mask"], sets[0]["u8"]
+    seeds = list(range(batch))
 
     def submit(i):
         hb = sets[i & 1]
-        ctx.submit_frames(hb["bgr"].array, hb["depth"].array, hb["recs"].array, offs_c, None, hb["mask"].array, hb["u8"].array)
+        r, o = api.assemble_batch(sim, seeds, W, H, db.ratios, out=hb["recs"].array)
+        hb["offs"] = o
+        ctx.submit_frames(hb["bgr"].array, hb["depth"].array, r, o, None, None, hb["u8"].array, hb["idx8"].array, None, hb["rng"].array)
 
     def run_e2e(n):
         submit(0)
@@ -312,11 +321,11 @@ def run_gpu(args):
         ctx.wait_frames()
 
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    link = None
     if args.skip_e2e:
         f0.record(stream); f1.record(stream)
     else:
-        ctx.render_frames(sets[0]["bgr"].array, sets[0]["depth"].array, sets[0]["recs"].array, offs_c, None, sets[0]["mask"].array,
-                          sets[0]["u8"].array, want=("mask", "u8"))      # synchronous call: sizes the arena
+        ctx.render_frames(bgr, d16, recs, offs_c, want=("u8", "idx8"))      # synchronous call: sizes the arena
         run_e2e(max(args.warmup, 3))
         barrier()
         f0.record(stream)
@@ -324,14 +333,24 @@ def run_gpu(args):
         f1.record(stream)
     barrier()
     ms_e2e = max(f0.elapsed_time(f1), 1e-6)
-    h2d = int(bgr.nbytes + depth.nbytes + recs.nbytes + offs_c.nbytes)
-    d2h = int(p_out_mask.array.nbytes + p_out_u8.array.nbytes)
-    checksum = float(p_out_mask.array.sum())
+    h2d = int(bgr.nbytes + d16.nbytes + recs.nbytes + offs_c.nbytes)
+    d2h = int(sets[0]["idx8"].array.nbytes + sets[0]["u8"].array.nbytes + sets[0]["rng"].array.nbytes)
+    checksum = float(sets[0]["idx8"].array.sum(dtype=np.int64))
+    same = bool(np.array_equal(sets[0]["u8"].array, d_out_u8.cpu().numpy()) and np.array_equal(sets[0]["idx8"].array, d_out_idx8.cpu().numpy())) \
+        if not args.skip_e2e else None
+    if not args.skip_e2e:
+        # the host link's ceiling, measured now with every rank copying at once (tools/pcie_ceiling.py is the stand-alone form)
+        barrier()
+        link = api.host_link_probe(local, 256, 0.6)
+        barrier()
     # ---- max over ranks ------------------------------------------------------------------------
     t = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
+    lk = torch.tensor(list(link or (0.0, 0.0)), dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(lk, op=dist.ReduceOp.SUM)
     ms_dev, ms_e2e = float(t[0]), float(t[1])
+    link_total = float(lk[0] + lk[1])
     total_frames = batch * world * args.steps
     if rank == 0:
         value = total_frames / (ms_dev / 1000.0)
@@ -357,13 +376,19 @@ def run_gpu(args):
                 "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "C2 KITTI 1242x375 25mm/hr", "batch_frames_per_gpu": batch, "streaks_per_frame": n_per_frame,
+                           "device_arm": "uint8 image + uint16 depth resident in HBM -> float32 image, float32 mask, uint8 image, uint8 mask index",
                            "l2": "inputs larger than L2 (%.0f MB per step per GPU, no flush)" % ((h2d) / 1e6),
                            "parallelism": "frames sharded x%d, no data-path collective" % world},
                 "clocks": clocks, "gpu_launches": launches,
+                "host_cores": host_cores(),
                 "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
-                        "checksum_mask": checksum,
-                        "outputs": "uint8 BGR image + float32 rain mask (what Generator.run saves)",
-                        "api": "rr_submit_frames / rr_wait_frames, two host buffer sets"},
+                        "checksum_mask": checksum, "equals_device_arm": same, "numa_bind": numa,
+                        "host_link_gbs": link_total if link else None,
+                        "host_link_note": "sum over ranks of concurrent page-locked H2D + D2H copies (rr_host_link_probe), measured in this run right after the timed region",
+                        "link_frac": ((h2d + d2h) * world * args.steps / (ms_e2e / 1000.0) / 1e9 / link_total) if link and link_total > 0 else None,
+                        "inputs": "uint8 BGR image + uint16 depth samples (what the PNG files hold) + streak records built per step from the simulator frames",
+                        "outputs": "uint8 BGR image + rain mask as plt.imsave's colormap index (uint8) and its (min, max) -- what Generator.run saves",
+                        "api": "rr_host_assemble_batch + rr_submit_frames_io / rr_wait_frames, two host buffer sets"},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
                              "algorithmic_bytes_per_frame": balg, "whole_step_frac": (balg * batch / (ms_dev / args.steps / 1000.0) / 1e9) / peak},
@@ -372,9 +397,9 @@ def run_gpu(args):
             workers = max(1, min(host_cores(), 16))
             times, streaks = cpu_steps(1, 1, workers)
             fps = workers / times[0]
-            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": workers, "kind": "port",
-                                    "sample": "%d processes x 1 frame of the same workload (~%d streaks/frame), oracle port, %.1f s wall" % (
-                                        workers, int(np.mean(streaks)), times[0])}
+            line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": workers, "host_cores": host_cores(), "kind": "port",
+                                    "sample": "%d processes x 1 frame (frames 0..%d of this batch, ~%d streaks/frame), oracle port, %.1f s wall" % (
+                                        workers, workers - 1, int(np.mean(streaks)), times[0])}
         print(json.dumps(line))
     ctx.close()
     if world > 1:

@@ -134,6 +134,35 @@ int rr_submit_frames(rr_context *ctx, int n_frames, const uint8_t *bgr, const fl
                      float *out_bgr, float *out_mask, uint8_t *out_bgr_u8);
 int rr_wait_frames(rr_context *ctx);
 
+/* Frame formats at the boundary.  The float32 forms above are what the reference holds in memory; the compact forms
+ * are what its files hold, and cut the bytes staged per frame from 14 to 9 per pixel:
+ *   depth  RR_DEPTH_U16_256: the 16-bit samples of the depth PNG as cv2.imread(IMREAD_UNCHANGED) returns them; the
+ *          library forms sample.astype(float32) / 256 (generator.py:360-365) on the device, exactly.
+ *   mask   out_mask_idx8: what plt.imsave(path, rainy_mask) (generator.py:467) stores per pixel before the colour
+ *          table: the float64 mask min/max-normalised, index = min(int(t * 256), 255) (matplotlib Normalize +
+ *          Colormap.__call__; all zeros for a flat mask); out_mask_u16: int(t * 65535 + 0.5); out_mask_range:
+ *          (min, max) of the float64 mask per frame, so that a caller can undo the normalisation.
+ * Every output pointer may be NULL; outputs that are NULL are neither produced nor copied. */
+enum { RR_DEPTH_F32_M = 0, RR_DEPTH_U16_256 = 1 };
+typedef struct rr_frame_io {
+    const uint8_t *bgr;              /* n*(rs*H)*(rs*W)*3 uint8                                   */
+    const void *depth;               /* n*H*W float32 metres, or uint16 samples (depth_format)    */
+    int32_t depth_format;            /* RR_DEPTH_F32_M / RR_DEPTH_U16_256                         */
+    int32_t reserved;
+    const rr_streak_rec *streaks;
+    const int32_t *streak_offsets;   /* n+1, always a HOST array                                  */
+    float *out_bgr;                  /* n*H*W*3 float32                                           */
+    float *out_mask;                 /* n*H*W   float32                                           */
+    uint8_t *out_bgr_u8;             /* n*H*W*3 uint8                                             */
+    uint8_t *out_mask_idx8;          /* n*H*W   uint8                                             */
+    uint16_t *out_mask_u16;          /* n*H*W   uint16                                            */
+    double *out_mask_range;          /* n*2     float64 (min, max)                                */
+} rr_frame_io;
+int rr_render_frames_io(rr_context *ctx, int n_frames, const rr_frame_io *io);
+int rr_submit_frames_io(rr_context *ctx, int n_frames, const rr_frame_io *io);     /* + rr_wait_frames */
+/* DEVICE pointers in *io (streak_offsets stays on the host), no copies; asynchronous unless sync != 0. */
+int rr_render_frames_device_io(rr_context *ctx, int n_frames, const rr_frame_io *io, int sync);
+
 /* Same with DEVICE pointers and no copies (inputs already resident in HBM); asynchronous on the
  * context stream unless sync != 0. */
 int rr_render_frames_device(rr_context *ctx, int n_frames, const uint8_t *d_bgr, const float *d_depth,
@@ -194,12 +223,28 @@ int rr_stream(rr_context *ctx, void **cuda_stream);
 /* Pinned host staging buffers for the callers of rr_render_frames (async copies need them). */
 int rr_host_alloc(void **ptr, size_t bytes);
 int rr_host_free(void *ptr);
+/* The same with cudaHostAllocWriteCombined when write_combined != 0 (buffers the host only writes: the input sets). */
+int rr_host_alloc_flags(void **ptr, size_t bytes, int write_combined);
+/* What the host link of this process sustains right now: concurrent page-locked host->device (direction & 1) and
+ * device->host (direction & 2) copies of `bytes` each on two streams for about `seconds`; GB/s per direction.
+ * bench.py and tools/pcie_ceiling.py run it on every rank at once so that end-to-end numbers read as a fraction of
+ * the box's measured ceiling. */
+int rr_host_link_probe(int device_id, size_t bytes, double seconds, int write_combined, int direction,
+                       double *h2d_gbs, double *d2h_gbs);
 
 /* Host logic (no GPU): the per-frame NumPy legacy RNG draws of the reference, bit-exact --
  * np.random.seed(seed); per streak randint(10*bucket, 10*bucket+10) (bad_weather.py:252-264) and,
  * for non-Big streaks, normal(0, noise_std) * noise_scale (generator.py:136). */
 int rr_host_draw_randoms(uint32_t seed, int n, const uint8_t *types, const int32_t *buckets, double noise_std,
                          double noise_scale, uint8_t *tex_idx, double *noise_deg);
+/* Host logic (no GPU): the records of a whole batch of image frames from their simulator frames in one call -- the
+ * in-frame filter (generator.py:413-420), the texture bucket (bad_weather.py:250-265) and the RNG draws above; frame f
+ * is seeded with seeds[f] (generator.py:318).  Output records in frame order, offsets[n_frames + 1]; src_index (nullable)
+ * = index of each output record in its simulator frame.  The wind rotation (generator.py:149-161) is left to the caller:
+ * it is the identity when noise_std or noise_scale is 0.  RR_ERR_CAPACITY when out_cap records do not suffice. */
+int rr_host_assemble_batch(int n_frames, const rr_streak_rec *const *sim, const int32_t *n_sim, const uint32_t *seeds,
+                           int W, int H, const double *db_ratios, int n_ratios, double noise_std, double noise_scale,
+                           rr_streak_rec *out, int64_t out_cap, int32_t *offsets, int32_t *src_index);
 /* Host logic (no GPU): native loader of the particle simulator's XML output -- replaces
  * DBManager.load_streaks_from_xml (common/bad_weather.py:148-248).  The root's children are camera
  * frames (<i id t d rs>), their children imaged streaks (<r pid wp1 wd1 wp2 wd2 ip1 iw1 ip2 iw2/>).
@@ -235,6 +280,19 @@ int rr_host_png_read_batch(int n, const char *const *image_paths, const char *co
                            float *depth, int Wd, int Hd, int n_threads, int32_t *status);
 int rr_host_png_write_batch(int n, const char *const *image_paths, const uint8_t *bgr, const char *const *mask_paths,
                             const float *mask, int W, int H, int level, int n_threads);
+/* The same decode with the depth delivered as the file's uint16 samples (rr_frame_io RR_DEPTH_U16_256). */
+int rr_host_png_read_batch_u16(int n, const char *const *image_paths, const char *const *depth_paths, uint8_t *bgr, int Wi, int Hi,
+                               uint16_t *depth, int Wd, int Hd, int n_threads, int32_t *status);
+/* The reference's own file formats (plt.imsave, generator.py:466-467): 8-bit RGBA for both files, the mask coloured through
+ * matplotlib's viridis table from its colormap index (rr_frame_io.out_mask_idx8).  level 1 = the library's own run +
+ * Huffman deflate encoder (csrc/rr_host_deflate.h), 0 stores, 2..9 zlib. */
+int rr_host_png_write_batch_rgba(int n, const char *const *image_paths, const uint8_t *bgr, const char *const *mask_paths,
+                                 const uint8_t *mask_idx8, int W, int H, int level, int n_threads);
+/* Compact files: 8-bit RGB image and 16-bit gray mask from rr_frame_io.out_mask_u16. */
+int rr_host_png_write_batch_u16(int n, const char *const *image_paths, const uint8_t *bgr, const char *const *mask_paths,
+                                const uint16_t *mask_u16, int W, int H, int level, int n_threads);
+/* Test hook of the deflate encoder: data -> zlib stream. */
+int rr_host_zlib_compress_fast(const uint8_t *data, size_t n, uint8_t *out, size_t cap, size_t *out_len);
 /* The simulator's force model evaluated on the host (CPU test-suite): terminal velocity solving
  * m g = F_drag(v), the drag at that speed and the drop mass. */
 void rr_host_sim_physics(double D_m, double *v_terminal, double *drag_at_vt, double *mass);

@@ -624,6 +624,36 @@ def render_frame(bg_u8: np.ndarray, depth: np.ndarray, streaks, textures, ratios
 
 
 # --------------------------------------------------------------------------------------
+# row 14: what plt.imsave(path, rainy_mask) stores (common/generator.py:467)
+# --------------------------------------------------------------------------------------
+
+def imsave_mask_index(mask: np.ndarray):
+    """plt.imsave of a 2-D float64 array, up to the colour table (matplotlib is absent here and unpinned by the
+    reference: PARITY UNPINNED, restated from matplotlib 3.x -- image.imsave -> ScalarMappable.to_rgba(bytes=True) ->
+    colors.Normalize.__call__ (autoscaled to the array's min / max: ``(x - vmin) / (vmax - vmin)`` in float64, zeros for
+    a flat array) -> Colormap.__call__ (``xa *= N; xa[xa == N] = N - 1; xa.astype(int)`` with N = 256)).
+    -> (uint8 index into the 256-entry colormap, (vmin, vmax))."""
+    m = np.asarray(mask, np.float64)
+    lo, hi = float(m.min()), float(m.max())
+    if lo == hi:
+        return np.zeros(m.shape, np.uint8), (lo, hi)
+    t = (m - lo) / (hi - lo)
+    xa = t * 256
+    xa[xa == 256] = 255
+    return xa.astype(int).astype(np.uint8), (lo, hi)
+
+
+def mask_u16(mask: np.ndarray) -> np.ndarray:
+    """The 16-bit gray form of the mask file this repo offers beside the colormapped one: int(t * 65535 + 0.5) with the
+    same normalisation (not a reference format)."""
+    m = np.asarray(mask, np.float64)
+    lo, hi = float(m.min()), float(m.max())
+    if lo == hi:
+        return np.zeros(m.shape, np.uint16)
+    return (((m - lo) / (hi - lo)) * 65535.0 + 0.5).astype(np.uint16)
+
+
+# --------------------------------------------------------------------------------------
 # file-level helpers (decode side of common/generator.py:352-367, bad_weather.py:108-146)
 # --------------------------------------------------------------------------------------
 

@@ -25,6 +25,16 @@ class Camera(C.Structure):
                 ("opacity_att", C.c_double), ("fallrate_mmh", C.c_double), ("render_scale", C.c_int32), ("reserved", C.c_int32)]
 
 
+class FrameIO(C.Structure):
+    """rr_frame_io"""
+    _fields_ = [("bgr", C.c_void_p), ("depth", C.c_void_p), ("depth_format", C.c_int32), ("reserved", C.c_int32),
+                ("streaks", C.c_void_p), ("streak_offsets", C.c_void_p), ("out_bgr", C.c_void_p), ("out_mask", C.c_void_p),
+                ("out_bgr_u8", C.c_void_p), ("out_mask_idx8", C.c_void_p), ("out_mask_u16", C.c_void_p), ("out_mask_range", C.c_void_p)]
+
+
+DEPTH_F32_M, DEPTH_U16_256 = 0, 1
+
+
 class SimParams(C.Structure):
     """rr_sim_params"""
     _fields_ = [("W", C.c_int32), ("H", C.c_int32), ("focal_m", C.c_double), ("pix_size_m", C.c_double), ("exposure_ms", C.c_double),
@@ -80,6 +90,9 @@ def load() -> C.CDLL:
         "rr_render_frames": [vp, C.c_int, u8p, f32p, vp, i32p, f32p, f32p, u8p],
         "rr_submit_frames": [vp, C.c_int, u8p, f32p, vp, i32p, f32p, f32p, u8p],
         "rr_wait_frames": [vp],
+        "rr_render_frames_io": [vp, C.c_int, C.POINTER(FrameIO)],
+        "rr_submit_frames_io": [vp, C.c_int, C.POINTER(FrameIO)],
+        "rr_render_frames_device_io": [vp, C.c_int, C.POINTER(FrameIO), C.c_int],
         "rr_render_frames_device": [vp, C.c_int, u8p, f32p, vp, i32p, f32p, f32p, u8p, C.c_int],
         "rr_fog_only": [vp, C.c_int, u8p, f32p, f64p],
         "rr_envmap_only": [vp, C.c_int, f64p, u8p],
@@ -93,13 +106,20 @@ def load() -> C.CDLL:
         "rr_synchronize": [vp],
         "rr_host_alloc": [C.POINTER(vp), C.c_size_t],
         "rr_host_free": [vp],
+        "rr_host_alloc_flags": [C.POINTER(vp), C.c_size_t, C.c_int],
+        "rr_host_link_probe": [C.c_int, C.c_size_t, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)],
         "rr_host_draw_randoms": [C.c_uint32, C.c_int, u8p, i32p, C.c_double, C.c_double, u8p, f64p],
+        "rr_host_assemble_batch": [C.c_int, vp, i32p, vp, C.c_int, C.c_int, f64p, C.c_int, C.c_double, C.c_double, vp, C.c_int64, i32p, i32p],
         "rr_host_load_particles_xml": [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)],
         "rr_host_particles_info": [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64)],
         "rr_host_particles_copy": [vp, vp, vp],
         "rr_host_png_info": [C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
         "rr_host_png_read_batch": [C.c_int, vp, vp, u8p, C.c_int, C.c_int, f32p, C.c_int, C.c_int, C.c_int, i32p],
         "rr_host_png_write_batch": [C.c_int, vp, u8p, vp, f32p, C.c_int, C.c_int, C.c_int, C.c_int],
+        "rr_host_png_read_batch_u16": [C.c_int, vp, vp, u8p, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, i32p],
+        "rr_host_png_write_batch_rgba": [C.c_int, vp, u8p, vp, u8p, C.c_int, C.c_int, C.c_int, C.c_int],
+        "rr_host_png_write_batch_u16": [C.c_int, vp, u8p, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int],
+        "rr_host_zlib_compress_fast": [u8p, C.c_size_t, u8p, C.c_size_t, C.POINTER(C.c_size_t)],
     }
     for name, args in protos.items():
         fn = getattr(lib, name)

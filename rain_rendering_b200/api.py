@@ -27,13 +27,15 @@ def draw_randoms(seed: int, types: np.ndarray, buckets: np.ndarray, noise_std: f
 class PinnedBuffer:
     """Page-locked host memory exposed as a numpy array (rr_host_alloc)."""
 
-    def __init__(self, shape, dtype):
+    def __init__(self, shape, dtype, write_combined=False):
+        """write_combined: cudaHostAllocWriteCombined -- for buffers the host only ever WRITES sequentially (inputs);
+        reading such memory from the CPU is very slow."""
         lib = _lib.load()
         self.shape = tuple(int(s) for s in shape)
         self.dtype = np.dtype(dtype)
         nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
         p = C.c_void_p()
-        _lib.check(lib.rr_host_alloc(C.byref(p), max(nbytes, 1)), "rr_host_alloc")
+        _lib.check(lib.rr_host_alloc_flags(C.byref(p), max(nbytes, 1), 1 if write_combined else 0), "rr_host_alloc_flags")
         self._p = p
         buf = (C.c_char * max(nbytes, 1)).from_address(p.value)
         self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
@@ -49,6 +51,15 @@ class PinnedBuffer:
             self.free()
         except Exception:
             pass
+
+
+def host_link_probe(device=0, mbytes=256, seconds=0.5, write_combined=False, direction=3):
+    """rr_host_link_probe -> (h2d GB/s, d2h GB/s) of concurrent page-locked copies on this process's GPU."""
+    lib = _lib.load()
+    a, b = C.c_double(0), C.c_double(0)
+    _lib.check(lib.rr_host_link_probe(int(device), int(mbytes) << 20, float(seconds), 1 if write_combined else 0, int(direction),
+                                      C.byref(a), C.byref(b)), "rr_host_link_probe")
+    return a.value, b.value
 
 
 class RainContext:
@@ -119,15 +130,30 @@ class RainContext:
         self.H_env, self.W_env = he.value, we.value
 
     # -- hot path ----------------------------------------------------------------------------
-    def render_frames(self, bgr, depth, streaks, offsets, out_bgr=None, out_mask=None, out_u8=None,
-                      want=("bgr", "mask", "u8")):
-        """bgr (n,H,W,3) uint8; depth (n,H,W) float32; streaks STREAK_DTYPE (concatenated);
-        offsets (n+1,) int32.  Returns dict of the requested outputs (numpy arrays)."""
+    def _frame_io(self, bgr, depth, streaks, offsets, out_bgr, out_mask, out_u8, out_idx8, out_u16, out_range):
+        """rr_frame_io of a batch (host arrays).  depth: float32 metres or the uint16 samples of the depth PNG."""
         n = bgr.shape[0]
         rs = self.render_scale
         assert bgr.shape == (n, self.H * rs, self.W * rs, 3) and bgr.dtype == np.uint8
-        assert depth.shape == (n, self.H, self.W) and depth.dtype == np.float32
+        assert depth.shape == (n, self.H, self.W) and depth.dtype in (np.float32, np.uint16)
         assert streaks.dtype == STREAK_DTYPE
+        assert offsets.dtype == np.int32 and offsets.flags["C_CONTIGUOUS"] and len(offsets) == n + 1
+        for a, shape, dt in ((out_bgr, (n, self.H, self.W, 3), np.float32), (out_mask, (n, self.H, self.W), np.float32),
+                             (out_u8, (n, self.H, self.W, 3), np.uint8), (out_idx8, (n, self.H, self.W), np.uint8),
+                             (out_u16, (n, self.H, self.W), np.uint16), (out_range, (n, 2), np.float64)):
+            assert a is None or (a.shape == shape and a.dtype == dt), "output array %s %s, expected %s %s" % (a.shape, a.dtype, shape, dt)
+        p = lambda a: None if a is None else _lib.ptr(a).value
+        io = _lib.FrameIO(p(bgr), p(depth), _lib.DEPTH_U16_256 if depth.dtype == np.uint16 else _lib.DEPTH_F32_M, 0, p(streaks), p(offsets),
+                          p(out_bgr), p(out_mask), p(out_u8), p(out_idx8), p(out_u16), p(out_range))
+        return n, io
+
+    def render_frames(self, bgr, depth, streaks, offsets, out_bgr=None, out_mask=None, out_u8=None,
+                      want=("bgr", "mask", "u8"), out_idx8=None, out_u16=None, out_range=None):
+        """bgr (n,H,W,3) uint8; depth (n,H,W) float32 metres or uint16 PNG samples; streaks STREAK_DTYPE (concatenated);
+        offsets (n+1,) int32.  ``want`` names the outputs to allocate when no array is passed: bgr (float32), mask
+        (float32), u8, idx8 (plt.imsave's colormap index of the mask), u16 (16-bit normalised mask), range ((min, max) of
+        the float64 mask).  Returns a dict of the outputs (numpy arrays)."""
+        n = bgr.shape[0]
         offsets = np.ascontiguousarray(offsets, dtype=np.int32)
         if out_bgr is None and "bgr" in want:
             out_bgr = np.empty((n, self.H, self.W, 3), np.float32)
@@ -135,20 +161,22 @@ class RainContext:
             out_mask = np.empty((n, self.H, self.W), np.float32)
         if out_u8 is None and "u8" in want:
             out_u8 = np.empty((n, self.H, self.W, 3), np.uint8)
-        _lib.check(self.lib.rr_render_frames(self.h, n, _lib.ptr(bgr), _lib.ptr(depth), _lib.ptr(streaks), _lib.ptr(offsets),
-                                             _lib.ptr(out_bgr), _lib.ptr(out_mask), _lib.ptr(out_u8)), "rr_render_frames")
-        return dict(bgr=out_bgr, mask=out_mask, u8=out_u8)
+        if out_idx8 is None and "idx8" in want:
+            out_idx8 = np.empty((n, self.H, self.W), np.uint8)
+        if out_u16 is None and "u16" in want:
+            out_u16 = np.empty((n, self.H, self.W), np.uint16)
+        if out_range is None and "range" in want:
+            out_range = np.empty((n, 2), np.float64)
+        n, io = self._frame_io(bgr, depth, streaks, offsets, out_bgr, out_mask, out_u8, out_idx8, out_u16, out_range)
+        _lib.check(self.lib.rr_render_frames_io(self.h, n, C.byref(io)), "rr_render_frames_io")
+        return dict(bgr=out_bgr, mask=out_mask, u8=out_u8, idx8=out_idx8, u16=out_u16, range=out_range)
 
-    def submit_frames(self, bgr, depth, streaks, offsets, out_bgr=None, out_mask=None, out_u8=None):
-        """Asynchronous rr_submit_frames: all arrays (page-locked for the copies to overlap) must stay
+    def submit_frames(self, bgr, depth, streaks, offsets, out_bgr=None, out_mask=None, out_u8=None, out_idx8=None, out_u16=None,
+                      out_range=None):
+        """Asynchronous rr_submit_frames_io: all arrays (page-locked for the copies to overlap) must stay
         alive and untouched until the matching ``wait_frames``; at most two batches in flight."""
-        n = bgr.shape[0]
-        rs = self.render_scale
-        assert bgr.shape == (n, self.H * rs, self.W * rs, 3) and bgr.dtype == np.uint8
-        assert depth.shape == (n, self.H, self.W) and depth.dtype == np.float32 and streaks.dtype == STREAK_DTYPE
-        assert offsets.dtype == np.int32 and offsets.flags["C_CONTIGUOUS"]
-        _lib.check(self.lib.rr_submit_frames(self.h, n, _lib.ptr(bgr), _lib.ptr(depth), _lib.ptr(streaks), _lib.ptr(offsets),
-                                             _lib.ptr(out_bgr), _lib.ptr(out_mask), _lib.ptr(out_u8)), "rr_submit_frames")
+        n, io = self._frame_io(bgr, depth, streaks, offsets, out_bgr, out_mask, out_u8, out_idx8, out_u16, out_range)
+        _lib.check(self.lib.rr_submit_frames_io(self.h, n, C.byref(io)), "rr_submit_frames_io")
 
     def wait_frames(self):
         _lib.check(self.lib.rr_wait_frames(self.h), "rr_wait_frames")
@@ -237,3 +265,39 @@ def assemble_frame_records(sim_frame: np.ndarray, W: int, H: int, db_ratios, see
         sim_frame["ip1m"][m] = rec["ip1m"]
         sim_frame["ip2m"][m] = rec["ip2m"]
     return rec
+
+
+def assemble_batch(sim_frames, seeds, W: int, H: int, db_ratios, noise_std: float = 0.0, noise_scale: float = 0.0, out=None):
+    """Records of a batch of image frames in ONE native call (rr_host_assemble_batch): ``sim_frames[k]`` is the simulator
+    frame (STREAK_DTYPE array) image frame k renders, ``seeds[k]`` its np.random.seed value (the frame index,
+    generator.py:318).  -> (concatenated records, int32 offsets).  ``out``: optional preallocated STREAK_DTYPE array
+    (e.g. a page-locked buffer) the records are written into.  With wind noise (noise_std and noise_scale non-zero) the
+    frames depend on each other through the write-back of generator.py:152-161 and are assembled one by one, in
+    order, by ``assemble_frame_records``."""
+    n = len(sim_frames)
+    if noise_std != 0.0 and noise_scale != 0.0:
+        recs, offs = [], [0]
+        for sim, seed in zip(sim_frames, seeds):
+            r = assemble_frame_records(sim, W, H, db_ratios, int(seed), noise_std, noise_scale)
+            recs.append(r)
+            offs.append(offs[-1] + len(r))
+        rec = np.concatenate(recs) if recs else np.zeros(0, STREAK_DTYPE)
+        if out is not None:
+            out[:len(rec)] = rec
+            rec = out[:len(rec)]
+        return rec, np.asarray(offs, np.int32)
+    lib = _lib.load()
+    total = int(sum(len(s) for s in sim_frames))
+    if out is None:
+        out = np.empty(max(total, 1), STREAK_DTYPE)
+    assert out.dtype == STREAK_DTYPE and out.flags["C_CONTIGUOUS"]
+    frames = [np.ascontiguousarray(s) for s in sim_frames]
+    ptrs = (C.c_void_p * max(n, 1))(*[f.ctypes.data if len(f) else None for f in frames])
+    counts = np.array([len(f) for f in frames], np.int32)
+    seeds = np.asarray(seeds, np.uint32)
+    ratios = np.ascontiguousarray(db_ratios, np.float64)
+    offs = np.zeros(n + 1, np.int32)
+    _lib.check(lib.rr_host_assemble_batch(n, C.cast(ptrs, C.c_void_p), _lib.ptr(counts), _lib.ptr(seeds), int(W), int(H), _lib.ptr(ratios),
+                                          len(ratios), float(noise_std), float(noise_scale), _lib.ptr(out), len(out), _lib.ptr(offs), None),
+               "rr_host_assemble_batch")
+    return out[:offs[-1]], offs

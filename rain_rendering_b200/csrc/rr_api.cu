@@ -48,7 +48,7 @@ struct rr_context {
     // per batch
     uint8_t *d_bgr = nullptr;
     double *d_bgf = nullptr;         // reduced float64 image (render_scale == 2)
-    float *d_depth = nullptr;
+    float *d_depth = nullptr;        // float32 metres, or the uint16 PNG samples in its first half (rr_frame_io.depth_format)
     rr_streak_rec *d_streaks = nullptr;
     int32_t *d_offsets = nullptr;
     int streak_cap = 0;
@@ -104,7 +104,7 @@ static void free_camera(rr_context *c) {
 
 extern "C" {
 
-int rr_version(void) { return 101; }
+int rr_version(void) { return 200; }
 int rr_sim_device_of(rr_context *c) { return c ? c->device : 0; }
 void rr_set_error(const char *msg) { set_err("%s", msg); }
 const char *rr_last_error(void) { return g_err; }
@@ -142,6 +142,7 @@ int rr_create(int device_id, rr_context **out) {
     memset(c->last_ms, 0, sizeof(c->last_ms));
     memset(&c->fb, 0, sizeof(c->fb));
     CK(rr_upload_constants());
+    CK(rr_prepare_device());
     *out = c;
     return RR_OK;
 }
@@ -311,10 +312,16 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
     CK(dev_alloc(c, &b.ambient, F));
     b.err_flag = nullptr;
     CK(dev_alloc(c, &b.tile_sum, F * rr_n_partials(W, H)));             // also holds the 64x4 partial sums of k_downscale2
+    CK(dev_alloc(c, &b.tile_min, F * rr_n_partials(W, H)));
+    CK(dev_alloc(c, &b.tile_max, F * rr_n_partials(W, H)));
     CK(dev_alloc(c, &b.frame_mean, F));
+    CK(dev_alloc(c, &b.maskd, F * np));
+    CK(dev_alloc(c, &b.mask_range, F * 2));
     CK(dev_alloc(c, &b.out_bgr, F * np * 3));
     CK(dev_alloc(c, &b.out_mask, F * np));
     CK(dev_alloc(c, &b.out_u8, F * np * 3));
+    CK(dev_alloc(c, &b.out_idx8, F * np));
+    CK(dev_alloc(c, &b.out_u16, F * np));
     {
         double mult = 6.0;
         const char *env = getenv("RR_ARENA_MULT");
@@ -394,17 +401,20 @@ static rr_frame_bufs sub_view(const rr_context *c, const rr_frame_bufs &b, int f
     const size_t np = (size_t)c->cam.W * c->cam.H, npe = (size_t)c->H_env * c->W_env;
     const size_t tiles = rr_n_partials(c->cam.W, c->cam.H);
     const int rs2 = c->cam.render_scale == 2 ? 4 : 1;
-    v.bgr += (size_t)f0 * np * 3 * rs2; v.depth += (size_t)f0 * np; v.streaks += s0;
+    v.bgr += (size_t)f0 * np * 3 * rs2; v.depth = (const char *)v.depth + (size_t)f0 * np * (v.depth_u16 ? 2 : 4); v.streaks += s0;
     if (v.bgf) v.bgf += (size_t)f0 * 3 * np;
     v.bg_sum += (size_t)f0 * 4; v.acs += (size_t)f0 * 4;
     v.chan_sum += (size_t)f0 * 4; v.rainy += (size_t)f0 * 3 * np; v.bg8 += (size_t)f0 * np * 4; v.fblur += (size_t)f0 * np; v.fext += (size_t)f0 * np;
     v.env8 += (size_t)f0 * npe * 4;
     v.pref += (size_t)f0 * 4 * c->H_env * (c->W_env + 1); v.rowtot += (size_t)f0 * c->H_env; v.ambient += f0;
     v.plans += s0; v.fcp += s0; v.sizes += s0; v.boxes += s0; v.scan += (size_t)scan_base * 6;
-    v.tile_sum += (size_t)f0 * tiles; v.frame_mean += f0;
+    v.tile_sum += (size_t)f0 * tiles; v.tile_min += (size_t)f0 * tiles; v.tile_max += (size_t)f0 * tiles; v.frame_mean += f0;
+    v.maskd += (size_t)f0 * np; v.mask_range += (size_t)f0 * 2;
     if (v.out_bgr) v.out_bgr += (size_t)f0 * np * 3;
     if (v.out_mask) v.out_mask += (size_t)f0 * np;
     if (v.out_u8) v.out_u8 += (size_t)f0 * np * 3;
+    if (v.out_idx8) v.out_idx8 += (size_t)f0 * np;
+    if (v.out_u16) v.out_u16 += (size_t)f0 * np;
     return v;
 }
 
@@ -465,9 +475,21 @@ static int wait_oldest(rr_context *c, bool grow) {
     return check_flag_slot(c, c->d_err2 + slot, c->call_S[slot], c->call_scan_base[slot], c->call_sub_n[slot], grow && c->inflight == 0);
 }
 
-static int submit_frames(rr_context *c, int F, const uint8_t *bgr, const float *depth, const rr_streak_rec *streaks,
-                         const int32_t *streak_offsets, float *out_bgr, float *out_mask, uint8_t *out_bgr_u8, bool timed,
-                         int default_sub) {
+// the device outputs a request does not ask for are not produced (NULL in the kernel's view)
+static void select_outputs(rr_frame_bufs &v, const rr_frame_bufs &all, const rr_frame_io &io) {
+    v.out_bgr = io.out_bgr ? all.out_bgr : nullptr;
+    v.out_mask = io.out_mask ? all.out_mask : nullptr;
+    v.out_u8 = io.out_bgr_u8 ? all.out_u8 : nullptr;
+    v.out_idx8 = io.out_mask_idx8 ? all.out_idx8 : nullptr;
+    v.out_u16 = io.out_mask_u16 ? all.out_u16 : nullptr;
+}
+
+static int submit_frames(rr_context *c, int F, const rr_frame_io &io, bool timed, int default_sub) {
+    const uint8_t *bgr = io.bgr;
+    const rr_streak_rec *streaks = io.streaks;
+    const int32_t *streak_offsets = io.streak_offsets;
+    const int du16 = io.depth_format == RR_DEPTH_U16_256;
+    const size_t dsz = du16 ? 2 : 4;
     const int n_streaks = streak_offsets[F];
     const size_t np = (size_t)c->cam.W * c->cam.H;
     const size_t rs2 = c->cam.render_scale == 2 ? 4 : 1;
@@ -511,7 +533,7 @@ static int submit_frames(rr_context *c, int F, const uint8_t *bgr, const float *
         rr_streak_rec *d_slot = c->d_streaks + (size_t)k * c->sub_cap;
         if (multi) CK(cudaStreamWaitEvent(hs, c->ev_done[k], 0));      // the previous batch no longer reads slot k's inputs
         CK(cudaMemcpyAsync(c->d_bgr + (size_t)f0 * np * 3 * rs2, bgr + (size_t)f0 * np * 3 * rs2, (size_t)nf * np * 3 * rs2, cudaMemcpyHostToDevice, hs));
-        CK(cudaMemcpyAsync(c->d_depth + (size_t)f0 * np, depth + (size_t)f0 * np, (size_t)nf * np * sizeof(float), cudaMemcpyHostToDevice, hs));
+        CK(cudaMemcpyAsync((char *)c->d_depth + (size_t)f0 * np * dsz, (const char *)io.depth + (size_t)f0 * np * dsz, (size_t)nf * np * dsz, cudaMemcpyHostToDevice, hs));
         if (ns) CK(cudaMemcpyAsync(d_slot, streaks + s0, (size_t)ns * sizeof(rr_streak_rec), cudaMemcpyHostToDevice, hs));
         CK(cudaMemcpyAsync(c->d_sub_offsets + (size_t)k * (c->max_batch + 1), so, (nf + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, hs));
         if (multi) {
@@ -522,9 +544,11 @@ static int submit_frames(rr_context *c, int F, const uint8_t *bgr, const float *
         c->scan_base[k] = sb; c->sub_n[k] = ns;
         c->call_scan_base[slot][k] = sb; c->call_sub_n[slot][k] = ns;
         rr_frame_bufs saved = c->fb;
-        saved.bgr = c->d_bgr; saved.depth = c->d_depth; saved.streaks = d_slot - s0;   // sub_view adds s0 back
+        saved.bgr = c->d_bgr; saved.depth = c->d_depth; saved.depth_u16 = du16; saved.streaks = d_slot - s0;   // sub_view adds s0 back
         saved.offsets = c->d_sub_offsets + (size_t)k * (c->max_batch + 1);
-        c->fb = sub_view(c, saved, f0, s0, sb);
+        rr_frame_bufs sel = saved;
+        select_outputs(sel, saved, io);
+        c->fb = sub_view(c, sel, f0, s0, sb);
         c->fb.offsets = saved.offsets;
         r = run_pipeline(c, nf, ns, timed && S == 1);
         saved.bgr = nullptr; saved.depth = nullptr; saved.streaks = nullptr;
@@ -533,9 +557,12 @@ static int submit_frames(rr_context *c, int F, const uint8_t *bgr, const float *
         sb += ns + 1;
         cudaStream_t ds = multi ? c->s_d2h : st;
         if (multi) { CK(cudaEventRecord(c->ev_done[k], st)); CK(cudaStreamWaitEvent(ds, c->ev_done[k], 0)); }
-        if (out_bgr) CK(cudaMemcpyAsync(out_bgr + (size_t)f0 * np * 3, b.out_bgr + (size_t)f0 * np * 3, (size_t)nf * np * 3 * sizeof(float), cudaMemcpyDeviceToHost, ds));
-        if (out_mask) CK(cudaMemcpyAsync(out_mask + (size_t)f0 * np, b.out_mask + (size_t)f0 * np, (size_t)nf * np * sizeof(float), cudaMemcpyDeviceToHost, ds));
-        if (out_bgr_u8) CK(cudaMemcpyAsync(out_bgr_u8 + (size_t)f0 * np * 3, b.out_u8 + (size_t)f0 * np * 3, (size_t)nf * np * 3, cudaMemcpyDeviceToHost, ds));
+        if (io.out_bgr) CK(cudaMemcpyAsync(io.out_bgr + (size_t)f0 * np * 3, b.out_bgr + (size_t)f0 * np * 3, (size_t)nf * np * 3 * sizeof(float), cudaMemcpyDeviceToHost, ds));
+        if (io.out_mask) CK(cudaMemcpyAsync(io.out_mask + (size_t)f0 * np, b.out_mask + (size_t)f0 * np, (size_t)nf * np * sizeof(float), cudaMemcpyDeviceToHost, ds));
+        if (io.out_bgr_u8) CK(cudaMemcpyAsync(io.out_bgr_u8 + (size_t)f0 * np * 3, b.out_u8 + (size_t)f0 * np * 3, (size_t)nf * np * 3, cudaMemcpyDeviceToHost, ds));
+        if (io.out_mask_idx8) CK(cudaMemcpyAsync(io.out_mask_idx8 + (size_t)f0 * np, b.out_idx8 + (size_t)f0 * np, (size_t)nf * np, cudaMemcpyDeviceToHost, ds));
+        if (io.out_mask_u16) CK(cudaMemcpyAsync(io.out_mask_u16 + (size_t)f0 * np, b.out_u16 + (size_t)f0 * np, (size_t)nf * np * 2, cudaMemcpyDeviceToHost, ds));
+        if (io.out_mask_range) CK(cudaMemcpyAsync(io.out_mask_range + (size_t)f0 * 2, b.mask_range + (size_t)f0 * 2, (size_t)nf * 2 * sizeof(double), cudaMemcpyDeviceToHost, ds));
         if (multi) CK(cudaEventRecord(c->ev_d2h[k], ds));
     }
     c->n_sub_last = S;
@@ -551,25 +578,39 @@ static int submit_frames(rr_context *c, int F, const uint8_t *bgr, const float *
     return RR_OK;
 }
 
-static int validate_batch(rr_context *c, int n_frames, const uint8_t *bgr, const float *depth, const rr_streak_rec *streaks,
-                          const int32_t *streak_offsets, const char *who) {
+static int validate_batch(rr_context *c, int n_frames, const rr_frame_io *io, const char *who) {
     int r = check_ready(c, n_frames, who);
     if (r != RR_OK) return r;
-    if (!bgr || !depth || !streak_offsets) { set_err("%s: NULL input", who); return RR_ERR_ARG; }
+    if (!io || !io->bgr || !io->depth || !io->streak_offsets) { set_err("%s: NULL input", who); return RR_ERR_ARG; }
+    if (io->depth_format != RR_DEPTH_F32_M && io->depth_format != RR_DEPTH_U16_256) { set_err("%s: unknown depth format %d", who, io->depth_format); return RR_ERR_ARG; }
     if (!c->d_db) { set_err("%s: no streak DB", who); return RR_ERR_STATE; }
-    const int n_streaks = streak_offsets[n_frames];
-    if (streak_offsets[0] != 0 || n_streaks < 0 || (n_streaks > 0 && !streaks)) { set_err("%s: bad streak offsets", who); return RR_ERR_ARG; }
+    const int n_streaks = io->streak_offsets[n_frames];
+    if (io->streak_offsets[0] != 0 || n_streaks < 0 || (n_streaks > 0 && !io->streaks)) { set_err("%s: bad streak offsets", who); return RR_ERR_ARG; }
     for (int f = 0; f < n_frames; f++)
-        if (streak_offsets[f + 1] < streak_offsets[f]) { set_err("%s: streak offsets not monotone", who); return RR_ERR_ARG; }
+        if (io->streak_offsets[f + 1] < io->streak_offsets[f]) { set_err("%s: streak offsets not monotone", who); return RR_ERR_ARG; }
     return RR_OK;
+}
+
+static rr_frame_io legacy_io(const uint8_t *bgr, const float *depth, const rr_streak_rec *streaks, const int32_t *streak_offsets,
+                             float *out_bgr, float *out_mask, uint8_t *out_bgr_u8) {
+    rr_frame_io io;
+    memset(&io, 0, sizeof(io));
+    io.bgr = bgr; io.depth = depth; io.depth_format = RR_DEPTH_F32_M; io.streaks = streaks; io.streak_offsets = streak_offsets;
+    io.out_bgr = out_bgr; io.out_mask = out_mask; io.out_bgr_u8 = out_bgr_u8;
+    return io;
+}
+
+int rr_submit_frames_io(rr_context *c, int n_frames, const rr_frame_io *io) {
+    int r = validate_batch(c, n_frames, io, "rr_submit_frames_io");
+    if (r != RR_OK) return r;
+    CK(cudaSetDevice(c->device));
+    return submit_frames(c, n_frames, *io, false, 2);
 }
 
 int rr_submit_frames(rr_context *c, int n_frames, const uint8_t *bgr, const float *depth, const rr_streak_rec *streaks,
                      const int32_t *streak_offsets, float *out_bgr, float *out_mask, uint8_t *out_bgr_u8) {
-    int r = validate_batch(c, n_frames, bgr, depth, streaks, streak_offsets, "rr_submit_frames");
-    if (r != RR_OK) return r;
-    CK(cudaSetDevice(c->device));
-    return submit_frames(c, n_frames, bgr, depth, streaks, streak_offsets, out_bgr, out_mask, out_bgr_u8, false, 2);
+    const rr_frame_io io = legacy_io(bgr, depth, streaks, streak_offsets, out_bgr, out_mask, out_bgr_u8);
+    return rr_submit_frames_io(c, n_frames, &io);
 }
 
 int rr_wait_frames(rr_context *c) {
@@ -578,14 +619,13 @@ int rr_wait_frames(rr_context *c) {
     return wait_oldest(c, true);
 }
 
-int rr_render_frames(rr_context *c, int n_frames, const uint8_t *bgr, const float *depth, const rr_streak_rec *streaks,
-                     const int32_t *streak_offsets, float *out_bgr, float *out_mask, uint8_t *out_bgr_u8) {
-    int r = validate_batch(c, n_frames, bgr, depth, streaks, streak_offsets, "rr_render_frames");
+int rr_render_frames_io(rr_context *c, int n_frames, const rr_frame_io *io) {
+    int r = validate_batch(c, n_frames, io, "rr_render_frames_io");
     if (r != RR_OK) return r;
     CK(cudaSetDevice(c->device));
     while (c->inflight) { r = wait_oldest(c, false); if (r != RR_OK) return r; }
     for (int attempt = 0;; attempt++) {
-        r = submit_frames(c, n_frames, bgr, depth, streaks, streak_offsets, out_bgr, out_mask, out_bgr_u8, true, 4);
+        r = submit_frames(c, n_frames, *io, true, 4);
         if (r != RR_OK) return r;
         const int S = c->n_sub_last;
         r = wait_oldest(c, attempt == 0);
@@ -600,52 +640,61 @@ int rr_render_frames(rr_context *c, int n_frames, const uint8_t *bgr, const floa
     }
 }
 
-int rr_render_frames_device(rr_context *c, int n_frames, const uint8_t *d_bgr, const float *d_depth,
-                            const rr_streak_rec *d_streaks, const int32_t *h_streak_offsets, float *d_out_bgr,
-                            float *d_out_mask, uint8_t *d_out_bgr_u8, int sync) {
-    int r = check_ready(c, n_frames, "rr_render_frames_device");
-    if (r != RR_OK) return r;
-    if (!d_bgr || !d_depth || !h_streak_offsets) { set_err("rr_render_frames_device: NULL input"); return RR_ERR_ARG; }
-    if (!c->d_db) { set_err("rr_render_frames_device: no streak DB"); return RR_ERR_STATE; }
-    CK(cudaSetDevice(c->device));
-    const int F = n_frames, n_streaks = h_streak_offsets[F];
+int rr_render_frames(rr_context *c, int n_frames, const uint8_t *bgr, const float *depth, const rr_streak_rec *streaks,
+                     const int32_t *streak_offsets, float *out_bgr, float *out_mask, uint8_t *out_bgr_u8) {
+    const rr_frame_io io = legacy_io(bgr, depth, streaks, streak_offsets, out_bgr, out_mask, out_bgr_u8);
+    return rr_render_frames_io(c, n_frames, &io);
+}
+
+// inputs and outputs of *io are DEVICE pointers (streak_offsets stays a host array); outputs may be NULL
+static int render_device(rr_context *c, int F, const rr_frame_io &io, int sync) {
+    int r;
+    const int n_streaks = io.streak_offsets[F];
     while (c->inflight) { r = wait_oldest(c, false); if (r != RR_OK) return r; }
     r = ensure_streak_cap(c, n_streaks, 0);
     if (r != RR_OK) return r;
     c->fb.err_flag = c->d_err2;
     cudaStream_t st = c->stream;
-    rr_frame_bufs b_saved = c->fb;
+    const rr_frame_bufs b_saved = c->fb;
     rr_frame_bufs &b = c->fb;
-    CK(cudaEventRecord(c->ev[RR_T_H2D], st));
-    CK(cudaMemcpyAsync(c->d_offsets, h_streak_offsets, (F + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    b.bgr = d_bgr; b.depth = d_depth; b.streaks = d_streaks; b.offsets = c->d_offsets; b.bgf = c->d_bgf;
-    if (d_out_bgr) b.out_bgr = d_out_bgr;
-    if (d_out_mask) b.out_mask = d_out_mask;
-    if (d_out_bgr_u8) b.out_u8 = d_out_bgr_u8;
-    c->n_sub_last = 1; c->scan_base[0] = 0; c->sub_n[0] = n_streaks;
-    CK(cudaMemsetAsync(b.err_flag, 0, sizeof(int), st));
-    r = run_pipeline(c, F, n_streaks, true);
-    b.out_bgr = b_saved.out_bgr; b.out_mask = b_saved.out_mask; b.out_u8 = b_saved.out_u8;
-    if (r != RR_OK) return r;
-    CK(cudaEventRecord(c->ev[RR_T_TOTAL], st));
-    if (sync) {
-        r = check_flag(c, true);
-        if (r == RR_ERR_CAPACITY && strstr(g_err, "grown")) {     // re-run once with the larger arena
-            b.bgr = d_bgr; b.depth = d_depth; b.streaks = d_streaks; b.offsets = c->d_offsets;
-            if (d_out_bgr) b.out_bgr = d_out_bgr;
-            if (d_out_mask) b.out_mask = d_out_mask;
-            if (d_out_bgr_u8) b.out_u8 = d_out_bgr_u8;
-            CK(cudaEventRecord(c->ev[RR_T_H2D], st));
-            CK(cudaMemsetAsync(b.err_flag, 0, sizeof(int), st));
-            r = run_pipeline(c, F, n_streaks, true);
-            b.out_bgr = b_saved.out_bgr; b.out_mask = b_saved.out_mask; b.out_u8 = b_saved.out_u8;
-            if (r != RR_OK) return r;
-            CK(cudaEventRecord(c->ev[RR_T_TOTAL], st));
-            r = check_flag(c, false);
-        }
+    for (int attempt = 0;; attempt++) {
+        CK(cudaEventRecord(c->ev[RR_T_H2D], st));
+        if (attempt == 0) CK(cudaMemcpyAsync(c->d_offsets, io.streak_offsets, (F + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        b.bgr = io.bgr; b.depth = io.depth; b.depth_u16 = io.depth_format == RR_DEPTH_U16_256; b.streaks = io.streaks; b.offsets = c->d_offsets;
+        b.bgf = c->d_bgf;
+        b.out_bgr = io.out_bgr; b.out_mask = io.out_mask; b.out_u8 = io.out_bgr_u8; b.out_idx8 = io.out_mask_idx8; b.out_u16 = io.out_mask_u16;
+        c->n_sub_last = 1; c->scan_base[0] = 0; c->sub_n[0] = n_streaks;
+        CK(cudaMemsetAsync(b.err_flag, 0, sizeof(int), st));
+        r = run_pipeline(c, F, n_streaks, true);
+        if (r == RR_OK && io.out_mask_range)
+            CK(cudaMemcpyAsync(io.out_mask_range, b.mask_range, (size_t)F * 2 * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        b.out_bgr = b_saved.out_bgr; b.out_mask = b_saved.out_mask; b.out_u8 = b_saved.out_u8; b.out_idx8 = b_saved.out_idx8; b.out_u16 = b_saved.out_u16;
+        b.bgr = nullptr; b.depth = nullptr; b.streaks = nullptr;
+        if (r != RR_OK) return r;
+        CK(cudaEventRecord(c->ev[RR_T_TOTAL], st));
+        if (!sync) return RR_OK;
+        r = check_flag(c, attempt == 0);
+        if (r == RR_ERR_CAPACITY && attempt == 0 && strstr(g_err, "grown")) continue;      // re-run once with the larger arena
         finish_timings(c);
+        return r;
     }
-    return r;
+}
+
+int rr_render_frames_device_io(rr_context *c, int n_frames, const rr_frame_io *io, int sync) {
+    int r = check_ready(c, n_frames, "rr_render_frames_device_io");
+    if (r != RR_OK) return r;
+    if (!io || !io->bgr || !io->depth || !io->streak_offsets) { set_err("rr_render_frames_device_io: NULL input"); return RR_ERR_ARG; }
+    if (io->depth_format != RR_DEPTH_F32_M && io->depth_format != RR_DEPTH_U16_256) { set_err("rr_render_frames_device_io: unknown depth format %d", io->depth_format); return RR_ERR_ARG; }
+    if (!c->d_db) { set_err("rr_render_frames_device_io: no streak DB"); return RR_ERR_STATE; }
+    CK(cudaSetDevice(c->device));
+    return render_device(c, n_frames, *io, sync);
+}
+
+int rr_render_frames_device(rr_context *c, int n_frames, const uint8_t *d_bgr, const float *d_depth,
+                            const rr_streak_rec *d_streaks, const int32_t *h_streak_offsets, float *d_out_bgr,
+                            float *d_out_mask, uint8_t *d_out_bgr_u8, int sync) {
+    const rr_frame_io io = legacy_io(d_bgr, d_depth, d_streaks, h_streak_offsets, d_out_bgr, d_out_mask, d_out_bgr_u8);
+    return rr_render_frames_device_io(c, n_frames, &io, sync);
 }
 
 int rr_fog_only(rr_context *c, int n_frames, const uint8_t *bgr, const float *depth, double *out_planar) {
@@ -659,7 +708,7 @@ int rr_fog_only(rr_context *c, int n_frames, const uint8_t *bgr, const float *de
     const size_t rs2 = c->cam.render_scale == 2 ? 4 : 1;
     CK(cudaMemcpyAsync(c->d_bgr, bgr, F * np * 3 * rs2, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->d_depth, depth, F * np * sizeof(float), cudaMemcpyHostToDevice, st));
-    b.bgr = c->d_bgr; b.depth = c->d_depth; b.bgf = c->d_bgf;
+    b.bgr = c->d_bgr; b.depth = c->d_depth; b.depth_u16 = 0; b.bgf = c->d_bgf;
     CK(rr_launch_stats(b, n_frames, c->cam.W, c->cam.H, rs2 == 4 ? 2 : 1, c->d_bgf, st));
     CK(rr_launch_fog(b, c->fogc, n_frames, c->cam.W, c->cam.H, st));
     c->launches += 5;
@@ -796,6 +845,65 @@ int rr_host_alloc(void **ptr, size_t bytes) {
     if (!ptr) { set_err("rr_host_alloc: ptr is NULL"); return RR_ERR_ARG; }
     CK(cudaHostAlloc(ptr, bytes ? bytes : 1, cudaHostAllocDefault));
     return RR_OK;
+}
+
+int rr_host_alloc_flags(void **ptr, size_t bytes, int write_combined) {
+    if (!ptr) { set_err("rr_host_alloc_flags: ptr is NULL"); return RR_ERR_ARG; }
+    CK(cudaHostAlloc(ptr, bytes ? bytes : 1, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+    return RR_OK;
+}
+
+// Concurrent pinned host->device and device->host copies on two streams for `seconds`: what the host link of this
+// process (PCIe + host memory, under whatever the other ranks of the box are doing at the same time) sustains.
+int rr_host_link_probe(int device_id, size_t bytes, double seconds, int write_combined, int direction, double *h2d_gbs,
+                       double *d2h_gbs) {
+    if (bytes < (1u << 20) || seconds <= 0 || !(direction & 3)) { set_err("rr_host_link_probe: bad arguments"); return RR_ERR_ARG; }
+    CK(cudaSetDevice(device_id));
+    void *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
+    cudaStream_t s[2] = {nullptr, nullptr};
+    cudaEvent_t e0[2] = {nullptr, nullptr}, e1[2] = {nullptr, nullptr};
+    int rc = RR_OK;
+    double gbs[2] = {0, 0};
+    do {
+        cudaError_t e;
+#define PB(call) if ((e = (call)) != cudaSuccess) { set_err("rr_host_link_probe: %s -> %s", #call, cudaGetErrorString(e)); rc = RR_ERR_CUDA; break; }
+        PB(cudaHostAlloc(&h_in, bytes, write_combined ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+        PB(cudaHostAlloc(&h_out, bytes, cudaHostAllocDefault));
+        memset(h_in, 1, bytes); memset(h_out, 0, bytes);            // first touch on the calling thread's NUMA node
+        PB(cudaMalloc(&d_in, bytes)); PB(cudaMalloc(&d_out, bytes));
+        PB(cudaMemset(d_out, 2, bytes));
+        for (int i = 0; i < 2; i++) { PB(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking)); PB(cudaEventCreate(&e0[i])); PB(cudaEventCreate(&e1[i])); }
+        if (rc != RR_OK) break;
+        // warm-up
+        if (direction & 1) PB(cudaMemcpyAsync(d_in, h_in, bytes, cudaMemcpyHostToDevice, s[0]));
+        if (direction & 2) PB(cudaMemcpyAsync(h_out, d_out, bytes, cudaMemcpyDeviceToHost, s[1]));
+        PB(cudaStreamSynchronize(s[0])); PB(cudaStreamSynchronize(s[1]));
+        // size the run from one timed round
+        long long reps = 1, done = 0;
+        double elapsed = 0;
+        for (int i = 0; i < 2; i++) PB(cudaEventRecord(e0[i], s[i]));
+        while (elapsed < seconds && rc == RR_OK) {
+            for (long long k = 0; k < reps; k++) {
+                if (direction & 1) PB(cudaMemcpyAsync(d_in, h_in, bytes, cudaMemcpyHostToDevice, s[0]));
+                if (direction & 2) PB(cudaMemcpyAsync(h_out, d_out, bytes, cudaMemcpyDeviceToHost, s[1]));
+            }
+            for (int i = 0; i < 2; i++) PB(cudaEventRecord(e1[i], s[i]));
+            PB(cudaStreamSynchronize(s[0])); PB(cudaStreamSynchronize(s[1]));
+            done += reps;
+            float ms0 = 0, ms1 = 0;
+            PB(cudaEventElapsedTime(&ms0, e0[0], e1[0])); PB(cudaEventElapsedTime(&ms1, e0[1], e1[1]));
+            elapsed = (ms0 > ms1 ? ms0 : ms1) / 1000.0;
+            if (direction & 1) gbs[0] = (double)done * bytes / (ms0 / 1000.0) / 1e9;
+            if (direction & 2) gbs[1] = (double)done * bytes / (ms1 / 1000.0) / 1e9;
+        }
+#undef PB
+    } while (0);
+    for (int i = 0; i < 2; i++) { if (e0[i]) cudaEventDestroy(e0[i]); if (e1[i]) cudaEventDestroy(e1[i]); if (s[i]) cudaStreamDestroy(s[i]); }
+    if (d_in) cudaFree(d_in); if (d_out) cudaFree(d_out);
+    if (h_in) cudaFreeHost(h_in); if (h_out) cudaFreeHost(h_out);
+    if (h2d_gbs) *h2d_gbs = gbs[0];
+    if (d2h_gbs) *d2h_gbs = gbs[1];
+    return rc;
 }
 
 int rr_host_free(void *ptr) {

@@ -87,3 +87,46 @@ extern "C" int rr_host_draw_randoms(uint32_t seed, int n, const uint8_t *types, 
     }
     return RR_OK;
 }
+
+// A batch of image frames' records from their simulator frames, one native call: the in-frame filter
+// (common/generator.py:413-420, on the current -- possibly wind-mutated -- positions), the texture bucket
+// (common/bad_weather.py:250-265: first i with ratio < ratios[i], else 4) and the frame's two NumPy RNG draws per
+// streak (generator.py:318,136; bad_weather.py:252-264).  Output records carry ip1 = ip1m, ip2 = ip2m (the angle is taken
+// from the positions before this frame's wind rotation, generator.py:138-144).  The rotation itself (generator.py:149-161)
+// is NOT applied here: with noise_std == 0 or noise_scale == 0 it is the identity on integer end points; otherwise the
+// caller applies it per frame (rain_rendering_b200/streaks.py: apply_wind_noise, in NumPy like the reference, because
+// the write-back makes frames depend on each other) -- src_index tells it which simulator record each output came from.
+extern "C" int rr_host_assemble_batch(int n_frames, const rr_streak_rec *const *sim, const int32_t *n_sim, const uint32_t *seeds,
+                                      int W, int H, const double *db_ratios, int n_ratios, double noise_std, double noise_scale,
+                                      rr_streak_rec *out, int64_t out_cap, int32_t *offsets, int32_t *src_index) {
+    if (n_frames < 0 || !n_sim || !seeds || !offsets || (n_frames > 0 && !sim) || (out_cap > 0 && !out) || (n_ratios > 0 && !db_ratios)) return RR_ERR_ARG;
+    const int m = H > W ? H : W, nr = n_ratios < 4 ? n_ratios : 4;
+    int64_t o = 0;
+    offsets[0] = 0;
+    MT mt;
+    for (int f = 0; f < n_frames; f++) {
+        const rr_streak_rec *S = sim[f];
+        if (n_sim[f] < 0 || (n_sim[f] > 0 && !S)) return RR_ERR_ARG;
+        mt.seed(seeds[f]);
+        for (int i = 0; i < n_sim[f]; i++) {
+            const rr_streak_rec &r = S[i];
+            const bool ok_w = 1 <= r.max_width && r.max_width < m, ok_l = 1 <= r.length && r.length < m;
+            const bool ins = 0 <= r.ip1m[0] && r.ip1m[0] < W && 0 <= r.ip1m[1] && r.ip1m[1] < H;
+            const bool ine = 0 <= r.ip2m[0] && r.ip2m[0] < W && 0 <= r.ip2m[1] && r.ip2m[1] < H;
+            if (!(ok_w && ok_l && (ins || ine))) continue;
+            if (o >= out_cap) return RR_ERR_CAPACITY;
+            rr_streak_rec &d = out[o];
+            d = r;
+            d.ip1[0] = r.ip1m[0]; d.ip1[1] = r.ip1m[1]; d.ip2[0] = r.ip2m[0]; d.ip2[1] = r.ip2m[1];
+            int b = 0;
+            while (b < nr && !(r.ratio < db_ratios[b])) b++;
+            d.tex_idx = (uint8_t)(10 * b + (int)mt.bounded(9));
+            d.noise_deg = r.type != 0 ? (0.0 + noise_std * mt.legacy_gauss()) * noise_scale : 0.0;
+            if (src_index) src_index[o] = i;
+            o++;
+        }
+        if (o > 0x7fffffff) return RR_ERR_CAPACITY;
+        offsets[f + 1] = (int32_t)o;
+    }
+    return RR_OK;
+}

@@ -23,6 +23,8 @@
 #include <thread>
 #include <vector>
 #include "../../include/rain_b200.h"
+#include "rr_host_deflate.h"
+#include "rr_viridis.h"
 
 extern "C" void rr_set_error(const char *msg);
 
@@ -57,7 +59,9 @@ int paeth(int a, int b, int c) {
 }
 
 // -> RR_OK, RR_PNG_UNSUPPORTED (valid PNG this codec does not handle) or RR_ERR_ARG (not a readable PNG)
-int decode(const char *path, Image *img, bool header_only) {
+// want_w / want_h > 0: the size the caller's buffer was made for -- anything else returns RR_PNG_SIZE right after the
+// header, before a single byte is allocated for the pixels (a 60-byte file may claim 65536 x 65536 RGBA16 = 34 GB)
+int decode(const char *path, Image *img, bool header_only, int want_w = 0, int want_h = 0) {
     std::vector<unsigned char> file;
     if (!read_file(path, &file)) return RR_ERR_ARG;
     if (file.size() < 8 + 25 || memcmp(file.data(), kSig, 8) != 0) return RR_ERR_ARG;
@@ -82,11 +86,14 @@ int decode(const char *path, Image *img, bool header_only) {
             have_hdr = true;
             img->channels = color == 0 ? 1 : color == 2 ? 3 : color == 4 ? 2 : color == 6 ? 4 : 0;
             if (header_only) { if (color == 3) img->channels = 3; return RR_OK; }
+            if (want_w > 0 && (img->w != want_w || img->h != want_h)) { ret = RR_PNG_SIZE; break; }
+            if ((uint64_t)img->w * (uint64_t)img->h > ((uint64_t)1 << 28)) { ret = RR_PNG_UNSUPPORTED; break; }     // 268 Mpx: not a camera frame
             if (img->channels == 0 || interlace != 0 || (img->depth != 8 && img->depth != 16) || data[10] != 0 || data[11] != 0) {
                 ret = RR_PNG_UNSUPPORTED;
                 break;
             }
             stride = (size_t)img->w * img->channels * (img->depth / 8);
+            if ((stride + 1) * (size_t)img->h + 1 > 0xfffffff0u) { ret = RR_PNG_UNSUPPORTED; break; }              // zlib counts in 32 bits
             raw.resize((stride + 1) * (size_t)img->h + 1);      // one spare byte: the stream must END (Adler-32 verified), not just fill the image
             if (inflateInit(&zs) != Z_OK) break;
             z_open = true;
@@ -169,6 +176,16 @@ int to_depth_f32(const Image &im, float *dst) {
     return RR_OK;
 }
 
+// cv2.imread(path, IMREAD_UNCHANGED) of a single-channel file as uint16 samples (the /256 happens on the device)
+int to_depth_u16(const Image &im, uint16_t *dst) {
+    if (im.channels != 1) return RR_PNG_UNSUPPORTED;
+    const size_t n = (size_t)im.w * im.h;
+    const unsigned char *s = im.px.data();
+    if (im.depth == 16) for (size_t i = 0; i < n; i++) dst[i] = (uint16_t)((s[2 * i] << 8) | s[2 * i + 1]);
+    else for (size_t i = 0; i < n; i++) dst[i] = s[i];
+    return RR_OK;
+}
+
 void chunk(std::vector<unsigned char> *out, const char *type, const unsigned char *data, size_t len) {
     unsigned char hdr[8];
     put32(hdr, (uint32_t)len);
@@ -180,6 +197,41 @@ void chunk(std::vector<unsigned char> *out, const char *type, const unsigned cha
     unsigned char tail[4];
     put32(tail, (uint32_t)c);
     out->insert(out->end(), tail, tail + 4);
+}
+
+// filt: h filtered scanlines ((stride + 1) bytes each, filter-type byte first) -> PNG file.
+// level 0 stores, 1 = this library's run + Huffman encoder (rr_host_deflate.h), 2..9 = zlib at that level.
+int write_png(const char *path, const std::vector<unsigned char> &filt, int w, int h, int color, int depth, int level) {
+    std::vector<unsigned char> comp;
+    if (level == 1) rr_deflate::zlib_compress_fast(filt.data(), filt.size(), comp);
+    else {
+        z_stream zs;
+        memset(&zs, 0, sizeof(zs));
+        if (deflateInit2(&zs, level, Z_DEFLATED, 15, 8, Z_DEFAULT_STRATEGY) != Z_OK) return RR_ERR_ARG;
+        comp.resize(deflateBound(&zs, (uLong)filt.size()));
+        zs.next_in = const_cast<unsigned char *>(filt.data()); zs.avail_in = (uInt)filt.size();
+        zs.next_out = comp.data(); zs.avail_out = (uInt)comp.size();
+        int r = deflate(&zs, Z_FINISH);
+        comp.resize(zs.total_out);
+        deflateEnd(&zs);
+        if (r != Z_STREAM_END) return RR_ERR_ARG;
+    }
+    std::vector<unsigned char> out;
+    out.reserve(comp.size() + 128);
+    out.insert(out.end(), kSig, kSig + 8);
+    unsigned char ihdr[13];
+    put32(ihdr, (uint32_t)w); put32(ihdr + 4, (uint32_t)h);
+    ihdr[8] = (unsigned char)depth; ihdr[9] = (unsigned char)color; ihdr[10] = ihdr[11] = ihdr[12] = 0;
+    chunk(&out, "IHDR", ihdr, 13);
+    chunk(&out, "IDAT", comp.data(), comp.size());
+    chunk(&out, "IEND", nullptr, 0);
+    std::string tmp = std::string(path) + ".part";
+    FILE *f = fopen(tmp.c_str(), "wb");
+    if (!f) return RR_ERR_ARG;
+    bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+    ok = (fclose(f) == 0) && ok;
+    if (!ok || rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); return RR_ERR_ARG; }
+    return RR_OK;
 }
 
 // rows: h scanlines of `stride` bytes (samples already big-endian / RGB order); bpp = bytes per pixel
@@ -198,34 +250,37 @@ int encode(const char *path, const unsigned char *rows, int w, int h, int color,
             for (size_t i = bpp; i < stride; i++) d[i] = (unsigned char)(s[i] - s[i - bpp]);
         }
     }
-    z_stream zs;
-    memset(&zs, 0, sizeof(zs));
-    // level 1 = Huffman coding only (no match search): 3x faster than zlib's level-1 matcher and no larger on Sub-filtered
-    // camera noise; higher levels use the regular matcher
-    if (deflateInit2(&zs, level, Z_DEFLATED, 15, 8, level == 1 ? Z_HUFFMAN_ONLY : Z_DEFAULT_STRATEGY) != Z_OK) return RR_ERR_ARG;
-    std::vector<unsigned char> comp(deflateBound(&zs, (uLong)filt.size()));
-    zs.next_in = filt.data(); zs.avail_in = (uInt)filt.size();
-    zs.next_out = comp.data(); zs.avail_out = (uInt)comp.size();
-    int r = deflate(&zs, Z_FINISH);
-    size_t clen = zs.total_out;
-    deflateEnd(&zs);
-    if (r != Z_STREAM_END) return RR_ERR_ARG;
-    std::vector<unsigned char> out;
-    out.reserve(clen + 128);
-    out.insert(out.end(), kSig, kSig + 8);
-    unsigned char ihdr[13];
-    put32(ihdr, (uint32_t)w); put32(ihdr + 4, (uint32_t)h);
-    ihdr[8] = (unsigned char)depth; ihdr[9] = (unsigned char)color; ihdr[10] = ihdr[11] = ihdr[12] = 0;
-    chunk(&out, "IHDR", ihdr, 13);
-    chunk(&out, "IDAT", comp.data(), clen);
-    chunk(&out, "IEND", nullptr, 0);
-    std::string tmp = std::string(path) + ".part";
-    FILE *f = fopen(tmp.c_str(), "wb");
-    if (!f) return RR_ERR_ARG;
-    bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
-    ok = (fclose(f) == 0) && ok;
-    if (!ok || rename(tmp.c_str(), path) != 0) { remove(tmp.c_str()); return RR_ERR_ARG; }
-    return RR_OK;
+    return write_png(path, filt, w, h, color, depth, level);
+}
+
+// The reference's file formats (generator.py:466-467, plt.imsave): 8-bit RGBA, alpha 255.  Colour conversion, alpha and the
+// Sub filter in one pass over the batch buffer.
+//   image: from the BGR uint8 frame;  mask: from the colormap index through matplotlib's viridis table (rr_viridis.h)
+int write_rgba(const char *path, const uint8_t *bgr, const uint8_t *idx8, int w, int h, int level) {
+    const size_t stride = (size_t)w * 4;
+    std::vector<unsigned char> filt((stride + 1) * (size_t)h);
+    const bool sub = level > 0;
+    for (int y = 0; y < h; y++) {
+        unsigned char *d = filt.data() + (stride + 1) * (size_t)y;
+        *d++ = sub ? 1 : 0;
+        unsigned pr = 0, pg = 0, pb = 0, pa = 0;
+        for (int x = 0; x < w; x++) {
+            unsigned r, g, b;
+            if (bgr) { const uint8_t *p = bgr + ((size_t)y * w + x) * 3; r = p[2]; g = p[1]; b = p[0]; }
+            else { const uint8_t *c = rr_viridis_rgb[idx8[(size_t)y * w + x]]; r = c[0]; g = c[1]; b = c[2]; }
+            d[4 * x] = (unsigned char)(r - pr); d[4 * x + 1] = (unsigned char)(g - pg); d[4 * x + 2] = (unsigned char)(b - pb);
+            d[4 * x + 3] = (unsigned char)(255u - pa);
+            if (sub) { pr = r; pg = g; pb = b; pa = 255u; }
+        }
+    }
+    return write_png(path, filt, w, h, 6, 8, level);
+}
+
+int write_gray16(const char *path, const uint16_t *v, int w, int h, int level) {
+    const size_t n = (size_t)w * h;
+    std::vector<unsigned char> g(n * 2);
+    for (size_t i = 0; i < n; i++) { g[2 * i] = (unsigned char)(v[i] >> 8); g[2 * i + 1] = (unsigned char)v[i]; }
+    return encode(path, g.data(), w, h, 0, 16, 2, level);
 }
 
 int write_bgr8(const char *path, const uint8_t *bgr, int w, int h, int level) {
@@ -265,7 +320,8 @@ void parallel_for(int n, int n_threads, F fn) {
 extern "C" int rr_host_png_info(const char *path, int32_t *w, int32_t *h, int32_t *channels, int32_t *bit_depth) {
     if (!path) { rr_set_error("rr_host_png_info: path is NULL"); return RR_ERR_ARG; }
     Image im;
-    int r = decode(path, &im, true);
+    int r = RR_ERR_ARG;
+    try { r = decode(path, &im, true); } catch (...) { r = RR_ERR_ARG; }
     if (r != RR_OK) { rr_set_error((std::string("rr_host_png_info: cannot read ") + path).c_str()); return r; }
     if (w) *w = im.w;
     if (h) *h = im.h;
@@ -277,9 +333,9 @@ extern "C" int rr_host_png_info(const char *path, int32_t *w, int32_t *h, int32_
 // Decodes n frames into the batch buffers (frame i at bgr + i * 3 * Wi * Hi and depth + i * Wd * Hd); a NULL path
 // list skips that kind.  status[i] receives RR_OK, RR_PNG_UNSUPPORTED / RR_ERR_ARG (file i must go through the
 // caller's fallback decoder) or RR_PNG_SIZE (decodable, but not the expected size).  Returns the number of
-// frames that are not RR_OK.
-extern "C" int rr_host_png_read_batch(int n, const char *const *image_paths, const char *const *depth_paths, uint8_t *bgr, int Wi, int Hi,
-                                      float *depth, int Wd, int Hd, int n_threads, int32_t *status) {
+// frames that are not RR_OK.  depth_u16 != 0: depth points to uint16 samples (rr_frame_io RR_DEPTH_U16_256).
+static int read_batch(int n, const char *const *image_paths, const char *const *depth_paths, uint8_t *bgr, int Wi, int Hi,
+                      void *depth, int depth_u16, int Wd, int Hd, int n_threads, int32_t *status) {
     if (n < 0 || !status || (image_paths && !bgr) || (depth_paths && !depth)) { rr_set_error("rr_host_png_read_batch: bad arguments"); return RR_ERR_ARG; }
     for (int i = 0; i < n; i++) status[i] = RR_OK;
     const int jobs = 2 * n;
@@ -287,17 +343,88 @@ extern "C" int rr_host_png_read_batch(int n, const char *const *image_paths, con
         const int i = j >> 1, kind = j & 1;
         const char *const *paths = kind ? depth_paths : image_paths;
         if (!paths || !paths[i]) return;
-        Image im;
-        int r = decode(paths[i], &im, false);
-        if (r == RR_OK) {
-            if (kind == 0) r = (im.w == Wi && im.h == Hi) ? to_bgr8(im, bgr + (size_t)i * 3 * Wi * Hi) : RR_PNG_SIZE;
-            else r = (im.w == Wd && im.h == Hd) ? to_depth_f32(im, depth + (size_t)i * Wd * Hd) : RR_PNG_SIZE;
-        }
+        int r = RR_ERR_ARG;
+        try {
+            Image im;
+            r = decode(paths[i], &im, false, kind ? Wd : Wi, kind ? Hd : Hi);
+            if (r == RR_OK) {
+                if (kind == 0) r = to_bgr8(im, bgr + (size_t)i * 3 * Wi * Hi);
+                else if (depth_u16) r = to_depth_u16(im, (uint16_t *)depth + (size_t)i * Wd * Hd);
+                else r = to_depth_f32(im, (float *)depth + (size_t)i * Wd * Hd);
+            }
+        } catch (...) { r = RR_ERR_ARG; }              // std::bad_alloc and friends must not cross a thread / the C ABI
         if (r != RR_OK) __atomic_store_n(&status[i], (int32_t)r, __ATOMIC_RELAXED);     // two writers at most (image, depth), both storing a failure code
     });
     int bad = 0;
     for (int i = 0; i < n; i++) bad += status[i] != RR_OK;
     return bad;
+}
+
+extern "C" int rr_host_png_read_batch(int n, const char *const *image_paths, const char *const *depth_paths, uint8_t *bgr, int Wi, int Hi,
+                                      float *depth, int Wd, int Hd, int n_threads, int32_t *status) {
+    return read_batch(n, image_paths, depth_paths, bgr, Wi, Hi, depth, 0, Wd, Hd, n_threads, status);
+}
+
+extern "C" int rr_host_png_read_batch_u16(int n, const char *const *image_paths, const char *const *depth_paths, uint8_t *bgr, int Wi, int Hi,
+                                          uint16_t *depth, int Wd, int Hd, int n_threads, int32_t *status) {
+    return read_batch(n, image_paths, depth_paths, bgr, Wi, Hi, depth, 1, Wd, Hd, n_threads, status);
+}
+
+// The reference's output files (generator.py:466-467): both 8-bit RGBA like plt.imsave writes them -- the rainy image from
+// the uint8 BGR frame, the rain mask from its colormap index (rr_frame_io.out_mask_idx8) through matplotlib's viridis
+// table.  Either list may be NULL.  Returns the number of files that failed.
+extern "C" int rr_host_png_write_batch_rgba(int n, const char *const *image_paths, const uint8_t *bgr, const char *const *mask_paths,
+                                            const uint8_t *mask_idx8, int W, int H, int level, int n_threads) {
+    if (n < 0 || W <= 0 || H <= 0 || (image_paths && !bgr) || (mask_paths && !mask_idx8) || level < 0 || level > 9) {
+        rr_set_error("rr_host_png_write_batch_rgba: bad arguments");
+        return RR_ERR_ARG;
+    }
+    std::atomic<int> bad(0);
+    parallel_for(2 * n, n_threads, [&](int j) {
+        const int i = j >> 1, kind = j & 1;
+        int r = RR_OK;
+        try {
+            if (kind == 0 && image_paths && image_paths[i]) r = write_rgba(image_paths[i], bgr + (size_t)i * 3 * W * H, nullptr, W, H, level);
+            if (kind == 1 && mask_paths && mask_paths[i]) r = write_rgba(mask_paths[i], nullptr, mask_idx8 + (size_t)i * W * H, W, H, level);
+        } catch (...) { r = RR_ERR_ARG; }
+        if (r != RR_OK) bad.fetch_add(1);
+    });
+    if (bad.load()) rr_set_error("rr_host_png_write_batch_rgba: some files could not be written");
+    return bad.load();
+}
+
+// Compact output files: 8-bit RGB image, 16-bit gray mask from the normalised uint16 mask (rr_frame_io.out_mask_u16).
+extern "C" int rr_host_png_write_batch_u16(int n, const char *const *image_paths, const uint8_t *bgr, const char *const *mask_paths,
+                                           const uint16_t *mask_u16, int W, int H, int level, int n_threads) {
+    if (n < 0 || W <= 0 || H <= 0 || (image_paths && !bgr) || (mask_paths && !mask_u16) || level < 0 || level > 9) {
+        rr_set_error("rr_host_png_write_batch_u16: bad arguments");
+        return RR_ERR_ARG;
+    }
+    std::atomic<int> bad(0);
+    parallel_for(2 * n, n_threads, [&](int j) {
+        const int i = j >> 1, kind = j & 1;
+        int r = RR_OK;
+        try {
+            if (kind == 0 && image_paths && image_paths[i]) r = write_bgr8(image_paths[i], bgr + (size_t)i * 3 * W * H, W, H, level);
+            if (kind == 1 && mask_paths && mask_paths[i]) r = write_gray16(mask_paths[i], mask_u16 + (size_t)i * W * H, W, H, level);
+        } catch (...) { r = RR_ERR_ARG; }
+        if (r != RR_OK) bad.fetch_add(1);
+    });
+    if (bad.load()) rr_set_error("rr_host_png_write_batch_u16: some files could not be written");
+    return bad.load();
+}
+
+// test hook of rr_host_deflate.h: data -> zlib stream (any inflate must reproduce data)
+extern "C" int rr_host_zlib_compress_fast(const uint8_t *data, size_t n, uint8_t *out, size_t cap, size_t *out_len) {
+    if ((n && !data) || !out || !out_len) { rr_set_error("rr_host_zlib_compress_fast: bad arguments"); return RR_ERR_ARG; }
+    try {
+        std::vector<unsigned char> z;
+        rr_deflate::zlib_compress_fast(data, n, z);
+        if (z.size() > cap) { rr_set_error("rr_host_zlib_compress_fast: output buffer too small"); return RR_ERR_CAPACITY; }
+        memcpy(out, z.data(), z.size());
+        *out_len = z.size();
+    } catch (...) { rr_set_error("rr_host_zlib_compress_fast: out of memory"); return RR_ERR_ARG; }
+    return RR_OK;
 }
 
 // Encodes n frames: 8-bit RGB files from bgr (n x H x W x 3, BGR order like the cv2.imwrite input) and 16-bit gray
@@ -312,8 +439,10 @@ extern "C" int rr_host_png_write_batch(int n, const char *const *image_paths, co
     parallel_for(2 * n, n_threads, [&](int j) {
         const int i = j >> 1, kind = j & 1;
         int r = RR_OK;
-        if (kind == 0 && image_paths && image_paths[i]) r = write_bgr8(image_paths[i], bgr + (size_t)i * 3 * W * H, W, H, level);
-        if (kind == 1 && mask_paths && mask_paths[i]) r = write_mask16(mask_paths[i], mask + (size_t)i * W * H, W, H, level);
+        try {
+            if (kind == 0 && image_paths && image_paths[i]) r = write_bgr8(image_paths[i], bgr + (size_t)i * 3 * W * H, W, H, level);
+            if (kind == 1 && mask_paths && mask_paths[i]) r = write_mask16(mask_paths[i], mask + (size_t)i * W * H, W, H, level);
+        } catch (...) { r = RR_ERR_ARG; }
         if (r != RR_OK) bad.fetch_add(1);
     });
     if (bad.load()) rr_set_error("rr_host_png_write_batch: some files could not be written");

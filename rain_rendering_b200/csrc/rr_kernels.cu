@@ -337,10 +337,13 @@ __device__ __forceinline__ void fog_taps_f32(const float *in, double acc[4]) {
 
 // extinction f_ext = float32 exp(-beta * depth / 1000), once per pixel (add_attenuation.py:43-48); k_fog's
 // overlapping tiles read it back (2.4 haloed reads per pixel) instead of re-evaluating the exponential
-__global__ void __launch_bounds__(256) k_fext(const float *depth, float *fext, float neg_beta32, size_t n) {
+template <bool U16>
+__global__ void __launch_bounds__(256) k_fext(const void *depth, float *fext, float neg_beta32, size_t n) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float d = __fdiv_rn(depth[i], 1000.f);                                  // add_attenuation.py:48 (float32)
+    // U16: the PNG's 16-bit samples; depth = sample.astype(float32) / 256 (generator.py:365) is exact in float32
+    const float metres = U16 ? __fdiv_rn((float)((const uint16_t *)depth)[i], 256.f) : ((const float *)depth)[i];
+    float d = __fdiv_rn(metres, 1000.f);                                    // add_attenuation.py:48 (float32)
     float xx = __fmul_rn(neg_beta32, d);
     fext[i] = (float)exp((double)xx);                                       // correctly rounded float32 exp ("canonical")
 }
@@ -535,14 +538,9 @@ cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F
     size_t smem = FOG_BYTES_A + FOG_BYTES_B + FOG_TY * FOG_TX * 3;
     {
         size_t n = (size_t)F * W * H;
-        k_fext<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.depth, b.fext, fc.neg_beta32, n);
+        if (b.depth_u16) k_fext<true><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.depth, b.fext, fc.neg_beta32, n);
+        else k_fext<false><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.depth, b.fext, fc.neg_beta32, n);
         k_fog_acs<<<(F * 4 + 127) / 128, 128, 0, st>>>(b.bg_sum, b.acs, fc, (double)W * (double)H, F);
-    }
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_fog, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr = true;
     }
     dim3 grid((W + FOG_TX - 1) / FOG_TX, (H + FOG_TY - 1) / FOG_TY, F);
     k_fog<<<grid, FOG_THREADS, smem, st>>>(b, fc, W, H);
@@ -1016,6 +1014,8 @@ cudaError_t rr_launch_scan(const rr_frame_bufs &b, int n_streaks, cudaStream_t s
 #define RAS_TXN 128           // widest / tallest patch with cached computeResizeAreaTab spans
 #define RAS_MAXD 1024         // patch pixels with accumulators resident in shared memory
 #define RAS_RBMAX 128         // rows per band of the area-fast path (RAS_CAP / canvas width; canvases are at least 32 wide)
+#define RAS_SMEM_BYTES (sizeof(double) * (2 * RAS_CAP + RAS_MAXD + 256) + sizeof(rr_area_span) * 2 * RAS_TXN + \
+                        sizeof(int) * (2 * RAS_MAXW + 2 * RAS_RBMAX))
 
 // Bilinear weights of remapBilinear: w = (1 - fy/32 or fy/32) * (1 - fx/32 or fx/32) in float32.  With 5-bit fractions
 // both factors and their product are exact, so w == p / 1024 with the integer p = {32 - fy, fy} * {32 - fx, fx}, and
@@ -1214,14 +1214,7 @@ __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs 
 cudaError_t rr_launch_raster(const rr_frame_bufs &b, const rr_static_tabs &t, const rr_cam_dev &cam, int n_streaks, int n_sm,
                              cudaStream_t st) {
     if (n_streaks == 0) return cudaSuccess;
-    const size_t smem = sizeof(double) * (2 * RAS_CAP + RAS_MAXD + 256) + sizeof(rr_area_span) * 2 * RAS_TXN +
-                        sizeof(int) * (2 * RAS_MAXW + 2 * RAS_RBMAX);
-    static bool attr = false;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        attr = true;
-    }
+    const size_t smem = RAS_SMEM_BYTES;
     int grid = n_sm * RAS_MINB;
     if (grid > n_streaks) grid = n_streaks;
     k_raster<<<grid, RAS_THREADS, smem, st>>>(b, t, cam, n_streaks);
@@ -1421,30 +1414,51 @@ __global__ void __launch_bounds__(COMP_THREADS, RR_COMP_MINB) k_composite(rr_fra
         }
         if (base + COMP_ROUND < s1) __syncthreads();         // the lists are rewritten by the next round
     }
-    double part = 0;
+    double part = 0, mlo = 1e300, mhi = -1e300;
 #pragma unroll
     for (int k = 0; k < RR_COMP_PY; k++) {
         const bool inside = x < W && y0 + k < H;
         if (inside) {
             const size_t pix = (size_t)(y0 + k) * W + x;
             if (touched[k]) { rb[pix] = vb[k]; rg[pix] = vg[k]; rr[pix] = vr[k]; }       // untouched pixels keep the fogged value
-            if (b.out_mask) b.out_mask[(size_t)f * npix + pix] = (float)mask[k];
+            b.maskd[(size_t)f * npix + pix] = mask[k];
+            mlo = mask[k] < mlo ? mask[k] : mlo; mhi = mask[k] > mhi ? mask[k] : mhi;
             part += (vb[k] + vg[k]) + vr[k];
         }
     }
     part = warp_sum(part);
-    if (lane == 0) b.tile_sum[(size_t)f * n_partials + (size_t)strip * tiles_x + blockIdx.x] = part;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double a = __shfl_xor_sync(0xffffffffu, mlo, o), c = __shfl_xor_sync(0xffffffffu, mhi, o);
+        mlo = a < mlo ? a : mlo; mhi = c > mhi ? c : mhi;
+    }
+    if (lane == 0) {
+        const size_t slot = (size_t)f * n_partials + (size_t)strip * tiles_x + blockIdx.x;
+        b.tile_sum[slot] = part; b.tile_min[slot] = mlo; b.tile_max[slot] = mhi;
+    }
 }
 
 __global__ void k_frame_mean(rr_frame_bufs b, int n_tiles, int stride, double npix3) {
     int f = blockIdx.x;
-    __shared__ double sh[256];
-    double s = 0;
-    for (int i = threadIdx.x; i < n_tiles; i += 256) s += b.tile_sum[(size_t)f * stride + i];
-    sh[threadIdx.x] = s;
+    __shared__ double sh[256], shlo[256], shhi[256];
+    double s = 0, lo = 1e300, hi = -1e300;
+    for (int i = threadIdx.x; i < n_tiles; i += 256) {
+        s += b.tile_sum[(size_t)f * stride + i];
+        const double a = b.tile_min[(size_t)f * stride + i], c = b.tile_max[(size_t)f * stride + i];
+        lo = a < lo ? a : lo; hi = c > hi ? c : hi;                 // strips below the image hold the neutral elements
+    }
+    sh[threadIdx.x] = s; shlo[threadIdx.x] = lo; shhi[threadIdx.x] = hi;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) { if (threadIdx.x < o) sh[threadIdx.x] += sh[threadIdx.x + o]; __syncthreads(); }
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) {
+            sh[threadIdx.x] += sh[threadIdx.x + o];
+            shlo[threadIdx.x] = shlo[threadIdx.x + o] < shlo[threadIdx.x] ? shlo[threadIdx.x + o] : shlo[threadIdx.x];
+            shhi[threadIdx.x] = shhi[threadIdx.x + o] > shhi[threadIdx.x] ? shhi[threadIdx.x + o] : shhi[threadIdx.x];
+        }
+        __syncthreads();
+    }
     if (threadIdx.x == 0) {
+        b.mask_range[2 * f] = shlo[0]; b.mask_range[2 * f + 1] = shhi[0];          // np.min / np.max of rainy_mask (exact, order free)
         double mean_rainy = sh[0] / npix3;                                          // generator.py:461
         double mean_bg = b.bgf ? ((b.bg_sum[f * 4] + b.bg_sum[f * 4 + 1]) + b.bg_sum[f * 4 + 2]) / npix3
                                : ((double)(b.chan_sum[f * 4] + b.chan_sum[f * 4 + 1] + b.chan_sum[f * 4 + 2]) / 255.0) / npix3;   // :462
@@ -1479,6 +1493,17 @@ __global__ void k_epilogue(rr_frame_bufs b, int npix, int F) {
             b.out_u8[i * 3 + c] = (uint8_t)(cl * 255);                              // plt.imsave float -> uint8
         }
     }
+    // the rain mask in the forms a caller saves: float32, or what plt.imsave(path, rainy_mask) (generator.py:467) makes of
+    // the float64 array -- Normalize: (m - min) / (max - min), zeros when flat; Colormap.__call__: int(t * 256), 256 -> 255
+    const double m = b.maskd[i];
+    if (b.out_mask) b.out_mask[i] = (float)m;
+    if (b.out_idx8 || b.out_u16) {
+        const double lo = b.mask_range[2 * f], hi = b.mask_range[2 * f + 1];
+        double t = 0.0;
+        if (hi > lo && m != lo) t = (m - lo) / (hi - lo);                           // m == lo: exactly 0 (and no zero-numerator division)
+        if (b.out_idx8) { const double q = t * 256.0; b.out_idx8[i] = q >= 256.0 ? (uint8_t)255 : (uint8_t)(int)q; }
+        if (b.out_u16) b.out_u16[i] = (uint16_t)(unsigned)(t * 65535.0 + 0.5);
+    }
 }
 
 cudaError_t rr_launch_epilogue(const rr_frame_bufs &b, int F, int W, int H, cudaStream_t st) {
@@ -1493,3 +1518,14 @@ cudaError_t rr_launch_env_prefix_only(const rr_frame_bufs &b, const rr_static_ta
     k_ambient<<<F, 32, 0, st>>>(b.rowtot, b.ambient, H);
     return cudaGetLastError();
 }
+
+
+// The opt-in to more than 48 KB of dynamic shared memory is a per-DEVICE function attribute: every context sets it for
+// its own device in rr_create (a process-wide "done once" flag would leave the second GPU of a process without it).
+cudaError_t rr_prepare_device() {
+    cudaError_t e = cudaFuncSetAttribute(k_fog, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(FOG_BYTES_A + FOG_BYTES_B + FOG_TY * FOG_TX * 3));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RAS_SMEM_BYTES);
+}
+

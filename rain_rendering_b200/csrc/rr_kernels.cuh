@@ -10,7 +10,8 @@ struct rr_frame_bufs {
     const double *bgf;         // [F][3][H][W] reduced float64 image when render_scale == 2, else NULL
     double *bg_sum;            // [F][4] per-channel sum of the (reduced) image in [0,1]
     double *acs;               // [F][4] beta_hg * mean irradiance per channel (k_fog_acs)
-    const float *depth;        // [F][H][W]
+    const void *depth;         // [F][H][W] float32 metres, or uint16 PNG samples (metres * 256) when depth_u16
+    int depth_u16;
     const rr_streak_rec *streaks;
     const int32_t *offsets;    // [F+1] device copy
     // per-frame intermediates
@@ -32,11 +33,16 @@ struct rr_frame_bufs {
     long long arena_cap;       // elements
     int *err_flag;             // device error flag (arena overflow)
     double *tile_sum;          // [F][rr_n_partials] partial sums of the composited image, one per compositor strip
+    double *tile_min, *tile_max;   // [F][rr_n_partials] extrema of the rain mask per compositor strip
     double *frame_mean;        // [F] mean(rainy_bg) - mean(bg)
+    double *maskd;             // [F][H][W] float64 rain mask (generator.py:393, bad_weather.py:450)
+    double *mask_range;        // [F][2] (min, max) of the float64 rain mask: what plt.imsave normalises with (generator.py:467)
     // outputs (device)
     float *out_bgr;            // [F][H][W][3]
     float *out_mask;           // [F][H][W]
     uint8_t *out_u8;           // [F][H][W][3]
+    uint8_t *out_idx8;         // [F][H][W] colormap index of plt.imsave(mask): min(int((m - lo) / (hi - lo) * 256), 255)
+    uint16_t *out_u16;         // [F][H][W] the mask min/max-normalised to 16 bits: int((m - lo) / (hi - lo) * 65535 + 0.5)
 };
 
 struct rr_static_tabs {
@@ -71,6 +77,7 @@ static inline size_t rr_n_partials(int W, int H) {
 }
 
 cudaError_t rr_upload_constants();
+cudaError_t rr_prepare_device();       // per-device function attributes (dynamic shared memory opt-in)
 // init-time tables
 cudaError_t rr_launch_env_tables(int W, int H, int focal_px, int cyl_w, int min_x, int W_env, int32_t *env_src,
                                  uint8_t *env_written, int32_t *cyl_first /* [H][cyl_w] scratch */, cudaStream_t st);

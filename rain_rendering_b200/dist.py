@@ -32,6 +32,58 @@ def init_process_group(backend: str = "nccl"):
     return rank, world, local
 
 
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.update(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa(local_rank: int):
+    """Pin the calling thread (and the threads it creates afterwards) to the CPUs of the NUMA node the GPU hangs off,
+    BEFORE page-locked staging buffers are allocated: pages are placed on the node of the thread that first touches
+    them, and a staging buffer on the other socket makes every host<->device copy cross the inter-socket link.
+    The reference's launcher leaves placement to the OS (main_threaded.py:176); with one process per GPU it decides
+    how far end-to-end throughput scales past one GPU.  Returns a dict describing what was done (for the bench line);
+    never raises -- on hosts without NUMA information nothing changes.  RAIN_B200_NUMA_BIND=0 disables it."""
+    info = {"bound": False}
+    if os.environ.get("RAIN_B200_NUMA_BIND", "1") == "0" or not hasattr(os, "sched_setaffinity"):
+        return info
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = local_rank
+        if vis:
+            parts = vis.split(",")
+            if local_rank < len(parts) and parts[local_rank].strip().isdigit():
+                idx = int(parts[local_rank])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        if isinstance(bus, bytes):
+            bus = bus.decode()
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:          # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        base = "/sys/bus/pci/devices/" + bus
+        node = int(open(base + "/numa_node").read())
+        cpus = _parse_cpulist(open(base + "/local_cpulist").read())
+        info.update(node=node, gpu_bus=bus)
+        allowed = os.sched_getaffinity(0)
+        want = cpus & allowed
+        if node < 0 or not want or want == allowed:
+            info["reason"] = "no NUMA locality to exploit (node %d, %d local of %d allowed CPUs)" % (node, len(want), len(allowed))
+            return info
+        os.sched_setaffinity(0, want)
+        info.update(bound=True, cpus=len(want), allowed=len(allowed))
+    except Exception as e:          # no NVML / no sysfs: leave placement to the OS
+        info["reason"] = "%s: %s" % (type(e).__name__, e)
+    return info
+
+
 def shard_range(n_items: int, rank: int, world: int):
     """Contiguous, balanced [start, stop) of ``n_items`` frames for ``rank`` (the reference's
     threaded launcher also hands out contiguous frame ranges, main_threaded.py:114-137)."""

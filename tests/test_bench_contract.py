@@ -12,7 +12,9 @@ def test_algorithmic_bytes_per_frame_is_the_survey_formula():
     sys.path.insert(0, ROOT)
     import bench
     W, H, N = 1242, 375, 403
-    assert bench.algorithmic_bytes_per_frame(W, H, N) == 3 * W * H + 4 * W * H + (12 + 4 + 3) * W * H + 128 * N
+    # SURVEY 8(d) with the round-2 boundary formats: the depth enters as the PNG's uint16 samples (2 bytes, was float32)
+    # and the uint8 colormap index of the saved mask is one more output
+    assert bench.algorithmic_bytes_per_frame(W, H, N) == 3 * W * H + 2 * W * H + (12 + 4 + 3 + 1) * W * H + 128 * N
     assert bench.REC_BYTES == 128 and bench.BATCH == 64 and bench.WORKLOAD == "C2"
 
 

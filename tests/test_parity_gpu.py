@@ -20,13 +20,22 @@ pytestmark = pytest.mark.gpu
 ULP1 = 2.0 ** -23
 
 
+def _check_image_ulp(bgr, ref64):
+    """north_star: the float32 image within 1 ULP of float32(reference).  True float32 ULP distance wherever the value is
+    at least 2^-6 in magnitude; below that (the mean shift moves values through zero, where an ULP shrinks without
+    bound while the float64 chain's own absolute error does not) the bound is 1 ULP *at 2^-6*, 2^-29."""
+    ref32 = ref64.astype(np.float32)
+    big = np.abs(ref32) >= 2.0 ** -6
+    assert ulp_diff_f32(bgr[big], ref32[big]).max() <= 1
+    if (~big).any():
+        assert np.abs(bgr[~big].astype(np.float64) - ref32[~big].astype(np.float64)).max() <= 2.0 ** -29
+
+
 def _check_frame(out, i, o):
     mask, bgr, u8 = out["mask"][i], out["bgr"][i], out["u8"][i]
     assert np.array_equal(mask > 0, o.rain_mask > 0), "rain-mask support differs"
     assert ulp_diff_f32(mask, o.rain_mask.astype(np.float32)).max() <= 1
-    ref32 = o.out_bgr.astype(np.float32)
-    tol = np.maximum(np.abs(ref32), 1.0).astype(np.float64) * ULP1
-    assert (np.abs(bgr.astype(np.float64) - ref32.astype(np.float64)) <= tol).all()
+    _check_image_ulp(bgr, o.out_bgr)
     assert np.abs(u8.astype(int) - o.out_u8.astype(int)).max() <= 1
 
 
@@ -232,6 +241,37 @@ def test_pipelined_submissions_equal_synchronous_renders():
     ctx.close()
 
 
+def test_compact_boundary_formats_uint16_depth_and_saved_mask_forms():
+    """rr_frame_io: the depth PNG's uint16 samples in (divided by 256 on the device, generator.py:365) and the rain
+    mask out in the forms that are saved (generator.py:467): plt.imsave's colormap index, the 16-bit normalised
+    mask and the (min, max) it was normalised with -- 9 instead of 14 staged bytes per pixel."""
+    from oracle import rain_oracle as ro
+    sc = Scenario(384, 256, 3, 1400, fallrate=25)
+    d16 = np.clip(np.rint(sc.depth * 256.0), 0, 65535).astype(np.uint16)
+    sc.depth = (d16.astype(np.float32) / 256.).astype(np.float32)        # what the reference decodes from that PNG
+    ctx = sc.context()
+    recs, offs = sc.records()
+    ref = ctx.render_frames(sc.bgr, sc.depth, recs, offs, want=("bgr", "mask", "u8", "idx8", "u16", "range"))
+    got = ctx.render_frames(sc.bgr, d16, recs, offs, want=("u8", "idx8", "range"))       # only what a writer needs
+    assert got["bgr"] is None and got["mask"] is None
+    assert np.array_equal(got["u8"], ref["u8"]) and np.array_equal(got["idx8"], ref["idx8"]) and np.array_equal(got["range"], ref["range"])
+    for i in range(sc.n_frames):
+        o = sc.oracle_frame(i, "canonical")
+        _check_frame(ref, i, o)
+        idx, (lo, hi) = ro.imsave_mask_index(o.rain_mask)
+        assert ref["range"][i, 0] == lo == 0.0 and abs(ref["range"][i, 1] / hi - 1) < 1e-12
+        # the device mask equals the oracle's to ~1e-16 relative, so an index can only differ where t * 256 sits on an integer
+        d = np.abs(ref["idx8"][i].astype(int) - idx.astype(int))
+        assert d.max() <= 1 and (d != 0).mean() < 1e-4
+        assert np.array_equal(ref["idx8"][i] > 0, idx > 0) or (d != 0).sum() < 8
+        d16m = np.abs(ref["u16"][i].astype(int) - ro.mask_u16(o.rain_mask).astype(int))
+        assert d16m.max() <= 1 and (d16m != 0).mean() < 1e-3
+    # a frame without rain: flat mask -> all zeros, range (0, 0)
+    none = ctx.render_frames(sc.bgr[:1], d16[:1], recs[:0], np.array([0, 0], np.int32), want=("idx8", "u16", "range"))
+    assert (none["idx8"] == 0).all() and (none["u16"] == 0).all() and (none["range"] == 0).all()
+    ctx.close()
+
+
 @pytest.mark.parametrize("name", ["small_256x192", "c1_640x480"])
 def test_against_reference_goldens(name):
     sc, g = golden_scenario(name)
@@ -250,6 +290,26 @@ def test_against_reference_goldens(name):
     # the reference authors' own acceptance metric (scripts/check_difference.py:17-49)
     diff = np.abs(out["u8"].astype(int) - ref_u8)
     assert diff.mean() < 0.01
+    ctx.close()
+
+
+def test_against_reference_golden_c2_frame():
+    """BASELINE C2's frame (1242x375, 25 mm/h, 609 streaks) against what the live reference produced for it: the uint8
+    image it would save (rainy_u8, RGB) and -- through the float32 mask's SHA being pinned by the oracle on the CPU
+    (tests/test_oracle.py) -- the mask, compared here with the oracle's float64 mask of the same frame."""
+    sc, g = golden_scenario("c2_1242x375")
+    ctx = sc.context()
+    recs, offs = sc.records()
+    assert np.diff(offs).tolist() == g["n_streaks"].tolist() == [609]
+    d16 = np.ascontiguousarray(g["depth_u16"])
+    out = ctx.render_frames(sc.bgr, d16, recs, offs, want=("bgr", "mask", "u8", "idx8"))
+    ref_u8 = g["rainy_u8"][..., ::-1].astype(int)
+    diff = np.abs(out["u8"].astype(int) - ref_u8)
+    assert diff.max() <= 1 and (diff != 0).mean() < 1e-3
+    assert diff.mean() < 0.01                                   # scripts/check_difference.py:17-49
+    o = sc.oracle_frame(0, "native")
+    assert np.array_equal(out["mask"][0] > 0, o.rain_mask > 0)
+    assert ulp_diff_f32(out["mask"][0], o.rain_mask.astype(np.float32)).max() <= 1
     ctx.close()
 
 
