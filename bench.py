@@ -393,6 +393,14 @@ def run_gpu(args):
                              "traffic": traffic, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
                              "algorithmic_bytes_per_frame": balg, "whole_step_frac": (balg * batch / (ms_dev / args.steps / 1000.0) / 1e9) / peak},
                 "stage_ms": kern}
+        if world == 1 and not args.skip_e2e and not args.no_dropin:
+            # the user-facing path: Generator(args).run() over PNG files (decode + render + encode), SURVEY 8(f) rank 2
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import dropin_e2e
+                line["dropin_png_e2e"] = dropin_e2e.measure(n_frames=args.dropin_frames, batch=batch)
+            except Exception as e:                      # the headline numbers above stand on their own
+                line["dropin_png_e2e"] = {"error": "%s: %s" % (type(e).__name__, e)}
         if world == 1 and not args.no_cpu_baseline:
             workers = max(1, min(host_cores(), 16))
             times, streaks = cpu_steps(1, 1, workers)
@@ -414,6 +422,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-dropin", action="store_true", help="skip the drop-in Generator.run() PNG pass (dropin_png_e2e)")
+    ap.add_argument("--dropin-frames", type=int, default=1024)
     ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: only the device-resident arm (the JSON line is then incomplete)")
     args = ap.parse_args()
     if args.impl == "reference":

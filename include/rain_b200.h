@@ -157,7 +157,19 @@ typedef struct rr_frame_io {
     uint8_t *out_mask_idx8;          /* n*H*W   uint8                                             */
     uint16_t *out_mask_u16;          /* n*H*W   uint16                                            */
     double *out_mask_range;          /* n*2     float64 (min, max)                                */
+    /* The saved files' image data finished on the device (host requests only; HOST buffers): complete zlib streams of the
+     * Sub-filtered 8-bit RGBA scanlines -- what goes between "IDAT" and its CRC -- of the rainy image (from the uint8
+     * output, alpha 255) and of the rain mask (its colormap index through matplotlib's viridis), as plt.imsave stores them
+     * (generator.py:466-467).  Stream i starts at out_png_* + i * png_stride and is out_png_*_sizes[i] bytes long;
+     * rr_host_png_write_streams frames and writes them.  png_stride >= rr_png_stream_bound(W, H). */
+    uint8_t *out_png_image;
+    uint8_t *out_png_mask;
+    uint32_t *out_png_image_sizes;   /* n */
+    uint32_t *out_png_mask_sizes;    /* n */
+    size_t png_stride;
 } rr_frame_io;
+/* Upper bound of one GPU-made PNG stream of a W x H RGBA image (the device reserves the same). */
+size_t rr_png_stream_bound(int W, int H);
 int rr_render_frames_io(rr_context *ctx, int n_frames, const rr_frame_io *io);
 int rr_submit_frames_io(rr_context *ctx, int n_frames, const rr_frame_io *io);     /* + rr_wait_frames */
 /* DEVICE pointers in *io (streak_offsets stays on the host), no copies; asynchronous unless sync != 0. */
@@ -214,6 +226,18 @@ typedef struct rr_sim_streak {  /* one <r .../> of the simulator XML, 120 bytes 
  * simulated for absolute frame index first_frame + f: the result depends only on (seed, index). */
 int rr_simulate_particles(rr_context *ctx, const rr_sim_params *p, int64_t first_frame, int n_frames,
                           int max_per_frame, rr_sim_streak *out, int32_t *counts, double *expected_per_frame);
+
+/* The same simulation kept on the device, all the way to the renderer's input: one launch simulates n_frames frames, turns
+ * the imaged drops into rr_streak_rec with the loader's arithmetic (common/bad_weather.py:200-238: positions / render_scale,
+ * y flip with the render height, rounding, ratio, length, type), applies the in-frame filter (common/generator.py:413-420) and
+ * makes each frame's NumPy RNG draws (np.random.seed(first_frame + f); generator.py:318,136; bad_weather.py:252-264) on the
+ * device.  *d_records receives a DEVICE pointer to the concatenated records (library-owned, valid until the next call on
+ * this context); only the n_frames + 1 offsets come back to the host (h_offsets) -- both go straight into
+ * rr_render_frames_device_io.  Records are bit-identical to rr_simulate_particles + the host loader + rr_host_assemble_batch.
+ * noise_std * noise_scale must be 0 (the wind write-back couples frames, generator.py:152-161). */
+int rr_simulate_records_device(rr_context *ctx, const rr_sim_params *p, int64_t first_frame, int n_frames, int render_scale,
+                               const double *db_ratios, int n_ratios, double noise_std, double noise_scale,
+                               rr_streak_rec **d_records, int32_t *h_offsets, double *expected_per_frame);
 
 int rr_debug_read(rr_context *ctx, int what, int frame, void *dst, size_t bytes);
 int rr_timings(rr_context *ctx, float *ms_per_stage /* RR_T_COUNT */);
@@ -291,6 +315,12 @@ int rr_host_png_write_batch_rgba(int n, const char *const *image_paths, const ui
 /* Compact files: 8-bit RGB image and 16-bit gray mask from rr_frame_io.out_mask_u16. */
 int rr_host_png_write_batch_u16(int n, const char *const *image_paths, const uint8_t *bgr, const char *const *mask_paths,
                                 const uint16_t *mask_u16, int W, int H, int level, int n_threads);
+/* Frames n finished zlib streams (rr_frame_io.out_png_*) as 8-bit RGBA PNG files: signature, IHDR, one IDAT with its
+ * CRC-32, IEND.  Returns the number of files that could not be written. */
+int rr_host_png_write_streams(int n, const char *const *paths, const uint8_t *streams, size_t stride, const uint32_t *sizes,
+                              int W, int H, int n_threads);
+/* Test hook of the decoder the PNG reader uses (csrc/rr_host_inflate.h): zlib stream -> exactly out_len bytes. */
+int rr_host_zlib_decompress_fast(const uint8_t *z, size_t zlen, uint8_t *out, size_t out_len);
 /* Test hook of the deflate encoder: data -> zlib stream. */
 int rr_host_zlib_compress_fast(const uint8_t *data, size_t n, uint8_t *out, size_t cap, size_t *out_len);
 /* The simulator's force model evaluated on the host (CPU test-suite): terminal velocity solving

@@ -29,7 +29,9 @@ class FrameIO(C.Structure):
     """rr_frame_io"""
     _fields_ = [("bgr", C.c_void_p), ("depth", C.c_void_p), ("depth_format", C.c_int32), ("reserved", C.c_int32),
                 ("streaks", C.c_void_p), ("streak_offsets", C.c_void_p), ("out_bgr", C.c_void_p), ("out_mask", C.c_void_p),
-                ("out_bgr_u8", C.c_void_p), ("out_mask_idx8", C.c_void_p), ("out_mask_u16", C.c_void_p), ("out_mask_range", C.c_void_p)]
+                ("out_bgr_u8", C.c_void_p), ("out_mask_idx8", C.c_void_p), ("out_mask_u16", C.c_void_p), ("out_mask_range", C.c_void_p),
+                ("out_png_image", C.c_void_p), ("out_png_mask", C.c_void_p), ("out_png_image_sizes", C.c_void_p),
+                ("out_png_mask_sizes", C.c_void_p), ("png_stride", C.c_size_t)]
 
 
 DEPTH_F32_M, DEPTH_U16_256 = 0, 1
@@ -64,6 +66,13 @@ DBG = dict(fog=0, env=1, omega=2, plans=3, rainy=4, env_src=5, arena=6, fext=7)
 _lib = None
 
 
+def shutil_which_nvcc():
+    try:
+        return _build.find_nvcc()
+    except Exception:
+        return None
+
+
 def load() -> C.CDLL:
     """Load (building first if needed) the CUDA library.  Raises if it cannot be had."""
     global _lib
@@ -72,9 +81,13 @@ def load() -> C.CDLL:
     if not os.environ.get("RR_LIB_OVERRIDE") and (not os.path.exists(LIB_PATH) or _build.stale()):
         try:
             _build.build()
-        except Exception as e:  # no silent fallback
+        except Exception as e:  # no silent fallback: neither to a CPU path nor to a library older than its sources
             if not os.path.exists(LIB_PATH):
                 raise RuntimeError("librain_b200.so is missing and could not be built (%s); there is no CPU fallback" % e)
+            if shutil_which_nvcc():
+                raise RuntimeError("librain_b200.so is older than its sources and rebuilding it failed: %s" % e)
+            import warnings
+            warnings.warn("librain_b200.so is older than its sources and there is no nvcc to rebuild it; loading the existing library")
     lib = C.CDLL(LIB_PATH)
     vp, i32p, u8p, f32p, f64p = C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p
     lib.rr_version.restype = C.c_int
@@ -100,6 +113,8 @@ def load() -> C.CDLL:
         "rr_debug_read": [vp, C.c_int, C.c_int, vp, C.c_size_t],
         "rr_solid_angles": [vp, C.c_int, C.c_int, f64p],
         "rr_simulate_particles": [vp, C.POINTER(SimParams), C.c_int64, C.c_int, C.c_int, vp, i32p, C.POINTER(C.c_double)],
+        "rr_simulate_records_device": [vp, C.POINTER(SimParams), C.c_int64, C.c_int, C.c_int, f64p, C.c_int, C.c_double, C.c_double,
+                                       C.POINTER(vp), i32p, C.POINTER(C.c_double)],
         "rr_timings": [vp, f32p],
         "rr_kernel_launches": [vp, C.POINTER(C.c_longlong)],
         "rr_stream": [vp, C.POINTER(vp)],
@@ -119,12 +134,16 @@ def load() -> C.CDLL:
         "rr_host_png_read_batch_u16": [C.c_int, vp, vp, u8p, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, i32p],
         "rr_host_png_write_batch_rgba": [C.c_int, vp, u8p, vp, u8p, C.c_int, C.c_int, C.c_int, C.c_int],
         "rr_host_png_write_batch_u16": [C.c_int, vp, u8p, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int],
+        "rr_host_png_write_streams": [C.c_int, vp, u8p, C.c_size_t, vp, C.c_int, C.c_int, C.c_int],
+        "rr_host_zlib_decompress_fast": [u8p, C.c_size_t, u8p, C.c_size_t],
         "rr_host_zlib_compress_fast": [u8p, C.c_size_t, u8p, C.c_size_t, C.POINTER(C.c_size_t)],
     }
     for name, args in protos.items():
         fn = getattr(lib, name)
         fn.argtypes = args
         fn.restype = C.c_int
+    lib.rr_png_stream_bound.argtypes = [C.c_int, C.c_int]
+    lib.rr_png_stream_bound.restype = C.c_size_t
     lib.rr_host_free_particles.argtypes = [vp]
     lib.rr_host_free_particles.restype = None
     lib.rr_host_norm2.argtypes = [C.c_int, f64p, f64p, f64p]

@@ -130,7 +130,11 @@ class RainContext:
         self.H_env, self.W_env = he.value, we.value
 
     # -- hot path ----------------------------------------------------------------------------
-    def _frame_io(self, bgr, depth, streaks, offsets, out_bgr, out_mask, out_u8, out_idx8, out_u16, out_range):
+    def png_stream_bound(self):
+        """bytes to reserve per GPU-made PNG stream of this camera's frames (rr_png_stream_bound)"""
+        return int(self.lib.rr_png_stream_bound(self.W, self.H))
+
+    def _frame_io(self, bgr, depth, streaks, offsets, out_bgr, out_mask, out_u8, out_idx8, out_u16, out_range, png=None):
         """rr_frame_io of a batch (host arrays).  depth: float32 metres or the uint16 samples of the depth PNG."""
         n = bgr.shape[0]
         rs = self.render_scale
@@ -144,11 +148,26 @@ class RainContext:
             assert a is None or (a.shape == shape and a.dtype == dt), "output array %s %s, expected %s %s" % (a.shape, a.dtype, shape, dt)
         p = lambda a: None if a is None else _lib.ptr(a).value
         io = _lib.FrameIO(p(bgr), p(depth), _lib.DEPTH_U16_256 if depth.dtype == np.uint16 else _lib.DEPTH_F32_M, 0, p(streaks), p(offsets),
-                          p(out_bgr), p(out_mask), p(out_u8), p(out_idx8), p(out_u16), p(out_range))
+                          p(out_bgr), p(out_mask), p(out_u8), p(out_idx8), p(out_u16), p(out_range), None, None, None, None, 0)
+        if png is not None:
+            # png: dict(image=(n, stride) uint8 or None, mask=..., image_sizes=(n,) uint32, mask_sizes=...): the saved files' image
+            # data as finished zlib streams (rr_frame_io.out_png_*), page-locked host arrays
+            stride = None
+            for k in ("image", "mask"):
+                a = png.get(k)
+                if a is None:
+                    continue
+                sz = png[k + "_sizes"]
+                assert a.dtype == np.uint8 and a.ndim == 2 and a.shape[0] >= n and a.flags["C_CONTIGUOUS"] and sz.dtype == np.uint32 and len(sz) >= n
+                assert stride in (None, a.shape[1]), "image and mask streams share one stride"
+                stride = a.shape[1]
+                setattr(io, "out_png_" + k, p(a))
+                setattr(io, "out_png_%s_sizes" % k, p(sz))
+            io.png_stride = stride or 0
         return n, io
 
     def render_frames(self, bgr, depth, streaks, offsets, out_bgr=None, out_mask=None, out_u8=None,
-                      want=("bgr", "mask", "u8"), out_idx8=None, out_u16=None, out_range=None):
+                      want=("bgr", "mask", "u8"), out_idx8=None, out_u16=None, out_range=None, png=None):
         """bgr (n,H,W,3) uint8; depth (n,H,W) float32 metres or uint16 PNG samples; streaks STREAK_DTYPE (concatenated);
         offsets (n+1,) int32.  ``want`` names the outputs to allocate when no array is passed: bgr (float32), mask
         (float32), u8, idx8 (plt.imsave's colormap index of the mask), u16 (16-bit normalised mask), range ((min, max) of
@@ -167,15 +186,15 @@ class RainContext:
             out_u16 = np.empty((n, self.H, self.W), np.uint16)
         if out_range is None and "range" in want:
             out_range = np.empty((n, 2), np.float64)
-        n, io = self._frame_io(bgr, depth, streaks, offsets, out_bgr, out_mask, out_u8, out_idx8, out_u16, out_range)
+        n, io = self._frame_io(bgr, depth, streaks, offsets, out_bgr, out_mask, out_u8, out_idx8, out_u16, out_range, png)
         _lib.check(self.lib.rr_render_frames_io(self.h, n, C.byref(io)), "rr_render_frames_io")
         return dict(bgr=out_bgr, mask=out_mask, u8=out_u8, idx8=out_idx8, u16=out_u16, range=out_range)
 
     def submit_frames(self, bgr, depth, streaks, offsets, out_bgr=None, out_mask=None, out_u8=None, out_idx8=None, out_u16=None,
-                      out_range=None):
+                      out_range=None, png=None):
         """Asynchronous rr_submit_frames_io: all arrays (page-locked for the copies to overlap) must stay
         alive and untouched until the matching ``wait_frames``; at most two batches in flight."""
-        n, io = self._frame_io(bgr, depth, streaks, offsets, out_bgr, out_mask, out_u8, out_idx8, out_u16, out_range)
+        n, io = self._frame_io(bgr, depth, streaks, offsets, out_bgr, out_mask, out_u8, out_idx8, out_u16, out_range, png)
         _lib.check(self.lib.rr_submit_frames_io(self.h, n, C.byref(io)), "rr_submit_frames_io")
 
     def wait_frames(self):
@@ -232,6 +251,34 @@ class RainContext:
             r = out[f, :counts[f]]
             frames.append(r[np.argsort(r["pid"], kind="stable")].copy())
         return frames, exp.value
+
+    def _sim_params(self, W, H, fallrate, focal_mm, pix_size_um, exposure_ms, sim_hz, cam_speed_kmh, z_near, z_far, d_min_mm, d_max_mm,
+                    min_width_px, seed):
+        return _lib.SimParams(int(W), int(H), focal_mm / 1000., pix_size_um * 1e-6, float(exposure_ms), float(fallrate), float(sim_hz),
+                              float(cam_speed_kmh), float(z_near), float(z_far), float(d_min_mm), float(d_max_mm), float(min_width_px), int(seed))
+
+    def simulate_records_device(self, first_frame, n_frames, W, H, fallrate, db_ratios, render_scale=1, focal_mm=6.0, pix_size_um=4.65,
+                                exposure_ms=2.0, sim_hz=2000.0, cam_speed_kmh=0.0, z_near=0.25, z_far=15.0, d_min_mm=0.1, d_max_mm=10.0,
+                                min_width_px=1.0, seed=0):
+        """rr_simulate_records_device: frames first_frame .. of the on-the-fly simulation as finished streak records that never
+        leave the device (W, H: sensor size before render_scale).  -> (device pointer of the concatenated rr_streak_rec, int32
+        offsets (n_frames + 1, host), expected candidates per frame).  The pointer stays valid until the next call."""
+        p = self._sim_params(W, H, fallrate, focal_mm, pix_size_um, exposure_ms, sim_hz, cam_speed_kmh, z_near, z_far, d_min_mm, d_max_mm,
+                             min_width_px, seed)
+        ratios = np.ascontiguousarray(db_ratios, np.float64)
+        ptr, exp = C.c_void_p(), C.c_double(0)
+        offs = np.zeros(n_frames + 1, np.int32)
+        _lib.check(self.lib.rr_simulate_records_device(self.h, C.byref(p), int(first_frame), int(n_frames), int(render_scale), _lib.ptr(ratios),
+                                                       len(ratios), 0.0, 0.0, C.byref(ptr), _lib.ptr(offs), C.byref(exp)), "rr_simulate_records_device")
+        return ptr.value, offs, exp.value
+
+    def render_frames_device(self, d_bgr, d_depth, depth_u16, d_records, offsets, d_out_bgr=None, d_out_mask=None, d_out_u8=None,
+                             d_out_idx8=None, d_out_u16=None, d_out_range=None, sync=True):
+        """rr_render_frames_device_io: every pointer is a DEVICE address (int), offsets a host int32 array."""
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        io = _lib.FrameIO(d_bgr, d_depth, _lib.DEPTH_U16_256 if depth_u16 else _lib.DEPTH_F32_M, 0, d_records, _lib.ptr(offsets).value,
+                          d_out_bgr, d_out_mask, d_out_u8, d_out_idx8, d_out_u16, d_out_range, None, None, None, None, 0)
+        _lib.check(self.lib.rr_render_frames_device_io(self.h, len(offsets) - 1, C.byref(io), 1 if sync else 0), "rr_render_frames_device_io")
 
     def timings(self):
         ms = np.zeros(len(_lib.T_NAMES), np.float32)

@@ -6,6 +6,7 @@
 #include <string.h>
 #include <vector>
 #include "rr_kernels.cuh"
+#include "rr_png_gpu.cuh"
 
 static thread_local char g_err[1024] = "";
 static void set_err(const char *fmt, ...) {
@@ -28,8 +29,21 @@ static void set_err(const char *fmt, ...) {
 struct rr_context {
     int device = 0, n_sm = 148;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[RR_T_COUNT + 2];
+    cudaEvent_t ev[RR_T_COUNT + 2];        // start of every timing slot
+    cudaEvent_t ev_end[RR_T_COUNT + 2];    // end of the slots that run beside others (the streak chain on its own stream)
+    bool slot_has_end[RR_T_COUNT + 2], slot_side[RR_T_COUNT + 2];
     float last_ms[RR_T_COUNT];
+    // GPU-side PNG image data (rr_frame_io.out_png_*): scratch shared by the two passes, streams per async slot and kind
+    bool png_ready = false;
+    rr_png_bufs png;                       // scratch + geometry; .stream / .sizes are filled per use
+    uint8_t *d_png_stream[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};      // [slot][0 image, 1 mask]
+    unsigned *d_png_sizes[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    cudaStream_t s_png = nullptr;          // fetches the finished streams (exact sizes) after a batch completes
+    rr_frame_io call_io[2];
+    void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};       // grow-only device buffers of the on-the-fly simulator
+    size_t scratch_bytes[4] = {0, 0, 0, 0};                // the requests in flight (host pointers of the PNG outputs)
+    bool serial = false;                   // RR_SERIAL=1: the streak chain runs on the main stream (profiling: one kernel at a time)
+    cudaEvent_t ev_plan = nullptr;
     long long launches = 0;
     // streak DB
     uint8_t *d_db = nullptr;
@@ -41,6 +55,10 @@ struct rr_context {
     rr_camera cam;
     rr_cam_dev camd;
     rr_fog_consts fogc;
+    // k_fog's tile load: TMA boxes of the reflect-padded extinction planes (RR_FOG_TMA=0 selects the register-staged form)
+    bool fog_tma = true;
+    CUtensorMap fog_map;
+    float *d_fext_lut = nullptr;
     int max_batch = 0, H_env = 0, W_env = 0, cyl_w = 0;
     int32_t *d_env_src = nullptr;
     uint8_t *d_env_written = nullptr, *d_env_tile_hole = nullptr;
@@ -99,13 +117,63 @@ static void free_camera(rr_context *c) {
     memset(&c->fb, 0, sizeof(c->fb));
     c->d_env_src = nullptr; c->d_env_written = nullptr; c->d_env_tile_hole = nullptr; c->d_omega = c->d_omega_pref = c->d_omega_total = nullptr;
     c->d_bgr = nullptr; c->d_bgf = nullptr; c->d_depth = nullptr; c->d_streaks = nullptr; c->d_offsets = nullptr;
-    c->d_sub_offsets = nullptr; c->d_err2 = nullptr;
+    c->d_sub_offsets = nullptr; c->d_err2 = nullptr; c->d_fext_lut = nullptr;
+    c->png_ready = false;
+    memset(&c->png, 0, sizeof(c->png));
+    memset(c->d_png_stream, 0, sizeof(c->d_png_stream)); memset(c->d_png_sizes, 0, sizeof(c->d_png_sizes));
 }
 
 extern "C" {
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point query: no link-time dependency on libcuda
+typedef CUresult (*rr_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                       const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                       CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static rr_encode_tiled_fn encode_tiled_fn() {
+    static rr_encode_tiled_fn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = (rr_encode_tiled_fn)p;
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+// 3-D float32 tensor map (x fastest) of `planes` planes of rows x pitch elements; one box = box_w x box_h x 1
+static int make_plane_map(CUtensorMap *map, void *base, int pitch, int rows, int planes, int box_w, int box_h) {
+    rr_encode_tiled_fn enc = encode_tiled_fn();
+    if (!enc) { set_err("cuTensorMapEncodeTiled is not available from this driver"); return RR_ERR_CUDA; }
+    const cuuint64_t dims[3] = {(cuuint64_t)pitch, (cuuint64_t)rows, (cuuint64_t)planes};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * sizeof(float), (cuuint64_t)pitch * rows * sizeof(float)};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)box_h, 1u}, estr[3] = {1u, 1u, 1u};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_err("cuTensorMapEncodeTiled failed (%d) for a %d x %d x %d float32 tensor", (int)r, pitch, rows, planes); return RR_ERR_CUDA; }
+    return RR_OK;
+}
+
+size_t rr_png_stream_bound(int W, int H) {
+    const size_t n = (size_t)H * ((size_t)4 * W + 1);
+    return ((n + n / 4 + 4096) + 3) & ~(size_t)3;
+}
+
 int rr_version(void) { return 200; }
 int rr_sim_device_of(rr_context *c) { return c ? c->device : 0; }
+void *rr_ctx_stream(rr_context *c) { return c ? (void *)c->stream : nullptr; }
+void *rr_ctx_scratch(rr_context *c, int which, size_t bytes) {
+    if (!c || which < 0 || which >= 4) return nullptr;
+    if (bytes > c->scratch_bytes[which]) {
+        cudaStreamSynchronize(c->stream);
+        if (c->scratch[which]) cudaFree(c->scratch[which]);
+        c->scratch[which] = nullptr; c->scratch_bytes[which] = 0;
+        const size_t want = bytes + bytes / 4 + 4096;
+        if (cudaMalloc(&c->scratch[which], want) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+        c->scratch_bytes[which] = want;
+    }
+    return c->scratch[which];
+}
 void rr_set_error(const char *msg) { set_err("%s", msg); }
 const char *rr_last_error(void) { return g_err; }
 
@@ -129,6 +197,9 @@ int rr_create(int device_id, rr_context **out) {
     CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->s_plan, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->s_png, cudaStreamNonBlocking));
+    memset(&c->png, 0, sizeof(c->png));
+    memset(c->call_io, 0, sizeof(c->call_io));
     CK(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (int i = 0; i < RR_MAX_SUB; i++) {
@@ -138,11 +209,14 @@ int rr_create(int device_id, rr_context **out) {
     }
     for (int i = 0; i < 2; i++) CK(cudaEventCreateWithFlags(&c->ev_call[i], cudaEventDisableTiming));
     CK(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
-    for (int i = 0; i < RR_T_COUNT + 2; i++) CK(cudaEventCreate(&c->ev[i]));
+    for (int i = 0; i < RR_T_COUNT + 2; i++) { CK(cudaEventCreate(&c->ev[i])); CK(cudaEventCreate(&c->ev_end[i])); c->slot_has_end[i] = c->slot_side[i] = false; }
+    CK(cudaEventCreateWithFlags(&c->ev_plan, cudaEventDisableTiming));
+    { const char *env = getenv("RR_SERIAL"); c->serial = env && atoi(env) != 0; }
     memset(c->last_ms, 0, sizeof(c->last_ms));
     memset(&c->fb, 0, sizeof(c->fb));
     CK(rr_upload_constants());
     CK(rr_prepare_device());
+    CK(rr_png_upload_constants());
     *out = c;
     return RR_OK;
 }
@@ -152,15 +226,18 @@ int rr_destroy(rr_context *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_camera(c);
+    for (int i = 0; i < 4; i++) if (c->scratch[i]) cudaFree(c->scratch[i]);
     if (c->d_db) cudaFree(c->d_db);
     if (c->d_tex_off) cudaFree(c->d_tex_off);
     if (c->d_tex_h) cudaFree(c->d_tex_h);
-    for (int i = 0; i < RR_T_COUNT + 2; i++) cudaEventDestroy(c->ev[i]);
+    for (int i = 0; i < RR_T_COUNT + 2; i++) { cudaEventDestroy(c->ev[i]); cudaEventDestroy(c->ev_end[i]); }
+    cudaEventDestroy(c->ev_plan);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->s_h2d);
     cudaStreamDestroy(c->s_d2h);
     cudaStreamSynchronize(c->s_plan);
     cudaStreamDestroy(c->s_plan);
+    cudaStreamDestroy(c->s_png);
     cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join);
     for (int i = 0; i < RR_MAX_SUB; i++) { cudaEventDestroy(c->ev_in[i]); cudaEventDestroy(c->ev_done[i]); cudaEventDestroy(c->ev_d2h[i]); }
     for (int i = 0; i < 2; i++) cudaEventDestroy(c->ev_call[i]);
@@ -288,7 +365,7 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
     CK(rr_launch_omega(He, We, c->d_omega, c->d_omega_pref, c->d_omega_total, c->stream));
     c->launches += 3;
     // per-batch buffers
-    const size_t F = (size_t)max_batch, np = (size_t)W * H, npe = (size_t)He * We;
+    const size_t F = (size_t)max_batch, np = (size_t)W * H;
     const int rs = cam->render_scale == 2 ? 2 : 1;
     rr_frame_bufs &b = c->fb;
     CK(dev_alloc(c, &c->d_bgr, F * np * 3 * rs * rs));
@@ -304,9 +381,28 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
     if (rs == 2) CK(dev_alloc(c, &c->d_bgf, F * 3 * np));
     CK(dev_alloc(c, &b.rainy, F * 3 * np));
     CK(dev_alloc(c, &b.bg8, F * np * 4));
-    CK(dev_alloc(c, &b.fext, F * np));
+    {
+        // extinction planes with the 12-pixel reflected halo materialised and a 16-byte pitch: every haloed fog tile is one TMA box
+        const char *env = getenv("RR_FOG_TMA");
+        c->fog_tma = !(env && atoi(env) == 0);
+        b.fext_Wp = (W + 24 + 3) & ~3; b.fext_Hp = H + 24;
+        CK(dev_alloc(c, &b.fext, F * (size_t)b.fext_Wp * b.fext_Hp));
+        CK(dev_alloc(c, &c->d_fext_lut, (size_t)65536));
+        CK(rr_launch_fext_lut(c->d_fext_lut, c->fogc.neg_beta32, c->stream));
+        c->launches += 1;
+        b.fext_lut = c->d_fext_lut;
+        if (c->fog_tma) {
+            int r = make_plane_map(&c->fog_map, b.fext, b.fext_Wp, b.fext_Hp, max_batch, 88, 56);
+            if (r != RR_OK) return r;
+        }
+    }
     CK(dev_alloc(c, &b.fblur, F * np));
-    CK(dev_alloc(c, &b.env8, F * npe * 4));
+    b.env_pitch = (We + 3) & ~3;
+    {
+        const char *env = getenv("RR_ENV_BULK");
+        b.env_bulk = !(env && atoi(env) == 0);
+    }
+    CK(dev_alloc(c, &b.env8, F * (size_t)He * b.env_pitch * 4));
     CK(dev_alloc(c, &b.pref, F * 4 * (size_t)He * (We + 1)));
     CK(dev_alloc(c, &b.rowtot, F * He));
     CK(dev_alloc(c, &b.ambient, F));
@@ -342,6 +438,42 @@ int rr_env_size(rr_context *c, int *H_env, int *W_env) {
     return RR_OK;
 }
 
+// device buffers of the GPU PNG path, allocated on first use (max_batch streams of each kind per async slot)
+static int ensure_png(rr_context *c) {
+    if (c->png_ready) return RR_OK;
+    drain(c);
+    rr_png_bufs &p = c->png;
+    const size_t F = (size_t)c->max_batch;
+    p.W = c->cam.W; p.H = c->cam.H;
+    p.n = (size_t)p.H * ((size_t)4 * p.W + 1);
+    if (p.n * 15 + 4096 >= 0xffffffffull || (size_t)4 * p.W + 64 > 40000) { set_err("GPU PNG encoding: %d x %d is too large for this path", p.W, p.H); return RR_ERR_ARG; }
+    p.n_pad = (p.n + 127) & ~(size_t)127;
+    p.cap = rr_png_stream_bound(p.W, p.H);
+    p.nchunks = (int)((p.n + 127) / 128);
+    CK(dev_alloc(c, &p.filt, F * p.n_pad));
+    CK(dev_alloc(c, &p.hist, F * 256));
+    CK(dev_alloc(c, &p.adler, F * 2));
+    CK(dev_alloc(c, &p.codes, F * 257));
+    CK(dev_alloc(c, &p.chunk_bits, F * (size_t)p.nchunks));
+    for (int s = 0; s < 2; s++)
+        for (int k = 0; k < 2; k++) {
+            CK(dev_alloc(c, &c->d_png_stream[s][k], F * p.cap));
+            CK(dev_alloc(c, &c->d_png_sizes[s][k], F));
+        }
+    c->png_ready = true;
+    return RR_OK;
+}
+
+// view of the PNG buffers for frames [f0, ...) of async slot `slot`, kind 0 image / 1 mask
+static rr_png_bufs png_view(const rr_context *c, int slot, int kind, int f0) {
+    rr_png_bufs v = c->png;
+    v.filt += (size_t)f0 * v.n_pad; v.hist += (size_t)f0 * 256; v.adler += (size_t)f0 * 2; v.codes += (size_t)f0 * 257;
+    v.chunk_bits += (size_t)f0 * v.nchunks;
+    v.stream = c->d_png_stream[slot][kind] + (size_t)f0 * v.cap;
+    v.sizes = c->d_png_sizes[slot][kind] + f0;
+    return v;
+}
+
 static rr_static_tabs tabs_of(rr_context *c) {
     rr_static_tabs t;
     t.env_src = c->d_env_src; t.env_written = c->d_env_written; t.env_tile_hole = c->d_env_tile_hole; t.omega = c->d_omega; t.omega_pref = c->d_omega_pref;
@@ -356,41 +488,71 @@ static int check_ready(rr_context *c, int n_frames, const char *who) {
     return RR_OK;
 }
 
-// the device pipeline for a batch whose inputs are already in fb.bgr / fb.depth / fb.streaks / fb.offsets
+// The device pipeline for a batch whose inputs are already in fb.bgr / fb.depth / fb.streaks / fb.offsets.
+// Two chains that meet at the compositor:
+//   frame chain  (main stream):  stats -> extinction -> fog -> environment map -> prefix sums -> per-streak photometry
+//   streak chain (side stream):  plan -> arena scan -> patch rasteriser -> defocus blur
+// The rasteriser and the blur need only the geometry k_plan derives from the streak records, the photometry needs the
+// frame's environment map; nothing in one chain reads what the other writes (k_setup fills the tint fields of the plans,
+// the streak chain reads their geometry fields), so the integer / load-bound streak kernels run beside the float64-bound
+// frame kernels on the same SMs.
 static int run_pipeline(rr_context *c, int F, int n_streaks, bool timed) {
     rr_frame_bufs &b = c->fb;
     const rr_static_tabs t = tabs_of(c);
-    cudaStream_t st = c->stream;
+    cudaStream_t st = c->stream, ss = c->serial ? c->stream : c->s_plan;
     const int W = c->cam.W, H = c->cam.H;
     c->camd.db_width = c->db_width; c->camd.n_tex = c->n_tex;
-    if (timed) CK(cudaEventRecord(c->ev[RR_T_FOG], st));
+    for (int i = 0; i < RR_T_COUNT; i++) c->slot_has_end[i] = c->slot_side[i] = false;
     // fork: everything this (sub-)batch depends on has been enqueued on st (inputs landed, the previous user of the plan /
-    // walker buffers is done); the geometry kernel runs on its own stream and joins before the photometry
-    CK(cudaEventRecord(c->ev_fork, st));
-    CK(cudaStreamWaitEvent(c->s_plan, c->ev_fork, 0));
-    CK(rr_launch_plan(b, t, c->camd, n_streaks, c->s_plan));
-    CK(cudaEventRecord(c->ev_join, c->s_plan));
+    // walker buffers and of the patch arena is done)
+    if (!c->serial) { CK(cudaEventRecord(c->ev_fork, st)); CK(cudaStreamWaitEvent(ss, c->ev_fork, 0)); }
+    if (timed) CK(cudaEventRecord(c->ev[RR_T_FOG], st));
     const int rs = c->cam.render_scale == 2 ? 2 : 1;
+    if (c->serial) {
+        CK(rr_launch_plan(b, t, c->camd, n_streaks, ss));
+    }
     CK(rr_launch_stats(b, F, W, H, rs, (double *)b.bgf, st));
-    CK(rr_launch_fog(b, c->fogc, F, W, H, st));
+    CK(rr_launch_fog(b, c->fogc, F, W, H, c->fog_tma ? &c->fog_map : nullptr, st));
     if (timed) CK(cudaEventRecord(c->ev[RR_T_ENV], st));
     CK(rr_launch_env(b, t, F, W, H, c->W_env, st));
     if (timed) CK(cudaEventRecord(c->ev[RR_T_SETUP], st));
-    CK(cudaStreamWaitEvent(st, c->ev_join, 0));
-    CK(rr_launch_setup(b, t, c->camd, F, n_streaks, st));
-    CK(rr_launch_scan(b, n_streaks, st));
-    if (timed) CK(cudaEventRecord(c->ev[RR_T_RASTER], st));
-    CK(rr_launch_raster(b, t, c->camd, n_streaks, c->n_sm, st));
-    if (timed) CK(cudaEventRecord(c->ev[RR_T_BLUR], st));
-    CK(rr_launch_blur(b, n_streaks, c->n_sm, st));
+    // ---- streak chain ----
+    if (!c->serial) {
+        CK(rr_launch_plan(b, t, c->camd, n_streaks, ss));
+        CK(cudaEventRecord(c->ev_plan, ss));
+    }
+    if (!c->serial) {
+        CK(rr_launch_scan(b, n_streaks, ss));
+        if (timed) CK(cudaEventRecord(c->ev[RR_T_RASTER], ss));
+        CK(rr_launch_raster(b, t, c->camd, n_streaks, c->n_sm, ss));
+        if (timed) { CK(cudaEventRecord(c->ev_end[RR_T_RASTER], ss)); CK(cudaEventRecord(c->ev[RR_T_BLUR], ss)); }
+        CK(rr_launch_blur(b, n_streaks, c->n_sm, ss));
+        if (timed) CK(cudaEventRecord(c->ev_end[RR_T_BLUR], ss));
+        c->slot_has_end[RR_T_RASTER] = c->slot_has_end[RR_T_BLUR] = true;
+        c->slot_side[RR_T_RASTER] = c->slot_side[RR_T_BLUR] = true;
+        CK(cudaEventRecord(c->ev_join, ss));
+        // ---- frame chain, continued: photometry needs the walkers k_plan prepared ----
+        CK(cudaStreamWaitEvent(st, c->ev_plan, 0));
+        CK(rr_launch_setup(b, t, c->camd, F, n_streaks, st));
+        if (timed) CK(cudaEventRecord(c->ev_end[RR_T_SETUP], st));
+        c->slot_has_end[RR_T_SETUP] = true;
+        CK(cudaStreamWaitEvent(st, c->ev_join, 0));
+    } else {
+        CK(rr_launch_setup(b, t, c->camd, F, n_streaks, st));
+        CK(rr_launch_scan(b, n_streaks, st));
+        if (timed) CK(cudaEventRecord(c->ev[RR_T_RASTER], st));
+        CK(rr_launch_raster(b, t, c->camd, n_streaks, c->n_sm, st));
+        if (timed) CK(cudaEventRecord(c->ev[RR_T_BLUR], st));
+        CK(rr_launch_blur(b, n_streaks, c->n_sm, st));
+    }
     if (timed) CK(cudaEventRecord(c->ev[RR_T_COMPOSITE], st));
     CK(rr_launch_composite(b, c->camd, F, st));
     if (timed) CK(cudaEventRecord(c->ev[RR_T_EPILOGUE], st));
     CK(rr_launch_epilogue(b, F, W, H, st));
     if (timed) CK(cudaEventRecord(c->ev[RR_T_D2H], st));
-    // stats 2, extinction + fog constants 2, fog 1, env map + prefix + ambient 3, plan + set-up 2, scan 1, raster + blur 2,
+    // stats 2, fog constants + extinction + fog 3, env map + prefix + ambient 3, plan + set-up 2, scan 1, raster + blur 2,
     // composite + frame mean 2, epilogue 1
-    c->launches += 2 + 2 + 1 + 3 + (n_streaks ? 2 : 0) + 1 + (n_streaks ? 2 : 0) + 2 + 1;
+    c->launches += 2 + 3 + 3 + (n_streaks ? 2 : 0) + 1 + (n_streaks ? 2 : 0) + 2 + 1;
     c->last_n_streaks = n_streaks;
     return RR_OK;
 }
@@ -398,14 +560,14 @@ static int run_pipeline(rr_context *c, int F, int n_streaks, bool timed) {
 // shifted view of the batch buffers for frames [f0, f0 + ...) whose streaks start at record s0
 static rr_frame_bufs sub_view(const rr_context *c, const rr_frame_bufs &b, int f0, int s0, long long scan_base) {
     rr_frame_bufs v = b;
-    const size_t np = (size_t)c->cam.W * c->cam.H, npe = (size_t)c->H_env * c->W_env;
+    const size_t np = (size_t)c->cam.W * c->cam.H;
     const size_t tiles = rr_n_partials(c->cam.W, c->cam.H);
     const int rs2 = c->cam.render_scale == 2 ? 4 : 1;
     v.bgr += (size_t)f0 * np * 3 * rs2; v.depth = (const char *)v.depth + (size_t)f0 * np * (v.depth_u16 ? 2 : 4); v.streaks += s0;
     if (v.bgf) v.bgf += (size_t)f0 * 3 * np;
     v.bg_sum += (size_t)f0 * 4; v.acs += (size_t)f0 * 4;
-    v.chan_sum += (size_t)f0 * 4; v.rainy += (size_t)f0 * 3 * np; v.bg8 += (size_t)f0 * np * 4; v.fblur += (size_t)f0 * np; v.fext += (size_t)f0 * np;
-    v.env8 += (size_t)f0 * npe * 4;
+    v.chan_sum += (size_t)f0 * 4; v.rainy += (size_t)f0 * 3 * np; v.bg8 += (size_t)f0 * np * 4; v.fblur += (size_t)f0 * np; v.frame0 += f0;
+    v.env8 += (size_t)f0 * c->H_env * b.env_pitch * 4;
     v.pref += (size_t)f0 * 4 * c->H_env * (c->W_env + 1); v.rowtot += (size_t)f0 * c->H_env; v.ambient += f0;
     v.plans += s0; v.fcp += s0; v.sizes += s0; v.boxes += s0; v.scan += (size_t)scan_base * 6;
     v.tile_sum += (size_t)f0 * tiles; v.tile_min += (size_t)f0 * tiles; v.tile_max += (size_t)f0 * tiles; v.frame_mean += f0;
@@ -422,7 +584,11 @@ static int finish_timings(rr_context *c) {
     // ev[RR_T_H2D] .. ev[RR_T_TOTAL] were recorded in order; slot i = time from ev[i] to ev[i+1]
     for (int i = RR_T_H2D; i < RR_T_TOTAL; i++) {
         float ms = 0;
-        cudaError_t e = cudaEventElapsedTime(&ms, c->ev[i], c->ev[i + 1]);
+        // a slot with its own end event (the side-stream stages; the set-up, after which the main stream waits for the side
+        // stream) uses it; the others end where the next main-stream slot starts
+        int nx = i + 1;
+        while (nx < RR_T_TOTAL && c->slot_side[nx]) nx++;
+        cudaError_t e = cudaEventElapsedTime(&ms, c->ev[i], c->slot_has_end[i] ? c->ev_end[i] : c->ev[nx]);
         c->last_ms[i] = e == cudaSuccess ? ms : -1.f;
     }
     float tot = 0;
@@ -472,6 +638,20 @@ static int wait_oldest(rr_context *c, bool grow) {
     const int slot = c->inflight == 2 ? c->parity : (c->parity ^ 1);
     CK(cudaEventSynchronize(c->ev_call[slot]));
     c->inflight--;
+    {   // the finished PNG streams: their sizes are on the host now, so exactly those bytes are fetched
+        const rr_frame_io &io = c->call_io[slot];
+        const int F = c->call_F[slot];
+        for (int kind = 0; kind < 2; kind++) {
+            uint8_t *host = kind ? io.out_png_mask : io.out_png_image;
+            const uint32_t *sizes = kind ? io.out_png_mask_sizes : io.out_png_image_sizes;
+            if (!host) continue;
+            for (int i = 0; i < F; i++) {
+                if (sizes[i] == 0 || sizes[i] > io.png_stride) { set_err("GPU PNG stream %d of the batch: %u bytes do not fit the %llu-byte stride", i, sizes[i], (unsigned long long)io.png_stride); return RR_ERR_CAPACITY; }
+                CK(cudaMemcpyAsync(host + (size_t)i * io.png_stride, c->d_png_stream[slot][kind] + (size_t)i * c->png.cap, sizes[i], cudaMemcpyDeviceToHost, c->s_png));
+            }
+        }
+        if (io.out_png_image || io.out_png_mask) CK(cudaStreamSynchronize(c->s_png));
+    }
     return check_flag_slot(c, c->d_err2 + slot, c->call_S[slot], c->call_scan_base[slot], c->call_sub_n[slot], grow && c->inflight == 0);
 }
 
@@ -479,8 +659,8 @@ static int wait_oldest(rr_context *c, bool grow) {
 static void select_outputs(rr_frame_bufs &v, const rr_frame_bufs &all, const rr_frame_io &io) {
     v.out_bgr = io.out_bgr ? all.out_bgr : nullptr;
     v.out_mask = io.out_mask ? all.out_mask : nullptr;
-    v.out_u8 = io.out_bgr_u8 ? all.out_u8 : nullptr;
-    v.out_idx8 = io.out_mask_idx8 ? all.out_idx8 : nullptr;
+    v.out_u8 = (io.out_bgr_u8 || io.out_png_image) ? all.out_u8 : nullptr;
+    v.out_idx8 = (io.out_mask_idx8 || io.out_png_mask) ? all.out_idx8 : nullptr;
     v.out_u16 = io.out_mask_u16 ? all.out_u16 : nullptr;
 }
 
@@ -515,6 +695,13 @@ static int submit_frames(rr_context *c, int F, const rr_frame_io &io, bool timed
     for (int k = 0; k < S; k++) { int ns = streak_offsets[fstart[k + 1]] - streak_offsets[fstart[k]]; if (ns > max_ns) max_ns = ns; }
     int r = ensure_streak_cap(c, n_streaks, max_ns);
     if (r != RR_OK) return r;
+    if (io.out_png_image || io.out_png_mask) {
+        if ((io.out_png_image && !io.out_png_image_sizes) || (io.out_png_mask && !io.out_png_mask_sizes) || io.png_stride < 64) {
+            set_err("rr_frame_io: PNG outputs need their size arrays and a stride"); return RR_ERR_ARG;
+        }
+        r = ensure_png(c);
+        if (r != RR_OK) return r;
+    }
     if (c->inflight == 2) { r = wait_oldest(c, false); if (r != RR_OK) return r; }
     const int slot = c->parity, prev = slot ^ 1;
     if (c->inflight && (c->call_S[prev] != S || c->call_F[prev] != F || c->call_multi[prev] != (int)multi)) drain(c);    // slot regions would not line up
@@ -551,6 +738,12 @@ static int submit_frames(rr_context *c, int F, const rr_frame_io &io, bool timed
         c->fb = sub_view(c, sel, f0, s0, sb);
         c->fb.offsets = saved.offsets;
         r = run_pipeline(c, nf, ns, timed && S == 1);
+        if (r == RR_OK && (io.out_png_image || io.out_png_mask)) {
+            // the saved files' image data, finished on the device (csrc/rr_png_gpu.cu)
+            if (io.out_png_image) { cudaError_t e = rr_launch_png_encode(png_view(c, slot, 0, f0), c->fb.out_u8, false, nf, st); if (e != cudaSuccess) { set_err("GPU PNG encode: %s", cudaGetErrorString(e)); r = RR_ERR_CUDA; } }
+            if (r == RR_OK && io.out_png_mask) { cudaError_t e = rr_launch_png_encode(png_view(c, slot, 1, f0), c->fb.out_idx8, true, nf, st); if (e != cudaSuccess) { set_err("GPU PNG encode: %s", cudaGetErrorString(e)); r = RR_ERR_CUDA; } }
+            c->launches += 5 * ((io.out_png_image ? 1 : 0) + (io.out_png_mask ? 1 : 0));
+        }
         saved.bgr = nullptr; saved.depth = nullptr; saved.streaks = nullptr;
         c->fb = saved;
         if (r != RR_OK) return r;
@@ -563,11 +756,14 @@ static int submit_frames(rr_context *c, int F, const rr_frame_io &io, bool timed
         if (io.out_mask_idx8) CK(cudaMemcpyAsync(io.out_mask_idx8 + (size_t)f0 * np, b.out_idx8 + (size_t)f0 * np, (size_t)nf * np, cudaMemcpyDeviceToHost, ds));
         if (io.out_mask_u16) CK(cudaMemcpyAsync(io.out_mask_u16 + (size_t)f0 * np, b.out_u16 + (size_t)f0 * np, (size_t)nf * np * 2, cudaMemcpyDeviceToHost, ds));
         if (io.out_mask_range) CK(cudaMemcpyAsync(io.out_mask_range + (size_t)f0 * 2, b.mask_range + (size_t)f0 * 2, (size_t)nf * 2 * sizeof(double), cudaMemcpyDeviceToHost, ds));
+        if (io.out_png_image) CK(cudaMemcpyAsync(io.out_png_image_sizes + f0, c->d_png_sizes[slot][0] + f0, (size_t)nf * sizeof(uint32_t), cudaMemcpyDeviceToHost, ds));
+        if (io.out_png_mask) CK(cudaMemcpyAsync(io.out_png_mask_sizes + f0, c->d_png_sizes[slot][1] + f0, (size_t)nf * sizeof(uint32_t), cudaMemcpyDeviceToHost, ds));
         if (multi) CK(cudaEventRecord(c->ev_d2h[k], ds));
     }
     c->n_sub_last = S;
     c->last_n_streaks = n_streaks;
     c->call_S[slot] = S; c->call_F[slot] = F; c->call_n[slot] = n_streaks; c->call_multi[slot] = (int)multi;
+    c->call_io[slot] = io;
     if (timed) {
         if (multi) { CK(cudaEventRecord(c->ev_out, c->s_d2h)); CK(cudaStreamWaitEvent(st, c->ev_out, 0)); }
         CK(cudaEventRecord(c->ev[RR_T_TOTAL], st));
@@ -710,7 +906,8 @@ int rr_fog_only(rr_context *c, int n_frames, const uint8_t *bgr, const float *de
     CK(cudaMemcpyAsync(c->d_depth, depth, F * np * sizeof(float), cudaMemcpyHostToDevice, st));
     b.bgr = c->d_bgr; b.depth = c->d_depth; b.depth_u16 = 0; b.bgf = c->d_bgf;
     CK(rr_launch_stats(b, n_frames, c->cam.W, c->cam.H, rs2 == 4 ? 2 : 1, c->d_bgf, st));
-    CK(rr_launch_fog(b, c->fogc, n_frames, c->cam.W, c->cam.H, st));
+    b.frame0 = 0;
+    CK(rr_launch_fog(b, c->fogc, n_frames, c->cam.W, c->cam.H, c->fog_tma ? &c->fog_map : nullptr, st));
     c->launches += 5;
     CK(cudaMemcpyAsync(out_planar, b.rainy, F * 3 * np * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -729,8 +926,8 @@ int rr_envmap_only(rr_context *c, int n_frames, const double *planar, uint8_t *o
     CK(rr_launch_planar_to_bg8(b.rainy, b.bg8, n_frames, c->cam.W, c->cam.H, st));
     CK(rr_launch_env(b, tabs_of(c), n_frames, c->cam.W, c->cam.H, c->W_env, st));
     c->launches += 4;
-    std::vector<uint8_t> tmp(F * npe * 4);                     // the device keeps (B, G, R, 0) words
-    CK(cudaMemcpyAsync(tmp.data(), b.env8, F * npe * 4, cudaMemcpyDeviceToHost, st));
+    std::vector<uint8_t> tmp(F * npe * 4);                     // the device keeps (B, G, R, 0) words in rows of env_pitch pixels
+    CK(cudaMemcpy2DAsync(tmp.data(), (size_t)c->W_env * 4, b.env8, (size_t)b.env_pitch * 4, (size_t)c->W_env * 4, F * c->H_env, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     for (size_t i = 0; i < F * npe; i++) { out_env[3 * i] = tmp[4 * i]; out_env[3 * i + 1] = tmp[4 * i + 1]; out_env[3 * i + 2] = tmp[4 * i + 2]; }
     return RR_OK;
@@ -751,7 +948,7 @@ int rr_streak_photometry_only(rr_context *c, const uint8_t *env_bgr_u8, int n_st
     rr_frame_bufs &b = c->fb;
     std::vector<uint8_t> env4(npe * 4, 0);                     // the device keeps (B, G, R, 0) words
     for (size_t i = 0; i < npe; i++) { env4[4 * i] = env_bgr_u8[3 * i]; env4[4 * i + 1] = env_bgr_u8[3 * i + 1]; env4[4 * i + 2] = env_bgr_u8[3 * i + 2]; }
-    CK(cudaMemcpyAsync(b.env8, env4.data(), npe * 4, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpy2DAsync(b.env8, (size_t)b.env_pitch * 4, env4.data(), (size_t)c->W_env * 4, (size_t)c->W_env * 4, c->H_env, cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(c->d_streaks, streaks, (size_t)n_streaks * sizeof(rr_streak_rec), cudaMemcpyHostToDevice, st));
     int32_t off[2] = {0, n_streaks};
     CK(cudaMemcpyAsync(c->d_offsets, off, sizeof(off), cudaMemcpyHostToDevice, st));
@@ -805,7 +1002,8 @@ int rr_debug_read(rr_context *c, int what, int frame, void *dst, size_t bytes) {
         case RR_DBG_ENV_U8: {                                  // device words (B, G, R, 0) -> packed BGR for the caller
             std::vector<uint8_t> tmp(npe * 4);
             CK(cudaStreamSynchronize(c->stream));
-            CK(cudaMemcpy(tmp.data(), b.env8 + (size_t)frame * npe * 4, npe * 4, cudaMemcpyDeviceToHost));
+            CK(cudaMemcpy2D(tmp.data(), (size_t)c->W_env * 4, b.env8 + (size_t)frame * c->H_env * b.env_pitch * 4, (size_t)b.env_pitch * 4,
+                            (size_t)c->W_env * 4, c->H_env, cudaMemcpyDeviceToHost));
             uint8_t *o = (uint8_t *)dst;
             for (size_t i = 0; i < npe && 3 * i + 2 < bytes; i++) { o[3 * i] = tmp[4 * i]; o[3 * i + 1] = tmp[4 * i + 1]; o[3 * i + 2] = tmp[4 * i + 2]; }
             return RR_OK;

@@ -1,0 +1,246 @@
+// A single-shot zlib-stream decoder for PNG image data (host code; adler32() from zlib is the only dependency).
+//
+// Decoding a frame's two PNGs is what bounds the drop-in pipeline once rendering takes 0.1 ms per frame, and 80 % of
+// that is zlib's inflate (a byte-oriented state machine built for streaming).  PNG gives us the whole compressed stream
+// and the exact decoded size up front, so this decoder works in one pass over contiguous buffers: a 64-bit bit buffer
+// refilled eight bytes at a time, an 11-bit first-level table for the literal/length code and an 8-bit one for the
+// distance code (second-level tables behind them for longer codes), literals decoded back to back, matches copied in
+// 8-byte steps.  Every write is bounds-checked against the known output size and every malformed code is an error:
+// corrupt input yields RR_ERR_ARG, never an overrun.  The Adler-32 trailer is verified.
+//
+// RFC 1950 (zlib container), RFC 1951 (deflate: stored, fixed and dynamic Huffman blocks).
+#pragma once
+#include <stdint.h>
+#include <string.h>
+#include <zlib.h>
+
+namespace rr_inflate {
+
+enum { LIT_BITS = 11, DIST_BITS = 8, LIT_TABLE = (1 << LIT_BITS) + 288 * 16, DIST_TABLE = (1 << DIST_BITS) + 32 * 128 };
+// table entry: low 8 bits = code bits to consume (0 = invalid code); bits 8..11 = extra bits (lengths / distances) or
+// the width of the second-level table (KIND_SUB); bits 12..15 kind; bits 16..31 = literal value / base / sub-table offset
+enum { KIND_LIT = 1, KIND_LEN = 2, KIND_EOB = 3, KIND_SUB = 4, KIND_DIST = 5 };
+static inline uint32_t entry(int kind, int bits, int extra, int value) { return (uint32_t)bits | ((uint32_t)extra << 8) | ((uint32_t)kind << 12) | ((uint32_t)value << 16); }
+
+static const uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+static const uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+static const uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+static const uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+
+static inline uint32_t reverse_bits(uint32_t v, int n) {
+    uint32_t r = 0;
+    for (int i = 0; i < n; i++) { r = (r << 1) | (v & 1); v >>= 1; }
+    return r;
+}
+
+// Builds the two-level decode table of a canonical Huffman code.  lens[0..n): code lengths (0 = unused).  what: 0 literal /
+// length alphabet, 1 distance alphabet, 2 code-length alphabet (values = the symbol itself).  Returns false when the code
+// is over-subscribed, or incomplete (except the single-code case deflate allows).
+static inline bool build_table(const uint8_t *lens, int n, int what, uint32_t *table, int primary_bits, int table_cap) {
+    int count[16] = {0};
+    for (int i = 0; i < n; i++) count[lens[i]]++;
+    count[0] = 0;
+    int max_len = 0, used = 0;
+    for (int l = 1; l < 16; l++) if (count[l]) { max_len = l; used += count[l]; }
+    for (int i = 0; i < (1 << primary_bits); i++) table[i] = 0;
+    if (used == 0) return what == 1;                               // no distance codes at all: legal when the block has no matches
+    // Kraft sum
+    long left = 1;
+    for (int l = 1; l <= 15; l++) { left <<= 1; left -= count[l]; if (left < 0) return false; }
+    if (left > 0 && !(used == 1 && max_len == 1)) return false;    // incomplete: only a lone 1-bit code is allowed
+    int next_code[16], code = 0;
+    for (int l = 1; l < 16; l++) { code = (code + count[l - 1]) << 1; next_code[l] = code; }
+    const int sub_bits = max_len > primary_bits ? max_len - primary_bits : 0;
+    int next_sub = 1 << primary_bits;
+    for (int s = 0; s < n; s++) {
+        const int l = lens[s];
+        if (!l) continue;
+        const uint32_t rev = reverse_bits((uint32_t)next_code[l]++, l);
+        uint32_t e;
+        if (what == 0) {
+            if (s < 256) e = entry(KIND_LIT, 0, 0, s);
+            else if (s == 256) e = entry(KIND_EOB, 0, 0, 0);
+            else if (s <= 285) e = entry(KIND_LEN, 0, kLenExtra[s - 257], kLenBase[s - 257]);
+            else e = 0;                                            // 286, 287: never valid in data
+        } else if (what == 1) {
+            e = s < 30 ? entry(KIND_DIST, 0, kDistExtra[s], kDistBase[s]) : 0;
+        } else e = entry(KIND_LIT, 0, 0, s);
+        if (l <= primary_bits) {
+            if (e) e |= (uint32_t)l;
+            for (uint32_t i = rev; i < (1u << primary_bits); i += 1u << l) table[i] = e;
+        } else {
+            const uint32_t prefix = rev & ((1u << primary_bits) - 1);
+            uint32_t pe = table[prefix];
+            if (((pe >> 12) & 15) != KIND_SUB) {
+                if (next_sub + (1 << sub_bits) > table_cap) return false;
+                for (int i = 0; i < (1 << sub_bits); i++) table[next_sub + i] = 0;
+                pe = entry(KIND_SUB, primary_bits, sub_bits, next_sub);
+                table[prefix] = pe;
+                next_sub += 1 << sub_bits;
+            }
+            const uint32_t base = pe >> 16;
+            if (e) e |= (uint32_t)(l - primary_bits);
+            for (uint32_t i = rev >> primary_bits; i < (1u << sub_bits); i += 1u << (l - primary_bits)) table[base + i] = e;
+        }
+    }
+    return true;
+}
+
+struct Bits {
+    const uint8_t *in, *in_end;     // in_end: end of the real data; the buffer carries >= 8 readable bytes beyond it
+    uint64_t buf = 0;
+    int cnt = 0;
+    inline void refill() {          // afterwards cnt >= 56
+        uint64_t w;
+        memcpy(&w, in, 8);          // little-endian hosts (x86-64 / aarch64)
+        buf |= w << cnt;
+        in += (63 - cnt) >> 3;
+        cnt |= 56;
+    }
+    inline uint32_t peek(int n) const { return (uint32_t)(buf & ((1ull << n) - 1)); }
+    inline void drop(int n) { buf >>= n; cnt -= n; }
+    // true when more bits have been consumed than the real input holds
+    inline bool overrun() const { return in - (cnt >> 3) > in_end; }
+};
+
+// in[0..in_len) must be followed by at least 8 readable bytes (any value).  Decodes exactly `out_len` bytes; a stream that
+// decodes to anything else is an error.  Returns true on success.
+static inline bool zlib_decompress(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_len) {
+    if (in_len < 6) return false;
+    if ((in[0] & 0x0f) != 8 || (in[0] >> 4) > 7 || (((unsigned)in[0] << 8) | in[1]) % 31 != 0 || (in[1] & 0x20)) return false;
+    Bits b;
+    b.in = in + 2;
+    b.in_end = in + in_len - 4;                                    // the Adler-32 is not deflate data
+    uint8_t *o = out, *const o_end = out + out_len;
+    static const uint8_t order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    uint32_t lit_table[LIT_TABLE], dist_table[DIST_TABLE], cl_table[1 << 7];
+    bool final_block = false;
+    while (!final_block) {
+        b.refill();
+        final_block = b.peek(1);
+        const int type = (b.peek(3) >> 1);
+        b.drop(3);
+        if (type == 0) {                                           // stored
+            b.drop(b.cnt & 7);
+            b.refill();
+            const uint32_t len = b.peek(16), nlen = (uint32_t)((b.buf >> 16) & 0xffff);
+            b.drop(32);
+            if ((len ^ 0xffff) != nlen) return false;
+            // give the unread whole bytes of the bit buffer back to the byte stream
+            const uint8_t *src = b.in - (b.cnt >> 3);
+            if (src + len > b.in_end || len > (size_t)(o_end - o)) return false;
+            memcpy(o, src, len);
+            o += len;
+            b.in = src + len; b.buf = 0; b.cnt = 0;
+            continue;
+        }
+        if (type == 3) return false;
+        if (type == 1) {                                           // fixed Huffman codes
+            uint8_t lens[288 + 32];
+            for (int i = 0; i < 144; i++) lens[i] = 8;
+            for (int i = 144; i < 256; i++) lens[i] = 9;
+            for (int i = 256; i < 280; i++) lens[i] = 7;
+            for (int i = 280; i < 288; i++) lens[i] = 8;
+            for (int i = 0; i < 32; i++) lens[288 + i] = 5;
+            if (!build_table(lens, 288, 0, lit_table, LIT_BITS, LIT_TABLE) || !build_table(lens + 288, 32, 1, dist_table, DIST_BITS, DIST_TABLE)) return false;
+        } else {                                                   // dynamic Huffman codes
+            const int hlit = (int)b.peek(5) + 257, hdist = (int)((b.buf >> 5) & 31) + 1, hclen = (int)((b.buf >> 10) & 15) + 4;
+            b.drop(14);
+            if (hlit > 286 || hdist > 30) return false;
+            uint8_t cl[19] = {0};
+            for (int i = 0; i < hclen; i++) {
+                if (b.cnt < 3) b.refill();
+                cl[order[i]] = (uint8_t)b.peek(3);
+                b.drop(3);
+            }
+            if (!build_table(cl, 19, 2, cl_table, 7, 1 << 7)) return false;
+            uint8_t lens[286 + 30 + 140];
+            int n = 0;
+            while (n < hlit + hdist) {
+                b.refill();
+                const uint32_t e = cl_table[b.peek(7)];
+                if (!(e & 0xff)) return false;
+                b.drop((int)(e & 0xff));
+                const int sym = (int)(e >> 16);
+                if (sym < 16) { lens[n++] = (uint8_t)sym; continue; }
+                int rep, val = 0;
+                if (sym == 16) { if (n == 0) return false; val = lens[n - 1]; rep = 3 + (int)b.peek(2); b.drop(2); }
+                else if (sym == 17) { rep = 3 + (int)b.peek(3); b.drop(3); }
+                else { rep = 11 + (int)b.peek(7); b.drop(7); }
+                if (n + rep > hlit + hdist) return false;
+                while (rep--) lens[n++] = (uint8_t)val;
+            }
+            if (b.overrun() || lens[256] == 0) return false;       // a block without an end-of-block code cannot end
+            if (!build_table(lens, hlit, 0, lit_table, LIT_BITS, LIT_TABLE) || !build_table(lens + hlit, hdist, 1, dist_table, DIST_BITS, DIST_TABLE)) return false;
+        }
+        // ---- the block's symbols ----
+        for (;;) {
+            b.refill();
+            if (b.overrun()) return false;
+            uint32_t e = lit_table[b.peek(LIT_BITS)];
+            // up to three literals per refill (3 x 15 bits); each one re-checks the output bound
+            int guard = 0;
+            while (((e >> 12) & 15) == KIND_LIT && guard < 3) {
+                if (o >= o_end) return false;
+                b.drop((int)(e & 0xff));
+                *o++ = (uint8_t)(e >> 16);
+                e = lit_table[b.peek(LIT_BITS)];
+                guard++;
+            }
+            if (guard == 3) continue;                              // refill before going on
+            int kind = (int)((e >> 12) & 15);
+            if (kind == KIND_SUB) {
+                b.drop((int)(e & 0xff));
+                e = lit_table[(e >> 16) + b.peek((int)((e >> 8) & 15))];
+                kind = (int)((e >> 12) & 15);
+                if (b.cnt < 40) b.refill();
+            }
+            if (!(e & 0xff)) return false;                         // invalid code
+            b.drop((int)(e & 0xff));
+            if (kind == KIND_LIT) {
+                if (o >= o_end) return false;
+                *o++ = (uint8_t)(e >> 16);
+                continue;
+            }
+            if (kind == KIND_EOB) break;
+            if (kind != KIND_LEN) return false;
+            const int xb = (int)((e >> 8) & 15);
+            const size_t len = (size_t)(e >> 16) + b.peek(xb);
+            b.drop(xb);
+            if (b.cnt < 32) b.refill();
+            uint32_t d = dist_table[b.peek(DIST_BITS)];
+            if (((d >> 12) & 15) == KIND_SUB) {
+                b.drop((int)(d & 0xff));
+                d = dist_table[(d >> 16) + b.peek((int)((d >> 8) & 15))];
+            }
+            if (!(d & 0xff) || ((d >> 12) & 15) != KIND_DIST) return false;
+            b.drop((int)(d & 0xff));
+            const int dxb = (int)((d >> 8) & 15);
+            const size_t dist = (size_t)(d >> 16) + b.peek(dxb);
+            b.drop(dxb);
+            if (dist > (size_t)(o - out) || len > (size_t)(o_end - o)) return false;
+            const uint8_t *s = o - dist;
+            if (dist >= 8 && (size_t)(o_end - o) >= len + 8) {     // 8 bytes at a time (may write up to 7 bytes past the match, inside the buffer)
+                uint8_t *q = o;
+                const uint8_t *const qe = o + len;
+                do { uint64_t w; memcpy(&w, s, 8); memcpy(q, &w, 8); s += 8; q += 8; } while (q < qe);
+            } else if (dist == 1) memset(o, *s, len);
+            else for (size_t i = 0; i < len; i++) o[i] = s[i];
+            o += len;
+        }
+        if (b.overrun()) return false;
+    }
+    if (o != o_end) return false;
+    // Adler-32 of the decoded data, big-endian, right after the last (byte-aligned) deflate byte
+    const uint8_t *tail = b.in - (b.cnt >> 3);
+    if (tail > b.in_end) return false;
+    const uint8_t *ad = in + in_len - 4;
+    const uint32_t want = ((uint32_t)ad[0] << 24) | ((uint32_t)ad[1] << 16) | ((uint32_t)ad[2] << 8) | ad[3];
+    size_t left = out_len;
+    uLong a = adler32(0L, Z_NULL, 0);
+    const uint8_t *p = out;
+    while (left) { const uInt n = left > (1u << 30) ? (1u << 30) : (uInt)left; a = adler32(a, p, n); p += n; left -= n; }
+    return (uint32_t)a == want;
+}
+
+}  // namespace rr_inflate

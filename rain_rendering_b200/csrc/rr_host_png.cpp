@@ -24,6 +24,7 @@
 #include <vector>
 #include "../../include/rain_b200.h"
 #include "rr_host_deflate.h"
+#include "rr_host_inflate.h"
 #include "rr_viridis.h"
 
 extern "C" void rr_set_error(const char *msg);
@@ -68,18 +69,16 @@ int decode(const char *path, Image *img, bool header_only, int want_w = 0, int w
     size_t pos = 8;
     bool have_hdr = false;
     int color = 0, interlace = 0;
-    std::vector<unsigned char> raw;
-    z_stream zs;
-    memset(&zs, 0, sizeof(zs));
-    bool z_open = false, z_done = false;
+    std::vector<unsigned char> raw, zdata;
     size_t stride = 0;
     int ret = RR_ERR_ARG;
+    bool have_end = false;
     while (pos + 12 <= file.size()) {
         uint32_t len = be32(&file[pos]);
         const unsigned char *type = &file[pos + 4], *data = &file[pos + 8];
         if (pos + 12 + (size_t)len > file.size()) break;
         if (!memcmp(type, "IHDR", 4)) {
-            if (len != 13) break;
+            if (len != 13 || have_hdr) break;
             img->w = (int)be32(data); img->h = (int)be32(data + 4);
             img->depth = data[8]; color = data[9]; interlace = data[12];
             if (img->w <= 0 || img->h <= 0 || img->w > 65536 || img->h > 65536) break;
@@ -94,25 +93,34 @@ int decode(const char *path, Image *img, bool header_only, int want_w = 0, int w
             }
             stride = (size_t)img->w * img->channels * (img->depth / 8);
             if ((stride + 1) * (size_t)img->h + 1 > 0xfffffff0u) { ret = RR_PNG_UNSUPPORTED; break; }              // zlib counts in 32 bits
-            raw.resize((stride + 1) * (size_t)img->h + 1);      // one spare byte: the stream must END (Adler-32 verified), not just fill the image
-            if (inflateInit(&zs) != Z_OK) break;
-            z_open = true;
-            zs.next_out = raw.data();
-            zs.avail_out = (uInt)raw.size();
+            zdata.reserve(file.size());
         } else if (!memcmp(type, "IDAT", 4)) {
-            if (!have_hdr || !z_open) break;
-            zs.next_in = const_cast<unsigned char *>(data);
-            zs.avail_in = len;
-            int r = inflate(&zs, Z_NO_FLUSH);
-            if (r == Z_STREAM_END) z_done = true;
-            else if (r != Z_OK && r != Z_BUF_ERROR) break;
+            if (!have_hdr) break;
+            zdata.insert(zdata.end(), data, data + len);          // the stream may be cut into several chunks
         } else if (!memcmp(type, "IEND", 4)) {
-            if (z_open && z_done && zs.total_out == raw.size() - 1) ret = RR_OK;
+            have_end = true;
             break;
         }
         pos += 12 + (size_t)len;
     }
-    if (z_open) inflateEnd(&zs);
+    if (ret == RR_ERR_ARG && have_hdr && have_end && !zdata.empty()) {
+        // the whole zlib stream and its exact decoded size are known: one pass of the library's own decoder
+        // (rr_host_inflate.h); whatever it refuses gets a second opinion from zlib, so a valid file is never lost
+        const size_t zlen = zdata.size(), need = (stride + 1) * (size_t)img->h;
+        zdata.resize(zlen + 16, 0);                                // readable slack for the 8-byte bit-buffer refills
+        raw.resize(need + 1);
+        if (rr_inflate::zlib_decompress(zdata.data(), zlen, raw.data(), need)) ret = RR_OK;
+        else {
+            z_stream zs;
+            memset(&zs, 0, sizeof(zs));
+            if (inflateInit(&zs) == Z_OK) {
+                zs.next_in = zdata.data(); zs.avail_in = (uInt)zlen;
+                zs.next_out = raw.data(); zs.avail_out = (uInt)raw.size();   // one spare byte: the stream must END (Adler-32 verified), not just fill the image
+                if (inflate(&zs, Z_FINISH) == Z_STREAM_END && zs.total_out == need) ret = RR_OK;
+                inflateEnd(&zs);
+            }
+        }
+    }
     if (ret != RR_OK) return ret;
     // unfilter in place into img->px
     const int bpp = img->channels * (img->depth / 8);
@@ -412,6 +420,54 @@ extern "C" int rr_host_png_write_batch_u16(int n, const char *const *image_paths
     });
     if (bad.load()) rr_set_error("rr_host_png_write_batch_u16: some files could not be written");
     return bad.load();
+}
+
+// Frames finished zlib streams (made on the GPU, rr_frame_io.out_png_*) as 8-bit RGBA PNG files.
+extern "C" int rr_host_png_write_streams(int n, const char *const *paths, const uint8_t *streams, size_t stride, const uint32_t *sizes,
+                                         int W, int H, int n_threads) {
+    if (n < 0 || W <= 0 || H <= 0 || (n > 0 && (!paths || !streams || !sizes))) { rr_set_error("rr_host_png_write_streams: bad arguments"); return RR_ERR_ARG; }
+    std::atomic<int> bad(0);
+    parallel_for(n, n_threads, [&](int i) {
+        int r = RR_ERR_ARG;
+        try {
+            if (paths[i] && sizes[i] >= 8 && sizes[i] <= stride) {
+                const unsigned char *z = streams + (size_t)i * stride;
+                std::vector<unsigned char> out;
+                out.reserve((size_t)sizes[i] + 128);
+                out.insert(out.end(), kSig, kSig + 8);
+                unsigned char ihdr[13];
+                put32(ihdr, (uint32_t)W); put32(ihdr + 4, (uint32_t)H);
+                ihdr[8] = 8; ihdr[9] = 6; ihdr[10] = ihdr[11] = ihdr[12] = 0;
+                chunk(&out, "IHDR", ihdr, 13);
+                chunk(&out, "IDAT", z, sizes[i]);
+                chunk(&out, "IEND", nullptr, 0);
+                std::string tmp = std::string(paths[i]) + ".part";
+                FILE *f = fopen(tmp.c_str(), "wb");
+                if (f) {
+                    bool ok = fwrite(out.data(), 1, out.size(), f) == out.size();
+                    ok = (fclose(f) == 0) && ok;
+                    if (ok && rename(tmp.c_str(), paths[i]) == 0) r = RR_OK;
+                    else remove(tmp.c_str());
+                }
+            }
+        } catch (...) { r = RR_ERR_ARG; }
+        if (r != RR_OK) bad.fetch_add(1);
+    });
+    if (bad.load()) rr_set_error("rr_host_png_write_streams: some files could not be written");
+    return bad.load();
+}
+
+// test hook of rr_host_inflate.h: zlib stream -> exactly out_len bytes (RR_ERR_ARG for anything malformed or of another size)
+extern "C" int rr_host_zlib_decompress_fast(const uint8_t *z, size_t zlen, uint8_t *out, size_t out_len) {
+    if (!z || (!out && out_len)) { rr_set_error("rr_host_zlib_decompress_fast: bad arguments"); return RR_ERR_ARG; }
+    try {
+        std::vector<unsigned char> buf(z, z + zlen);
+        buf.resize(zlen + 16, 0);
+        std::vector<unsigned char> tmp(out_len + 8);
+        if (!rr_inflate::zlib_decompress(buf.data(), zlen, tmp.data(), out_len)) return RR_ERR_ARG;
+        if (out_len) memcpy(out, tmp.data(), out_len);
+    } catch (...) { return RR_ERR_ARG; }
+    return RR_OK;
 }
 
 // test hook of rr_host_deflate.h: data -> zlib stream (any inflate must reproduce data)

@@ -5,6 +5,41 @@
 #include <stdio.h>
 
 // ------------------------------------------------------------------------------------------
+// TMA (cp.async.bulk[.tensor]) + mbarrier, inline PTX for sm_100a
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");       // visible to the async proxy before a copy signals it
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "RR_MBAR_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra RR_MBAR_DONE;\n"
+        "bra RR_MBAR_WAIT;\n"
+        "RR_MBAR_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one box of a 3-D tensor map -> shared memory; completion (box bytes) is signalled on the mbarrier
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, int x, int y, int z, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
+                 "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+                 : "memory");
+}
+// bytes (a multiple of 16, both addresses 16-byte aligned) global -> shared memory
+__device__ __forceinline__ void bulk_load_1d(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes),
+                 "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
 // constants (uploaded once by rr_upload_constants)
 // ------------------------------------------------------------------------------------------
 __constant__ double c_k64[25];      // cv2.getGaussianKernel(25, 25, CV_64F)   (add_attenuation.py:79-80)
@@ -319,13 +354,23 @@ cudaError_t rr_launch_stats(const rr_frame_bufs &b, int F, int W, int H, int ren
 // Sliding-window separable passes: each thread produces 4 consecutive outputs from 28 inputs held in
 // registers; every output still accumulates its 25 products in the reference order.
 // ROW: inputs are consecutive padded columns starting at a multiple of 4; else rows STRIDE apart.
-template <bool ROW, int STRIDE>
+// ROW: 0 = a column (elements STRIDE apart), 1 = a row in the padded layout, 2 = a row of the dense tile TMA delivered
+// (16-byte aligned: seven 128-bit loads; lanes 4 elements apart then touch consecutive quads -- conflict free)
+template <int ROW, int STRIDE>
 __device__ __forceinline__ void fog_taps_f32(const float *in, double acc[4]) {
     // exact float32 products in float64, ascending taps.  The product of two float32 values is exact in
     // float64, so fma(k, v, a) == a + k * v bit for bit: one instruction per tap instead of two.
     double v[28];
+    if (ROW == 2) {
 #pragma unroll
-    for (int i = 0; i < 28; i++) v[i] = (double)in[ROW ? FOG_PAD(i) : i * STRIDE];
+        for (int q = 0; q < 7; q++) {
+            const float4 t = ((const float4 *)in)[q];
+            v[4 * q] = (double)t.x; v[4 * q + 1] = (double)t.y; v[4 * q + 2] = (double)t.z; v[4 * q + 3] = (double)t.w;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 28; i++) v[i] = (double)in[ROW ? FOG_PAD(i) : i * STRIDE];
+    }
 #pragma unroll
     for (int o = 0; o < 4; o++) {
         double a = c_k32d[0] * v[o];
@@ -357,17 +402,55 @@ __global__ void k_fog_acs(const double *bg_sum, double *acs, rr_fog_consts fc, d
     acs[i] = fc.beta_hg * irr_mean;
 }
 
-__global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, rr_fog_consts fc, int W, int H) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float *E = (float *)smem_raw;                         // [FOG_EH][FOG_ES]  extinction on the haloed tile
-    float *FH = E + FOG_EH * FOG_ES;                      // [FOG_EH][FOG_FS]  float32 row pass of f_ext
+// The TMA form of the fog stage reads the extinction from a REFLECT-PADDED plane: k_fext_pad materialises the
+// BORDER_REFLECT_101 halo (FOG_R pixels on every side) once, with a row pitch that is a multiple of 16 bytes, so that
+// every haloed tile of k_fog -- border tiles included -- is one box of a tensor map and no thread forms a reflected
+// index.  Element (py, px) of the plane is f_ext(r101(py - FOG_R), r101(px - FOG_R)); pitch columns beyond W + 2 FOG_R
+// are zero (tiles never consume them).  With uint16 depth the exponential is a 65536-entry table (k_fext_lut, built
+// per camera): the correctly rounded float32 value of every possible sample.
+__global__ void __launch_bounds__(256) k_fext_lut(float *lut, float neg_beta32) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 65536) return;
+    const float metres = __fdiv_rn((float)i, 256.f);
+    const float d = __fdiv_rn(metres, 1000.f);
+    lut[i] = (float)exp((double)__fmul_rn(neg_beta32, d));
+}
+
+template <bool U16>
+__global__ void __launch_bounds__(256) k_fext_pad(const void *depth, const float *lut, float *fextp, float neg_beta32, int W, int H, int Wp, int Hp) {
+    const int f = blockIdx.z, py = blockIdx.y;
+    const int px = blockIdx.x * blockDim.x + threadIdx.x;
+    if (px >= Wp) return;
+    float v = 0.f;
+    if (px < W + 2 * FOG_R) {
+        const size_t src = ((size_t)f * H + r101(py - FOG_R, H)) * W + r101(px - FOG_R, W);
+        if (U16) v = lut[((const uint16_t *)depth)[src]];
+        else {
+            const float d = __fdiv_rn(((const float *)depth)[src], 1000.f);
+            v = (float)exp((double)__fmul_rn(neg_beta32, d));
+        }
+    }
+    fextp[((size_t)f * Hp + py) * Wp + px] = v;
+}
+
+#define FOG_ED 88             // row stride of the dense extinction tile (== FOG_EW, 352 bytes)
+#define FOG_BYTES_A_TMA (sizeof(float) * FOG_EH * (FOG_ED + FOG_FS))
+
+template <bool TMA>
+__global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, rr_fog_consts fc, int W, int H, const __grid_constant__ CUtensorMap fmap) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int ES = TMA ? FOG_ED : FOG_ES;
+    constexpr size_t BYTES_A = TMA ? FOG_BYTES_A_TMA : FOG_BYTES_A;
+    float *E = (float *)smem_raw;                         // [FOG_EH][ES]      extinction on the haloed tile (TMA: dense, as the box arrives)
+    float *FH = E + FOG_EH * ES;                          // [FOG_EH][FOG_FS]  float32 row pass of f_ext
     double *LH = (double *)smem_raw;                      // [FOG_EH][FOG_FS]  float64 row pass; reuses E + FH once both are consumed
-    double *D = (double *)(smem_raw + FOG_BYTES_A);       // [FOG_EH][FOG_LS]  1 - f_ext (float32 op, widened)
-    uint8_t *IB = smem_raw + FOG_BYTES_A + FOG_BYTES_B;   // [FOG_TY][FOG_TX * 3]  the tile's image bytes
+    double *D = (double *)(smem_raw + BYTES_A);           // [FOG_EH][FOG_LS]  1 - f_ext (float32 op, widened)
+    uint8_t *IB = smem_raw + BYTES_A + FOG_BYTES_B;       // [FOG_TY][FOG_TX * 3]  the tile's image bytes
+    __shared__ __align__(8) unsigned long long tile_bar;
     const int f = blockIdx.z;
     const int x0 = blockIdx.x * FOG_TX, y0 = blockIdx.y * FOG_TY;
     const int tid = threadIdx.x;
-    const float *fext = b.fext + (size_t)f * W * H;
+    const float *fext = b.fext + (size_t)f * W * H;          // tight plane (the non-TMA form)
     const uint8_t *bgr = b.bgr + (size_t)f * W * H * 3;
     double Acs[3];
 #pragma unroll
@@ -382,7 +465,44 @@ __global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, 
     // bytes, which wait in shared memory for the compose step at the very end.  A warp takes whole rows (the
     // reflected row index is warp-uniform, the reflected column indices are formed once per lane), so an element
     // costs a handful of instructions of index arithmetic.
-    {
+    if (TMA) {
+        // one elected thread asks the TMA unit for the haloed extinction tile (88 x 56 float32, one box of the padded
+        // plane) while all threads fetch the tile's image bytes; then everybody waits on the mbarrier
+        if (tid == 0) mbar_init(&tile_bar, 1);
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&tile_bar, (unsigned)(sizeof(float) * FOG_EH * FOG_ED));
+            tma_load_3d(E, &fmap, x0, y0, b.frame0 + f, &tile_bar);
+        }
+        constexpr int NW = FOG_THREADS / 32, BR = FOG_TY / NW, BC = FOG_TX * 3 / 32;
+        const int lane = tid & 31, warp = tid >> 5;
+        if (!b.bgf) {
+            uint8_t bv[BR][BC];
+#pragma unroll
+            for (int q = 0; q < BR; q++) {
+                const int row = warp + NW * q;
+                const bool rok = y0 + row < H;
+                const uint8_t *src = bgr + ((size_t)(rok ? y0 + row : 0) * W + x0) * 3;
+#pragma unroll
+                for (int j = 0; j < BC; j++) {
+                    const int col = lane + 32 * j;
+                    bv[q][j] = (rok && x0 * 3 + col < W * 3) ? src[col] : (uint8_t)0;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < BR; q++)
+#pragma unroll
+                for (int j = 0; j < BC; j++) IB[(warp + NW * q) * (FOG_TX * 3) + lane + 32 * j] = bv[q][j];
+        }
+        mbar_wait(&tile_bar, 0);
+        // 1 - f_ext of the haloed tile, widened, into the padded float64 layout of the row pass
+        for (int i = tid; i < FOG_EH * FOG_EW; i += FOG_THREADS) {
+            const int ey = i / FOG_EW, ex = i - ey * FOG_EW;
+            double d = (double)(1.0f - E[ey * FOG_ED + ex]);                // (1 - f_ext) is a float32 op in numpy (:71)
+            if (linear) d = d < 0 ? 0 : (d > 1 ? 1 : d);                    // clip(A d, 0, 1) = A clip(d, 0, 1) for 0 <= A <= 1
+            D[ey * FOG_LS + FOG_PAD(ex)] = d;
+        }
+    } else {
         constexpr int NW = FOG_THREADS / 32;                                // warps
         constexpr int ER = (FOG_EH + NW - 1) / NW;                          // extinction rows per warp
         constexpr int EC = (FOG_EW + 31) / 32;                              // column steps per row
@@ -449,7 +569,8 @@ __global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, 
     for (int i = tid; i < FOG_EH * (FOG_TX / 4); i += FOG_THREADS) {
         int ey = i / (FOG_TX / 4), ox = (i - ey * (FOG_TX / 4)) * 4;
         double a[4];
-        fog_taps_f32<true, 0>(E + ey * FOG_ES + FOG_PAD(ox), a);
+        if (TMA) fog_taps_f32<2, 0>(E + ey * FOG_ED + ox, a);
+        else fog_taps_f32<1, 0>(E + ey * FOG_ES + FOG_PAD(ox), a);
 #pragma unroll
         for (int o = 0; o < 4; o++) FH[ey * FOG_FS + FOG_PAD(ox) + o] = (float)a[o];
     }
@@ -460,10 +581,10 @@ __global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, 
     float fb[8];
     {
         double a[4];
-        fog_taps_f32<false, FOG_FS>(FH + cy0 * FOG_FS + pcx, a);
+        fog_taps_f32<0, FOG_FS>(FH + cy0 * FOG_FS + pcx, a);
 #pragma unroll
         for (int o = 0; o < 4; o++) fb[o] = (float)a[o];
-        fog_taps_f32<false, FOG_FS>(FH + (cy0 + 4) * FOG_FS + pcx, a);
+        fog_taps_f32<0, FOG_FS>(FH + (cy0 + 4) * FOG_FS + pcx, a);
 #pragma unroll
         for (int o = 0; o < 4; o++) fb[4 + o] = (float)a[o];
     }
@@ -532,18 +653,36 @@ __global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, 
     }
 }
 
-cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, cudaStream_t st) {
+cudaError_t rr_launch_fext_lut(float *lut, float neg_beta32, cudaStream_t st) {
+    k_fext_lut<<<256, 256, 0, st>>>(lut, neg_beta32);
+    return cudaGetLastError();
+}
+
+cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, const CUtensorMap *fmap, cudaStream_t st) {
     static_assert(FOG_ES >= FOG_PAD(FOG_EW - 1) + 1 && FOG_LS >= FOG_PAD(FOG_EW - 1) + 1 && FOG_FS >= FOG_PAD(FOG_TX - 1) + 1, "fog strides");
-    static_assert(sizeof(double) * FOG_EH * FOG_FS <= FOG_BYTES_A, "LH must fit in the E + FH region");
-    size_t smem = FOG_BYTES_A + FOG_BYTES_B + FOG_TY * FOG_TX * 3;
-    {
-        size_t n = (size_t)F * W * H;
-        if (b.depth_u16) k_fext<true><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.depth, b.fext, fc.neg_beta32, n);
-        else k_fext<false><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.depth, b.fext, fc.neg_beta32, n);
-        k_fog_acs<<<(F * 4 + 127) / 128, 128, 0, st>>>(b.bg_sum, b.acs, fc, (double)W * (double)H, F);
-    }
+    static_assert(sizeof(double) * FOG_EH * FOG_FS <= FOG_BYTES_A && sizeof(double) * FOG_EH * FOG_FS <= FOG_BYTES_A_TMA, "LH must fit in the E + FH region");
+    static_assert(FOG_ED == FOG_EW && (FOG_ED * sizeof(float)) % 16 == 0 && FOG_BYTES_A_TMA % 8 == 0, "dense tile layout");
+    k_fog_acs<<<(F * 4 + 127) / 128, 128, 0, st>>>(b.bg_sum, b.acs, fc, (double)W * (double)H, F);
     dim3 grid((W + FOG_TX - 1) / FOG_TX, (H + FOG_TY - 1) / FOG_TY, F);
-    k_fog<<<grid, FOG_THREADS, smem, st>>>(b, fc, W, H);
+    if (fmap) {
+        dim3 g((b.fext_Wp + 255) / 256, b.fext_Hp, F);
+        float *dst = b.fext + (size_t)b.frame0 * b.fext_Hp * b.fext_Wp;     // the tensor map spans the whole plane stack: frame0 + f
+        if (b.depth_u16) k_fext_pad<true><<<g, 256, 0, st>>>(b.depth, b.fext_lut, dst, fc.neg_beta32, W, H, b.fext_Wp, b.fext_Hp);
+        else k_fext_pad<false><<<g, 256, 0, st>>>(b.depth, b.fext_lut, dst, fc.neg_beta32, W, H, b.fext_Wp, b.fext_Hp);
+        const size_t smem = FOG_BYTES_A_TMA + FOG_BYTES_B + FOG_TY * FOG_TX * 3;
+        k_fog<true><<<grid, FOG_THREADS, smem, st>>>(b, fc, W, H, *fmap);
+    } else {
+        const size_t n = (size_t)F * W * H;
+        float *dst = b.fext + (size_t)b.frame0 * W * H;
+        rr_frame_bufs v = b;
+        v.fext = dst;
+        if (b.depth_u16) k_fext<true><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.depth, dst, fc.neg_beta32, n);
+        else k_fext<false><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(b.depth, dst, fc.neg_beta32, n);
+        const size_t smem = FOG_BYTES_A + FOG_BYTES_B + FOG_TY * FOG_TX * 3;
+        CUtensorMap dummy;
+        memset(&dummy, 0, sizeof(dummy));
+        k_fog<false><<<grid, FOG_THREADS, smem, st>>>(v, fc, W, H, dummy);
+    }
     return cudaGetLastError();
 }
 
@@ -594,13 +733,13 @@ cudaError_t rr_launch_env_tile_flags(const uint8_t *env_written, uint8_t *tile_h
 }
 
 __global__ void __launch_bounds__(256) k_env_map(const uint8_t *bg8, const int32_t *env_src, const uint8_t *env_written,
-                                                 const uint8_t *tile_hole, uint8_t *env8, int H, int W_env, int npix_img) {
+                                                 const uint8_t *tile_hole, uint8_t *env8, int H, int W_env, int pitch, int npix_img) {
     __shared__ unsigned in[ENV_TY + 2 * ENV_R][ENV_TX + 2 * ENV_R];
     __shared__ unsigned short hp[ENV_TY + 2 * ENV_R][ENV_TX][3];
     const int f = blockIdx.z;
     const int x0 = blockIdx.x * ENV_TX, y0 = blockIdx.y * ENV_TY;
     const unsigned *img = (const unsigned *)bg8 + (size_t)f * npix_img;
-    unsigned *out = (unsigned *)env8 + (size_t)f * H * W_env;
+    unsigned *out = (unsigned *)env8 + (size_t)f * H * pitch;      // rows of `pitch` pixels (16-byte aligned for the bulk copies of k_env_prefix)
     const bool any_hole = tile_hole[blockIdx.y * gridDim.x + blockIdx.x] != 0;      // block-uniform, static per camera
     if (any_hole) {
         for (int i = threadIdx.x; i < (ENV_TY + 2 * ENV_R) * (ENV_TX + 2 * ENV_R); i += 256) {
@@ -630,12 +769,12 @@ __global__ void __launch_bounds__(256) k_env_map(const uint8_t *bg8, const int32
         int oy = i / ENV_TX, ox = i - oy * ENV_TX;
         int gy = y0 + oy, gx = x0 + ox;
         if (gy >= H || gx >= W_env) continue;
-        size_t pix = (size_t)gy * W_env + gx;
+        const size_t pix = (size_t)gy * W_env + gx, opix = (size_t)gy * pitch + gx;
         if (env_written[pix]) {
-            if (any_hole) out[pix] = in[oy + ENV_R][ox + ENV_R];
+            if (any_hole) out[opix] = in[oy + ENV_R][ox + ENV_R];
             else {
                 int sidx = env_src[pix];
-                out[pix] = sidx >= 0 ? img[sidx] : 0u;
+                out[opix] = sidx >= 0 ? img[sidx] : 0u;
             }
         } else {
             unsigned s0 = 0, s1 = 0, s2 = 0;
@@ -643,7 +782,7 @@ __global__ void __launch_bounds__(256) k_env_map(const uint8_t *bg8, const int32
             for (int t = 0; t < 15; t++) {
                 s0 += c_k15[t] * hp[oy + t][ox][0]; s1 += c_k15[t] * hp[oy + t][ox][1]; s2 += c_k15[t] * hp[oy + t][ox][2];
             }
-            out[pix] = ((s0 + 32768u) >> 16) | (((s1 + 32768u) >> 16) << 8) | (((s2 + 32768u) >> 16) << 16);
+            out[opix] = ((s0 + 32768u) >> 16) | (((s1 + 32768u) >> 16) << 8) | (((s2 + 32768u) >> 16) << 16);
         }
     }
 }
@@ -665,15 +804,20 @@ __global__ void __launch_bounds__(256) k_env_map(const uint8_t *bg8, const int32
 // shared staging of the tile's prefixes: 32 bytes per pixel plus 16 bytes after every 8 pixels, so that the
 // per-thread 16-byte stores (stride 272 bytes between lanes) and the per-warp linear reads are conflict free
 #define EP_STAGE_BYTES (EP_TILE * 32 + EP_THREADS * 16)
+// BULK: the row's pixels arrive by 1-D bulk copies (cp.async.bulk, the TMA unit) into two alternating shared-memory buffers,
+// signalled on mbarriers: tile t + 1 is in flight while tile t is converted.  Needs 16-byte aligned rows: env8 carries a
+// pitch of a multiple of 4 pixels.  Otherwise the register-staged form (global -> registers -> shared, next tile prefetched).
+template <bool BULK>
 __global__ void __launch_bounds__(EP_THREADS) k_env_prefix(const uint8_t *env8, const double *omega, double *pref, double *rowtot,
-                                                           int H, int W_env) {
-    __shared__ __align__(16) unsigned char s_bytes[EP_TILE * 4 + 32];
+                                                           int H, int W_env, int pitch) {
+    __shared__ __align__(128) unsigned char s_bytes[BULK ? 2 * EP_TILE * 4 : EP_TILE * 4 + 32];
+    __shared__ __align__(8) unsigned long long s_bar[2];
     __shared__ __align__(16) unsigned char s_stage[EP_STAGE_BYTES];
     __shared__ __align__(16) double s_toff[EP_THREADS][4];
     __shared__ double s_wtot[EP_WARPS][4];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r = blockIdx.x, f = blockIdx.y;
-    const uint8_t *row = env8 + ((size_t)f * H + r) * W_env * 4;          // pixels are 32-bit words (B, G, R, 0)
+    const uint8_t *row = env8 + ((size_t)f * H + r) * pitch * 4;          // pixels are 32-bit words (B, G, R, 0)
     const double *om = omega + (size_t)r * W_env;
     double2 *p2 = (double2 *)pref + ((size_t)f * H + r) * (W_env + 1) * 2;
     double cx = 0, cy = 0, cY = 0, cw = 0;          // carry: prefix of everything left of the tile
@@ -688,33 +832,51 @@ __global__ void __launch_bounds__(EP_THREADS) k_env_prefix(const uint8_t *env8, 
         *nvec = (*shift + n * 4 + 15) >> 4;
         return (const uint4 *)(gsrc - *shift);                             // the buffers carry 256 bytes of slack
     };
-    {
+    auto issue_bulk = [&](int t) {                  // one thread: tile t -> buffer t & 1
+        const int c0 = t * EP_TILE;
+        const unsigned bytes = (unsigned)(((pitch - c0) < EP_TILE ? (pitch - c0) : EP_TILE) * 4);
+        mbar_expect_tx(&s_bar[t & 1], bytes);
+        bulk_load_1d(s_bytes + (size_t)(t & 1) * EP_TILE * 4, row + (size_t)c0 * 4, bytes, &s_bar[t & 1]);
+    };
+    if (BULK) {
+        if (tid == 0) { mbar_init(&s_bar[0], 1); mbar_init(&s_bar[1], 1); }
+        __syncthreads();
+        if (tid == 0) issue_bulk(0);
+    } else {
         int sh0, nv0;
         const uint4 *g0 = tile_src(0, &sh0, &nv0);
 #pragma unroll
         for (int q = 0; q < EP_VEC; q++) { const int i = tid + q * EP_THREADS; pv[q] = i < nv0 ? g0[i] : make_uint4(0, 0, 0, 0); }
     }
-    for (int c0 = 0; c0 < W_env; c0 += EP_TILE) {
+    int tile = 0;
+    for (int c0 = 0; c0 < W_env; c0 += EP_TILE, tile++) {
         const int n = (W_env - c0) < EP_TILE ? (W_env - c0) : EP_TILE;
-        int shift, nvec;
-        tile_src(c0, &shift, &nvec);
+        int shift = 0, nvec = 0;
+        if (!BULK) tile_src(c0, &shift, &nvec);
         // the thread's solid angles are requested now and consumed after the staging barrier
         const int px0 = tid * EP_PER;
         double wv[EP_PER];
 #pragma unroll
         for (int k = 0; k < EP_PER; k++) wv[k] = (px0 + k < n) ? om[c0 + px0 + k] : 0.0;
         __syncthreads();                            // previous tile fully written out (s_stage, s_toff, s_bytes)
+        if (BULK) {
+            // the buffer of tile - 1 is free (barrier above): send tile + 1 into it, then wait for this tile's bytes
+            if (tid == 0 && c0 + EP_TILE < W_env) issue_bulk(tile + 1);
+            mbar_wait(&s_bar[tile & 1], (unsigned)((tile >> 1) & 1));
+        } else {
 #pragma unroll
-        for (int q = 0; q < EP_VEC; q++) { const int i = tid + q * EP_THREADS; if (i < nvec) ((uint4 *)s_bytes)[i] = pv[q]; }
-        if (c0 + EP_TILE < W_env) {
-            int sh1, nv1;
-            const uint4 *g1 = tile_src(c0 + EP_TILE, &sh1, &nv1);
+            for (int q = 0; q < EP_VEC; q++) { const int i = tid + q * EP_THREADS; if (i < nvec) ((uint4 *)s_bytes)[i] = pv[q]; }
+            if (c0 + EP_TILE < W_env) {
+                int sh1, nv1;
+                const uint4 *g1 = tile_src(c0 + EP_TILE, &sh1, &nv1);
 #pragma unroll
-            for (int q = 0; q < EP_VEC; q++) { const int i = tid + q * EP_THREADS; pv[q] = i < nv1 ? g1[i] : make_uint4(0, 0, 0, 0); }
+                for (int q = 0; q < EP_VEC; q++) { const int i = tid + q * EP_THREADS; pv[q] = i < nv1 ? g1[i] : make_uint4(0, 0, 0, 0); }
+            }
+            __syncthreads();
         }
-        __syncthreads();
         // ---- this thread's EP_PER consecutive pixels ----
-        const unsigned *wds = (const unsigned *)s_bytes + (shift >> 2) + px0;
+        const unsigned *wds = BULK ? (const unsigned *)(s_bytes + (size_t)(tile & 1) * EP_TILE * 4) + px0
+                                   : (const unsigned *)s_bytes + (shift >> 2) + px0;
         double sx = 0, sy = 0, sY = 0, sw_ = 0;
         unsigned char *st = s_stage + (size_t)tid * (EP_PER * 32 + 16);
 #pragma unroll
@@ -770,9 +932,10 @@ __global__ void __launch_bounds__(EP_THREADS) k_env_prefix(const uint8_t *env8, 
 }
 
 static cudaError_t launch_env_prefix(const uint8_t *env8, const double *omega, double *pref, double *rowtot, int F, int H, int W_env,
-                                     cudaStream_t st) {
+                                     int pitch, bool bulk, cudaStream_t st) {
     dim3 g3(H, F);
-    k_env_prefix<<<g3, EP_THREADS, 0, st>>>(env8, omega, pref, rowtot, H, W_env);
+    if (bulk) k_env_prefix<true><<<g3, EP_THREADS, 0, st>>>(env8, omega, pref, rowtot, H, W_env, pitch);
+    else k_env_prefix<false><<<g3, EP_THREADS, 0, st>>>(env8, omega, pref, rowtot, H, W_env, pitch);
     return cudaGetLastError();
 }
 
@@ -787,8 +950,8 @@ __global__ void k_ambient(const double *rowtot, double *ambient, int H) {
 
 cudaError_t rr_launch_env(const rr_frame_bufs &b, const rr_static_tabs &t, int F, int W, int H, int W_env, cudaStream_t st) {
     dim3 g2((W_env + ENV_TX - 1) / ENV_TX, (H + ENV_TY - 1) / ENV_TY, F);
-    k_env_map<<<g2, 256, 0, st>>>(b.bg8, t.env_src, t.env_written, t.env_tile_hole, b.env8, H, W_env, W * H);
-    cudaError_t e = launch_env_prefix(b.env8, t.omega, b.pref, b.rowtot, F, H, W_env, st);
+    k_env_map<<<g2, 256, 0, st>>>(b.bg8, t.env_src, t.env_written, t.env_tile_hole, b.env8, H, W_env, b.env_pitch, W * H);
+    cudaError_t e = launch_env_prefix(b.env8, t.omega, b.pref, b.rowtot, F, H, W_env, b.env_pitch, b.env_bulk != 0, st);
     if (e != cudaSuccess) return e;
     k_ambient<<<F, 32, 0, st>>>(b.rowtot, b.ambient, H);
     return cudaGetLastError();
@@ -844,7 +1007,8 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32, SETUP_MINB) k_setup(rr_frame
         sx = warp_sum(sx); sy = warp_sum(sy); sY = warp_sum(sY); sw = warp_sum(sw);
     }
     if (lane == 0) {
-        // the geometric half of the plan was written by k_plan; add the photometry, or withdraw the streak
+        // the geometric half of the plan was written by k_plan (which also withdrew degenerate streaks); add the photometry.
+        // Only the tint / diagnostic fields are written: the streak chain may be reading the geometry fields right now.
         rr_plan &P = b.plans[s];
         const bool ok = P.valid && m > 0;
         if (ok) {
@@ -857,11 +1021,6 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32, SETUP_MINB) k_setup(rr_frame
             double kb, kg, kr;
             rr_tint(fov_x, fov_y, drop_Y, &kb, &kg, &kr);
             P.kb = kb; P.kg = kg; P.kr = kr;
-        } else {
-            P.valid = 0;
-            P.pw = P.ph = P.bw = P.bh = 0;
-            b.sizes[s] = make_int4(0, 0, 0, 0);
-            b.boxes[s] = make_int4(0, 0, 0, 0);
         }
     }
 }
@@ -882,12 +1041,6 @@ __global__ void __launch_bounds__(128) k_plan(rr_frame_bufs b, rr_static_tabs t,
     if (ok) ok = rr_plan_patch(rec, cam, t.tex_h[rec.tex_idx], p);
     if (ok) p.tex_off = t.tex_off[rec.tex_idx];
     else p.pw = p.ph = p.bw = p.bh = 0;
-    p.valid = ok ? 1 : 0;
-    b.plans[s] = p;
-    long long g_, v_, a_; int vx0_, vw_;
-    plan_sizes(p, &g_, &v_, &a_, &vx0_, &vw_);
-    b.sizes[s] = make_int4((int)g_, (int)v_, (int)a_, 0);
-    b.boxes[s] = a_ > 0 ? make_int4(p.bx0, p.by0, p.bw, p.bh) : make_int4(0, 0, 0, 0);
     // field-of-view mask
     __align__(16) rr_fcp fc;
     memset(&fc, 0, sizeof(fc));
@@ -898,7 +1051,17 @@ __global__ void __launch_bounds__(128) k_plan(rr_frame_bufs b, rr_static_tabs t,
         const int m = npoly > 0 ? rr_clip_fov_polygon(px, py, npoly, cols, rows, fc.vx, fc.vy) : 0;
         fc.npts = m;
         if (m > 0) rr_fcp_prepare(fc, cols, rows);
+        else ok = false;                                  // degenerate field of view: the reference skips the streak (generator.py:185-189)
     }
+    // the streak's fate is settled here (k_setup only adds the photometry), so that the arena scan, the rasteriser and the
+    // blur can run beside the frame stages
+    if (!ok) p.pw = p.ph = p.bw = p.bh = 0;
+    p.valid = ok ? 1 : 0;
+    b.plans[s] = p;
+    long long g_, v_, a_; int vx0_, vw_;
+    plan_sizes(p, &g_, &v_, &a_, &vx0_, &vw_);
+    b.sizes[s] = make_int4((int)g_, (int)v_, (int)a_, 0);
+    b.boxes[s] = a_ > 0 ? make_int4(p.bx0, p.by0, p.bw, p.bh) : make_int4(0, 0, 0, 0);
     {
         const int4 *src = (const int4 *)&fc;
         int4 *dst = (int4 *)(b.fcp + s);
@@ -1022,6 +1185,7 @@ cudaError_t rr_launch_scan(const rr_frame_bufs &b, int n_streaks, cudaStream_t s
 // fl(v * w) == fl((v / 1024) * p) bit for bit (scaling by a power of two is exact): the kernel keeps the texture
 // look-up table pre-scaled by 2^-10 (lut[u] = u / 255.0 / 1024) and multiplies by the integer products.
 #define RAS_LUT_SCALE 0.0009765625
+#define RAS_UNIT (1.0 / 261120.0)     // 1 / (255 * 1024): what one unit of ras_sample_int's integer sum is worth
 __device__ __forceinline__ double ras_sample(const uint8_t *tex, int tw, int th, const double *lut, int X, int Y) {
     // rr_warp_affine_linear with the fixed-point coordinates already formed.  One code path for interior and
     // border samples (out-of-texture taps contribute the border value 0 with their weight, exactly the
@@ -1039,6 +1203,23 @@ __device__ __forceinline__ double ras_sample(const uint8_t *tex, int tw, int th,
     const double v2 = (x0ok & y1ok) ? lut[S[tw]] : 0.0;
     const double v3 = (x1ok & y1ok) ? lut[S[tw + 1]] : 0.0;
     return v0 * w0 + v1 * w1 + v2 * w2 + v3 * w3;
+}
+
+// The same sample as an exact integer: sum of texel * weight products, 0 .. 255 * 1024.  remapBilinear rounds each of its
+// four float64 products; the integer sum carries no rounding at all, and the two differ by < 3e-16 relative -- nine
+// orders of magnitude below the float32 ULP the output is held to.  It takes the dependent look-up-table loads, four
+// int -> double conversions and seven float64 operations per canvas pixel out of the chain loop.
+__device__ __forceinline__ int ras_sample_int(const uint8_t *tex, int tw, int th, int X, int Y) {
+    const int sx = X >> RR_INTER_BITS, sy = Y >> RR_INTER_BITS;
+    const bool x0ok = (unsigned)sx < (unsigned)tw, x1ok = (unsigned)(sx + 1) < (unsigned)tw;
+    const bool y0ok = (unsigned)sy < (unsigned)th, y1ok = (unsigned)(sy + 1) < (unsigned)th;
+    if (!((x0ok | x1ok) & (y0ok | y1ok))) return 0;
+    const int fx = X & (RR_INTER_TAB - 1), fy = Y & (RR_INTER_TAB - 1);
+    const uint8_t *S = tex + sy * tw + sx;
+    const int t00 = (x0ok & y0ok) ? S[0] : 0, t01 = (x1ok & y0ok) ? S[1] : 0;
+    const int t10 = (x0ok & y1ok) ? S[tw] : 0, t11 = (x1ok & y1ok) ? S[tw + 1] : 0;
+    const int top = (RR_INTER_TAB - fx) * t00 + fx * t01, bot = (RR_INTER_TAB - fx) * t10 + fx * t11;
+    return (RR_INTER_TAB - fy) * top + fy * bot;
 }
 
 __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs b, rr_static_tabs t, rr_cam_dev cam, int n) {
@@ -1113,14 +1294,25 @@ __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs 
                     if (c_hi > z_hi) c_hi = z_hi;
                     double buf = 0;
                     if (c_lo <= c_hi) {
-                        const double aF = tx.a_first, aM = tx.a_mid, aL = tx.a_last;
+                        // integer sample sums per weight class: the partial first / last column and the full-weight middle
+                        // (at most 512 columns of at most 255 * 1024 each: no overflow)
                         const int m_lo = tx.s_first, m_hi = tx.s_first + tx.n;       // full-weight columns [m_lo, m_hi)
-                        for (int c = c_lo; c <= c_hi; c++) {
-                            const double alpha = c < m_lo ? aF : (c >= m_hi ? aL : aM);
-                            const int X = (xr + adx[c]) >> (10 - RR_INTER_BITS);
-                            const int Y = (yr + bdx[c]) >> (10 - RR_INTER_BITS);
-                            buf += ras_sample(tex, tw, th, lut, X, Y) * alpha;
+                        int sF = 0, sM = 0, sL = 0;
+                        if (c_lo < m_lo) sF = ras_sample_int(tex, tw, th, (xr + adx[c_lo]) >> (10 - RR_INTER_BITS), (yr + bdx[c_lo]) >> (10 - RR_INTER_BITS));
+                        if (c_hi >= m_hi) sL = ras_sample_int(tex, tw, th, (xr + adx[c_hi]) >> (10 - RR_INTER_BITS), (yr + bdx[c_hi]) >> (10 - RR_INTER_BITS));
+                        const int a = c_lo < m_lo ? m_lo : c_lo, e = c_hi >= m_hi ? m_hi - 1 : c_hi;
+                        int c = a;
+                        for (; c + 1 <= e; c += 2) {             // two independent samples in flight
+                            const int X0 = (xr + adx[c]) >> (10 - RR_INTER_BITS), Y0 = (yr + bdx[c]) >> (10 - RR_INTER_BITS);
+                            const int X1 = (xr + adx[c + 1]) >> (10 - RR_INTER_BITS), Y1 = (yr + bdx[c + 1]) >> (10 - RR_INTER_BITS);
+                            const int v0 = ras_sample_int(tex, tw, th, X0, Y0), v1 = ras_sample_int(tex, tw, th, X1, Y1);
+                            sM += v0 + v1;
                         }
+                        if (c <= e) sM += ras_sample_int(tex, tw, th, (xr + adx[c]) >> (10 - RR_INTER_BITS), (yr + bdx[c]) >> (10 - RR_INTER_BITS));
+                        // texel / 255 / 1024 folded into one constant (RAS_UNIT), the three weights applied left to right
+                        buf = ((double)sF * RAS_UNIT) * (double)tx.a_first;
+                        buf += ((double)sM * RAS_UNIT) * (double)tx.a_mid;
+                        buf += ((double)sL * RAS_UNIT) * (double)tx.a_last;
                     }
                     CB[r * pw + dx] = buf;
                 }
@@ -1513,7 +1705,7 @@ cudaError_t rr_launch_epilogue(const rr_frame_bufs &b, int F, int W, int H, cuda
 }
 
 cudaError_t rr_launch_env_prefix_only(const rr_frame_bufs &b, const rr_static_tabs &t, int F, int H, int W_env, cudaStream_t st) {
-    cudaError_t e = launch_env_prefix(b.env8, t.omega, b.pref, b.rowtot, F, H, W_env, st);
+    cudaError_t e = launch_env_prefix(b.env8, t.omega, b.pref, b.rowtot, F, H, W_env, b.env_pitch, b.env_bulk != 0, st);
     if (e != cudaSuccess) return e;
     k_ambient<<<F, 32, 0, st>>>(b.rowtot, b.ambient, H);
     return cudaGetLastError();
@@ -1523,8 +1715,11 @@ cudaError_t rr_launch_env_prefix_only(const rr_frame_bufs &b, const rr_static_ta
 // The opt-in to more than 48 KB of dynamic shared memory is a per-DEVICE function attribute: every context sets it for
 // its own device in rr_create (a process-wide "done once" flag would leave the second GPU of a process without it).
 cudaError_t rr_prepare_device() {
-    cudaError_t e = cudaFuncSetAttribute(k_fog, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(k_fog<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)(FOG_BYTES_A + FOG_BYTES_B + FOG_TY * FOG_TX * 3));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_fog<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(FOG_BYTES_A_TMA + FOG_BYTES_B + FOG_TY * FOG_TX * 3));
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RAS_SMEM_BYTES);
 }

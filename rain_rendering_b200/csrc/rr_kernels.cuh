@@ -1,7 +1,9 @@
 // Kernel launch wrappers of the rain-rendering hot path (sm_100a).  See DESIGN.md for the
 // data layout; every wrapper launches on the given stream and returns the CUDA error state.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
+#include <string.h>
 #include "rr_streak_geom.h"
 
 struct rr_frame_bufs {
@@ -18,9 +20,15 @@ struct rr_frame_bufs {
     unsigned long long *chan_sum;  // [F][4]  sum of uint8 per channel (B,G,R), [3] unused
     double *rainy;             // [F][3][H][W] planar BGR float64
     uint8_t *bg8;              // [F][H][W][4] floor(rainy*255) as (B, G, R, 0): one 32-bit word per pixel
-    float *fext;               // [F][H][W] extinction exp(-beta d), written by k_fext for k_fog
+    float *fext;               // extinction exp(-beta d) of the WHOLE batch buffer (not shifted by sub-batch views: frame0 is):
+                               // TMA form [F][H + 24][Wp] reflect-padded planes (k_fext_pad), else [F][H][W] (k_fext)
+    int frame0;                // first frame of this (sub-)batch inside fext
+    int fext_Wp, fext_Hp;      // padded plane size (pitch a multiple of 4 floats = 16 bytes)
+    const float *fext_lut;     // [65536] exp table of the uint16 depth samples (per camera)
     float *fblur;              // [F][H][W] blurred extinction (debug / stage test)
-    uint8_t *env8;             // [F][H][W_env][4] final environment map, (B, G, R, 0) words
+    uint8_t *env8;             // [F][H][env_pitch][4] final environment map, (B, G, R, 0) words; env_pitch = W_env rounded up to 4 pixels
+    int env_pitch;             // pixels per row of env8 (16-byte aligned rows: k_env_prefix fetches them with bulk copies)
+    int env_bulk;              // k_env_prefix's row fetch: 1 = cp.async.bulk into two buffers, 0 = register-staged
     double *pref;              // [F][H][W_env+1][4] row prefix sums of (omega*x, omega*y, omega*Y, omega), interleaved
     double *rowtot;            // [F][H] row totals of omega*Y
     double *ambient;           // [F] sum over the map of omega*Y
@@ -85,7 +93,9 @@ cudaError_t rr_launch_env_tile_flags(const uint8_t *env_written, uint8_t *tile_h
 cudaError_t rr_launch_omega(int H_env, int W_env, double *omega, double *omega_pref, double *omega_total, cudaStream_t st);
 // per batch
 cudaError_t rr_launch_stats(const rr_frame_bufs &b, int F, int W, int H, int render_scale, double *bgf_out, cudaStream_t st);
-cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, cudaStream_t st);
+// fmap: tensor map of the padded extinction planes (TMA form of the tile load), or NULL for the register-staged form
+cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, const CUtensorMap *fmap, cudaStream_t st);
+cudaError_t rr_launch_fext_lut(float *lut, float neg_beta32, cudaStream_t st);
 cudaError_t rr_launch_env(const rr_frame_bufs &b, const rr_static_tabs &t, int F, int W, int H, int W_env, cudaStream_t st);
 // k_plan needs only the streak records: it may run on another stream while the frame stages (fog, environment map) run
 cudaError_t rr_launch_plan(const rr_frame_bufs &b, const rr_static_tabs &t, const rr_cam_dev &cam, int n_streaks, cudaStream_t st);

@@ -73,10 +73,21 @@ __host__ __device__ inline double sim_region(const sim_consts &c, double D, doub
     return a * (zmax * zmax * zmax - c.z0 * c.z0 * c.z0) / 3 + b * (zmax * zmax - c.z0 * c.z0) / 2;
 }
 
+// One candidate drop of one frame -> its imaged streak, or false when it is not imaged (outside the sensor, sub-pixel)
+__device__ bool sim_candidate(const sim_consts &c, const double *cdf, const double *lut_d, int64_t frame, int i, rr_sim_streak *res);
+
 __global__ void k_sim_frame(sim_consts c, const double *cdf, const double *lut_d, int64_t frame, int n_cand, int cap,
                             rr_sim_streak *out, int *counter) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_cand) return;
+    rr_sim_streak r;
+    if (!sim_candidate(c, cdf, lut_d, frame, i, &r)) return;
+    int slot = atomicAdd(counter, 1);
+    if (slot >= cap) return;
+    out[slot] = r;
+}
+
+__device__ bool sim_candidate(const sim_consts &c, const double *cdf, const double *lut_d, int64_t frame, int i, rr_sim_streak *res) {
     // diameter: inverse transform on the LUT (the binary scans a 50001-entry table linearly)
     double u = sim_u01(c.seed, (uint64_t)frame, i, 0);
     int lo = 0, hi = SIM_NLUT - 1;
@@ -85,7 +96,7 @@ __global__ void k_sim_frame(sim_consts c, const double *cdf, const double *lut_d
     double v = sim_v_terminal(D);
     double zmax;
     sim_region(c, D, v, &zmax);
-    if (zmax <= c.z0) return;
+    if (zmax <= c.z0) return false;
     // position uniform in the region: depth with density proportional to the cross-section area
     double a = (c.W + 2 * c.margin_x) * c.H / (c.f_px * c.f_px), b = (c.W + 2 * c.margin_x) / c.f_px * (v * c.T);
     double F0 = a * c.z0 * c.z0 * c.z0 / 3 + b * c.z0 * c.z0 / 2, F1 = a * zmax * zmax * zmax / 3 + b * zmax * zmax / 2;
@@ -113,15 +124,13 @@ __global__ void k_sim_frame(sim_consts c, const double *cdf, const double *lut_d
         z -= c.vcam * c.dt;             // camera moves forward: relative drift towards the camera
     }
     double x2 = x, y2 = y, z2 = z;
-    if (z2 <= 1e-3) return;
+    if (z2 <= 1e-3) return false;
     double u1 = c.W / 2 + c.f_px * x1 / z1, v1 = c.H / 2 + c.f_px * y1 / z1;     // y up
     double u2 = c.W / 2 + c.f_px * x2 / z2, v2 = c.H / 2 + c.f_px * y2 / z2;
     bool in1 = u1 >= 0 && u1 < c.W && v1 >= 0 && v1 < c.H, in2 = u2 >= 0 && u2 < c.W && v2 >= 0 && v2 < c.H;
-    if (!(in1 || in2)) return;                                                  // IsIn()
+    if (!(in1 || in2)) return false;                                            // IsIn()
     double w1 = D * c.f_px / z1, w2 = D * c.f_px / z2;
-    if ((w1 > w2 ? w1 : w2) < c.wmin) return;                                   // IsFoglike()
-    int slot = atomicAdd(counter, 1);
-    if (slot >= cap) return;
+    if ((w1 > w2 ? w1 : w2) < c.wmin) return false;                             // IsFoglike()
     rr_sim_streak r;
     r.wp1[0] = x1; r.wp1[1] = y1; r.wp1[2] = -z1;
     r.wp2[0] = x2; r.wp2[1] = y2; r.wp2[2] = -z2;
@@ -129,19 +138,18 @@ __global__ void k_sim_frame(sim_consts c, const double *cdf, const double *lut_d
     r.ip1[0] = u1; r.ip1[1] = v1; r.ip2[0] = u2; r.ip2[1] = v2;
     r.iw1 = w1; r.iw2 = w2;
     r.pid = i;
-    out[slot] = r;
+    *res = r;
+    return true;
 }
 
 struct rr_context;
 extern "C" int rr_sim_device_of(rr_context *c);   // rr_api.cu
 extern "C" void rr_set_error(const char *msg);
 
-extern "C" int rr_simulate_particles(rr_context *ctx, const rr_sim_params *p, int64_t first_frame, int n_frames, int max_per_frame,
-                                     rr_sim_streak *out, int32_t *counts, double *expected_per_frame) {
-    if (!ctx || !p || !out || !counts || n_frames <= 0 || max_per_frame <= 0) { rr_set_error("rr_simulate_particles: bad arguments"); return RR_ERR_ARG; }
+// ---- host-side preparation shared by the two entry points ---------------------------------------------------------------
+static int sim_prepare(const rr_sim_params *p, sim_consts *cc, std::vector<double> *cdf_out, std::vector<double> *d_out, double *mean_out) {
     if (p->W <= 0 || p->H <= 0 || p->focal_m <= 0 || p->pix_size_m <= 0 || p->fallrate_mmh <= 0 || p->sim_hz <= 0 || p->z_far <= p->z_near ||
         p->d_max_mm <= p->d_min_mm || p->min_width_px <= 0) { rr_set_error("rr_simulate_particles: invalid parameters"); return RR_ERR_ARG; }
-    if (cudaSetDevice(rr_sim_device_of(ctx)) != cudaSuccess) { rr_set_error("rr_simulate_particles: cudaSetDevice failed"); return RR_ERR_CUDA; }
     sim_consts c;
     c.f_px = p->focal_m / p->pix_size_m; c.W = p->W; c.H = p->H; c.T = p->exposure_ms / 1000.0;
     c.dt = (double)(float)(1.0 / p->sim_hz);
@@ -171,10 +179,37 @@ extern "C" int rr_simulate_particles(rr_context *ctx, const rr_sim_params *p, in
         w[i] = K * N / v * dD_mm * vol;
         mean += w[i];
     }
-    if (expected_per_frame) *expected_per_frame = mean;
     double acc = 0;
     for (int i = 0; i < SIM_NLUT; i++) { acc += w[i]; cdf[i] = mean > 0 ? acc / mean : 1.0; }
     cdf[SIM_NLUT - 1] = 1.0;
+    *cc = c; *cdf_out = cdf; *d_out = d; *mean_out = mean;
+    return RR_OK;
+}
+
+// candidates of one frame: Poisson count (normal approximation above 64, Knuth below), counter-based
+static int sim_poisson(const sim_consts &c, double mean, int64_t frame) {
+    int n_cand;
+    if (mean > 64) {
+        double u1 = sim_u01(c.seed, (uint64_t)frame, 0xFFFFFFFFull, 7), u2 = sim_u01(c.seed, (uint64_t)frame, 0xFFFFFFFFull, 8);
+        double g = sqrt(-2 * log(u1)) * cos(2 * SIM_PI * u2);
+        n_cand = (int)lrint(mean + sqrt(mean) * g);
+    } else {
+        double L = exp(-mean), pacc = 1; n_cand = -1; uint64_t k = 0;
+        do { n_cand++; pacc *= sim_u01(c.seed, (uint64_t)frame, 0xFFFFFFFFull, 9 + k++); } while (pacc > L);
+    }
+    return n_cand < 0 ? 0 : n_cand;
+}
+
+extern "C" int rr_simulate_particles(rr_context *ctx, const rr_sim_params *p, int64_t first_frame, int n_frames, int max_per_frame,
+                                     rr_sim_streak *out, int32_t *counts, double *expected_per_frame) {
+    if (!ctx || !p || !out || !counts || n_frames <= 0 || max_per_frame <= 0) { rr_set_error("rr_simulate_particles: bad arguments"); return RR_ERR_ARG; }
+    if (cudaSetDevice(rr_sim_device_of(ctx)) != cudaSuccess) { rr_set_error("rr_simulate_particles: cudaSetDevice failed"); return RR_ERR_CUDA; }
+    sim_consts c;
+    std::vector<double> cdf, d;
+    double mean = 0;
+    int rc = sim_prepare(p, &c, &cdf, &d, &mean);
+    if (rc != RR_OK) return rc;
+    if (expected_per_frame) *expected_per_frame = mean;
     double *d_cdf = nullptr, *d_d = nullptr; rr_sim_streak *d_out = nullptr; int *d_cnt = nullptr;
     cudaError_t e;
     if ((e = cudaMalloc(&d_cdf, sizeof(double) * SIM_NLUT)) != cudaSuccess || (e = cudaMalloc(&d_d, sizeof(double) * SIM_NLUT)) != cudaSuccess ||
@@ -183,20 +218,9 @@ extern "C" int rr_simulate_particles(rr_context *ctx, const rr_sim_params *p, in
     }
     cudaMemcpy(d_cdf, cdf.data(), sizeof(double) * SIM_NLUT, cudaMemcpyHostToDevice);
     cudaMemcpy(d_d, d.data(), sizeof(double) * SIM_NLUT, cudaMemcpyHostToDevice);
-    int rc = RR_OK;
     for (int f = 0; f < n_frames && rc == RR_OK; f++) {
         int64_t frame = first_frame + f;
-        // Poisson count (normal approximation above 64, Knuth below), counter-based
-        int n_cand;
-        if (mean > 64) {
-            double u1 = sim_u01(c.seed, (uint64_t)frame, 0xFFFFFFFFull, 7), u2 = sim_u01(c.seed, (uint64_t)frame, 0xFFFFFFFFull, 8);
-            double g = sqrt(-2 * log(u1)) * cos(2 * SIM_PI * u2);
-            n_cand = (int)lrint(mean + sqrt(mean) * g);
-        } else {
-            double L = exp(-mean), pacc = 1; n_cand = -1; uint64_t k = 0;
-            do { n_cand++; pacc *= sim_u01(c.seed, (uint64_t)frame, 0xFFFFFFFFull, 9 + k++); } while (pacc > L);
-        }
-        if (n_cand < 0) n_cand = 0;
+        const int n_cand = sim_poisson(c, mean, frame);
         cudaMemset(d_cnt, 0, sizeof(int));
         if (n_cand > 0) k_sim_frame<<<(n_cand + 127) / 128, 128>>>(c, d_cdf, d_d, frame, n_cand, max_per_frame, d_out, d_cnt);
         int cnt = 0;
@@ -207,6 +231,211 @@ extern "C" int rr_simulate_particles(rr_context *ctx, const rr_sim_params *p, in
     }
     cudaFree(d_cdf); cudaFree(d_d); cudaFree(d_out); cudaFree(d_cnt);
     return rc;
+}
+
+// ---- device-resident form: simulator -> loader arithmetic -> in-frame filter -> RNG draws, records stay in HBM ----------
+// One launch simulates every candidate of every frame and turns the imaged ones into rr_streak_rec exactly as
+// DBManager.load_streaks_from_xml would from the simulator's XML (common/bad_weather.py:200-238; same float64 operations in
+// the same order as rain_rendering_b200/streaks.py: records_from_raw) and applies the in-frame filter (generator.py:413-420);
+// a block per frame then compacts the survivors in candidate (= pid) order and one thread walks them with the frame's NumPy
+// legacy MT19937 stream (np.random.seed(frame index), generator.py:318): randint for the texture (bad_weather.py:252-264),
+// normal for the wind noise of non-Big drops (generator.py:136; with noise_std == 0 only its draws are consumed).
+struct sim_mt {                       // the NumPy legacy stream (csrc/rr_host.cpp holds the host twin)
+    uint32_t *key;
+    int pos, has_gauss;
+    double gauss;
+    __device__ void seed(uint32_t s) {
+        for (int i = 0; i < 624; i++) { key[i] = s; s = 1812433253u * (s ^ (s >> 30)) + (uint32_t)i + 1u; }
+        pos = 624; has_gauss = 0; gauss = 0.0;
+    }
+    __device__ void gen() {
+        const uint32_t N = 624, M = 397, A = 0x9908b0dfu, UP = 0x80000000u, LO = 0x7fffffffu;
+        uint32_t y, i;
+        for (i = 0; i < N - M; i++) { y = (key[i] & UP) | (key[i + 1] & LO); key[i] = key[i + M] ^ (y >> 1) ^ ((0u - (y & 1u)) & A); }
+        for (; i < N - 1; i++) { y = (key[i] & UP) | (key[i + 1] & LO); key[i] = key[i + M - N] ^ (y >> 1) ^ ((0u - (y & 1u)) & A); }
+        y = (key[N - 1] & UP) | (key[0] & LO);
+        key[N - 1] = key[M - 1] ^ (y >> 1) ^ ((0u - (y & 1u)) & A);
+        pos = 0;
+    }
+    __device__ uint32_t next32() {
+        if (pos == 624) gen();
+        uint32_t y = key[pos++];
+        y ^= (y >> 11); y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= (y >> 18);
+        return y;
+    }
+    __device__ double next_double() {
+        const int32_t a = (int32_t)(next32() >> 5), b = (int32_t)(next32() >> 6);
+        return (a * 67108864.0 + b) / 9007199254740992.0;
+    }
+    __device__ uint32_t bounded9() {              // legacy randint(low, low + 10): range 9, mask 15
+        uint32_t v;
+        do { v = next32() & 15u; } while (v > 9u);
+        return v;
+    }
+    __device__ double legacy_gauss() {
+        if (has_gauss) { const double t = gauss; has_gauss = 0; gauss = 0.0; return t; }
+        double f, x1, x2, r2;
+        do {
+            x1 = 2.0 * next_double() - 1.0;
+            x2 = 2.0 * next_double() - 1.0;
+            r2 = x1 * x1 + x2 * x2;
+        } while (r2 >= 1.0 || r2 == 0.0);
+        f = sqrt(-2.0 * log(r2) / r2);
+        gauss = f * x1; has_gauss = 1;
+        return f * x2;
+    }
+};
+
+__global__ void __launch_bounds__(128) k_sim_records(sim_consts c, const double *cdf, const double *lut_d, int64_t first_frame, const int *n_cand,
+                                                    int max_cand, int render_scale, int W, int H, rr_streak_rec *cand, unsigned char *flags) {
+    const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= max_cand) return;
+    unsigned char keep = 0;
+    rr_sim_streak s;
+    if (i < n_cand[f] && sim_candidate(c, cdf, lut_d, first_frame + f, i, &s)) {
+        // DBManager.load_streaks_from_xml (bad_weather.py:208-238) on the simulator's values
+        const double rs = (double)render_scale;
+        double p1x = s.ip1[0] / rs, p1y = s.ip1[1] / rs, p2x = s.ip2[0] / rs, p2y = s.ip2[1] / rs;       // :208-209
+        const double iw1 = s.iw1 / rs, iw2 = s.iw2 / rs;                                                   // :210-211
+        p1y = (double)H - p1y; p2y = (double)H - p2y;                                                      // :221-222
+        rr_streak_rec r;
+        r.wp1[0] = s.wp1[0]; r.wp1[1] = s.wp1[1]; r.wp1[2] = s.wp1[2] * -1;                                // :223-224
+        r.wp2[0] = s.wp2[0]; r.wp2[1] = s.wp2[1]; r.wp2[2] = s.wp2[2] * -1;
+        const double dx = fabs(p1x - p2x), dy = fabs(p1y - p2y);
+        const long long max_width = (long long)(iw1 > iw2 ? iw1 : iw2);                                    // :226 int() truncation
+        const double nrm = sqrt(fma(dy, dy, dx * dx));                                                     // np.linalg.norm, :229
+        const double cos_theta = 0.0 * (dx / nrm) + -1.0 * (-(dy / nrm));                                  // :228-231
+        r.ratio = (double)max_width / (dy / cos_theta);                                                    // :232-233
+        const long long x1 = (long long)rint(p1x), y1 = (long long)rint(p1y), x2 = (long long)rint(p2x), y2 = (long long)rint(p2y);   // :234-235 half-even
+        const double ddx = (double)(x1 - x2), ddy = (double)(y1 - y2);
+        const long long length = (long long)ceil(sqrt(ddx * ddx + ddy * ddy));                             // :236
+        r.iw1 = iw1; r.iw2 = iw2; r.noise_deg = 0.0;
+        r.ip1[0] = r.ip1m[0] = (int32_t)x1; r.ip1[1] = r.ip1m[1] = (int32_t)y1;
+        r.ip2[0] = r.ip2m[0] = (int32_t)x2; r.ip2[1] = r.ip2m[1] = (int32_t)y2;
+        r.max_width = (int32_t)max_width; r.length = (int32_t)length; r.pid = (int32_t)s.pid;
+        r.type = max_width >= 4 ? 0 : (max_width > 1 ? 1 : 2);                                             // :99-106
+        r.tex_idx = 0; r.pad[0] = r.pad[1] = 0;
+        const int m = H > W ? H : W;
+        const bool loaded = max_width >= 1 && length >= 1;                                                 // :238
+        const bool ok_w = 1 <= max_width && max_width < m, ok_l = 1 <= length && length < m;               // generator.py:413-420
+        const bool ins = 0 <= x1 && x1 < W && 0 <= y1 && y1 < H, ine = 0 <= x2 && x2 < W && 0 <= y2 && y2 < H;
+        if (loaded && ok_w && ok_l && (ins || ine)) { keep = 1; cand[(size_t)f * max_cand + i] = r; }
+    }
+    flags[(size_t)f * max_cand + i] = keep;
+}
+
+__global__ void __launch_bounds__(256) k_sim_count(const unsigned char *flags, int max_cand, int *counts) {
+    const int f = blockIdx.x;
+    int n = 0;
+    for (int i = threadIdx.x; i < max_cand; i += 256) n += flags[(size_t)f * max_cand + i];
+    __shared__ int sh[8];
+    for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = n;
+    __syncthreads();
+    if (threadIdx.x == 0) { int t = 0; for (int k = 0; k < 8; k++) t += sh[k]; counts[f] = t; }
+}
+
+__global__ void k_sim_offsets(const int *counts, int F, int32_t *offsets) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { int o = 0; offsets[0] = 0; for (int f = 0; f < F; f++) { o += counts[f]; offsets[f + 1] = o; } }
+}
+
+__global__ void __launch_bounds__(256) k_sim_compact_draw(const rr_streak_rec *cand, const unsigned char *flags, int max_cand, const int32_t *offsets,
+                                                         int64_t first_frame, double r0, double r1, double r2, double r3, int n_ratios,
+                                                         double noise_std, double noise_scale, rr_streak_rec *out) {
+    __shared__ uint32_t key[624];
+    __shared__ int wsum[8];
+    __shared__ int base;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) base = offsets[f];
+    __syncthreads();
+    // ordered compaction: candidate order = pid order = the order the loader's dict and the in-frame filter keep
+    for (int i0 = 0; i0 < max_cand; i0 += 256) {
+        const int i = i0 + tid;
+        const int k = i < max_cand ? flags[(size_t)f * max_cand + i] : 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) wsum[warp] = __popc(bal);
+        __syncthreads();
+        int pre = base;
+        for (int w = 0; w < warp; w++) pre += wsum[w];
+        if (k) {
+            const int4 *src = (const int4 *)(cand + (size_t)f * max_cand + i);
+            int4 *dst = (int4 *)(out + pre + __popc(bal & ((1u << lane) - 1)));
+#pragma unroll
+            for (int q = 0; q < (int)(sizeof(rr_streak_rec) / sizeof(int4)); q++) dst[q] = src[q];
+        }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int w = 0; w < 8; w++) t += wsum[w]; base += t; }
+        __syncthreads();
+    }
+    if (tid != 0) return;
+    __threadfence_block();
+    sim_mt mt;
+    mt.key = key;
+    mt.seed((uint32_t)(first_frame + f));                          // np.random.seed(frame index), generator.py:318
+    const double ratios[4] = {r0, r1, r2, r3};
+    const int nr = n_ratios < 4 ? n_ratios : 4;
+    for (int s = offsets[f]; s < offsets[f + 1]; s++) {
+        rr_streak_rec &r = out[s];
+        int b = 0;
+        while (b < nr && !(r.ratio < ratios[b])) b++;
+        r.tex_idx = (uint8_t)(10 * b + (int)mt.bounded9());        // bad_weather.py:252-264
+        r.noise_deg = r.type != 0 ? (0.0 + noise_std * mt.legacy_gauss()) * noise_scale : 0.0;      // generator.py:136
+    }
+}
+
+extern "C" void *rr_ctx_scratch(rr_context *c, int which, size_t bytes);      // rr_api.cu: grow-only device buffers of the context
+extern "C" void *rr_ctx_stream(rr_context *c);
+
+extern "C" int rr_simulate_records_device(rr_context *ctx, const rr_sim_params *p, int64_t first_frame, int n_frames, int render_scale,
+                                          const double *db_ratios, int n_ratios, double noise_std, double noise_scale,
+                                          rr_streak_rec **d_records, int32_t *h_offsets, double *expected_per_frame) {
+    if (!ctx || !p || !d_records || !h_offsets || n_frames <= 0 || render_scale < 1 || (n_ratios > 0 && !db_ratios)) { rr_set_error("rr_simulate_records_device: bad arguments"); return RR_ERR_ARG; }
+    if (noise_std != 0.0 && noise_scale != 0.0) {
+        rr_set_error("rr_simulate_records_device: wind noise couples consecutive frames through the write-back of generator.py:152-161; "
+                     "use rr_simulate_particles + the host record assembly for noise_std * noise_scale != 0");
+        return RR_ERR_ARG;
+    }
+    if (first_frame < 0 || first_frame + n_frames > 0xffffffffll) { rr_set_error("rr_simulate_records_device: frame index out of the 32-bit seed range"); return RR_ERR_ARG; }
+    if (cudaSetDevice(rr_sim_device_of(ctx)) != cudaSuccess) { rr_set_error("rr_simulate_records_device: cudaSetDevice failed"); return RR_ERR_CUDA; }
+    sim_consts c;
+    std::vector<double> cdf, d;
+    double mean = 0;
+    int rc = sim_prepare(p, &c, &cdf, &d, &mean);
+    if (rc != RR_OK) return rc;
+    if (expected_per_frame) *expected_per_frame = mean;
+    std::vector<int> n_cand(n_frames);
+    int max_cand = 1;
+    for (int f = 0; f < n_frames; f++) { n_cand[f] = sim_poisson(c, mean, first_frame + f); if (n_cand[f] > max_cand) max_cand = n_cand[f]; }
+    const int W = p->W / render_scale, H = p->H / render_scale;
+    cudaStream_t st = (cudaStream_t)rr_ctx_stream(ctx);
+    const size_t F = (size_t)n_frames;
+    double *d_tab = (double *)rr_ctx_scratch(ctx, 0, sizeof(double) * 2 * SIM_NLUT + sizeof(int) * (2 * F + 2) + sizeof(int32_t) * (F + 1));
+    rr_streak_rec *d_cand = (rr_streak_rec *)rr_ctx_scratch(ctx, 1, sizeof(rr_streak_rec) * F * max_cand);
+    unsigned char *d_flags = (unsigned char *)rr_ctx_scratch(ctx, 2, F * max_cand);
+    rr_streak_rec *d_out = (rr_streak_rec *)rr_ctx_scratch(ctx, 3, sizeof(rr_streak_rec) * F * max_cand);
+    if (!d_tab || !d_cand || !d_flags || !d_out) { rr_set_error("rr_simulate_records_device: out of device memory"); return RR_ERR_CUDA; }
+    double *d_cdf = d_tab, *d_d = d_tab + SIM_NLUT;
+    int *d_ncand = (int *)(d_tab + 2 * SIM_NLUT), *d_counts = d_ncand + F;
+    int32_t *d_offsets = (int32_t *)(d_counts + F + 2);
+    cudaError_t e;
+#define SIMCK(call) if ((e = (call)) != cudaSuccess) { rr_set_error(cudaGetErrorString(e)); return RR_ERR_CUDA; }
+    SIMCK(cudaMemcpyAsync(d_cdf, cdf.data(), sizeof(double) * SIM_NLUT, cudaMemcpyHostToDevice, st));
+    SIMCK(cudaMemcpyAsync(d_d, d.data(), sizeof(double) * SIM_NLUT, cudaMemcpyHostToDevice, st));
+    SIMCK(cudaMemcpyAsync(d_ncand, n_cand.data(), sizeof(int) * F, cudaMemcpyHostToDevice, st));
+    dim3 g((max_cand + 127) / 128, n_frames);
+    k_sim_records<<<g, 128, 0, st>>>(c, d_cdf, d_d, first_frame, d_ncand, max_cand, render_scale, W, H, d_cand, d_flags);
+    k_sim_count<<<n_frames, 256, 0, st>>>(d_flags, max_cand, d_counts);
+    k_sim_offsets<<<1, 32, 0, st>>>(d_counts, n_frames, d_offsets);
+    const double rr[4] = {n_ratios > 0 ? db_ratios[0] : 0, n_ratios > 1 ? db_ratios[1] : 0, n_ratios > 2 ? db_ratios[2] : 0, n_ratios > 3 ? db_ratios[3] : 0};
+    k_sim_compact_draw<<<n_frames, 256, 0, st>>>(d_cand, d_flags, max_cand, d_offsets, first_frame, rr[0], rr[1], rr[2], rr[3], n_ratios, noise_std,
+                                                  noise_scale, d_out);
+    SIMCK(cudaGetLastError());
+    // the only thing that comes back: the n + 1 frame offsets (the render entry points take them as a host array)
+    SIMCK(cudaMemcpyAsync(h_offsets, d_offsets, sizeof(int32_t) * (F + 1), cudaMemcpyDeviceToHost, st));
+    SIMCK(cudaStreamSynchronize(st));
+#undef SIMCK
+    *d_records = d_out;
+    return RR_OK;
 }
 
 // host-side evaluation of the force model for the CPU tests (no GPU needed)

@@ -73,8 +73,10 @@ def test_generator_run_writes_the_oracle_images():
         paths = synth.write_dataset(root, "customdb", "seq1", W, H, nf, 25, 1200, seed=3, n_sim_frames=2)
         a = _args(paths, "customdb", 25)
         os.environ["RAIN_B200_BATCH"] = "2"          # 5 frames -> batches of 2, 2, 1
+        a.save_envmap = True
         g = gen.Generator(a)
         g.run()
+        assert g.last_stats["frames"] == nf
         out_dir = os.path.join(paths["output"], "customdb", "seq1", "rain", "25mm")
         tex, ratios = ro.load_streak_database(a.texture, a.norm_coeff)
         frames = ro.load_streaks_from_xml(paths["xml"], 1, W, H)
@@ -86,11 +88,100 @@ def test_generator_run_writes_the_oracle_images():
             bg, depth = ro.read_frame(os.path.join(a.images["seq1"], name + ".png"), os.path.join(a.depth["seq1"], name + ".png"))
             o = ro.render_frame(bg, depth, frames[i % 2], tex, ratios, cam, i, f32_mode="canonical")
             assert np.abs(got.astype(int) - o.out_u8.astype(int)).max() <= 1
+            # the reference's file formats (plt.imsave): RGBA, the mask coloured through viridis from its normalised index
+            rgba = cv2.imread(os.path.join(out_dir, "rainy_image", name + ".png"), cv2.IMREAD_UNCHANGED)
+            assert rgba.shape == (H, W, 4) and (rgba[..., 3] == 255).all()
+            m = cv2.imread(os.path.join(out_dir, "rain_mask", name + ".png"), cv2.IMREAD_UNCHANGED)
+            idx, _ = ro.imsave_mask_index(o.rain_mask)
+            from rain_rendering_b200 import pngio
+            lut = pngio.viridis_rgb()
+            same = (m[..., 2::-1] == lut[idx]).all(-1)
+            near = (m[..., 2::-1] == lut[np.minimum(idx.astype(int) + 1, 255)]).all(-1) | (m[..., 2::-1] == lut[np.maximum(idx.astype(int) - 1, 0)]).all(-1)
+            assert m.shape == (H, W, 4) and (same | near).all() and (~same).mean() < 1e-4
+            env_file = os.path.join(paths["output"], "customdb", "seq1", "envmap", name + ".png")
+            env = cv2.imread(env_file, cv2.IMREAD_UNCHANGED)
+            want_env = ((np.round(o.env * 255).astype(np.uint8) / 255.0) * 255).astype(np.uint8)       # plt.imsave of BGR_env_map[..., ::-1]
+            assert env is not None and env.shape[2] == 4 and np.array_equal(env[..., :3], want_env)
+        # the compact pair of files: RGB image + the normalised mask as 16-bit gray
+        a.save_envmap = False
+        a.output = os.path.join(root, "out_compact")
+        os.environ["RAIN_B200_OUTPUT_FORMAT"] = "compact"
+        try:
+            gen.Generator(a).run()
+        finally:
+            del os.environ["RAIN_B200_OUTPUT_FORMAT"]
+        cdir = os.path.join(a.output, "customdb", "seq1", "rain", "25mm")
+        for i in range(nf):
+            name = "%06d" % i
+            c = cv2.imread(os.path.join(cdir, "rainy_image", name + ".png"), cv2.IMREAD_UNCHANGED)
+            assert c.shape == (H, W, 3) and np.array_equal(c, cv2.imread(os.path.join(out_dir, "rainy_image", name + ".png")))
+            m16 = cv2.imread(os.path.join(cdir, "rain_mask", name + ".png"), cv2.IMREAD_UNCHANGED)
+            assert m16.dtype == np.uint16 and m16.shape == (H, W) and m16.max() == 65535 and m16.min() == 0
+        a.output = paths["output"]
+        with pytest.raises(NotImplementedError):                   # 'white' / 'naive_db' are not silently rendered as the full model
+            a.rendering_strategy = "white"
+            gen.Generator(a)
+        a.rendering_strategy = None
         # skip strategy: nothing is re-rendered
         a.conflict_strategy = "skip"
         t = os.path.getmtime(os.path.join(out_dir, "rainy_image", "000000.png"))
         gen.Generator(a).run()
         assert os.path.getmtime(os.path.join(out_dir, "rainy_image", "000000.png")) == t
+        shutil.rmtree(root, ignore_errors=True)
+    finally:
+        sys.path.remove(DROPIN)
+        for k in [k for k in sys.modules if k == "common" or k.startswith("common.")]:
+            del sys.modules[k]
+
+
+@pytest.mark.gpu
+def test_generator_run_nuscenes_arrangement_jpg_images_and_npy_depth():
+    """The nuScenes branch of Generator.run (generator.py:235-246,306-311): images and depth maps arrive as per-sequence FILE
+    LISTS, CAM_FRONT frames are .jpg (decoded by OpenCV: the native codec is PNG only), depth is float32 .npy, the size is
+    probed with cv2.imread and the simulator frames are spread over the files with np.linspace."""
+    for k in [k for k in sys.modules if k == "common" or k.startswith("common.")]:
+        del sys.modules[k]
+    sys.path.insert(0, DROPIN)
+    try:
+        from rain_rendering_b200 import synth
+        from oracle import rain_oracle as ro
+        import common.generator as gen
+        root = tempfile.mkdtemp(prefix="rr_nusc_")
+        W, H, nf = 400, 224, 5
+        paths = synth.write_dataset(root, "nuscenes", "scene-0001", W, H, nf, 25, 600, seed=4, n_sim_frames=3)
+        src = os.path.join(paths["dataset_root"], "nuscenes", "scene-0001")
+        imgs, deps = [], []
+        for i in range(nf):
+            png = os.path.join(src, "rgb", "%06d.png" % i)
+            jpg = os.path.join(src, "rgb", "n015-cam_front-%06d.jpg" % i)
+            cv2.imwrite(jpg, cv2.imread(png), [cv2.IMWRITE_JPEG_QUALITY, 95])
+            os.remove(png)
+            d = cv2.imread(os.path.join(src, "depth", "%06d.png" % i), cv2.IMREAD_UNCHANGED).astype(np.float32) / 256.
+            npy = os.path.join(src, "depth", "n015-cam_front-%06d.npy" % i)
+            np.save(npy, d)
+            imgs.append(jpg); deps.append(npy)
+        a = _args(paths, "nuscenes", 25, seq="scene-0001")
+        a.images, a.depth = {"scene-0001": imgs}, {"scene-0001": deps}
+        a.noise_scale, a.noise_std = 0.0, 0.0
+        os.environ["RAIN_B200_BATCH"] = "4"
+        gen.Generator(a).run()
+        out_dir = os.path.join(paths["output"], "nuscenes", "scene-0001", "rain", "25mm")
+        tex, ratios = ro.load_streak_database(a.texture, a.norm_coeff)
+        frames = ro.load_streaks_from_xml(paths["xml"], 1, W, H)
+        c = synth.CAMERAS["nuscenes"]
+        cam = ro.Camera(W=W, H=H, focal_mm=c["cam_focal"], f_number=c["cam_f_number"], exposure_ms=c["cam_exposure"], gain=c["cam_gain"],
+                        fallrate=25, opacity_attenuation=0.9)
+        render_ix = np.linspace(0, len(frames), nf, endpoint=False, dtype=int)
+        for i in range(nf):
+            got = cv2.imread(os.path.join(out_dir, "rainy_image", "n015-cam_front-%06d.png" % i))
+            assert got is not None
+            o = ro.render_frame(cv2.imread(imgs[i]), np.load(deps[i]), frames[int(render_ix[i]) % len(frames)], tex, ratios, cam, int(render_ix[i]),
+                                f32_mode="canonical")
+            assert np.abs(got.astype(int) - o.out_u8.astype(int)).max() <= 1
+        # a float64 depth map would change the reference's arithmetic (generator.py:367): refused, never downcast
+        np.save(deps[0], np.load(deps[0]).astype(np.float64))
+        with pytest.raises(NotImplementedError):
+            gen.Generator(a).run()
         shutil.rmtree(root, ignore_errors=True)
     finally:
         sys.path.remove(DROPIN)
@@ -138,25 +229,28 @@ class _FakeBuf:
 
 
 class _FakeCtx:
-    """Stands in for RainContext: 'renders' u8 = bgr + 1, mask = depth * 2 when a batch is waited for, and can be told
-    to report a patch-arena overflow on the n-th wait (the asynchronous API does not grow the arena itself)."""
+    """Stands in for RainContext: 'renders' u8 = bgr + 1, mask index = low byte of the depth sample when a batch is waited
+    for, and can be told to report a patch-arena overflow on the n-th wait (the asynchronous API does not grow the arena
+    itself)."""
     W, H, render_scale = 24, 16, 1
 
     def __init__(self, overflow_on_wait=None):
         self.q, self.log, self.waits, self.overflow_on_wait = [], [], 0, overflow_on_wait
 
-    def _render(self, bgr, depth, mask, u8):
-        u8[...] = bgr + 1
-        mask[...] = depth * 2
+    def _render(self, bgr, depth, out):
+        out["out_u8"][...] = bgr + 1
+        out["out_idx8"][...] = (depth >> 8).astype(np.uint8)
+        out["out_range"][...] = 0
 
-    def render_frames(self, bgr, depth, recs, offs, out_bgr, out_mask, out_u8, want=()):
+    def render_frames(self, bgr, depth, recs, offs, want=(), **out):
+        assert depth.dtype == np.uint16 and len(recs) == offs[-1]
         self.log.append(("sync", len(bgr), int(offs[-1])))
-        self._render(bgr, depth, out_mask, out_u8)
+        self._render(bgr, depth, out)
 
-    def submit_frames(self, bgr, depth, recs, offs, out_bgr, out_mask, out_u8):
-        assert len(self.q) < 2
+    def submit_frames(self, bgr, depth, recs, offs, **out):
+        assert len(self.q) < 2 and len(recs) == offs[-1]
         self.log.append(("submit", len(bgr), int(offs[-1])))
-        self.q.append((bgr, depth, out_mask, out_u8))
+        self.q.append((bgr, depth, out))
 
     def wait_frames(self):
         from rain_rendering_b200._lib import RainError
@@ -190,20 +284,24 @@ def test_frame_pipeline_orders_batches_and_recovers_from_arena_overflow(tmp_path
         Image.fromarray(np.full((H, W, 3), 7, np.uint8)).convert("P").save(str(src / "i007.png"))     # palette: OpenCV fallback
         fallbacks = []
 
-        def fallback(image_file, depth_file):
+        def fallback(image_file, depth_file, depth_u16):
+            assert depth_u16
             fallbacks.append(os.path.basename(image_file))
             d = cv2.imread(depth_file, cv2.IMREAD_UNCHANGED)
             if d is None:
                 return None, None
-            return cv2.imread(image_file), d.astype(np.float32) / 256.
+            return cv2.imread(image_file), d
 
         ctx = _FakeCtx(overflow_on_wait)
         pipe = gen._FramePipeline(ctx, batch=3, io_threads=4, fallback_decode=fallback, alloc=_FakeBuf)
         order = []
 
-        def assemble(i):
-            order.append(i)
-            return np.zeros(i % 3 + 1, STREAK_DTYPE)
+        def assemble(indices, record_buffer):
+            order.extend(indices)
+            counts = [i % 3 + 1 for i in indices]
+            buf = record_buffer(sum(counts))
+            assert buf.dtype == STREAK_DTYPE and len(buf) >= sum(counts)
+            return buf[:sum(counts)], np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
 
         for b0 in range(0, 11, 3):
             q = [(str(src / ("i%03d.png" % i)), str(src / ("d%03d.png" % i)), i, str(tmp_path / "rainy_image" / ("%03d.png" % i)),
@@ -224,8 +322,10 @@ def test_frame_pipeline_orders_batches_and_recovers_from_arena_overflow(tmp_path
                 continue
             img = cv2.imread(str(p))
             assert img is not None and np.array_equal(img, cv2.imread(str(src / ("i%03d.png" % i))) + 1), i      # the fake context renders u8 = bgr + 1
-            assert (tmp_path / "rain_mask" / ("%03d.png" % i)).exists()
-        assert pipe.frames_done == 10
+            m = cv2.imread(str(tmp_path / "rain_mask" / ("%03d.png" % i)), cv2.IMREAD_UNCHANGED)     # RGBA: viridis of the index the fake "rendered"
+            from rain_rendering_b200 import pngio
+            assert m.shape == (H, W, 4) and (m[..., 2::-1] == pngio.viridis_rgb()[i]).all() and (m[..., 3] == 255).all()
+        assert pipe.frames_done == 10 and set(pipe.stats) >= {"decode_wait", "gpu_wait", "write_wait", "assemble"}
     finally:
         sys.path.remove(DROPIN)
         for k in [k for k in sys.modules if k == "common" or k.startswith("common.")]:

@@ -272,6 +272,72 @@ def test_compact_boundary_formats_uint16_depth_and_saved_mask_forms():
     ctx.close()
 
 
+def test_png_image_data_made_on_the_gpu_decodes_to_the_rendered_pixels(tmp_path):
+    """rr_frame_io.out_png_*: the zlib streams the device emits (Sub filter + one literal-only dynamic Huffman block + Adler-32)
+    must inflate -- with Python's zlib, and as framed PNG files with OpenCV's libpng -- to exactly the uint8 image and the
+    viridis-coloured mask index of the same render.  Odd width (1 + 4 W bytes per scanline: rows straddle word boundaries),
+    a frame without rain (a mask of one colour: two used symbols) and batches through the asynchronous path."""
+    import zlib
+    import cv2
+    from rain_rendering_b200 import api, pngio
+    W, H = 333, 200
+    sc = Scenario(W, H, 5, 1400, fallrate=25)
+    ctx = sc.context()
+    recs, offs = sc.records()
+    keep = np.ones(len(recs), bool)
+    keep[offs[3]:offs[4]] = False                      # frame 3 gets no streaks
+    recs = recs[keep]
+    offs = np.concatenate([offs[:4], offs[4:] - (offs[4] - offs[3])]).astype(np.int32)
+    ref = ctx.render_frames(sc.bgr, sc.depth, recs, offs, want=("u8", "idx8"))
+    stride = ctx.png_stream_bound()
+    n = sc.n_frames
+    lut = pngio.viridis_rgb()
+
+    def check(png):
+        for kind in ("image", "mask"):
+            for i in range(n):
+                size = int(png[kind + "_sizes"][i])
+                assert 0 < size <= stride
+                raw = np.frombuffer(zlib.decompress(png[kind][i, :size].tobytes()), np.uint8).reshape(H, 4 * W + 1)
+                assert (raw[:, 0] == 1).all()                                              # Sub filter on every scanline
+                px = np.cumsum(raw[:, 1:].reshape(H, W, 4).astype(np.uint32), axis=1).astype(np.uint8)   # undo Sub
+                want = ref["u8"][i][..., ::-1] if kind == "image" else lut[ref["idx8"][i]]
+                assert np.array_equal(px[..., :3], want) and (px[..., 3] == 255).all(), (kind, i)
+    png = dict(image=np.zeros((n, stride), np.uint8), mask=np.zeros((n, stride), np.uint8), image_sizes=np.zeros(n, np.uint32), mask_sizes=np.zeros(n, np.uint32))
+    ctx.render_frames(sc.bgr, sc.depth, recs, offs, want=(), png=png)
+    check(png)
+    assert png["mask_sizes"][3] < png["mask_sizes"][0] and png["image_sizes"].min() > 1000
+    # framed as files: what OpenCV reads back
+    paths = [str(tmp_path / ("r%d.png" % i)) for i in range(n)]
+    assert pngio.write_streams(paths, png["image"], png["image_sizes"], W, H, 3) == 0
+    for i in range(n):
+        a = cv2.imread(paths[i], cv2.IMREAD_UNCHANGED)
+        assert a.shape == (H, W, 4) and np.array_equal(a[..., :3], ref["u8"][i]) and (a[..., 3] == 255).all()
+    # asynchronous submissions with page-locked buffers: same streams, byte for byte
+    sets = []
+    for _ in range(2):
+        hb = dict(bgr=api.PinnedBuffer(sc.bgr.shape, np.uint8), depth=api.PinnedBuffer(sc.depth.shape, np.float32), recs=api.PinnedBuffer(recs.shape, recs.dtype),
+                  image=api.PinnedBuffer((n, stride), np.uint8), mask=api.PinnedBuffer((n, stride), np.uint8),
+                  image_sizes=api.PinnedBuffer((n,), np.uint32), mask_sizes=api.PinnedBuffer((n,), np.uint32))
+        hb["bgr"].array[...] = sc.bgr; hb["depth"].array[...] = sc.depth; hb["recs"].array[...] = recs
+        sets.append(hb)
+    for k in range(4):
+        hb = sets[k & 1]
+        if k >= 2:
+            ctx.wait_frames()
+        ctx.submit_frames(hb["bgr"].array, hb["depth"].array, hb["recs"].array, offs,
+                          png=dict(image=hb["image"].array, mask=hb["mask"].array, image_sizes=hb["image_sizes"].array, mask_sizes=hb["mask_sizes"].array))
+    ctx.wait_frames(); ctx.wait_frames()
+    for hb in sets:
+        got = dict(image=hb["image"].array, mask=hb["mask"].array, image_sizes=hb["image_sizes"].array, mask_sizes=hb["mask_sizes"].array)
+        check(got)
+        for kind in ("image", "mask"):
+            assert np.array_equal(got[kind + "_sizes"], png[kind + "_sizes"])
+            for i in range(n):
+                assert np.array_equal(got[kind][i, :got[kind + "_sizes"][i]], png[kind][i, :png[kind + "_sizes"][i]])
+    ctx.close()
+
+
 @pytest.mark.parametrize("name", ["small_256x192", "c1_640x480"])
 def test_against_reference_goldens(name):
     sc, g = golden_scenario(name)
@@ -310,6 +376,27 @@ def test_against_reference_golden_c2_frame():
     o = sc.oracle_frame(0, "native")
     assert np.array_equal(out["mask"][0] > 0, o.rain_mask > 0)
     assert ulp_diff_f32(out["mask"][0], o.rain_mask.astype(np.float32)).max() <= 1
+    ctx.close()
+
+
+@pytest.mark.parametrize("name,W,H,n_xml,dataset,fallrate,rs", [
+    ("C3", 1024, 512, 1300, "cityscapes", 50, 2),        # 2048x1024 frames reduced on the device, 5 ms exposure
+    ("C4-100", 1600, 900, 2600, "nuscenes", 100, 1),     # W_env 2373: three prefix tiles per row; f/1.8 defocus
+    ("C4-200", 1600, 900, 4800, "nuscenes", 200, 1),
+    ("C5", 1242, 375, 2600, "kitti", 100, 1),            # KITTI at 100 mm/h: ~1600 streaks in the frame
+])
+def test_baseline_configs_at_full_size_one_frame_each(name, W, H, n_xml, dataset, fallrate, rs):
+    """BASELINE.json configs C3, C4 (the two heavy rates of its sweep) and C5 at their real sizes and streak counts
+    (synth.WORKLOADS), one frame each against the oracle: the oracle needs tens of seconds per such frame."""
+    sc = Scenario(W, H, 1, n_xml, fallrate=fallrate, dataset=dataset, render_scale=rs)
+    ctx = sc.context()
+    recs, offs = sc.records()
+    lo = {"C3": 600, "C4-100": 1200, "C4-200": 2200, "C5": 1200}[name]
+    assert offs[-1] > lo, (name, offs[-1])
+    out = ctx.render_frames(sc.bgr, sc.depth, recs, offs)
+    o = sc.oracle_frame(0, "canonical")
+    assert o.n_streaks == offs[1]
+    _check_frame(out, 0, o)
     ctx.close()
 
 

@@ -83,6 +83,122 @@ def test_encode_round_trips_through_cv2(tmp_path, level):
     assert pngio.write_batch([str(tmp_path / "no_such_dir" / "x.png")], bgr[:1], None, None, level, 1) == 1
 
 
+def test_deflate_encoder_streams_are_valid_zlib_for_edge_cases():
+    """csrc/rr_host_deflate.h: run + dynamic-Huffman blocks.  Python's zlib must reproduce the input (it also verifies the
+    Adler-32): empty and tiny inputs, runs around the 258-byte match limit, blocks longer than 65536 tokens, a symbol
+    distribution whose optimal code is deeper than 15 bits (length-limiting repair), incompressible noise."""
+    import zlib
+    rng = np.random.RandomState(0)
+    fib = [1, 1]
+    while len(fib) < 30:
+        fib.append(fib[-1] + fib[-2])
+    skew = np.concatenate([np.full(min(f, 200000), i, np.uint8) for i, f in enumerate(fib)])
+    rng.shuffle(skew)
+    cases = [b"", b"a", b"ab", b"aaa", b"aaaa", b"a" * 258, b"a" * 259, b"a" * 260, b"ab" + b"c" * 261 + b"d", bytes(100000),
+             b"abc" * 1000, rng.randint(0, 256, 70000).astype(np.uint8).tobytes(), rng.randint(0, 2, 200000).astype(np.uint8).tobytes(),
+             (rng.rand(300000) < 0.01).astype(np.uint8).tobytes(), bytes(range(256)) * 300,
+             np.repeat(rng.randint(0, 256, 5000).astype(np.uint8), rng.randint(1, 600, 5000)).tobytes(), skew.tobytes()]
+    for c in cases:
+        z = pngio.zlib_compress_fast(c)
+        assert zlib.decompress(z) == c, len(c)
+    assert len(pngio.zlib_compress_fast(bytes(100000))) < 200                  # runs really are matches
+    noise = cases[11]
+    assert len(pngio.zlib_compress_fast(noise)) < len(noise) + 400              # and noise costs only the block headers
+
+
+def test_inflate_decoder_against_zlib_streams_of_every_block_type_and_mutations():
+    """csrc/rr_host_inflate.h: what zlib produces at every level / strategy (stored, fixed and dynamic Huffman blocks, long
+    matches, codes longer than the 11-bit first-level table) must decode to the input; truncated, corrupted or
+    wrong-size streams must be refused, never crash or overrun."""
+    import zlib
+    rng = np.random.RandomState(1)
+    fib = [1, 1]
+    while len(fib) < 24:
+        fib.append(fib[-1] + fib[-2])
+    skew = np.concatenate([np.full(f, i, np.uint8) for i, f in enumerate(fib)])
+    rng.shuffle(skew)
+    smooth = np.cumsum(rng.randint(-2, 3, 200000)).astype(np.uint8).tobytes()
+    datas = [b"", b"a", b"hello hello hello hello", bytes(70000), rng.randint(0, 256, 100000).astype(np.uint8).tobytes(), smooth, skew.tobytes(),
+             (b"0123456789abcdef" * 5000) + rng.randint(0, 256, 3000).astype(np.uint8).tobytes() + bytes(range(256)) * 40,
+             np.repeat(rng.randint(0, 256, 3000).astype(np.uint8), rng.randint(1, 400, 3000)).tobytes()]
+    n_streams = 0
+    for d in datas:
+        for level in (0, 1, 6, 9):
+            for strat in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FILTERED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FIXED):
+                c = zlib.compressobj(level, zlib.DEFLATED, 15, 8, strat)
+                z = c.compress(d[:len(d) // 2]) + c.flush(zlib.Z_FULL_FLUSH) + c.compress(d[len(d) // 2:]) + c.flush()
+                assert pngio.zlib_decompress_fast(z, len(d)) == d, (len(d), level, strat)
+                n_streams += 1
+                if len(d) > 100:
+                    assert pngio.zlib_decompress_fast(z, len(d) - 1) is None and pngio.zlib_decompress_fast(z, len(d) + 1) is None
+                    assert pngio.zlib_decompress_fast(z[:len(z) // 2], len(d)) is None
+        z = pngio.zlib_compress_fast(d)                                      # and the library's own encoder
+        assert pngio.zlib_decompress_fast(z, len(d)) == d
+    assert n_streams == len(datas) * 20
+    # mutations: whatever comes back is either None or exactly what zlib itself would accept
+    z0 = zlib.compress(smooth, 6)
+    accepted = 0
+    for it in range(1500):
+        b = bytearray(z0)
+        for _ in range(rng.randint(1, 4)):
+            b[rng.randint(2, len(b))] = rng.randint(0, 256)
+        got = pngio.zlib_decompress_fast(bytes(b), len(smooth))
+        if got is not None:
+            accepted += 1
+            assert zlib.decompress(bytes(b)) == got
+    assert accepted < 20                                                     # the Adler-32 catches nearly everything that still parses
+
+
+def test_reference_format_files_rgba_image_and_viridis_mask(tmp_path):
+    """plt.imsave's formats (common/generator.py:466-467): RGBA with alpha 255; the mask through the colormap."""
+    H, W, n = 45, 83, 4
+    bgr = np.stack([_rand((H, W, 3), np.uint8, 150 + i) for i in range(n)])
+    idx = np.stack([_rand((H, W), np.uint8, 170 + i) for i in range(n)])
+    idx[2] = 0                                                                  # a frame without rain: one colour
+    idx[3, :, :40] = 255
+    lut = pngio.viridis_rgb()
+    assert lut[0].tolist() == [68, 1, 84] and lut[255].tolist() == [253, 231, 36] and lut[128].tolist() == [32, 144, 140]
+    for level in (0, 1, 6):
+        ip = [str(tmp_path / ("r%d_%d.png" % (level, i))) for i in range(n)]
+        mp = [str(tmp_path / ("m%d_%d.png" % (level, i))) for i in range(n)]
+        assert pngio.write_batch_rgba(ip, bgr, mp, idx, level, 3) == 0
+        for i in range(n):
+            a = cv2.imread(ip[i], cv2.IMREAD_UNCHANGED)
+            assert a.shape == (H, W, 4) and np.array_equal(a[..., :3], bgr[i]) and (a[..., 3] == 255).all()
+            m = cv2.imread(mp[i], cv2.IMREAD_UNCHANGED)
+            assert m.shape == (H, W, 4) and np.array_equal(m[..., 2::-1], lut[idx[i]]) and (m[..., 3] == 255).all()
+    # the compact pair: RGB + 16-bit gray
+    u16 = np.stack([_rand((H, W), np.uint16, 190 + i) for i in range(n)])
+    ip = [str(tmp_path / ("c%d.png" % i)) for i in range(n)]
+    mp = [str(tmp_path / ("cm%d.png" % i)) for i in range(n)]
+    assert pngio.write_batch_u16(ip, bgr, mp, u16, 1, 2) == 0
+    for i in range(n):
+        assert np.array_equal(cv2.imread(ip[i]), bgr[i]) and np.array_equal(cv2.imread(mp[i], cv2.IMREAD_UNCHANGED), u16[i])
+
+
+def test_depth_as_uint16_samples_and_header_bombs(tmp_path):
+    H, W = 33, 47
+    d16 = _rand((H, W), np.uint16, 7); d8 = _rand((H, W), np.uint8, 8)
+    p16, p8 = str(tmp_path / "d16.png"), str(tmp_path / "d8.png")
+    cv2.imwrite(p16, d16); cv2.imwrite(p8, d8)
+    out = np.zeros((2, H, W), np.uint16)
+    assert pngio.read_batch(None, [p16, p8], None, out, 2).tolist() == [0, 0]
+    assert np.array_equal(out[0], d16) and np.array_equal(out[1], d8.astype(np.uint16))
+    # a tiny file whose header claims 65536 x 65536 RGBA16 (34 GB): refused on the size before anything is allocated
+    import struct
+    import zlib
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+    bomb = b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", 65536, 65536, 16, 6, 0, 0, 0)) + chunk(b"IDAT", zlib.compress(b"\0" * 64)) + chunk(b"IEND", b"")
+    pb = str(tmp_path / "bomb.png")
+    open(pb, "wb").write(bomb)
+    img = np.zeros((1, H, W, 3), np.uint8)
+    assert pngio.read_batch([pb], None, img, None, 1).tolist() == [pngio.SIZE]
+    assert pngio.read_batch([pb], None, img, None, 4).tolist() == [pngio.SIZE]
+    big = np.zeros((1, 8, 8, 3), np.uint8)                                     # even when the caller's size matches the lie
+    assert pngio.info(pb)[:2] == (65536, 65536)
+
+
 def test_codec_speed_on_a_kitti_sized_frame(tmp_path):
     bgr, depth = synth.make_frame(1242, 375, 3)
     p, q = str(tmp_path / "a.png"), str(tmp_path / "d.png")

@@ -90,3 +90,108 @@ def test_simulator_feeds_the_renderer():
     out = ctx.render_frames(np.stack([f[0] for f in frames]), np.stack([f[1] for f in frames]), np.concatenate(recs), np.array(offs, np.int32))
     assert np.isfinite(out["bgr"]).all() and (out["mask"] > 0).mean() > 0.02
     ctx.close()
+
+
+def _device_records(ptr, n):
+    """copy n rr_streak_rec back from a raw device pointer (tests only)"""
+    import torch
+    from rain_rendering_b200.dist import _DevicePtr
+    if n == 0:
+        return np.zeros(0, S.STREAK_DTYPE)
+    t = torch.as_tensor(_DevicePtr(ptr, n * S.STREAK_DTYPE.itemsize), device=torch.device("cuda", 0))
+    return t.cpu().numpy().view(S.STREAK_DTYPE).copy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("W,H,rs,fallrate,exposure", [(1242, 375, 1, 25, 2.0), (2048, 1024, 2, 50, 5.0)])
+def test_device_resident_simulation_gives_the_host_paths_records_bit_for_bit(W, H, rs, fallrate, exposure):
+    """rr_simulate_records_device (BASELINE C3: on-the-fly simulation feeding the renderer with no host round trip of the
+    streaks) against the host route it replaces: rr_simulate_particles -> the XML loader's arithmetic (records_from_sim,
+    common/bad_weather.py:200-238) -> in-frame filter + NumPy-RNG mirror (assemble_batch).  Same float64 operations in the
+    same order and the same MT19937 stream: the records must be identical, byte for byte."""
+    ctx = api.RainContext(0)
+    db = synth.make_streak_db(0)
+    n, first = 6, 3
+    pix = 4.65 * 1242 / W
+    sims, mean = ctx.simulate_particles(first, n, W, H, fallrate, pix_size_um=pix, exposure_ms=exposure, seed=5)
+    host = [S.records_from_sim(sim, rs, W // rs, H // rs) for sim in sims]
+    want, want_offs = api.assemble_batch(host, list(range(first, first + n)), W // rs, H // rs, db.ratios)
+    ptr, offs, mean_d = ctx.simulate_records_device(first, n, W, H, fallrate, db.ratios, render_scale=rs, pix_size_um=pix, exposure_ms=exposure, seed=5)
+    assert mean_d == mean and np.array_equal(offs, want_offs) and offs[-1] > 50 * n
+    got = _device_records(ptr, int(offs[-1]))
+    for name in S.STREAK_DTYPE.names:
+        assert np.array_equal(got[name], want[name], equal_nan=True) if got[name].dtype.kind == "f" else np.array_equal(got[name], want[name]), name
+    assert set(np.unique(got["type"]).tolist()) <= {0, 1, 2} and len(np.unique(got["tex_idx"])) > 5
+    # and straight into the renderer, device to device
+    import torch
+    Wr, Hr = W // rs, H // rs
+    ctx.set_streak_db(db.textures, db.ratios)
+    ctx.set_camera(Wr, Hr, exposure_ms=exposure, fallrate=fallrate, max_batch=n, render_scale=rs)
+    frames = [synth.make_frame(W, H, i) for i in range(n)]
+    bgr = np.stack([f[0] for f in frames])
+    d16 = np.stack([np.rint(synth.make_frame(Wr, Hr, i)[1] * 256).astype(np.uint16) for i in range(n)])
+    dev = torch.device("cuda", 0)
+    t_bgr, t_d = torch.from_numpy(bgr).to(dev), torch.from_numpy(d16.view(np.int16)).to(dev)
+    t_u8 = torch.empty((n, Hr, Wr, 3), dtype=torch.uint8, device=dev)
+    t_mask = torch.empty((n, Hr, Wr), dtype=torch.float32, device=dev)
+    ptr, offs, _ = ctx.simulate_records_device(first, n, W, H, fallrate, db.ratios, render_scale=rs, pix_size_um=pix, exposure_ms=exposure, seed=5)
+    ctx.render_frames_device(t_bgr.data_ptr(), t_d.data_ptr(), True, ptr, offs, d_out_mask=t_mask.data_ptr(), d_out_u8=t_u8.data_ptr())
+    ref = ctx.render_frames(bgr, d16, want, want_offs, want=("mask", "u8"))
+    assert np.array_equal(t_u8.cpu().numpy(), ref["u8"]) and np.array_equal(t_mask.cpu().numpy(), ref["mask"])
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_drop_sizes_follow_marshall_palmer_and_counts_follow_the_rate():
+    """statistical parity of the simulator stand-in.  (1) The diameters of the imaged drops must follow the
+    density the model states -- Marshall-Palmer N(D) = 8000 exp(-4.1 R^-0.21 D) weighted by 1 / v(D) (airborne
+    concentration of a flux) and by the volume in which a drop of that size is imaged wider than a pixel: chi-square
+    against that density, computed here independently from the force model.  (2) The mean streak count at five rates
+    follows the water budget: proportional to R * integral(N V)^-1 ..., i.e. to the expectation the library reports, and
+    grows monotonically with R."""
+    ctx = api.RainContext(0)
+    W, H, T = 1242, 375, 2.0
+    f_px = 6e-3 / 4.65e-6
+    R = 25.0
+    frames, mean = ctx.simulate_particles(0, 150, W, H, R, exposure_ms=T, seed=21)
+    allr = np.concatenate(frames)
+    d_mm = allr["wd1"] * 1e3
+    assert len(d_mm) > 20000
+    # expected density of imaged diameters
+    edges = np.linspace(0.1, 6.0, 25)
+    centres = np.linspace(0.1, 10.0, 4001)
+    lam = 4.1 * R ** -0.21
+    v = np.array([_phys(D * 1e-3)[0] for D in centres])
+    zmax = np.minimum(centres * 1e-3 * f_px / 1.0, 15.0)
+    z0 = 0.25
+    a = (W + 4) * H / f_px ** 2
+    b = (W + 4) / f_px * (v * T / 1000.0)
+    vol = np.where(zmax > z0, a * (zmax ** 3 - z0 ** 3) / 3 + b * (zmax ** 2 - z0 ** 2) / 2, 0.0)
+    dens = 8000 * np.exp(-lam * centres) / v * vol
+    # candidates are drawn from `dens`; imaged streaks are the candidates with an end point on the sensor and wide enough:
+    # compare the CANDIDATE-level shape through the acceptance-free region (every candidate with D >= 1.2 mm whose zmax is the
+    # far plane is accepted with the same geometric probability up to the v T band), i.e. test the tail shape
+    sel = (d_mm >= 1.2) & (d_mm < 6.0)
+    obs = np.histogram(d_mm[sel], bins=edges[edges >= 1.2 - 1e-9])[0].astype(float)
+    cdf = np.concatenate([[0], np.cumsum((dens[1:] + dens[:-1]) / 2 * np.diff(centres))])
+    sub = edges[edges >= 1.2 - 1e-9]
+    exp = np.diff(np.interp(sub, centres, cdf))
+    exp = exp / exp.sum() * obs.sum()
+    keep = exp > 20
+    chi2 = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum()
+    dof = keep.sum() - 1
+    assert chi2 < dof + 6 * np.sqrt(2 * dof) + 0.02 * obs.sum() * 0.05, (chi2, dof)     # statistical scatter + a 5 % model tolerance (acceptance band)
+    # counts vs rate
+    rates = [5, 10, 25, 50, 100]
+    means, counts = [], []
+    for r in rates:
+        fr, m = ctx.simulate_particles(0, 40, W, H, r, exposure_ms=T, seed=3)
+        means.append(m)
+        counts.append(np.mean([len(f) for f in fr]))
+    counts, means = np.array(counts), np.array(means)
+    assert (np.diff(counts) > 0).all() and (np.diff(means) > 0).all()
+    ratio = counts / means                         # imaged / candidates: geometry only, nearly independent of R
+    assert ratio.max() / ratio.min() < 1.25
+    growth = np.log(counts[-1] / counts[0]) / np.log(rates[-1] / rates[0])
+    assert 0.6 < growth < 1.05                      # sub-linear: the Marshall-Palmer slope flattens with R
+    ctx.close()
