@@ -398,7 +398,9 @@ def run_gpu(args):
             try:
                 sys.path.insert(0, os.path.join(ROOT, "tools"))
                 import dropin_e2e
-                line["dropin_png_e2e"] = dropin_e2e.measure(n_frames=args.dropin_frames, batch=batch)
+                import contextlib
+                with contextlib.redirect_stdout(sys.stderr):          # Generator.run() prints progress like the reference: not on the JSON channel
+                    line["dropin_png_e2e"] = dropin_e2e.measure(n_frames=args.dropin_frames, batch=batch)
             except Exception as e:                      # the headline numbers above stand on their own
                 line["dropin_png_e2e"] = {"error": "%s: %s" % (type(e).__name__, e)}
         if world == 1 and not args.no_cpu_baseline:
@@ -414,6 +416,80 @@ def run_gpu(args):
         dist.destroy_process_group()
 
 
+def run_gpu_c3(args):
+    """BASELINE config C3: Cityscapes 2048x1024 frames rendered at 1024x512 (render_scale 2), 50 mm/h, ON-THE-FLY particle
+    simulation.  A step = rr_simulate_records_device (simulator -> loader arithmetic -> in-frame filter -> RNG draws, records
+    stay in HBM; only the 65 frame offsets come back) + rr_render_frames_device_io over 64 resident frames.  One GPU; prints
+    one JSON line (kept under profiles/, not the driver's headline)."""
+    import ctypes as C
+    import torch
+    from rain_rendering_b200 import _lib, api
+    wl = synth.WORKLOADS["C3"]
+    W, H, rs = wl["W"], wl["H"], 2
+    cam = synth.CAMERAS[wl["dataset"]]
+    batch = args.batch
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    db = synth.make_streak_db(0)
+    frames = [synth.make_frame(W * rs, H * rs, i) for i in range(batch)]
+    bgr = np.stack([f[0] for f in frames])
+    d16 = np.stack([np.rint(synth.make_frame(W, H, i)[1] * 256.0).astype(np.uint16) for i in range(batch)])
+    ctx = api.RainContext(0)
+    ctx.set_streak_db(db.textures, db.ratios)
+    ctx.set_camera(W, H, cam["cam_focal"], cam["cam_f_number"], cam["cam_exposure"], cam["cam_gain"], wl["fallrate"], 1.0, batch, render_scale=rs)
+    stream_ptr = C.c_void_p()
+    ctx.lib.rr_stream(ctx.h, C.byref(stream_ptr))
+    stream = torch.cuda.ExternalStream(stream_ptr.value, device=dev)
+    t_bgr, t_d = torch.from_numpy(bgr).to(dev), torch.from_numpy(d16.view(np.int16)).to(dev)
+    t_out = torch.empty((batch, H, W, 3), dtype=torch.float32, device=dev)
+    t_mask = torch.empty((batch, H, W), dtype=torch.float32, device=dev)
+    t_u8 = torch.empty((batch, H, W, 3), dtype=torch.uint8, device=dev)
+    t_idx = torch.empty((batch, H, W), dtype=torch.uint8, device=dev)
+    pix = 4.65 * 1242.0 / (W * rs)                      # the synthetic optics scale the pixel pitch with the sensor width (synth.make_particles)
+    n_streaks = []
+
+    def step(k):
+        ptr, offs, _ = ctx.simulate_records_device(k * batch, batch, W * rs, H * rs, wl["fallrate"], db.ratios, render_scale=rs, pix_size_um=pix,
+                                                   exposure_ms=cam["cam_exposure"], seed=1)
+        n_streaks.append(int(offs[-1]))
+        ctx.render_frames_device(t_bgr.data_ptr(), t_d.data_ptr(), True, ptr, offs, t_out.data_ptr(), t_mask.data_ptr(), t_u8.data_ptr(), t_idx.data_ptr())
+
+    for k in range(max(args.warmup, 3)):
+        step(k)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    launches0 = ctx.kernel_launches()
+    stage_ms = {k: 0.0 for k in ctx.timings()}
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_streaks.clear()
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for k in range(args.steps):
+        step(100 + k)
+        for kk, v in ctx.timings().items():
+            stage_ms[kk] += v
+    e1.record(stream)
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    kern = {k: v / args.steps for k, v in stage_ms.items() if k not in ("h2d", "d2h", "total")}
+    render_ms = stage_ms["total"] / args.steps
+    line = {"metric": "rainy frames/sec at 2048x1024 -> 1024x512, 50mm/hr, on-the-fly simulation", "value": batch * args.steps / (ms / 1000.0), "unit": "frames/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C3 Cityscapes 2048x1024 (render 1024x512) 50mm/hr, on-the-fly particle simulation", "batch_frames_per_gpu": batch,
+                       "streaks_per_frame": float(np.mean(n_streaks)) / batch,
+                       "l2": "inputs larger than L2 (%.0f MB per step, no flush)" % ((bgr.nbytes + d16.nbytes) / 1e6)},
+            "clocks": clocks, "gpu_launches": ctx.kernel_launches() - launches0,
+            "sim_ms_per_step": ms / args.steps - render_ms, "render_ms_per_step": render_ms, "wall_ms_per_step": 1000.0 * wall / args.steps,
+            "note": "simulation + record building on the device (4 launches, one 260-byte D2H of the frame offsets), then the render; no streak data crosses the host link",
+            "stage_ms": kern}
+    print(json.dumps(line))
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -422,12 +498,15 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="C2", choices=["C2", "C3"], help="C2: the headline (default).  C3: Cityscapes with on-the-fly simulation, one GPU")
     ap.add_argument("--no-dropin", action="store_true", help="skip the drop-in Generator.run() PNG pass (dropin_png_e2e)")
     ap.add_argument("--dropin-frames", type=int, default=1024)
     ap.add_argument("--skip-e2e", action="store_true", help="profiling aid: only the device-resident arm (the JSON line is then incomplete)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "C3":
+        run_gpu_c3(args)
     else:
         run_gpu(args)
 

@@ -40,8 +40,8 @@ struct rr_context {
     unsigned *d_png_sizes[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
     cudaStream_t s_png = nullptr;          // fetches the finished streams (exact sizes) after a batch completes
     rr_frame_io call_io[2];
-    void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};       // grow-only device buffers of the on-the-fly simulator
-    size_t scratch_bytes[4] = {0, 0, 0, 0};                // the requests in flight (host pointers of the PNG outputs)
+    void *scratch[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};       // grow-only device buffers of the on-the-fly simulator
+    size_t scratch_bytes[5] = {0, 0, 0, 0, 0};                // the requests in flight (host pointers of the PNG outputs)
     bool serial = false;                   // RR_SERIAL=1: the streak chain runs on the main stream (profiling: one kernel at a time)
     cudaEvent_t ev_plan = nullptr;
     long long launches = 0;
@@ -162,8 +162,10 @@ size_t rr_png_stream_bound(int W, int H) {
 int rr_version(void) { return 200; }
 int rr_sim_device_of(rr_context *c) { return c ? c->device : 0; }
 void *rr_ctx_stream(rr_context *c) { return c ? (void *)c->stream : nullptr; }
+void rr_ctx_count_launches(rr_context *c, int n) { if (c) c->launches += n; }
 void *rr_ctx_scratch(rr_context *c, int which, size_t bytes) {
-    if (!c || which < 0 || which >= 4) return nullptr;
+    if (!c || which < 0 || which >= 5) return nullptr;
+    if (bytes == 0) return c->scratch[which];                      // query: the buffer as it stands (NULL when never allocated)
     if (bytes > c->scratch_bytes[which]) {
         cudaStreamSynchronize(c->stream);
         if (c->scratch[which]) cudaFree(c->scratch[which]);
@@ -226,7 +228,7 @@ int rr_destroy(rr_context *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     free_camera(c);
-    for (int i = 0; i < 4; i++) if (c->scratch[i]) cudaFree(c->scratch[i]);
+    for (int i = 0; i < 5; i++) if (c->scratch[i]) cudaFree(c->scratch[i]);
     if (c->d_db) cudaFree(c->d_db);
     if (c->d_tex_off) cudaFree(c->d_tex_off);
     if (c->d_tex_h) cudaFree(c->d_tex_h);

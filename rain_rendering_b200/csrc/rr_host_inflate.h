@@ -174,20 +174,38 @@ static inline bool zlib_decompress(const uint8_t *in, size_t in_len, uint8_t *ou
             if (!build_table(lens, hlit, 0, lit_table, LIT_BITS, LIT_TABLE) || !build_table(lens + hlit, hdist, 1, dist_table, DIST_BITS, DIST_TABLE)) return false;
         }
         // ---- the block's symbols ----
+        uint8_t *const o_fast_end = out_len > 320 ? o_end - 320 : out;     // below it four literals and a match need no bound checks
         for (;;) {
             b.refill();
-            if (b.overrun()) return false;
+            if (b.in > b.in_end && b.overrun()) return false;
             uint32_t e = lit_table[b.peek(LIT_BITS)];
-            // up to three literals per refill (3 x 15 bits); each one re-checks the output bound
-            int guard = 0;
-            while (((e >> 12) & 15) == KIND_LIT && guard < 3) {
-                if (o >= o_end) return false;
-                b.drop((int)(e & 0xff));
-                *o++ = (uint8_t)(e >> 16);
-                e = lit_table[b.peek(LIT_BITS)];
-                guard++;
+            if (o < o_fast_end) {
+                // fast path: up to four literals per refill (4 x 11 bits of first-level codes leave 12 bits for the next look-up)
+                if (((e >> 12) & 15) == KIND_LIT) {
+                    b.drop((int)(e & 0xff)); *o++ = (uint8_t)(e >> 16); e = lit_table[b.peek(LIT_BITS)];
+                    if (((e >> 12) & 15) == KIND_LIT) {
+                        b.drop((int)(e & 0xff)); *o++ = (uint8_t)(e >> 16); e = lit_table[b.peek(LIT_BITS)];
+                        if (((e >> 12) & 15) == KIND_LIT) {
+                            b.drop((int)(e & 0xff)); *o++ = (uint8_t)(e >> 16); e = lit_table[b.peek(LIT_BITS)];
+                            if (((e >> 12) & 15) == KIND_LIT) {
+                                b.drop((int)(e & 0xff)); *o++ = (uint8_t)(e >> 16);
+                                continue;
+                            }
+                        }
+                    }
+                }
+            } else {
+                // near the end of the output: one literal at a time, every write checked
+                int guard = 0;
+                while (((e >> 12) & 15) == KIND_LIT && guard < 3) {
+                    if (o >= o_end) return false;
+                    b.drop((int)(e & 0xff));
+                    *o++ = (uint8_t)(e >> 16);
+                    e = lit_table[b.peek(LIT_BITS)];
+                    guard++;
+                }
+                if (guard == 3) continue;                          // refill before going on
             }
-            if (guard == 3) continue;                              // refill before going on
             int kind = (int)((e >> 12) & 15);
             if (kind == KIND_SUB) {
                 b.drop((int)(e & 0xff));

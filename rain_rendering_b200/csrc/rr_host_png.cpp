@@ -51,7 +51,9 @@ bool read_file(const char *path, std::vector<unsigned char> *buf) {
 
 struct Image {
     int w = 0, h = 0, channels = 0, depth = 0;     // depth: bits per sample (8 or 16)
-    std::vector<unsigned char> px;                  // unfiltered scanlines, h * w * channels * depth/8, samples big-endian
+    std::vector<unsigned char> px;                  // unfiltered scanlines, each (stride + 1) bytes: filter byte, then w * channels * depth/8 sample bytes (big-endian)
+    size_t stride = 0;
+    const unsigned char *row(int y) const { return px.data() + (stride + 1) * (size_t)y + 1; }
 };
 
 int paeth(int a, int b, int c) {
@@ -122,53 +124,70 @@ int decode(const char *path, Image *img, bool header_only, int want_w = 0, int w
         }
     }
     if (ret != RR_OK) return ret;
-    // unfilter in place into img->px
+    // unfilter IN PLACE (each scanline keeps its filter byte in front): no second buffer, and the Sub filter -- what
+    // OpenCV's writer and this library's own use throughout -- runs as bpp independent running sums
     const int bpp = img->channels * (img->depth / 8);
-    img->px.resize(stride * (size_t)img->h);
-    const unsigned char *prev = nullptr;
+    img->stride = stride;
+    unsigned char *prev = nullptr;
     for (int y = 0; y < img->h; y++) {
-        const unsigned char *src = raw.data() + (stride + 1) * (size_t)y;
-        unsigned char *dst = img->px.data() + stride * (size_t)y;
-        const int ft = src[0];
-        src++;
+        unsigned char *row = raw.data() + (stride + 1) * (size_t)y + 1;
+        const int ft = row[-1];
         switch (ft) {
-            case 0: memcpy(dst, src, stride); break;
+            case 0: break;
             case 1:
-                for (size_t i = 0; i < stride; i++) dst[i] = (unsigned char)(src[i] + (i >= (size_t)bpp ? dst[i - bpp] : 0));
+                if (bpp == 3) {
+                    unsigned a = 0, b = 0, c = 0;
+                    size_t i = 0;
+                    for (; i + 3 <= stride; i += 3) { a += row[i]; b += row[i + 1]; c += row[i + 2]; row[i] = (unsigned char)a; row[i + 1] = (unsigned char)b; row[i + 2] = (unsigned char)c; }
+                } else if (bpp == 2) {
+                    unsigned a = 0, b = 0;
+                    for (size_t i = 0; i + 2 <= stride; i += 2) { a += row[i]; b += row[i + 1]; row[i] = (unsigned char)a; row[i + 1] = (unsigned char)b; }
+                } else if (bpp == 4) {
+                    unsigned a = 0, b = 0, c = 0, d = 0;
+                    for (size_t i = 0; i + 4 <= stride; i += 4) {
+                        a += row[i]; b += row[i + 1]; c += row[i + 2]; d += row[i + 3];
+                        row[i] = (unsigned char)a; row[i + 1] = (unsigned char)b; row[i + 2] = (unsigned char)c; row[i + 3] = (unsigned char)d;
+                    }
+                } else {
+                    for (size_t i = bpp; i < stride; i++) row[i] = (unsigned char)(row[i] + row[i - bpp]);
+                }
                 break;
             case 2:
-                for (size_t i = 0; i < stride; i++) dst[i] = (unsigned char)(src[i] + (prev ? prev[i] : 0));
+                if (prev) for (size_t i = 0; i < stride; i++) row[i] = (unsigned char)(row[i] + prev[i]);
                 break;
             case 3:
                 for (size_t i = 0; i < stride; i++) {
-                    int a = i >= (size_t)bpp ? dst[i - bpp] : 0, b = prev ? prev[i] : 0;
-                    dst[i] = (unsigned char)(src[i] + ((a + b) >> 1));
+                    int a = i >= (size_t)bpp ? row[i - bpp] : 0, b = prev ? prev[i] : 0;
+                    row[i] = (unsigned char)(row[i] + ((a + b) >> 1));
                 }
                 break;
             case 4:
                 for (size_t i = 0; i < stride; i++) {
-                    int a = i >= (size_t)bpp ? dst[i - bpp] : 0, b = prev ? prev[i] : 0, c = (prev && i >= (size_t)bpp) ? prev[i - bpp] : 0;
-                    dst[i] = (unsigned char)(src[i] + paeth(a, b, c));
+                    int a = i >= (size_t)bpp ? row[i - bpp] : 0, b = prev ? prev[i] : 0, c = (prev && i >= (size_t)bpp) ? prev[i - bpp] : 0;
+                    row[i] = (unsigned char)(row[i] + paeth(a, b, c));
                 }
                 break;
             default: return RR_ERR_ARG;
         }
-        prev = dst;
+        prev = row;
     }
+    img->px.swap(raw);                  // scanlines of stride + 1 bytes (filter byte first), unfiltered
     return RR_OK;
 }
 
 // cv2.imread(path) semantics: BGR uint8, gray replicated, alpha dropped, 16-bit -> high byte
 int to_bgr8(const Image &im, uint8_t *dst) {
     const int step = im.depth / 8, ch = im.channels;
-    const size_t n = (size_t)im.w * im.h;
-    const unsigned char *s = im.px.data();
-    if (ch == 1 || ch == 2) {
-        for (size_t i = 0; i < n; i++) { uint8_t g = s[i * ch * step]; dst[3 * i] = dst[3 * i + 1] = dst[3 * i + 2] = g; }
-    } else {
-        for (size_t i = 0; i < n; i++) {
-            const unsigned char *p = s + i * ch * step;
-            dst[3 * i] = p[2 * step]; dst[3 * i + 1] = p[step]; dst[3 * i + 2] = p[0];
+    for (int y = 0; y < im.h; y++) {
+        const unsigned char *s = im.row(y);
+        uint8_t *d = dst + (size_t)y * im.w * 3;
+        if (ch == 1 || ch == 2) {
+            for (int i = 0; i < im.w; i++) { uint8_t g = s[(size_t)i * ch * step]; d[3 * i] = d[3 * i + 1] = d[3 * i + 2] = g; }
+        } else {
+            for (int i = 0; i < im.w; i++) {
+                const unsigned char *p = s + (size_t)i * ch * step;
+                d[3 * i] = p[2 * step]; d[3 * i + 1] = p[step]; d[3 * i + 2] = p[0];
+            }
         }
     }
     return RR_OK;
@@ -177,20 +196,24 @@ int to_bgr8(const Image &im, uint8_t *dst) {
 // cv2.imread(path, IMREAD_UNCHANGED).astype(np.float32) / 256. for a single-channel file
 int to_depth_f32(const Image &im, float *dst) {
     if (im.channels != 1) return RR_PNG_UNSUPPORTED;
-    const size_t n = (size_t)im.w * im.h;
-    const unsigned char *s = im.px.data();
-    if (im.depth == 16) for (size_t i = 0; i < n; i++) dst[i] = (float)((s[2 * i] << 8) | s[2 * i + 1]) / 256.f;
-    else for (size_t i = 0; i < n; i++) dst[i] = (float)s[i] / 256.f;
+    for (int y = 0; y < im.h; y++) {
+        const unsigned char *s = im.row(y);
+        float *d = dst + (size_t)y * im.w;
+        if (im.depth == 16) for (int i = 0; i < im.w; i++) d[i] = (float)((s[2 * i] << 8) | s[2 * i + 1]) / 256.f;
+        else for (int i = 0; i < im.w; i++) d[i] = (float)s[i] / 256.f;
+    }
     return RR_OK;
 }
 
 // cv2.imread(path, IMREAD_UNCHANGED) of a single-channel file as uint16 samples (the /256 happens on the device)
 int to_depth_u16(const Image &im, uint16_t *dst) {
     if (im.channels != 1) return RR_PNG_UNSUPPORTED;
-    const size_t n = (size_t)im.w * im.h;
-    const unsigned char *s = im.px.data();
-    if (im.depth == 16) for (size_t i = 0; i < n; i++) dst[i] = (uint16_t)((s[2 * i] << 8) | s[2 * i + 1]);
-    else for (size_t i = 0; i < n; i++) dst[i] = s[i];
+    for (int y = 0; y < im.h; y++) {
+        const unsigned char *s = im.row(y);
+        uint16_t *d = dst + (size_t)y * im.w;
+        if (im.depth == 16) for (int i = 0; i < im.w; i++) d[i] = (uint16_t)((s[2 * i] << 8) | s[2 * i + 1]);
+        else for (int i = 0; i < im.w; i++) d[i] = s[i];
+    }
     return RR_OK;
 }
 

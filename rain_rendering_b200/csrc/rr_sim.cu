@@ -74,26 +74,32 @@ __host__ __device__ inline double sim_region(const sim_consts &c, double D, doub
 }
 
 // One candidate drop of one frame -> its imaged streak, or false when it is not imaged (outside the sensor, sub-pixel)
-__device__ bool sim_candidate(const sim_consts &c, const double *cdf, const double *lut_d, int64_t frame, int i, rr_sim_streak *res);
+// (lut_v: terminal velocity of every table diameter, computed once per parameter set on the device -- k_sim_vt)
+__device__ bool sim_candidate(const sim_consts &c, const double *cdf, const double *lut_d, const double *lut_v, int64_t frame, int i, rr_sim_streak *res);
 
-__global__ void k_sim_frame(sim_consts c, const double *cdf, const double *lut_d, int64_t frame, int n_cand, int cap,
+__global__ void k_sim_vt(const double *lut_d, double *lut_v) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < SIM_NLUT) lut_v[i] = sim_v_terminal(lut_d[i]);
+}
+
+__global__ void k_sim_frame(sim_consts c, const double *cdf, const double *lut_d, const double *lut_v, int64_t frame, int n_cand, int cap,
                             rr_sim_streak *out, int *counter) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_cand) return;
     rr_sim_streak r;
-    if (!sim_candidate(c, cdf, lut_d, frame, i, &r)) return;
+    if (!sim_candidate(c, cdf, lut_d, lut_v, frame, i, &r)) return;
     int slot = atomicAdd(counter, 1);
     if (slot >= cap) return;
     out[slot] = r;
 }
 
-__device__ bool sim_candidate(const sim_consts &c, const double *cdf, const double *lut_d, int64_t frame, int i, rr_sim_streak *res) {
+__device__ bool sim_candidate(const sim_consts &c, const double *cdf, const double *lut_d, const double *lut_v, int64_t frame, int i, rr_sim_streak *res) {
     // diameter: inverse transform on the LUT (the binary scans a 50001-entry table linearly)
     double u = sim_u01(c.seed, (uint64_t)frame, i, 0);
     int lo = 0, hi = SIM_NLUT - 1;
     while (lo < hi) { int mid = (lo + hi) >> 1; if (cdf[mid] < u) lo = mid + 1; else hi = mid; }
     double D = lut_d[lo];
-    double v = sim_v_terminal(D);
+    double v = lut_v[lo];                 // sim_v_terminal(D), tabulated
     double zmax;
     sim_region(c, D, v, &zmax);
     if (zmax <= c.z0) return false;
@@ -212,17 +218,19 @@ extern "C" int rr_simulate_particles(rr_context *ctx, const rr_sim_params *p, in
     if (expected_per_frame) *expected_per_frame = mean;
     double *d_cdf = nullptr, *d_d = nullptr; rr_sim_streak *d_out = nullptr; int *d_cnt = nullptr;
     cudaError_t e;
-    if ((e = cudaMalloc(&d_cdf, sizeof(double) * SIM_NLUT)) != cudaSuccess || (e = cudaMalloc(&d_d, sizeof(double) * SIM_NLUT)) != cudaSuccess ||
+    if ((e = cudaMalloc(&d_cdf, sizeof(double) * SIM_NLUT)) != cudaSuccess || (e = cudaMalloc(&d_d, sizeof(double) * 2 * SIM_NLUT)) != cudaSuccess ||
         (e = cudaMalloc(&d_out, sizeof(rr_sim_streak) * (size_t)max_per_frame)) != cudaSuccess || (e = cudaMalloc(&d_cnt, sizeof(int))) != cudaSuccess) {
         rr_set_error(cudaGetErrorString(e)); cudaFree(d_cdf); cudaFree(d_d); cudaFree(d_out); cudaFree(d_cnt); return RR_ERR_CUDA;
     }
     cudaMemcpy(d_cdf, cdf.data(), sizeof(double) * SIM_NLUT, cudaMemcpyHostToDevice);
     cudaMemcpy(d_d, d.data(), sizeof(double) * SIM_NLUT, cudaMemcpyHostToDevice);
+    double *d_v = d_d + SIM_NLUT;
+    k_sim_vt<<<SIM_NLUT / 128, 128>>>(d_d, d_v);
     for (int f = 0; f < n_frames && rc == RR_OK; f++) {
         int64_t frame = first_frame + f;
         const int n_cand = sim_poisson(c, mean, frame);
         cudaMemset(d_cnt, 0, sizeof(int));
-        if (n_cand > 0) k_sim_frame<<<(n_cand + 127) / 128, 128>>>(c, d_cdf, d_d, frame, n_cand, max_per_frame, d_out, d_cnt);
+        if (n_cand > 0) k_sim_frame<<<(n_cand + 127) / 128, 128>>>(c, d_cdf, d_d, d_v, frame, n_cand, max_per_frame, d_out, d_cnt);
         int cnt = 0;
         if ((e = cudaMemcpy(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) { rr_set_error(cudaGetErrorString(e)); rc = RR_ERR_CUDA; break; }
         if (cnt > max_per_frame) { rr_set_error("rr_simulate_particles: more streaks than max_per_frame"); rc = RR_ERR_CAPACITY; cnt = max_per_frame; }
@@ -286,13 +294,13 @@ struct sim_mt {                       // the NumPy legacy stream (csrc/rr_host.c
     }
 };
 
-__global__ void __launch_bounds__(128) k_sim_records(sim_consts c, const double *cdf, const double *lut_d, int64_t first_frame, const int *n_cand,
+__global__ void __launch_bounds__(128) k_sim_records(sim_consts c, const double *cdf, const double *lut_d, const double *lut_v, int64_t first_frame, const int *n_cand,
                                                     int max_cand, int render_scale, int W, int H, rr_streak_rec *cand, unsigned char *flags) {
     const int f = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= max_cand) return;
     unsigned char keep = 0;
     rr_sim_streak s;
-    if (i < n_cand[f] && sim_candidate(c, cdf, lut_d, first_frame + f, i, &s)) {
+    if (i < n_cand[f] && sim_candidate(c, cdf, lut_d, lut_v, first_frame + f, i, &s)) {
         // DBManager.load_streaks_from_xml (bad_weather.py:208-238) on the simulator's values
         const double rs = (double)render_scale;
         double p1x = s.ip1[0] / rs, p1y = s.ip1[1] / rs, p2x = s.ip2[0] / rs, p2y = s.ip2[1] / rs;       // :208-209
@@ -385,6 +393,7 @@ __global__ void __launch_bounds__(256) k_sim_compact_draw(const rr_streak_rec *c
 
 extern "C" void *rr_ctx_scratch(rr_context *c, int which, size_t bytes);      // rr_api.cu: grow-only device buffers of the context
 extern "C" void *rr_ctx_stream(rr_context *c);
+extern "C" void rr_ctx_count_launches(rr_context *c, int n);
 
 extern "C" int rr_simulate_records_device(rr_context *ctx, const rr_sim_params *p, int64_t first_frame, int n_frames, int render_scale,
                                           const double *db_ratios, int n_ratios, double noise_std, double noise_scale,
@@ -397,11 +406,23 @@ extern "C" int rr_simulate_records_device(rr_context *ctx, const rr_sim_params *
     }
     if (first_frame < 0 || first_frame + n_frames > 0xffffffffll) { rr_set_error("rr_simulate_records_device: frame index out of the 32-bit seed range"); return RR_ERR_ARG; }
     if (cudaSetDevice(rr_sim_device_of(ctx)) != cudaSuccess) { rr_set_error("rr_simulate_records_device: cudaSetDevice failed"); return RR_ERR_CUDA; }
+    // the tables of a parameter set (diameter CDF, diameters, terminal velocities) are built once and stay on the device
+    static thread_local rr_sim_params cached_p;
+    static thread_local sim_consts cached_c;
+    static thread_local double cached_mean = 0;
+    static thread_local rr_context *cached_ctx = nullptr;
+    rr_sim_params key = *p;
+    key.seed = 0;
+    const bool hit = cached_ctx == ctx && memcmp(&key, &cached_p, sizeof(key)) == 0 && rr_ctx_scratch(ctx, 0, 0) != nullptr;
     sim_consts c;
     std::vector<double> cdf, d;
     double mean = 0;
-    int rc = sim_prepare(p, &c, &cdf, &d, &mean);
-    if (rc != RR_OK) return rc;
+    int rc = RR_OK;
+    if (hit) { c = cached_c; c.seed = p->seed; mean = cached_mean; }
+    else {
+        rc = sim_prepare(p, &c, &cdf, &d, &mean);
+        if (rc != RR_OK) return rc;
+    }
     if (expected_per_frame) *expected_per_frame = mean;
     std::vector<int> n_cand(n_frames);
     int max_cand = 1;
@@ -409,27 +430,35 @@ extern "C" int rr_simulate_records_device(rr_context *ctx, const rr_sim_params *
     const int W = p->W / render_scale, H = p->H / render_scale;
     cudaStream_t st = (cudaStream_t)rr_ctx_stream(ctx);
     const size_t F = (size_t)n_frames;
-    double *d_tab = (double *)rr_ctx_scratch(ctx, 0, sizeof(double) * 2 * SIM_NLUT + sizeof(int) * (2 * F + 2) + sizeof(int32_t) * (F + 1));
+    double *d_tab = (double *)rr_ctx_scratch(ctx, 0, sizeof(double) * 3 * SIM_NLUT);
+    int *d_ints = (int *)rr_ctx_scratch(ctx, 4, sizeof(int) * (2 * F + 2) + sizeof(int32_t) * (F + 1));
     rr_streak_rec *d_cand = (rr_streak_rec *)rr_ctx_scratch(ctx, 1, sizeof(rr_streak_rec) * F * max_cand);
     unsigned char *d_flags = (unsigned char *)rr_ctx_scratch(ctx, 2, F * max_cand);
     rr_streak_rec *d_out = (rr_streak_rec *)rr_ctx_scratch(ctx, 3, sizeof(rr_streak_rec) * F * max_cand);
-    if (!d_tab || !d_cand || !d_flags || !d_out) { rr_set_error("rr_simulate_records_device: out of device memory"); return RR_ERR_CUDA; }
-    double *d_cdf = d_tab, *d_d = d_tab + SIM_NLUT;
-    int *d_ncand = (int *)(d_tab + 2 * SIM_NLUT), *d_counts = d_ncand + F;
+    if (!d_tab || !d_ints || !d_cand || !d_flags || !d_out) { rr_set_error("rr_simulate_records_device: out of device memory"); cached_ctx = nullptr; return RR_ERR_CUDA; }
+    double *d_cdf = d_tab, *d_d = d_tab + SIM_NLUT, *d_v = d_tab + 2 * SIM_NLUT;
+    int *d_ncand = d_ints, *d_counts = d_ncand + F;
     int32_t *d_offsets = (int32_t *)(d_counts + F + 2);
     cudaError_t e;
-#define SIMCK(call) if ((e = (call)) != cudaSuccess) { rr_set_error(cudaGetErrorString(e)); return RR_ERR_CUDA; }
-    SIMCK(cudaMemcpyAsync(d_cdf, cdf.data(), sizeof(double) * SIM_NLUT, cudaMemcpyHostToDevice, st));
-    SIMCK(cudaMemcpyAsync(d_d, d.data(), sizeof(double) * SIM_NLUT, cudaMemcpyHostToDevice, st));
+#define SIMCK(call) if ((e = (call)) != cudaSuccess) { rr_set_error(cudaGetErrorString(e)); cached_ctx = nullptr; return RR_ERR_CUDA; }
+    if (!hit) {
+        SIMCK(cudaMemcpyAsync(d_cdf, cdf.data(), sizeof(double) * SIM_NLUT, cudaMemcpyHostToDevice, st));
+        SIMCK(cudaMemcpyAsync(d_d, d.data(), sizeof(double) * SIM_NLUT, cudaMemcpyHostToDevice, st));
+        k_sim_vt<<<SIM_NLUT / 128, 128, 0, st>>>(d_d, d_v);
+        SIMCK(cudaStreamSynchronize(st));           // cdf / d are host vectors about to go out of scope
+        cached_p = key; cached_c = c; cached_mean = mean; cached_ctx = ctx;
+        rr_ctx_count_launches(ctx, 1);
+    }
     SIMCK(cudaMemcpyAsync(d_ncand, n_cand.data(), sizeof(int) * F, cudaMemcpyHostToDevice, st));
     dim3 g((max_cand + 127) / 128, n_frames);
-    k_sim_records<<<g, 128, 0, st>>>(c, d_cdf, d_d, first_frame, d_ncand, max_cand, render_scale, W, H, d_cand, d_flags);
+    k_sim_records<<<g, 128, 0, st>>>(c, d_cdf, d_d, d_v, first_frame, d_ncand, max_cand, render_scale, W, H, d_cand, d_flags);
     k_sim_count<<<n_frames, 256, 0, st>>>(d_flags, max_cand, d_counts);
     k_sim_offsets<<<1, 32, 0, st>>>(d_counts, n_frames, d_offsets);
     const double rr[4] = {n_ratios > 0 ? db_ratios[0] : 0, n_ratios > 1 ? db_ratios[1] : 0, n_ratios > 2 ? db_ratios[2] : 0, n_ratios > 3 ? db_ratios[3] : 0};
     k_sim_compact_draw<<<n_frames, 256, 0, st>>>(d_cand, d_flags, max_cand, d_offsets, first_frame, rr[0], rr[1], rr[2], rr[3], n_ratios, noise_std,
                                                   noise_scale, d_out);
     SIMCK(cudaGetLastError());
+    rr_ctx_count_launches(ctx, 4);
     // the only thing that comes back: the n + 1 frame offsets (the render entry points take them as a host array)
     SIMCK(cudaMemcpyAsync(h_offsets, d_offsets, sizeof(int32_t) * (F + 1), cudaMemcpyDeviceToHost, st));
     SIMCK(cudaStreamSynchronize(st));

@@ -112,7 +112,9 @@ class DBManager:
         if dataset == 'nuscenes_gan':
             raise NotImplementedError("nuscenes_gan rescaling (bad_weather.py:213-219) is out of scope")
         try:
-            frames = _S.load_streaks_from_xml(self.streaks_path_xml, settings["render_scale"], image_shape_WH[0], image_shape_WH[1])
+            # use_pickle: the reference's cache of the parsed simulation (:155-178), here a binary file of packed records
+            frames = _S.load_streaks_from_xml(self.streaks_path_xml, settings["render_scale"], image_shape_WH[0], image_shape_WH[1],
+                                              use_cache=bool(use_pickle) or os.environ.get("RAIN_B200_PARTICLES_CACHE", "0") == "1")
         except Exception:
             raise Exception("Reading XML file {} crashed, which is likely due to corrupted particles simulation files. If so, delete this simulation folder manually and re-run to allow generation of new simulation.".format(self.streaks_path_xml))
         for i, rec in enumerate(frames):
@@ -184,22 +186,13 @@ class RainRenderer:
         self.fov = fov
 
     def compute_circle(self, o, is_infinity=False):
-        if is_infinity:
-            return self.f ** 2 / (self.N * o)
-        result = ((o - self.focus_plane) * self.f ** 2) / (o * (self.focus_plane - self.f) * self.N)
-        return result / 4.65e-06
+        raise NotImplementedError("the circle of confusion is evaluated per streak on the device (rr_plan_patch, csrc/rr_streak_geom.h); "
+                                  "RainContext.debug_read('plans') returns sig_y = c and sig_x = c / 2 of every streak")
 
     @staticmethod
     def warping_points(drop, drop_texture, image_width, image_height):
-        x0, x1 = round(drop.image_position_start[0]), round(drop.image_position_end[0])
-        y0, y1 = round(drop.image_position_start[1]), round(drop.image_position_end[1])
-        d0, d1 = np.floor(drop.image_diameter_start), np.floor(drop.image_diameter_end)
-        minx, miny = max(min(x0, x1), 0), max(min(y0, y1), 0)
-        maxx, maxy = min(max(x0 + d0, x1 + d1), image_width), min(max(y0, y1), image_height)
-        eps = 0.001
-        p1 = np.float32([[0, 0], [drop_texture.shape[1], 0], [drop_texture.shape[1], drop_texture.shape[0]], [0, drop_texture.shape[0]]])
-        p2 = np.float32([[x0 - minx, y0 - miny], [x0 - minx + d0, y0 - miny], [x1 - minx + d1 + eps, y1 - miny], [x1 - minx + eps, y1 - miny]])
-        return p1, p2, np.array([maxx, maxy]), np.array([minx, miny])
+        raise NotImplementedError("the Big-drop warp quad is built on the device (rr_plan_patch, csrc/rr_streak_geom.h); "
+                                  "use Generator.run / RainContext.render_frames")
 
     def circle_of_confusion(self, drop, drop_distance, drop_dict):
         raise NotImplementedError("defocus runs inside the CUDA path (k_blur_v/k_blur_h); use Generator.run / RainContext.render_frames")

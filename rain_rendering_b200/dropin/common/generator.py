@@ -32,6 +32,56 @@ USE_DEPTH_WEIGHTING = 0
 OUTPUT_FORMATS = ("reference", "compact", "matplotlib")
 
 
+class _PinnedPool:
+    """Page-locked staging buffers are expensive to make (cudaHostAlloc pins ~1.4 GB for three sets of KITTI-sized batches:
+    the better part of a second) and identical from one (sequence, weather) to the next, so they are kept per process and
+    handed out again by (shape, dtype); ``free`` on a pooled buffer returns it to the pool."""
+
+    def __init__(self):
+        self.free_lists = {}
+
+    def __call__(self, shape, dtype):
+        key = (tuple(int(v) for v in shape), np.dtype(dtype).str)
+        lst = self.free_lists.setdefault(key, [])
+        buf = lst.pop() if lst else _api.PinnedBuffer(shape, dtype)
+        return _PooledBuffer(self, key, buf)
+
+    def release_all(self):
+        for lst in self.free_lists.values():
+            for b in lst:
+                b.free()
+        self.free_lists = {}
+
+
+class _PooledBuffer:
+    def __init__(self, pool, key, buf):
+        self._pool, self._key, self._buf = pool, key, buf
+        self.array = buf.array
+
+    def free(self):
+        if self._buf is not None:
+            self._pool.free_lists.setdefault(self._key, []).append(self._buf)
+            self._buf, self.array = None, None
+
+
+_POOL = _PinnedPool()
+_CONTEXTS = {}          # device -> RainContext, kept for the life of the process (a new Generator per sequence reuses it)
+
+
+def _release_process_state():
+    try:
+        _POOL.release_all()
+        for c in _CONTEXTS.values():
+            c.close()
+        _CONTEXTS.clear()
+    except Exception:
+        pass
+
+
+import atexit as _atexit        # noqa: E402
+_atexit.register(_release_process_state)
+
+
 class _FramePipeline:
     """Decode -> render -> encode with everything overlapped.  Batches go through ``rr_submit_frames_io`` /
     ``rr_wait_frames`` with two sets of page-locked buffers; PNG decoding and encoding run on native threads
@@ -52,7 +102,7 @@ class _FramePipeline:
         # streams (rr_frame_io.out_png_*); the host frames them and writes the files
         self.gpu_png = bool(gpu_png) and out_format == "reference"
         rs, W, H = ctx.render_scale, ctx.W, ctx.H
-        alloc = alloc or _api.PinnedBuffer            # page-locked, so that the copies overlap the kernels
+        alloc = alloc or _POOL                        # page-locked, so that the copies overlap the kernels; pooled per process
         # three sets of host buffers: one being decoded into, up to two submitted (rr_submit_frames keeps two batches in
         # flight), the outputs of the oldest being written
         self.sets = []
@@ -451,7 +501,9 @@ class Generator:
                 self.db.load_streaks_from_xml(self.dataset, self.settings, [imW, imH], use_pickle=False, verbose=self.verbose)
                 frame_render_dict = list(self.db.streaks_simulator.values())
                 if self._ctx is None:
-                    self._ctx = _api.RainContext(self.device)
+                    if self.device not in _CONTEXTS:
+                        _CONTEXTS[self.device] = _api.RainContext(self.device)
+                    self._ctx = _CONTEXTS[self.device]
                 ctx = self._ctx
                 ctx.set_streak_db(self.db.streaks_light, self.db.ratio)
                 gain = self.camera_gain if self.camera_gain else 20      # generator.py:232-233,260-261
@@ -466,10 +518,11 @@ class Generator:
                     idx = list(range(f_start, f_end, f_step))
                 print("{} images".format(len(idx)))
                 frames_exist_nb = 0
-                t0 = time.time()
+                t_setup = time.time()
                 pipe = _FramePipeline(ctx, self.batch, self.io_threads, fallback_decode=self._decode,
                                       png_level=int(os.environ.get("RAIN_B200_PNG_LEVEL", "1")), depth_u16=depth_u16,
                                       out_format=self.output_format, gpu_png=self.gpu_png)
+                t0 = time.time()      # the frame loop proper; what came before is per-(sequence, weather) set-up
                 queue = []            # (image file, depth file, frame index for the records, out paths)
                 env_jobs = []         # --save_envmap: (frame position in its batch's queue, path)
 
@@ -514,7 +567,7 @@ class Generator:
                     pipe.finish(assemble)
                 finally:
                     pipe.close()
-                    self.last_stats = dict(pipe.stats, frames=pipe.frames_done, seconds=time.time() - t0)
+                    self.last_stats = dict(pipe.stats, frames=pipe.frames_done, seconds=time.time() - t0, buffers_s=t0 - t_setup)
                 if env_jobs:
                     self._save_envmaps(ctx, env_jobs, depth_u16, frame_render_dict, imW, imH)
                 if frames_exist_nb > 0:

@@ -109,13 +109,43 @@ def load_streaks_from_xml_py(path: str, render_scale: int, W: int, H: int, with_
     return list(frames.values())
 
 
-def load_streaks_from_xml(path: str, render_scale: int, W: int, H: int, with_ids: bool = False):
+CACHE_VERSION = "rr-b200-1"
+CACHE_SUFFIX = ".rrcache.npz"
+
+
+def _cache_key(path: str, render_scale: int, W: int, H: int):
+    import hashlib
+    h = hashlib.md5()
+    with open(path, "rb") as f:
+        for blk in iter(lambda: f.read(1 << 22), b""):
+            h.update(blk)
+    return np.array([CACHE_VERSION, h.hexdigest(), "%d,%d,%d" % (int(W), int(H), int(render_scale))])
+
+
+def load_streaks_from_xml(path: str, render_scale: int, W: int, H: int, with_ids: bool = False, use_cache: bool = False):
     """DBManager.load_streaks_from_xml (bad_weather.py:148-248) through the library's native loader
     (``rr_host_load_particles_xml``, csrc/rr_host_xml.cpp).  -> list, one entry per simulator frame in
     the order the reference's dict holds them, of STREAK_DTYPE arrays (tex_idx / noise_deg still zero: they
-    are drawn per rendered frame).  ``with_ids`` also returns the frame ids."""
+    are drawn per rendered frame).  ``with_ids`` also returns the frame ids.
+
+    ``use_cache``: the reference's pickle cache (bad_weather.py:155-178) as a binary file of packed records beside the XML
+    (``<xml>.rrcache.npz``), valid while the XML's md5, the image size and the render scale are unchanged (the same three
+    conditions the reference checks: version, sim_hash, image_shapeWH); a stale or unreadable cache is rebuilt."""
     import ctypes as C
     from . import _lib
+    cache, key = path + CACHE_SUFFIX, None
+    if use_cache:
+        key = _cache_key(path, render_scale, W, H)
+        if os.path.exists(cache):
+            try:
+                with np.load(cache, allow_pickle=False) as z:
+                    if np.array_equal(z["key"], key) and z["rec"].dtype == STREAK_DTYPE and z["hdr"].dtype == _lib.XML_FRAME_DTYPE:
+                        hdr, rec = z["hdr"], z["rec"]
+                        frames = [rec[int(f["first"]):int(f["first"] + f["count"])].copy() for f in hdr]
+                        return (frames, [int(f["id"]) for f in hdr]) if with_ids else frames
+                print("Particles cache out-dated. Regenerate.")
+            except Exception:
+                print("Particles cache unreadable. Regenerate.")
     lib = _lib.load()
     h = C.c_void_p()
     _lib.check(lib.rr_host_load_particles_xml(os.fsencode(path), int(render_scale), int(W), int(H), C.byref(h)), "rr_host_load_particles_xml")
@@ -127,6 +157,13 @@ def load_streaks_from_xml(path: str, render_scale: int, W: int, H: int, with_ids
         _lib.check(lib.rr_host_particles_copy(h, _lib.ptr(hdr), _lib.ptr(rec)), "rr_host_particles_copy")
     finally:
         lib.rr_host_free_particles(h)
+    if use_cache:
+        try:
+            tmp = cache + ".part.%d.npz" % os.getpid()
+            np.savez(tmp, key=key, hdr=hdr, rec=rec)
+            os.replace(tmp, cache)
+        except OSError:
+            pass                        # a read-only dataset tree: no cache, no error (the reference would raise here)
     frames = [rec[int(f["first"]):int(f["first"] + f["count"])].copy() for f in hdr]
     if with_ids:
         return frames, [int(f["id"]) for f in hdr]

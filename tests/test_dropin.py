@@ -36,6 +36,62 @@ print("OK")
     assert out.returncode == 0 and "OK" in out.stdout, out.stdout + out.stderr
 
 
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "main.py")), reason="reference tree not mounted")
+def test_reference_main_check_arg_runs_for_nuscenes_through_the_repaired_plugin(tmp_path):
+    """BASELINE C4 through the reference's own main.check_arg.  Upstream, ``import config.nuscenes`` already
+    fails (config/nuscenes.py:4), then :28 and :56; with the drop-in first on the path the repaired plug-in resolves the
+    frames (file lists that answer os.path.exists like a folder, main.py:152-158), and the untouched rest of check_arg
+    finds the particle files for every rate of the sweep."""
+    from rain_rendering_b200 import synth
+    root = str(tmp_path)
+    W, H, nf = 320, 180, 4
+    paths = synth.write_dataset(root, "nuscenes", "scene-0001", W, H, nf, 25, 200, seed=2, n_sim_frames=2)
+    ds = os.path.join(paths["dataset_root"], "nuscenes")
+    cam = os.path.join(ds, "samples", "CAM_FRONT")
+    os.makedirs(cam)
+    depth_root = os.path.join(root, "depth", "nuscenes")
+    os.makedirs(depth_root)
+    rel = []
+    for i in range(nf):
+        img = cv2.imread(os.path.join(ds, "scene-0001", "rgb", "%06d.png" % i))
+        name = "n015-2018-cam_front__%04d" % i
+        cv2.imwrite(os.path.join(cam, name + ".jpg"), img)
+        np.save(os.path.join(depth_root, name + ".npy"), np.full((H, W), 10.0, np.float32))
+        rel.append(os.path.join("samples", "CAM_FRONT", name + ".jpg"))
+    with open(os.path.join(ds, "rain_b200_index.json"), "w") as f:
+        import json
+        json.dump({"scenes": {"scene-0001": rel[:3], "scene-0002": rel[3:]}}, f)
+    # particle files for two rates of the sweep, where main.py globs for them (main.py:176-209, my_utils.particles_path)
+    for seq in ("scene-0001", "scene-0002"):
+        for rate in (5, 100):
+            d = os.path.join(paths["particles"], "nuscenes", seq, "rain", "%dmm" % rate)
+            os.makedirs(d, exist_ok=True)
+            shutil.copyfile(paths["xml"], os.path.join(d, "sim_camera0.xml"))
+    code = r"""
+import sys, os
+sys.path[:0] = [%r, %r, %r, %r]
+os.chdir(%r)
+import numpy as np
+np.int = int; np.float = float
+import main, config.nuscenes as cn
+assert cn.__file__.startswith(%r), cn.__file__
+import config.kitti as ck
+assert ck.__file__.startswith(%r), ck.__file__
+a = main.check_arg(["--dataset", "nuscenes", "--dataset_root", %r, "--depth", %r, "--particles", %r, "--streaks_db", %r,
+                    "--intensity", "5,100", "--output", %r, "--noverbose"])
+assert list(a.sequences) == ["scene-0001", "scene-0002"], a.sequences
+assert len(a.images["scene-0001"]) == 3 and len(a.images["scene-0002"]) == 1 and a.images["scene-0001"][0].endswith(".jpg")
+assert a.depth["scene-0001"][0].endswith(".npy") and os.path.isfile(a.depth["scene-0001"][0])
+assert [w["fallrate"] for w in a.weather] == [5, 100]
+assert all(len(a.particles[s]) == 2 and all(p.endswith("_camera0.xml") for p in a.particles[s]) for s in a.sequences)
+assert a.settings["cam_focal"] == 5.5 and a.settings["cam_f_number"] == 1.8 and a.settings["render_scale"] == 1
+print("OK")
+""" % (DROPIN, ROOT, os.path.join(ROOT, "oracle", "ref_shims"), REF, REF, DROPIN, REF, paths["dataset_root"], os.path.join(root, "depth"),
+       paths["particles"], paths["streaks_db"], os.path.join(root, "out"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=180)
+    assert out.returncode == 0 and "OK" in out.stdout, out.stdout[-2000:] + out.stderr[-3000:]
+
+
 def _args(paths, dataset, fallrate, seq="seq1"):
     from rain_rendering_b200 import synth
     cam = synth.CAMERAS[dataset]

@@ -130,3 +130,23 @@ def test_public_header_is_plain_c(tmp_path):
     assert out.returncode == 0, out.stderr
     ver, rec, sim, xf, k = out.stdout.split()
     assert (int(rec), int(sim), int(xf)) == (128, 120, 32) and int(ver) >= 100 and abs(float(k) - 0.041670) < 1e-5
+
+
+def test_integration_md_camera_stub_matches_the_header():
+    """The ctypes stub a maintainer would copy out of INTEGRATION.md must describe rr_camera exactly (a stub eight bytes short
+    makes rr_set_camera read past the caller's struct)."""
+    import ctypes as C
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    m = re.search(r"class Camera\(C\.Structure\):.*?\n(?=assert C\.sizeof)", md, re.S)
+    assert m, "INTEGRATION.md no longer shows the Camera stub"
+    ns = {"C": C}
+    exec(m.group(0), ns)
+    stub = ns["Camera"]
+    assert C.sizeof(stub) == C.sizeof(_lib.Camera) == 96
+    assert [(n, t) for n, t in stub._fields_] == [(n, t) for n, t in _lib.Camera._fields_]
+    # and the header says the same: 2 + 2 int32 around ten doubles
+    hdr = open(os.path.join(root, "include", "rain_b200.h")).read()
+    body = hdr[hdr.index("typedef struct rr_camera {"):hdr.index("} rr_camera;")]
+    assert len(re.findall(r"\bdouble\s+\w+;", body)) == 10 and "int32_t W, H;" in body and "int32_t render_scale;" in body and "int32_t reserved;" in body

@@ -52,3 +52,53 @@ def test_jobs_are_spread_over_gpus_with_the_dropin_on_the_path(tmp_path):
         assert rec["gpu"] == str(gpu) and rec["args"] == args
         assert rec["pp"][0].endswith(os.path.join("rain_rendering_b200", "dropin")) and os.path.isdir(os.path.join(rec["pp"][1], "oracle"))
         assert (tmp_path / ("automate_error_%s.txt" % L.log_pattern(args))).exists()
+
+
+import pytest
+
+
+@pytest.mark.gpu
+def test_launcher_really_renders_two_concurrent_jobs_on_the_gpu(tmp_path):
+    """Two jobs of the main_threaded.py split (two frame ranges of one intensity) as two concurrent child processes on GPU 0,
+    each driving the drop-in Generator over its own range -- through the launcher's own process management, environment
+    (drop-in first on PYTHONPATH, RAIN_B200_DEVICE) and log files.  The reference's main.py is not on the GPU box, so the
+    children run a stand-in that does what main.py:226-231 does with an argument object built for a synthetic tree."""
+    import cv2
+    import numpy as np
+    from rain_rendering_b200 import synth
+    root = str(tmp_path)
+    W, H, nf = 320, 192, 6
+    paths = synth.write_dataset(root, "customdb", "seq1", W, H, nf, 25, 500, seed=8, n_sim_frames=2)
+    tools = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools")
+    fake = tmp_path / "main.py"
+    fake.write_text(
+        "import sys, json, argparse\n"
+        "sys.path.insert(0, %r)\n"
+        "import dropin_e2e\n"
+        "p = argparse.ArgumentParser()\n"
+        "p.add_argument('--intensity', type=int); p.add_argument('--frame_start', type=int, default=0); p.add_argument('--frame_end', type=int)\n"
+        "p.add_argument('--conflict_strategy'); p.add_argument('--noverbose', action='store_true'); p.add_argument('--dataset')\n"
+        "r = p.parse_args()\n"
+        "from common.generator import Generator          # resolves to the drop-in: the launcher put it first on PYTHONPATH\n"
+        "a = dropin_e2e.make_args(json.load(open(%r)), 'customdb', r.intensity)\n"
+        "a.conflict_strategy, a.frame_start, a.frame_end, a.verbose = r.conflict_strategy, r.frame_start, r.frame_end, False\n"
+        "g = Generator(a); g.run(); print('RENDERED', g.last_stats['frames'])\n" % (tools, str(tmp_path / "paths.json")))
+    import json
+    json.dump(paths, open(str(tmp_path / "paths.json"), "w"))
+    os.environ["RAIN_B200_BATCH"] = "2"
+    try:
+        jobs = L.build_jobs(["--dataset", "customdb", "--intensity", "25", "--scene_threaded", "--frame_start", "0", "--frame_end", str(nf)])
+        assert len(jobs) == 1                                    # 6 frames < 41: one range; split it by hand into two ranges
+        jobs = [L._set(L._set(jobs[0], "--frame_start", 0), "--frame_end", 3), L._set(L._set(jobs[0], "--frame_start", 3), "--frame_end", nf)]
+        done = L.run_jobs(jobs, n_gpus=1, jobs_per_gpu=2, main_py=str(fake), cwd=str(tmp_path), poll_s=0.1)
+    finally:
+        del os.environ["RAIN_B200_BATCH"]
+    assert [d[2] for d in done] == [0, 0], [(tmp_path / ("automate_error_%s.txt" % L.log_pattern(j))).read_text()[-1500:] for j in jobs]
+    for j in jobs:
+        assert "RENDERED 3" in (tmp_path / ("automate_log_%s.txt" % L.log_pattern(j))).read_text()
+    out_dir = os.path.join(paths["output"], "customdb", "seq1", "rain", "25mm")
+    imgs = [cv2.imread(os.path.join(out_dir, "rainy_image", "%06d.png" % i)) for i in range(nf)]
+    assert all(im is not None and im.shape == (H, W, 3) for im in imgs)
+    assert all(os.path.exists(os.path.join(out_dir, "rain_mask", "%06d.png" % i)) for i in range(nf))
+    assert all(np.abs(im.astype(int) - cv2.imread(os.path.join(paths["dataset_root"], "customdb", "seq1", "rgb", "%06d.png" % i)).astype(int)).mean() > 0.1
+               for i, im in enumerate(imgs))                     # really rendered: rain and fog changed the frames

@@ -184,6 +184,26 @@ def test_degenerate_streaks_are_skipped_like_the_reference():
     ctx.close()
 
 
+def test_two_contexts_on_two_devices_in_one_process():
+    """The opt-in to > 48 KB of dynamic shared memory (k_fog, k_raster) is a per-DEVICE function attribute: a process-wide
+    "set once" flag left the second GPU of a process without it (round 1).  Contexts on devices 0 and 1, rendered
+    alternately, must both match the single-device result.  Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    sc = Scenario(384, 256, 2, 900, fallrate=25)
+    recs, offs = sc.records()
+    ctx0 = sc.context(device=0)
+    ctx1 = sc.context(device=1)
+    a0 = ctx0.render_frames(sc.bgr, sc.depth, recs, offs)
+    a1 = ctx1.render_frames(sc.bgr, sc.depth, recs, offs)
+    b0 = ctx0.render_frames(sc.bgr, sc.depth, recs, offs)
+    for k in ("bgr", "mask", "u8"):
+        assert np.array_equal(a0[k], a1[k]) and np.array_equal(a0[k], b0[k])
+    _check_frame(a1, 0, sc.oracle_frame(0, "canonical"))
+    ctx1.close(); ctx0.close()
+
+
 def test_determinism_and_batch_independence():
     sc = Scenario(512, 256, 3, 900, fallrate=25)
     ctx = sc.context()

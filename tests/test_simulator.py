@@ -168,19 +168,17 @@ def test_drop_sizes_follow_marshall_palmer_and_counts_follow_the_rate():
     b = (W + 4) / f_px * (v * T / 1000.0)
     vol = np.where(zmax > z0, a * (zmax ** 3 - z0 ** 3) / 3 + b * (zmax ** 2 - z0 ** 2) / 2, 0.0)
     dens = 8000 * np.exp(-lam * centres) / v * vol
-    # candidates are drawn from `dens`; imaged streaks are the candidates with an end point on the sensor and wide enough:
-    # compare the CANDIDATE-level shape through the acceptance-free region (every candidate with D >= 1.2 mm whose zmax is the
-    # far plane is accepted with the same geometric probability up to the v T band), i.e. test the tail shape
-    sel = (d_mm >= 1.2) & (d_mm < 6.0)
-    obs = np.histogram(d_mm[sel], bins=edges[edges >= 1.2 - 1e-9])[0].astype(float)
+    # Candidates are drawn from `dens` and placed uniformly in the region the volume term describes; every candidate in it is
+    # imaged (it is wide enough by construction of the region and an end point falls on the sensor) except those in the
+    # two-pixel side margins, a diameter-independent fraction: the imaged diameters follow `dens` itself.
+    obs = np.histogram(d_mm, bins=edges)[0].astype(float)
     cdf = np.concatenate([[0], np.cumsum((dens[1:] + dens[:-1]) / 2 * np.diff(centres))])
-    sub = edges[edges >= 1.2 - 1e-9]
-    exp = np.diff(np.interp(sub, centres, cdf))
+    exp = np.diff(np.interp(edges, centres, cdf))
     exp = exp / exp.sum() * obs.sum()
     keep = exp > 20
     chi2 = ((obs[keep] - exp[keep]) ** 2 / exp[keep]).sum()
-    dof = keep.sum() - 1
-    assert chi2 < dof + 6 * np.sqrt(2 * dof) + 0.02 * obs.sum() * 0.05, (chi2, dof)     # statistical scatter + a 5 % model tolerance (acceptance band)
+    dof = int(keep.sum()) - 1
+    assert dof >= 10 and chi2 / dof < 3.0, (chi2, dof, obs[keep][:8], exp[keep][:8])      # statistical scatter gives ~1; a 3 % shape error gives > 5
     # counts vs rate
     rates = [5, 10, 25, 50, 100]
     means, counts = [], []

@@ -121,3 +121,35 @@ def test_native_loader_is_much_faster_than_etree(tmp_path):
     _same(a, b)
     assert (t1 - t0) < (t2 - t1), (t1 - t0, t2 - t1)
     print("native %.3f s, etree+numpy %.3f s for %.1f MB" % (t1 - t0, t2 - t1, os.path.getsize(xml) / 1e6))
+
+
+def test_binary_particles_cache_follows_the_reference_pickle_rules(tmp_path):
+    """The reference caches the parsed simulation beside the XML and reuses it while version, md5 of the XML and image shape
+    are unchanged (common/bad_weather.py:155-178); ours is a binary file of packed records with the same three conditions
+    (plus the render scale, which the reference folds into the image shape)."""
+    import os
+    import time
+    parts = synth.make_particles(640, 480, 3, 120, 2.0, seed=9)
+    x = str(tmp_path / "sim_camera0.xml")
+    synth.write_particles_xml(parts, x, 2.0)
+    plain, ids = S.load_streaks_from_xml(x, 1, 640, 480, with_ids=True)
+    assert not os.path.exists(x + S.CACHE_SUFFIX)
+    first, ids1 = S.load_streaks_from_xml(x, 1, 640, 480, with_ids=True, use_cache=True)
+    assert os.path.exists(x + S.CACHE_SUFFIX) and ids1 == ids
+    t = os.path.getmtime(x + S.CACHE_SUFFIX)
+    again, ids2 = S.load_streaks_from_xml(x, 1, 640, 480, with_ids=True, use_cache=True)
+    assert os.path.getmtime(x + S.CACHE_SUFFIX) == t and ids2 == ids
+    for a, b, c in zip(plain, first, again):
+        assert a.tobytes() == b.tobytes() == c.tobytes()
+    # another image shape or render scale: the cache is rebuilt, and holds the new records
+    time.sleep(0.01)
+    other = S.load_streaks_from_xml(x, 1, 512, 384, use_cache=True)
+    assert other[0].tobytes() == S.load_streaks_from_xml(x, 1, 512, 384)[0].tobytes() and other[0].tobytes() != plain[0].tobytes()
+    # a changed XML (md5) invalidates it
+    parts2 = synth.make_particles(640, 480, 3, 80, 2.0, seed=10)
+    synth.write_particles_xml(parts2, x, 2.0)
+    new = S.load_streaks_from_xml(x, 1, 512, 384, use_cache=True)
+    assert new[0].tobytes() == S.load_streaks_from_xml(x, 1, 512, 384)[0].tobytes() and len(new[0]) != len(other[0])
+    # garbage in the cache file is not fatal
+    open(x + S.CACHE_SUFFIX, "wb").write(b"not an npz")
+    assert S.load_streaks_from_xml(x, 1, 512, 384, use_cache=True)[0].tobytes() == new[0].tobytes()
