@@ -292,6 +292,15 @@ def run_gpu(args):
     ms_dev = e0.elapsed_time(e1)
     launches = ctx.kernel_launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
+    # every stage's own duration: the same step a few more times with the streak chain on the main stream (in the timed region
+    # above it runs beside the frame chain, so the stage times there overlap and add up to more than the step)
+    ctx.set_option("serial", 1)
+    solo_ms = {k: 0.0 for k in ctx.timings()}
+    for _ in range(3):
+        step_device(1)
+        for k, v in ctx.timings().items():
+            solo_ms[k] += v / 3.0
+    ctx.set_option("serial", 0)
     # ---- end-to-end arm: pinned HOST buffers through the public API ---------------------------------
     # rr_submit_frames_io / rr_wait_frames with two sets of host buffers: while batch k renders, batch k+1 is
     # copied in and batch k-1 is copied out.  Every step builds its streak records from the simulator frames
@@ -389,7 +398,12 @@ def run_gpu(args):
                         "inputs": "uint8 BGR image + uint16 depth samples (what the PNG files hold) + streak records built per step from the simulator frames",
                         "outputs": "uint8 BGR image + rain mask as plt.imsave's colormap index (uint8) and its (min, max) -- what Generator.run saves",
                         "api": "rr_host_assemble_batch + rr_submit_frames_io / rr_wait_frames, two host buffer sets"},
+                "stage_ms_solo": {k: v for k, v in solo_ms.items() if k not in ("h2d", "d2h", "total")},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                             "kernel_ms_in_step": kern[dom], "kernel_ms_solo": solo_ms[dom],
+                             "frac_solo": (balg * batch / (solo_ms[dom] / 1000.0) / 1e9) / peak if solo_ms[dom] > 0 else None,
+                             "note": "stage_ms / achieved: durations inside the timed region, where the streak chain (raster, blur) runs beside the frame chain "
+                                     "(fog, env, setup) on a second stream and the stages slow each other; *_solo: the same stage alone",
                              "traffic": traffic, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
                              "algorithmic_bytes_per_frame": balg, "whole_step_frac": (balg * batch / (ms_dev / args.steps / 1000.0) / 1e9) / peak},
                 "stage_ms": kern}

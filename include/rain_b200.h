@@ -240,6 +240,9 @@ int rr_simulate_records_device(rr_context *ctx, const rr_sim_params *p, int64_t 
                                rr_streak_rec **d_records, int32_t *h_offsets, double *expected_per_frame);
 
 int rr_debug_read(rr_context *ctx, int what, int frame, void *dst, size_t bytes);
+/* Run-time options.  "serial" (0 / 1): 1 = the streak chain runs on the main stream, one kernel at a time (what a profiler sees;
+ * rr_timings then gives every stage's own duration); 0 (default) = it runs beside the frame chain on a second stream. */
+int rr_set_option(rr_context *ctx, const char *name, int value);
 int rr_timings(rr_context *ctx, float *ms_per_stage /* RR_T_COUNT */);
 int rr_kernel_launches(rr_context *ctx, long long *count);   /* kernels launched since rr_create */
 int rr_stream(rr_context *ctx, void **cuda_stream);

@@ -115,6 +115,7 @@ def load() -> C.CDLL:
         "rr_simulate_particles": [vp, C.POINTER(SimParams), C.c_int64, C.c_int, C.c_int, vp, i32p, C.POINTER(C.c_double)],
         "rr_simulate_records_device": [vp, C.POINTER(SimParams), C.c_int64, C.c_int, C.c_int, f64p, C.c_int, C.c_double, C.c_double,
                                        C.POINTER(vp), i32p, C.POINTER(C.c_double)],
+        "rr_set_option": [vp, C.c_char_p, C.c_int],
         "rr_timings": [vp, f32p],
         "rr_kernel_launches": [vp, C.POINTER(C.c_longlong)],
         "rr_stream": [vp, C.POINTER(vp)],

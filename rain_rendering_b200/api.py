@@ -280,6 +280,9 @@ class RainContext:
                           d_out_bgr, d_out_mask, d_out_u8, d_out_idx8, d_out_u16, d_out_range, None, None, None, None, 0)
         _lib.check(self.lib.rr_render_frames_device_io(self.h, len(offsets) - 1, C.byref(io), 1 if sync else 0), "rr_render_frames_device_io")
 
+    def set_option(self, name: str, value: int):
+        _lib.check(self.lib.rr_set_option(self.h, name.encode(), int(value)), "rr_set_option")
+
     def timings(self):
         ms = np.zeros(len(_lib.T_NAMES), np.float32)
         _lib.check(self.lib.rr_timings(self.h, _lib.ptr(ms)), "rr_timings")

@@ -57,7 +57,7 @@ struct rr_context {
     rr_fog_consts fogc;
     // k_fog's tile load: TMA boxes of the reflect-padded extinction planes (RR_FOG_TMA=0 selects the register-staged form)
     bool fog_tma = true;
-    CUtensorMap fog_map;
+    CUtensorMap fog_map, fog_map_roll;     // boxes of 88 x 56 (k_fog) and 88 x 32 (k_fog_roll) floats of the padded planes
     float *d_fext_lut = nullptr;
     int max_batch = 0, H_env = 0, W_env = 0, cyl_w = 0;
     int32_t *d_env_src = nullptr;
@@ -252,6 +252,7 @@ int rr_destroy(rr_context *c) {
 int rr_alloc_streak_db(rr_context *c, int n_tex, const int32_t *heights, int width) {
     if (!c || n_tex <= 0 || n_tex > 255 || !heights || width <= 0) { set_err("rr_alloc_streak_db: bad arguments"); return RR_ERR_ARG; }
     CK(cudaSetDevice(c->device));
+    if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_plan); }
     if (c->d_db) { cudaFree(c->d_db); cudaFree(c->d_tex_off); cudaFree(c->d_tex_h); c->d_db = nullptr; }
     std::vector<int32_t> off(n_tex);
     size_t total = 0;
@@ -387,6 +388,8 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
         // extinction planes with the 12-pixel reflected halo materialised and a 16-byte pitch: every haloed fog tile is one TMA box
         const char *env = getenv("RR_FOG_TMA");
         c->fog_tma = !(env && atoi(env) == 0);
+        const char *roll = getenv("RR_FOG_ROLL");
+        b.fog_roll = c->fog_tma && !(roll && atoi(roll) == 0);
         b.fext_Wp = (W + 24 + 3) & ~3; b.fext_Hp = H + 24;
         CK(dev_alloc(c, &b.fext, F * (size_t)b.fext_Wp * b.fext_Hp));
         CK(dev_alloc(c, &c->d_fext_lut, (size_t)65536));
@@ -395,6 +398,8 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
         b.fext_lut = c->d_fext_lut;
         if (c->fog_tma) {
             int r = make_plane_map(&c->fog_map, b.fext, b.fext_Wp, b.fext_Hp, max_batch, 88, 56);
+            if (r != RR_OK) return r;
+            r = make_plane_map(&c->fog_map_roll, b.fext, b.fext_Wp, b.fext_Hp, max_batch, 88, 32);
             if (r != RR_OK) return r;
         }
     }
@@ -405,7 +410,7 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
         b.env_bulk = !(env && atoi(env) == 0);
     }
     CK(dev_alloc(c, &b.env8, F * (size_t)He * b.env_pitch * 4));
-    CK(dev_alloc(c, &b.pref, F * 4 * (size_t)He * (We + 1)));
+    CK(dev_alloc(c, &b.pref, F * RR_PREF_N * (size_t)He * (We + 1)));
     CK(dev_alloc(c, &b.rowtot, F * He));
     CK(dev_alloc(c, &b.ambient, F));
     b.err_flag = nullptr;
@@ -514,7 +519,7 @@ static int run_pipeline(rr_context *c, int F, int n_streaks, bool timed) {
         CK(rr_launch_plan(b, t, c->camd, n_streaks, ss));
     }
     CK(rr_launch_stats(b, F, W, H, rs, (double *)b.bgf, st));
-    CK(rr_launch_fog(b, c->fogc, F, W, H, c->fog_tma ? &c->fog_map : nullptr, st));
+    CK(rr_launch_fog(b, c->fogc, F, W, H, c->fog_tma ? &c->fog_map : nullptr, &c->fog_map_roll, st));
     if (timed) CK(cudaEventRecord(c->ev[RR_T_ENV], st));
     CK(rr_launch_env(b, t, F, W, H, c->W_env, st));
     if (timed) CK(cudaEventRecord(c->ev[RR_T_SETUP], st));
@@ -554,7 +559,7 @@ static int run_pipeline(rr_context *c, int F, int n_streaks, bool timed) {
     if (timed) CK(cudaEventRecord(c->ev[RR_T_D2H], st));
     // stats 2, fog constants + extinction + fog 3, env map + prefix + ambient 3, plan + set-up 2, scan 1, raster + blur 2,
     // composite + frame mean 2, epilogue 1
-    c->launches += 2 + 3 + 3 + (n_streaks ? 2 : 0) + 1 + (n_streaks ? 2 : 0) + 2 + 1;
+    c->launches += 2 + 3 + (b.fog_roll ? 1 : 0) + 3 + (n_streaks ? 2 : 0) + 1 + (n_streaks ? 2 : 0) + 2 + 1;
     c->last_n_streaks = n_streaks;
     return RR_OK;
 }
@@ -570,7 +575,7 @@ static rr_frame_bufs sub_view(const rr_context *c, const rr_frame_bufs &b, int f
     v.bg_sum += (size_t)f0 * 4; v.acs += (size_t)f0 * 4;
     v.chan_sum += (size_t)f0 * 4; v.rainy += (size_t)f0 * 3 * np; v.bg8 += (size_t)f0 * np * 4; v.fblur += (size_t)f0 * np; v.frame0 += f0;
     v.env8 += (size_t)f0 * c->H_env * b.env_pitch * 4;
-    v.pref += (size_t)f0 * 4 * c->H_env * (c->W_env + 1); v.rowtot += (size_t)f0 * c->H_env; v.ambient += f0;
+    v.pref += (size_t)f0 * RR_PREF_N * c->H_env * (c->W_env + 1); v.rowtot += (size_t)f0 * c->H_env; v.ambient += f0;
     v.plans += s0; v.fcp += s0; v.sizes += s0; v.boxes += s0; v.scan += (size_t)scan_base * 6;
     v.tile_sum += (size_t)f0 * tiles; v.tile_min += (size_t)f0 * tiles; v.tile_max += (size_t)f0 * tiles; v.frame_mean += f0;
     v.maskd += (size_t)f0 * np; v.mask_range += (size_t)f0 * 2;
@@ -909,7 +914,7 @@ int rr_fog_only(rr_context *c, int n_frames, const uint8_t *bgr, const float *de
     b.bgr = c->d_bgr; b.depth = c->d_depth; b.depth_u16 = 0; b.bgf = c->d_bgf;
     CK(rr_launch_stats(b, n_frames, c->cam.W, c->cam.H, rs2 == 4 ? 2 : 1, c->d_bgf, st));
     b.frame0 = 0;
-    CK(rr_launch_fog(b, c->fogc, n_frames, c->cam.W, c->cam.H, c->fog_tma ? &c->fog_map : nullptr, st));
+    CK(rr_launch_fog(b, c->fogc, n_frames, c->cam.W, c->cam.H, c->fog_tma ? &c->fog_map : nullptr, &c->fog_map_roll, st));
     c->launches += 5;
     CK(cudaMemcpyAsync(out_planar, b.rainy, F * 3 * np * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -1021,6 +1026,16 @@ int rr_debug_read(rr_context *c, int what, int frame, void *dst, size_t bytes) {
     CK(cudaStreamSynchronize(c->stream));
     CK(cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost));
     return RR_OK;
+}
+
+int rr_set_option(rr_context *c, const char *name, int value) {
+    if (!c || !name) { set_err("rr_set_option: bad arguments"); return RR_ERR_ARG; }
+    CK(cudaSetDevice(c->device));
+    while (c->inflight) { int q = wait_oldest(c, false); if (q != RR_OK) return q; }
+    drain(c);
+    if (!strcmp(name, "serial")) { c->serial = value != 0; return RR_OK; }
+    set_err("rr_set_option: unknown option '%s'", name);
+    return RR_ERR_ARG;
 }
 
 int rr_timings(rr_context *c, float *ms) {

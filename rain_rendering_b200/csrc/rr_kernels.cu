@@ -7,6 +7,14 @@
 // ------------------------------------------------------------------------------------------
 // TMA (cp.async.bulk[.tensor]) + mbarrier, inline PTX for sm_100a
 // ------------------------------------------------------------------------------------------
+// streaming (evict-first) store for data written once and read much later or never by this GPU: keeps it from pushing
+// reusable lines out of L2.  RR_NO_STREAM_STORES=1 at build time turns them into plain stores (A/B measurements).
+#ifdef RR_NO_STREAM_STORES
+#define RR_STREAM_STORE(ptr, val) (*(ptr) = (val))
+#else
+#define RR_STREAM_STORE(ptr, val) __stcs((ptr), (val))
+#endif
+
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -421,12 +429,14 @@ __global__ void __launch_bounds__(256) k_fext_pad(const void *depth, const float
     const int f = blockIdx.z, py = blockIdx.y;
     const int px = blockIdx.x * blockDim.x + threadIdx.x;
     if (px >= Wp) return;
+    // the source row is the block's (one reflected row index per block); columns reflect per thread
+    const size_t row0 = ((size_t)f * H + r101(py - FOG_R, H)) * W;
     float v = 0.f;
     if (px < W + 2 * FOG_R) {
-        const size_t src = ((size_t)f * H + r101(py - FOG_R, H)) * W + r101(px - FOG_R, W);
-        if (U16) v = lut[((const uint16_t *)depth)[src]];
+        const int sx = r101(px - FOG_R, W);
+        if (U16) v = __ldg(&lut[__ldg((const uint16_t *)depth + row0 + sx)]);
         else {
-            const float d = __fdiv_rn(((const float *)depth)[src], 1000.f);
+            const float d = __fdiv_rn(((const float *)depth)[row0 + sx], 1000.f);
             v = (float)exp((double)__fmul_rn(neg_beta32, d));
         }
     }
@@ -437,7 +447,8 @@ __global__ void __launch_bounds__(256) k_fext_pad(const void *depth, const float
 #define FOG_BYTES_A_TMA (sizeof(float) * FOG_EH * (FOG_ED + FOG_FS))
 
 template <bool TMA>
-__global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, rr_fog_consts fc, int W, int H, const __grid_constant__ CUtensorMap fmap) {
+__global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, rr_fog_consts fc, int W, int H, int skip_linear,
+                                                               const __grid_constant__ CUtensorMap fmap) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     constexpr int ES = TMA ? FOG_ED : FOG_ES;
     constexpr size_t BYTES_A = TMA ? FOG_BYTES_A_TMA : FOG_BYTES_A;
@@ -460,6 +471,7 @@ __global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, 
     // blur(A*d) = A*blur(d) up to float64 rounding (shortcut 3).  Otherwise each channel is
     // blurred on its own: l_in_c = clip(A_c * (1 - f_ext), 0, 1) is then formed while the row pass loads its inputs.
     const bool linear = Acs[0] >= 0 && Acs[0] <= 1 && Acs[1] >= 0 && Acs[1] <= 1 && Acs[2] >= 0 && Acs[2] <= 1;
+    if (skip_linear && linear) return;                    // k_fog_roll renders this frame (block-uniform)
     // All global loads of the tile are issued up front, back to back (the kernel runs 4 warps per scheduler, too
     // few to hide a load that is consumed right away): the haloed extinction values, and the tile's own image
     // bytes, which wait in shared memory for the compose step at the very end.  A warp takes whole rows (the
@@ -653,12 +665,189 @@ __global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, 
     }
 }
 
+// ---- rolling form of the fog stage --------------------------------------------------------------------------------------
+// k_fog spends 1.75 row passes per output row: every 64 x 32 tile recomputes the row passes of its 24 halo rows, which its
+// vertical neighbours compute too.  Here a CTA owns a 64-column strip and walks DOWN it: the row-pass results (float32 pass of
+// f_ext, float64 pass of 1 - f_ext) live in two 32-row slots of a ring in shared memory, every step row-filters ONE new block
+// of 32 padded rows (one TMA box of the reflect-padded plane, 88 x 32) and column-filters the 56-row window that the ring now
+// holds -- one row pass per output row, a quarter of the stage's float64 work gone.  A strip is cut into FOGR_SEG-tile
+// segments so that the grid keeps the machine full (each segment pays one extra block).  Only the frames whose in-scatter
+// images are one image times a scalar ("linear", the common case) take this form; the others leave at once and are
+// rendered by k_fog, which in turn skips the linear frames.
+#define FOGR_SEG 6            // tiles per CTA (H = 375: 12 tiles -> 2 segments)
+#define FOGR_BR 32            // rows per block = FOG_TY
+#define FOGR_BYTES_FH (sizeof(float) * 2 * FOGR_BR * FOG_FS)          // float32 row-pass ring   [2][32][FOG_FS]
+#define FOGR_BYTES_LH (sizeof(double) * 2 * FOGR_BR * FOG_FS)         // float64 row-pass ring   [2][32][FOG_FS]
+#define FOGR_BYTES_E (sizeof(float) * FOGR_BR * FOG_ED)               // the block as TMA delivers it [32][88]
+#define FOGR_BYTES_D (sizeof(double) * FOGR_BR * FOG_LS)              // 1 - f_ext of the block, widened, padded layout
+#define FOGR_SMEM (FOGR_BYTES_E + FOGR_BYTES_FH + FOGR_BYTES_LH + FOGR_BYTES_D + FOG_TY * FOG_TX * 3)
+
+__device__ __forceinline__ bool fog_frame_linear(const rr_frame_bufs &b, int f, double Acs[3]) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) Acs[c] = b.acs[f * 4 + c];
+    return Acs[0] >= 0 && Acs[0] <= 1 && Acs[1] >= 0 && Acs[1] <= 1 && Acs[2] >= 0 && Acs[2] <= 1;
+}
+
+__global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog_roll(rr_frame_bufs b, rr_fog_consts fc, int W, int H, int tiles_y,
+                                                                    const __grid_constant__ CUtensorMap fmap) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float *E = (float *)smem_raw;                                            // [32][FOG_ED]
+    float *FH = (float *)(smem_raw + FOGR_BYTES_E);                          // [2][32][FOG_FS]
+    double *LH = (double *)(smem_raw + FOGR_BYTES_E + FOGR_BYTES_FH);        // [2][32][FOG_FS]
+    double *D = (double *)(smem_raw + FOGR_BYTES_E + FOGR_BYTES_FH + FOGR_BYTES_LH);   // [32][FOG_LS]
+    uint8_t *IB = smem_raw + FOGR_BYTES_E + FOGR_BYTES_FH + FOGR_BYTES_LH + FOGR_BYTES_D;
+    __shared__ __align__(8) unsigned long long blk_bar;
+    const int f = blockIdx.z, tid = threadIdx.x;
+    double Acs[3];
+    if (!fog_frame_linear(b, f, Acs)) return;                                // k_fog renders this frame (block-uniform)
+    const int x0 = blockIdx.x * FOG_TX;
+    const int t_first = blockIdx.y * FOGR_SEG, t_last = (t_first + FOGR_SEG < tiles_y ? t_first + FOGR_SEG : tiles_y) - 1;
+    const uint8_t *bgr = b.bgr + (size_t)f * W * H * 3;
+    constexpr int NW = FOG_THREADS / 32, BR = FOG_TY / NW, BC = FOG_TX * 3 / 32;
+    const int lane = tid & 31, warp = tid >> 5;
+    const int cx = tid & (FOG_TX - 1), cy0 = (tid / FOG_TX) * 8, pcx = FOG_PAD(cx);
+    if (tid == 0) mbar_init(&blk_bar, 1);
+    __syncthreads();
+    unsigned uses = 0;                                                       // completed waits on blk_bar (its phase parity)
+    auto request = [&](int blk) {                                            // one thread: padded rows [32 blk, 32 blk + 32) of the strip
+        mbar_expect_tx(&blk_bar, (unsigned)FOGR_BYTES_E);
+        tma_load_3d(E, &fmap, x0, blk * FOGR_BR, b.frame0 + f, &blk_bar);
+    };
+    // row passes of the block that sits in E, into ring slot `slot`
+    auto row_passes = [&](int slot) {
+        mbar_wait(&blk_bar, uses & 1u);
+        uses++;
+        for (int i = tid; i < FOGR_BR * FOG_EW; i += FOG_THREADS) {
+            const int ey = i / FOG_EW, ex = i - ey * FOG_EW;
+            double d = (double)(1.0f - E[ey * FOG_ED + ex]);                 // (1 - f_ext) is a float32 op in numpy (:71)
+            d = d < 0 ? 0 : (d > 1 ? 1 : d);                                 // clip(A d, 0, 1) = A clip(d, 0, 1) for 0 <= A <= 1
+            D[ey * FOG_LS + FOG_PAD(ex)] = d;
+        }
+        float *fh = FH + slot * FOGR_BR * FOG_FS;
+        for (int i = tid; i < FOGR_BR * (FOG_TX / 4); i += FOG_THREADS) {
+            const int ey = i / (FOG_TX / 4), ox = (i - ey * (FOG_TX / 4)) * 4;
+            double a[4];
+            fog_taps_f32<2, 0>(E + ey * FOG_ED + ox, a);
+#pragma unroll
+            for (int o = 0; o < 4; o++) fh[ey * FOG_FS + FOG_PAD(ox) + o] = (float)a[o];
+        }
+        __syncthreads();                                                     // E consumed, D complete
+    };
+    auto row_pass64 = [&](int slot) {
+        double *lh = LH + slot * FOGR_BR * FOG_FS;
+        for (int i = tid; i < FOGR_BR * (FOG_TX / 4); i += FOG_THREADS) {
+            const int ey = i / (FOG_TX / 4), ox = (i - ey * (FOG_TX / 4)) * 4;
+            const double *row = D + ey * FOG_LS + FOG_PAD(ox);
+            double v[28];
+#pragma unroll
+            for (int k = 0; k < 28; k++) v[k] = row[FOG_PAD(k)];
+#pragma unroll
+            for (int o = 0; o < 4; o++) {
+                double a = c_k64[0] * v[o];
+#pragma unroll
+                for (int t = 1; t < 25; t++) a = __fma_rn(c_k64[t], v[o + t], a);   // cv::RowFilter, fused like OpenCV's build (see k_fog)
+                lh[ey * FOG_FS + FOG_PAD(ox) + o] = a;
+            }
+        }
+    };
+    // prologue: block t_first into slot (t_first & 1)
+    if (tid == 0) request(t_first);
+    row_passes(t_first & 1);
+    if (tid == 0) request(t_first + 1);                                      // E is free again: the next block travels under the float64 pass
+    row_pass64(t_first & 1);
+    for (int t = t_first; t <= t_last; t++) {
+        const int y0 = t * FOG_TY;
+        // the tile's image bytes, requested now and parked in shared memory until the compose step
+        uint8_t bv[BR][BC];
+        if (!b.bgf) {
+#pragma unroll
+            for (int q = 0; q < BR; q++) {
+                const int row = warp + NW * q;
+                const bool rok = y0 + row < H;
+                const uint8_t *src = bgr + ((size_t)(rok ? y0 + row : 0) * W + x0) * 3;
+#pragma unroll
+                for (int j = 0; j < BC; j++) {
+                    const int col = lane + 32 * j;
+                    bv[q][j] = (rok && x0 * 3 + col < W * 3) ? src[col] : (uint8_t)0;
+                }
+            }
+        }
+        // block t + 1 (already requested) into the other slot
+        const int s1 = (t + 1) & 1;
+        row_passes(s1);
+        if (t < t_last && tid == 0) request(t + 2);
+        row_pass64(s1);
+        if (!b.bgf) {
+#pragma unroll
+            for (int q = 0; q < BR; q++)
+#pragma unroll
+                for (int j = 0; j < BC; j++) IB[(warp + NW * q) * (FOG_TX * 3) + lane + 32 * j] = bv[q][j];
+        }
+        __syncthreads();                                                     // both slots and IB complete
+        // window row r (0 .. 55) of tile t: block t + (r >> 5), row r & 31 of its slot
+        const int tpar = t & 1;
+        float fb[8];
+        {
+            double v[32];
+#pragma unroll
+            for (int k = 0; k < 32; k++) {
+                const int r = cy0 + k;
+                v[k] = (double)FH[(((tpar + (r >> 5)) & 1) * FOGR_BR + (r & 31)) * FOG_FS + pcx];
+            }
+#pragma unroll
+            for (int o = 0; o < 8; o++) {
+                double a = c_k32d[0] * v[o];
+#pragma unroll
+                for (int tt = 1; tt < 25; tt++) a = __fma_rn(c_k32d[tt], v[o + tt], a);   // exact float32 products, ascending taps (fog_taps_f32)
+                fb[o] = (float)a;
+            }
+        }
+        if (b.fblur) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int gy = y0 + cy0 + k, gx = x0 + cx;
+                if (gy < H && gx < W) b.fblur[(size_t)f * W * H + (size_t)gy * W + gx] = fb[k];
+            }
+        }
+        {
+            double v[32];
+#pragma unroll
+            for (int k = 0; k < 32; k++) {
+                const int r = cy0 + k;
+                v[k] = LH[(((tpar + (r >> 5)) & 1) * FOGR_BR + (r & 31)) * FOG_FS + pcx];
+            }
+#pragma unroll
+            for (int o = 0; o < 8; o++) {
+                double acc = c_k64[12] * v[o + 12];                          // cv::SymmColumnFilter order
+#pragma unroll
+                for (int tt = 1; tt <= 12; tt++) acc += c_k64[12 + tt] * (v[o + 12 + tt] + v[o + 12 - tt]);
+                const int gy = y0 + cy0 + o, gx = x0 + cx;
+                if (gy < H && gx < W) {
+                    const size_t pix = (size_t)gy * W + gx;
+                    unsigned packed = 0;
+#pragma unroll
+                    for (int cc = 0; cc < 3; cc++) {
+                        const double I = b.bgf ? b.bgf[((size_t)f * 3 + cc) * W * H + pix] : rr_u8_unit(IB[((cy0 + o) * FOG_TX + cx) * 3 + cc]);
+                        double l = I * (double)fb[o] + Acs[cc] * acc;        // add_attenuation.py:85
+                        l = l < 0 ? 0 : (l > 1 ? 1 : l);
+                        b.rainy[((size_t)f * 3 + cc) * W * H + pix] = l;
+                        packed |= (unsigned)(uint8_t)(l * 255) << (8 * cc);  // bad_weather.py:744
+                    }
+                    ((unsigned *)b.bg8)[(size_t)f * W * H + pix] = packed;
+                }
+            }
+        }
+        __syncthreads();                                                     // the window is consumed: slot (t & 1) and IB may be overwritten
+    }
+}
+
 cudaError_t rr_launch_fext_lut(float *lut, float neg_beta32, cudaStream_t st) {
     k_fext_lut<<<256, 256, 0, st>>>(lut, neg_beta32);
     return cudaGetLastError();
 }
 
-cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, const CUtensorMap *fmap, cudaStream_t st) {
+cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, const CUtensorMap *fmap, const CUtensorMap *fmap_roll,
+                          cudaStream_t st) {
     static_assert(FOG_ES >= FOG_PAD(FOG_EW - 1) + 1 && FOG_LS >= FOG_PAD(FOG_EW - 1) + 1 && FOG_FS >= FOG_PAD(FOG_TX - 1) + 1, "fog strides");
     static_assert(sizeof(double) * FOG_EH * FOG_FS <= FOG_BYTES_A && sizeof(double) * FOG_EH * FOG_FS <= FOG_BYTES_A_TMA, "LH must fit in the E + FH region");
     static_assert(FOG_ED == FOG_EW && (FOG_ED * sizeof(float)) % 16 == 0 && FOG_BYTES_A_TMA % 8 == 0, "dense tile layout");
@@ -670,7 +859,12 @@ cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F
         if (b.depth_u16) k_fext_pad<true><<<g, 256, 0, st>>>(b.depth, b.fext_lut, dst, fc.neg_beta32, W, H, b.fext_Wp, b.fext_Hp);
         else k_fext_pad<false><<<g, 256, 0, st>>>(b.depth, b.fext_lut, dst, fc.neg_beta32, W, H, b.fext_Wp, b.fext_Hp);
         const size_t smem = FOG_BYTES_A_TMA + FOG_BYTES_B + FOG_TY * FOG_TX * 3;
-        k_fog<true><<<grid, FOG_THREADS, smem, st>>>(b, fc, W, H, *fmap);
+        if (b.fog_roll) {
+            // linear frames by the rolling kernel, the others by k_fog: each leaves the other's frames at once
+            dim3 gr(grid.x, (grid.y + FOGR_SEG - 1) / FOGR_SEG, F);
+            k_fog_roll<<<gr, FOG_THREADS, FOGR_SMEM, st>>>(b, fc, W, H, (int)grid.y, *fmap_roll);
+        }
+        k_fog<true><<<grid, FOG_THREADS, smem, st>>>(b, fc, W, H, b.fog_roll, *fmap);
     } else {
         const size_t n = (size_t)F * W * H;
         float *dst = b.fext + (size_t)b.frame0 * W * H;
@@ -681,7 +875,7 @@ cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F
         const size_t smem = FOG_BYTES_A + FOG_BYTES_B + FOG_TY * FOG_TX * 3;
         CUtensorMap dummy;
         memset(&dummy, 0, sizeof(dummy));
-        k_fog<false><<<grid, FOG_THREADS, smem, st>>>(v, fc, W, H, dummy);
+        k_fog<false><<<grid, FOG_THREADS, smem, st>>>(v, fc, W, H, 0, dummy);
     }
     return cudaGetLastError();
 }
@@ -803,7 +997,12 @@ __global__ void __launch_bounds__(256) k_env_map(const uint8_t *bg8, const int32
 #define EP_WARPS (EP_THREADS / 32)
 // shared staging of the tile's prefixes: 32 bytes per pixel plus 16 bytes after every 8 pixels, so that the
 // per-thread 16-byte stores (stride 272 bytes between lanes) and the per-warp linear reads are conflict free
-#define EP_STAGE_BYTES (EP_TILE * 32 + EP_THREADS * 16)
+#ifndef RR_PREF_N
+#define RR_PREF_N 4           // doubles per prefix entry: 4 = (w x, w y, w Y, w): one 32-byte sector per span end point; 3 drops w (k_setup then reads the
+                              // per-camera prefix of w): measured on B200, -0.03 ms in k_env_prefix, +0.05 ms in k_setup -- no gain, 4 stays
+#endif
+#define EP_ENTRY (RR_PREF_N * 8)
+#define EP_STAGE_BYTES (EP_TILE * EP_ENTRY + EP_THREADS * 16)
 // BULK: the row's pixels arrive by 1-D bulk copies (cp.async.bulk, the TMA unit) into two alternating shared-memory buffers,
 // signalled on mbarriers: tile t + 1 is in flight while tile t is converted.  Needs 16-byte aligned rows: env8 carries a
 // pitch of a multiple of 4 pixels.  Otherwise the register-staged form (global -> registers -> shared, next tile prefetched).
@@ -819,7 +1018,7 @@ __global__ void __launch_bounds__(EP_THREADS) k_env_prefix(const uint8_t *env8, 
     const int r = blockIdx.x, f = blockIdx.y;
     const uint8_t *row = env8 + ((size_t)f * H + r) * pitch * 4;          // pixels are 32-bit words (B, G, R, 0)
     const double *om = omega + (size_t)r * W_env;
-    double2 *p2 = (double2 *)pref + ((size_t)f * H + r) * (W_env + 1) * 2;
+    double *prow = pref + ((size_t)f * H + r) * (W_env + 1) * RR_PREF_N;
     double cx = 0, cy = 0, cY = 0, cw = 0;          // carry: prefix of everything left of the tile
     // The pixels of a tile travel global -> registers -> shared memory, and the registers are refilled with the NEXT
     // tile's pixels right after they have been parked, so that load runs under this tile's arithmetic.
@@ -878,11 +1077,12 @@ __global__ void __launch_bounds__(EP_THREADS) k_env_prefix(const uint8_t *env8, 
         const unsigned *wds = BULK ? (const unsigned *)(s_bytes + (size_t)(tile & 1) * EP_TILE * 4) + px0
                                    : (const unsigned *)s_bytes + (shift >> 2) + px0;
         double sx = 0, sy = 0, sY = 0, sw_ = 0;
-        unsigned char *st = s_stage + (size_t)tid * (EP_PER * 32 + 16);
+        unsigned char *st = s_stage + (size_t)tid * (EP_PER * EP_ENTRY + 16);
 #pragma unroll
         for (int k = 0; k < EP_PER; k++) {
-            ((double2 *)(st + k * 32))[0] = make_double2(sx, sy);
-            ((double2 *)(st + k * 32))[1] = make_double2(sY, sw_);
+            double *se = (double *)(st + k * EP_ENTRY);
+            se[0] = sx; se[1] = sy; se[2] = sY;
+            if (RR_PREF_N == 4) se[3] = sw_;
             if (px0 + k < n) {
                 const unsigned pxw = wds[k];
                 const double bb = rr_u8_unit((uint8_t)(pxw & 255u)), gg = rr_u8_unit((uint8_t)((pxw >> 8) & 255u)),
@@ -915,18 +1115,18 @@ __global__ void __launch_bounds__(EP_THREADS) k_env_prefix(const uint8_t *env8, 
         s_toff[tid][0] = ox + ex; s_toff[tid][1] = oy + ey; s_toff[tid][2] = oY + eY; s_toff[tid][3] = ow + ew;
         cx = tx_; cy = ty_; cY = tY_; cw = tw_;
         __syncthreads();
-        // ---- coalesced write-out: half-entries (16 bytes) in linear order ----
-        double2 *dst = p2 + (size_t)c0 * 2;
-        for (int h = tid; h < 2 * n; h += EP_THREADS) {
-            const int px = h >> 1, half = h & 1;
-            const double2 v = *(const double2 *)(s_stage + (size_t)px * 32 + (size_t)(px >> 3) * 16 + half * 16);
-            const double2 o = *(const double2 *)&s_toff[px >> 3][half * 2];
-            dst[h] = make_double2(o.x + v.x, o.y + v.y);
+        // ---- coalesced write-out: the tile's doubles in linear order (streaming stores: 1.1 GB per step that nothing re-reads soon) ----
+        double *dst = prow + (size_t)c0 * RR_PREF_N;
+        for (int h = tid; h < RR_PREF_N * n; h += EP_THREADS) {
+            const int px = h / RR_PREF_N, comp = h - px * RR_PREF_N;
+            const double v = *(const double *)(s_stage + (size_t)px * EP_ENTRY + (size_t)(px >> 3) * 16 + comp * 8);
+            RR_STREAM_STORE(&dst[h], s_toff[px >> 3][comp] + v);
         }
     }
     if (tid == 0) {
-        p2[(size_t)W_env * 2] = make_double2(cx, cy);
-        p2[(size_t)W_env * 2 + 1] = make_double2(cY, cw);
+        double *pe = prow + (size_t)W_env * RR_PREF_N;
+        pe[0] = cx; pe[1] = cy; pe[2] = cY;
+        if (RR_PREF_N == 4) pe[3] = cw;
         rowtot[(size_t)f * H + r] = cY;
     }
 }
@@ -939,13 +1139,13 @@ static cudaError_t launch_env_prefix(const uint8_t *env8, const double *omega, d
     return cudaGetLastError();
 }
 
+// sum over the map of omega * Y per frame: one warp, lanes take rows in stride, then a fixed shuffle tree (deterministic)
 __global__ void k_ambient(const double *rowtot, double *ambient, int H) {
-    int f = blockIdx.x;
-    if (threadIdx.x == 0) {
-        double s = 0;
-        for (int r = 0; r < H; r++) s += rowtot[(size_t)f * H + r];
-        ambient[f] = s;
-    }
+    const int f = blockIdx.x;
+    double s = 0;
+    for (int r = threadIdx.x; r < H; r += 32) s += rowtot[(size_t)f * H + r];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) ambient[f] = s;
 }
 
 cudaError_t rr_launch_env(const rr_frame_bufs &b, const rr_static_tabs &t, int F, int W, int H, int W_env, cudaStream_t st) {
@@ -995,13 +1195,16 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32, SETUP_MINB) k_setup(rr_frame
         if (ymin < 0) ymin = 0;
         if (ymax > rows - 1) ymax = rows - 1;
         const size_t stride = (size_t)(cols + 1);
-        const double4 *P = (const double4 *)b.pref + (size_t)f * rows * stride;
+        const double *P = b.pref + (size_t)f * rows * stride * RR_PREF_N;
         int ivl[RR_MAX_POLY + 2], ivh[RR_MAX_POLY + 2];
         for (int y = ymin + lane; y <= ymax; y += 32) {
             int k = rr_fcp_row(fc, y, ivl, ivh);
             for (int j = 0; j < k; j++) {
-                double4 a = P[(size_t)y * stride + ivl[j]], e = P[(size_t)y * stride + ivh[j] + 1];
-                sx += e.x - a.x; sy += e.y - a.y; sY += e.z - a.z; sw += e.w - a.w;
+                const double *a = P + ((size_t)y * stride + ivl[j]) * RR_PREF_N, *e = P + ((size_t)y * stride + ivh[j] + 1) * RR_PREF_N;
+                sx += e[0] - a[0]; sy += e[1] - a[1]; sY += e[2] - a[2];
+                // the solid angles do not depend on the frame: their row prefix is a per-camera table (L2 resident)
+                if (RR_PREF_N == 4) sw += e[3] - a[3];
+                else sw += t.omega_pref[(size_t)y * stride + ivh[j] + 1] - t.omega_pref[(size_t)y * stride + ivl[j]];
             }
         }
         sx = warp_sum(sx); sy = warp_sum(sy); sY = warp_sum(sY); sw = warp_sum(sw);
@@ -1679,7 +1882,7 @@ __global__ void k_epilogue(rr_frame_bufs b, int npix, int F) {
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         double v = b.rainy[((size_t)f * 3 + c) * npix + pix] - d;                   // :464
-        if (b.out_bgr) b.out_bgr[i * 3 + c] = (float)v;
+        if (b.out_bgr) RR_STREAM_STORE(&b.out_bgr[i * 3 + c], (float)v);
         if (b.out_u8) {
             double cl = v < 0 ? 0 : (v > 1 ? 1 : v);
             b.out_u8[i * 3 + c] = (uint8_t)(cl * 255);                              // plt.imsave float -> uint8
@@ -1688,7 +1891,7 @@ __global__ void k_epilogue(rr_frame_bufs b, int npix, int F) {
     // the rain mask in the forms a caller saves: float32, or what plt.imsave(path, rainy_mask) (generator.py:467) makes of
     // the float64 array -- Normalize: (m - min) / (max - min), zeros when flat; Colormap.__call__: int(t * 256), 256 -> 255
     const double m = b.maskd[i];
-    if (b.out_mask) b.out_mask[i] = (float)m;
+    if (b.out_mask) RR_STREAM_STORE(&b.out_mask[i], (float)m);
     if (b.out_idx8 || b.out_u16) {
         const double lo = b.mask_range[2 * f], hi = b.mask_range[2 * f + 1];
         double t = 0.0;
@@ -1720,6 +1923,8 @@ cudaError_t rr_prepare_device() {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_fog<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)(FOG_BYTES_A_TMA + FOG_BYTES_B + FOG_TY * FOG_TX * 3));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_fog_roll, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FOGR_SMEM);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_raster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RAS_SMEM_BYTES);
 }

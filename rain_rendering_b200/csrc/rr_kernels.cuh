@@ -24,12 +24,13 @@ struct rr_frame_bufs {
                                // TMA form [F][H + 24][Wp] reflect-padded planes (k_fext_pad), else [F][H][W] (k_fext)
     int frame0;                // first frame of this (sub-)batch inside fext
     int fext_Wp, fext_Hp;      // padded plane size (pitch a multiple of 4 floats = 16 bytes)
+    int fog_roll;              // 1: linear frames go through k_fog_roll (strip-walking form), 0: every frame through k_fog
     const float *fext_lut;     // [65536] exp table of the uint16 depth samples (per camera)
     float *fblur;              // [F][H][W] blurred extinction (debug / stage test)
     uint8_t *env8;             // [F][H][env_pitch][4] final environment map, (B, G, R, 0) words; env_pitch = W_env rounded up to 4 pixels
     int env_pitch;             // pixels per row of env8 (16-byte aligned rows: k_env_prefix fetches them with bulk copies)
     int env_bulk;              // k_env_prefix's row fetch: 1 = cp.async.bulk into two buffers, 0 = register-staged
-    double *pref;              // [F][H][W_env+1][4] row prefix sums of (omega*x, omega*y, omega*Y, omega), interleaved
+    double *pref;              // [F][H][W_env+1][RR_PREF_N] row prefix sums of (omega*x, omega*y, omega*Y[, omega]), interleaved
     double *rowtot;            // [F][H] row totals of omega*Y
     double *ambient;           // [F] sum over the map of omega*Y
     rr_plan *plans;            // [n_streaks]
@@ -65,6 +66,10 @@ struct rr_static_tabs {
     const int32_t *tex_h;      // [n_tex]
 };
 
+#ifndef RR_PREF_N
+#define RR_PREF_N 4
+#endif
+
 struct rr_fog_consts {
     float neg_beta32;          // float32(-beta_ext)
     double irr_scale_num;      // 4 * N^2
@@ -94,7 +99,8 @@ cudaError_t rr_launch_omega(int H_env, int W_env, double *omega, double *omega_p
 // per batch
 cudaError_t rr_launch_stats(const rr_frame_bufs &b, int F, int W, int H, int render_scale, double *bgf_out, cudaStream_t st);
 // fmap: tensor map of the padded extinction planes (TMA form of the tile load), or NULL for the register-staged form
-cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, const CUtensorMap *fmap, cudaStream_t st);
+cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, const CUtensorMap *fmap, const CUtensorMap *fmap_roll,
+                          cudaStream_t st);
 cudaError_t rr_launch_fext_lut(float *lut, float neg_beta32, cudaStream_t st);
 cudaError_t rr_launch_env(const rr_frame_bufs &b, const rr_static_tabs &t, int F, int W, int H, int W_env, cudaStream_t st);
 // k_plan needs only the streak records: it may run on another stream while the frame stages (fog, environment map) run
