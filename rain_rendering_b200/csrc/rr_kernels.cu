@@ -674,7 +674,9 @@ __global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog(rr_frame_bufs b, 
 // segments so that the grid keeps the machine full (each segment pays one extra block).  Only the frames whose in-scatter
 // images are one image times a scalar ("linear", the common case) take this form; the others leave at once and are
 // rendered by k_fog, which in turn skips the linear frames.
+#ifndef FOGR_SEG
 #define FOGR_SEG 6            // tiles per CTA (H = 375: 12 tiles -> 2 segments)
+#endif
 #define FOGR_BR 32            // rows per block = FOG_TY
 #define FOGR_BYTES_FH (sizeof(float) * 2 * FOGR_BR * FOG_FS)          // float32 row-pass ring   [2][32][FOG_FS]
 #define FOGR_BYTES_LH (sizeof(double) * 2 * FOGR_BR * FOG_FS)         // float64 row-pass ring   [2][32][FOG_FS]
