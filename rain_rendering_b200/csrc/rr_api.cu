@@ -195,6 +195,8 @@ int rr_create(int device_id, rr_context **out) {
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device_id));
     c->n_sm = prop.multiProcessorCount;
+    // (a higher stream priority for the frame chain, the longer of the two chains of a step, was measured: 4.01 -> 4.13 ms --
+    // the starved blur then delays the join; both chains run at the default priority)
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));

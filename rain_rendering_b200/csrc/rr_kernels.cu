@@ -1165,6 +1165,67 @@ cudaError_t rr_launch_env(const rr_frame_bufs &b, const rr_static_tabs &t, int F
 // ------------------------------------------------------------------------------------------
 struct rr_plan;
 __device__ __forceinline__ void plan_sizes(const rr_plan &p, long long *g, long long *v, long long *a, int *vx0, int *vw);
+// Column intervals of one mask row, merged, handed to `emit(lo, hi)` left to right: what rr_fcp_row (rr_cvmath.h) returns,
+// without its arrays.  A row of a (near-)convex polygon has the scan span and the Bresenham runs of the two or three outline
+// edges that cross it: up to SETUP_NI intervals live in registers (slots filled by predicated moves, a fixed compare-exchange
+// network sorts them, the merge walks the fixed slots); a row with more falls back to the general routine.  The general
+// routine's insertion sort lives in local memory and ran with 13 of 32 lanes active (30 % of k_setup's stall samples).
+#define SETUP_NI 6
+template <class EMIT>
+__device__ __forceinline__ void setup_row_intervals(const rr_fcp &f, int y, EMIT &&emit) {
+    if (y < 0 || y >= f.H) return;
+    int L[SETUP_NI], Hh[SETUP_NI];
+#pragma unroll
+    for (int k = 0; k < SETUP_NI; k++) { L[k] = 0x7fffffff; Hh[k] = -0x7fffffff; }
+    int n = 0;
+    auto push = [&](int a, int b) {
+#pragma unroll
+        for (int k = 0; k < SETUP_NI; k++) if (n == k) { L[k] = a; Hh[k] = b; }
+        n++;
+    };
+    if (y >= f.ymin && y <= f.ymax && y < f.y_stop) {
+        int64_t xa, xb;
+        if (rr_fcp_side_x(f, 0, y, &xa) && rr_fcp_side_x(f, 1, y, &xb)) {
+            if (xa > xb) { int64_t t = xa; xa = xb; xb = t; }
+            const int64_t half = 1 << 15;
+            int xx1 = (int)((xa + half) >> 16), xx2 = (int)((xb + half) >> 16);
+            if (xx2 >= 0 && xx1 < f.W) {
+                if (xx1 < 0) xx1 = 0;
+                if (xx2 >= f.W) xx2 = f.W - 1;
+                if (xx1 <= xx2) push(xx1, xx2);
+            }
+        }
+    }
+    for (int k = 0; k < f.ne; k++) {
+        int a, b;
+        if (rr_line_row(f.ex0[k], f.ey0[k], f.ex1[k], f.ey1[k], y, &a, &b)) push(a, b);
+    }
+    if (n == 0) return;
+    if (n > SETUP_NI) {                       // rare: many outline runs on one row
+        int lo[RR_MAX_POLY + 2], hi[RR_MAX_POLY + 2];
+        const int m = rr_fcp_row(f, y, lo, hi);
+        for (int j = 0; j < m; j++) emit(lo[j], hi[j]);
+        return;
+    }
+    // sort the six slots by their left end (empty slots carry INT_MAX and sink to the end): odd-even transposition network
+#define SETUP_CE(i, j) { if (L[i] > L[j]) { int t_ = L[i]; L[i] = L[j]; L[j] = t_; t_ = Hh[i]; Hh[i] = Hh[j]; Hh[j] = t_; } }
+#pragma unroll
+    for (int round = 0; round < SETUP_NI; round++) {
+        if (round & 1) { SETUP_CE(1, 2) SETUP_CE(3, 4) }
+        else { SETUP_CE(0, 1) SETUP_CE(2, 3) SETUP_CE(4, 5) }
+    }
+#undef SETUP_CE
+    int cl = L[0], ch = Hh[0];
+#pragma unroll
+    for (int k = 1; k < SETUP_NI; k++) {
+        if (L[k] != 0x7fffffff) {
+            if (L[k] <= ch + 1) { if (Hh[k] > ch) ch = Hh[k]; }       // touching or overlapping: one interval
+            else { emit(cl, ch); cl = L[k]; ch = Hh[k]; }
+        }
+    }
+    emit(cl, ch);
+}
+
 #define SETUP_WARPS 4
 #ifndef SETUP_MINB
 #define SETUP_MINB 8          // 64 registers: latency bound, more resident warps win (sweep r01h)
@@ -1198,16 +1259,14 @@ __global__ void __launch_bounds__(SETUP_WARPS * 32, SETUP_MINB) k_setup(rr_frame
         if (ymax > rows - 1) ymax = rows - 1;
         const size_t stride = (size_t)(cols + 1);
         const double *P = b.pref + (size_t)f * rows * stride * RR_PREF_N;
-        int ivl[RR_MAX_POLY + 2], ivh[RR_MAX_POLY + 2];
         for (int y = ymin + lane; y <= ymax; y += 32) {
-            int k = rr_fcp_row(fc, y, ivl, ivh);
-            for (int j = 0; j < k; j++) {
-                const double *a = P + ((size_t)y * stride + ivl[j]) * RR_PREF_N, *e = P + ((size_t)y * stride + ivh[j] + 1) * RR_PREF_N;
+            setup_row_intervals(fc, y, [&](int lo_, int hi_) {
+                const double *a = P + ((size_t)y * stride + lo_) * RR_PREF_N, *e = P + ((size_t)y * stride + hi_ + 1) * RR_PREF_N;
                 sx += e[0] - a[0]; sy += e[1] - a[1]; sY += e[2] - a[2];
                 // the solid angles do not depend on the frame: their row prefix is a per-camera table (L2 resident)
                 if (RR_PREF_N == 4) sw += e[3] - a[3];
-                else sw += t.omega_pref[(size_t)y * stride + ivh[j] + 1] - t.omega_pref[(size_t)y * stride + ivl[j]];
-            }
+                else sw += t.omega_pref[(size_t)y * stride + hi_ + 1] - t.omega_pref[(size_t)y * stride + lo_];
+            });
         }
         sx = warp_sum(sx); sy = warp_sum(sy); sY = warp_sum(sY); sw = warp_sum(sw);
     }
@@ -1378,6 +1437,9 @@ cudaError_t rr_launch_scan(const rr_frame_bufs &b, int n_streaks, cudaStream_t s
 #ifndef RAS_MINB
 #define RAS_MINB 5            // resident CTAs per SM the register allocation is tuned for
 #endif
+#ifndef RAS_UNROLL
+#define RAS_UNROLL 2          // canvas samples a chain keeps in flight
+#endif
 #define RAS_MAXW 512          // widest rotated canvas handled by the staged path
 #define RAS_TXN 128           // widest / tallest patch with cached computeResizeAreaTab spans
 #define RAS_MAXD 1024         // patch pixels with accumulators resident in shared memory
@@ -1507,13 +1569,15 @@ __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs 
                         if (c_hi >= m_hi) sL = ras_sample_int(tex, tw, th, (xr + adx[c_hi]) >> (10 - RR_INTER_BITS), (yr + bdx[c_hi]) >> (10 - RR_INTER_BITS));
                         const int a = c_lo < m_lo ? m_lo : c_lo, e = c_hi >= m_hi ? m_hi - 1 : c_hi;
                         int c = a;
-                        for (; c + 1 <= e; c += 2) {             // two independent samples in flight
-                            const int X0 = (xr + adx[c]) >> (10 - RR_INTER_BITS), Y0 = (yr + bdx[c]) >> (10 - RR_INTER_BITS);
-                            const int X1 = (xr + adx[c + 1]) >> (10 - RR_INTER_BITS), Y1 = (yr + bdx[c + 1]) >> (10 - RR_INTER_BITS);
-                            const int v0 = ras_sample_int(tex, tw, th, X0, Y0), v1 = ras_sample_int(tex, tw, th, X1, Y1);
-                            sM += v0 + v1;
+                        for (; c + RAS_UNROLL - 1 <= e; c += RAS_UNROLL) {       // RAS_UNROLL independent samples in flight
+                            int v[RAS_UNROLL];
+#pragma unroll
+                            for (int u = 0; u < RAS_UNROLL; u++)
+                                v[u] = ras_sample_int(tex, tw, th, (xr + adx[c + u]) >> (10 - RR_INTER_BITS), (yr + bdx[c + u]) >> (10 - RR_INTER_BITS));
+#pragma unroll
+                            for (int u = 0; u < RAS_UNROLL; u++) sM += v[u];
                         }
-                        if (c <= e) sM += ras_sample_int(tex, tw, th, (xr + adx[c]) >> (10 - RR_INTER_BITS), (yr + bdx[c]) >> (10 - RR_INTER_BITS));
+                        for (; c <= e; c++) sM += ras_sample_int(tex, tw, th, (xr + adx[c]) >> (10 - RR_INTER_BITS), (yr + bdx[c]) >> (10 - RR_INTER_BITS));
                         // texel / 255 / 1024 folded into one constant (RAS_UNIT), the three weights applied left to right
                         buf = ((double)sF * RAS_UNIT) * (double)tx.a_first;
                         buf += ((double)sM * RAS_UNIT) * (double)tx.a_mid;

@@ -151,6 +151,15 @@ __device__ bool sim_candidate(const sim_consts &c, const double *cdf, const doub
 struct rr_context;
 extern "C" int rr_sim_device_of(rr_context *c);   // rr_api.cu
 extern "C" void rr_set_error(const char *msg);
+extern "C" void *rr_ctx_scratch(rr_context *c, int which, size_t bytes);      // rr_api.cu: grow-only device buffers of the context
+extern "C" void *rr_ctx_stream(rr_context *c);
+extern "C" void rr_ctx_count_launches(rr_context *c, int n);
+
+// which parameter set the tables in the context's scratch buffer 0 (diameter CDF, diameters, terminal velocities) belong to
+static thread_local rr_sim_params g_tab_params;
+static thread_local sim_consts g_tab_consts;
+static thread_local double g_tab_mean = 0;
+static thread_local rr_context *g_tab_ctx = nullptr;
 
 // ---- host-side preparation shared by the two entry points ---------------------------------------------------------------
 static int sim_prepare(const rr_sim_params *p, sim_consts *cc, std::vector<double> *cdf_out, std::vector<double> *d_out, double *mean_out) {
@@ -216,28 +225,42 @@ extern "C" int rr_simulate_particles(rr_context *ctx, const rr_sim_params *p, in
     int rc = sim_prepare(p, &c, &cdf, &d, &mean);
     if (rc != RR_OK) return rc;
     if (expected_per_frame) *expected_per_frame = mean;
-    double *d_cdf = nullptr, *d_d = nullptr; rr_sim_streak *d_out = nullptr; int *d_cnt = nullptr;
+    // tables and output slices live in the context's grow-only scratch buffers; frames go to the device in chunks: all
+    // launches of a chunk first, one read-back of its counters, then exactly the records that were produced
+    cudaStream_t st = (cudaStream_t)rr_ctx_stream(ctx);
+    const int CH = n_frames < 64 ? n_frames : 64;
+    double *d_tab = (double *)rr_ctx_scratch(ctx, 0, sizeof(double) * 3 * SIM_NLUT);
+    int *d_cnt = (int *)rr_ctx_scratch(ctx, 4, sizeof(int) * 64 + 1024);
+    rr_sim_streak *d_out = (rr_sim_streak *)rr_ctx_scratch(ctx, 1, sizeof(rr_sim_streak) * (size_t)CH * max_per_frame);
+    if (!d_tab || !d_cnt || !d_out) { rr_set_error("rr_simulate_particles: out of device memory"); return RR_ERR_CUDA; }
+    double *d_cdf = d_tab, *d_d = d_tab + SIM_NLUT, *d_v = d_tab + 2 * SIM_NLUT;
     cudaError_t e;
-    if ((e = cudaMalloc(&d_cdf, sizeof(double) * SIM_NLUT)) != cudaSuccess || (e = cudaMalloc(&d_d, sizeof(double) * 2 * SIM_NLUT)) != cudaSuccess ||
-        (e = cudaMalloc(&d_out, sizeof(rr_sim_streak) * (size_t)max_per_frame)) != cudaSuccess || (e = cudaMalloc(&d_cnt, sizeof(int))) != cudaSuccess) {
-        rr_set_error(cudaGetErrorString(e)); cudaFree(d_cdf); cudaFree(d_d); cudaFree(d_out); cudaFree(d_cnt); return RR_ERR_CUDA;
+#define SIMCK(call) if ((e = (call)) != cudaSuccess) { rr_set_error(cudaGetErrorString(e)); return RR_ERR_CUDA; }
+    SIMCK(cudaMemcpyAsync(d_cdf, cdf.data(), sizeof(double) * SIM_NLUT, cudaMemcpyHostToDevice, st));
+    SIMCK(cudaMemcpyAsync(d_d, d.data(), sizeof(double) * SIM_NLUT, cudaMemcpyHostToDevice, st));
+    k_sim_vt<<<SIM_NLUT / 128, 128, 0, st>>>(d_d, d_v);
+    SIMCK(cudaStreamSynchronize(st));
+    { rr_sim_params key = *p; key.seed = 0; g_tab_params = key; g_tab_consts = c; g_tab_mean = mean; g_tab_ctx = ctx; }   // what scratch buffer 0 now holds
+    std::vector<int> cnt(CH);
+    for (int f0 = 0; f0 < n_frames && rc == RR_OK; f0 += CH) {
+        const int nf = n_frames - f0 < CH ? n_frames - f0 : CH;
+        SIMCK(cudaMemsetAsync(d_cnt, 0, sizeof(int) * nf, st));
+        for (int f = 0; f < nf; f++) {
+            const int64_t frame = first_frame + f0 + f;
+            const int n_cand = sim_poisson(c, mean, frame);
+            if (n_cand > 0) k_sim_frame<<<(n_cand + 127) / 128, 128, 0, st>>>(c, d_cdf, d_d, d_v, frame, n_cand, max_per_frame, d_out + (size_t)f * max_per_frame, d_cnt + f);
+        }
+        SIMCK(cudaMemcpyAsync(cnt.data(), d_cnt, sizeof(int) * nf, cudaMemcpyDeviceToHost, st));
+        SIMCK(cudaStreamSynchronize(st));
+        for (int f = 0; f < nf; f++) {
+            int n = cnt[f];
+            if (n > max_per_frame) { rr_set_error("rr_simulate_particles: more streaks than max_per_frame"); rc = RR_ERR_CAPACITY; n = max_per_frame; }
+            counts[f0 + f] = n;
+            if (n) SIMCK(cudaMemcpyAsync(out + (size_t)(f0 + f) * max_per_frame, d_out + (size_t)f * max_per_frame, sizeof(rr_sim_streak) * n, cudaMemcpyDeviceToHost, st));
+        }
+        SIMCK(cudaStreamSynchronize(st));
     }
-    cudaMemcpy(d_cdf, cdf.data(), sizeof(double) * SIM_NLUT, cudaMemcpyHostToDevice);
-    cudaMemcpy(d_d, d.data(), sizeof(double) * SIM_NLUT, cudaMemcpyHostToDevice);
-    double *d_v = d_d + SIM_NLUT;
-    k_sim_vt<<<SIM_NLUT / 128, 128>>>(d_d, d_v);
-    for (int f = 0; f < n_frames && rc == RR_OK; f++) {
-        int64_t frame = first_frame + f;
-        const int n_cand = sim_poisson(c, mean, frame);
-        cudaMemset(d_cnt, 0, sizeof(int));
-        if (n_cand > 0) k_sim_frame<<<(n_cand + 127) / 128, 128>>>(c, d_cdf, d_d, d_v, frame, n_cand, max_per_frame, d_out, d_cnt);
-        int cnt = 0;
-        if ((e = cudaMemcpy(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost)) != cudaSuccess) { rr_set_error(cudaGetErrorString(e)); rc = RR_ERR_CUDA; break; }
-        if (cnt > max_per_frame) { rr_set_error("rr_simulate_particles: more streaks than max_per_frame"); rc = RR_ERR_CAPACITY; cnt = max_per_frame; }
-        counts[f] = cnt;
-        if (cnt) cudaMemcpy(out + (size_t)f * max_per_frame, d_out, sizeof(rr_sim_streak) * cnt, cudaMemcpyDeviceToHost);
-    }
-    cudaFree(d_cdf); cudaFree(d_d); cudaFree(d_out); cudaFree(d_cnt);
+#undef SIMCK
     return rc;
 }
 
@@ -391,9 +414,6 @@ __global__ void __launch_bounds__(256) k_sim_compact_draw(const rr_streak_rec *c
     }
 }
 
-extern "C" void *rr_ctx_scratch(rr_context *c, int which, size_t bytes);      // rr_api.cu: grow-only device buffers of the context
-extern "C" void *rr_ctx_stream(rr_context *c);
-extern "C" void rr_ctx_count_launches(rr_context *c, int n);
 
 extern "C" int rr_simulate_records_device(rr_context *ctx, const rr_sim_params *p, int64_t first_frame, int n_frames, int render_scale,
                                           const double *db_ratios, int n_ratios, double noise_std, double noise_scale,
@@ -407,18 +427,14 @@ extern "C" int rr_simulate_records_device(rr_context *ctx, const rr_sim_params *
     if (first_frame < 0 || first_frame + n_frames > 0xffffffffll) { rr_set_error("rr_simulate_records_device: frame index out of the 32-bit seed range"); return RR_ERR_ARG; }
     if (cudaSetDevice(rr_sim_device_of(ctx)) != cudaSuccess) { rr_set_error("rr_simulate_records_device: cudaSetDevice failed"); return RR_ERR_CUDA; }
     // the tables of a parameter set (diameter CDF, diameters, terminal velocities) are built once and stay on the device
-    static thread_local rr_sim_params cached_p;
-    static thread_local sim_consts cached_c;
-    static thread_local double cached_mean = 0;
-    static thread_local rr_context *cached_ctx = nullptr;
     rr_sim_params key = *p;
     key.seed = 0;
-    const bool hit = cached_ctx == ctx && memcmp(&key, &cached_p, sizeof(key)) == 0 && rr_ctx_scratch(ctx, 0, 0) != nullptr;
+    const bool hit = g_tab_ctx == ctx && memcmp(&key, &g_tab_params, sizeof(key)) == 0 && rr_ctx_scratch(ctx, 0, 0) != nullptr;
     sim_consts c;
     std::vector<double> cdf, d;
     double mean = 0;
     int rc = RR_OK;
-    if (hit) { c = cached_c; c.seed = p->seed; mean = cached_mean; }
+    if (hit) { c = g_tab_consts; c.seed = p->seed; mean = g_tab_mean; }
     else {
         rc = sim_prepare(p, &c, &cdf, &d, &mean);
         if (rc != RR_OK) return rc;
@@ -435,18 +451,18 @@ extern "C" int rr_simulate_records_device(rr_context *ctx, const rr_sim_params *
     rr_streak_rec *d_cand = (rr_streak_rec *)rr_ctx_scratch(ctx, 1, sizeof(rr_streak_rec) * F * max_cand);
     unsigned char *d_flags = (unsigned char *)rr_ctx_scratch(ctx, 2, F * max_cand);
     rr_streak_rec *d_out = (rr_streak_rec *)rr_ctx_scratch(ctx, 3, sizeof(rr_streak_rec) * F * max_cand);
-    if (!d_tab || !d_ints || !d_cand || !d_flags || !d_out) { rr_set_error("rr_simulate_records_device: out of device memory"); cached_ctx = nullptr; return RR_ERR_CUDA; }
+    if (!d_tab || !d_ints || !d_cand || !d_flags || !d_out) { rr_set_error("rr_simulate_records_device: out of device memory"); g_tab_ctx = nullptr; return RR_ERR_CUDA; }
     double *d_cdf = d_tab, *d_d = d_tab + SIM_NLUT, *d_v = d_tab + 2 * SIM_NLUT;
     int *d_ncand = d_ints, *d_counts = d_ncand + F;
     int32_t *d_offsets = (int32_t *)(d_counts + F + 2);
     cudaError_t e;
-#define SIMCK(call) if ((e = (call)) != cudaSuccess) { rr_set_error(cudaGetErrorString(e)); cached_ctx = nullptr; return RR_ERR_CUDA; }
+#define SIMCK(call) if ((e = (call)) != cudaSuccess) { rr_set_error(cudaGetErrorString(e)); g_tab_ctx = nullptr; return RR_ERR_CUDA; }
     if (!hit) {
         SIMCK(cudaMemcpyAsync(d_cdf, cdf.data(), sizeof(double) * SIM_NLUT, cudaMemcpyHostToDevice, st));
         SIMCK(cudaMemcpyAsync(d_d, d.data(), sizeof(double) * SIM_NLUT, cudaMemcpyHostToDevice, st));
         k_sim_vt<<<SIM_NLUT / 128, 128, 0, st>>>(d_d, d_v);
         SIMCK(cudaStreamSynchronize(st));           // cdf / d are host vectors about to go out of scope
-        cached_p = key; cached_c = c; cached_mean = mean; cached_ctx = ctx;
+        g_tab_params = key; g_tab_consts = c; g_tab_mean = mean; g_tab_ctx = ctx;
         rr_ctx_count_launches(ctx, 1);
     }
     SIMCK(cudaMemcpyAsync(d_ncand, n_cand.data(), sizeof(int) * F, cudaMemcpyHostToDevice, st));
