@@ -43,13 +43,17 @@ struct rr_context {
     void *scratch[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};       // grow-only device buffers of the on-the-fly simulator
     size_t scratch_bytes[5] = {0, 0, 0, 0, 0};                // the requests in flight (host pointers of the PNG outputs)
     bool serial = false;                   // RR_SERIAL=1: the streak chain runs on the main stream (profiling: one kernel at a time)
-    cudaEvent_t ev_plan = nullptr;
+    cudaEvent_t ev_plan = nullptr, ev_fext = nullptr;
+    bool fext_side = false;                // RR_FEXT_SIDE=1: the extinction plane on the side stream beside the statistics (measured: 3.83 -> 3.88 ms, off)
     long long launches = 0;
     // streak DB
     uint8_t *d_db = nullptr;
     size_t db_bytes = 0;
     int n_tex = 0, db_width = 0;
-    int32_t *d_tex_off = nullptr, *d_tex_h = nullptr;
+    int32_t *d_tex_off = nullptr, *d_tex_h = nullptr, *d_tex_poff = nullptr;
+    uint8_t *d_dbp = nullptr;            // zero-bordered texture copies, rebuilt from d_db before the first render after the DB changed
+    bool padded_valid = false;
+    int max_tex_h = 0;
     // camera
     bool have_cam = false;
     rr_camera cam;
@@ -215,6 +219,8 @@ int rr_create(int device_id, rr_context **out) {
     CK(cudaEventCreateWithFlags(&c->ev_out, cudaEventDisableTiming));
     for (int i = 0; i < RR_T_COUNT + 2; i++) { CK(cudaEventCreate(&c->ev[i])); CK(cudaEventCreate(&c->ev_end[i])); c->slot_has_end[i] = c->slot_side[i] = false; }
     CK(cudaEventCreateWithFlags(&c->ev_plan, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev_fext, cudaEventDisableTiming));
+    { const char *env = getenv("RR_FEXT_SIDE"); c->fext_side = env && atoi(env) != 0; }
     { const char *env = getenv("RR_SERIAL"); c->serial = env && atoi(env) != 0; }
     memset(c->last_ms, 0, sizeof(c->last_ms));
     memset(&c->fb, 0, sizeof(c->fb));
@@ -234,8 +240,11 @@ int rr_destroy(rr_context *c) {
     if (c->d_db) cudaFree(c->d_db);
     if (c->d_tex_off) cudaFree(c->d_tex_off);
     if (c->d_tex_h) cudaFree(c->d_tex_h);
+    if (c->d_tex_poff) cudaFree(c->d_tex_poff);
+    if (c->d_dbp) cudaFree(c->d_dbp);
     for (int i = 0; i < RR_T_COUNT + 2; i++) { cudaEventDestroy(c->ev[i]); cudaEventDestroy(c->ev_end[i]); }
     cudaEventDestroy(c->ev_plan);
+    cudaEventDestroy(c->ev_fext);
     cudaStreamDestroy(c->stream);
     cudaStreamDestroy(c->s_h2d);
     cudaStreamDestroy(c->s_d2h);
@@ -255,17 +264,26 @@ int rr_alloc_streak_db(rr_context *c, int n_tex, const int32_t *heights, int wid
     if (!c || n_tex <= 0 || n_tex > 255 || !heights || width <= 0) { set_err("rr_alloc_streak_db: bad arguments"); return RR_ERR_ARG; }
     CK(cudaSetDevice(c->device));
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_plan); }
-    if (c->d_db) { cudaFree(c->d_db); cudaFree(c->d_tex_off); cudaFree(c->d_tex_h); c->d_db = nullptr; }
-    std::vector<int32_t> off(n_tex);
-    size_t total = 0;
+    if (c->d_db) { cudaFree(c->d_db); cudaFree(c->d_tex_off); cudaFree(c->d_tex_h); cudaFree(c->d_tex_poff); cudaFree(c->d_dbp); c->d_db = nullptr; }
+    std::vector<int32_t> off(n_tex), poff(n_tex);
+    size_t total = 0, ptotal = 0;
+    c->max_tex_h = 0;
     for (int i = 0; i < n_tex; i++) {
         if (heights[i] <= 0) { set_err("rr_alloc_streak_db: texture %d has height %d", i, heights[i]); return RR_ERR_ARG; }
         off[i] = (int32_t)total;
+        poff[i] = (int32_t)ptotal;
         total += (size_t)heights[i] * width;
+        ptotal += (size_t)(heights[i] + 2) * (width + 2);
+        if (heights[i] > c->max_tex_h) c->max_tex_h = heights[i];
     }
+    if (ptotal > 0x7fffffff) { set_err("rr_alloc_streak_db: streak DB too large"); return RR_ERR_ARG; }
     CK(cudaMalloc((void **)&c->d_db, total + 256));
     CK(cudaMalloc((void **)&c->d_tex_off, sizeof(int32_t) * n_tex));
     CK(cudaMalloc((void **)&c->d_tex_h, sizeof(int32_t) * n_tex));
+    CK(cudaMalloc((void **)&c->d_tex_poff, sizeof(int32_t) * n_tex));
+    CK(cudaMalloc((void **)&c->d_dbp, ptotal + 256));
+    CK(cudaMemcpy(c->d_tex_poff, poff.data(), sizeof(int32_t) * n_tex, cudaMemcpyHostToDevice));
+    c->padded_valid = false;             // built from d_db right before the first render (the bytes may arrive by NCCL broadcast)
     CK(cudaMemcpy(c->d_tex_off, off.data(), sizeof(int32_t) * n_tex, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_tex_h, heights, sizeof(int32_t) * n_tex, cudaMemcpyHostToDevice));
     c->db_bytes = total; c->n_tex = n_tex; c->db_width = width;
@@ -487,6 +505,7 @@ static rr_static_tabs tabs_of(rr_context *c) {
     rr_static_tabs t;
     t.env_src = c->d_env_src; t.env_written = c->d_env_written; t.env_tile_hole = c->d_env_tile_hole; t.omega = c->d_omega; t.omega_pref = c->d_omega_pref;
     t.omega_total = c->d_omega_total; t.db = c->d_db; t.tex_off = c->d_tex_off; t.tex_h = c->d_tex_h;
+    t.dbp = c->d_dbp; t.tex_poff = c->d_tex_poff;
     return t;
 }
 
@@ -512,6 +531,11 @@ static int run_pipeline(rr_context *c, int F, int n_streaks, bool timed) {
     const int W = c->cam.W, H = c->cam.H;
     c->camd.db_width = c->db_width; c->camd.n_tex = c->n_tex;
     for (int i = 0; i < RR_T_COUNT; i++) c->slot_has_end[i] = c->slot_side[i] = false;
+    if (!c->padded_valid) {              // first render with this streak DB: the rasteriser's zero-bordered texture copies
+        CK(rr_launch_build_padded(c->d_db, c->d_tex_off, c->d_tex_h, c->d_tex_poff, c->n_tex, c->db_width, c->max_tex_h, c->d_dbp, st));
+        c->padded_valid = true;
+        c->launches += 1;
+    }
     // fork: everything this (sub-)batch depends on has been enqueued on st (inputs landed, the previous user of the plan /
     // walker buffers and of the patch arena is done)
     if (!c->serial) { CK(cudaEventRecord(c->ev_fork, st)); CK(cudaStreamWaitEvent(ss, c->ev_fork, 0)); }
@@ -520,8 +544,12 @@ static int run_pipeline(rr_context *c, int F, int n_streaks, bool timed) {
     if (c->serial) {
         CK(rr_launch_plan(b, t, c->camd, n_streaks, ss));
     }
+    // the extinction plane depends on the depth only: on the side stream, beside the channel statistics
+    const bool fext_side = !c->serial && c->fog_tma && c->fext_side;
+    if (fext_side) { CK(rr_launch_fext_pad(b, c->fogc, F, W, H, ss)); CK(cudaEventRecord(c->ev_fext, ss)); }
     CK(rr_launch_stats(b, F, W, H, rs, (double *)b.bgf, st));
-    CK(rr_launch_fog(b, c->fogc, F, W, H, c->fog_tma ? &c->fog_map : nullptr, &c->fog_map_roll, st));
+    if (fext_side) CK(cudaStreamWaitEvent(st, c->ev_fext, 0));
+    CK(rr_launch_fog(b, c->fogc, F, W, H, c->fog_tma ? &c->fog_map : nullptr, &c->fog_map_roll, fext_side, st));
     if (timed) CK(cudaEventRecord(c->ev[RR_T_ENV], st));
     CK(rr_launch_env(b, t, F, W, H, c->W_env, st));
     if (timed) CK(cudaEventRecord(c->ev[RR_T_SETUP], st));
@@ -729,20 +757,22 @@ static int submit_frames(rr_context *c, int F, const rr_frame_io &io, bool timed
         for (int i = 0; i <= nf; i++) so[i] = streak_offsets[f0 + i] - s0;
         cudaStream_t hs = multi ? c->s_h2d : st;
         rr_streak_rec *d_slot = c->d_streaks + (size_t)k * c->sub_cap;
-        if (multi) CK(cudaStreamWaitEvent(hs, c->ev_done[k], 0));      // the previous batch no longer reads slot k's inputs
-        CK(cudaMemcpyAsync(c->d_bgr + (size_t)f0 * np * 3 * rs2, bgr + (size_t)f0 * np * 3 * rs2, (size_t)nf * np * 3 * rs2, cudaMemcpyHostToDevice, hs));
-        CK(cudaMemcpyAsync((char *)c->d_depth + (size_t)f0 * np * dsz, (const char *)io.depth + (size_t)f0 * np * dsz, (size_t)nf * np * dsz, cudaMemcpyHostToDevice, hs));
+        uint8_t *d_bgr = c->d_bgr;
+        char *d_depth = (char *)c->d_depth;
+        if (multi) CK(cudaStreamWaitEvent(hs, c->ev_done[k], 0));     // the previous user of this slot no longer reads its inputs
+        CK(cudaMemcpyAsync(d_bgr + (size_t)f0 * np * 3 * rs2, bgr + (size_t)f0 * np * 3 * rs2, (size_t)nf * np * 3 * rs2, cudaMemcpyHostToDevice, hs));
+        CK(cudaMemcpyAsync(d_depth + (size_t)f0 * np * dsz, (const char *)io.depth + (size_t)f0 * np * dsz, (size_t)nf * np * dsz, cudaMemcpyHostToDevice, hs));
         if (ns) CK(cudaMemcpyAsync(d_slot, streaks + s0, (size_t)ns * sizeof(rr_streak_rec), cudaMemcpyHostToDevice, hs));
         CK(cudaMemcpyAsync(c->d_sub_offsets + (size_t)k * (c->max_batch + 1), so, (nf + 1) * sizeof(int32_t), cudaMemcpyHostToDevice, hs));
         if (multi) {
             CK(cudaEventRecord(c->ev_in[k], hs));
             CK(cudaStreamWaitEvent(st, c->ev_in[k], 0));
-            CK(cudaStreamWaitEvent(st, c->ev_d2h[k], 0));             // the previous batch's outputs of slot k have left the device
+            CK(cudaStreamWaitEvent(st, c->ev_d2h[k], 0));            // the previous user's outputs of this slot have left the device
         }
         c->scan_base[k] = sb; c->sub_n[k] = ns;
         c->call_scan_base[slot][k] = sb; c->call_sub_n[slot][k] = ns;
         rr_frame_bufs saved = c->fb;
-        saved.bgr = c->d_bgr; saved.depth = c->d_depth; saved.depth_u16 = du16; saved.streaks = d_slot - s0;   // sub_view adds s0 back
+        saved.bgr = d_bgr; saved.depth = d_depth; saved.depth_u16 = du16; saved.streaks = d_slot - s0;   // sub_view adds s0 back
         saved.offsets = c->d_sub_offsets + (size_t)k * (c->max_batch + 1);
         rr_frame_bufs sel = saved;
         select_outputs(sel, saved, io);
@@ -761,12 +791,13 @@ static int submit_frames(rr_context *c, int F, const rr_frame_io &io, bool timed
         sb += ns + 1;
         cudaStream_t ds = multi ? c->s_d2h : st;
         if (multi) { CK(cudaEventRecord(c->ev_done[k], st)); CK(cudaStreamWaitEvent(ds, c->ev_done[k], 0)); }
-        if (io.out_bgr) CK(cudaMemcpyAsync(io.out_bgr + (size_t)f0 * np * 3, b.out_bgr + (size_t)f0 * np * 3, (size_t)nf * np * 3 * sizeof(float), cudaMemcpyDeviceToHost, ds));
-        if (io.out_mask) CK(cudaMemcpyAsync(io.out_mask + (size_t)f0 * np, b.out_mask + (size_t)f0 * np, (size_t)nf * np * sizeof(float), cudaMemcpyDeviceToHost, ds));
-        if (io.out_bgr_u8) CK(cudaMemcpyAsync(io.out_bgr_u8 + (size_t)f0 * np * 3, b.out_u8 + (size_t)f0 * np * 3, (size_t)nf * np * 3, cudaMemcpyDeviceToHost, ds));
-        if (io.out_mask_idx8) CK(cudaMemcpyAsync(io.out_mask_idx8 + (size_t)f0 * np, b.out_idx8 + (size_t)f0 * np, (size_t)nf * np, cudaMemcpyDeviceToHost, ds));
-        if (io.out_mask_u16) CK(cudaMemcpyAsync(io.out_mask_u16 + (size_t)f0 * np, b.out_u16 + (size_t)f0 * np, (size_t)nf * np * 2, cudaMemcpyDeviceToHost, ds));
-        if (io.out_mask_range) CK(cudaMemcpyAsync(io.out_mask_range + (size_t)f0 * 2, b.mask_range + (size_t)f0 * 2, (size_t)nf * 2 * sizeof(double), cudaMemcpyDeviceToHost, ds));
+        const size_t fo = (size_t)f0;
+        if (io.out_bgr) CK(cudaMemcpyAsync(io.out_bgr + (size_t)f0 * np * 3, b.out_bgr + fo * np * 3, (size_t)nf * np * 3 * sizeof(float), cudaMemcpyDeviceToHost, ds));
+        if (io.out_mask) CK(cudaMemcpyAsync(io.out_mask + (size_t)f0 * np, b.out_mask + fo * np, (size_t)nf * np * sizeof(float), cudaMemcpyDeviceToHost, ds));
+        if (io.out_bgr_u8) CK(cudaMemcpyAsync(io.out_bgr_u8 + (size_t)f0 * np * 3, b.out_u8 + fo * np * 3, (size_t)nf * np * 3, cudaMemcpyDeviceToHost, ds));
+        if (io.out_mask_idx8) CK(cudaMemcpyAsync(io.out_mask_idx8 + (size_t)f0 * np, b.out_idx8 + fo * np, (size_t)nf * np, cudaMemcpyDeviceToHost, ds));
+        if (io.out_mask_u16) CK(cudaMemcpyAsync(io.out_mask_u16 + (size_t)f0 * np, b.out_u16 + fo * np, (size_t)nf * np * 2, cudaMemcpyDeviceToHost, ds));
+        if (io.out_mask_range) CK(cudaMemcpyAsync(io.out_mask_range + (size_t)f0 * 2, b.mask_range + fo * 2, (size_t)nf * 2 * sizeof(double), cudaMemcpyDeviceToHost, ds));
         if (io.out_png_image) CK(cudaMemcpyAsync(io.out_png_image_sizes + f0, c->d_png_sizes[slot][0] + f0, (size_t)nf * sizeof(uint32_t), cudaMemcpyDeviceToHost, ds));
         if (io.out_png_mask) CK(cudaMemcpyAsync(io.out_png_mask_sizes + f0, c->d_png_sizes[slot][1] + f0, (size_t)nf * sizeof(uint32_t), cudaMemcpyDeviceToHost, ds));
         if (multi) CK(cudaEventRecord(c->ev_d2h[k], ds));
@@ -918,7 +949,7 @@ int rr_fog_only(rr_context *c, int n_frames, const uint8_t *bgr, const float *de
     b.bgr = c->d_bgr; b.depth = c->d_depth; b.depth_u16 = 0; b.bgf = c->d_bgf;
     CK(rr_launch_stats(b, n_frames, c->cam.W, c->cam.H, rs2 == 4 ? 2 : 1, c->d_bgf, st));
     b.frame0 = 0;
-    CK(rr_launch_fog(b, c->fogc, n_frames, c->cam.W, c->cam.H, c->fog_tma ? &c->fog_map : nullptr, &c->fog_map_roll, st));
+    CK(rr_launch_fog(b, c->fogc, n_frames, c->cam.W, c->cam.H, c->fog_tma ? &c->fog_map : nullptr, &c->fog_map_roll, false, st));
     c->launches += 5;
     CK(cudaMemcpyAsync(out_planar, b.rainy, F * 3 * np * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

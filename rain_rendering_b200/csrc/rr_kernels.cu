@@ -848,18 +848,28 @@ cudaError_t rr_launch_fext_lut(float *lut, float neg_beta32, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// The extinction plane of the TMA form needs only the depth: it may run on another stream beside k_stats (rr_launch_fog is
+// then told that the plane is already on its way: fext_done).
+cudaError_t rr_launch_fext_pad(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, cudaStream_t st) {
+    dim3 g((b.fext_Wp + 255) / 256, b.fext_Hp, F);
+    float *dst = b.fext + (size_t)b.frame0 * b.fext_Hp * b.fext_Wp;     // the tensor map spans the whole plane stack: frame0 + f
+    if (b.depth_u16) k_fext_pad<true><<<g, 256, 0, st>>>(b.depth, b.fext_lut, dst, fc.neg_beta32, W, H, b.fext_Wp, b.fext_Hp);
+    else k_fext_pad<false><<<g, 256, 0, st>>>(b.depth, b.fext_lut, dst, fc.neg_beta32, W, H, b.fext_Wp, b.fext_Hp);
+    return cudaGetLastError();
+}
+
 cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, const CUtensorMap *fmap, const CUtensorMap *fmap_roll,
-                          cudaStream_t st) {
+                          bool fext_done, cudaStream_t st) {
     static_assert(FOG_ES >= FOG_PAD(FOG_EW - 1) + 1 && FOG_LS >= FOG_PAD(FOG_EW - 1) + 1 && FOG_FS >= FOG_PAD(FOG_TX - 1) + 1, "fog strides");
     static_assert(sizeof(double) * FOG_EH * FOG_FS <= FOG_BYTES_A && sizeof(double) * FOG_EH * FOG_FS <= FOG_BYTES_A_TMA, "LH must fit in the E + FH region");
     static_assert(FOG_ED == FOG_EW && (FOG_ED * sizeof(float)) % 16 == 0 && FOG_BYTES_A_TMA % 8 == 0, "dense tile layout");
     k_fog_acs<<<(F * 4 + 127) / 128, 128, 0, st>>>(b.bg_sum, b.acs, fc, (double)W * (double)H, F);
     dim3 grid((W + FOG_TX - 1) / FOG_TX, (H + FOG_TY - 1) / FOG_TY, F);
     if (fmap) {
-        dim3 g((b.fext_Wp + 255) / 256, b.fext_Hp, F);
-        float *dst = b.fext + (size_t)b.frame0 * b.fext_Hp * b.fext_Wp;     // the tensor map spans the whole plane stack: frame0 + f
-        if (b.depth_u16) k_fext_pad<true><<<g, 256, 0, st>>>(b.depth, b.fext_lut, dst, fc.neg_beta32, W, H, b.fext_Wp, b.fext_Hp);
-        else k_fext_pad<false><<<g, 256, 0, st>>>(b.depth, b.fext_lut, dst, fc.neg_beta32, W, H, b.fext_Wp, b.fext_Hp);
+        if (!fext_done) {
+            cudaError_t e = rr_launch_fext_pad(b, fc, F, W, H, st);
+            if (e != cudaSuccess) return e;
+        }
         const size_t smem = FOG_BYTES_A_TMA + FOG_BYTES_B + FOG_TY * FOG_TX * 3;
         if (b.fog_roll) {
             // linear frames by the rolling kernel, the others by k_fog: each leaves the other's frames at once
@@ -1303,7 +1313,7 @@ __global__ void __launch_bounds__(128) k_plan(rr_frame_bufs b, rr_static_tabs t,
     memset(&p, 0, sizeof(p));
     bool ok = rec.tex_idx < cam.n_tex;
     if (ok) ok = rr_plan_patch(rec, cam, t.tex_h[rec.tex_idx], p);
-    if (ok) p.tex_off = t.tex_off[rec.tex_idx];
+    if (ok) { p.tex_off = t.tex_off[rec.tex_idx]; p.g_off = t.tex_poff[rec.tex_idx]; }
     else p.pw = p.ph = p.bw = p.bh = 0;
     // field-of-view mask
     __align__(16) rr_fcp fc;
@@ -1437,6 +1447,14 @@ cudaError_t rr_launch_scan(const rr_frame_bufs &b, int n_streaks, cudaStream_t s
 #ifndef RAS_MINB
 #define RAS_MINB 5            // resident CTAs per SM the register allocation is tuned for
 #endif
+#ifndef RAS_PADDED
+#define RAS_PADDED 1          // chain-loop sampler: 1 = zero-bordered texture copies (no per-tap predicates), 0 = plain textures
+#endif
+#if RAS_PADDED
+#define RAS_SAMPLE(X, Y) ras_sample_pad(texp, tw, th, X, Y)
+#else
+#define RAS_SAMPLE(X, Y) ras_sample_int(tex, tw, th, X, Y)
+#endif
 #ifndef RAS_UNROLL
 #define RAS_UNROLL 2          // canvas samples a chain keeps in flight
 #endif
@@ -1489,6 +1507,37 @@ __device__ __forceinline__ int ras_sample_int(const uint8_t *tex, int tw, int th
     return (RR_INTER_TAB - fy) * top + fy * bot;
 }
 
+// The chain loop's sampler on ZERO-BORDERED copies of the textures: a texture of h x w texels is stored as (h + 2) x (w + 2) bytes
+// with a one-texel border of zeros (the warp's border constant), so the four taps of a bilinear sample at (sx, sy) with
+// sx in [-1, w - 1], sy in [-1, h - 1] are four unconditional byte loads -- no per-tap predicates and selects; outside that
+// range all four taps are border and the sample is 0.  Same bytes per texel as the plain copy (a 4-texel word per sample was
+// measured slower: four times the footprint in L1).
+__device__ __forceinline__ int ras_sample_pad(const uint8_t *P, int tw, int th, int X, int Y) {
+    const int sx = X >> RR_INTER_BITS, sy = Y >> RR_INTER_BITS;
+    if ((unsigned)(sx + 1) > (unsigned)tw || (unsigned)(sy + 1) > (unsigned)th) return 0;
+    const uint8_t *S = P + (sy + 1) * (tw + 2) + (sx + 1);
+    const int fx = X & (RR_INTER_TAB - 1), fy = Y & (RR_INTER_TAB - 1);
+    const int top = (RR_INTER_TAB - fx) * (int)S[0] + fx * (int)S[1];
+    const int bot = (RR_INTER_TAB - fx) * (int)S[tw + 2] + fx * (int)S[tw + 3];
+    return (RR_INTER_TAB - fy) * top + fy * bot;
+}
+
+__global__ void k_build_padded(const uint8_t *db, const int32_t *tex_off, const int32_t *tex_h, const int32_t *tex_poff, int tw, uint8_t *dbp) {
+    const int k = blockIdx.y, th = tex_h[k];
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (th + 2) * (tw + 2)) return;
+    const int r = i / (tw + 2), c = i - r * (tw + 2);
+    const int y = r - 1, x = c - 1;
+    dbp[tex_poff[k] + i] = (y >= 0 && y < th && x >= 0 && x < tw) ? db[tex_off[k] + y * tw + x] : (uint8_t)0;
+}
+
+cudaError_t rr_launch_build_padded(const uint8_t *db, const int32_t *tex_off, const int32_t *tex_h, const int32_t *tex_poff, int n_tex, int tw,
+                                   int max_h, uint8_t *dbp, cudaStream_t st) {
+    dim3 g(((max_h + 2) * (tw + 2) + 255) / 256, n_tex);
+    k_build_padded<<<g, 256, 0, st>>>(db, tex_off, tex_h, tex_poff, tw, dbp);
+    return cudaGetLastError();
+}
+
 __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs b, rr_static_tabs t, rr_cam_dev cam, int n) {
     extern __shared__ double ras_smem[];
     double *C = ras_smem;                       // [RAS_CAP]   area-fast: canvas band;  area: first half of the chain sums
@@ -1514,6 +1563,7 @@ __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs 
         plan_sizes(p, &g, &vv, &aa, &vx0_, &vw_);
         if (g == 0) continue;
         const uint8_t *tex = t.db + p.tex_off;
+        const uint8_t *texp = t.dbp + p.g_off;          // the zero-bordered copy (ras_sample_pad)
         double *out = b.arena + b.scan[(size_t)s * 6 + 0];
         const bool staged = p.type != RR_BIG && (p.resize_mode == RR_RESIZE_AREA || p.resize_mode == RR_RESIZE_AREA_FAST) &&
                             p.nW <= RAS_MAXW && p.pw <= RAS_TXN && p.ph <= RAS_TXN && g <= RAS_MAXD;
@@ -1565,19 +1615,19 @@ __global__ void __launch_bounds__(RAS_THREADS, RAS_MINB) k_raster(rr_frame_bufs 
                         // (at most 512 columns of at most 255 * 1024 each: no overflow)
                         const int m_lo = tx.s_first, m_hi = tx.s_first + tx.n;       // full-weight columns [m_lo, m_hi)
                         int sF = 0, sM = 0, sL = 0;
-                        if (c_lo < m_lo) sF = ras_sample_int(tex, tw, th, (xr + adx[c_lo]) >> (10 - RR_INTER_BITS), (yr + bdx[c_lo]) >> (10 - RR_INTER_BITS));
-                        if (c_hi >= m_hi) sL = ras_sample_int(tex, tw, th, (xr + adx[c_hi]) >> (10 - RR_INTER_BITS), (yr + bdx[c_hi]) >> (10 - RR_INTER_BITS));
+                        if (c_lo < m_lo) sF = RAS_SAMPLE((xr + adx[c_lo]) >> (10 - RR_INTER_BITS), (yr + bdx[c_lo]) >> (10 - RR_INTER_BITS));
+                        if (c_hi >= m_hi) sL = RAS_SAMPLE((xr + adx[c_hi]) >> (10 - RR_INTER_BITS), (yr + bdx[c_hi]) >> (10 - RR_INTER_BITS));
                         const int a = c_lo < m_lo ? m_lo : c_lo, e = c_hi >= m_hi ? m_hi - 1 : c_hi;
                         int c = a;
                         for (; c + RAS_UNROLL - 1 <= e; c += RAS_UNROLL) {       // RAS_UNROLL independent samples in flight
                             int v[RAS_UNROLL];
 #pragma unroll
                             for (int u = 0; u < RAS_UNROLL; u++)
-                                v[u] = ras_sample_int(tex, tw, th, (xr + adx[c + u]) >> (10 - RR_INTER_BITS), (yr + bdx[c + u]) >> (10 - RR_INTER_BITS));
+                                v[u] = RAS_SAMPLE((xr + adx[c + u]) >> (10 - RR_INTER_BITS), (yr + bdx[c + u]) >> (10 - RR_INTER_BITS));
 #pragma unroll
                             for (int u = 0; u < RAS_UNROLL; u++) sM += v[u];
                         }
-                        for (; c <= e; c++) sM += ras_sample_int(tex, tw, th, (xr + adx[c]) >> (10 - RR_INTER_BITS), (yr + bdx[c]) >> (10 - RR_INTER_BITS));
+                        for (; c <= e; c++) sM += RAS_SAMPLE((xr + adx[c]) >> (10 - RR_INTER_BITS), (yr + bdx[c]) >> (10 - RR_INTER_BITS));
                         // texel / 255 / 1024 folded into one constant (RAS_UNIT), the three weights applied left to right
                         buf = ((double)sF * RAS_UNIT) * (double)tx.a_first;
                         buf += ((double)sM * RAS_UNIT) * (double)tx.a_mid;

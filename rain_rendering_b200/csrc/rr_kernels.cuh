@@ -62,6 +62,8 @@ struct rr_static_tabs {
     const double *omega_pref;  // [H][W_env+1]
     const double *omega_total; // [1] numpy-order total
     const uint8_t *db;         // concatenated textures
+    const uint8_t *dbp;        // the same with a one-texel zero border around each (k_raster's bilinear sampler), built by k_build_padded
+    const int32_t *tex_poff;   // [n_tex] byte offset of each bordered texture in dbp
     const int32_t *tex_off;    // [n_tex]
     const int32_t *tex_h;      // [n_tex]
 };
@@ -95,12 +97,15 @@ cudaError_t rr_prepare_device();       // per-device function attributes (dynami
 cudaError_t rr_launch_env_tables(int W, int H, int focal_px, int cyl_w, int min_x, int W_env, int32_t *env_src,
                                  uint8_t *env_written, int32_t *cyl_first /* [H][cyl_w] scratch */, cudaStream_t st);
 cudaError_t rr_launch_env_tile_flags(const uint8_t *env_written, uint8_t *tile_hole, int H, int W_env, cudaStream_t st);
+cudaError_t rr_launch_build_padded(const uint8_t *db, const int32_t *tex_off, const int32_t *tex_h, const int32_t *tex_poff, int n_tex, int tw,
+                                   int max_h, uint8_t *dbp, cudaStream_t st);
 cudaError_t rr_launch_omega(int H_env, int W_env, double *omega, double *omega_pref, double *omega_total, cudaStream_t st);
 // per batch
 cudaError_t rr_launch_stats(const rr_frame_bufs &b, int F, int W, int H, int render_scale, double *bgf_out, cudaStream_t st);
 // fmap: tensor map of the padded extinction planes (TMA form of the tile load), or NULL for the register-staged form
 cudaError_t rr_launch_fog(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, const CUtensorMap *fmap, const CUtensorMap *fmap_roll,
-                          cudaStream_t st);
+                          bool fext_done, cudaStream_t st);
+cudaError_t rr_launch_fext_pad(const rr_frame_bufs &b, const rr_fog_consts &fc, int F, int W, int H, cudaStream_t st);
 cudaError_t rr_launch_fext_lut(float *lut, float neg_beta32, cudaStream_t st);
 cudaError_t rr_launch_env(const rr_frame_bufs &b, const rr_static_tabs &t, int F, int W, int H, int W_env, cudaStream_t st);
 // k_plan needs only the streak records: it may run on another stream while the frame stages (fog, environment map) run

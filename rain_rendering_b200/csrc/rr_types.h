@@ -45,7 +45,7 @@ struct rr_plan {
     int32_t bx0, by0;       // top-left of the composited block in the image (after clip)
     int32_t cropx, cropy;   // columns/rows of the blurred patch cut away at the left/top
     int32_t bw, bh;         // composited block size (after clipping to the image)
-    int64_t g_off;          // unused (kept for the layout the tests read through rr_debug_read)
+    int64_t g_off;          // byte offset of the texture's zero-bordered copy in the device DB (k_raster's sampler)
     int64_t a_off;          // element offset of the blurred alpha block (bw x bh) in the arena
     // --- photometry ------------------------------------------------------------------
     double kb, kg, kr;      // tint per unit alpha, BGR
