@@ -242,14 +242,22 @@ def run_gpu(args):
     batch = args.batch
     db, bgr, depth, d16, sim, recs, offs = build_batch(wl, rank, batch)
     n_streaks = int(offs[-1])
-    ctx = api.RainContext(local)
-    rdist.broadcast_streak_db(ctx, db.textures if rank == 0 else None, src=0)     # the one collective
-    ctx.set_camera(W, H, cam["cam_focal"], cam["cam_f_number"], cam["cam_exposure"], cam["cam_gain"], wl["fallrate"], 1.0, batch)
+    # `lanes` independent contexts on this GPU take the steps in turn (api.RainLanes): the kernels of consecutive batches
+    # overlap, in the device-resident arm and end to end alike
+    n_lanes = max(1, args.lanes)
+    lanes = api.RainLanes(local, n_lanes)
+    for c in lanes.ctxs:
+        rdist.broadcast_streak_db(c, db.textures if rank == 0 else None, src=0)   # the one collective (once per lane, at set-up)
+    lanes.set_camera(W, H, cam["cam_focal"], cam["cam_f_number"], cam["cam_exposure"], cam["cam_gain"], wl["fallrate"], 1.0, batch)
+    ctx = lanes.ctxs[0]
     from rain_rendering_b200 import _lib
     lib, C = ctx.lib, __import__("ctypes")
-    stream_ptr = C.c_void_p()
-    lib.rr_stream(ctx.h, C.byref(stream_ptr))
-    stream = torch.cuda.ExternalStream(stream_ptr.value, device=torch.device("cuda", local))
+    streams = []
+    for c in lanes.ctxs:
+        stream_ptr = C.c_void_p()
+        lib.rr_stream(c.h, C.byref(stream_ptr))
+        streams.append(torch.cuda.ExternalStream(stream_ptr.value, device=torch.device("cuda", local)))
+    stream = streams[0]
 
     def barrier():
         if world > 1:
@@ -262,42 +270,56 @@ def run_gpu(args):
     d_bgr = torch.from_numpy(bgr).to(dev)
     d_depth = torch.from_numpy(d16.view(np.int16)).to(dev)
     d_recs = torch.from_numpy(recs.view(np.uint8).reshape(-1)).to(dev)
-    d_out_bgr = torch.empty((batch, H, W, 3), dtype=torch.float32, device=dev)
-    d_out_mask = torch.empty((batch, H, W), dtype=torch.float32, device=dev)
-    d_out_u8 = torch.empty((batch, H, W, 3), dtype=torch.uint8, device=dev)
-    d_out_idx8 = torch.empty((batch, H, W), dtype=torch.uint8, device=dev)
     offs_c = np.ascontiguousarray(offs)
-    io_dev = _lib.FrameIO(d_bgr.data_ptr(), d_depth.data_ptr(), _lib.DEPTH_U16_256, 0, d_recs.data_ptr(), _lib.ptr(offs_c).value,
-                          d_out_bgr.data_ptr(), d_out_mask.data_ptr(), d_out_u8.data_ptr(), d_out_idx8.data_ptr(), None, None)
+    outs, io_dev = [], []
+    for _ in range(n_lanes):                # the inputs are shared (read-only), every lane writes its own outputs
+        o = dict(bgr=torch.empty((batch, H, W, 3), dtype=torch.float32, device=dev), mask=torch.empty((batch, H, W), dtype=torch.float32, device=dev),
+                 u8=torch.empty((batch, H, W, 3), dtype=torch.uint8, device=dev), idx8=torch.empty((batch, H, W), dtype=torch.uint8, device=dev))
+        outs.append(o)
+        io_dev.append(_lib.FrameIO(d_bgr.data_ptr(), d_depth.data_ptr(), _lib.DEPTH_U16_256, 0, d_recs.data_ptr(), _lib.ptr(offs_c).value,
+                                   o["bgr"].data_ptr(), o["mask"].data_ptr(), o["u8"].data_ptr(), o["idx8"].data_ptr(), None, None))
+    d_out_u8, d_out_idx8 = outs[0]["u8"], outs[0]["idx8"]
 
-    def step_device(sync=0):
-        _lib.check(lib.rr_render_frames_device_io(ctx.h, batch, C.byref(io_dev), sync), "rr_render_frames_device_io")
+    def step_device(i, sync=0):
+        k = i % n_lanes
+        _lib.check(lib.rr_render_frames_device_io(lanes.ctxs[k].h, batch, C.byref(io_dev[k]), sync), "rr_render_frames_device_io")
 
-    for _ in range(max(args.warmup, 3)):
-        step_device(1)
-    stage_ms = {k: 0.0 for k in ctx.timings()}
+    def join_lanes():                       # lane 0's stream waits for the work queued on the others
+        for st in streams[1:]:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            stream.wait_event(ev)
+
+    for i in range(max(args.warmup, 3) * n_lanes):
+        step_device(i, 1)                   # synchronous: the first one sizes the lane's patch arena
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
         sampler.start()
-    launches0 = ctx.kernel_launches()
+    launches0 = lanes.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
-    for _ in range(args.steps):
-        step_device(1)                      # synchronous per step: also yields the per-stage event timings
-        for k, v in ctx.timings().items():
-            stage_ms[k] += v
+    for i in range(args.steps):
+        step_device(i, 0)                   # queued: a lane's steps follow each other on its stream, the lanes overlap
+    join_lanes()
     e1.record(stream)
     barrier()
     ms_dev = e0.elapsed_time(e1)
-    launches = ctx.kernel_launches() - launches0
+    # per-stage CUDA-event durations of every lane's LAST step of the timed region (rr_synchronize settles them)
+    stage_ms = {k: 0.0 for k in ctx.timings()}
+    used = [c for j, c in enumerate(lanes.ctxs) if j < args.steps]
+    for c in used:
+        c.synchronize()
+        for k, v in c.timings().items():
+            stage_ms[k] += v * args.steps / len(used)          # scaled to the sum over the steps the lines below divide by
+    launches = lanes.kernel_launches() - launches0
     clocks = sampler.stop() if rank == 0 else None
     # every stage's own duration: the same step a few more times with the streak chain on the main stream (in the timed region
     # above it runs beside the frame chain, so the stage times there overlap and add up to more than the step)
     ctx.set_option("serial", 1)
     solo_ms = {k: 0.0 for k in ctx.timings()}
     for _ in range(3):
-        step_device(1)
+        step_device(0, 1)
         for k, v in ctx.timings().items():
             solo_ms[k] += v / 3.0
     ctx.set_option("serial", 0)
@@ -307,38 +329,47 @@ def run_gpu(args):
     # (in-frame filter + the NumPy RNG mirror, rr_host_assemble_batch -- host work a caller pays per frame), copies its
     # inputs host->device in the forms the files hold (uint8 image, uint16 depth samples) and copies back what
     # Generator.run saves (generator.py:466-467): the uint8 image and the mask as plt.imsave's colormap index + range.
+    n_sets = lanes.capacity                  # a host set is reused when the submission that used it has been waited for
     sets = []
-    for _ in range(2):
+    for _ in range(n_sets):
         hb = dict(bgr=api.PinnedBuffer(bgr.shape, np.uint8), depth=api.PinnedBuffer(d16.shape, np.uint16),
-                  recs=api.PinnedBuffer((sum(len(f) for f in sim),), STREAK_DTYPE), idx8=api.PinnedBuffer((batch, H, W), np.uint8),
+                  idx8=api.PinnedBuffer((batch, H, W), np.uint8),
                   u8=api.PinnedBuffer((batch, H, W, 3), np.uint8), rng=api.PinnedBuffer((batch, 2), np.float64))
         hb["bgr"].array[...] = bgr; hb["depth"].array[...] = d16
         sets.append(hb)
+    # the records rotate over one more buffer: batch i is assembled while the oldest submission may still be copying out
+    rec_sets = [api.PinnedBuffer((sum(len(f) for f in sim),), STREAK_DTYPE) for _ in range(n_sets + 1)]
     seeds = list(range(batch))
 
-    def submit(i):
-        hb = sets[i & 1]
-        r, o = api.assemble_batch(sim, seeds, W, H, db.ratios, out=hb["recs"].array)
-        hb["offs"] = o
-        ctx.submit_frames(hb["bgr"].array, hb["depth"].array, r, o, None, None, hb["u8"].array, hb["idx8"].array, None, hb["rng"].array)
+    def assemble(i):
+        return api.assemble_batch(sim, seeds, W, H, db.ratios, out=rec_sets[i % (n_sets + 1)].array)
+
+    def submit(i, r, o):
+        hb = sets[i % n_sets]
+        lanes.submit_frames(hb["bgr"].array, hb["depth"].array, r, o, None, None, hb["u8"].array, hb["idx8"].array, None, hb["rng"].array)
 
     def run_e2e(n):
-        submit(0)
-        for i in range(1, n):
-            submit(i)
-            ctx.wait_frames()
-        ctx.wait_frames()
+        # host work of the next batch first, then the wait for the oldest one: the wait -> assemble -> copy-in chain would
+        # otherwise be as long as the GPU's step
+        for i in range(n):
+            r, o = assemble(i)
+            if lanes.inflight == lanes.capacity:
+                lanes.wait_frames()
+            submit(i, r, o)
+        while lanes.inflight:
+            lanes.wait_frames()
 
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     link = None
     if args.skip_e2e:
         f0.record(stream); f1.record(stream)
     else:
-        ctx.render_frames(bgr, d16, recs, offs_c, want=("u8", "idx8"))      # synchronous call: sizes the arena
-        run_e2e(max(args.warmup, 3))
+        for c in lanes.ctxs:
+            c.render_frames(bgr, d16, recs, offs_c, want=("u8", "idx8"))    # synchronous call: sizes the lane's host-path buffers
+        run_e2e(max(args.warmup, 3) * n_lanes)
         barrier()
         f0.record(stream)
-        run_e2e(args.steps)
+        run_e2e(args.steps)                 # returns when every output is in host memory; lane 0's stream is idle by then
         f1.record(stream)
     barrier()
     ms_e2e = max(f0.elapsed_time(f1), 1e-6)
@@ -366,16 +397,20 @@ def run_gpu(args):
         e2e = total_frames / (ms_e2e / 1000.0)
         n_per_frame = n_streaks / batch
         balg = algorithmic_bytes_per_frame(W, H, n_per_frame)
-        # dominant kernel (stage) of the device-resident step, timed live with CUDA events on the library's stream
+        # dominant kernel (stage) of the device-resident step, timed live with CUDA events on the library's stream.  Inside the
+        # timed region the stages of the two chains and of the lanes overlap, so an event span there is not a kernel's duration:
+        # the roofline uses the stage's own duration (the pass with one kernel at a time right after the timed region, which is
+        # also what the ncu launch list shows); the in-step spans are reported beside it.
         kern = {k: v / args.steps for k, v in stage_ms.items() if k not in ("h2d", "d2h", "total")}
-        dom = max(kern, key=kern.get)
+        solo = {k: v for k, v in solo_ms.items() if k not in ("h2d", "d2h", "total")}
+        dom = max(solo, key=solo.get)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = balg * batch / (kern[dom] / 1000.0) / 1e9
+        achieved = balg * batch / (solo[dom] / 1000.0) / 1e9
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get(dom)
@@ -385,6 +420,9 @@ def run_gpu(args):
                 "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
                 "config": {"workload": "C2 KITTI 1242x375 25mm/hr", "batch_frames_per_gpu": batch, "streaks_per_frame": n_per_frame,
+                           "lanes_per_gpu": n_lanes,
+                           "lanes": "independent contexts on one GPU taking the steps (64-frame batches) in turn, so that consecutive batches overlap "
+                                    "(api.RainLanes); --lanes 1 = one context, one step at a time",
                            "device_arm": "uint8 image + uint16 depth resident in HBM -> float32 image, float32 mask, uint8 image, uint8 mask index",
                            "l2": "inputs larger than L2 (%.0f MB per step per GPU, no flush)" % ((h2d) / 1e6),
                            "parallelism": "frames sharded x%d, no data-path collective" % world},
@@ -397,13 +435,17 @@ def run_gpu(args):
                         "link_frac": ((h2d + d2h) * world * args.steps / (ms_e2e / 1000.0) / 1e9 / link_total) if link and link_total > 0 else None,
                         "inputs": "uint8 BGR image + uint16 depth samples (what the PNG files hold) + streak records built per step from the simulator frames",
                         "outputs": "uint8 BGR image + rain mask as plt.imsave's colormap index (uint8) and its (min, max) -- what Generator.run saves",
-                        "api": "rr_host_assemble_batch + rr_submit_frames_io / rr_wait_frames, two host buffer sets"},
+                        "api": "rr_host_assemble_batch + rr_submit_frames_io / rr_wait_frames round-robin over %d contexts (api.RainLanes), "
+                               "%d host buffer sets" % (n_lanes, lanes.capacity)},
                 "stage_ms_solo": {k: v for k, v in solo_ms.items() if k not in ("h2d", "d2h", "total")},
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "kernel_ms_in_step": kern[dom], "kernel_ms_solo": solo_ms[dom],
-                             "frac_solo": (balg * batch / (solo_ms[dom] / 1000.0) / 1e9) / peak if solo_ms[dom] > 0 else None,
-                             "note": "stage_ms / achieved: durations inside the timed region, where the streak chain (raster, blur) runs beside the frame chain "
-                                     "(fog, env, setup) on a second stream and the stages slow each other; *_solo: the same stage alone",
+                             "kernel_ms": solo[dom], "stage_span_ms_in_step": kern[dom],
+                             "frac_in_step": (balg * batch / (kern[dom] / 1000.0) / 1e9) / peak if kern[dom] > 0 else None,
+                             "note": "achieved / frac: algorithmic bytes of one 64-frame launch / the dominant stage's own duration (CUDA events, one "
+                                     "kernel at a time, measured in this run right after the timed region; agrees with the ncu launch list).  "
+                                     "stage_ms / *_in_step: event spans of every lane's last step inside the timed region, where the streak chain "
+                                     "(raster, blur) runs beside the frame chain (fog, env, setup) and the lanes run beside each other: the spans "
+                                     "overlap and add up to more than the step",
                              "traffic": traffic, "peak_source": "measured" if "hbm_gbs" in peaks else "fallback",
                              "algorithmic_bytes_per_frame": balg, "whole_step_frac": (balg * batch / (ms_dev / args.steps / 1000.0) / 1e9) / peak},
                 "stage_ms": kern}
@@ -425,7 +467,7 @@ def run_gpu(args):
                                     "sample": "%d processes x 1 frame (frames 0..%d of this batch, ~%d streaks/frame), oracle port, %.1f s wall" % (
                                         workers, workers - 1, int(np.mean(streaks)), times[0])}
         print(json.dumps(line))
-    ctx.close()
+    lanes.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -510,6 +552,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--lanes", type=int, default=2, help="independent contexts per GPU that take the steps in turn (api.RainLanes)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="C2", choices=["C2", "C3"], help="C2: the headline (default).  C3: Cityscapes with on-the-fly simulation, one GPU")

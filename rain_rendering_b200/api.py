@@ -297,6 +297,94 @@ class RainContext:
         _lib.check(self.lib.rr_synchronize(self.h), "rr_synchronize")
 
 
+class RainLanes:
+    """Several independent contexts ("lanes") on ONE GPU that take batches in turn.  Each lane has its own streams, device
+    buffers and patch arena, so the kernels of batch i + 1 run beside those of batch i: the float64-bound frame stages of one
+    batch fill the issue slots the integer / load-bound streak stages of another leave, and no stage's tail runs alone.
+    Measured on C2, end to end from page-locked host buffers: 15.4 k frames/s through one context with two submissions in flight,
+    17.2 k through two lanes with two each (profiles/r02d_lanes_e2e.txt).  Frames are independent (generator.py:318 reseeds per
+    frame), so the results are those of a single context, bit for bit (tests/test_parity_gpu.py).
+
+    The submission interface is RainContext's with a deeper queue: ``submit_frames`` / ``render_frames_device(sync=False)`` go
+    to the lanes round-robin, ``wait_frames`` retires the OLDEST submission; at most ``capacity`` submissions may be in flight.
+    A C caller does the same with ``lanes`` rr_context handles."""
+
+    def __init__(self, device: int = 0, lanes: int = 2, context_factory=None):
+        assert lanes >= 1
+        make = context_factory or RainContext
+        self.ctxs = [make(device) for _ in range(lanes)]
+        self.device = device
+        self.turn = 0                     # lane of the next submission
+        self.fifo = []                    # lanes of the submissions in flight, oldest first
+        self.per_lane = 2                 # rr_submit_frames keeps at most two batches in flight per context
+
+    @property
+    def capacity(self) -> int:
+        return self.per_lane * len(self.ctxs)
+
+    @property
+    def inflight(self) -> int:
+        return len(self.fifo)
+
+    def close(self):
+        for c in self.ctxs:
+            c.close()
+
+    # -- configuration: every lane gets the same streak DB and camera -----------------------------------------
+    def set_streak_db(self, textures, ratios=None):
+        for c in self.ctxs:
+            c.set_streak_db(textures, ratios)
+
+    def set_camera(self, *a, **k):
+        for c in self.ctxs:
+            c.set_camera(*a, **k)
+        self.W, self.H, self.max_batch = self.ctxs[0].W, self.ctxs[0].H, self.ctxs[0].max_batch
+
+    def set_option(self, name: str, value: int):
+        for c in self.ctxs:
+            c.set_option(name, value)
+
+    @property
+    def db_ratios(self):
+        return self.ctxs[0].db_ratios
+
+    # -- submissions ---------------------------------------------------------------------------------------------
+    def _next_lane(self):
+        if len(self.fifo) >= self.capacity:
+            raise _lib.RainError("RainLanes: %d submissions in flight, wait_frames() first" % len(self.fifo))
+        k = self.turn
+        self.turn = (k + 1) % len(self.ctxs)
+        return k
+
+    def submit_frames(self, *a, **kw):
+        """RainContext.submit_frames on the next lane (page-locked arrays, alive and untouched until their wait_frames)."""
+        k = self._next_lane()
+        self.ctxs[k].submit_frames(*a, **kw)
+        self.fifo.append(k)
+
+    def wait_frames(self):
+        """Blocks until the OLDEST submission is complete (its outputs are in the caller's arrays)."""
+        if not self.fifo:
+            raise _lib.RainError("RainLanes.wait_frames: nothing in flight")
+        k = self.fifo.pop(0)
+        self.ctxs[k].wait_frames()
+
+    def render_frames(self, *a, **kw):
+        """Synchronous render on the next lane (drains nothing else)."""
+        k = self.turn
+        self.turn = (k + 1) % len(self.ctxs)
+        return self.ctxs[k].render_frames(*a, **kw)
+
+    def synchronize(self):
+        while self.fifo:
+            self.wait_frames()
+        for c in self.ctxs:
+            c.synchronize()
+
+    def kernel_launches(self) -> int:
+        return sum(c.kernel_launches() for c in self.ctxs)
+
+
 def assemble_frame_records(sim_frame: np.ndarray, W: int, H: int, db_ratios, seed: int, noise_std: float = 0.0,
                            noise_scale: float = 0.0, mutate: bool = True) -> np.ndarray:
     """One image frame's records from a simulator frame (STREAK_DTYPE array, XML order):

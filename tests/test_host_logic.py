@@ -150,3 +150,39 @@ def test_integration_md_camera_stub_matches_the_header():
     hdr = open(os.path.join(root, "include", "rain_b200.h")).read()
     body = hdr[hdr.index("typedef struct rr_camera {"):hdr.index("} rr_camera;")]
     assert len(re.findall(r"\bdouble\s+\w+;", body)) == 10 and "int32_t W, H;" in body and "int32_t render_scale;" in body and "int32_t reserved;" in body
+
+
+def test_lanes_queue_is_fifo_over_the_contexts_round_robin():
+    """api.RainLanes without a GPU (fake contexts): submissions go to the lanes in turn, wait_frames retires the oldest,
+    the queue holds two per lane, and configuration calls reach every lane."""
+    log = []
+
+    class Fake:
+        def __init__(self, device):
+            self.k = len(log_ctx); log_ctx.append(self); self.W = self.H = self.max_batch = 0; self.db_ratios = None; self.n = 0
+        def set_streak_db(self, t, r=None): self.db_ratios = r
+        def set_camera(self, W, H, *a, **k): self.W, self.H, self.max_batch = W, H, 4
+        def submit_frames(self, tag): log.append(("submit", self.k, tag)); self.n += 1
+        def wait_frames(self): log.append(("wait", self.k)); self.n -= 1
+        def synchronize(self): log.append(("sync", self.k))
+        def kernel_launches(self): return 10 + self.k
+        def close(self): pass
+
+    log_ctx = []
+    lanes = api.RainLanes(0, 3, context_factory=Fake)
+    lanes.set_streak_db([], [1.0]); lanes.set_camera(64, 32)
+    assert (lanes.W, lanes.H, lanes.max_batch) == (64, 32, 4) and all(c.db_ratios == [1.0] for c in log_ctx)
+    assert lanes.capacity == 6 and lanes.kernel_launches() == 33
+    for t in range(6):
+        lanes.submit_frames(t)
+    assert [e[1] for e in log] == [0, 1, 2, 0, 1, 2]
+    with pytest.raises(_lib.RainError):
+        lanes.submit_frames(6)
+    lanes.wait_frames(); lanes.wait_frames()
+    assert log[-2:] == [("wait", 0), ("wait", 1)] and lanes.inflight == 4
+    lanes.submit_frames(6)                       # the turn continues where it stopped: lane 0
+    assert log[-1] == ("submit", 0, 6)
+    lanes.synchronize()
+    assert lanes.inflight == 0 and all(c.n == 0 for c in log_ctx)
+    with pytest.raises(_lib.RainError):
+        lanes.wait_frames()

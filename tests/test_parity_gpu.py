@@ -261,6 +261,57 @@ def test_pipelined_submissions_equal_synchronous_renders():
     ctx.close()
 
 
+@pytest.mark.gpu
+def test_lanes_round_robin_over_contexts_equals_one_context():
+    """api.RainLanes: batches submitted in turn to three contexts on one GPU (up to six in flight, their kernels
+    overlapping) come out bit for bit as one context renders them synchronously, in submission order."""
+    from rain_rendering_b200 import api
+    scs = [Scenario(384, 256, 8, 900 + 150 * k, fallrate=25, seed=k) for k in range(3)]
+    one = scs[0].context()
+    c = scs[0].cam
+    lanes = api.RainLanes(0, 3)
+    lanes.set_streak_db(scs[0].db.textures, scs[0].db.ratios)
+    lanes.set_camera(scs[0].W, scs[0].H, c.focal_mm, c.f_number, c.exposure_ms, c.gain, c.fallrate, c.opacity_attenuation, scs[0].n_frames)
+    assert lanes.capacity == 6
+    want, inputs = [], []
+    for sc in scs:
+        recs, offs = sc.records()
+        want.append(one.render_frames(sc.bgr, sc.depth, recs, offs))
+        inputs.append((sc, recs, offs))
+    order = [0, 1, 2, 2, 1, 0, 1, 2, 0, 0, 2]
+    sets, inflight = [], []
+    def host_set(i):
+        sc, recs, offs = inputs[i]
+        hb = dict(i=i, bgr=api.PinnedBuffer(sc.bgr.shape, np.uint8), depth=api.PinnedBuffer(sc.depth.shape, np.float32),
+                  recs=api.PinnedBuffer(recs.shape, recs.dtype), offs=offs, out=api.PinnedBuffer(sc.bgr.shape, np.float32),
+                  mask=api.PinnedBuffer(sc.depth.shape, np.float32), u8=api.PinnedBuffer(sc.bgr.shape, np.uint8))
+        hb["bgr"].array[...] = sc.bgr; hb["depth"].array[...] = sc.depth; hb["recs"].array[...] = recs
+        hb["out"].array[...] = 0; hb["mask"].array[...] = -1; hb["u8"].array[...] = 0
+        return hb
+    def retire():
+        lanes.wait_frames()
+        hb = inflight.pop(0)
+        w = want[hb["i"]]
+        assert np.array_equal(hb["out"].array, w["bgr"]) and np.array_equal(hb["mask"].array, w["mask"]) and np.array_equal(hb["u8"].array, w["u8"])
+    for i in order:
+        if lanes.inflight == lanes.capacity:
+            retire()
+        hb = host_set(i)                      # a fresh host set per submission: none is in flight twice
+        lanes.submit_frames(hb["bgr"].array, hb["depth"].array, hb["recs"].array, hb["offs"], hb["out"].array, hb["mask"].array, hb["u8"].array)
+        inflight.append(hb)
+    with pytest.raises(api._lib.RainError):
+        while True:                           # the queue refuses a seventh submission
+            hb = host_set(0)
+            sets.append(hb)
+            lanes.submit_frames(hb["bgr"].array, hb["depth"].array, hb["recs"].array, hb["offs"], hb["out"].array, hb["mask"].array, hb["u8"].array)
+            inflight.append(hb)
+    while inflight:
+        retire()
+    with pytest.raises(api._lib.RainError):
+        lanes.wait_frames()
+    lanes.close(); one.close()
+
+
 def test_compact_boundary_formats_uint16_depth_and_saved_mask_forms():
     """rr_frame_io: the depth PNG's uint16 samples in (divided by 256 on the device, generator.py:365) and the rain
     mask out in the forms that are saved (generator.py:467): plt.imsave's colormap index, the 16-bit normalised
