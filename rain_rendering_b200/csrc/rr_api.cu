@@ -54,6 +54,7 @@ struct rr_context {
     uint8_t *d_dbp = nullptr;            // zero-bordered texture copies, rebuilt from d_db before the first render after the DB changed
     bool padded_valid = false;
     int max_tex_h = 0;
+    std::vector<int32_t> tex_heights;    // layout of the current DB (a DB of the same layout is written in place)
     // camera
     bool have_cam = false;
     rr_camera cam;
@@ -264,6 +265,11 @@ int rr_alloc_streak_db(rr_context *c, int n_tex, const int32_t *heights, int wid
     if (!c || n_tex <= 0 || n_tex > 255 || !heights || width <= 0) { set_err("rr_alloc_streak_db: bad arguments"); return RR_ERR_ARG; }
     CK(cudaSetDevice(c->device));
     if (c->stream) { cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->s_plan); }
+    if (c->d_db && n_tex == c->n_tex && width == c->db_width && (int)c->tex_heights.size() == n_tex &&
+        memcmp(c->tex_heights.data(), heights, sizeof(int32_t) * n_tex) == 0) {
+        c->padded_valid = false;         // same layout (a new Generator over the same streak DB): keep the buffers, new bytes follow
+        return RR_OK;
+    }
     if (c->d_db) { cudaFree(c->d_db); cudaFree(c->d_tex_off); cudaFree(c->d_tex_h); cudaFree(c->d_tex_poff); cudaFree(c->d_dbp); c->d_db = nullptr; }
     std::vector<int32_t> off(n_tex), poff(n_tex);
     size_t total = 0, ptotal = 0;
@@ -287,6 +293,7 @@ int rr_alloc_streak_db(rr_context *c, int n_tex, const int32_t *heights, int wid
     CK(cudaMemcpy(c->d_tex_off, off.data(), sizeof(int32_t) * n_tex, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(c->d_tex_h, heights, sizeof(int32_t) * n_tex, cudaMemcpyHostToDevice));
     c->db_bytes = total; c->n_tex = n_tex; c->db_width = width;
+    c->tex_heights.assign(heights, heights + n_tex);
     c->camd.db_width = width; c->camd.n_tex = n_tex;
     return RR_OK;
 }
@@ -303,6 +310,7 @@ int rr_streak_db_device_ptr(rr_context *c, void **dev_ptr, size_t *bytes) {
     if (!c || !c->d_db) { set_err("rr_streak_db_device_ptr: no streak DB"); return RR_ERR_STATE; }
     if (dev_ptr) *dev_ptr = c->d_db;
     if (bytes) *bytes = c->db_bytes;
+    c->padded_valid = false;             // the caller is about to write the textures (NCCL broadcast)
     return RR_OK;
 }
 
@@ -338,6 +346,8 @@ int rr_set_camera(rr_context *c, const rr_camera *cam, int max_batch) {
     if (cam->W < 32 || cam->H < 32 || cam->W > 8192 || cam->H > 8192) { set_err("rr_set_camera: unsupported size %dx%d", cam->W, cam->H); return RR_ERR_ARG; }
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
+    if (c->have_cam && max_batch == c->max_batch && memcmp(&c->cam, cam, sizeof(rr_camera)) == 0)
+        return RR_OK;                    // same camera, same batch (a new Generator for the next sequence): tables and buffers stand
     free_camera(c);
     c->cam = *cam;
     c->max_batch = max_batch;

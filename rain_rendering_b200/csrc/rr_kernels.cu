@@ -757,6 +757,7 @@ __global__ void __launch_bounds__(FOG_THREADS, FOG_MINB) k_fog_roll(rr_frame_buf
     row_passes(t_first & 1);
     if (tid == 0) request(t_first + 1);                                      // E is free again: the next block travels under the float64 pass
     row_pass64(t_first & 1);
+    __syncthreads();                                                         // D consumed: the loop's first row_passes overwrites it (racecheck)
     for (int t = t_first; t <= t_last; t++) {
         const int y0 = t * FOG_TY;
         // the tile's image bytes, requested now and parked in shared memory until the compose step

@@ -100,7 +100,7 @@ struct png_bits {                      // serial bit writer of the block header 
 };
 
 __global__ void __launch_bounds__(256) k_png_codes(rr_png_bufs p) {
-    __shared__ unsigned freq[257];
+    __shared__ unsigned freq[260];       // 257 used; padded to whole 128-bit words: the compiler reads the rank loop's operands four at a time
     __shared__ int sorted[257];
     __shared__ unsigned weight[514];
     __shared__ short parent[514];

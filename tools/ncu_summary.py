@@ -16,7 +16,7 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
            "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "smsp__inst_executed.sum",
            "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "smsp__thread_inst_executed_per_inst_executed.ratio"]
 STAGE = {"k_stats": "fog", "k_stats_final": "fog", "k_downscale2": "fog", "k_downscale2_final": "fog", "k_fext": "fog", "k_fog": "fog",
-         "k_fext_pad": "fog", "k_fog_acs": "fog",
+         "k_fext_pad": "fog", "k_fog_acs": "fog", "k_fog_roll": "fog",
          "k_env_map": "env", "k_env_prefix": "env", "k_ambient": "env", "k_plan": "setup", "k_setup": "setup", "k_scan": "setup",
          "k_raster": "raster", "k_blur": "blur", "k_composite": "composite", "k_frame_mean": "composite", "k_epilogue": "epilogue"}
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
