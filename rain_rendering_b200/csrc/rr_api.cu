@@ -325,6 +325,7 @@ static int ensure_streak_cap(rr_context *c, int n, int n_sub = -1) {
         drain(c);
         int cap = n + n / 4 + 1024;
         CK(dev_alloc(c, &c->fb.plans, (size_t)cap));
+        CK(cudaMemset(c->fb.plans, 0, sizeof(rr_plan) * (size_t)cap));     // the struct's padding is copied word by word (k_raster): keep initcheck quiet
         CK(dev_alloc(c, &c->fb.fcp, (size_t)cap));
         CK(dev_alloc(c, &c->fb.sizes, (size_t)cap));
         CK(dev_alloc(c, &c->fb.boxes, (size_t)cap));
