@@ -299,8 +299,10 @@ def run_gpu(args):
     launches0 = lanes.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
+    t_enq = time.perf_counter()
     for i in range(args.steps):
         step_device(i, 0)                   # queued: a lane's steps follow each other on its stream, the lanes overlap
+    t_enq = time.perf_counter() - t_enq     # host time to enqueue the steps (the GPU is still working on them)
     join_lanes()
     e1.record(stream)
     barrier()
@@ -427,6 +429,7 @@ def run_gpu(args):
                            "l2": "inputs larger than L2 (%.0f MB per step per GPU, no flush)" % ((h2d) / 1e6),
                            "parallelism": "frames sharded x%d, no data-path collective" % world},
                 "clocks": clocks, "gpu_launches": launches,
+                "host_enqueue_ms_per_step": 1000.0 * t_enq / args.steps,
                 "host_cores": host_cores(),
                 "e2e": {"value": e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                         "checksum_mask": checksum, "equals_device_arm": same, "numa_bind": numa,
