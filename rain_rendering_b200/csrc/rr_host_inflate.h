@@ -1,9 +1,9 @@
-// A single-shot zlib-stream decoder for PNG image data (host code; adler32() from zlib is the only dependency).
+// A single-shot zlib-stream decoder for PNG image data (host code, no dependency).
 //
 // Decoding a frame's two PNGs is what bounds the drop-in pipeline once rendering takes 0.1 ms per frame, and 80 % of
 // that is zlib's inflate (a byte-oriented state machine built for streaming).  PNG gives us the whole compressed stream
 // and the exact decoded size up front, so this decoder works in one pass over contiguous buffers: a 64-bit bit buffer
-// refilled eight bytes at a time, an 11-bit first-level table for the literal/length code and an 8-bit one for the
+// refilled eight bytes at a time, a 12-bit first-level table for the literal/length code (literal pairs where two codes fit) and an 8-bit one for the
 // distance code (second-level tables behind them for longer codes), literals decoded back to back, matches copied in
 // 8-byte steps.  Every write is bounds-checked against the known output size and every malformed code is an error:
 // corrupt input yields RR_ERR_ARG, never an overrun.  The Adler-32 trailer is verified.
@@ -16,9 +16,13 @@
 
 namespace rr_inflate {
 
-enum { LIT_BITS = 11, DIST_BITS = 8, LIT_TABLE = (1 << LIT_BITS) + 288 * 16, DIST_TABLE = (1 << DIST_BITS) + 32 * 128 };
-// table entry: low 8 bits = code bits to consume (0 = invalid code); bits 8..11 = extra bits (lengths / distances) or
-// the width of the second-level table (KIND_SUB); bits 12..15 kind; bits 16..31 = literal value / base / sub-table offset
+enum { LIT_BITS = 12, DIST_BITS = 8, LIT_TABLE = (1 << LIT_BITS) + 288 * 16, DIST_TABLE = (1 << DIST_BITS) + 32 * 128 };
+// table entry: low 8 bits = code bits to consume (0 = invalid code); bits 8..11 = extra bits (lengths / distances), the
+// width of the second-level table (KIND_SUB) or the number of literals the entry carries (KIND_LIT: 1 or 2); bits 12..15
+// kind; bits 16..31 = literal value(s) (first in the low byte) / base / sub-table offset.
+// Literal PAIRS: PNG image data that barely compresses is almost all literals with short codes (5 - 6 bits on average), so
+// two consecutive literals often fit into one first-level look-up; pair_literals() rewrites those entries after the table is
+// built, and the decoder stores 16 bits and advances by the entry's count.
 enum { KIND_LIT = 1, KIND_LEN = 2, KIND_EOB = 3, KIND_SUB = 4, KIND_DIST = 5 };
 static inline uint32_t entry(int kind, int bits, int extra, int value) { return (uint32_t)bits | ((uint32_t)extra << 8) | ((uint32_t)kind << 12) | ((uint32_t)value << 16); }
 
@@ -27,10 +31,12 @@ static const uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 
 static const uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
 static const uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 
-static inline uint32_t reverse_bits(uint32_t v, int n) {
-    uint32_t r = 0;
-    for (int i = 0; i < n; i++) { r = (r << 1) | (v & 1); v >>= 1; }
-    return r;
+static inline uint32_t reverse_bits(uint32_t v, int n) {          // the low n (1 .. 15) bits of v, reversed
+    v = ((v & 0x5555u) << 1) | ((v >> 1) & 0x5555u);
+    v = ((v & 0x3333u) << 2) | ((v >> 2) & 0x3333u);
+    v = ((v & 0x0f0fu) << 4) | ((v >> 4) & 0x0f0fu);
+    v = ((v << 8) | (v >> 8)) & 0xffffu;
+    return v >> (16 - n);
 }
 
 // Builds the two-level decode table of a canonical Huffman code.  lens[0..n): code lengths (0 = unused).  what: 0 literal /
@@ -42,11 +48,12 @@ static inline bool build_table(const uint8_t *lens, int n, int what, uint32_t *t
     count[0] = 0;
     int max_len = 0, used = 0;
     for (int l = 1; l < 16; l++) if (count[l]) { max_len = l; used += count[l]; }
-    for (int i = 0; i < (1 << primary_bits); i++) table[i] = 0;
-    if (used == 0) return what == 1;                               // no distance codes at all: legal when the block has no matches
     // Kraft sum
     long left = 1;
     for (int l = 1; l <= 15; l++) { left <<= 1; left -= count[l]; if (left < 0) return false; }
+    if (left > 0 || used == 0 || max_len > primary_bits)           // otherwise a complete code writes every first-level entry below
+        for (int i = 0; i < (1 << primary_bits); i++) table[i] = 0;   // (with second-level tables the KIND_SUB test reads them first)
+    if (used == 0) return what == 1;                               // no distance codes at all: legal when the block has no matches
     if (left > 0 && !(used == 1 && max_len == 1)) return false;    // incomplete: only a lone 1-bit code is allowed
     int next_code[16], code = 0;
     for (int l = 1; l < 16; l++) { code = (code + count[l - 1]) << 1; next_code[l] = code; }
@@ -58,13 +65,13 @@ static inline bool build_table(const uint8_t *lens, int n, int what, uint32_t *t
         const uint32_t rev = reverse_bits((uint32_t)next_code[l]++, l);
         uint32_t e;
         if (what == 0) {
-            if (s < 256) e = entry(KIND_LIT, 0, 0, s);
+            if (s < 256) e = entry(KIND_LIT, 0, 1, s);
             else if (s == 256) e = entry(KIND_EOB, 0, 0, 0);
             else if (s <= 285) e = entry(KIND_LEN, 0, kLenExtra[s - 257], kLenBase[s - 257]);
             else e = 0;                                            // 286, 287: never valid in data
         } else if (what == 1) {
             e = s < 30 ? entry(KIND_DIST, 0, kDistExtra[s], kDistBase[s]) : 0;
-        } else e = entry(KIND_LIT, 0, 0, s);
+        } else e = entry(KIND_LIT, 0, 1, s);
         if (l <= primary_bits) {
             if (e) e |= (uint32_t)l;
             for (uint32_t i = rev; i < (1u << primary_bits); i += 1u << l) table[i] = e;
@@ -84,6 +91,45 @@ static inline bool build_table(const uint8_t *lens, int n, int what, uint32_t *t
         }
     }
     return true;
+}
+
+// First-level entries whose index holds TWO complete literal codes become pair entries (count 2, both bytes, the bits of
+// both codes).  The second code is looked up in a copy of the single-literal table: its entry is replicated over the unknown
+// high bits, so index >> l1 finds it whenever l1 + l2 <= primary_bits.
+static inline void pair_literals(uint32_t *table, int primary_bits) {
+    static_assert(LIT_BITS <= 12, "pair_literals' copy holds 4096 entries");
+    const int n = 1 << primary_bits;
+    uint32_t single[1 << 12];
+    memcpy(single, table, sizeof(uint32_t) * n);
+    for (int i = 0; i < n; i++) {
+        const uint32_t e = single[i];
+        if (((e >> 12) & 15) != KIND_LIT) continue;
+        const int l1 = (int)(e & 0xff);
+        if (l1 >= primary_bits) continue;
+        const uint32_t e2 = single[i >> l1];
+        if (((e2 >> 12) & 15) != KIND_LIT) continue;
+        const int l2 = (int)(e2 & 0xff);
+        if (l1 + l2 > primary_bits) continue;
+        table[i] = entry(KIND_LIT, l1 + l2, 2, (int)((e >> 16) & 0xff) | (int)(((e2 >> 16) & 0xff) << 8));
+    }
+}
+
+// Adler-32 (RFC 1950) in blocks short enough for 32-bit sums, written so that the compiler vectorises the two sums (an AVX2
+// clone is picked at load time where the CPU has it): 0.15 ms for a 1.4 MB image against 0.7 ms in zlib's byte loop.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+__attribute__((target_clones("avx2", "default")))
+#endif
+inline uint32_t adler32_blocks(const uint8_t *p, size_t n) {
+    uint32_t a = 1, b = 0;
+    while (n) {
+        const uint32_t L = n < 5552 ? (uint32_t)n : 5552u;        // 255 * L (L + 1) / 2 < 2^32
+        uint32_t s1 = 0, s2 = 0;
+        for (uint32_t i = 0; i < L; i++) { s1 += p[i]; s2 += (L - i) * p[i]; }
+        b = (uint32_t)((b + (uint64_t)L * a + s2) % 65521u);
+        a = (a + s1) % 65521u;
+        p += L; n -= L;
+    }
+    return (b << 16) | a;
 }
 
 struct Bits {
@@ -143,6 +189,7 @@ static inline bool zlib_decompress(const uint8_t *in, size_t in_len, uint8_t *ou
             for (int i = 280; i < 288; i++) lens[i] = 8;
             for (int i = 0; i < 32; i++) lens[288 + i] = 5;
             if (!build_table(lens, 288, 0, lit_table, LIT_BITS, LIT_TABLE) || !build_table(lens + 288, 32, 1, dist_table, DIST_BITS, DIST_TABLE)) return false;
+            pair_literals(lit_table, LIT_BITS);
         } else {                                                   // dynamic Huffman codes
             const int hlit = (int)b.peek(5) + 257, hdist = (int)((b.buf >> 5) & 31) + 1, hclen = (int)((b.buf >> 10) & 15) + 4;
             b.drop(14);
@@ -172,6 +219,7 @@ static inline bool zlib_decompress(const uint8_t *in, size_t in_len, uint8_t *ou
             }
             if (b.overrun() || lens[256] == 0) return false;       // a block without an end-of-block code cannot end
             if (!build_table(lens, hlit, 0, lit_table, LIT_BITS, LIT_TABLE) || !build_table(lens + hlit, hdist, 1, dist_table, DIST_BITS, DIST_TABLE)) return false;
+            pair_literals(lit_table, LIT_BITS);
         }
         // ---- the block's symbols ----
         uint8_t *const o_fast_end = out_len > 320 ? o_end - 320 : out;     // below it four literals and a match need no bound checks
@@ -180,27 +228,33 @@ static inline bool zlib_decompress(const uint8_t *in, size_t in_len, uint8_t *ou
             if (b.in > b.in_end && b.overrun()) return false;
             uint32_t e = lit_table[b.peek(LIT_BITS)];
             if (o < o_fast_end) {
-                // fast path: up to four literals per refill (4 x 11 bits of first-level codes leave 12 bits for the next look-up)
+                // fast path: up to four look-ups (eight literals) per refill: 4 x 12 bits of first-level codes fit the 56 bits a refill guarantees.  A literal entry stores two bytes and advances by its count (the second byte of a single
+                // is overwritten by whatever comes next; the output has 320 bytes of head-room here).
+#define RR_INF_LIT() { b.drop((int)(e & 0xff)); const uint16_t v_ = (uint16_t)(e >> 16); memcpy(o, &v_, 2); o += (e >> 8) & 15; e = lit_table[b.peek(LIT_BITS)]; }
                 if (((e >> 12) & 15) == KIND_LIT) {
-                    b.drop((int)(e & 0xff)); *o++ = (uint8_t)(e >> 16); e = lit_table[b.peek(LIT_BITS)];
+                    RR_INF_LIT()
                     if (((e >> 12) & 15) == KIND_LIT) {
-                        b.drop((int)(e & 0xff)); *o++ = (uint8_t)(e >> 16); e = lit_table[b.peek(LIT_BITS)];
+                        RR_INF_LIT()
                         if (((e >> 12) & 15) == KIND_LIT) {
-                            b.drop((int)(e & 0xff)); *o++ = (uint8_t)(e >> 16); e = lit_table[b.peek(LIT_BITS)];
+                            RR_INF_LIT()
                             if (((e >> 12) & 15) == KIND_LIT) {
-                                b.drop((int)(e & 0xff)); *o++ = (uint8_t)(e >> 16);
+                                b.drop((int)(e & 0xff)); const uint16_t v_ = (uint16_t)(e >> 16); memcpy(o, &v_, 2); o += (e >> 8) & 15;
                                 continue;
                             }
                         }
                     }
                 }
+#undef RR_INF_LIT
             } else {
-                // near the end of the output: one literal at a time, every write checked
+                // near the end of the output: one entry at a time, every write checked
                 int guard = 0;
                 while (((e >> 12) & 15) == KIND_LIT && guard < 3) {
-                    if (o >= o_end) return false;
+                    const int c = (int)((e >> 8) & 15);
+                    if ((size_t)(o_end - o) < (size_t)c) return false;
                     b.drop((int)(e & 0xff));
-                    *o++ = (uint8_t)(e >> 16);
+                    o[0] = (uint8_t)(e >> 16);
+                    if (c == 2) o[1] = (uint8_t)(e >> 24);
+                    o += c;
                     e = lit_table[b.peek(LIT_BITS)];
                     guard++;
                 }
@@ -215,9 +269,12 @@ static inline bool zlib_decompress(const uint8_t *in, size_t in_len, uint8_t *ou
             }
             if (!(e & 0xff)) return false;                         // invalid code
             b.drop((int)(e & 0xff));
-            if (kind == KIND_LIT) {
-                if (o >= o_end) return false;
-                *o++ = (uint8_t)(e >> 16);
+            if (kind == KIND_LIT) {                                // a second-level literal (single), or a first-level entry the paths above left
+                const int c = (int)((e >> 8) & 15);
+                if ((size_t)(o_end - o) < (size_t)c) return false;
+                o[0] = (uint8_t)(e >> 16);
+                if (c == 2) o[1] = (uint8_t)(e >> 24);
+                o += c;
                 continue;
             }
             if (kind == KIND_EOB) break;
@@ -254,11 +311,7 @@ static inline bool zlib_decompress(const uint8_t *in, size_t in_len, uint8_t *ou
     if (tail > b.in_end) return false;
     const uint8_t *ad = in + in_len - 4;
     const uint32_t want = ((uint32_t)ad[0] << 24) | ((uint32_t)ad[1] << 16) | ((uint32_t)ad[2] << 8) | ad[3];
-    size_t left = out_len;
-    uLong a = adler32(0L, Z_NULL, 0);
-    const uint8_t *p = out;
-    while (left) { const uInt n = left > (1u << 30) ? (1u << 30) : (uInt)left; a = adler32(a, p, n); p += n; left -= n; }
-    return (uint32_t)a == want;
+    return adler32_blocks(out, out_len) == want;
 }
 
 }  // namespace rr_inflate

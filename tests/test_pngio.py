@@ -108,7 +108,7 @@ def test_deflate_encoder_streams_are_valid_zlib_for_edge_cases():
 
 def test_inflate_decoder_against_zlib_streams_of_every_block_type_and_mutations():
     """csrc/rr_host_inflate.h: what zlib produces at every level / strategy (stored, fixed and dynamic Huffman blocks, long
-    matches, codes longer than the 11-bit first-level table) must decode to the input; truncated, corrupted or
+    matches, codes longer than the 12-bit first-level table) must decode to the input; truncated, corrupted or
     wrong-size streams must be refused, never crash or overrun."""
     import zlib
     rng = np.random.RandomState(1)
@@ -147,6 +147,31 @@ def test_inflate_decoder_against_zlib_streams_of_every_block_type_and_mutations(
             accepted += 1
             assert zlib.decompress(bytes(b)) == got
     assert accepted < 20                                                     # the Adler-32 catches nearly everything that still parses
+
+
+def test_inflate_literal_pairs_tail_path_and_adler_blocks():
+    """Literal-pair entries of the first-level table (two short codes in one look-up): literal-heavy data with short codes,
+    every output length around the 320-byte head-room where the decoder switches to the checked path, lengths around the
+    5552-byte Adler-32 blocks, and a wrong trailer."""
+    import zlib
+    rng = np.random.RandomState(7)
+    # skewed byte distribution: Huffman codes of 2 .. 12 bits, no matches worth taking at level 1 / HUFFMAN_ONLY
+    p = np.array([0.30, 0.20, 0.12, 0.10, 0.08] + [0.20 / 251] * 251)
+    src = rng.choice(256, size=70000, p=p / p.sum()).astype(np.uint8).tobytes()
+    lengths = list(range(0, 12)) + list(range(300, 345)) + [640, 641, 5551, 5552, 5553, 11103, 11104, 11105, 70000]
+    for n in lengths:
+        d = src[:n]
+        for strat in (zlib.Z_HUFFMAN_ONLY, zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED):
+            c = zlib.compressobj(6, zlib.DEFLATED, 15, 8, strat)
+            z = c.compress(d) + c.flush()
+            assert pngio.zlib_decompress_fast(z, n) == d, (n, strat)
+            if n:
+                assert pngio.zlib_decompress_fast(z, n - 1) is None, (n, strat)
+                bad = bytearray(z); bad[-1] ^= 1                         # Adler-32 trailer off by one bit
+                assert pngio.zlib_decompress_fast(bytes(bad), n) is None
+    # all 0xff: the largest sums the Adler-32 blocks have to hold
+    d = b"\xff" * 200001
+    assert pngio.zlib_decompress_fast(zlib.compress(d, 1), len(d)) == d
 
 
 def test_reference_format_files_rgba_image_and_viridis_mask(tmp_path):
