@@ -272,6 +272,13 @@ int rr_host_draw_randoms(uint32_t seed, int n, const uint8_t *types, const int32
 int rr_host_assemble_batch(int n_frames, const rr_streak_rec *const *sim, const int32_t *n_sim, const uint32_t *seeds,
                            int W, int H, const double *db_ratios, int n_ratios, double noise_std, double noise_scale,
                            rr_streak_rec *out, int64_t out_cap, int32_t *offsets, int32_t *src_index);
+/* Host logic (no GPU): the field-of-view polygon of ONE streak in environment-map pixels -- FovComputation.
+ * compute_fov_plane_points (common/bad_weather.py:596-704) for the camera at the origin and N = 20 cone rays: the 20 rays,
+ * their lat-long image points and the wrap splice (20 or 24 vertices, x then y, into xy[48]).  It is the same header code
+ * (csrc/rr_streak_geom.h) k_plan compiles for the device, evaluated on the host for callers that want the polygon itself;
+ * the render path never calls it.  *n_vertices = 0 where the reference's try block would fail ("Drop skipped", :699-704). */
+int rr_host_fov_polygon(const rr_streak_rec *rec, double radius, double fov_deg, int rows, int cols, double *xy,
+                        int32_t *n_vertices);
 /* Host logic (no GPU): native loader of the particle simulator's XML output -- replaces
  * DBManager.load_streaks_from_xml (common/bad_weather.py:148-248).  The root's children are camera
  * frames (<i id t d rs>), their children imaged streaks (<r pid wp1 wd1 wp2 wd2 ip1 iw1 ip2 iw2/>).

@@ -126,6 +126,7 @@ def load() -> C.CDLL:
         "rr_host_link_probe": [C.c_int, C.c_size_t, C.c_double, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)],
         "rr_host_draw_randoms": [C.c_uint32, C.c_int, u8p, i32p, C.c_double, C.c_double, u8p, f64p],
         "rr_host_assemble_batch": [C.c_int, vp, i32p, vp, C.c_int, C.c_int, f64p, C.c_int, C.c_double, C.c_double, vp, C.c_int64, i32p, i32p],
+        "rr_host_fov_polygon": [vp, C.c_double, C.c_double, C.c_int, C.c_int, f64p, C.POINTER(C.c_int32)],
         "rr_host_load_particles_xml": [C.c_char_p, C.c_int, C.c_int, C.c_int, C.POINTER(vp)],
         "rr_host_particles_info": [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int64)],
         "rr_host_particles_copy": [vp, vp, vp],

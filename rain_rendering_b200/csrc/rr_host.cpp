@@ -10,6 +10,7 @@
 #include <math.h>
 #include <stdint.h>
 #include "../../include/rain_b200.h"
+#include "rr_streak_geom.h"
 
 namespace {
 struct MT {
@@ -128,5 +129,17 @@ extern "C" int rr_host_assemble_batch(int n_frames, const rr_streak_rec *const *
         if (o > 0x7fffffff) return RR_ERR_CAPACITY;
         offsets[f + 1] = (int32_t)o;
     }
+    return RR_OK;
+}
+
+// FovComputation.compute_fov_plane_points (common/bad_weather.py:596-704) on the host: the header code of the device path
+// (rr_fov_polygon, csrc/rr_streak_geom.h), for callers that want the polygon itself.
+extern "C" int rr_host_fov_polygon(const rr_streak_rec *rec, double radius, double fov_deg, int rows, int cols, double *xy,
+                                   int32_t *n_vertices) {
+    if (!rec || !xy || !n_vertices || rows <= 0 || cols <= 0) return RR_ERR_ARG;
+    double px[RR_FOV_N + 4], py[RR_FOV_N + 4];
+    const int n = rr_fov_polygon(*rec, radius, fov_deg, rows, cols, px, py);
+    for (int i = 0; i < n; i++) { xy[2 * i] = px[i]; xy[2 * i + 1] = py[i]; }
+    *n_vertices = n;
     return RR_OK;
 }

@@ -3,9 +3,12 @@
 Kept importable with the reference's names and call signatures:
 ``DBManager``, ``RainRenderer``, ``FovComputation``, ``EnvironmentMapGenerator``, ``DropType``,
 ``Streak``, ``Frame``.  The accelerated unit is the frame batch (``Generator.run`` ->
-``rr_render_frames``); the reference's per-streak entry points whose work now happens inside
-the CUDA kernels (``add_drop_to_image``, ``compute_fov_plane_points``, ``make_rain_layer``)
-raise ``NotImplementedError`` naming the call that replaces them -- there is no CPU path here.
+``rr_render_frames``); the reference's per-streak *rendering* entry points whose work now happens inside
+the CUDA kernels (``add_drop_to_image``, ``circle_of_confusion``, ``make_rain_layer``) raise
+``NotImplementedError`` naming the call that replaces them -- there is no CPU rendering path here.
+The per-streak *geometry* calls (``compute_circle``, ``warping_points``,
+``FovComputation.compute_fov_plane_points``) answer with the reference's values: the polygon through
+``rr_host_fov_polygon`` -- the header code ``k_plan`` compiles for the device, run on the host.
 """
 import os
 from enum import Enum
@@ -186,13 +189,30 @@ class RainRenderer:
         self.fov = fov
 
     def compute_circle(self, o, is_infinity=False):
-        raise NotImplementedError("the circle of confusion is evaluated per streak on the device (rr_plan_patch, csrc/rr_streak_geom.h); "
-                                  "RainContext.debug_read('plans') returns sig_y = c and sig_x = c / 2 of every streak")
+        """Thin-lens blur circle of an object at distance ``o`` (common/bad_weather.py:464-469), in pixels of the
+        reference's hard-wired 4.65 um pitch unless ``is_infinity``.  The render path evaluates the same expression per
+        streak on the device (rr_plan_patch, csrc/rr_streak_geom.h: sig_y = |c|, sig_x = |c| / 2)."""
+        f2 = self.f ** 2
+        if is_infinity:
+            return f2 / (self.N * o)
+        return ((o - self.focus_plane) * f2) / (o * (self.focus_plane - self.f) * self.N) / 4.65e-06
 
     @staticmethod
     def warping_points(drop, drop_texture, image_width, image_height):
-        raise NotImplementedError("the Big-drop warp quad is built on the device (rr_plan_patch, csrc/rr_streak_geom.h); "
-                                  "use Generator.run / RainContext.render_frames")
+        """Source and destination quads of a Big drop's perspective warp, and the patch's corners in the image
+        (common/bad_weather.py:300-328) -> (p1, p2, maxC, minC).  The render path builds the same quad on the device
+        (rr_plan_patch)."""
+        xs, ys = round(drop.image_position_start[0]), round(drop.image_position_start[1])
+        xe, ye = round(drop.image_position_end[0]), round(drop.image_position_end[1])
+        ds, de = np.floor(drop.image_diameter_start), np.floor(drop.image_diameter_end)
+        lo = np.array([max(min(xs, xe), 0), max(min(ys, ye), 0)])
+        hi = np.array([min(max(xs + ds, xe + de), image_width), min(max(ys, ye), image_height)])
+        th, tw = drop_texture.shape[:2]
+        eps = 0.001                                   # keeps the perspective matrix regular (:313)
+        src = np.float32([[0, 0], [tw, 0], [tw, th], [0, th]])
+        dst = np.float32([[xs - lo[0], ys - lo[1]], [xs - lo[0] + ds, ys - lo[1]],
+                          [xe - lo[0] + de + eps, ye - lo[1]], [xe - lo[0] + eps, ye - lo[1]]])
+        return src, dst, hi, lo
 
     def circle_of_confusion(self, drop, drop_distance, drop_dict):
         raise NotImplementedError("defocus runs inside the CUDA path (k_blur_v/k_blur_h); use Generator.run / RainContext.render_frames")
@@ -210,8 +230,32 @@ class FovComputation:
     def __init__(self, camera):
         self.camera = camera
 
-    def compute_fov_plane_points(self, *a, **k):
-        raise NotImplementedError("the field-of-view polygon is computed on the GPU (k_setup); use RainContext.streak_photometry_only")
+    def compute_fov_plane_points(self, drop_dict, radius, fov, N, env_shape):
+        """Field-of-view polygon of one drop in environment-map pixels (common/bad_weather.py:596-704) ->
+        (polygon (n, 2), cone points on the sphere, drop position, drop direction).  The polygon comes from
+        ``rr_host_fov_polygon``: the header code k_plan compiles for the device (csrc/rr_streak_geom.h), evaluated on the
+        host -- 20 cone rays, camera at the origin (what Generator uses, generator.py:268); other arguments are refused.
+        The cone points (unused by the reference's caller, generator.py:175) are returned as an empty (0, 3) array.  A drop
+        the reference would skip prints 'Drop skipped' and returns its except-branch tuple (:699-704)."""
+        import ctypes as C
+        from rain_rendering_b200 import _lib
+        if N != 20 or np.any(np.asarray(self.camera, np.float64) != 0):
+            raise NotImplementedError("compute_fov_plane_points: the B200 path evaluates N = 20 rays for a camera at the origin")
+        w0 = np.asarray(drop_dict.world_position_start, np.float64)
+        w1 = np.asarray(drop_dict.world_position_end, np.float64)
+        position = (w0 + w1) / 2
+        position[1], position[2] = position[2], position[1].copy()        # y <-> z (:599)
+        direction = position / np.linalg.norm(position)
+        rec = np.zeros(1, _S.STREAK_DTYPE)
+        rec["wp1"][0], rec["wp2"][0] = w0, w1
+        xy = np.zeros(48)
+        n = C.c_int32(0)
+        _lib.check(_lib.load().rr_host_fov_polygon(_lib.ptr(rec), float(radius), float(fov), int(env_shape[0]), int(env_shape[1]),
+                                                   _lib.ptr(xy), C.byref(n)), "rr_host_fov_polygon")
+        if n.value == 0:
+            print('Drop skipped')
+            return np.array([]), np.array([]), direction, position
+        return xy[:2 * n.value].reshape(-1, 2).copy(), np.zeros((0, 3)), position, direction
 
 
 class EnvironmentMapGenerator:

@@ -460,3 +460,117 @@ def test_dropin_particles_simulation_writes_the_xml_main_py_expects(tmp_path):
         sys.path.remove(DROPIN)
         for k in [k for k in sys.modules if k == "tools" or k.startswith("tools.")]:
             del sys.modules[k]
+
+
+def _import_dropin_bad_weather():
+    for k in [k for k in sys.modules if k == "common" or k.startswith("common.")]:
+        del sys.modules[k]
+    sys.path.insert(0, DROPIN)
+    try:
+        import common.bad_weather as bw
+    finally:
+        sys.path.remove(DROPIN)
+    return bw
+
+
+def test_dropin_geometry_calls_answer_like_the_oracle():
+    """compute_circle, warping_points and FovComputation.compute_fov_plane_points of the drop-in return the reference's
+    values (oracle restatement, pinned to the live reference by tests/test_oracle.py); the polygon goes through
+    rr_host_fov_polygon, the header code the device path compiles."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from util import Scenario
+    from oracle import rain_oracle as ro
+    try:
+        bw = _import_dropin_bad_weather()
+        sc = Scenario(1242, 375, 1, 600, dataset="kitti", seed=11)
+        cam = sc.cam
+        env_shape = (cam.H, sc.tables.W_env, 3)
+        rr = bw.RainRenderer(cam.focal_m, cam.f_number, cam.focus_plane, cam.radius, cam.fov_deg)
+        fc = bw.FovComputation(camera=np.array([0, 0, 0]))
+        n_big = n24 = 0
+        streaks = sc.oracle_frames[0]
+        assert len(streaks) > 300
+        for s in streaks:
+            d = bw.Streak()
+            d.world_position_start, d.world_position_end = s.wp1.copy(), s.wp2.copy()
+            d.image_position_start, d.image_position_end = s.ip1.copy(), s.ip2.copy()
+            d.image_diameter_start, d.image_diameter_end, d.max_width = s.iw1, s.iw2, s.max_width
+            pts, pts3d, pos, direction = fc.compute_fov_plane_points(d, cam.radius, cam.fov_deg, 20, env_shape)
+            ref = ro.fov_polygon(s, cam, env_shape)
+            assert pts.shape == ref.shape and (len(ref) == 0 or np.abs(pts - ref).max() < 1e-9)
+            n24 += len(ref) == 24
+            P = (s.wp1 + s.wp2) / 2
+            P[1], P[2] = P[2], P[1].copy()
+            assert np.array_equal(pos, P) and np.allclose(direction, P / np.linalg.norm(P), rtol=0, atol=1e-15)
+            o = abs(P[1])
+            if cam.pix_size == 4.65e-06:
+                assert rr.compute_circle(o) == ro.circle_of_confusion_px(o, cam)
+            if s.drop_type == ro.BIG:
+                n_big += 1
+                tex = sc.db.textures[0]
+                p1, p2, maxC, minC = bw.RainRenderer.warping_points(d, tex, cam.W, cam.H)
+                q1, q2, qmax, qmin = ro.warping_points(s, tex.shape[1], tex.shape[0], cam.W, cam.H)
+                assert np.array_equal(p1, q1) and np.array_equal(p2, q2) and np.array_equal(maxC, qmax) and np.array_equal(minC, qmin)
+        assert n_big > 5
+        assert rr.compute_circle(3.0, is_infinity=True) == cam.focal_m ** 2 / (cam.f_number * 3.0)
+        with pytest.raises(NotImplementedError):
+            fc.compute_fov_plane_points(d, cam.radius, cam.fov_deg, 16, env_shape)
+        with pytest.raises(NotImplementedError):
+            bw.FovComputation(camera=np.array([0, 1, 0])).compute_fov_plane_points(d, cam.radius, cam.fov_deg, 20, env_shape)
+        with pytest.raises(NotImplementedError):
+            rr.add_drop_to_image()
+    finally:
+        for k in [k for k in sys.modules if k == "common" or k.startswith("common.")]:
+            del sys.modules[k]
+
+
+@pytest.mark.skipif(not os.path.isfile(os.path.join(REF, "main.py")), reason="reference tree not mounted")
+def test_dropin_geometry_calls_answer_like_the_live_reference():
+    """The same three calls against the UNTOUCHED reference classes, in a subprocess each side (both packages are called
+    ``common``)."""
+    code = r"""
+import sys, os, pickle
+import numpy as np
+side, ROOT, DROPIN, REF = sys.argv[1:5]
+sys.path.insert(0, ROOT)
+if side == "ref":
+    from oracle import ref_harness
+    bw = ref_harness.load_reference()["bw"]
+else:
+    sys.path.insert(0, DROPIN)
+    import common.bad_weather as bw
+rng = np.random.RandomState(3)
+out = []
+rr = bw.RainRenderer(0.006, 6.0, 6.0, 10.0, 165.0)
+fc = bw.FovComputation(camera=np.array([0, 0, 0]))
+for i in range(200):
+    d = bw.Streak()
+    c = np.array([rng.uniform(-6, 6), rng.uniform(-2, 3), rng.uniform(0.5, 25)])
+    d.world_position_start = c + rng.uniform(-0.05, 0.05, 3)
+    d.world_position_end = c + rng.uniform(-0.05, 0.05, 3)
+    d.image_position_start = rng.randint(-20, 1300, 2)
+    d.image_position_end = d.image_position_start + rng.randint(-15, 60, 2)
+    d.image_diameter_start, d.image_diameter_end = rng.uniform(4, 12), rng.uniform(4, 12)
+    pts, _, pos, direction = fc.compute_fov_plane_points(d, 10.0, 165.0, 20, (375, 1909, 3))
+    p1, p2, maxC, minC = bw.RainRenderer.warping_points(d, np.zeros((200 + i, 32)), 1242, 375)
+    out.append((np.asarray(pts), np.asarray(pos), np.asarray(direction), rr.compute_circle(abs(c[2])), rr.compute_circle(abs(c[2]), True),
+                np.asarray(p1), np.asarray(p2), np.asarray(maxC, float), np.asarray(minC, float)))
+pickle.dump(out, open(sys.argv[5], "wb"))
+"""
+    res = {}
+    for side in ("ref", "dropin"):
+        path = os.path.join(tempfile.gettempdir(), "rr_geom_%s_%d.pkl" % (side, os.getpid()))
+        r = subprocess.run([sys.executable, "-c", code, side, ROOT, DROPIN, REF, path], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout + r.stderr
+        import pickle
+        res[side] = pickle.load(open(path, "rb"))
+        os.remove(path)
+    n24 = 0
+    for a, b in zip(res["ref"], res["dropin"]):
+        assert a[0].shape == b[0].shape and (a[0].size == 0 or np.abs(a[0] - b[0]).max() < 1e-9)
+        n24 += len(a[0]) == 24
+        assert np.array_equal(a[1], b[1]) and np.abs(a[2] - b[2]).max() < 1e-15
+        assert a[3] == b[3] and a[4] == b[4]
+        for k in (5, 6, 7, 8):
+            assert np.array_equal(a[k], b[k])
+    assert n24 > 0
