@@ -31,66 +31,101 @@ static const uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 
 static const uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
 static const uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 
-static inline uint32_t reverse_bits(uint32_t v, int n) {          // the low n (1 .. 15) bits of v, reversed
-    v = ((v & 0x5555u) << 1) | ((v >> 1) & 0x5555u);
-    v = ((v & 0x3333u) << 2) | ((v >> 2) & 0x3333u);
-    v = ((v & 0x0f0fu) << 4) | ((v >> 4) & 0x0f0fu);
-    v = ((v << 8) | (v >> 8)) & 0xffffu;
-    return v >> (16 - n);
-}
-
 // Builds the two-level decode table of a canonical Huffman code.  lens[0..n): code lengths (0 = unused).  what: 0 literal /
 // length alphabet, 1 distance alphabet, 2 code-length alphabet (values = the symbol itself).  Returns false when the code
 // is over-subscribed, or incomplete (except the single-code case deflate allows).
+//
+// A deflate block of OpenCV's / libpng's writers holds about 16 K symbols, so a 1.4 MB image rebuilds its tables 85 times:
+// the build is written for speed.  Symbols are visited in canonical order (counting sort by length); the first-level table
+// grows with the code length -- while the codes are l bits long only the first 2^l entries exist, and moving on to l + 1
+// bits DOUBLES the table with one memcpy (an l-bit code's entry repeats every 2^l indices) -- so every entry is written
+// once, sequentially, instead of by one strided loop per symbol.  The stream's bit order is LSB first, so the table is
+// indexed by the bit-REVERSED code; `code` below is kept reversed and incremented from its top bit.
+static inline uint32_t symbol_entry(int what, int s) {
+    if (what == 0) {
+        if (s < 256) return entry(KIND_LIT, 0, 1, s);
+        if (s == 256) return entry(KIND_EOB, 0, 0, 0);
+        if (s <= 285) return entry(KIND_LEN, 0, kLenExtra[s - 257], kLenBase[s - 257]);
+        return 0;                                                  // 286, 287: never valid in data
+    }
+    if (what == 1) return s < 30 ? entry(KIND_DIST, 0, kDistExtra[s], kDistBase[s]) : 0;
+    return entry(KIND_LIT, 0, 1, s);
+}
+
 static inline bool build_table(const uint8_t *lens, int n, int what, uint32_t *table, int primary_bits, int table_cap) {
     int count[16] = {0};
     for (int i = 0; i < n; i++) count[lens[i]]++;
     count[0] = 0;
-    int max_len = 0, used = 0;
-    for (int l = 1; l < 16; l++) if (count[l]) { max_len = l; used += count[l]; }
+    int max_len = 0, min_len = 0, used = 0;
+    for (int l = 15; l >= 1; l--) if (count[l]) { if (!max_len) max_len = l; min_len = l; used += count[l]; }
     // Kraft sum
     long left = 1;
     for (int l = 1; l <= 15; l++) { left <<= 1; left -= count[l]; if (left < 0) return false; }
-    if (left > 0 || used == 0 || max_len > primary_bits)           // otherwise a complete code writes every first-level entry below
-        for (int i = 0; i < (1 << primary_bits); i++) table[i] = 0;   // (with second-level tables the KIND_SUB test reads them first)
-    if (used == 0) return what == 1;                               // no distance codes at all: legal when the block has no matches
-    if (left > 0 && !(used == 1 && max_len == 1)) return false;    // incomplete: only a lone 1-bit code is allowed
-    int next_code[16], code = 0;
-    for (int l = 1; l < 16; l++) { code = (code + count[l - 1]) << 1; next_code[l] = code; }
-    const int sub_bits = max_len > primary_bits ? max_len - primary_bits : 0;
-    int next_sub = 1 << primary_bits;
-    for (int s = 0; s < n; s++) {
-        const int l = lens[s];
-        if (!l) continue;
-        const uint32_t rev = reverse_bits((uint32_t)next_code[l]++, l);
-        uint32_t e;
-        if (what == 0) {
-            if (s < 256) e = entry(KIND_LIT, 0, 1, s);
-            else if (s == 256) e = entry(KIND_EOB, 0, 0, 0);
-            else if (s <= 285) e = entry(KIND_LEN, 0, kLenExtra[s - 257], kLenBase[s - 257]);
-            else e = 0;                                            // 286, 287: never valid in data
-        } else if (what == 1) {
-            e = s < 30 ? entry(KIND_DIST, 0, kDistExtra[s], kDistBase[s]) : 0;
-        } else e = entry(KIND_LIT, 0, 1, s);
-        if (l <= primary_bits) {
-            if (e) e |= (uint32_t)l;
-            for (uint32_t i = rev; i < (1u << primary_bits); i += 1u << l) table[i] = e;
-        } else {
-            const uint32_t prefix = rev & ((1u << primary_bits) - 1);
-            uint32_t pe = table[prefix];
-            if (((pe >> 12) & 15) != KIND_SUB) {
-                if (next_sub + (1 << sub_bits) > table_cap) return false;
-                for (int i = 0; i < (1 << sub_bits); i++) table[next_sub + i] = 0;
-                pe = entry(KIND_SUB, primary_bits, sub_bits, next_sub);
-                table[prefix] = pe;
-                next_sub += 1 << sub_bits;
+    if (used == 0) {                                               // no distance codes at all: legal when the block has no matches
+        for (int i = 0; i < (1 << primary_bits); i++) table[i] = 0;
+        return what == 1;
+    }
+    if (left > 0) {                                                // incomplete: only a lone 1-bit code is allowed
+        if (!(used == 1 && max_len == 1)) return false;
+        int s = 0;
+        while (!lens[s]) s++;
+        uint32_t e = symbol_entry(what, s);
+        if (e) e |= 1u;
+        for (int i = 0; i < (1 << primary_bits); i += 2) { table[i] = e; table[i + 1] = 0; }
+        return true;
+    }
+    // symbols in canonical order
+    uint16_t sorted[320];
+    int offs[17];
+    offs[1] = 0;
+    for (int l = 1; l < 16; l++) offs[l + 1] = offs[l] + count[l];
+    for (int s = 0; s < n; s++) if (lens[s]) sorted[offs[lens[s]]++] = (uint16_t)s;
+    // ---- first level ----
+    uint32_t code = 0;                                             // bit-reversed code of the next symbol
+    int k = 0, len = min_len;
+    int cur_bits = len < primary_bits ? len : primary_bits;        // the table holds 2^cur_bits entries so far
+    for (; len <= primary_bits && len <= max_len; len++) {
+        for (; cur_bits < len; cur_bits++) memcpy(table + (1u << cur_bits), table, sizeof(uint32_t) << cur_bits);
+        const uint32_t ones = (1u << len) - 1;
+        for (int c = count[len]; c > 0; c--) {
+            uint32_t e = symbol_entry(what, sorted[k++]);
+            if (e) e |= (uint32_t)len;
+            table[code] = e;
+            if (code == ones) {                                    // the all-ones code: the last one of a complete code
+                for (; cur_bits < primary_bits; cur_bits++) memcpy(table + (1u << cur_bits), table, sizeof(uint32_t) << cur_bits);
+                return k == used;
             }
-            const uint32_t base = pe >> 16;
-            if (e) e |= (uint32_t)(l - primary_bits);
-            for (uint32_t i = rev >> primary_bits; i < (1u << sub_bits); i += 1u << (l - primary_bits)) table[base + i] = e;
+            const uint32_t bit = 1u << (31 - __builtin_clz(code ^ ones));     // highest 0 bit: the carry of the increment stops there
+            code = (code & (bit - 1)) | bit;
         }
     }
-    return true;
+    for (; cur_bits < primary_bits; cur_bits++) memcpy(table + (1u << cur_bits), table, sizeof(uint32_t) << cur_bits);
+    // ---- codes longer than the first level: one second-level table of 2^(max_len - primary_bits) entries per prefix; codes
+    // with the same first `primary_bits` stream bits are neighbours in canonical order ----
+    const int sub_bits = max_len - primary_bits;
+    const uint32_t pmask = (1u << primary_bits) - 1;
+    int next_sub = 1 << primary_bits;
+    uint32_t cur_prefix = 0xffffffffu, base = 0;
+    for (; len <= max_len; len++) {
+        const uint32_t ones = (1u << len) - 1;
+        for (int c = count[len]; c > 0; c--) {
+            uint32_t e = symbol_entry(what, sorted[k++]);
+            if (e) e |= (uint32_t)(len - primary_bits);
+            const uint32_t prefix = code & pmask;
+            if (prefix != cur_prefix) {
+                if (next_sub + (1 << sub_bits) > table_cap) return false;
+                cur_prefix = prefix;
+                base = (uint32_t)next_sub;
+                next_sub += 1 << sub_bits;
+                table[prefix] = entry(KIND_SUB, primary_bits, sub_bits, (int)base);
+            }
+            for (uint32_t i = code >> primary_bits; i < (1u << sub_bits); i += 1u << (len - primary_bits)) table[base + i] = e;
+            if (code == ones) return k == used;
+            const uint32_t bit = 1u << (31 - __builtin_clz(code ^ ones));
+            code = (code & (bit - 1)) | bit;
+        }
+    }
+    return false;                                                  // unreachable for a complete code (the all-ones code ends it)
 }
 
 // First-level entries whose index holds TWO complete literal codes become pair entries (count 2, both bytes, the bits of
@@ -101,16 +136,22 @@ static inline void pair_literals(uint32_t *table, int primary_bits) {
     const int n = 1 << primary_bits;
     uint32_t single[1 << 12];
     memcpy(single, table, sizeof(uint32_t) * n);
-    for (int i = 0; i < n; i++) {
-        const uint32_t e = single[i];
+    // an l1-bit literal owns the entries i0 + (k << l1), i0 < 2^l1: visit every literal once, at its first entry, and walk
+    // its copies with k -- single[k] is then the entry of the bits that follow the first code
+    for (int i0 = 0; i0 < n / 2; i0++) {
+        const uint32_t e = single[i0];
         if (((e >> 12) & 15) != KIND_LIT) continue;
         const int l1 = (int)(e & 0xff);
-        if (l1 >= primary_bits) continue;
-        const uint32_t e2 = single[i >> l1];
-        if (((e2 >> 12) & 15) != KIND_LIT) continue;
-        const int l2 = (int)(e2 & 0xff);
-        if (l1 + l2 > primary_bits) continue;
-        table[i] = entry(KIND_LIT, l1 + l2, 2, (int)((e >> 16) & 0xff) | (int)(((e2 >> 16) & 0xff) << 8));
+        if (i0 >> l1) continue;                                     // a copy, not the first entry (also skips l1 = primary_bits)
+        const int room = primary_bits - l1;                         // bits left for the second code
+        const uint32_t lit1 = (e >> 16) & 0xff;
+        for (int k = 0; k < (1 << room); k++) {
+            const uint32_t e2 = single[k];
+            if (((e2 >> 12) & 15) != KIND_LIT) continue;
+            const int l2 = (int)(e2 & 0xff);
+            if (l2 > room) continue;
+            table[i0 + (k << l1)] = entry(KIND_LIT, l1 + l2, 2, (int)(lit1 | (((e2 >> 16) & 0xff) << 8)));
+        }
     }
 }
 
