@@ -341,7 +341,18 @@ static inline bool zlib_decompress(const uint8_t *in, size_t in_len, uint8_t *ou
                 const uint8_t *const qe = o + len;
                 do { uint64_t w; memcpy(&w, s, 8); memcpy(q, &w, 8); s += 8; q += 8; } while (q < qe);
             } else if (dist == 1) memset(o, *s, len);
-            else for (size_t i = 0; i < len; i++) o[i] = s[i];
+            else if (len >= 24 && (size_t)(o_end - o) >= len + 8) {
+                // a short period (2 .. 7): 8 * dist bytes of the repeating sequence are dist whole 64-bit words; they are built
+                // once in registers / the stack and stored round robin -- no load ever touches bytes just written (a copy from
+                // "dist rounded up to 8" bytes back stalls on store forwarding whenever that is not a multiple of 8)
+                uint8_t pat[56];
+                for (size_t i = 0, k = 0; i < 8 * dist; i++) { pat[i] = s[k]; if (++k == dist) k = 0; }
+                uint64_t pw[7];
+                memcpy(pw, pat, 8 * dist);
+                uint8_t *q = o;
+                const uint8_t *const qe = o + len;
+                for (size_t k = 0; q < qe; q += 8) { memcpy(q, &pw[k], 8); if (++k == dist) k = 0; }
+            } else for (size_t i = 0; i < len; i++) o[i] = s[i];
             o += len;
         }
         if (b.overrun()) return false;

@@ -120,7 +120,9 @@ def test_inflate_decoder_against_zlib_streams_of_every_block_type_and_mutations(
     smooth = np.cumsum(rng.randint(-2, 3, 200000)).astype(np.uint8).tobytes()
     datas = [b"", b"a", b"hello hello hello hello", bytes(70000), rng.randint(0, 256, 100000).astype(np.uint8).tobytes(), smooth, skew.tobytes(),
              (b"0123456789abcdef" * 5000) + rng.randint(0, 256, 3000).astype(np.uint8).tobytes() + bytes(range(256)) * 40,
-             np.repeat(rng.randint(0, 256, 3000).astype(np.uint8), rng.randint(1, 400, 3000)).tobytes()]
+             np.repeat(rng.randint(0, 256, 3000).astype(np.uint8), rng.randint(1, 400, 3000)).tobytes(),
+             # long matches with periods 2 .. 7 (copied in words from a multiple of the period back)
+             b"".join(bytes(rng.randint(0, 256, per).astype(np.uint8)) * int(rng.randint(3, 200)) for per in list(range(2, 8)) * 40)]
     n_streams = 0
     for d in datas:
         for level in (0, 1, 6, 9):
