@@ -61,10 +61,36 @@ int paeth(int a, int b, int c) {
     return (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
 }
 
+// Where decode() delivers the pixels: row by row, right after a scanline is unfiltered (it is still in L1 then), into the
+// caller's batch buffer.  SINK_NONE keeps them in Image::px only.
+enum { SINK_NONE = 0, SINK_BGR8 = 1, SINK_DEPTH_U16 = 2, SINK_DEPTH_F32 = 3 };
+struct RowSink { int kind = SINK_NONE; void *dst = nullptr; };
+
+// cv2.imread(path) semantics for one scanline: BGR uint8, gray replicated, alpha dropped, 16-bit -> high byte
+inline void row_to_bgr8(int w, int ch, int step, const unsigned char *s, uint8_t *d) {
+    if (ch == 1 || ch == 2) {
+        for (int i = 0; i < w; i++) { uint8_t g = s[(size_t)i * ch * step]; d[3 * i] = d[3 * i + 1] = d[3 * i + 2] = g; }
+    } else {
+        for (int i = 0; i < w; i++) {
+            const unsigned char *p = s + (size_t)i * ch * step;
+            d[3 * i] = p[2 * step]; d[3 * i + 1] = p[step]; d[3 * i + 2] = p[0];
+        }
+    }
+}
+// cv2.imread(path, IMREAD_UNCHANGED) of a single-channel scanline: uint16 samples, or .astype(np.float32) / 256.
+inline void row_to_u16(int w, int depth, const unsigned char *s, uint16_t *d) {
+    if (depth == 16) for (int i = 0; i < w; i++) d[i] = (uint16_t)((s[2 * i] << 8) | s[2 * i + 1]);
+    else for (int i = 0; i < w; i++) d[i] = s[i];
+}
+inline void row_to_f32(int w, int depth, const unsigned char *s, float *d) {
+    if (depth == 16) for (int i = 0; i < w; i++) d[i] = (float)((s[2 * i] << 8) | s[2 * i + 1]) / 256.f;
+    else for (int i = 0; i < w; i++) d[i] = (float)s[i] / 256.f;
+}
+
 // -> RR_OK, RR_PNG_UNSUPPORTED (valid PNG this codec does not handle) or RR_ERR_ARG (not a readable PNG)
 // want_w / want_h > 0: the size the caller's buffer was made for -- anything else returns RR_PNG_SIZE right after the
 // header, before a single byte is allocated for the pixels (a 60-byte file may claim 65536 x 65536 RGBA16 = 34 GB)
-int decode(const char *path, Image *img, bool header_only, int want_w = 0, int want_h = 0) {
+int decode(const char *path, Image *img, bool header_only, int want_w = 0, int want_h = 0, const RowSink *sink = nullptr) {
     std::vector<unsigned char> file;
     if (!read_file(path, &file)) return RR_ERR_ARG;
     if (file.size() < 8 + 25 || memcmp(file.data(), kSig, 8) != 0) return RR_ERR_ARG;
@@ -124,6 +150,8 @@ int decode(const char *path, Image *img, bool header_only, int want_w = 0, int w
         }
     }
     if (ret != RR_OK) return ret;
+    const int sink_kind = sink ? sink->kind : SINK_NONE;
+    if ((sink_kind == SINK_DEPTH_U16 || sink_kind == SINK_DEPTH_F32) && img->channels != 1) return RR_PNG_UNSUPPORTED;
     // unfilter IN PLACE (each scanline keeps its filter byte in front): no second buffer, and the Sub filter -- what
     // OpenCV's writer and this library's own use throughout -- runs as bpp independent running sums
     const int bpp = img->channels * (img->depth / 8);
@@ -132,6 +160,30 @@ int decode(const char *path, Image *img, bool header_only, int want_w = 0, int w
     for (int y = 0; y < img->h; y++) {
         unsigned char *row = raw.data() + (stride + 1) * (size_t)y + 1;
         const int ft = row[-1];
+        // Sub / None scanlines of the two layouts the frame pipeline reads (8-bit RGB, 16-bit gray) go to the sink in ONE pass:
+        // the running sums are written straight into the batch buffer in its sample order, and the scanline stays filtered
+        // in `raw` -- allowed when the next scanline does not look at this one (Up, Average and Paeth do)
+        const bool next_reads_this = y + 1 < img->h && raw[(stride + 1) * (size_t)(y + 1)] >= 2;
+        if (ft <= 1 && !next_reads_this && sink_kind == SINK_BGR8 && img->channels == 3 && img->depth == 8) {
+            uint8_t *d = (uint8_t *)sink->dst + (size_t)y * img->w * 3;
+            if (ft == 1) {
+                unsigned a = 0, b = 0, c = 0;
+                for (size_t i = 0; i + 3 <= stride; i += 3) { a += row[i]; b += row[i + 1]; c += row[i + 2]; d[i] = (uint8_t)c; d[i + 1] = (uint8_t)b; d[i + 2] = (uint8_t)a; }
+            } else {
+                for (size_t i = 0; i + 3 <= stride; i += 3) { d[i] = row[i + 2]; d[i + 1] = row[i + 1]; d[i + 2] = row[i]; }
+            }
+            prev = row;
+            continue;
+        }
+        if (ft <= 1 && !next_reads_this && sink_kind == SINK_DEPTH_U16 && img->channels == 1 && img->depth == 16) {
+            uint16_t *d = (uint16_t *)sink->dst + (size_t)y * img->w;
+            if (ft == 1) {
+                unsigned a = 0, b = 0;
+                for (int i = 0; i < img->w; i++) { a += row[2 * i]; b += row[2 * i + 1]; d[i] = (uint16_t)(((a & 255u) << 8) | (b & 255u)); }
+            } else row_to_u16(img->w, 16, row, d);
+            prev = row;
+            continue;
+        }
         switch (ft) {
             case 0: break;
             case 1:
@@ -169,51 +221,12 @@ int decode(const char *path, Image *img, bool header_only, int want_w = 0, int w
                 break;
             default: return RR_ERR_ARG;
         }
+        if (sink_kind == SINK_BGR8) row_to_bgr8(img->w, img->channels, img->depth / 8, row, (uint8_t *)sink->dst + (size_t)y * img->w * 3);
+        else if (sink_kind == SINK_DEPTH_U16) row_to_u16(img->w, img->depth, row, (uint16_t *)sink->dst + (size_t)y * img->w);
+        else if (sink_kind == SINK_DEPTH_F32) row_to_f32(img->w, img->depth, row, (float *)sink->dst + (size_t)y * img->w);
         prev = row;
     }
     img->px.swap(raw);                  // scanlines of stride + 1 bytes (filter byte first), unfiltered
-    return RR_OK;
-}
-
-// cv2.imread(path) semantics: BGR uint8, gray replicated, alpha dropped, 16-bit -> high byte
-int to_bgr8(const Image &im, uint8_t *dst) {
-    const int step = im.depth / 8, ch = im.channels;
-    for (int y = 0; y < im.h; y++) {
-        const unsigned char *s = im.row(y);
-        uint8_t *d = dst + (size_t)y * im.w * 3;
-        if (ch == 1 || ch == 2) {
-            for (int i = 0; i < im.w; i++) { uint8_t g = s[(size_t)i * ch * step]; d[3 * i] = d[3 * i + 1] = d[3 * i + 2] = g; }
-        } else {
-            for (int i = 0; i < im.w; i++) {
-                const unsigned char *p = s + (size_t)i * ch * step;
-                d[3 * i] = p[2 * step]; d[3 * i + 1] = p[step]; d[3 * i + 2] = p[0];
-            }
-        }
-    }
-    return RR_OK;
-}
-
-// cv2.imread(path, IMREAD_UNCHANGED).astype(np.float32) / 256. for a single-channel file
-int to_depth_f32(const Image &im, float *dst) {
-    if (im.channels != 1) return RR_PNG_UNSUPPORTED;
-    for (int y = 0; y < im.h; y++) {
-        const unsigned char *s = im.row(y);
-        float *d = dst + (size_t)y * im.w;
-        if (im.depth == 16) for (int i = 0; i < im.w; i++) d[i] = (float)((s[2 * i] << 8) | s[2 * i + 1]) / 256.f;
-        else for (int i = 0; i < im.w; i++) d[i] = (float)s[i] / 256.f;
-    }
-    return RR_OK;
-}
-
-// cv2.imread(path, IMREAD_UNCHANGED) of a single-channel file as uint16 samples (the /256 happens on the device)
-int to_depth_u16(const Image &im, uint16_t *dst) {
-    if (im.channels != 1) return RR_PNG_UNSUPPORTED;
-    for (int y = 0; y < im.h; y++) {
-        const unsigned char *s = im.row(y);
-        uint16_t *d = dst + (size_t)y * im.w;
-        if (im.depth == 16) for (int i = 0; i < im.w; i++) d[i] = (uint16_t)((s[2 * i] << 8) | s[2 * i + 1]);
-        else for (int i = 0; i < im.w; i++) d[i] = s[i];
-    }
     return RR_OK;
 }
 
@@ -377,12 +390,11 @@ static int read_batch(int n, const char *const *image_paths, const char *const *
         int r = RR_ERR_ARG;
         try {
             Image im;
-            r = decode(paths[i], &im, false, kind ? Wd : Wi, kind ? Hd : Hi);
-            if (r == RR_OK) {
-                if (kind == 0) r = to_bgr8(im, bgr + (size_t)i * 3 * Wi * Hi);
-                else if (depth_u16) r = to_depth_u16(im, (uint16_t *)depth + (size_t)i * Wd * Hd);
-                else r = to_depth_f32(im, (float *)depth + (size_t)i * Wd * Hd);
-            }
+            RowSink sink;
+            if (kind == 0) { sink.kind = SINK_BGR8; sink.dst = bgr + (size_t)i * 3 * Wi * Hi; }
+            else if (depth_u16) { sink.kind = SINK_DEPTH_U16; sink.dst = (uint16_t *)depth + (size_t)i * Wd * Hd; }
+            else { sink.kind = SINK_DEPTH_F32; sink.dst = (float *)depth + (size_t)i * Wd * Hd; }
+            r = decode(paths[i], &im, false, kind ? Wd : Wi, kind ? Hd : Hi, &sink);
         } catch (...) { r = RR_ERR_ARG; }              // std::bad_alloc and friends must not cross a thread / the C ABI
         if (r != RR_OK) __atomic_store_n(&status[i], (int32_t)r, __ATOMIC_RELAXED);     // two writers at most (image, depth), both storing a failure code
     });

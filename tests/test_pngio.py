@@ -39,6 +39,76 @@ def test_decode_equals_cv2_imread_for_every_supported_layout(tmp_path):
                 assert np.array_equal(d[0], cv2.imread(p, cv2.IMREAD_UNCHANGED).astype(np.float32) / 256.)
 
 
+def _write_png_with_row_filters(path, arr, filters):
+    """A PNG whose scanline y uses filter type filters[y] (0 None, 1 Sub, 2 Up, 3 Average, 4 Paeth): what libpng's adaptive
+    filtering produces and OpenCV's writer (Sub only) never does."""
+    import struct
+    import zlib
+    H, W = arr.shape[:2]
+    ch = 1 if arr.ndim == 2 else arr.shape[2]
+    depth = arr.dtype.itemsize * 8
+    raw = arr.astype(">u2").tobytes() if depth == 16 else arr.tobytes()
+    bpp, stride = ch * depth // 8, W * ch * depth // 8
+    rows = [np.frombuffer(raw[y * stride:(y + 1) * stride], np.uint8).astype(np.int32) for y in range(H)]
+    out = bytearray()
+    zero = np.zeros(stride, np.int32)
+    for y in range(H):
+        cur, up = rows[y], rows[y - 1] if y else zero
+        left = np.concatenate([zero[:bpp], cur[:-bpp]])
+        upleft = np.concatenate([zero[:bpp], up[:-bpp]])
+        ft = int(filters[y])
+        if ft == 0:
+            pred = zero
+        elif ft == 1:
+            pred = left
+        elif ft == 2:
+            pred = up
+        elif ft == 3:
+            pred = (left + up) >> 1
+        else:
+            pa, pb, pc = np.abs(up - upleft), np.abs(left - upleft), np.abs(left + up - 2 * upleft)
+            pred = np.where((pa <= pb) & (pa <= pc), left, np.where(pb <= pc, up, upleft))
+        out.append(ft)
+        out += ((cur - pred) & 255).astype(np.uint8).tobytes()
+    def chunk(t, d):
+        return struct.pack(">I", len(d)) + t + d + struct.pack(">I", zlib.crc32(t + d) & 0xffffffff)
+    color = {1: 0, 2: 4, 3: 2, 4: 6}[ch]
+    z = zlib.compress(bytes(out), 6)
+    with open(path, "wb") as f:
+        f.write(b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", W, H, depth, color, 0, 0, 0)) +
+                chunk(b"IDAT", z[:len(z) // 2]) + chunk(b"IDAT", z[len(z) // 2:]) + chunk(b"IEND", b""))
+
+
+def test_decode_with_every_row_filter_and_their_mixtures(tmp_path):
+    """Scanlines filtered with None / Sub / Up / Average / Paeth in every order (the decoder leaves Sub and None lines
+    filtered when it can hand them to the batch buffer in one pass -- only if the NEXT line does not need them), two IDAT
+    chunks, all layouts: equal to cv2.imread."""
+    rng = np.random.RandomState(9)
+    H, W = 41, 37
+    smooth = lambda shape, dt: (np.cumsum(rng.randint(-3, 4, shape), axis=1) % (256 if dt == np.uint8 else 65536)).astype(dt)
+    layouts = {"rgb8": smooth((H, W, 3), np.uint8), "gray16": smooth((H, W), np.uint16), "gray8": smooth((H, W), np.uint8),
+               "rgba8": smooth((H, W, 4), np.uint8), "rgb16": smooth((H, W, 3), np.uint16)}
+    patterns = [np.full(H, t) for t in range(5)] + [rng.randint(0, 5, H) for _ in range(6)] + [np.arange(H) % 2, 1 + np.arange(H) % 2,
+                np.where(np.arange(H) % 3 == 0, 4, 1), np.where(np.arange(H) == H - 1, 2, 1), np.where(np.arange(H) == 0, 1, 3)]
+    for name, arr in layouts.items():
+        for k, filt in enumerate(patterns):
+            p = str(tmp_path / ("%s_%d.png" % (name, k)))
+            _write_png_with_row_filters(p, arr, filt)
+            ref = cv2.imread(p)
+            assert ref is not None
+            out = np.zeros((1, H, W, 3), np.uint8)
+            assert pngio.read_batch([p], None, out, None, 1).tolist() == [0], (name, k)
+            assert np.array_equal(out[0], ref), (name, filt.tolist())
+            if arr.ndim == 2:
+                unch = cv2.imread(p, cv2.IMREAD_UNCHANGED)
+                d16 = np.zeros((1, H, W), np.uint16)
+                assert pngio.read_batch(None, [p], None, d16, 1).tolist() == [0]
+                assert np.array_equal(d16[0], unch.astype(np.uint16)), (name, filt.tolist())
+                d32 = np.zeros((1, H, W), np.float32)
+                assert pngio.read_batch(None, [p], None, d32, 1).tolist() == [0]
+                assert np.array_equal(d32[0], unch.astype(np.float32) / 256.)
+
+
 def test_batches_wrong_sizes_and_unsupported_files(tmp_path):
     H, W, n = 40, 64, 7
     imgs = [_rand((H, W, 3), np.uint8, 10 + i) for i in range(n)]
